@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the fingerprint path (BASELINE.json: audio-hours/s fingerprinted, compares/s).
+
+    python bench.py --gpus N --steps K --warmup W                 # the CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's own CPU code on the host cores
+
+A step = one pass of fingerprint extraction over one batch of synthetic PCM: BASELINE config 2, 10,000 x 30 s clips
+(83.3 audio-hours, 6.6 GB of float32) per GPU, resident in HBM when the timed region starts.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 5512.0
+CLIP_LEN = 165360            # 30 s
+SUBFPS = 19
+ALGO_BYTES_PER_CLIP = CLIP_LEN * 4 + SUBFPS * 25        # 4 B per sample in + 25 B per subfingerprint out
+FLOP_PER_WINDOW = 60300.0                               # 2.5 N log2 N + band stage
+WINDOWS_PER_CLIP = SUBFPS * 128
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop, self._t = [], set(), None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml; self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8: "hw_slowdown",
+                 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True); self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_extract_baseline(n_clips, threads, fft_f32=True):
+    """The reference's own code (oracle/_ref) — or the C port when it was never built — on a bounded sample of the workload."""
+    from oracle import oracle as o
+    chk = o.best()
+    cfg = o.Cfg.default()
+    pcm = np.stack([chk.synth_clip(c, CLIP_LEN) for c in range(min(n_clips, 64))])
+    if n_clips > pcm.shape[0]:
+        pcm = np.concatenate([pcm] * ((n_clips + pcm.shape[0] - 1) // pcm.shape[0]))[:n_clips]      # timing only: content repeats
+    _, secs = chk.extract_batch(cfg, pcm, threads=threads, want_bits=False, fft_f32=fft_f32)
+    hours = n_clips * CLIP_LEN / SR / 3600.0
+    return chk, hours / secs, secs
+
+
+def cpu_search_baseline(chk, threads, n_db=20000, n_q=4):
+    rng = np.random.default_rng(1)
+    def codes(n, c):
+        s = rng.integers(0, 2, size=(n, c, 100)); out = np.zeros((n, c, 200), np.uint8); out[..., 0::2] = s == 0; out[..., 1::2] = s == 1
+        return out
+    _, secs = chk.search(codes(n_db, SUBFPS), codes(n_q, 6), 200, threads=threads)
+    return n_db * n_q * 84 / secs
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the same path, same metric, all host threads.
+    Each step fingerprints a bounded sample (args.ref_clips x 30 s) of the config-2 workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    times = []
+    chk = None
+    for i in range(args.warmup + args.steps):
+        chk, _, secs = cpu_extract_baseline(args.ref_clips, threads)
+        if i >= args.warmup:
+            times.append(secs)
+    total = float(np.sum(times)); hours = args.ref_clips * CLIP_LEN / SR / 3600.0
+    value = hours * args.steps / total
+    sample = "%d x 30 s clips (%.2f audio-hours) of the 10,000-clip workload per step; float32 FFT stands in for vDSP" % (args.ref_clips, hours)
+    line = {"impl": "reference", "metric": "audio-hours/s fingerprinted", "value": value, "unit": "audio-hours/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "configs[1] sample: batch fingerprint extraction of synthetic 30 s clips at reference defaults", "clips_per_step": args.ref_clips,
+                                            "clip_seconds": 30, "window": 2048, "stride": 64, "bands": 32, "subfingerprint_length": 200},
+            "cpu_baseline": {"value": value, "unit": "audio-hours/s", "cores": threads, "kind": chk.kind, "sample": sample},
+            "e2e": {"value": value, "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--clips", type=int, default=10000, help="30 s clips per GPU per step (config 2: 10,000)")
+    ap.add_argument("--ref-clips", type=int, default=384, help="clips per step of the CPU reference arm / cpu_baseline sample")
+    ap.add_argument("--db-clips", type=int, default=1000000, help="database clips (whole job) for the search leg (config 4: 1M)")
+    ap.add_argument("--queries", type=int, default=1000)
+    ap.add_argument("--no-search", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--microbench", action="store_true", help="also measure the FP32 / POPC / LOP3 pipe rates (roofline context)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import lbaudiodetective_b200 as lb
+    from lbaudiodetective_b200.dist import shard_range, gather_topk
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lb.load_library(build_if_missing=False)          # the bench must run the in-tree CUDA library, never a fallback
+    if not lb.device_available():
+        raise RuntimeError("no CUDA device: the fingerprint path has no CPU fallback")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n_clips = args.clips
+    det = lb.Detective()
+    stream = torch.cuda.current_stream().cuda_stream
+    pcm = torch.empty((n_clips, CLIP_LEN), dtype=torch.float32, device="cuda")
+    lb.synthesize_device(pcm.data_ptr(), n_clips, CLIP_LEN, CLIP_LEN, first_clip_id=rank * n_clips, stream=stream)      # every rank: its own clips
+    words = torch.zeros((n_clips, SUBFPS, 8), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+
+    def step():
+        det.process_batch_device(pcm.data_ptr(), n_clips, CLIP_LEN, CLIP_LEN, words.data_ptr(), stream)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    det.kernel_timing(enable=True, reset=True)
+    launches0 = det.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    n_timed, kernel_ms_total = det.kernel_timing(enable=False, reset=True)
+    gpu_launches = det.kernel_launches - launches0
+    hours_per_gpu_step = n_clips * CLIP_LEN / SR / 3600.0
+    value = hours_per_gpu_step * world * args.steps / (ms_total * 1e-3)
+    kernel_ms = kernel_ms_total / max(n_timed, 1)
+
+    # ---- sanity on the timed output: structure of the words (never the thing measured) ----
+    w = words[:: max(1, n_clips // 64)].cpu().numpy().view(np.uint32)
+    assert ((w[..., :4] & w[..., 4:]) == 0).all() and (np.unpackbits((w[..., :4] | w[..., 4:]).view(np.uint8), axis=-1).sum(-1) == 100).all()
+
+    # ---- roofline of the dominant kernel (the fused extraction kernel) ----
+    hbm_peak, peak_src = measured_peaks()
+    algo_bytes = n_clips * ALGO_BYTES_PER_CLIP
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    flops = n_clips * WINDOWS_PER_CLIP * FLOP_PER_WINDOW
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "kernel": "extract_fused_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                "note": "FP32-issue bound, not HBM bound (235 flop per new PCM byte, SURVEY.md §8d); fp32 figures alongside",
+                "fp32_tflops_algorithmic": flops / (kernel_ms * 1e-3) / 1e12, "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12}
+    if args.microbench and rank == 0:
+        mb = lb.microbench(); roofline["fp32_peak_tflops_measured"] = mb["fp32_tflops"]; roofline["fp32_frac_of_measured"] = roofline["fp32_tflops_algorithmic"] / mb["fp32_tflops"]
+        roofline["popc_gops_measured"] = mb["popc_gops"]; roofline["lop3_gops_measured"] = mb["lop3_gops"]
+
+    # ---- e2e: the same pass through the host-buffer C-ABI call (H2D of the PCM and D2H of the words inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        host_pcm = torch.empty((n_clips, CLIP_LEN), dtype=torch.float32, pin_memory=True); host_pcm.copy_(pcm); torch.cuda.synchronize()
+        host_words = torch.zeros((n_clips, SUBFPS, 8), dtype=torch.int32, pin_memory=True)
+        def e2e_step():
+            det.process_batch_ptr(host_pcm.data_ptr(), n_clips, CLIP_LEN, CLIP_LEN, host_words.data_ptr())      # LBAudioDetectiveProcessPCMBatch: returns when the words are on the host
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        assert np.array_equal(host_words.numpy()[:: max(1, n_clips // 64)].view(np.uint32), w)
+        e2e = {"value": hours_per_gpu_step * world * args.steps / dt, "unit": "audio-hours/s", "h2d_bytes_per_step": n_clips * CLIP_LEN * 4,
+               "d2h_bytes_per_step": n_clips * SUBFPS * 32, "ms_per_step": 1e3 * dt / args.steps, "api": "LBAudioDetectiveProcessPCMBatch (pinned host buffers)"}
+        del host_pcm, host_words
+    del pcm
+    torch.cuda.empty_cache()
+
+    # ---- search leg (config 4): args.queries 10 s queries vs a args.db_clips-clip database sharded over the ranks, top-10, one gather ----
+    search = None
+    if not args.no_search:
+        lo, hi = shard_range(args.db_clips, rank, world)
+        n_local = hi - lo
+        db = lb.Database(200); db.set_clip_index_base(lo)
+        codes = torch.empty((n_local, SUBFPS, 8), dtype=torch.int32, device="cuda")
+        lb.random_codes_device(codes.data_ptr(), n_local * SUBFPS, 200, seed=1234 + rank, stream=stream); torch.cuda.synchronize()
+        db.add_packed_device(codes.data_ptr(), n_local, SUBFPS)
+        g = torch.Generator(device="cpu"); g.manual_seed(7)
+        # queries: 6-subfingerprint excerpts of database clips of rank 0's shard (so every rank can build the same batch), at a random offset
+        q_src = torch.randint(0, max(1, args.db_clips // world), (args.queries,), generator=g)
+        q_off = torch.randint(0, SUBFPS - 6 + 1, (args.queries,), generator=g)
+        if rank == 0:
+            qw = torch.stack([codes[int(c), int(o):int(o) + 6] for c, o in zip(q_src, q_off)]).contiguous()
+        else:
+            qw = torch.empty((args.queries, 6, 8), dtype=torch.int32, device="cuda")
+        if world > 1:
+            dist.broadcast(qw, src=0)
+        del codes
+        d_sc = torch.empty((args.queries, 10), dtype=torch.float32, device="cuda"); d_idx = torch.empty((args.queries, 10), dtype=torch.int32, device="cuda")
+        def search_step():
+            db.search_device(qw.data_ptr(), args.queries, 6, 10, d_sc.data_ptr(), d_idx.data_ptr(), stream=stream)
+            torch.cuda.synchronize()
+            gs, gi = gather_topk(d_sc.cpu().numpy(), d_idx.cpu().numpy().view(np.uint32))
+            return lb.merge_topk(gs, gi) if world > 1 else (gs[0], gi[0])
+        for _ in range(2):
+            sc, idx = search_step()
+        db.kernel_timing(enable=True, reset=True)
+        barrier(); t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sc, idx = search_step()
+        barrier(); dt = max_over_ranks(time.perf_counter() - t0)
+        n_k, k_ms = db.kernel_timing(enable=False, reset=True)
+        assert np.array_equal(idx[:, 0], q_src.numpy().astype(np.uint32)) and (sc[:, 0] == 1.0).all()       # every query finds the clip it was cut from
+        compares = args.queries * args.db_clips * 84
+        search = {"metric": "Hamming compares/s", "value": compares * args.steps / dt, "unit": "compares/s", "ms_per_step": 1e3 * dt / args.steps,
+                  "kernel_ms": k_ms / max(n_k, 1), "kernel_compares_per_s_per_gpu": (args.queries * n_local * 84) / (k_ms / max(n_k, 1) * 1e-3),
+                  "queries": args.queries, "db_clips": args.db_clips, "k": 10, "scaling": "strong", "workload": "configs[3]: 1,000 x 6-subfp queries vs 1M x 19-subfp clips, 14 offsets",
+                  "gpu_launches": db.kernel_launches}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        chk, v, secs = cpu_extract_baseline(args.ref_clips, threads)
+        cpu = {"value": v, "unit": "audio-hours/s", "cores": threads, "kind": chk.kind,
+               "sample": "%d x 30 s clips of the same synthetic workload (%.1f s of wall time); float32 FFT stands in for vDSP" % (args.ref_clips, secs),
+               "search_compares_per_s": cpu_search_baseline(chk, threads)}
+    line = {"metric": "audio-hours/s fingerprinted", "value": value, "unit": "audio-hours/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: batch fingerprint extraction of %d synthetic 30 s clips per GPU (fused FFT+bands+Haar+top-t kernel)" % n_clips,
+                       "clips_per_gpu": n_clips, "clip_seconds": 30, "window": 2048, "stride": 64, "bands": 32, "subfingerprint_length": 200,
+                       "l2_policy": "inputs (%.1f GB per GPU) larger than L2" % (n_clips * CLIP_LEN * 4 / 1e9)},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "search": search}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,59 @@
+/*
+ * LBAudioDetectiveDatabase.h — batched form of the reference's matcher (an addition; the reference has no such type).
+ *
+ * The reference compares one pair at a time with LBAudioDetectiveFingerprintCompareToFingerprint (FP.h:134,
+ * FP.m:119-149); its only "database" is the linear scan + argmax of the essay's server.  This type
+ * keeps many fingerprints packed on one GPU and evaluates
+ *        score[q][c] = LBAudioDetectiveFingerprintCompareToFingerprint(clip_c, query_q, range)
+ * (archive first, query second — the argument order of LBAudioDetectiveTests.m:68) for whole query batches in one
+ * __popc kernel, bit-exact with the pairwise function, and returns per-query top-k ordered (score desc, clip asc).
+ * Multi-GPU: one database shard per process/GPU; LBAudioDetectiveDatabaseMergeTopK merges gathered shard results.
+ */
+#ifndef LBAUDIODETECTIVE_DATABASE_H
+#define LBAUDIODETECTIVE_DATABASE_H
+#include "LBAudioDetectiveTypes.h"
+#include "LBAudioDetectiveFingerprint.h"
+LBAD_EXTERN_C_BEGIN
+
+typedef struct LBAudioDetectiveDatabase *LBAudioDetectiveDatabaseRef;
+
+/* All fingerprints in a database share one subfingerprint length L.  Bound to the current CUDA device. */
+LBAD_API LBAudioDetectiveDatabaseRef LBAudioDetectiveDatabaseNew(UInt32 inSubfingerprintLength);
+LBAD_API OSStatus LBAudioDetectiveDatabaseDispose(LBAudioDetectiveDatabaseRef inDatabase);
+LBAD_API UInt32 LBAudioDetectiveDatabaseGetNumberOfClips(LBAudioDetectiveDatabaseRef inDatabase);
+LBAD_API UInt64 LBAudioDetectiveDatabaseGetNumberOfSubfingerprints(LBAudioDetectiveDatabaseRef inDatabase);
+/* Global clip id of local clip 0 (for sharded databases; default 0). */
+LBAD_API OSStatus LBAudioDetectiveDatabaseSetClipIndexBase(LBAudioDetectiveDatabaseRef inDatabase, UInt32 inBase);
+/* Appends one fingerprint; *outClipIndex (optional) receives its local clip index. */
+LBAD_API OSStatus LBAudioDetectiveDatabaseAddFingerprint(LBAudioDetectiveDatabaseRef inDatabase, LBAudioDetectiveFingerprintRef inFingerprint, UInt32* outClipIndex);
+/* Appends inNumberOfClips clips given packed (host memory): inWords is the concatenation of all their
+ * subfingerprints (2*W words each); inCounts[c] subfingerprints per clip, or NULL with inUniformCount each. */
+LBAD_API OSStatus LBAudioDetectiveDatabaseAddPacked(LBAudioDetectiveDatabaseRef inDatabase, const UInt32* inWords, UInt32 inNumberOfClips, const UInt32* inCounts, UInt32 inUniformCount);
+/* Same with inDeviceWords already on the device (uniform counts only): device-to-device append. */
+LBAD_API OSStatus LBAudioDetectiveDatabaseAddPackedDevice(LBAudioDetectiveDatabaseRef inDatabase, const UInt32* inDeviceWords, UInt32 inNumberOfClips, UInt32 inUniformCount);
+
+/* Top-k search.  Queries: inNumberOfQueries packed fingerprints with inQueryCount subfingerprints each (host
+ * memory, [query][subfp][2*W]).  inRange 0 means L.  outScores/outClipIndices: [query][k], ordered by score
+ * descending then clip index ascending; unused slots (fewer than k clips) hold score -1 and index 0xFFFFFFFF.
+ * outAllScores (optional, host) receives the full [query][clip] score matrix — for parity tests on small inputs. */
+LBAD_API OSStatus LBAudioDetectiveDatabaseSearchPacked(LBAudioDetectiveDatabaseRef inDatabase, const UInt32* inQueryWords, UInt32 inNumberOfQueries, UInt32 inQueryCount,
+                                                      UInt32 inRange, UInt32 inK, Float32* outScores, UInt32* outClipIndices, Float32* outAllScores);
+/* Convenience over fingerprint objects (all with the same number of subfingerprints). */
+LBAD_API OSStatus LBAudioDetectiveDatabaseSearch(LBAudioDetectiveDatabaseRef inDatabase, const LBAudioDetectiveFingerprintRef* inQueries, UInt32 inNumberOfQueries,
+                                                UInt32 inRange, UInt32 inK, Float32* outScores, UInt32* outClipIndices);
+/* Device-resident form used for timing: query words and outputs are device pointers, enqueued on inStream
+ * (cudaStream_t; NULL = the database's stream), no synchronisation. */
+LBAD_API OSStatus LBAudioDetectiveDatabaseSearchDevice(LBAudioDetectiveDatabaseRef inDatabase, const UInt32* inDeviceQueryWords, UInt32 inNumberOfQueries, UInt32 inQueryCount,
+                                                      UInt32 inRange, UInt32 inK, Float32* outDeviceScores, UInt32* outDeviceClipIndices, void* inStream);
+/* Merges inNumberOfLists top-k lists per query ([list][query][k], e.g. one per GPU after a gather) into one,
+ * ordered (score desc, clip index asc) — the result equals a single-GPU search over the union.  Host memory. */
+LBAD_API OSStatus LBAudioDetectiveDatabaseMergeTopK(const Float32* inScores, const UInt32* inClipIndices, UInt32 inNumberOfLists, UInt32 inNumberOfQueries, UInt32 inK,
+                                                   Float32* outScores, UInt32* outClipIndices);
+/* Number of CompareSubfingerprints evaluations one search performs (for compares/s). */
+LBAD_API UInt64 LBAudioDetectiveDatabaseComparesPerQuery(LBAudioDetectiveDatabaseRef inDatabase, UInt32 inQueryCount);
+LBAD_API UInt64 LBAudioDetectiveDatabaseGetKernelLaunchCount(LBAudioDetectiveDatabaseRef inDatabase);
+/* Device time of the search kernel alone (see LBAudioDetectiveGetKernelTiming). */
+LBAD_API UInt32 LBAudioDetectiveDatabaseGetKernelTiming(LBAudioDetectiveDatabaseRef inDatabase, Boolean inEnable, Boolean inReset, Float64* outTotalMilliseconds);
+
+LBAD_EXTERN_C_END
+#endif

@@ -1,0 +1,447 @@
+"""ctypes mirror of include/LBAudioDetective*.h — same names, argument meaning and error behaviour as the C API.
+
+Nothing here computes: every method marshals numpy buffers (or raw device pointers) into libLBAudioDetectiveCUDA.so.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libLBAudioDetectiveCUDA.so")
+ROWS_PER_FRAME = 128
+ARGUMENT_INVALID = 1
+DEVICE_UNAVAILABLE = -7001
+DEVICE_ERROR = -7002
+
+_lib = None
+
+
+class LBADError(RuntimeError):
+    def __init__(self, status, what):
+        self.status = status
+        RuntimeError.__init__(self, "%s failed with OSStatus %d%s" % (what, status, _last_error()))
+
+
+def _last_error():
+    try:
+        s = _lib.LBAudioDetectiveSupportLastError()
+        return (": " + s.decode()) if s else ""
+    except Exception:
+        return ""
+
+
+def load_library(build_if_missing: bool = True):
+    """Loads the C-ABI library; fails loudly if it is missing (there is no fallback implementation)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise FileNotFoundError(LIB_PATH + " is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        from . import build as _b
+        _b.build()
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, f32, f64, u8 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float, C.c_double, C.c_ubyte
+    P = C.POINTER
+    sig = {
+        "LBAudioDetectiveNew": (vp, []),
+        "LBAudioDetectiveDispose": (C.c_int32, [vp]),
+        "LBAudioDetectiveGetProcessingSampleRate": (f64, [vp]),
+        "LBAudioDetectiveGetNumberOfPitchSteps": (u32, [vp]),
+        "LBAudioDetectiveGetSubfingerprintLength": (u32, [vp]),
+        "LBAudioDetectiveGetWindowSize": (u32, [vp]),
+        "LBAudioDetectiveGetAnalysisStride": (u32, [vp]),
+        "LBAudioDetectiveSetRecordingSampleRate": (C.c_int32, [vp, f64]),
+        "LBAudioDetectiveSetProcessingSampleRate": (C.c_int32, [vp, f64]),
+        "LBAudioDetectiveSetNumberOfPitchSteps": (C.c_int32, [vp, u32]),
+        "LBAudioDetectiveSetSubfingerprintLength": (C.c_int32, [vp, u32]),
+        "LBAudioDetectiveSetWindowSize": (C.c_int32, [vp, u32]),
+        "LBAudioDetectiveSetAnalysisStride": (C.c_int32, [vp, u32]),
+        "LBAudioDetectiveProcessPCM": (C.c_int32, [vp, vp, u64, P(vp)]),
+        "LBAudioDetectiveComparePCM": (C.c_int32, [vp, vp, u64, vp, u64, u32, P(f32)]),
+        "LBAudioDetectiveCheckConfiguration": (C.c_int32, [vp]),
+        "LBAudioDetectiveGetNumberOfSubfingerprintsForLength": (u64, [vp, u64]),
+        "LBAudioDetectiveGetBandTable": (C.c_int32, [vp, vp, vp, vp]),
+        "LBAudioDetectiveProcessPCMBatch": (C.c_int32, [vp, vp, u32, u64, u64, vp]),
+        "LBAudioDetectiveProcessPCMBatchDevice": (C.c_int32, [vp, vp, u32, u64, u64, vp, vp]),
+        "LBAudioDetectiveProcessPCMStages": (C.c_int32, [vp, vp, u64, vp, vp, vp, u8]),
+        "LBAudioDetectiveTransformImages": (C.c_int32, [vp, vp, u32, vp, vp]),
+        "LBAudioDetectiveGetKernelLaunchCount": (u64, [vp]),
+        "LBAudioDetectiveGetKernelTiming": (u32, [vp, u8, u8, P(f64)]),
+        "LBAudioDetectiveFingerprintNew": (vp, [u32]),
+        "LBAudioDetectiveFingerprintDispose": (None, [vp]),
+        "LBAudioDetectiveFingerprintCopy": (vp, [vp]),
+        "LBAudioDetectiveFingerprintGetSubfingerprintLength": (u32, [vp]),
+        "LBAudioDetectiveFingerprintGetNumberOfSubfingerprints": (u32, [vp]),
+        "LBAudioDetectiveFingerprintGetSubfingerprintAtIndex": (u32, [vp, u32, vp]),
+        "LBAudioDetectiveFingerprintSetSubfingerprintLength": (u8, [vp, P(u32)]),
+        "LBAudioDetectiveFingerprintAddSubfingerprint": (None, [vp, vp]),
+        "LBAudioDetectiveFingerprintEqualToFingerprint": (u8, [vp, vp]),
+        "LBAudioDetectiveFingerprintCompareToFingerprint": (f32, [vp, vp, u32]),
+        "LBAudioDetectiveFingerprintCompareSubfingerprints": (f32, [vp, vp, vp, u32]),
+        "LBAudioDetectiveFingerprintPackedWordsPerPlane": (u32, [u32]),
+        "LBAudioDetectiveFingerprintGetPackedSubfingerprintAtIndex": (u32, [vp, u32, vp]),
+        "LBAudioDetectiveFingerprintAddPackedSubfingerprints": (C.c_int32, [vp, vp, u32]),
+        "LBAudioDetectiveFingerprintToString": (C.c_size_t, [vp, C.c_char_p, C.c_size_t]),
+        "LBAudioDetectiveFingerprintFromString": (vp, [C.c_char_p]),
+        "LBAudioDetectiveDatabaseNew": (vp, [u32]),
+        "LBAudioDetectiveDatabaseDispose": (C.c_int32, [vp]),
+        "LBAudioDetectiveDatabaseGetNumberOfClips": (u32, [vp]),
+        "LBAudioDetectiveDatabaseGetNumberOfSubfingerprints": (u64, [vp]),
+        "LBAudioDetectiveDatabaseSetClipIndexBase": (C.c_int32, [vp, u32]),
+        "LBAudioDetectiveDatabaseAddFingerprint": (C.c_int32, [vp, vp, P(u32)]),
+        "LBAudioDetectiveDatabaseAddPacked": (C.c_int32, [vp, vp, u32, vp, u32]),
+        "LBAudioDetectiveDatabaseAddPackedDevice": (C.c_int32, [vp, vp, u32, u32]),
+        "LBAudioDetectiveDatabaseSearchPacked": (C.c_int32, [vp, vp, u32, u32, u32, u32, vp, vp, vp]),
+        "LBAudioDetectiveDatabaseSearch": (C.c_int32, [vp, P(vp), u32, u32, u32, vp, vp]),
+        "LBAudioDetectiveDatabaseSearchDevice": (C.c_int32, [vp, vp, u32, u32, u32, u32, vp, vp, vp]),
+        "LBAudioDetectiveDatabaseMergeTopK": (C.c_int32, [vp, vp, u32, u32, u32, vp, vp]),
+        "LBAudioDetectiveDatabaseComparesPerQuery": (u64, [vp, u32]),
+        "LBAudioDetectiveDatabaseGetKernelLaunchCount": (u64, [vp]),
+        "LBAudioDetectiveDatabaseGetKernelTiming": (u32, [vp, u8, u8, P(f64)]),
+        "LBAudioDetectiveSupportSynthesizeDevice": (C.c_int32, [vp, u32, u64, u64, u64, u64, f64, vp]),
+        "LBAudioDetectiveSupportRandomCodesDevice": (C.c_int32, [vp, u64, u32, u64, vp]),
+        "LBAudioDetectiveSupportMicrobench": (C.c_int32, [P(f64), P(f64), P(f64)]),
+        "LBAudioDetectiveSupportLastError": (C.c_char_p, []),
+        "LBAudioDetectiveSupportDeviceAvailable": (u8, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)          # AttributeError here = the library does not export what include/*.h declares
+        fn.restype = res
+        fn.argtypes = args
+    L._lbad_signatures = sig
+    _lib = L
+    return L
+
+
+def lib():
+    return load_library()
+
+
+def device_available() -> bool:
+    return bool(lib().LBAudioDetectiveSupportDeviceAvailable())
+
+
+def _check(status, what):
+    if status != 0:
+        raise LBADError(status, what)
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def words_per_plane(length: int) -> int:
+    return int(lib().LBAudioDetectiveFingerprintPackedWordsPerPlane(length))
+
+
+def pack_booleans(bits: np.ndarray) -> np.ndarray:
+    """[..., L] Booleans -> [..., 2*W] packed words (P plane then M plane). Pure data-format conversion."""
+    bits = np.ascontiguousarray(bits, dtype=np.uint8)
+    L = bits.shape[-1]; W = words_per_plane(L)
+    flat = bits.reshape(-1, L)
+    out = np.zeros((flat.shape[0], 2 * W), np.uint32)
+    for plane in (0, 1):
+        b = flat[:, plane::2].astype(np.uint64)
+        for w in range(W):
+            chunk = b[:, 32 * w:32 * (w + 1)]
+            if chunk.shape[1]:
+                out[:, plane * W + w] = (chunk << np.arange(chunk.shape[1], dtype=np.uint64)).sum(axis=1).astype(np.uint32)
+    return out.reshape(bits.shape[:-1] + (2 * W,))
+
+
+def unpack_words(words: np.ndarray, length: int) -> np.ndarray:
+    """Inverse of pack_booleans."""
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    W = words.shape[-1] // 2
+    flat = words.reshape(-1, 2 * W)
+    out = np.zeros((flat.shape[0], length), np.uint8)
+    for i in range(length):
+        pair = i >> 1
+        out[:, i] = (flat[:, (W if i & 1 else 0) + (pair >> 5)] >> np.uint32(pair & 31)) & 1
+    return out.reshape(words.shape[:-1] + (length,))
+
+
+class Fingerprint:
+    """LBAudioDetectiveFingerprintRef (include/LBAudioDetectiveFingerprint.h)."""
+
+    def __init__(self, subfingerprint_length=0, _ref=None):
+        self._L = lib()
+        self.ref = _ref if _ref is not None else self._L.LBAudioDetectiveFingerprintNew(subfingerprint_length)
+
+    def dispose(self):
+        if self.ref:
+            self._L.LBAudioDetectiveFingerprintDispose(self.ref); self.ref = None
+
+    def __del__(self):
+        try:
+            self.dispose()
+        except Exception:
+            pass
+
+    def copy(self):
+        return Fingerprint(_ref=self._L.LBAudioDetectiveFingerprintCopy(self.ref))
+
+    @property
+    def subfingerprint_length(self):
+        return int(self._L.LBAudioDetectiveFingerprintGetSubfingerprintLength(self.ref))
+
+    @property
+    def count(self):
+        return int(self._L.LBAudioDetectiveFingerprintGetNumberOfSubfingerprints(self.ref))
+
+    def set_subfingerprint_length(self, n):
+        io = C.c_uint32(n)
+        ok = bool(self._L.LBAudioDetectiveFingerprintSetSubfingerprintLength(self.ref, C.byref(io)))
+        return ok, int(io.value)
+
+    def subfingerprint(self, i):
+        out = np.zeros(self.subfingerprint_length, np.uint8)
+        self._L.LBAudioDetectiveFingerprintGetSubfingerprintAtIndex(self.ref, i, _ptr(out))
+        return out
+
+    def booleans(self):
+        n, L = self.count, self.subfingerprint_length
+        return np.stack([self.subfingerprint(i) for i in range(n)]) if n else np.zeros((0, L), np.uint8)
+
+    def packed(self):
+        n, W = self.count, words_per_plane(self.subfingerprint_length)
+        out = np.zeros((n, 2 * W), np.uint32)
+        for i in range(n):
+            self._L.LBAudioDetectiveFingerprintGetPackedSubfingerprintAtIndex(self.ref, i, _ptr(out[i]))
+        return out
+
+    def add_subfingerprint(self, bits):
+        b = np.ascontiguousarray(bits, dtype=np.uint8)
+        assert b.size >= self.subfingerprint_length
+        self._L.LBAudioDetectiveFingerprintAddSubfingerprint(self.ref, _ptr(b))
+
+    def add_packed(self, words):
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        _check(self._L.LBAudioDetectiveFingerprintAddPackedSubfingerprints(self.ref, _ptr(w), w.reshape(-1, w.shape[-1]).shape[0]), "AddPackedSubfingerprints")
+
+    @staticmethod
+    def from_booleans(bits):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        fp = Fingerprint(bits.shape[1] if bits.ndim == 2 else 0)
+        for row in bits:
+            fp.add_subfingerprint(row)
+        return fp
+
+    def equal(self, other):
+        return bool(self._L.LBAudioDetectiveFingerprintEqualToFingerprint(self.ref, other.ref))
+
+    def compare(self, other, rng):
+        """LBAudioDetectiveFingerprintCompareToFingerprint(self, other, rng) — runs on the GPU."""
+        return float(self._L.LBAudioDetectiveFingerprintCompareToFingerprint(self.ref, other.ref, rng))
+
+    def compare_subfingerprints(self, s1, s2, rng):
+        a = np.ascontiguousarray(np.concatenate([s1, [0, 0]]), dtype=np.uint8); b = np.ascontiguousarray(np.concatenate([s2, [0, 0]]), dtype=np.uint8)
+        return float(self._L.LBAudioDetectiveFingerprintCompareSubfingerprints(self.ref, _ptr(a), _ptr(b), rng))
+
+    def to_string(self):
+        need = self._L.LBAudioDetectiveFingerprintToString(self.ref, None, 0)
+        buf = C.create_string_buffer(need)
+        self._L.LBAudioDetectiveFingerprintToString(self.ref, buf, need)
+        return buf.value.decode()
+
+    @staticmethod
+    def from_string(s):
+        ref = lib().LBAudioDetectiveFingerprintFromString(s.encode())
+        return Fingerprint(_ref=ref) if ref else None
+
+
+class Detective:
+    """LBAudioDetectiveRef (include/LBAudioDetective.h)."""
+
+    def __init__(self):
+        self._L = lib()
+        self.ref = self._L.LBAudioDetectiveNew()
+
+    def dispose(self):
+        if self.ref:
+            st = self._L.LBAudioDetectiveDispose(self.ref); self.ref = None
+            return st
+        return ARGUMENT_INVALID
+
+    def __del__(self):
+        try:
+            self.dispose()
+        except Exception:
+            pass
+
+    # getters / setters, same names as the C API minus the prefix
+    sample_rate = property(lambda s: float(s._L.LBAudioDetectiveGetProcessingSampleRate(s.ref)))
+    pitch_steps = property(lambda s: int(s._L.LBAudioDetectiveGetNumberOfPitchSteps(s.ref)))
+    subfingerprint_length = property(lambda s: int(s._L.LBAudioDetectiveGetSubfingerprintLength(s.ref)))
+    window_size = property(lambda s: int(s._L.LBAudioDetectiveGetWindowSize(s.ref)))
+    analysis_stride = property(lambda s: int(s._L.LBAudioDetectiveGetAnalysisStride(s.ref)))
+
+    def set_sample_rate(self, v): return int(self._L.LBAudioDetectiveSetProcessingSampleRate(self.ref, v))
+    def set_pitch_steps(self, v): return int(self._L.LBAudioDetectiveSetNumberOfPitchSteps(self.ref, v))
+    def set_subfingerprint_length(self, v): return int(self._L.LBAudioDetectiveSetSubfingerprintLength(self.ref, v))
+    def set_window_size(self, v): return int(self._L.LBAudioDetectiveSetWindowSize(self.ref, v))
+    def set_analysis_stride(self, v): return int(self._L.LBAudioDetectiveSetAnalysisStride(self.ref, v))
+    def check_configuration(self): return int(self._L.LBAudioDetectiveCheckConfiguration(self.ref))
+
+    def subfingerprints_for_length(self, n):
+        return int(self._L.LBAudioDetectiveGetNumberOfSubfingerprintsForLength(self.ref, n))
+
+    def band_table(self):
+        B = self.pitch_steps
+        idx = np.zeros(B + 1, np.uint32); lo = np.zeros(B, np.uint32); hi = np.zeros(B, np.uint32)
+        _check(self._L.LBAudioDetectiveGetBandTable(self.ref, _ptr(idx), _ptr(lo), _ptr(hi)), "GetBandTable")
+        return idx, lo, hi
+
+    def process_pcm(self, pcm, check=True):
+        """LBAudioDetectiveProcessPCM -> Fingerprint (raises LBADError unless check=False, then returns (status, fp))."""
+        pcm = _f32(pcm); out = C.c_void_p()
+        st = self._L.LBAudioDetectiveProcessPCM(self.ref, _ptr(pcm), pcm.size, C.byref(out))
+        fp = Fingerprint(_ref=out.value) if out.value else None
+        if not check:
+            return int(st), fp
+        _check(st, "LBAudioDetectiveProcessPCM")
+        return fp
+
+    def compare_pcm(self, pcm1, pcm2, rng=0):
+        a = _f32(pcm1); b = _f32(pcm2); out = C.c_float(-1.0)
+        _check(self._L.LBAudioDetectiveComparePCM(self.ref, _ptr(a), a.size, _ptr(b), b.size, rng, C.byref(out)), "LBAudioDetectiveComparePCM")
+        return float(out.value)
+
+    def process_batch(self, pcm2d, out_words=None):
+        """Host [clips][samples] float32 -> [clips][subfps][2W] packed words."""
+        pcm2d = _f32(pcm2d); n_clips, clip_len = pcm2d.shape
+        n = self.subfingerprints_for_length(clip_len); W = words_per_plane(self.subfingerprint_length)
+        if out_words is None:
+            out_words = np.zeros((n_clips, n, 2 * W), np.uint32)
+        _check(self._L.LBAudioDetectiveProcessPCMBatch(self.ref, _ptr(pcm2d), n_clips, clip_len, clip_len, _ptr(out_words)), "LBAudioDetectiveProcessPCMBatch")
+        return out_words
+
+    def process_batch_ptr(self, host_ptr, n_clips, clip_len, clip_stride, out_ptr):
+        _check(self._L.LBAudioDetectiveProcessPCMBatch(self.ref, host_ptr, n_clips, clip_len, clip_stride, out_ptr), "LBAudioDetectiveProcessPCMBatch")
+
+    def process_batch_device(self, d_pcm_ptr, n_clips, clip_len, clip_stride, d_words_ptr, stream=None):
+        _check(self._L.LBAudioDetectiveProcessPCMBatchDevice(self.ref, d_pcm_ptr, n_clips, clip_len, clip_stride, d_words_ptr, stream), "LBAudioDetectiveProcessPCMBatchDevice")
+
+    def process_stages(self, pcm, fused):
+        """(images, haar, booleans) of one clip; fused selects the fused kernel or the generic two-kernel path."""
+        pcm = _f32(pcm); n = self.subfingerprints_for_length(pcm.size); B = self.pitch_steps; L = self.subfingerprint_length
+        img = np.zeros((n, ROWS_PER_FRAME, B), np.float32); haar = np.zeros_like(img); bits = np.zeros((n, L), np.uint8)
+        _check(self._L.LBAudioDetectiveProcessPCMStages(self.ref, _ptr(pcm), pcm.size, _ptr(img), _ptr(haar), _ptr(bits), 1 if fused else 0), "LBAudioDetectiveProcessPCMStages")
+        return img, haar, bits
+
+    def transform_images(self, images):
+        images = _f32(images); n = images.shape[0]
+        haar = np.zeros_like(images); bits = np.zeros((n, self.subfingerprint_length), np.uint8)
+        _check(self._L.LBAudioDetectiveTransformImages(self.ref, _ptr(images), n, _ptr(haar), _ptr(bits)), "LBAudioDetectiveTransformImages")
+        return haar, bits
+
+    @property
+    def kernel_launches(self):
+        return int(self._L.LBAudioDetectiveGetKernelLaunchCount(self.ref))
+
+    def kernel_timing(self, enable=True, reset=True):
+        ms = C.c_double(0.0)
+        n = self._L.LBAudioDetectiveGetKernelTiming(self.ref, 1 if enable else 0, 1 if reset else 0, C.byref(ms))
+        return int(n), float(ms.value)
+
+
+class Database:
+    """LBAudioDetectiveDatabaseRef (include/LBAudioDetectiveDatabase.h)."""
+
+    def __init__(self, subfingerprint_length=200):
+        self._L = lib()
+        self.L = subfingerprint_length
+        self.ref = self._L.LBAudioDetectiveDatabaseNew(subfingerprint_length)
+        if not self.ref:
+            raise LBADError(DEVICE_UNAVAILABLE, "LBAudioDetectiveDatabaseNew")
+
+    def dispose(self):
+        if self.ref:
+            self._L.LBAudioDetectiveDatabaseDispose(self.ref); self.ref = None
+
+    def __del__(self):
+        try:
+            self.dispose()
+        except Exception:
+            pass
+
+    clips = property(lambda s: int(s._L.LBAudioDetectiveDatabaseGetNumberOfClips(s.ref)))
+    subfingerprints = property(lambda s: int(s._L.LBAudioDetectiveDatabaseGetNumberOfSubfingerprints(s.ref)))
+
+    def set_clip_index_base(self, base):
+        _check(self._L.LBAudioDetectiveDatabaseSetClipIndexBase(self.ref, base), "SetClipIndexBase")
+
+    def add_fingerprint(self, fp):
+        idx = C.c_uint32(0)
+        _check(self._L.LBAudioDetectiveDatabaseAddFingerprint(self.ref, fp.ref, C.byref(idx)), "DatabaseAddFingerprint")
+        return int(idx.value)
+
+    def add_packed(self, words, counts=None):
+        """words: [clips][count][2W] (uniform) or flat [total][2W] with counts[clips]."""
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        if counts is None:
+            n_clips, uniform = w.shape[0], w.shape[1]
+            _check(self._L.LBAudioDetectiveDatabaseAddPacked(self.ref, _ptr(w), n_clips, None, uniform), "DatabaseAddPacked")
+        else:
+            c = np.ascontiguousarray(counts, dtype=np.uint32)
+            _check(self._L.LBAudioDetectiveDatabaseAddPacked(self.ref, _ptr(w), c.size, _ptr(c), 0), "DatabaseAddPacked")
+
+    def add_packed_device(self, d_words_ptr, n_clips, uniform_count):
+        _check(self._L.LBAudioDetectiveDatabaseAddPackedDevice(self.ref, d_words_ptr, n_clips, uniform_count), "DatabaseAddPackedDevice")
+
+    def search_packed(self, qwords, k, rng=0, all_scores=False):
+        """qwords [queries][count][2W] -> (scores [q][k], clip indices [q][k][, full score matrix])."""
+        q = np.ascontiguousarray(qwords, dtype=np.uint32); n_q, cq = q.shape[0], q.shape[1]
+        sc = np.zeros((n_q, k), np.float32); idx = np.zeros((n_q, k), np.uint32)
+        full = np.zeros((n_q, self.clips), np.float32) if all_scores else None
+        _check(self._L.LBAudioDetectiveDatabaseSearchPacked(self.ref, _ptr(q), n_q, cq, rng, k, _ptr(sc), _ptr(idx), _ptr(full)), "DatabaseSearchPacked")
+        return (sc, idx, full) if all_scores else (sc, idx)
+
+    def search(self, fingerprints, k, rng=0):
+        n = len(fingerprints); arr = (C.c_void_p * n)(*[f.ref for f in fingerprints])
+        sc = np.zeros((n, k), np.float32); idx = np.zeros((n, k), np.uint32)
+        _check(self._L.LBAudioDetectiveDatabaseSearch(self.ref, arr, n, rng, k, _ptr(sc), _ptr(idx)), "DatabaseSearch")
+        return sc, idx
+
+    def search_device(self, d_q_ptr, n_q, q_count, k, d_scores_ptr, d_idx_ptr, rng=0, stream=None):
+        _check(self._L.LBAudioDetectiveDatabaseSearchDevice(self.ref, d_q_ptr, n_q, q_count, rng, k, d_scores_ptr, d_idx_ptr, stream), "DatabaseSearchDevice")
+
+    def compares_per_query(self, q_count):
+        return int(self._L.LBAudioDetectiveDatabaseComparesPerQuery(self.ref, q_count))
+
+    @property
+    def kernel_launches(self):
+        return int(self._L.LBAudioDetectiveDatabaseGetKernelLaunchCount(self.ref))
+
+    def kernel_timing(self, enable=True, reset=True):
+        ms = C.c_double(0.0)
+        n = self._L.LBAudioDetectiveDatabaseGetKernelTiming(self.ref, 1 if enable else 0, 1 if reset else 0, C.byref(ms))
+        return int(n), float(ms.value)
+
+
+def merge_topk(scores, indices):
+    """[lists][queries][k] -> merged [queries][k], ordered (score desc, index asc); runs the device merge kernel."""
+    s = np.ascontiguousarray(scores, dtype=np.float32); i = np.ascontiguousarray(indices, dtype=np.uint32)
+    n_lists, n_q, k = s.shape
+    os_ = np.zeros((n_q, k), np.float32); oi = np.zeros((n_q, k), np.uint32)
+    _check(lib().LBAudioDetectiveDatabaseMergeTopK(_ptr(s), _ptr(i), n_lists, n_q, k, _ptr(os_), _ptr(oi)), "DatabaseMergeTopK")
+    return os_, oi
+
+
+def synthesize_device(d_out_ptr, n_clips, clip_len, clip_stride, first_clip_id=0, base_seed=0x1BAD5EED, sample_rate=5512.0, stream=None):
+    _check(lib().LBAudioDetectiveSupportSynthesizeDevice(d_out_ptr, n_clips, clip_len, clip_stride, first_clip_id, base_seed, sample_rate, stream), "SupportSynthesizeDevice")
+
+
+def random_codes_device(d_words_ptr, n_subfps, subfingerprint_length=200, seed=1, stream=None):
+    _check(lib().LBAudioDetectiveSupportRandomCodesDevice(d_words_ptr, n_subfps, subfingerprint_length, seed, stream), "SupportRandomCodesDevice")
+
+
+def microbench():
+    a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+    _check(lib().LBAudioDetectiveSupportMicrobench(C.byref(a), C.byref(b), C.byref(c)), "SupportMicrobench")
+    return {"fp32_tflops": a.value, "popc_gops": b.value, "lop3_gops": c.value}

@@ -1,0 +1,283 @@
+/*
+ * LBAudioDetective.c — host side of the detective: configuration object, band-table construction and the
+ * PCM entry points.  All signal processing is delegated to the CUDA layer (lbad_extract.cu); nothing here
+ * touches a sample.  Reference: /root/reference/LBAudioDetective/LBAudioDetective.m (m:) and .h (h:).
+ */
+#include "lbad_host.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+/* m:20-26 (+ the one constant upstream declares but never defines, h:19) */
+const OSStatus kLBAudioDetectiveArgumentInvalid = 1;
+const UInt32 kLBAudioDetectiveDefaultWindowSize = 2048;
+const UInt32 kLBAudioDetectiveDefaultAnalysisStride = 64;
+const UInt32 kLBAudioDetectiveDefaultNumberOfPitchSteps = 32;
+const UInt32 kLBAudioDetectiveDefaultNumberOfRowsPerFrame = 128;
+const UInt32 kLBAudioDetectiveDefaultFingerprintComparisonRange = 0;
+const UInt32 kLBAudioDetectiveDefaultSubfingerprintLength = 200;
+const OSStatus kLBAudioDetectiveDeviceUnavailable = LBAD_ERR_NODEVICE;
+const OSStatus kLBAudioDetectiveDeviceError = LBAD_ERR_CUDA;
+
+/* replaces struct LBAudioDetective (m:28-44): the vDSP scratch (m:37-43) becomes a device-side plan */
+struct LBAudioDetective {
+    AudioStreamBasicDescription processingFormat;
+    UInt32 subfingerprintLength;
+    UInt32 windowSize;
+    UInt32 analysisStride;
+    UInt32 pitchStepCount;
+    lbadcu_plan* plan;          /* built lazily; any setter invalidates it */
+    UInt64 launchesBefore;      /* launches of plans that were since destroyed */
+};
+
+static void invalidate_plan(LBAudioDetectiveRef d) {
+    if (d->plan) { d->launchesBefore += lbadcu_plan_launches(d->plan); lbadcu_plan_destroy(d->plan); d->plan = NULL; }
+}
+
+/* m:77-90 */
+LBAudioDetectiveRef LBAudioDetectiveNew(void) {
+    LBAudioDetectiveRef d = calloc(1, sizeof *d);
+    if (!d) return NULL;
+    d->processingFormat = LBAudioDetectiveDefaultProcessingFormat();
+    d->subfingerprintLength = kLBAudioDetectiveDefaultSubfingerprintLength;
+    LBAudioDetectiveSetWindowSize(d, kLBAudioDetectiveDefaultWindowSize);     /* return value ignored, as upstream (m:85) */
+    d->analysisStride = kLBAudioDetectiveDefaultAnalysisStride;
+    d->pitchStepCount = kLBAudioDetectiveDefaultNumberOfPitchSteps;
+    return d;
+}
+
+/* m:92-111 */
+OSStatus LBAudioDetectiveDispose(LBAudioDetectiveRef d) {
+    if (d == NULL) return kLBAudioDetectiveArgumentInvalid;
+    invalidate_plan(d);
+    free(d);
+    return noErr;
+}
+
+/* m:116-131 */
+AudioStreamBasicDescription LBAudioDetectiveDefaultProcessingFormat(void) {
+    UInt32 bytesPerSample = sizeof(Float32);
+    AudioStreamBasicDescription asbd;
+    memset(&asbd, 0, sizeof asbd);
+    asbd.mFormatID = kAudioFormatLinearPCM;
+    asbd.mFormatFlags = kAudioFormatFlagIsFloat | kAudioFormatFlagIsPacked;
+    asbd.mBitsPerChannel = 8 * bytesPerSample;
+    asbd.mFramesPerPacket = 1;
+    asbd.mChannelsPerFrame = 1;
+    asbd.mBytesPerPacket = bytesPerSample * asbd.mFramesPerPacket;
+    asbd.mBytesPerFrame = bytesPerSample * asbd.mChannelsPerFrame;
+    asbd.mSampleRate = 5512.0;
+    return asbd;
+}
+
+/* m:133-151 */
+Float64 LBAudioDetectiveGetProcessingSampleRate(LBAudioDetectiveRef d) { return d->processingFormat.mSampleRate; }
+UInt32 LBAudioDetectiveGetNumberOfPitchSteps(LBAudioDetectiveRef d) { return d->pitchStepCount; }
+UInt32 LBAudioDetectiveGetSubfingerprintLength(LBAudioDetectiveRef d) { return d->subfingerprintLength; }
+UInt32 LBAudioDetectiveGetWindowSize(LBAudioDetectiveRef d) { return d->windowSize; }
+UInt32 LBAudioDetectiveGetAnalysisStride(LBAudioDetectiveRef d) { return d->analysisStride; }
+
+/* h:143 — declared upstream, never defined */
+OSStatus LBAudioDetectiveSetRecordingSampleRate(LBAudioDetectiveRef d, Float64 inSampleRate) { (void)d; (void)inSampleRate; return noErr; }
+
+/* m:156-160 */
+OSStatus LBAudioDetectiveSetProcessingSampleRate(LBAudioDetectiveRef d, Float64 inSampleRate) {
+    d->processingFormat.mSampleRate = inSampleRate; invalidate_plan(d);
+    return noErr;
+}
+/* m:162-166 */
+OSStatus LBAudioDetectiveSetNumberOfPitchSteps(LBAudioDetectiveRef d, UInt32 inNumberOfPitchSteps) {
+    d->pitchStepCount = inNumberOfPitchSteps; invalidate_plan(d);
+    return noErr;
+}
+/* m:168-172 */
+OSStatus LBAudioDetectiveSetSubfingerprintLength(LBAudioDetectiveRef d, UInt32 inSubfingerprintLength) {
+    d->subfingerprintLength = inSubfingerprintLength; invalidate_plan(d);
+    return noErr;
+}
+/* m:174-195, including the inverted power-of-two check of m:183-187 (Q13) */
+OSStatus LBAudioDetectiveSetWindowSize(LBAudioDetectiveRef d, UInt32 inWindowSize) {
+    OSStatus error = noErr;
+    invalidate_plan(d);
+    d->windowSize = inWindowSize;
+    UInt32 log2n = inWindowSize ? (UInt32)round(log2((double)inWindowSize)) : 0;
+    UInt32 n = log2n < 32 ? (1u << log2n) : 0;
+    if (n == inWindowSize) error = kLBAudioDetectiveArgumentInvalid;
+    return error;
+}
+/* m:197-201 */
+OSStatus LBAudioDetectiveSetAnalysisStride(LBAudioDetectiveRef d, UInt32 inAnalysisStride) {
+    d->analysisStride = inAnalysisStride; invalidate_plan(d);
+    return noErr;
+}
+
+/* m:361-371 and m:380-383, evaluated once per configuration instead of once per window */
+static void band_table(LBAudioDetectiveRef d, UInt32* indices, UInt32* klow, UInt32* khigh) {
+    UInt32 B = d->pitchStepCount, nFrames = d->windowSize;
+    Float64 sr = d->processingFormat.mSampleRate;
+    Float64 maxFreq = sr / 2.0;
+    Float64 minFreq = 318.0;
+    Float64 logBase = exp(log(maxFreq / minFreq) / B);
+    Float64 mincoef = (Float64)d->windowSize / sr * minFreq;
+    for (UInt32 j = 0; j <= B; j++) {
+        UInt32 start = (UInt32)((pow(logBase, j) - 1.0) * mincoef);
+        indices[j] = start + (UInt32)mincoef;
+    }
+    for (UInt32 i = 0; i < B; i++) {
+        klow[i] = (UInt32)(((2 * indices[i]) / (sr / nFrames)) - 1);
+        khigh[i] = (UInt32)(((2 * indices[i + 1]) / (sr / nFrames)) - 1);
+    }
+}
+
+static int is_pow2(UInt32 v) { return v && !(v & (v - 1)); }
+
+static OSStatus fill_geometry(LBAudioDetectiveRef d, lbadcu_geometry* g, UInt32* outIndices) {
+    UInt32 N = d->windowSize, B = d->pitchStepCount, L = d->subfingerprintLength;
+    Float64 sr = d->processingFormat.mSampleRate;
+    if (!is_pow2(N) || N < LBAD_MIN_WINDOW || N > LBAD_MAX_WINDOW) return kLBAudioDetectiveArgumentInvalid;
+    if (!is_pow2(B) || B < 4 || B > LBAD_MAX_BANDS) return kLBAudioDetectiveArgumentInvalid;
+    if (d->analysisStride == 0 || !(sr > 0.0) || !isfinite(sr)) return kLBAudioDetectiveArgumentInvalid;
+    if (L < 2 || (L & 1) || L > LBAD_MAX_SUBLEN || L / 2 > LBAD_ROWS_PER_FRAME * B) return kLBAudioDetectiveArgumentInvalid;
+    /* guard the double -> UInt32 conversions of m:369-370, m:382-383 (undefined when negative or huge) */
+    Float64 mincoef = (Float64)N / sr * 318.0;
+    if (!(mincoef >= 1.0) || mincoef > 1e6 || sr / 2.0 <= 318.0) return kLBAudioDetectiveArgumentInvalid;
+    if (((2.0 * (UInt32)mincoef) / (sr / N)) - 1.0 < 0.0) return kLBAudioDetectiveArgumentInvalid;
+    UInt32 indices[LBAD_MAX_BANDS + 1];
+    memset(g, 0, sizeof *g);
+    band_table(d, indices, g->klow, g->khigh);
+    for (UInt32 i = 0; i < B; i++) {
+        if (g->klow[i] > g->khigh[i] || g->khigh[i] > N / 2) return kLBAudioDetectiveArgumentInvalid;   /* Q15 */
+        g->divisor[i] = (Float32)(indices[i + 1] - indices[i]);                                          /* m:404 */
+    }
+    UInt32 width = (UInt32)(N / 2.0);                                                                    /* m:373 */
+    g->pos_scale = (Float32)(width / 2);                                                                 /* m:391 */
+    g->window = N; g->stride = d->analysisStride; g->bands = B; g->sublen = L;
+    if (outIndices) memcpy(outIndices, indices, (B + 1) * sizeof(UInt32));
+    return noErr;
+}
+
+static OSStatus ensure_plan(LBAudioDetectiveRef d) {
+    if (d->plan) return noErr;
+    lbadcu_geometry g;
+    OSStatus e = fill_geometry(d, &g, NULL);
+    if (e != noErr) return e;
+    return lbad_status(lbadcu_plan_create(&g, &d->plan));
+}
+
+OSStatus LBAudioDetectiveCheckConfiguration(LBAudioDetectiveRef d) {
+    if (!d) return kLBAudioDetectiveArgumentInvalid;
+    lbadcu_geometry g;
+    return fill_geometry(d, &g, NULL);
+}
+
+UInt64 LBAudioDetectiveGetNumberOfSubfingerprintsForLength(LBAudioDetectiveRef d, UInt64 n) {
+    if (!d || n < d->windowSize || d->analysisStride == 0) return 0;
+    UInt64 imageWidth = (n - d->windowSize) / d->analysisStride;                 /* m:250 */
+    return imageWidth / kLBAudioDetectiveDefaultNumberOfRowsPerFrame;            /* m:255 */
+}
+
+OSStatus LBAudioDetectiveGetBandTable(LBAudioDetectiveRef d, UInt32* outIndices, UInt32* outLow, UInt32* outHigh) {
+    if (!d) return kLBAudioDetectiveArgumentInvalid;
+    lbadcu_geometry g; UInt32 indices[LBAD_MAX_BANDS + 1];
+    OSStatus e = fill_geometry(d, &g, indices);
+    if (e != noErr) return e;
+    if (outIndices) memcpy(outIndices, indices, (d->pitchStepCount + 1) * sizeof(UInt32));
+    if (outLow) memcpy(outLow, g.klow, d->pitchStepCount * sizeof(UInt32));
+    if (outHigh) memcpy(outHigh, g.khigh, d->pitchStepCount * sizeof(UInt32));
+    return noErr;
+}
+
+/* replaces m:208-308 */
+OSStatus LBAudioDetectiveProcessPCM(LBAudioDetectiveRef d, const Float32* inSamples, UInt64 inNumberFrames, LBAudioDetectiveFingerprintRef* outFingerprint) {
+    if (!d || !outFingerprint) return kLBAudioDetectiveArgumentInvalid;
+    *outFingerprint = NULL;
+    if (!inSamples) return kLBAudioDetectiveArgumentInvalid;                     /* m:211-214 */
+    OSStatus e = ensure_plan(d);
+    if (e != noErr) return e;
+    LBAudioDetectiveFingerprintRef fp = LBAudioDetectiveFingerprintNew(0);       /* m:297 */
+    UInt32 L = d->subfingerprintLength;
+    LBAudioDetectiveFingerprintSetSubfingerprintLength(fp, &L);                  /* m:326-327 */
+    *outFingerprint = fp;
+    if (inNumberFrames < d->windowSize) return kLBAudioDetectiveArgumentInvalid; /* upstream underflows at m:250 */
+    UInt64 count = LBAudioDetectiveGetNumberOfSubfingerprintsForLength(d, inNumberFrames);
+    if (count == 0) return noErr;
+    if (count > 0x7fffffffu) return kLBAudioDetectiveArgumentInvalid;
+    UInt32 W = lbad_words_per_plane(L);
+    UInt32* words = malloc((size_t)count * 2 * W * sizeof(UInt32));
+    if (!words) return kLBAudioDetectiveArgumentInvalid;
+    e = lbad_status(lbadcu_extract_host(d->plan, inSamples, 1, inNumberFrames, inNumberFrames, words, NULL, NULL, 0));
+    if (e == noErr) e = lbad_fingerprint_append_packed(fp, words, (UInt32)count);   /* m:328 */
+    free(words);
+    return e;
+}
+
+/* replaces m:442-464 */
+OSStatus LBAudioDetectiveComparePCM(LBAudioDetectiveRef d, const Float32* s1, UInt64 n1, const Float32* s2, UInt64 n2, UInt32 inComparisonRange, Float32* outMatch) {
+    if (!d) return kLBAudioDetectiveArgumentInvalid;
+    if (inComparisonRange == 0) inComparisonRange = d->subfingerprintLength;     /* m:443-445 */
+    LBAudioDetectiveFingerprintRef fp1 = NULL, fp2 = NULL;
+    OSStatus error = LBAudioDetectiveProcessPCM(d, s1, n1, &fp1);                /* m:449 */
+    if (error == noErr) error = LBAudioDetectiveProcessPCM(d, s2, n2, &fp2);     /* m:453 */
+    if (error == noErr && outMatch) *outMatch = LBAudioDetectiveFingerprintCompareToFingerprint(fp1, fp2, inComparisonRange);   /* m:456-458 */
+    LBAudioDetectiveFingerprintDispose(fp1);                                     /* m:460-461 */
+    LBAudioDetectiveFingerprintDispose(fp2);
+    return error;
+}
+
+OSStatus LBAudioDetectiveProcessPCMBatch(LBAudioDetectiveRef d, const Float32* inSamples, UInt32 nClips, UInt64 framesPerClip, UInt64 clipStride, UInt32* outWords) {
+    if (!d || !inSamples || !outWords || nClips == 0 || clipStride < framesPerClip) return kLBAudioDetectiveArgumentInvalid;
+    OSStatus e = ensure_plan(d);
+    if (e != noErr) return e;
+    if (framesPerClip < d->windowSize) return kLBAudioDetectiveArgumentInvalid;
+    return lbad_status(lbadcu_extract_host(d->plan, inSamples, nClips, framesPerClip, clipStride, outWords, NULL, NULL, 0));
+}
+
+OSStatus LBAudioDetectiveProcessPCMBatchDevice(LBAudioDetectiveRef d, const Float32* dSamples, UInt32 nClips, UInt64 framesPerClip, UInt64 clipStride, UInt32* dWords, void* stream) {
+    if (!d || !dSamples || !dWords || nClips == 0 || clipStride < framesPerClip) return kLBAudioDetectiveArgumentInvalid;
+    OSStatus e = ensure_plan(d);
+    if (e != noErr) return e;
+    if (framesPerClip < d->windowSize) return kLBAudioDetectiveArgumentInvalid;
+    return lbad_status(lbadcu_extract_device(d->plan, dSamples, nClips, framesPerClip, clipStride, dWords, NULL, NULL, 0, stream));
+}
+
+OSStatus LBAudioDetectiveProcessPCMStages(LBAudioDetectiveRef d, const Float32* inSamples, UInt64 n, Float32* outImages, Float32* outHaar, Boolean* outBooleans, Boolean useFused) {
+    if (!d || !inSamples) return kLBAudioDetectiveArgumentInvalid;
+    OSStatus e = ensure_plan(d);
+    if (e != noErr) return e;
+    if (n < d->windowSize) return kLBAudioDetectiveArgumentInvalid;
+    if (useFused && !lbadcu_plan_fused_supported(d->plan)) return kLBAudioDetectiveArgumentInvalid;
+    UInt64 count = LBAudioDetectiveGetNumberOfSubfingerprintsForLength(d, n);
+    if (count == 0) return noErr;
+    UInt32 L = d->subfingerprintLength, W = lbad_words_per_plane(L);
+    UInt32* words = malloc((size_t)count * 2 * W * sizeof(UInt32));
+    if (!words) return kLBAudioDetectiveArgumentInvalid;
+    e = lbad_status(lbadcu_extract_host(d->plan, inSamples, 1, n, n, words, outImages, outHaar, useFused ? 1 : 2));
+    if (e == noErr && outBooleans) for (UInt64 i = 0; i < count; i++) lbad_unpack_words(words + i * 2 * W, L, W, outBooleans + i * L);
+    free(words);
+    return e;
+}
+
+OSStatus LBAudioDetectiveTransformImages(LBAudioDetectiveRef d, const Float32* inImages, UInt32 inCount, Float32* outHaar, Boolean* outBooleans) {
+    if (!d || !inImages || inCount == 0) return kLBAudioDetectiveArgumentInvalid;
+    OSStatus e = ensure_plan(d);
+    if (e != noErr) return e;
+    UInt32 L = d->subfingerprintLength, W = lbad_words_per_plane(L);
+    UInt32* words = malloc((size_t)inCount * 2 * W * sizeof(UInt32));
+    if (!words) return kLBAudioDetectiveArgumentInvalid;
+    e = lbad_status(lbadcu_transform_images_host(d->plan, inImages, inCount, outHaar, words));
+    if (e == noErr && outBooleans) for (UInt32 i = 0; i < inCount; i++) lbad_unpack_words(words + (size_t)i * 2 * W, L, W, outBooleans + (size_t)i * L);
+    free(words);
+    return e;
+}
+
+UInt64 LBAudioDetectiveGetKernelLaunchCount(LBAudioDetectiveRef d) {
+    if (!d) return 0;
+    return d->launchesBefore + (d->plan ? lbadcu_plan_launches(d->plan) : 0);
+}
+
+UInt32 LBAudioDetectiveGetKernelTiming(LBAudioDetectiveRef d, Boolean inEnable, Boolean inReset, Float64* outTotalMilliseconds) {
+    if (outTotalMilliseconds) *outTotalMilliseconds = 0.0;
+    if (!d || ensure_plan(d) != noErr) return 0;
+    return lbadcu_plan_timing(d->plan, inEnable, inReset, outTotalMilliseconds);
+}

@@ -1,0 +1,100 @@
+/*
+ * LBAudioDetectiveDatabase.c — host side of the batched matcher (see include/LBAudioDetectiveDatabase.h).
+ * Marshals packed fingerprints into the CUDA layer (lbad_search.cu); no match arithmetic happens here.
+ */
+#include "lbad_host.h"
+#include <stdlib.h>
+#include <string.h>
+
+struct LBAudioDetectiveDatabase {
+    UInt32 subfingerprintLength;
+    UInt32 W;
+    lbadcu_db* db;
+};
+
+LBAudioDetectiveDatabaseRef LBAudioDetectiveDatabaseNew(UInt32 inSubfingerprintLength) {
+    UInt32 W = lbad_words_per_plane(inSubfingerprintLength);
+    if (!W) return NULL;
+    LBAudioDetectiveDatabaseRef d = calloc(1, sizeof *d);
+    if (!d) return NULL;
+    d->subfingerprintLength = inSubfingerprintLength; d->W = W;
+    if (lbadcu_db_create(W, &d->db) != LBAD_OK) { free(d); return NULL; }
+    return d;
+}
+
+OSStatus LBAudioDetectiveDatabaseDispose(LBAudioDetectiveDatabaseRef d) {
+    if (!d) return kLBAudioDetectiveArgumentInvalid;
+    lbadcu_db_destroy(d->db); free(d);
+    return noErr;
+}
+
+UInt32 LBAudioDetectiveDatabaseGetNumberOfClips(LBAudioDetectiveDatabaseRef d) { return d ? lbadcu_db_clips(d->db) : 0; }
+UInt64 LBAudioDetectiveDatabaseGetNumberOfSubfingerprints(LBAudioDetectiveDatabaseRef d) { return d ? lbadcu_db_subfps(d->db) : 0; }
+
+OSStatus LBAudioDetectiveDatabaseSetClipIndexBase(LBAudioDetectiveDatabaseRef d, UInt32 inBase) {
+    if (!d) return kLBAudioDetectiveArgumentInvalid;
+    lbadcu_db_set_base(d->db, inBase);
+    return noErr;
+}
+
+OSStatus LBAudioDetectiveDatabaseAddFingerprint(LBAudioDetectiveDatabaseRef d, LBAudioDetectiveFingerprintRef fp, UInt32* outClipIndex) {
+    if (!d || !fp || fp->subfingerprintLength != d->subfingerprintLength) return kLBAudioDetectiveArgumentInvalid;
+    UInt32 idx = lbadcu_db_clips(d->db), n = fp->subfingerprintCount, dummy[16] = {0};
+    OSStatus e = lbad_status(lbadcu_db_append(d->db, n ? fp->words : dummy, 0, 1, &n, 0));
+    if (e == noErr && outClipIndex) *outClipIndex = idx;
+    return e;
+}
+
+OSStatus LBAudioDetectiveDatabaseAddPacked(LBAudioDetectiveDatabaseRef d, const UInt32* inWords, UInt32 nClips, const UInt32* inCounts, UInt32 uniform) {
+    if (!d || !inWords) return kLBAudioDetectiveArgumentInvalid;
+    return lbad_status(lbadcu_db_append(d->db, inWords, 0, nClips, inCounts, uniform));
+}
+
+OSStatus LBAudioDetectiveDatabaseAddPackedDevice(LBAudioDetectiveDatabaseRef d, const UInt32* inDeviceWords, UInt32 nClips, UInt32 uniform) {
+    if (!d || !inDeviceWords) return kLBAudioDetectiveArgumentInvalid;
+    return lbad_status(lbadcu_db_append(d->db, inDeviceWords, 1, nClips, NULL, uniform));
+}
+
+static UInt32 pairs_for(LBAudioDetectiveDatabaseRef d, UInt32 inRange) {
+    if (inRange == 0) inRange = d->subfingerprintLength;                         /* LBAudioDetective.m:443-445 */
+    return lbad_pairs_for_range(inRange, d->subfingerprintLength);
+}
+
+OSStatus LBAudioDetectiveDatabaseSearchPacked(LBAudioDetectiveDatabaseRef d, const UInt32* inQueryWords, UInt32 nQ, UInt32 qCount, UInt32 inRange, UInt32 inK,
+                                              Float32* outScores, UInt32* outClipIndices, Float32* outAllScores) {
+    if (!d || (!inQueryWords && qCount) || !outScores || !outClipIndices) return kLBAudioDetectiveArgumentInvalid;
+    UInt32 dummy[16] = {0};
+    return lbad_status(lbadcu_db_search_host(d->db, qCount ? inQueryWords : dummy, nQ, qCount, pairs_for(d, inRange), inK, outScores, outClipIndices, outAllScores));
+}
+
+OSStatus LBAudioDetectiveDatabaseSearch(LBAudioDetectiveDatabaseRef d, const LBAudioDetectiveFingerprintRef* inQueries, UInt32 nQ, UInt32 inRange, UInt32 inK,
+                                        Float32* outScores, UInt32* outClipIndices) {
+    if (!d || !inQueries || nQ == 0) return kLBAudioDetectiveArgumentInvalid;
+    UInt32 qCount = inQueries[0]->subfingerprintCount;
+    for (UInt32 i = 0; i < nQ; i++)
+        if (inQueries[i]->subfingerprintCount != qCount || inQueries[i]->subfingerprintLength != d->subfingerprintLength) return kLBAudioDetectiveArgumentInvalid;
+    size_t per = (size_t)qCount * 2 * d->W;
+    UInt32* words = malloc(((per * nQ) > 0 ? per * nQ : 1) * sizeof(UInt32));
+    if (!words) return kLBAudioDetectiveArgumentInvalid;
+    for (UInt32 i = 0; i < nQ; i++) memcpy(words + per * i, inQueries[i]->words, per * sizeof(UInt32));
+    OSStatus e = LBAudioDetectiveDatabaseSearchPacked(d, words, nQ, qCount, inRange, inK, outScores, outClipIndices, NULL);
+    free(words);
+    return e;
+}
+
+OSStatus LBAudioDetectiveDatabaseSearchDevice(LBAudioDetectiveDatabaseRef d, const UInt32* dQ, UInt32 nQ, UInt32 qCount, UInt32 inRange, UInt32 inK,
+                                              Float32* dScores, UInt32* dIdx, void* stream) {
+    if (!d || !dQ || !dScores || !dIdx) return kLBAudioDetectiveArgumentInvalid;
+    return lbad_status(lbadcu_db_search_device(d->db, dQ, nQ, qCount, pairs_for(d, inRange), inK, dScores, dIdx, NULL, stream));
+}
+
+OSStatus LBAudioDetectiveDatabaseMergeTopK(const Float32* inScores, const UInt32* inClipIndices, UInt32 nLists, UInt32 nQ, UInt32 inK, Float32* outScores, UInt32* outClipIndices) {
+    return lbad_status(lbadcu_merge_topk_host(inScores, inClipIndices, nLists, nQ, inK, outScores, outClipIndices));
+}
+
+UInt64 LBAudioDetectiveDatabaseComparesPerQuery(LBAudioDetectiveDatabaseRef d, UInt32 qCount) { return d ? lbadcu_db_compares_per_query(d->db, qCount) : 0; }
+UInt64 LBAudioDetectiveDatabaseGetKernelLaunchCount(LBAudioDetectiveDatabaseRef d) { return d ? lbadcu_db_launches(d->db) : 0; }
+UInt32 LBAudioDetectiveDatabaseGetKernelTiming(LBAudioDetectiveDatabaseRef d, Boolean inEnable, Boolean inReset, Float64* outTotalMilliseconds) {
+    if (outTotalMilliseconds) *outTotalMilliseconds = 0.0;
+    return d ? lbadcu_db_timing(d->db, inEnable, inReset, outTotalMilliseconds) : 0;
+}

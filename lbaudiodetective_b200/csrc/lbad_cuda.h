@@ -1,0 +1,97 @@
+/*
+ * lbad_cuda.h — internal C interface between the host-side API layer (plain C: LBAudioDetective.c,
+ * LBAudioDetectiveFingerprint.c, LBAudioDetectiveDatabase.c) and the CUDA layer (lbad_extract.cu,
+ * lbad_search.cu, lbad_synth.cu).  Plain pointers and sizes only.  Not installed; not part of the public ABI.
+ */
+#ifndef LBAD_CUDA_H
+#define LBAD_CUDA_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBAD_ROWS_PER_FRAME 128u     /* LBAudioDetective.m:25 */
+#define LBAD_MAX_BANDS      64u
+#define LBAD_MAX_WINDOW     2048u
+#define LBAD_MIN_WINDOW     256u
+#define LBAD_MAX_SUBLEN     512u
+
+#define LBAD_OK              0
+#define LBAD_ERR_ARG         1       /* kLBAudioDetectiveArgumentInvalid */
+#define LBAD_ERR_NODEVICE   (-7001)
+#define LBAD_ERR_CUDA       (-7002)
+
+/* Geometry + host-computed tables (the band table follows LBAudioDetective.m:361-383 in double precision). */
+typedef struct {
+    uint32_t window;                 /* N, power of two, 256..2048 */
+    uint32_t stride;                 /* hop */
+    uint32_t bands;                  /* B, power of two, 4..64 */
+    uint32_t sublen;                 /* L Booleans kept per subfingerprint */
+    uint32_t klow[LBAD_MAX_BANDS];   /* first FFT bin of each band (m:382) */
+    uint32_t khigh[LBAD_MAX_BANDS];  /* one past the last bin (m:383) */
+    float    divisor[LBAD_MAX_BANDS];/* (Float32)(indices[i+1]-indices[i]) (m:404) */
+    float    pos_scale;              /* (Float32)(width/2) with width = N/2 (m:373, m:391) */
+} lbadcu_geometry;
+
+typedef struct lbadcu_plan lbadcu_plan;
+
+/* 0 if a CUDA device is usable */
+int  lbadcu_device_available(void);
+const char* lbadcu_last_error(void);
+
+int  lbadcu_plan_create(const lbadcu_geometry* g, lbadcu_plan** out);
+void lbadcu_plan_destroy(lbadcu_plan* p);
+int  lbadcu_plan_fused_supported(const lbadcu_plan* p);
+void* lbadcu_plan_stream(lbadcu_plan* p);
+uint64_t lbadcu_plan_launches(const lbadcu_plan* p);
+uint32_t lbadcu_plan_timing(lbadcu_plan* p, int enable, int reset, double* total_ms);
+
+/* Extraction over DEVICE-resident PCM.  Clip c starts at d_pcm + c*clip_stride and has clip_len samples; every
+ * clip yields frames = ((clip_len - N)/hop)/128 subfingerprints.  d_words: [clip][frame][2*W].
+ * mode: 0 = auto (fused when supported), 1 = force fused, 2 = force generic.  d_images / d_haar (optional stage
+ * dumps): [clip][frame][128][B].  Enqueues on `stream` (NULL = the plan's stream); does not synchronise. */
+int  lbadcu_extract_device(lbadcu_plan* p, const float* d_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
+                           uint32_t* d_words, float* d_images, float* d_haar, int mode, void* stream);
+/* Host-memory front end: uploads in chunks on two streams, runs the kernels, downloads the packed words. */
+int  lbadcu_extract_host(lbadcu_plan* p, const float* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
+                         uint32_t* h_words, float* h_images, float* h_haar, int mode);
+/* Haar + top-t + pack on device images [count][128][B] (generic kernel). */
+int  lbadcu_transform_images_host(lbadcu_plan* p, const float* h_images, uint32_t count, float* h_haar, uint32_t* h_words);
+
+/* ---- search ---- */
+typedef struct lbadcu_db lbadcu_db;
+int  lbadcu_db_create(uint32_t words_per_plane, lbadcu_db** out);
+void lbadcu_db_destroy(lbadcu_db* db);
+uint32_t lbadcu_db_clips(const lbadcu_db* db);
+uint64_t lbadcu_db_subfps(const lbadcu_db* db);
+uint32_t lbadcu_db_min_count(const lbadcu_db* db);
+uint32_t lbadcu_db_max_count(const lbadcu_db* db);
+void lbadcu_db_set_base(lbadcu_db* db, uint32_t base);
+void* lbadcu_db_stream(lbadcu_db* db);
+uint64_t lbadcu_db_launches(const lbadcu_db* db);
+uint32_t lbadcu_db_timing(lbadcu_db* db, int enable, int reset, double* total_ms);
+/* counts == NULL -> uniform_count for every clip; words on host or device */
+int  lbadcu_db_append(lbadcu_db* db, const uint32_t* words, int words_on_device, uint32_t n_clips, const uint32_t* counts, uint32_t uniform_count);
+/* pairs = number of (P,M) bit pairs compared = ceil(min(range, L)/2).  Outputs [q][k]; d_all optional [q][clips]. */
+int  lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_qwords, uint32_t n_q, uint32_t q_count, uint32_t pairs, uint32_t k,
+                             float* d_scores, uint32_t* d_idx, float* d_all, void* stream);
+int  lbadcu_db_search_host(lbadcu_db* db, const uint32_t* h_qwords, uint32_t n_q, uint32_t q_count, uint32_t pairs, uint32_t k,
+                           float* h_scores, uint32_t* h_idx, float* h_all);
+uint64_t lbadcu_db_compares_per_query(const lbadcu_db* db, uint32_t q_count);
+/* merges [list][q][k] top-k lists (host memory) with the device merge kernel; order (score desc, index asc) */
+int  lbadcu_merge_topk_host(const float* h_sc, const uint32_t* h_id, uint32_t n_lists, uint32_t n_q, uint32_t k, float* o_sc, uint32_t* o_id);
+
+/* ---- synthetic PCM on the device (bench support; same formula as the host generator, device libm) ---- */
+int  lbadcu_synth_device(float* d_out, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride, uint64_t first_clip_id,
+                         uint64_t base_seed, double sample_rate, void* stream);
+/* random rank-sign codes straight into packed words, for search timing at sizes extraction would take long to fill */
+int  lbadcu_random_codes_device(uint32_t* d_words, uint64_t n_subfps, uint32_t words_per_plane, uint32_t pairs, uint64_t seed, void* stream);
+
+/* ---- microbenchmarks (roofline denominators measured on the box: FP32 FMA rate, POPC rate) ---- */
+int  lbadcu_microbench(double* fp32_tflops, double* popc_gops, double* lop3_gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,671 @@
+/*
+ * lbad_extract.cu — fingerprint extraction kernels for sm_100a.
+ *
+ * Replaces, on the GPU, the reference's whole extraction path (file:line into /root/reference/LBAudioDetective/):
+ *   framing loop                      LBAudioDetective.m:250-293
+ *   vDSP real FFT                     LBAudioDetective.m:351-355
+ *   band energies (Q4/Q5/Q6 quirks)   LBAudioDetective.m:373-405
+ *   2-D standard Haar                 LBAudioDetectiveFrame.m:113-153
+ *   ordered top-t sign bits           LBAudioDetectiveFrame.m:165-191, truncation LBAudioDetective.m:321-328
+ *
+ * Two paths:
+ *   fused   (window 2048, 32 bands, even hop, frame span fits shared memory): ONE kernel, persistent CTAs, one frame
+ *           (= one subfingerprint) per CTA iteration.  The frame's 127*hop+2048 samples are brought into shared
+ *           memory once by a 1-D TMA bulk copy (cp.async.bulk + mbarrier), so every PCM sample is read from HBM
+ *           once; each warp runs a 2048-point real FFT per window entirely in registers (2 x radix-32 with one
+ *           shared-memory transpose), bins the bands, and the CTA then does Haar + top-t + packing in shared
+ *           memory and writes 2*W words.
+ *   generic (any supported geometry): bands kernel (one warp per window, shared-memory radix-2 FFT) -> images in
+ *           global memory -> Haar/select kernel (one CTA per frame).  Also the on-device cross-check of the fused path.
+ */
+#include "lbad_common.cuh"
+#include "lbad_math.cuh"
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <stdlib.h>
+#include <vector>
+
+namespace lbad {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+    fprintf(stderr, "LBAudioDetective(CUDA): %s\n", g_err);
+}
+
+/* ------------------------------------------------------------------------------------------------ tables ---- */
+
+struct BandTable {                       /* by-value kernel parameter */
+    uint32_t klow[LBAD_MAX_BANDS];
+    uint32_t khigh[LBAD_MAX_BANDS];
+    float    divisor[LBAD_MAX_BANDS];
+};
+
+struct Geo {                             /* by-value kernel parameter */
+    uint32_t window, log2m, stride, bands, pairs, words_per_plane;
+    uint32_t kmin, kmax;                 /* union of the band ranges: [kmin, kmax) */
+    float inv_pos_scale;
+    uint32_t frames_per_clip;
+    uint64_t clip_stride;
+};
+
+/* --------------------------------------------------------------------------- Haar + select building blocks ---- */
+
+struct SelectSmem {
+    uint32_t counters[32];
+    uint32_t warp_tot[32];
+    uint32_t surv_key[256];
+    uint32_t surv_idx[256];              /* flat index | sign code << 16 (1: v > 0, 2: v < 0) */
+    uint32_t words[16];
+    uint32_t nsurv;
+    uint32_t pad[3];
+};
+
+/* Ordered top-T by |v| (stable: lower flat index first on ties) -> packed sign planes.
+ * THREADS threads, each owning E consecutive flat indices [tid*E, tid*E+E); elem(idx) returns the coefficient.
+ * Must be called by all threads of the CTA.  out: 2*W words (global). */
+template <int THREADS, int E, class Elem>
+__device__ __forceinline__ void select_and_pack(Elem elem, const int T, const int W, uint32_t* __restrict__ out, SelectSmem& sm) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t key[E];
+    uint32_t pos = 0, neg = 0;           /* sign bits of my E elements (E <= 32) */
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const float v = elem(tid * E + e);
+        key[e] = __float_as_uint(v) & 0x7fffffffu;
+        pos |= (v > 0.0f ? 1u : 0u) << e;
+        neg |= (v < 0.0f ? 1u : 0u) << e;
+    }
+    if (tid < 32) sm.counters[tid] = 0;
+    if (tid < 16) sm.words[tid] = 0;
+    if (tid == 0) sm.nsurv = 0;
+    __syncthreads();
+    /* largest threshold with count(key >= threshold) >= T, one bit at a time */
+    uint32_t thr = 0;
+    for (int bit = 30; bit >= 0; --bit) {
+        const uint32_t cand = thr | (1u << bit);
+        uint32_t c = 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) c += (key[e] >= cand) ? 1u : 0u;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0 && c) atomicAdd(&sm.counters[bit], c);
+        __syncthreads();
+        if (sm.counters[bit] >= (uint32_t)T) thr = cand;
+    }
+    /* strictly greater: all survive; equal: the first (T - n_gt) in flat-index order survive */
+    uint32_t ngt = 0, neq = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) { ngt += key[e] > thr; neq += key[e] == thr; }
+    uint32_t packed = (ngt << 16) | neq;                 /* both totals <= 8192 */
+    uint32_t incl = packed;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) sm.warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) { const uint32_t t = sm.warp_tot[w]; total += t; if (w < wid) before += t; }
+    const uint32_t eq_before = ((before + incl - packed) & 0xffffu);
+    const uint32_t need_eq = (uint32_t)T - (total >> 16);
+    uint32_t eq_rank = eq_before;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        bool take = key[e] > thr;
+        if (key[e] == thr) { take = eq_rank < need_eq; eq_rank++; }
+        if (take) {
+            const uint32_t slot = atomicAdd(&sm.nsurv, 1u);
+            if (slot < 256u) {
+                sm.surv_key[slot] = key[e];
+                sm.surv_idx[slot] = (uint32_t)(tid * E + e) | (((pos >> e) & 1u) << 16) | (((neg >> e) & 1u) << 17);
+            }
+        }
+    }
+    __syncthreads();
+    /* rank by counting: survivor j precedes s iff key_j > key_s, or equal keys and idx_j < idx_s */
+    for (int s = tid; s < T; s += THREADS) {
+        const uint32_t ks = sm.surv_key[s], is = sm.surv_idx[s], idx = is & 0xffffu;
+        uint32_t rank = 0;
+        for (int j = 0; j < T; j++) {
+            const uint32_t kj = sm.surv_key[j], ij = sm.surv_idx[j] & 0xffffu;
+            rank += (kj > ks || (kj == ks && ij < idx)) ? 1u : 0u;
+        }
+        if (is & (1u << 16)) atomicOr(&sm.words[rank >> 5], 1u << (rank & 31));
+        if (is & (1u << 17)) atomicOr(&sm.words[W + (rank >> 5)], 1u << (rank & 31));
+    }
+    __syncthreads();
+    if (tid < 2 * W) out[tid] = sm.words[tid];
+}
+
+/* 1-D Haar of LBAudioDetectiveFrame.m:134-153 on a strided vector, sequential, any length (integer halving). */
+__device__ __forceinline__ void haar_1d_seq(float* a, int stride, int n, float* tmp, int tstride) {
+    const float sn = sqrtf((float)n), s2 = sqrtf(2.0f);
+    for (int i = 0; i < n; i++) a[i * stride] = __fdiv_rn(a[i * stride], sn);
+    while (n > 1) {
+        n /= 2;
+        for (int i = 0; i < n; i++) {
+            const float x0 = a[(2 * i) * stride], x1 = a[(2 * i + 1) * stride];
+            tmp[i * tstride] = __fdiv_rn(__fadd_rn(x0, x1), s2);
+            tmp[(n + i) * tstride] = __fdiv_rn(__fsub_rn(x0, x1), s2);
+        }
+        for (int i = 0; i < 2 * n; i++) a[i * stride] = tmp[i * tstride];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ generic path ---- */
+
+constexpr int GEN_WARPS = 4;
+
+/* One warp per window: shared-memory radix-2 DIF FFT of M = N/2 complex points, real split on the band bins only,
+ * band sums in the reference's order.  Writes images[frame][row][band]. */
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+bands_generic_kernel(const float* __restrict__ pcm, float* __restrict__ images, const float2* __restrict__ tw_m,
+                     const float2* __restrict__ tw_n, const Geo g, const BandTable bt, const uint64_t total_windows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t M = g.window / 2;
+    float2* z = reinterpret_cast<float2*>(smem_raw) + (size_t)wid * M;
+    float* v = reinterpret_cast<float*>(reinterpret_cast<float2*>(smem_raw) + (size_t)GEN_WARPS * M) + (size_t)wid * M;
+    const uint64_t wpc = (uint64_t)g.frames_per_clip * LBAD_ROWS_PER_FRAME;      /* windows used per clip */
+    for (uint64_t w = (uint64_t)blockIdx.x * GEN_WARPS + wid; w < total_windows; w += (uint64_t)gridDim.x * GEN_WARPS) {
+        const uint64_t clip = w / wpc, wi = w % wpc;
+        const float* x = pcm + clip * g.clip_stride + wi * g.stride;          /* m:262-290: window i starts at hop*i */
+        for (uint32_t i = lane; i < M; i += 32) z[i] = make_float2(x[2 * i], x[2 * i + 1]);   /* vDSP_ctoz, m:353 */
+        __syncwarp();
+        for (uint32_t h = M / 2; h >= 1; h >>= 1) {
+            const uint32_t tstep = (M / 2) / h;
+            for (uint32_t t = lane; t < M / 2; t += 32) {
+                const uint32_t j = t & (h - 1), a = ((t / h) * 2 * h) + j, b = a + h;
+                const float2 za = z[a], zb = z[b], tw = tw_m[j * tstep];      /* tw = (cos, -sin) */
+                const float dr = za.x - zb.x, di = za.y - zb.y;
+                z[a] = make_float2(za.x + zb.x, za.y + zb.y);
+                z[b] = make_float2(dr * tw.x - di * tw.y, dr * tw.y + di * tw.x);
+            }
+            __syncwarp();
+        }
+        const uint32_t sh = 32 - g.log2m;
+        for (uint32_t k = g.kmin + lane; k < g.kmax; k += 32) {
+            float xr, xi;
+            if (k == 0) {                                                       /* DC in re, Nyquist packed in im (Q2) */
+                const float2 z0 = z[0];
+                xr = 2.0f * (z0.x + z0.y); xi = 2.0f * (z0.x - z0.y);
+            } else {
+                const float2 zk = z[__brev(k) >> sh], zp = z[__brev(M - k) >> sh], tw = tw_n[k];   /* tw = (cos, sin) */
+                real_split_2x(zk.x, zk.y, zp.x, zp.y, tw.x, tw.y, xr, xi);
+            }
+            v[k] = bin_energy(xr, xi, g.inv_pos_scale);                         /* m:387-401 */
+        }
+        __syncwarp();
+        for (uint32_t b = lane; b < g.bands; b += 32) {                         /* m:379-405, sums in increasing k */
+            float p = 0.0f;
+            for (uint32_t k = bt.klow[b]; k < bt.khigh[b]; k++) p = __fadd_rn(p, v[k]);
+            images[w * g.bands + b] = __fdiv_rn(p, bt.divisor[b]);
+        }
+        __syncwarp();
+    }
+}
+
+constexpr int HS_THREADS = 256;
+
+/* One CTA per frame: Haar (rows then columns, Frame.m:113-132) + ordered top-T + pack. */
+template <int B>
+__global__ void __launch_bounds__(HS_THREADS)
+haar_select_kernel(const float* __restrict__ images, float* __restrict__ haar_out, uint32_t* __restrict__ words,
+                   const int T, const int W, const uint32_t total_frames) {
+    constexpr int R = LBAD_ROWS_PER_FRAME, LD = B + 1;
+    extern __shared__ __align__(16) float hs_smem[];
+    float* a = hs_smem;
+    float* tmp = hs_smem + R * LD;
+    __shared__ SelectSmem sel;
+    const int tid = threadIdx.x;
+    for (uint32_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+        const float* img = images + (size_t)f * R * B;
+        for (int i = tid; i < R * B; i += HS_THREADS) a[(i / B) * LD + (i % B)] = img[i];
+        __syncthreads();
+        if (tid < R) haar_1d_seq(a + tid * LD, 1, B, tmp + tid * LD, 1);                 /* rows, Frame.m:114-116 */
+        __syncthreads();
+        if (tid < B) haar_1d_seq(a + tid, LD, R, tmp + tid, LD);                          /* columns, Frame.m:118-131 */
+        __syncthreads();
+        if (haar_out) for (int i = tid; i < R * B; i += HS_THREADS) haar_out[(size_t)f * R * B + i] = a[(i / B) * LD + (i % B)];
+        select_and_pack<HS_THREADS, (R * B) / HS_THREADS>([&](int idx) { return a[(idx / B) * LD + (idx % B)]; }, T, W,
+                                                          words + (size_t)f * 2 * W, sel);
+        __syncthreads();
+    }
+}
+
+/* -------------------------------------------------------------------------------------------- fused path ---- */
+
+constexpr int FUSED_WARPS = 4;
+constexpr int FUSED_THREADS = FUSED_WARPS * 32;
+constexpr int FUSED_LD = 33;                 /* image row stride (floats) */
+constexpr int SCR_LD = 34;                   /* transpose scratch row stride (float2) */
+
+struct FusedSmemLayout {
+    uint32_t samples_bytes, total_bytes;
+    uint32_t off_scratch, off_tw1, off_tw2, off_img, off_sel, off_bar;
+};
+static FusedSmemLayout fused_layout(uint32_t span_floats) {
+    FusedSmemLayout L;
+    L.samples_bytes = (span_floats * 4 + 15) & ~15u;
+    uint32_t o = L.samples_bytes;
+    L.off_scratch = o; o += FUSED_WARPS * 32 * SCR_LD * 8;
+    L.off_tw1 = o;     o += 32 * 32 * 8;
+    L.off_tw2 = o;     o += 32 * 32 * 8;
+    L.off_img = o;     o += LBAD_ROWS_PER_FRAME * FUSED_LD * 4;
+    L.off_sel = o;     o += (sizeof(SelectSmem) + 15) & ~15u;
+    L.off_bar = o;     o += 16;
+    L.total_bytes = o;
+    return L;
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 2)
+extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words, float* __restrict__ images_out,
+                     float* __restrict__ haar_out, const float2* __restrict__ g_tw1, const float2* __restrict__ g_tw2,
+                     const Geo g, const BandTable bt, const FusedSmemLayout L, const uint32_t span_floats,
+                     const uint32_t total_frames, const int use_tma) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float*  samples = reinterpret_cast<float*>(smem);
+    float2* tw1 = reinterpret_cast<float2*>(smem + L.off_tw1);
+    float2* tw2 = reinterpret_cast<float2*>(smem + L.off_tw2);
+    float*  img = reinterpret_cast<float*>(smem + L.off_img);
+    SelectSmem& sel = *reinterpret_cast<SelectSmem*>(smem + L.off_sel);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float2* scr = reinterpret_cast<float2*>(smem + L.off_scratch) + wid * (32 * SCR_LD);
+    float* vbuf = reinterpret_cast<float*>(scr);             /* band scratch aliases the transpose scratch */
+
+    for (int i = tid; i < 1024; i += FUSED_THREADS) { tw1[i] = g_tw1[i]; tw2[i] = g_tw2[i]; }
+    if (tid == 0 && use_tma) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncthreads();
+
+    const uint32_t klow = bt.klow[lane], khigh = bt.khigh[lane];
+    const float divisor = bt.divisor[lane];
+    const int k2lo = (int)(g.kmin >> 5), k2hi = (int)((g.kmax - 1) >> 5);
+    const uint32_t hop = g.stride;
+    const uint32_t bytes = span_floats * 4;
+
+    auto frame_src = [&](uint32_t f) -> const float* {
+        const uint32_t clip = f / g.frames_per_clip, fr = f % g.frames_per_clip;
+        return pcm + (uint64_t)clip * g.clip_stride + (uint64_t)fr * LBAD_ROWS_PER_FRAME * hop;   /* m:262-290 */
+    };
+
+    uint32_t f = blockIdx.x, parity = 0;
+    if (f < total_frames && use_tma && tid == 0) { mbar_arrive_expect_tx(bar, bytes); bulk_copy_g2s(samples, frame_src(f), bytes, bar); }
+
+    for (; f < total_frames; f += gridDim.x) {
+        if (use_tma) { mbar_wait(bar, parity); parity ^= 1; }
+        else {
+            const float* src = frame_src(f);
+            for (uint32_t i = tid; i < span_floats; i += FUSED_THREADS) samples[i] = src[i];
+            __syncthreads();
+        }
+
+        /* ---- 32 windows per warp: FFT -> bands -> image row ---- */
+        for (int it = 0; it < (int)LBAD_ROWS_PER_FRAME / FUSED_WARPS; ++it) {
+            const int row = it * FUSED_WARPS + wid;
+            const float* win = samples + (size_t)row * hop;
+            float re[32], im[32];
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) {                                   /* vDSP_ctoz (m:353): z[n] = x[2n] + i x[2n+1] */
+                const float2 t = *reinterpret_cast<const float2*>(win + 2 * (32 * n1 + lane));
+                re[n1] = t.x; im[n1] = t.y;
+            }
+            fft32(re, im);                                                      /* over n1; position p holds k1 = bitrev5(p) */
+#pragma unroll
+            for (int p = 0; p < 32; p++) {
+                const int k1 = bitrev5(p);
+                const float2 w = tw1[k1 * 32 + lane];                           /* exp(-2 pi i lane k1 / 1024) */
+                scr[k1 * SCR_LD + lane] = make_float2(re[p] * w.x - im[p] * w.y, re[p] * w.y + im[p] * w.x);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 16; q++) {                                      /* lane = k1 reads A[n2][k1], n2 = 2q, 2q+1 */
+                const float4 t = *reinterpret_cast<const float4*>(&scr[lane * SCR_LD + 2 * q]);
+                re[2 * q] = t.x; im[2 * q] = t.y; re[2 * q + 1] = t.z; im[2 * q + 1] = t.w;
+            }
+            fft32(re, im);                                                      /* over n2; position p holds Z[lane + 32 bitrev5(p)] */
+            __syncwarp();                                                       /* scratch is about to be reused as vbuf */
+            const int src_lane = (32 - lane) & 31;
+#pragma unroll
+            for (int k2 = 0; k2 < 32; k2++) {
+                if (k2 >= k2lo && k2 <= k2hi) {                                 /* warp-uniform */
+                    const int p = bitrev5(k2), pp = bitrev5(31 - k2), p0 = bitrev5((32 - k2) & 31);
+                    float pr = __shfl_sync(0xffffffffu, re[pp], src_lane);      /* Z[1024 - k] lives in lane 32-lane, k2' = 31-k2 */
+                    float pi = __shfl_sync(0xffffffffu, im[pp], src_lane);
+                    if (lane == 0) { pr = re[p0]; pi = im[p0]; }                /* ... except lane 0: own register k2' = 32-k2 */
+                    const float2 w = tw2[k2 * 32 + lane];                       /* (cos, sin) of 2 pi k / 2048 */
+                    float xr, xi;
+                    real_split_2x(re[p], im[p], pr, pi, w.x, w.y, xr, xi);
+                    if (k2 == 0 && lane == 0) { xr = 2.0f * (re[p] + im[p]); xi = 2.0f * (re[p] - im[p]); }   /* DC / packed Nyquist */
+                    vbuf[k2 * 32 + lane] = bin_energy(xr, xi, g.inv_pos_scale);
+                }
+            }
+            __syncwarp();
+            float pacc = 0.0f;                                                  /* lane = band; m:379-405 order */
+            for (uint32_t k = klow; k < khigh; k++) pacc = __fadd_rn(pacc, vbuf[k]);
+            img[row * FUSED_LD + lane] = __fdiv_rn(pacc, divisor);
+            __syncwarp();
+        }
+        __syncthreads();                                                        /* image complete; samples free */
+
+        const uint32_t fnext = f + gridDim.x;
+        if (use_tma && tid == 0 && fnext < total_frames) {                      /* next frame's load overlaps the tail */
+            mbar_arrive_expect_tx(bar, bytes); bulk_copy_g2s(samples, frame_src(fnext), bytes, bar);
+        }
+        if (images_out) {
+            float* o = images_out + (size_t)f * LBAD_ROWS_PER_FRAME * 32;
+            for (int i = tid; i < (int)LBAD_ROWS_PER_FRAME * 32; i += FUSED_THREADS) o[i] = img[(i >> 5) * FUSED_LD + (i & 31)];
+        }
+
+        /* ---- Haar rows (length 32), Frame.m:114-116 + 134-153; thread = row ---- */
+        {
+            float a[32], t[32];
+            const float s32 = sqrtf(32.0f), s2 = sqrtf(2.0f), s128 = sqrtf(128.0f);
+#pragma unroll
+            for (int c = 0; c < 32; c++) a[c] = __fdiv_rn(img[tid * FUSED_LD + c], s32);
+#pragma unroll
+            for (int n = 16; n >= 1; n >>= 1) {
+#pragma unroll
+                for (int i = 0; i < n; i++) {
+                    t[i] = __fdiv_rn(__fadd_rn(a[2 * i], a[2 * i + 1]), s2);
+                    t[n + i] = __fdiv_rn(__fsub_rn(a[2 * i], a[2 * i + 1]), s2);
+                }
+#pragma unroll
+                for (int i = 0; i < 2 * n; i++) a[i] = t[i];
+            }
+            /* the column pass starts by dividing every element by sqrtf(128) (Frame.m:137-139): fold it into the write-back */
+#pragma unroll
+            for (int c = 0; c < 32; c++) img[tid * FUSED_LD + c] = __fdiv_rn(a[c], s128);
+        }
+        __syncthreads();
+        /* ---- Haar columns (length 128), Frame.m:118-131; each level: read pairs, barrier, write ---- */
+        {
+            const float s2 = sqrtf(2.0f);
+            const int c = tid & 31, i0 = tid >> 5;
+#pragma unroll 1
+            for (int n = 64; n >= 1; n >>= 1) {
+                float x0[16], x1[16];
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const int i = i0 + 4 * q;
+                    if (i < n) { x0[q] = img[(2 * i) * FUSED_LD + c]; x1[q] = img[(2 * i + 1) * FUSED_LD + c]; }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const int i = i0 + 4 * q;
+                    if (i < n) {
+                        img[i * FUSED_LD + c] = __fdiv_rn(__fadd_rn(x0[q], x1[q]), s2);
+                        img[(n + i) * FUSED_LD + c] = __fdiv_rn(__fsub_rn(x0[q], x1[q]), s2);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (haar_out) {
+            float* o = haar_out + (size_t)f * LBAD_ROWS_PER_FRAME * 32;
+            for (int i = tid; i < (int)LBAD_ROWS_PER_FRAME * 32; i += FUSED_THREADS) o[i] = img[(i >> 5) * FUSED_LD + (i & 31)];
+        }
+        /* ---- ordered top-T -> packed words, Frame.m:165-191 ---- */
+        select_and_pack<FUSED_THREADS, 32>([&](int idx) { return img[(idx >> 5) * FUSED_LD + (idx & 31)]; }, (int)g.pairs,
+                                           (int)g.words_per_plane, words + (size_t)f * 2 * g.words_per_plane, sel);
+        __syncthreads();
+    }
+}
+
+}  // namespace lbad
+
+/* ================================================================================================== host ==== */
+
+using namespace lbad;
+
+struct lbadcu_plan {
+    lbadcu_geometry geo;
+    Geo g;
+    BandTable bt;
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_streams[3] = {nullptr, nullptr, nullptr};
+    float2 *d_tw_m = nullptr, *d_tw_n = nullptr, *d_tw1 = nullptr, *d_tw2 = nullptr;
+    float* d_scratch_images = nullptr; size_t scratch_frames = 0;
+    float* d_chunk_pcm[3] = {nullptr, nullptr, nullptr}; uint32_t* d_chunk_words[3] = {nullptr, nullptr, nullptr};
+    size_t chunk_pcm_floats = 0, chunk_words = 0;
+    bool fused_ok = false; int sm_count = 0; size_t smem_optin = 0;
+    uint64_t launches = 0;
+    LaunchTimer timer;
+    int stage_mode = -1;      /* -1 auto, 0 plain loads, 1 TMA (env LBAD_STAGE=ldg|tma) */
+};
+
+extern "C" const char* lbadcu_last_error(void) { return g_err; }
+
+extern "C" int lbadcu_device_available(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return LBAD_ERR_NODEVICE; }
+    return LBAD_OK;
+}
+
+static uint32_t ilog2(uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l; }
+
+extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out) {
+    *out = nullptr;
+    if (lbadcu_device_available() != LBAD_OK) { set_error("no CUDA device available (this library has no CPU fallback)"); return LBAD_ERR_NODEVICE; }
+    const uint32_t N = geo->window, B = geo->bands, M = N / 2;
+    if (N < LBAD_MIN_WINDOW || N > LBAD_MAX_WINDOW || (N & (N - 1)) || B < 4 || B > LBAD_MAX_BANDS || (B & (B - 1)) || geo->stride == 0 ||
+        geo->sublen < 2 || geo->sublen > LBAD_MAX_SUBLEN || (geo->sublen & 1) || geo->sublen / 2 > LBAD_ROWS_PER_FRAME * B) return LBAD_ERR_ARG;
+    uint32_t kmin = 0xffffffffu, kmax = 0;
+    for (uint32_t b = 0; b < B; b++) {
+        if (geo->klow[b] > geo->khigh[b] || geo->khigh[b] > M) return LBAD_ERR_ARG;      /* Q15: band table must stay inside the spectrum */
+        if (geo->klow[b] < geo->khigh[b]) { kmin = geo->klow[b] < kmin ? geo->klow[b] : kmin; kmax = geo->khigh[b] > kmax ? geo->khigh[b] : kmax; }
+    }
+    if (kmin >= kmax) { kmin = 0; kmax = 1; }
+    lbadcu_plan* p = new lbadcu_plan();
+    p->geo = *geo;
+    LBAD_CUDA_TRY(cudaGetDevice(&p->device));
+    cudaDeviceProp prop; LBAD_CUDA_TRY(cudaGetDeviceProperties(&prop, p->device));
+    p->sm_count = prop.multiProcessorCount; p->smem_optin = prop.sharedMemPerBlockOptin;
+    Geo& g = p->g;
+    g.window = N; g.log2m = ilog2(M); g.stride = geo->stride; g.bands = B; g.pairs = geo->sublen / 2;
+    g.words_per_plane = g.pairs <= 64 ? 2 : g.pairs <= 128 ? 4 : 8;
+    g.kmin = kmin; g.kmax = kmax; g.inv_pos_scale = 1.0f / geo->pos_scale; g.frames_per_clip = 0; g.clip_stride = 0;
+    for (uint32_t b = 0; b < LBAD_MAX_BANDS; b++) { p->bt.klow[b] = b < B ? geo->klow[b] : 0; p->bt.khigh[b] = b < B ? geo->khigh[b] : 0; p->bt.divisor[b] = b < B ? geo->divisor[b] : 1.0f; }
+    LBAD_CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; i++) LBAD_CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_streams[i], cudaStreamNonBlocking));
+    /* twiddle tables, evaluated in double and rounded once */
+    std::vector<float2> twm(M / 2), twn(M), tw1(1024), tw2(1024);
+    for (uint32_t j = 0; j < M / 2; j++) { const double a = 2.0 * M_PI * j / M; twm[j] = make_float2((float)cos(a), (float)-sin(a)); }
+    for (uint32_t k = 0; k < M; k++) { const double a = 2.0 * M_PI * k / N; twn[k] = make_float2((float)cos(a), (float)sin(a)); }
+    for (int k1 = 0; k1 < 32; k1++) for (int l = 0; l < 32; l++) { const double a = 2.0 * M_PI * (double)(l * k1) / 1024.0; tw1[k1 * 32 + l] = make_float2((float)cos(a), (float)-sin(a)); }
+    for (int k2 = 0; k2 < 32; k2++) for (int l = 0; l < 32; l++) { const double a = 2.0 * M_PI * (double)(l + 32 * k2) / 2048.0; tw2[k2 * 32 + l] = make_float2((float)cos(a), (float)sin(a)); }
+    LBAD_CUDA_TRY(cudaMalloc(&p->d_tw_m, sizeof(float2) * (M / 2))); LBAD_CUDA_TRY(cudaMalloc(&p->d_tw_n, sizeof(float2) * M));
+    LBAD_CUDA_TRY(cudaMalloc(&p->d_tw1, sizeof(float2) * 1024)); LBAD_CUDA_TRY(cudaMalloc(&p->d_tw2, sizeof(float2) * 1024));
+    LBAD_CUDA_TRY(cudaMemcpy(p->d_tw_m, twm.data(), sizeof(float2) * (M / 2), cudaMemcpyHostToDevice));
+    LBAD_CUDA_TRY(cudaMemcpy(p->d_tw_n, twn.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
+    LBAD_CUDA_TRY(cudaMemcpy(p->d_tw1, tw1.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
+    LBAD_CUDA_TRY(cudaMemcpy(p->d_tw2, tw2.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
+    /* fused path: window 2048, 32 bands, even hop, frame span fits in shared memory */
+    const uint64_t span = 127ull * geo->stride + N;
+    p->fused_ok = (N == 2048 && B == 32 && (geo->stride % 2 == 0) && span * 4 < (1u << 20) && fused_layout((uint32_t)span).total_bytes <= p->smem_optin);
+    const char* st = getenv("LBAD_STAGE");
+    p->stage_mode = st ? (strcmp(st, "tma") == 0 ? 1 : strcmp(st, "ldg") == 0 ? 0 : -1) : -1;
+    *out = p;
+    return LBAD_OK;
+}
+
+extern "C" void lbadcu_plan_destroy(lbadcu_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    p->timer.clear();
+    cudaFree(p->d_tw_m); cudaFree(p->d_tw_n); cudaFree(p->d_tw1); cudaFree(p->d_tw2); cudaFree(p->d_scratch_images);
+    for (int i = 0; i < 3; i++) { cudaFree(p->d_chunk_pcm[i]); cudaFree(p->d_chunk_words[i]); if (p->copy_streams[i]) cudaStreamDestroy(p->copy_streams[i]); }
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+extern "C" int lbadcu_plan_fused_supported(const lbadcu_plan* p) { return p->fused_ok ? 1 : 0; }
+extern "C" void* lbadcu_plan_stream(lbadcu_plan* p) { return p->stream; }
+extern "C" uint64_t lbadcu_plan_launches(const lbadcu_plan* p) { return p->launches; }
+extern "C" uint32_t lbadcu_plan_timing(lbadcu_plan* p, int enable, int reset, double* total_ms) {
+    uint32_t n = p->timer.collect(total_ms, reset != 0);
+    p->timer.enabled = enable != 0;
+    return n;
+}
+
+template <int B>
+static int launch_haar_select(lbadcu_plan* p, const float* d_images, float* d_haar, uint32_t* d_words, uint32_t frames, cudaStream_t s) {
+    const uint32_t grid = frames < (uint32_t)p->sm_count * 4 ? frames : (uint32_t)p->sm_count * 4;
+    const size_t smem = 2 * (size_t)LBAD_ROWS_PER_FRAME * (B + 1) * sizeof(float);
+    LBAD_CUDA_TRY(cudaFuncSetAttribute(haar_select_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    haar_select_kernel<B><<<grid, HS_THREADS, smem, s>>>(d_images, d_haar, d_words, (int)p->g.pairs, (int)p->g.words_per_plane, frames);
+    p->launches++;
+    LBAD_CUDA_TRY(cudaGetLastError());
+    return LBAD_OK;
+}
+
+static int haar_select_dispatch(lbadcu_plan* p, const float* d_images, float* d_haar, uint32_t* d_words, uint32_t frames, cudaStream_t s) {
+    switch (p->g.bands) {
+        case 4:  return launch_haar_select<4>(p, d_images, d_haar, d_words, frames, s);
+        case 8:  return launch_haar_select<8>(p, d_images, d_haar, d_words, frames, s);
+        case 16: return launch_haar_select<16>(p, d_images, d_haar, d_words, frames, s);
+        case 32: return launch_haar_select<32>(p, d_images, d_haar, d_words, frames, s);
+        case 64: return launch_haar_select<64>(p, d_images, d_haar, d_words, frames, s);
+    }
+    return LBAD_ERR_ARG;
+}
+
+extern "C" int lbadcu_extract_device(lbadcu_plan* p, const float* d_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
+                                     uint32_t* d_words, float* d_images, float* d_haar, int mode, void* stream) {
+    if (!p || !d_pcm || !d_words) return LBAD_ERR_ARG;
+    if (clip_len < p->g.window) return LBAD_ERR_ARG;
+    LBAD_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : p->stream;
+    const uint64_t frames_per_clip = ((clip_len - p->g.window) / p->g.stride) / LBAD_ROWS_PER_FRAME;   /* m:250-255 */
+    const uint64_t total_frames64 = frames_per_clip * n_clips;
+    if (total_frames64 == 0) return LBAD_OK;
+    if (total_frames64 > 0x7fffffffull) return LBAD_ERR_ARG;
+    const uint32_t total_frames = (uint32_t)total_frames64;
+    Geo g = p->g; g.frames_per_clip = (uint32_t)frames_per_clip; g.clip_stride = clip_stride;
+    const bool fused = mode == 1 ? true : mode == 2 ? false : p->fused_ok;
+    if (fused && !p->fused_ok) return LBAD_ERR_ARG;
+    if (fused) {
+        const uint32_t span = 127u * g.stride + g.window;
+        const FusedSmemLayout L = fused_layout(span);
+        /* TMA bulk copies need 16-byte aligned sources and sizes */
+        bool tma_ok = ((uintptr_t)d_pcm % 16 == 0) && (clip_stride % 4 == 0) && (g.stride % 4 == 0);
+        if (p->stage_mode == 0) tma_ok = false;
+        LBAD_CUDA_TRY(cudaFuncSetAttribute(extract_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes));
+        int per_sm = 0;
+        LBAD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extract_fused_kernel, FUSED_THREADS, L.total_bytes));
+        if (per_sm < 1) per_sm = 1;
+        const uint32_t cap = (uint32_t)(p->sm_count * per_sm);
+        const uint32_t grid = total_frames < cap ? total_frames : cap;
+        p->timer.begin(s);
+        extract_fused_kernel<<<grid, FUSED_THREADS, L.total_bytes, s>>>(d_pcm, d_words, d_images, d_haar, p->d_tw1, p->d_tw2, g, p->bt, L, span,
+                                                                        total_frames, tma_ok ? 1 : 0);
+        p->timer.end(s);
+        p->launches++;
+        LBAD_CUDA_TRY(cudaGetLastError());
+        return LBAD_OK;
+    }
+    /* generic: bands -> (scratch) images -> Haar/select, in slabs of frames when no dump buffer was given */
+    const uint32_t M = g.window / 2;
+    const size_t smem = (size_t)GEN_WARPS * M * (sizeof(float2) + sizeof(float));
+    LBAD_CUDA_TRY(cudaFuncSetAttribute(bands_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t clips_per_slab = n_clips;
+    if (!d_images) {
+        const uint64_t want_clips = 8192 / frames_per_clip ? 8192 / frames_per_clip : 1;      /* ~8192 frames (128 MB at B=32) per slab */
+        clips_per_slab = (uint32_t)(want_clips < n_clips ? want_clips : n_clips);
+        const size_t need = (size_t)clips_per_slab * frames_per_clip;
+        if (p->scratch_frames < need) {
+            LBAD_CUDA_TRY(cudaStreamSynchronize(s));
+            cudaFree(p->d_scratch_images); p->d_scratch_images = nullptr; p->scratch_frames = 0;
+            LBAD_CUDA_TRY(cudaMalloc(&p->d_scratch_images, need * LBAD_ROWS_PER_FRAME * LBAD_MAX_BANDS * sizeof(float)));
+            p->scratch_frames = need;
+        }
+    }
+    for (uint32_t c0 = 0; c0 < n_clips; c0 += clips_per_slab) {
+        const uint32_t nc = (n_clips - c0) < clips_per_slab ? (n_clips - c0) : clips_per_slab;
+        const uint32_t nf = (uint32_t)(nc * frames_per_clip);
+        const uint64_t nw = (uint64_t)nf * LBAD_ROWS_PER_FRAME;
+        float* imgs = d_images ? d_images + (size_t)c0 * frames_per_clip * LBAD_ROWS_PER_FRAME * g.bands : p->d_scratch_images;
+        const uint64_t want = (nw + GEN_WARPS - 1) / GEN_WARPS;
+        const uint32_t grid = (uint32_t)(want < (uint64_t)p->sm_count * 16 ? want : (uint64_t)p->sm_count * 16);
+        p->timer.begin(s);
+        bands_generic_kernel<<<grid, GEN_WARPS * 32, smem, s>>>(d_pcm + (uint64_t)c0 * clip_stride, imgs, p->d_tw_m, p->d_tw_n, g, p->bt, nw);
+        p->timer.end(s);
+        p->launches++;
+        LBAD_CUDA_TRY(cudaGetLastError());
+        float* haar = d_haar ? d_haar + (size_t)c0 * frames_per_clip * LBAD_ROWS_PER_FRAME * g.bands : nullptr;
+        int e = haar_select_dispatch(p, imgs, haar, d_words + (size_t)c0 * frames_per_clip * 2 * g.words_per_plane, nf, s);
+        if (e != LBAD_OK) return e;
+    }
+    return LBAD_OK;
+}
+
+extern "C" int lbadcu_transform_images_host(lbadcu_plan* p, const float* h_images, uint32_t count, float* h_haar, uint32_t* h_words) {
+    if (!p || !h_images || count == 0) return LBAD_ERR_ARG;
+    LBAD_CUDA_TRY(cudaSetDevice(p->device));
+    const size_t n = (size_t)count * LBAD_ROWS_PER_FRAME * p->g.bands, nw = (size_t)count * 2 * p->g.words_per_plane;
+    float *d_img = nullptr, *d_haar = nullptr; uint32_t* d_words = nullptr;
+    LBAD_CUDA_TRY(cudaMalloc(&d_img, n * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&d_haar, n * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&d_words, nw * sizeof(uint32_t)));
+    LBAD_CUDA_TRY(cudaMemcpyAsync(d_img, h_images, n * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    int e = haar_select_dispatch(p, d_img, d_haar, d_words, count, p->stream);
+    if (e == LBAD_OK) {
+        if (h_haar) LBAD_CUDA_TRY(cudaMemcpyAsync(h_haar, d_haar, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+        if (h_words) LBAD_CUDA_TRY(cudaMemcpyAsync(h_words, d_words, nw * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
+        LBAD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    }
+    cudaFree(d_img); cudaFree(d_haar); cudaFree(d_words);
+    return e;
+}
+
+/* Host-memory front end.  Clips are processed in chunks on three streams so that the H2D copy of chunk i+1, the
+ * kernels of chunk i and the D2H of chunk i-1 overlap (they do when the caller's buffers are pinned). */
+extern "C" int lbadcu_extract_host(lbadcu_plan* p, const float* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
+                                   uint32_t* h_words, float* h_images, float* h_haar, int mode) {
+    if (!p || !h_pcm || !h_words || n_clips == 0) return LBAD_ERR_ARG;
+    if (clip_len < p->g.window) return LBAD_ERR_ARG;
+    LBAD_CUDA_TRY(cudaSetDevice(p->device));
+    const uint64_t frames_per_clip = ((clip_len - p->g.window) / p->g.stride) / LBAD_ROWS_PER_FRAME;
+    if (frames_per_clip == 0) return LBAD_OK;
+    const size_t words_per_clip = (size_t)frames_per_clip * 2 * p->g.words_per_plane;
+    const size_t img_per_clip = (size_t)frames_per_clip * LBAD_ROWS_PER_FRAME * p->g.bands;
+    const uint64_t clip_pad = (clip_len + 3) & ~3ull;                  /* device clip stride: keeps every clip 16-byte aligned */
+    uint64_t clips_per_chunk = (48ull << 20) / clip_pad;                /* ~192 MB of PCM per chunk */
+    if (clips_per_chunk < 1) clips_per_chunk = 1;
+    if (clips_per_chunk > n_clips) clips_per_chunk = n_clips;
+    const size_t need_pcm = (size_t)clips_per_chunk * clip_pad, need_words = (size_t)clips_per_chunk * words_per_clip;
+    const int nbuf = n_clips > clips_per_chunk ? 3 : 1;
+    if (p->chunk_pcm_floats < need_pcm || p->chunk_words < need_words) {
+        for (int i = 0; i < 3; i++) { cudaFree(p->d_chunk_pcm[i]); cudaFree(p->d_chunk_words[i]); p->d_chunk_pcm[i] = nullptr; p->d_chunk_words[i] = nullptr; }
+        p->chunk_pcm_floats = p->chunk_words = 0;
+    }
+    for (int i = 0; i < nbuf; i++) {
+        if (!p->d_chunk_pcm[i]) LBAD_CUDA_TRY(cudaMalloc(&p->d_chunk_pcm[i], need_pcm * sizeof(float)));
+        if (!p->d_chunk_words[i]) LBAD_CUDA_TRY(cudaMalloc(&p->d_chunk_words[i], need_words * sizeof(uint32_t)));
+    }
+    p->chunk_pcm_floats = need_pcm; p->chunk_words = need_words;
+    float *d_img = nullptr, *d_haar = nullptr;
+    if (h_images) LBAD_CUDA_TRY(cudaMalloc(&d_img, (size_t)clips_per_chunk * img_per_clip * sizeof(float)));
+    if (h_haar) LBAD_CUDA_TRY(cudaMalloc(&d_haar, (size_t)clips_per_chunk * img_per_clip * sizeof(float)));
+    int rc = LBAD_OK;
+    uint32_t chunk = 0;
+    for (uint64_t c0 = 0; c0 < n_clips && rc == LBAD_OK; c0 += clips_per_chunk, chunk++) {
+        const uint32_t nc = (uint32_t)((n_clips - c0) < clips_per_chunk ? (n_clips - c0) : clips_per_chunk);
+        const int b = (int)(chunk % (uint32_t)nbuf);
+        cudaStream_t s = nbuf == 1 ? p->stream : p->copy_streams[b];
+        if (clip_stride == clip_pad) LBAD_CUDA_TRY(cudaMemcpyAsync(p->d_chunk_pcm[b], h_pcm + c0 * clip_stride, (size_t)nc * clip_pad * sizeof(float), cudaMemcpyHostToDevice, s));
+        else LBAD_CUDA_TRY(cudaMemcpy2DAsync(p->d_chunk_pcm[b], clip_pad * sizeof(float), h_pcm + c0 * clip_stride, clip_stride * sizeof(float),
+                                             clip_len * sizeof(float), nc, cudaMemcpyHostToDevice, s));
+        rc = lbadcu_extract_device(p, p->d_chunk_pcm[b], nc, clip_len, clip_pad, p->d_chunk_words[b], d_img, d_haar, mode, s);
+        if (rc != LBAD_OK) break;
+        LBAD_CUDA_TRY(cudaMemcpyAsync(h_words + c0 * words_per_clip, p->d_chunk_words[b], (size_t)nc * words_per_clip * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (h_images) LBAD_CUDA_TRY(cudaMemcpyAsync(h_images + c0 * img_per_clip, d_img, (size_t)nc * img_per_clip * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (h_haar) LBAD_CUDA_TRY(cudaMemcpyAsync(h_haar + c0 * img_per_clip, d_haar, (size_t)nc * img_per_clip * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (h_images || h_haar) LBAD_CUDA_TRY(cudaStreamSynchronize(s));      /* the dump buffers are shared between chunks */
+    }
+    for (int i = 0; i < 3; i++) LBAD_CUDA_TRY(cudaStreamSynchronize(p->copy_streams[i]));
+    LBAD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    cudaFree(d_img); cudaFree(d_haar);
+    return rc;
+}

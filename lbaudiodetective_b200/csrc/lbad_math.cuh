@@ -1,0 +1,108 @@
+/*
+ * lbad_math.cuh — per-lane arithmetic of the fingerprint kernels, written as __host__ __device__ inline code so
+ * that the exact same functions run inside the CUDA kernels (lbad_extract.cu, lbad_search.cu) and inside the
+ * host-side lane emulator used by the CPU unit tests (tests/test_lane_emulation.py -> csrc/lane_emulator.cpp).
+ *
+ * Layout of the 2048-point real FFT used by the fused kernel (one warp per window):
+ *   z[n] = x[2n] + i x[2n+1], n < 1024 = 32 x 32.   n = 32 n1 + n2,  k = k1 + 32 k2.
+ *   pass 1: lane n2 holds z[32 n1 + n2] (n1 = register index) and does a 32-point DFT over n1 -> A[n2][k1]
+ *   twiddle: A[n2][k1] *= exp(-2 pi i n2 k1 / 1024)
+ *   transpose through shared memory so that lane k1 holds A[n2][k1] for all n2
+ *   pass 2: 32-point DFT over n2 -> Z[k1 + 32 k2] in lane k1
+ *   split : 2 X[k] = (Z[k] + conj Z[1024-k]) - i exp(-2 pi i k / 2048) (Z[k] - conj Z[1024-k])
+ * which is vDSP_fft_zrip's output convention (x2, e^{-i theta}) as the reference consumes it (LBAudioDetective.m:353-355).
+ * The in-register 32-point DFT is a fully unrolled radix-2 DIF; register position p ends up holding output
+ * index bitrev5(p), and callers account for that permutation at compile time.
+ */
+#ifndef LBAD_MATH_CUH
+#define LBAD_MATH_CUH
+#include <stdint.h>
+#include <utility>
+
+#if defined(__CUDACC__)
+#define LBAD_HD __host__ __device__ __forceinline__
+#else
+#define LBAD_HD inline
+#endif
+
+namespace lbad {
+
+LBAD_HD constexpr int bitrev5(int p) {
+    return ((p & 1) << 4) | ((p & 2) << 2) | (p & 4) | ((p & 8) >> 2) | ((p & 16) >> 4);
+}
+
+/* cos / sin of 2*pi*m/32 for m in [0, 16) */
+LBAD_HD constexpr float cos32(int m) {
+    return m == 0 ? 1.0f : m == 1 ? 0.98078528040323043f : m == 2 ? 0.92387953251128674f : m == 3 ? 0.83146961230254524f
+         : m == 4 ? 0.70710678118654752f : m == 5 ? 0.55557023301960218f : m == 6 ? 0.38268343236508977f : m == 7 ? 0.19509032201612825f
+         : m == 8 ? 0.0f : -cos32(16 - m);
+}
+LBAD_HD constexpr float sin32(int m) { return m <= 8 ? cos32(8 - m) : cos32(m - 8); }
+
+/* one radix-2 DIF butterfly of a 32-point transform: half-span H, block start S, offset J within the half-block */
+template <int H, int S, int J>
+LBAD_HD void fft32_butterfly(float (&re)[32], float (&im)[32]) {
+    constexpr int a = S + J, b = S + J + H;
+    constexpr int m = J * (16 / H);              /* twiddle exp(-2 pi i m / 32), 0 <= m < 16 */
+    constexpr float kS2 = 0.70710678118654752f;
+    const float ar = re[a], ai = im[a], br = re[b], bi = im[b];
+    re[a] = ar + br; im[a] = ai + bi;
+    const float dr = ar - br, di = ai - bi;
+    if constexpr (m == 0)       { re[b] = dr; im[b] = di; }
+    else if constexpr (m == 8)  { re[b] = di; im[b] = -dr; }                               /* x (-i) */
+    else if constexpr (m == 4)  { re[b] = (dr + di) * kS2; im[b] = (di - dr) * kS2; }      /* x (1-i)/sqrt2 */
+    else if constexpr (m == 12) { re[b] = (di - dr) * kS2; im[b] = (dr + di) * (-kS2); }   /* x (-1-i)/sqrt2 */
+    else {
+        constexpr float c = cos32(m), s = sin32(m);                                        /* x (c - i s) */
+        re[b] = dr * c + di * s;
+        im[b] = di * c - dr * s;
+    }
+}
+
+template <int H, int... I>
+LBAD_HD void fft32_stage(float (&re)[32], float (&im)[32], std::integer_sequence<int, I...>) {
+    (fft32_butterfly<H, (I / H) * 2 * H, I % H>(re, im), ...);
+}
+
+/* in-place forward 32-point DFT (e^{-i theta}); output index of register position p is bitrev5(p) */
+LBAD_HD void fft32(float (&re)[32], float (&im)[32]) {
+    using seq = std::make_integer_sequence<int, 16>;
+    fft32_stage<16>(re, im, seq{});
+    fft32_stage<8>(re, im, seq{});
+    fft32_stage<4>(re, im, seq{});
+    fft32_stage<2>(re, im, seq{});
+    fft32_stage<1>(re, im, seq{});
+}
+
+/* 2 X[k] from Z[k] = (zr, zi) and Z[M-k] = (pr, pi), with w = exp(-2 pi i k / N) = (c, -s) given as c, s */
+LBAD_HD void real_split_2x(float zr, float zi, float pr, float pi, float c, float s, float& xr, float& xi) {
+    const float er = zr + pr, ei = zi - pi;      /* Z + conj Z' */
+    const float dr = zr - pr, di = zi + pi;      /* Z - conj Z' */
+    xr = er + (c * di - s * dr);                 /* -i w d = (-s dr + c di) + i (-c dr - s di) */
+    xi = ei - (c * dr + s * di);
+}
+
+/* LBAudioDetective.m:387-401 for one bin: positive parts only are divided by pos_scale (a power of two, so the
+ * multiply by its reciprocal is exact), then re^2 + im^2 evaluated unfused in f32 as the reference does.
+ * Returns 0 for a non-finite value (the reference skips it). */
+LBAD_HD float bin_energy(float re, float im, float inv_pos_scale) {
+    re = re > 0.0f ? re * inv_pos_scale : re;
+    im = im > 0.0f ? im * inv_pos_scale : im;
+#if defined(__CUDA_ARCH__)
+    const float v = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+    return (v - v == 0.0f) ? v : 0.0f;           /* finite <=> v - v == 0 */
+#else
+    volatile float a = re * re, b = im * im;     /* keep the host build from contracting */
+    const float v = a + b;
+    return (v - v == 0.0f) ? v : 0.0f;
+#endif
+}
+
+/* Hit mask of one 32-pair word (LBAudioDetectiveFingerprint.m:155-169):
+ * pairs where fp1 has a bit set (P1|M1) and both bits agree with fp2. */
+LBAD_HD uint32_t hit_word(uint32_t p1, uint32_t m1, uint32_t p2, uint32_t m2) {
+    return (p1 | m1) & ~(p1 ^ p2) & ~(m1 ^ m2);
+}
+
+}  // namespace lbad
+#endif

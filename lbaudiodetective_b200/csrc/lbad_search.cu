@@ -1,0 +1,458 @@
+/*
+ * lbad_search.cu — fingerprint database search kernels for sm_100a.
+ *
+ * Replaces, on the GPU, the reference's matcher (file:line into /root/reference/LBAudioDetective/LBAudioDetectiveFingerprint.m):
+ *   CompareSubfingerprints   FP.m:151-176   masked 2-bit-pair agreement ratio hits/possible
+ *   CompareToFingerprint     FP.m:119-149   swap so fp1 is the longer, time-offset search, f32 mean, running max
+ * evaluated for every (query, database clip) pair as  score = CompareToFingerprint(clip, query, range)  — the
+ * argument order of LBAudioDetectiveTests.m:68 — followed by a per-query top-k ordered (score desc, clip index asc).
+ *
+ * Bit-exactness: hits and possible are integer popcounts (identity in SURVEY.md §2.3); hits/possible is produced
+ * by multiply + two FMAs against a correctly rounded reciprocal (Markstein), verified exhaustively to equal the
+ * IEEE quotient for all 0 <= hits <= possible <= 256 (tests/test_host_logic.py); the per-offset sum adds the
+ * ratios in increasing subfingerprint order in f32; the mean uses an IEEE divide; the running max reproduces
+ * Apple's MAX macro (NaN from an empty fingerprint leaves the match at 0).
+ *
+ * Mapping: one warp = 32 queries (one per lane, query words in registers) x a contiguous chunk of clips; the
+ * database words are warp-uniform broadcast loads, so the ~600 MB database streams through L2 once per 32 queries.
+ * The kernel is integer-pipe bound (LOP3 + POPC), not HBM bound.
+ */
+#include "lbad_common.cuh"
+#include "lbad_math.cuh"
+#include <vector>
+#include <algorithm>
+
+namespace lbad {
+
+constexpr int SEARCH_WARPS = 4;
+constexpr uint32_t EMPTY_IDX = 0xffffffffu;
+
+__constant__ float c_rcp[257];            /* c_rcp[p] = RN(1/p), c_rcp[0] = 0 */
+
+template <int W> struct PairMask { uint32_t w[W]; };
+template <int W> __host__ __device__ inline PairMask<W> make_mask(uint32_t pairs) {
+    PairMask<W> m;
+    for (int i = 0; i < W; i++) m.w[i] = pairs >= 32u * (i + 1) ? 0xffffffffu : (pairs > 32u * i ? ((1u << (pairs - 32u * i)) - 1u) : 0u);
+    return m;
+}
+
+/* per-lane top-k kept in shared memory, lane-strided: slot r of lane l at [r*32 + l] */
+struct TopK {
+    float* sc; uint32_t* id; int k, lane;
+    __device__ __forceinline__ void init() { for (int r = 0; r < k; r++) { sc[r * 32 + lane] = -1.0f; id[r * 32 + lane] = EMPTY_IDX; } }
+    __device__ __forceinline__ float worst() const { return sc[(k - 1) * 32 + lane]; }
+    /* clips arrive in ascending index order, so a tie never displaces an earlier clip */
+    __device__ __forceinline__ void insert(float s, uint32_t c) {
+        int pos = k - 1;
+        while (pos > 0 && sc[(pos - 1) * 32 + lane] < s) { sc[pos * 32 + lane] = sc[(pos - 1) * 32 + lane]; id[pos * 32 + lane] = id[(pos - 1) * 32 + lane]; pos--; }
+        sc[pos * 32 + lane] = s; id[pos * 32 + lane] = c;
+    }
+};
+
+/* hits/possible as f32, exactly the IEEE quotient (FP.m:171-175); possible == 0 -> 0 because c_rcp[0] == 0 and hits == 0 */
+__device__ __forceinline__ float ratio_exact(uint32_t hits, float fposs, float rcp) {
+    const float fh = (float)hits;
+    const float q0 = __fmul_rn(fh, rcp);
+    const float rem = fmaf(-q0, fposs, fh);
+    return fmaf(rem, rcp, q0);
+}
+
+/* Fast path: every clip in the database has at least CQ subfingerprints, so the clip is always fp1 (FP.m:123-131:
+ * no swap when counts are equal).  For each database subfingerprint j the CQ query subfingerprints i are compared
+ * and added to the running sum of offset o = j - i, held in a CQ-deep shift register; offset o completes at j = o+CQ-1. */
+template <int W, int CQ, bool MASKED>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32)
+search_fast_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ offsets, const uint32_t n_clips, const uint32_t clip_base,
+                   const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t pairs, const int k,
+                   const uint32_t n_qgroups, const uint32_t clips_per_chunk, float* __restrict__ part_sc, uint32_t* __restrict__ part_id,
+                   float* __restrict__ all_scores, const uint32_t total_warps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * SEARCH_WARPS + wid;
+    if (gw >= total_warps) return;
+    const uint32_t qg = gw % n_qgroups, chunk = gw / n_qgroups;
+    const uint32_t q = qg * 32 + lane;
+    const bool qvalid = q < n_q;
+    TopK top{reinterpret_cast<float*>(smem_raw) + (size_t)wid * 2 * k * 32, reinterpret_cast<uint32_t*>(smem_raw) + (size_t)wid * 2 * k * 32 + (size_t)k * 32, k, lane};
+    top.init();
+    const PairMask<W> mask = make_mask<W>(pairs);
+    uint32_t qp[CQ][W], qm[CQ][W];
+#pragma unroll
+    for (int i = 0; i < CQ; i++)
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            qp[i][w] = qvalid ? qwords[((size_t)q * CQ + i) * 2 * W + w] : 0u;
+            qm[i][w] = qvalid ? qwords[((size_t)q * CQ + i) * 2 * W + W + w] : 0u;
+        }
+    const uint32_t c_begin = chunk * clips_per_chunk;
+    const uint32_t c_end = min(n_clips, c_begin + clips_per_chunk);
+    for (uint32_t c = c_begin; c < c_end; c++) {
+        const uint32_t s0 = offsets[c], c1 = offsets[c + 1] - s0;            /* warp-uniform */
+        float acc[CQ];
+#pragma unroll
+        for (int i = 0; i < CQ; i++) acc[i] = 0.0f;
+        float best = 0.0f;                                                    /* FP.m:133 */
+        const uint32_t last_off = c1 - CQ;                                    /* offsets 0..c1-CQ, FP.m:136 */
+        for (uint32_t j = 0; j < c1; j++) {
+            uint32_t p1[W], m1[W];
+            const uint32_t* src = db + ((size_t)s0 + j) * 2 * W;
+            if (W % 4 == 0) {
+#pragma unroll
+                for (int w = 0; w < W; w += 4) {
+                    const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + w)), b = __ldg(reinterpret_cast<const uint4*>(src + W + w));
+                    p1[w] = a.x; p1[w + 1] = a.y; p1[w + 2] = a.z; p1[w + 3] = a.w; m1[w] = b.x; m1[w + 1] = b.y; m1[w + 2] = b.z; m1[w + 3] = b.w;
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < W; w += 2) {
+                    const uint2 a = __ldg(reinterpret_cast<const uint2*>(src + w)), b = __ldg(reinterpret_cast<const uint2*>(src + W + w));
+                    p1[w] = a.x; p1[w + 1] = a.y; m1[w] = b.x; m1[w + 1] = b.y;
+                }
+            }
+            uint32_t possible = 0;
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                if (MASKED) { p1[w] &= mask.w[w]; m1[w] &= mask.w[w]; }
+                possible += __popc(p1[w] | m1[w]);                            /* FP.m:159-160, warp-uniform */
+            }
+            const float fposs = (float)possible, rcp = c_rcp[possible];
+#pragma unroll
+            for (int i = 0; i < CQ; i++) {
+                /* term i of offset o = j - i; skip offsets outside [0, c1-CQ] (warp-uniform test) */
+                if (j >= (uint32_t)i && j - i <= last_off) {
+                    uint32_t hits = 0;
+#pragma unroll
+                    for (int w = 0; w < W; w++) hits += __popc(hit_word(p1[w], m1[w], qp[i][w], qm[i][w]));   /* FP.m:162-167 */
+                    acc[i] = __fadd_rn(acc[i], ratio_exact(hits, fposs, rcp));  /* FP.m:139-142, increasing i per offset */
+                }
+            }
+            if (j >= (uint32_t)(CQ - 1)) {                                     /* offset j-CQ+1 is complete */
+                const float mean = __fdiv_rn(acc[CQ - 1], (float)CQ);          /* FP.m:144 */
+                best = (best < mean) ? mean : best;                            /* Apple MAX */
+            }
+#pragma unroll
+            for (int i = CQ - 1; i > 0; i--) acc[i] = acc[i - 1];
+            acc[0] = 0.0f;
+        }
+        if (qvalid) {
+            if (all_scores) all_scores[(size_t)q * n_clips + c] = best;
+            if (best > top.worst()) top.insert(best, clip_base + c);
+        }
+    }
+    if (qvalid) for (int r = 0; r < k; r++) {
+        part_sc[((size_t)chunk * n_q + q) * k + r] = top.sc[r * 32 + lane];
+        part_id[((size_t)chunk * n_q + q) * k + r] = top.id[r * 32 + lane];
+    }
+}
+
+/* Generic path: any query length (uniform over the launch, words staged in shared memory), any clip length,
+ * including clips SHORTER than the query, where the reference swaps and the query becomes fp1 (FP.m:123-131). */
+template <int W>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32)
+search_generic_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ offsets, const uint32_t n_clips, const uint32_t clip_base,
+                      const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t cq, const uint32_t pairs, const int k,
+                      const uint32_t n_qgroups, const uint32_t clips_per_chunk, float* __restrict__ part_sc, uint32_t* __restrict__ part_id,
+                      float* __restrict__ all_scores, const uint32_t total_warps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * SEARCH_WARPS + wid;
+    if (gw >= total_warps) return;
+    const uint32_t qg = gw % n_qgroups, chunk = gw / n_qgroups;
+    const uint32_t q = qg * 32 + lane;
+    const bool qvalid = q < n_q;
+    const size_t per_warp = (size_t)2 * k * 32 + (size_t)cq * 2 * W * 32;      /* 4-byte words */
+    uint32_t* base = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)wid * per_warp;
+    TopK top{reinterpret_cast<float*>(base), base + (size_t)k * 32, k, lane};
+    top.init();
+    uint32_t* qs = base + (size_t)2 * k * 32;                                  /* [cq][2W][32] */
+    const PairMask<W> mask = make_mask<W>(pairs);
+    for (uint32_t i = 0; i < cq; i++)
+        for (int w = 0; w < 2 * W; w++) qs[(i * 2 * W + w) * 32 + lane] = qvalid ? (qwords[((size_t)q * cq + i) * 2 * W + w] & mask.w[w % W]) : 0u;
+    __syncwarp();
+    const uint32_t c_begin = chunk * clips_per_chunk;
+    const uint32_t c_end = min(n_clips, c_begin + clips_per_chunk);
+    for (uint32_t c = c_begin; c < c_end; c++) {
+        const uint32_t s0 = offsets[c], cd = offsets[c + 1] - s0;
+        const bool db_first = cd >= cq;                                        /* FP.m:123: swap only if count1 < count2 */
+        const uint32_t c1 = db_first ? cd : cq, c2 = db_first ? cq : cd;
+        float best = 0.0f;
+        for (uint32_t o = 0; o + c2 <= c1; o++) {                              /* FP.m:136 */
+            float sum = 0.0f;
+            for (uint32_t i = 0; i < c2; i++) {                                /* FP.m:139-142 */
+                const uint32_t jd = db_first ? o + i : i, jq = db_first ? i : o + i;
+                const uint32_t* src = db + ((size_t)s0 + jd) * 2 * W;
+                uint32_t hits = 0, possible = 0;
+#pragma unroll
+                for (int w = 0; w < W; w++) {
+                    const uint32_t dp = __ldg(src + w) & mask.w[w], dm = __ldg(src + W + w) & mask.w[w];
+                    const uint32_t xp = qs[(jq * 2 * W + w) * 32 + lane], xm = qs[(jq * 2 * W + W + w) * 32 + lane];
+                    if (db_first) { possible += __popc(dp | dm); hits += __popc(hit_word(dp, dm, xp, xm)); }
+                    else          { possible += __popc(xp | xm); hits += __popc(hit_word(xp, xm, dp, dm)); }
+                }
+                const float r = possible ? __fdiv_rn((float)hits, (float)possible) : 0.0f;   /* FP.m:171-175 */
+                sum = __fadd_rn(sum, r);
+            }
+            const float mean = __fdiv_rn(sum, (float)c2);                      /* FP.m:144; c2 == 0 -> NaN */
+            best = (best < mean) ? mean : best;                                /* Apple MAX keeps `best` on NaN */
+        }
+        if (qvalid) {
+            if (all_scores) all_scores[(size_t)q * n_clips + c] = best;
+            if (best > top.worst()) top.insert(best, clip_base + c);
+        }
+    }
+    if (qvalid) for (int r = 0; r < k; r++) {
+        part_sc[((size_t)chunk * n_q + q) * k + r] = top.sc[r * 32 + lane];
+        part_id[((size_t)chunk * n_q + q) * k + r] = top.id[r * 32 + lane];
+    }
+}
+
+/* (score desc, clip index asc) strict order; a is "better" than b */
+__device__ __forceinline__ bool better(float sa, uint32_t ia, float sb, uint32_t ib) { return sa > sb || (sa == sb && ia < ib); }
+
+/* One warp per query: k-way merge of n_lists partial top-k lists [list][q][k] by repeated selection. */
+__global__ void __launch_bounds__(128)
+merge_topk_kernel(const float* __restrict__ part_sc, const uint32_t* __restrict__ part_id, const uint32_t n_lists, const uint32_t n_q, const int k,
+                  float* __restrict__ out_sc, uint32_t* __restrict__ out_id) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (q >= n_q) return;
+    const uint32_t n_cand = n_lists * (uint32_t)k;
+    float last_s = INFINITY; uint32_t last_i = 0;                              /* everything is "after" (+inf, 0) */
+    bool first = true;
+    for (int r = 0; r < k; r++) {
+        float bs = -2.0f; uint32_t bi = EMPTY_IDX; bool have = false;
+        for (uint32_t t = lane; t < n_cand; t += 32) {
+            const uint32_t list = t / k, slot = t % k;
+            const float s = part_sc[((size_t)list * n_q + q) * k + slot]; const uint32_t i = part_id[((size_t)list * n_q + q) * k + slot];
+            if (i == EMPTY_IDX) continue;
+            if (!first && !better(last_s, last_i, s, i)) continue;             /* already emitted */
+            if (!have || better(s, i, bs, bi)) { bs = s; bi = i; have = true; }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, bs, d); const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, d);
+            const bool oh = __shfl_xor_sync(0xffffffffu, have ? 1 : 0, d) != 0;
+            if (oh && (!have || better(os, oi, bs, bi))) { bs = os; bi = oi; have = true; }
+        }
+        if (lane == 0) { out_sc[(size_t)q * k + r] = have ? bs : -1.0f; out_id[(size_t)q * k + r] = have ? bi : EMPTY_IDX; }
+        if (have) { last_s = bs; last_i = bi; first = false; } else { last_s = -INFINITY; last_i = EMPTY_IDX; first = false; }
+    }
+}
+
+}  // namespace lbad
+
+/* ================================================================================================== host ==== */
+
+using namespace lbad;
+
+struct lbadcu_db {
+    int device = 0; uint32_t W = 4;
+    cudaStream_t stream = nullptr;
+    uint32_t* d_words = nullptr; size_t cap_subfps = 0, n_subfps = 0;
+    std::vector<uint32_t> h_offsets{0};
+    uint32_t* d_offsets = nullptr; size_t d_offsets_cap = 0; bool offsets_dirty = true;
+    uint32_t min_count = 0xffffffffu, max_count = 0, base = 0;
+    float* d_part_sc = nullptr; uint32_t* d_part_id = nullptr; size_t part_cap = 0;
+    int sm_count = 0; size_t smem_optin = 0;
+    uint64_t launches = 0;
+    LaunchTimer timer;
+};
+
+static int upload_rcp() {
+    float h[257]; h[0] = 0.0f;
+    for (int p = 1; p <= 256; p++) h[p] = 1.0f / (float)p;
+    LBAD_CUDA_TRY(cudaMemcpyToSymbol(c_rcp, h, sizeof h));
+    return LBAD_OK;
+}
+
+extern "C" int lbadcu_db_create(uint32_t W, lbadcu_db** out) {
+    *out = nullptr;
+    if (W != 2 && W != 4 && W != 8) return LBAD_ERR_ARG;
+    if (lbadcu_device_available() != LBAD_OK) { set_error("no CUDA device available (this library has no CPU fallback)"); return LBAD_ERR_NODEVICE; }
+    lbadcu_db* db = new lbadcu_db(); db->W = W;
+    LBAD_CUDA_TRY(cudaGetDevice(&db->device));
+    cudaDeviceProp prop; LBAD_CUDA_TRY(cudaGetDeviceProperties(&prop, db->device));
+    db->sm_count = prop.multiProcessorCount; db->smem_optin = prop.sharedMemPerBlockOptin;
+    LBAD_CUDA_TRY(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+    int e = upload_rcp(); if (e != LBAD_OK) return e;       /* per device; cheap enough to repeat per database */
+    *out = db;
+    return LBAD_OK;
+}
+
+extern "C" void lbadcu_db_destroy(lbadcu_db* db) {
+    if (!db) return;
+    cudaSetDevice(db->device);
+    cudaStreamSynchronize(db->stream);
+    db->timer.clear();
+    cudaFree(db->d_words); cudaFree(db->d_offsets); cudaFree(db->d_part_sc); cudaFree(db->d_part_id);
+    cudaStreamDestroy(db->stream);
+    delete db;
+}
+
+extern "C" uint32_t lbadcu_db_clips(const lbadcu_db* db) { return (uint32_t)db->h_offsets.size() - 1; }
+extern "C" uint64_t lbadcu_db_subfps(const lbadcu_db* db) { return db->n_subfps; }
+extern "C" uint32_t lbadcu_db_min_count(const lbadcu_db* db) { return db->min_count; }
+extern "C" uint32_t lbadcu_db_max_count(const lbadcu_db* db) { return db->max_count; }
+extern "C" void lbadcu_db_set_base(lbadcu_db* db, uint32_t base) { db->base = base; }
+extern "C" void* lbadcu_db_stream(lbadcu_db* db) { return db->stream; }
+extern "C" uint64_t lbadcu_db_launches(const lbadcu_db* db) { return db->launches; }
+extern "C" uint32_t lbadcu_db_timing(lbadcu_db* db, int enable, int reset, double* total_ms) {
+    uint32_t n = db->timer.collect(total_ms, reset != 0);
+    db->timer.enabled = enable != 0;
+    return n;
+}
+
+extern "C" int lbadcu_db_append(lbadcu_db* db, const uint32_t* words, int on_device, uint32_t n_clips, const uint32_t* counts, uint32_t uniform) {
+    if (!db || (!words && n_clips)) return LBAD_ERR_ARG;
+    LBAD_CUDA_TRY(cudaSetDevice(db->device));
+    uint64_t add = 0;
+    for (uint32_t c = 0; c < n_clips; c++) add += counts ? counts[c] : uniform;
+    if (db->n_subfps + add > 0xfffffff0ull) return LBAD_ERR_ARG;
+    if (db->n_subfps + add > db->cap_subfps) {
+        size_t cap = std::max<size_t>(db->cap_subfps * 2, db->n_subfps + add);
+        uint32_t* nw = nullptr;
+        LBAD_CUDA_TRY(cudaMalloc(&nw, cap * 2 * db->W * sizeof(uint32_t)));
+        if (db->n_subfps) LBAD_CUDA_TRY(cudaMemcpyAsync(nw, db->d_words, db->n_subfps * 2 * db->W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, db->stream));
+        LBAD_CUDA_TRY(cudaStreamSynchronize(db->stream));
+        cudaFree(db->d_words); db->d_words = nw; db->cap_subfps = cap;
+    }
+    if (add) LBAD_CUDA_TRY(cudaMemcpyAsync(db->d_words + db->n_subfps * 2 * db->W, words, add * 2 * db->W * sizeof(uint32_t),
+                                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, db->stream));
+    LBAD_CUDA_TRY(cudaStreamSynchronize(db->stream));
+    db->h_offsets.reserve(db->h_offsets.size() + n_clips);
+    for (uint32_t c = 0; c < n_clips; c++) {
+        const uint32_t n = counts ? counts[c] : uniform;
+        db->h_offsets.push_back(db->h_offsets.back() + n);
+        db->min_count = std::min(db->min_count, n); db->max_count = std::max(db->max_count, n);
+    }
+    db->n_subfps += add; db->offsets_dirty = true;
+    return LBAD_OK;
+}
+
+extern "C" uint64_t lbadcu_db_compares_per_query(const lbadcu_db* db, uint32_t cq) {
+    uint64_t total = 0;
+    for (size_t c = 0; c + 1 < db->h_offsets.size(); c++) {
+        const uint64_t cd = db->h_offsets[c + 1] - db->h_offsets[c];
+        const uint64_t c1 = std::max<uint64_t>(cd, cq), c2 = std::min<uint64_t>(cd, cq);
+        total += (c1 - c2 + 1) * c2;                                            /* FP.m:136-142 */
+    }
+    return total;
+}
+
+template <int W, int CQ>
+static void launch_fast(lbadcu_db* db, bool masked, uint32_t blocks, size_t smem, cudaStream_t s, const uint32_t* d_q, uint32_t n_q, uint32_t pairs, int k,
+                        uint32_t n_qgroups, uint32_t cpc, float* d_all, uint32_t total_warps) {
+    const uint32_t n_clips = lbadcu_db_clips(db);
+    if (masked) {
+        cudaFuncSetAttribute(search_fast_kernel<W, CQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        search_fast_kernel<W, CQ, true><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
+                                                                                db->d_part_sc, db->d_part_id, d_all, total_warps);
+    } else {
+        cudaFuncSetAttribute(search_fast_kernel<W, CQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        search_fast_kernel<W, CQ, false><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
+                                                                                 db->d_part_sc, db->d_part_id, d_all, total_warps);
+    }
+}
+
+template <int W>
+static void launch_generic(lbadcu_db* db, uint32_t blocks, size_t smem, cudaStream_t s, const uint32_t* d_q, uint32_t n_q, uint32_t cq, uint32_t pairs, int k,
+                           uint32_t n_qgroups, uint32_t cpc, float* d_all, uint32_t total_warps) {
+    cudaFuncSetAttribute(search_generic_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    search_generic_kernel<W><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_offsets, lbadcu_db_clips(db), db->base, d_q, n_q, cq, pairs, k, n_qgroups, cpc,
+                                                                     db->d_part_sc, db->d_part_id, d_all, total_warps);
+}
+
+extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint32_t n_q, uint32_t cq, uint32_t pairs, uint32_t k,
+                                       float* d_scores, uint32_t* d_idx, float* d_all, void* stream) {
+    if (!db || !d_q || !d_scores || !d_idx || n_q == 0 || k == 0 || k > 64) return LBAD_ERR_ARG;
+    LBAD_CUDA_TRY(cudaSetDevice(db->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : db->stream;
+    const uint32_t W = db->W, n_clips = lbadcu_db_clips(db);
+    if (pairs > 32 * W) pairs = 32 * W;
+    if (db->offsets_dirty) {
+        if (db->d_offsets_cap < db->h_offsets.size()) {
+            cudaFree(db->d_offsets); db->d_offsets = nullptr;
+            LBAD_CUDA_TRY(cudaMalloc(&db->d_offsets, db->h_offsets.size() * sizeof(uint32_t)));
+            db->d_offsets_cap = db->h_offsets.size();
+        }
+        LBAD_CUDA_TRY(cudaMemcpyAsync(db->d_offsets, db->h_offsets.data(), db->h_offsets.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        LBAD_CUDA_TRY(cudaStreamSynchronize(s));
+        db->offsets_dirty = false;
+    }
+    const uint32_t n_qgroups = (n_q + 31) / 32;
+    uint32_t n_chunks = ((uint32_t)db->sm_count * 32 + n_qgroups - 1) / n_qgroups;       /* ~32 warps per SM */
+    if (n_chunks > n_clips) n_chunks = n_clips;
+    if (n_chunks < 1) n_chunks = 1;
+    const uint32_t cpc = n_clips ? (n_clips + n_chunks - 1) / n_chunks : 1;
+    n_chunks = n_clips ? (n_clips + cpc - 1) / cpc : 1;
+    const size_t need = (size_t)n_chunks * n_q * k;
+    if (db->part_cap < need) {
+        LBAD_CUDA_TRY(cudaStreamSynchronize(s));
+        cudaFree(db->d_part_sc); cudaFree(db->d_part_id); db->d_part_sc = nullptr; db->d_part_id = nullptr;
+        LBAD_CUDA_TRY(cudaMalloc(&db->d_part_sc, need * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&db->d_part_id, need * sizeof(uint32_t)));
+        db->part_cap = need;
+    }
+    const uint32_t total_warps = n_chunks * n_qgroups;
+    const uint32_t blocks = (total_warps + SEARCH_WARPS - 1) / SEARCH_WARPS;
+    const bool fast = n_clips > 0 && db->min_count >= cq && (cq == 1 || cq == 6);
+    const bool masked = pairs < 32 * W;       /* words beyond L are zero already; a mask is only needed for a shorter range */
+    const size_t smem_fast = (size_t)SEARCH_WARPS * 2 * k * 32 * 4;
+    const size_t smem_gen = (size_t)SEARCH_WARPS * ((size_t)2 * k * 32 + (size_t)cq * 2 * W * 32) * 4;
+    if (!fast && smem_gen > db->smem_optin) return LBAD_ERR_ARG;
+    db->timer.begin(s);
+#define LBAD_FAST(WW, CC) launch_fast<WW, CC>(db, masked, blocks, smem_fast, s, d_q, n_q, pairs, (int)k, n_qgroups, cpc, d_all, total_warps)
+#define LBAD_GEN(WW) launch_generic<WW>(db, blocks, smem_gen, s, d_q, n_q, cq, pairs, (int)k, n_qgroups, cpc, d_all, total_warps)
+    if (fast) {
+        if (W == 2) { if (cq == 1) LBAD_FAST(2, 1); else LBAD_FAST(2, 6); }
+        else if (W == 4) { if (cq == 1) LBAD_FAST(4, 1); else LBAD_FAST(4, 6); }
+        else { if (cq == 1) LBAD_FAST(8, 1); else LBAD_FAST(8, 6); }
+    } else {
+        if (W == 2) LBAD_GEN(2); else if (W == 4) LBAD_GEN(4); else LBAD_GEN(8);
+    }
+#undef LBAD_FAST
+#undef LBAD_GEN
+    db->timer.end(s);
+    db->launches++;
+    LBAD_CUDA_TRY(cudaGetLastError());
+    merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_chunks, n_q, (int)k, d_scores, d_idx);
+    db->launches++;
+    LBAD_CUDA_TRY(cudaGetLastError());
+    return LBAD_OK;
+}
+
+extern "C" int lbadcu_db_search_host(lbadcu_db* db, const uint32_t* h_q, uint32_t n_q, uint32_t cq, uint32_t pairs, uint32_t k,
+                                     float* h_scores, uint32_t* h_idx, float* h_all) {
+    if (!db || !h_scores || !h_idx || n_q == 0 || k == 0) return LBAD_ERR_ARG;
+    LBAD_CUDA_TRY(cudaSetDevice(db->device));
+    const uint32_t W = db->W, n_clips = lbadcu_db_clips(db);
+    const size_t qn = (size_t)n_q * cq * 2 * W;
+    uint32_t* d_q = nullptr; float* d_sc = nullptr; uint32_t* d_id = nullptr; float* d_all = nullptr;
+    LBAD_CUDA_TRY(cudaMalloc(&d_q, (qn ? qn : 1) * sizeof(uint32_t)));
+    LBAD_CUDA_TRY(cudaMalloc(&d_sc, (size_t)n_q * k * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&d_id, (size_t)n_q * k * sizeof(uint32_t)));
+    if (h_all && n_clips) LBAD_CUDA_TRY(cudaMalloc(&d_all, (size_t)n_q * n_clips * sizeof(float)));
+    if (qn) LBAD_CUDA_TRY(cudaMemcpyAsync(d_q, h_q, qn * sizeof(uint32_t), cudaMemcpyHostToDevice, db->stream));
+    int e = lbadcu_db_search_device(db, d_q, n_q, cq, pairs, k, d_sc, d_id, d_all, db->stream);
+    if (e == LBAD_OK) {
+        LBAD_CUDA_TRY(cudaMemcpyAsync(h_scores, d_sc, (size_t)n_q * k * sizeof(float), cudaMemcpyDeviceToHost, db->stream));
+        LBAD_CUDA_TRY(cudaMemcpyAsync(h_idx, d_id, (size_t)n_q * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, db->stream));
+        if (d_all) LBAD_CUDA_TRY(cudaMemcpyAsync(h_all, d_all, (size_t)n_q * n_clips * sizeof(float), cudaMemcpyDeviceToHost, db->stream));
+        LBAD_CUDA_TRY(cudaStreamSynchronize(db->stream));
+    }
+    cudaFree(d_q); cudaFree(d_sc); cudaFree(d_id); cudaFree(d_all);
+    return e;
+}
+
+/* k-way merge of gathered per-shard lists on the device (same kernel as the per-chunk merge) */
+extern "C" int lbadcu_merge_topk_host(const float* h_sc, const uint32_t* h_id, uint32_t n_lists, uint32_t n_q, uint32_t k, float* o_sc, uint32_t* o_id) {
+    if (!h_sc || !h_id || !o_sc || !o_id || n_lists == 0 || n_q == 0 || k == 0) return LBAD_ERR_ARG;
+    if (lbadcu_device_available() != LBAD_OK) { set_error("no CUDA device available (this library has no CPU fallback)"); return LBAD_ERR_NODEVICE; }
+    const size_t n = (size_t)n_lists * n_q * k;
+    float *d_sc = nullptr, *d_o = nullptr; uint32_t *d_id = nullptr, *d_oi = nullptr;
+    LBAD_CUDA_TRY(cudaMalloc(&d_sc, n * 4)); LBAD_CUDA_TRY(cudaMalloc(&d_id, n * 4)); LBAD_CUDA_TRY(cudaMalloc(&d_o, (size_t)n_q * k * 4)); LBAD_CUDA_TRY(cudaMalloc(&d_oi, (size_t)n_q * k * 4));
+    LBAD_CUDA_TRY(cudaMemcpy(d_sc, h_sc, n * 4, cudaMemcpyHostToDevice)); LBAD_CUDA_TRY(cudaMemcpy(d_id, h_id, n * 4, cudaMemcpyHostToDevice));
+    merge_topk_kernel<<<(n_q + 3) / 4, 128>>>(d_sc, d_id, n_lists, n_q, (int)k, d_o, d_oi);
+    LBAD_CUDA_TRY(cudaGetLastError());
+    LBAD_CUDA_TRY(cudaMemcpy(o_sc, d_o, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost)); LBAD_CUDA_TRY(cudaMemcpy(o_id, d_oi, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_sc); cudaFree(d_id); cudaFree(d_o); cudaFree(d_oi);
+    return LBAD_OK;
+}

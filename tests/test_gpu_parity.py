@@ -1,0 +1,322 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star):
+  * band energies: 1e-4 relative (per element, on the synthetic chirp+tone+noise input, whose noise floor keeps every
+    band well above the f32 FFT error);
+  * Haar coefficients: 1e-4 relative to the image's largest |coefficient| (small ones are cancellation results);
+  * sign bits: <= 0.1 % mismatching Booleans (rank swaps where magnitudes tie within tolerance), reported;
+  * everything downstream of identical inputs — Haar given images, bits given coefficients, scores and top-k given
+    bits — bit-exact.
+"""
+import numpy as np
+import pytest
+from oracle.oracle import Cfg
+
+pytestmark = pytest.mark.gpu
+
+BAND_RTOL = 1e-4
+HAAR_RTOL_OF_MAX = 1e-4
+BIT_MISMATCH_BUDGET = 1e-3
+
+
+def mismatch_rate(a, b):
+    assert a.shape == b.shape
+    return float((a != b).mean())
+
+
+# ------------------------------------------------------------------ extraction ----
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "generic"])
+def test_config1_stages_against_golden(lb, config1, fused):
+    d = lb.Detective()
+    worst_band = worst_haar = 0.0; mism = 0; total = 0
+    for c in range(2):
+        img, haar, bits = d.process_stages(config1["pcm"][c], fused=fused)
+        gi, gh, gb = config1["images"][c], config1["haar"][c], config1["bits"][c]
+        assert img.shape == gi.shape == (6, 128, 32)
+        worst_band = max(worst_band, float((np.abs(img - gi) / np.abs(gi)).max()))
+        worst_haar = max(worst_haar, float((np.abs(haar - gh).reshape(6, -1).max(axis=1) / np.abs(gh).reshape(6, -1).max(axis=1)).max()))
+        mism += int((bits != gb).sum()); total += bits.size
+    print("band rel err %.3g, haar err/max %.3g, bit mismatches %d/%d" % (worst_band, worst_haar, mism, total))
+    assert worst_band < BAND_RTOL
+    assert worst_haar < HAAR_RTOL_OF_MAX
+    assert mism / total <= BIT_MISMATCH_BUDGET
+
+
+def test_fused_equals_generic_bits(lb, port):
+    """Two independent kernels (register radix-32 FFT vs shared-memory radix-2 FFT) agree within the bit budget."""
+    d = lb.Detective(); pcm = port.synth_clip(31, 165360)
+    _, _, bf = d.process_stages(pcm, fused=True)
+    _, _, bg = d.process_stages(pcm, fused=False)
+    assert bf.shape == (19, 200) and mismatch_rate(bf, bg) <= BIT_MISMATCH_BUDGET
+
+
+def test_process_pcm_against_oracle(lb, checker):
+    cfg = Cfg.default(); d = lb.Detective(); mism = 0; total = 0
+    for clip, n in ((40, 55120), (41, 165360), (42, 16536), (43, 10240), (44, 10240 + 8191), (45, 10240 + 8192)):
+        pcm = checker.synth_clip(clip, n)
+        fp = d.process_pcm(pcm); want = checker.process(cfg, pcm)
+        assert fp.count == want.shape[0] and fp.subfingerprint_length == 200
+        got = fp.booleans(); mism += int((got != want).sum()); total += want.size
+        assert np.array_equal(lb.unpack_words(fp.packed(), 200), got)
+    print("bit mismatches %d/%d vs %s oracle" % (mism, total, checker.kind))
+    assert mism / total <= BIT_MISMATCH_BUDGET
+
+
+def test_transform_images_bit_exact(lb, checker, config1):
+    """Given identical spectral images, Haar (IEEE divides, same order) and the ordered top-t are bit-exact."""
+    d = lb.Detective()
+    rng = np.random.default_rng(7)
+    images = np.concatenate([config1["images"][0], (rng.random((4, 128, 32)) ** 4 * 50).astype(np.float32)])
+    ties = np.zeros((1, 128, 32), np.float32); ties[0, 5, 3] = 2.0; ties[0, 6, 3] = -2.0; ties[0, 100, 31] = 2.0; ties[0, 64:, :8] = 1.0
+    images = np.concatenate([images, ties, np.zeros((1, 128, 32), np.float32)])
+    haar, bits = d.transform_images(images)
+    for i in range(images.shape[0]):
+        want_h = checker.haar(images[i])
+        assert np.array_equal(haar[i], want_h), i
+        assert np.array_equal(bits[i], checker.extract_bits(want_h, 200)[:200]), i
+    assert bits[-1].sum() == 0                                            # silence: every coefficient is zero -> no bit set
+
+
+def test_bits_from_coefficients_with_exact_ties(lb, checker):
+    """Top-t on coefficient sets full of exact magnitude ties: the stable order (lower flat index first) must hold."""
+    d = lb.Detective(); rng = np.random.default_rng(8)
+    # images whose Haar transform is easy to control: a constant image has a single non-zero coefficient; use small integers instead
+    images = rng.integers(0, 3, size=(6, 128, 32)).astype(np.float32)
+    haar, bits = d.transform_images(images)
+    for i in range(6):
+        want_h = checker.haar(images[i])
+        assert np.array_equal(haar[i], want_h)
+        assert np.array_equal(bits[i], checker.extract_bits(want_h, 200)[:200])
+
+
+def test_config5_sweep_against_golden(lb, sweep):
+    """Window-size x subfingerprint-length sweep (BASELINE config 5) through the generic path; budget over the sweep."""
+    mism = total = 0
+    for window in (512, 1024, 2048):
+        for sublen in (100, 200, 400):
+            d = lb.Detective(); d.set_window_size(window); d.set_subfingerprint_length(sublen)
+            assert d.check_configuration() == 0
+            for name in ("clip", "query"):
+                want = sweep["%s_%d_%d" % (name, window, sublen)]
+                fp = d.process_pcm(sweep["base" if name == "clip" else "query"])
+                assert fp.count == want.shape[0] and fp.subfingerprint_length == sublen
+                m = int((fp.booleans() != want).sum()); mism += m; total += want.size
+                if m:
+                    print("window %d sublen %d %s: %d mismatching Booleans" % (window, sublen, name, m))
+    print("sweep: %d/%d mismatching Booleans" % (mism, total))
+    assert mism / total <= BIT_MISMATCH_BUDGET
+
+
+def test_other_geometry_against_oracle(lb, checker):
+    cases = [dict(window=256, stride=64), dict(stride=128, sample_rate=8000.0), dict(bands=16, sublen=64), dict(stride=50), dict(bands=64, sublen=512),
+             dict(stride=2), dict(window=1024, stride=1000)]
+    mism = total = 0
+    for kw in cases:
+        cfg = Cfg.default(**kw); d = lb.Detective()
+        d.set_window_size(cfg.window); d.set_analysis_stride(cfg.stride); d.set_pitch_steps(cfg.bands); d.set_subfingerprint_length(cfg.sublen); d.set_sample_rate(cfg.sample_rate)
+        assert d.check_configuration() == 0, kw
+        n = 40000 if cfg.stride <= 128 else 128 * cfg.stride * 2 + cfg.window + 7
+        pcm = checker.synth_clip(50, n, cfg.sample_rate)
+        want = checker.process(cfg, pcm) if checker.kind == "port" else checker.process(cfg, pcm, direct=True)
+        got = d.process_pcm(pcm).booleans()
+        assert got.shape == want.shape and want.shape[0] >= 1, kw
+        m = int((got != want).sum()); mism += m; total += want.size
+        if m:
+            print(kw, "%d mismatching Booleans of %d" % (m, want.size))
+    assert mism / total <= BIT_MISMATCH_BUDGET
+
+
+def test_invariants_of_the_reference_tests(lb, port):
+    pcm = port.synth_clip(60, 82680)
+    a = lb.Detective().process_pcm(pcm); b = lb.Detective().process_pcm(pcm)
+    assert a.equal(b)                                                     # testFingerprintVersatility (Tests.m:119-139)
+    assert a.copy().equal(a)                                              # testFingerprintComparison (Tests.m:141-155)
+    assert a.compare(a, 200) == 1.0
+
+
+def test_edge_cases(lb, port):
+    d = lb.Detective()
+    st, fp = d.process_pcm(np.zeros(2047, np.float32), check=False)
+    assert st == lb.ARGUMENT_INVALID and fp.count == 0                    # shorter than one window (upstream underflows, m:250)
+    fp = d.process_pcm(np.zeros(10239, np.float32)); assert fp.count == 0 # not enough windows for one frame
+    fp = d.process_pcm(np.zeros(10240, np.float32)); assert fp.count == 1 and fp.booleans().sum() == 0
+    big = np.full(10240, 1e30, np.float32)                                # energies overflow to inf and are skipped (m:398-401)
+    fp = d.process_pcm(big); assert fp.count == 1
+    d.set_window_size(4096); st, fp = d.process_pcm(np.zeros(20000, np.float32), check=False)
+    assert st == lb.ARGUMENT_INVALID
+
+
+def test_batch_equals_single(lb, port):
+    d = lb.Detective()
+    pcm = np.stack([port.synth_clip(70 + i, 55120) for i in range(5)])
+    words = d.process_batch(pcm)
+    assert words.shape == (5, 6, 8)
+    for i in range(5):
+        assert np.array_equal(words[i], d.process_pcm(pcm[i]).packed())
+    # ragged stride / unaligned clip length take the non-TMA staging path and must agree
+    odd = np.ascontiguousarray(pcm[:, :55001])
+    w2 = d.process_batch(odd)
+    for i in range(5):
+        assert np.array_equal(w2[i], d.process_pcm(odd[i]).packed())
+
+
+def test_device_resident_batch(lb, port):
+    import torch
+    d = lb.Detective(); n, clip_len = 64, 165360
+    x = torch.empty((n, clip_len), dtype=torch.float32, device="cuda")
+    lb.synthesize_device(x.data_ptr(), n, clip_len, clip_len, first_clip_id=1000)
+    out = torch.zeros((n, 19, 8), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    d.process_batch_device(x.data_ptr(), n, clip_len, clip_len, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    host = d.process_batch(x.cpu().numpy())
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), host)
+    bits = lb.unpack_words(host, 200)
+    assert bits.reshape(-1, 100, 2).sum(axis=2).max() <= 1                # never both sign bits of a rank
+    assert bits.sum() == bits.shape[0] * bits.shape[1] * 100              # noisy audio: every selected wavelet is non-zero
+    assert d.kernel_launches >= 2
+
+
+# --------------------------------------------------------------------- matching ----
+
+def test_compare_toy_vectors(lb, kat):
+    t = kat["compare_toy"]; a = np.array(t["a"], np.uint8); b = np.array(t["b"], np.uint8)
+    fp = lb.Fingerprint(8)
+    assert fp.compare_subfingerprints(a, b, 8) == t["ab8"]
+    assert fp.compare_subfingerprints(b, a, 8) == t["ba8"]
+    assert fp.compare_subfingerprints(a, b, 4) == t["ab4"]
+    assert fp.compare_subfingerprints(np.zeros(8, np.uint8), b, 8) == 0.0  # possible == 0 (FP.m:171-173)
+
+
+def test_compare_cases_bit_exact(lb, compare_cases):
+    for c in compare_cases:
+        f1 = lb.Fingerprint.from_booleans(c["fp1"].reshape(int(c["c1"]), int(c["L"]))) if int(c["c1"]) else lb.Fingerprint(int(c["L"]))
+        f2 = lb.Fingerprint.from_booleans(c["fp2"].reshape(int(c["c2"]), int(c["L"]))) if int(c["c2"]) else lb.Fingerprint(int(c["L"]))
+        got = np.float32(f1.compare(f2, int(c["range"])))
+        assert got == c["score"], (int(c["c1"]), int(c["c2"]), int(c["L"]), int(c["range"]), got, c["score"])
+
+
+def test_compare_random_bit_exact(lb, checker):
+    rng = np.random.default_rng(11)
+    for _ in range(60):
+        L = int(rng.choice([100, 200, 400])); c1 = int(rng.integers(0, 9)); c2 = int(rng.integers(0, 9)); rg = int(rng.integers(1, L + 40))
+        if c1 + c2 == 0:
+            continue
+        b1 = (rng.random((c1, L)) < 0.4).astype(np.uint8); b2 = (rng.random((c2, L)) < 0.4).astype(np.uint8)
+        f1 = lb.Fingerprint.from_booleans(b1) if c1 else lb.Fingerprint(L); f2 = lb.Fingerprint.from_booleans(b2) if c2 else lb.Fingerprint(L)
+        assert np.float32(f1.compare(f2, rg)) == np.float32(checker.compare_fp(b1, b2, rg)), (L, c1, c2, rg)
+
+
+def test_compare_pcm_config1(lb, config1):
+    d = lb.Detective(); p = config1["pcm"]
+    got01 = np.float32(d.compare_pcm(p[0], p[1], 0)); got00 = np.float32(d.compare_pcm(p[0], p[0], 0))
+    assert got00 == 1.0
+    # bits may differ within the 0.1 % budget, which moves the score by at most a few 1/possible steps
+    assert abs(got01 - config1["score_01"]) <= 0.01
+    f0 = lb.Fingerprint.from_booleans(config1["bits"][0]); f1 = lb.Fingerprint.from_booleans(config1["bits"][1])
+    assert np.float32(f0.compare(f1, 200)) == config1["score_01"]          # on identical bits: bit-exact
+    assert np.float32(f1.compare(f0, 200)) == config1["score_10"]
+    assert np.float32(f0.compare(f1, 100)) == config1["score_01_r100"]
+
+
+def rank_sign_codes(rng, n, count, L):
+    sign = rng.integers(0, 2, size=(n, count, L // 2))
+    out = np.zeros((n, count, L), np.uint8); out[..., 0::2] = sign == 0; out[..., 1::2] = sign == 1
+    return out
+
+
+@pytest.mark.parametrize("L,q_count,db_count,rng_len", [(200, 6, 19, 0), (200, 1, 5, 0), (200, 6, 19, 77), (100, 1, 5, 0), (400, 1, 5, 0),
+                                                         (200, 3, 19, 0), (200, 6, 4, 0), (200, 6, 6, 0), (400, 6, 19, 300)])
+def test_search_scores_and_topk_bit_exact(lb, checker, L, q_count, db_count, rng_len):
+    rng = np.random.default_rng(100 + L + q_count + db_count + rng_len)
+    n_db, n_q, k = 300, 37, 10
+    dbb = rank_sign_codes(rng, n_db, db_count, L)
+    qb = rank_sign_codes(rng, n_q, q_count, L)
+    for q in range(0, n_q, 3):                                             # plant noisy excerpts so the top of the list is interesting
+        c = int(rng.integers(0, n_db)); n = min(q_count, db_count); o = int(rng.integers(0, db_count - n + 1))
+        qb[q, :n] = dbb[c, o:o + n]; flip = rng.random(qb[q].shape) < 0.03; qb[q] = np.where(flip, 1 - qb[q], qb[q])
+    db = lb.Database(L); db.add_packed(lb.pack_booleans(dbb))
+    assert db.clips == n_db and db.subfingerprints == n_db * db_count
+    sc, idx, full = db.search_packed(lb.pack_booleans(qb), k, rng=rng_len, all_scores=True)
+    want, _ = checker.search(dbb, qb, rng_len if rng_len else L)
+    assert np.array_equal(full, want)
+    order = np.lexsort((np.arange(n_db)[None, :].repeat(n_q, 0), -want.astype(np.float64)), axis=1)[:, :k]     # score desc, clip asc
+    assert np.array_equal(idx, order.astype(np.uint32))
+    assert np.array_equal(sc, np.take_along_axis(want, order, axis=1))
+    assert db.compares_per_query(q_count) == n_db * (abs(db_count - q_count) + 1) * min(db_count, q_count)
+
+
+def test_search_ragged_database_and_fingerprint_api(lb, checker):
+    rng = np.random.default_rng(12); L = 200
+    counts = rng.integers(0, 25, size=120)
+    fps_bits = [rank_sign_codes(rng, 1, int(c), L)[0] for c in counts]
+    db = lb.Database(L); db.set_clip_index_base(5000)
+    for b in fps_bits:
+        db.add_fingerprint(lb.Fingerprint.from_booleans(b) if len(b) else lb.Fingerprint(L))
+    qs = [rank_sign_codes(rng, 1, 6, L)[0] for _ in range(9)]
+    qs[0] = fps_bits[int(np.argmax(counts))][:6].copy()
+    sc, idx = db.search([lb.Fingerprint.from_booleans(q) for q in qs], k=5)
+    for qi, q in enumerate(qs):
+        want = np.array([np.float32(checker.compare_fp(b, q, L)) if len(b) else np.float32(0) for b in fps_bits])
+        order = np.lexsort((np.arange(len(want)), -want.astype(np.float64)))[:5]
+        assert np.array_equal(idx[qi], (order + 5000).astype(np.uint32))
+        assert np.array_equal(sc[qi], want[order])
+    assert sc[0, 0] == 1.0 and idx[0, 0] == 5000 + int(np.argmax(counts))
+
+
+def test_topk_with_fewer_clips_than_k(lb):
+    rng = np.random.default_rng(13); db = lb.Database(200)
+    db.add_packed(lb.pack_booleans(rank_sign_codes(rng, 3, 6, 200)))
+    sc, idx = db.search_packed(lb.pack_booleans(rank_sign_codes(rng, 2, 6, 200)), k=8)
+    assert (idx[:, 3:] == 0xFFFFFFFF).all() and (sc[:, 3:] == -1).all() and (idx[:, :3] < 3).all()
+
+
+def test_merge_topk_equals_single_list(lb):
+    rng = np.random.default_rng(14); n_lists, n_q, k = 8, 50, 10
+    sc = np.round(rng.random((n_lists, n_q, k)), 2).astype(np.float32)     # rounded: plenty of ties across lists
+    idx = rng.permutation(n_lists * n_q * k).reshape(n_lists, n_q, k).astype(np.uint32)
+    o = np.lexsort((idx, -sc.astype(np.float64)), axis=2)
+    sc = np.take_along_axis(sc, o, 2); idx = np.take_along_axis(idx, o, 2)
+    ms, mi = lb.merge_topk(sc, idx)
+    alls = sc.transpose(1, 0, 2).reshape(n_q, -1); alli = idx.transpose(1, 0, 2).reshape(n_q, -1)
+    o = np.lexsort((alli, -alls.astype(np.float64)), axis=1)[:, :k]
+    assert np.array_equal(mi, np.take_along_axis(alli, o, 1)) and np.array_equal(ms, np.take_along_axis(alls, o, 1))
+
+
+def test_extract_then_search_end_to_end(lb, port):
+    """Queries cut from database clips (config 4 shape, small): the right clip comes first; noise keeps it first."""
+    d = lb.Detective(); n_db = 40
+    pcm = np.stack([port.synth_clip(200 + i, 165360) for i in range(n_db)])
+    words = d.process_batch(pcm)
+    db = lb.Database(200); db.add_packed(words)
+    q_pcm = np.stack([pcm[i, 8192 * 3: 8192 * 3 + 55120] for i in range(0, n_db, 4)])
+    noisy = np.stack([port.add_noise(q, 900 + j, 0.0158) for j, q in enumerate(q_pcm)])
+    for q, floor in ((q_pcm, 1.0), (noisy, 0.6)):
+        sc, idx = db.search_packed(d.process_batch(q), k=3)
+        assert np.array_equal(idx[:, 0], np.arange(0, n_db, 4).astype(np.uint32))
+        assert (sc[:, 0] >= floor).all() and (sc[:, 1] < sc[:, 0]).all()
+
+
+def test_full_size_properties(lb):
+    """BASELINE config-2 shaped work at reduced clip count: determinism and structure of 2,000 x 30 s clips on device."""
+    import torch
+    d = lb.Detective(); n, clip_len = 2000, 165360
+    x = torch.empty((n, clip_len), dtype=torch.float32, device="cuda")
+    lb.synthesize_device(x.data_ptr(), n // 2, clip_len, clip_len, first_clip_id=0)
+    x[n // 2:] = x[:n // 2]                                                 # second half duplicates the first
+    out = torch.zeros((n, 19, 8), dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    d.process_batch_device(x.data_ptr(), n, clip_len, clip_len, out.data_ptr(), s)
+    torch.cuda.synchronize()
+    w = out.cpu().numpy().view(np.uint32)
+    assert np.array_equal(w[:n // 2], w[n // 2:])                           # same PCM -> same words wherever it is scheduled
+    out2 = torch.zeros_like(out); d.process_batch_device(x.data_ptr(), n, clip_len, clip_len, out2.data_ptr(), s); torch.cuda.synchronize()
+    assert torch.equal(out, out2)                                           # idempotent
+    assert ((w[..., :4] & w[..., 4:]) == 0).all()                           # P and M planes never overlap
+    pop = np.unpackbits((w[..., :4] | w[..., 4:]).view(np.uint8), axis=-1).sum(axis=-1)
+    assert (pop == 100).all()                                               # exactly t_eff = 100 ranks carry a sign
+    assert (w[..., 3] >> 4 == 0).all() and (w[..., 7] >> 4 == 0).all()      # nothing beyond pair 99
+    db = lb.Database(200); db.add_packed_device(out.data_ptr(), n // 2, 19)
+    sc, idx = db.search_packed(w[5:n // 2:97, 4:10], k=1)                   # 6-subfp excerpts of database clips
+    assert np.array_equal(idx[:, 0], np.arange(5, n // 2, 97).astype(np.uint32)) and (sc == 1.0).all()
