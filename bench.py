@@ -170,7 +170,10 @@ def main():
 
     n_clips = args.clips
     det = lb.Detective()
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream()                      # a real (non-NULL) stream: NULL would mean "the detective's own stream" to the C API
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     pcm = torch.empty((n_clips, CLIP_LEN), dtype=torch.float32, device="cuda")
     lb.synthesize_device(pcm.data_ptr(), n_clips, CLIP_LEN, CLIP_LEN, first_clip_id=rank * n_clips, stream=stream)      # every rank: its own clips
     words = torch.zeros((n_clips, SUBFPS, 8), dtype=torch.int32, device="cuda")

@@ -1,0 +1,33 @@
+"""Small driver for ncu captures: a few launches of the extraction kernel and of the search kernel on synthetic data."""
+import argparse
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import lbaudiodetective_b200 as lb
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--clips", type=int, default=2000)
+ap.add_argument("--db-clips", type=int, default=200000)
+ap.add_argument("--queries", type=int, default=1000)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--what", default="both")
+a = ap.parse_args()
+s = torch.cuda.Stream(); torch.cuda.set_stream(s)
+if a.what in ("both", "extract"):
+    d = lb.Detective(); n, L = a.clips, 165360
+    x = torch.empty((n, L), dtype=torch.float32, device="cuda"); lb.synthesize_device(x.data_ptr(), n, L, L, stream=s.cuda_stream)
+    w = torch.zeros((n, 19, 8), dtype=torch.int32, device="cuda")
+    for _ in range(a.reps):
+        d.process_batch_device(x.data_ptr(), n, L, L, w.data_ptr(), s.cuda_stream)
+    torch.cuda.synchronize()
+if a.what in ("both", "search"):
+    db = lb.Database(200); n = a.db_clips
+    codes = torch.empty((n, 19, 8), dtype=torch.int32, device="cuda"); lb.random_codes_device(codes.data_ptr(), n * 19, 200, seed=5, stream=s.cuda_stream); torch.cuda.synchronize()
+    db.add_packed_device(codes.data_ptr(), n, 19)
+    q = codes[:a.queries, 3:9].contiguous(); sc = torch.empty((a.queries, 10), dtype=torch.float32, device="cuda"); ix = torch.empty((a.queries, 10), dtype=torch.int32, device="cuda")
+    for _ in range(a.reps):
+        db.search_device(q.data_ptr(), a.queries, 6, 10, sc.data_ptr(), ix.data_ptr(), stream=s.cuda_stream)
+    torch.cuda.synchronize()
+    assert (ix[:, 0].cpu().numpy() == np.arange(a.queries)).all()
+print("prof_run done")
