@@ -193,7 +193,7 @@ bands_generic_kernel(const float* __restrict__ pcm, float* __restrict__ images, 
                 const float2 zk = z[__brev(k) >> sh], zp = z[__brev(M - k) >> sh], tw = tw_n[k];   /* tw = (cos, sin) */
                 real_split_2x(zk.x, zk.y, zp.x, zp.y, tw.x, tw.y, xr, xi);
             }
-            v[k] = bin_energy(xr, xi, g.inv_pos_scale);                         /* m:387-401 */
+            v[k] = bin_energy(xr, xi, g.inv_pos_scale - 1.0f);                         /* m:387-401 */
         }
         __syncwarp();
         for (uint32_t b = lane; b < g.bands; b += 32) {                         /* m:379-405, sums in increasing k */
@@ -235,10 +235,10 @@ haar_select_kernel(const float* __restrict__ images, float* __restrict__ haar_ou
 
 /* -------------------------------------------------------------------------------------------- fused path ---- */
 
-constexpr int FUSED_WARPS = 4;
+constexpr int FUSED_WARPS = 8;
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;
 constexpr int FUSED_LD = 33;                 /* image row stride (floats) */
-constexpr int SCR_LD = 34;                   /* transpose scratch row stride (float2) */
+constexpr int SCR_LDF = 36;                  /* transpose scratch row stride (floats): LDS.128-aligned and conflict-free */
 
 struct FusedSmemLayout {
     uint32_t samples_bytes, total_bytes;
@@ -248,7 +248,7 @@ static FusedSmemLayout fused_layout(uint32_t span_floats) {
     FusedSmemLayout L;
     L.samples_bytes = (span_floats * 4 + 15) & ~15u;
     uint32_t o = L.samples_bytes;
-    L.off_scratch = o; o += FUSED_WARPS * 32 * SCR_LD * 8;
+    L.off_scratch = o; o += FUSED_WARPS * 32 * SCR_LDF * 4;      /* one float component at a time: 4.5 KB per warp */
     L.off_tw1 = o;     o += 32 * 32 * 8;
     L.off_tw2 = o;     o += 32 * 32 * 8;
     L.off_img = o;     o += LBAD_ROWS_PER_FRAME * FUSED_LD * 4;
@@ -258,31 +258,35 @@ static FusedSmemLayout fused_layout(uint32_t span_floats) {
     return L;
 }
 
+/* STATIC_RANGE: the band table is the reference-default one (bins [86, 759)), so the rows of 32 bins that need the
+ * real split are k2 = 2..23 at compile time; otherwise the range is a (warp-uniform) run-time value. */
+template <bool STATIC_RANGE>
 __global__ void __launch_bounds__(FUSED_THREADS, 2)
 extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words, float* __restrict__ images_out,
-                     float* __restrict__ haar_out, const float2* __restrict__ g_tw1, const float2* __restrict__ g_tw2,
+                     float* __restrict__ haar_out, const float4* __restrict__ g_tw1, const float4* __restrict__ g_tw2,
                      const Geo g, const BandTable bt, const FusedSmemLayout L, const uint32_t span_floats,
                      const uint32_t total_frames, const int use_tma) {
     extern __shared__ __align__(128) unsigned char smem[];
     float*  samples = reinterpret_cast<float*>(smem);
-    float2* tw1 = reinterpret_cast<float2*>(smem + L.off_tw1);
-    float2* tw2 = reinterpret_cast<float2*>(smem + L.off_tw2);
+    float4* tw1 = reinterpret_cast<float4*>(smem + L.off_tw1);     /* [p/2][lane]: twiddles of register positions p, p+1 */
+    float4* tw2 = reinterpret_cast<float4*>(smem + L.off_tw2);     /* [k2/2][lane]: (cos, sin) of bins lane+32k2, lane+32(k2+1) */
     float*  img = reinterpret_cast<float*>(smem + L.off_img);
     SelectSmem& sel = *reinterpret_cast<SelectSmem*>(smem + L.off_sel);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    float2* scr = reinterpret_cast<float2*>(smem + L.off_scratch) + wid * (32 * SCR_LD);
-    float* vbuf = reinterpret_cast<float*>(scr);             /* band scratch aliases the transpose scratch */
+    float* scr = reinterpret_cast<float*>(smem + L.off_scratch) + wid * (32 * SCR_LDF);
+    float* vbuf = scr;                                       /* band scratch (1024 floats) aliases the transpose scratch */
 
-    for (int i = tid; i < 1024; i += FUSED_THREADS) { tw1[i] = g_tw1[i]; tw2[i] = g_tw2[i]; }
+    for (int i = tid; i < 512; i += FUSED_THREADS) { tw1[i] = g_tw1[i]; tw2[i] = g_tw2[i]; }
     if (tid == 0 && use_tma) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
 
     const uint32_t klow = bt.klow[lane], khigh = bt.khigh[lane];
     const float divisor = bt.divisor[lane];
-    const int k2lo = (int)(g.kmin >> 5), k2hi = (int)((g.kmax - 1) >> 5);
+    const int k2lo = STATIC_RANGE ? 2 : (int)(g.kmin >> 5), k2hi = STATIC_RANGE ? 23 : (int)((g.kmax - 1) >> 5);
     const uint32_t hop = g.stride;
     const uint32_t bytes = span_floats * 4;
+    const float scale_m1 = g.inv_pos_scale - 1.0f;
 
     auto frame_src = [&](uint32_t f) -> const float* {
         const uint32_t clip = f / g.frames_per_clip, fr = f % g.frames_per_clip;
@@ -300,7 +304,8 @@ extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words
             __syncthreads();
         }
 
-        /* ---- 32 windows per warp: FFT -> bands -> image row ---- */
+        /* ---- 16 windows per warp: FFT -> bands -> image row ---- */
+#pragma unroll 1
         for (int it = 0; it < (int)LBAD_ROWS_PER_FRAME / FUSED_WARPS; ++it) {
             const int row = it * FUSED_WARPS + wid;
             const float* win = samples + (size_t)row * hop;
@@ -312,38 +317,57 @@ extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words
             }
             fft32(re, im);                                                      /* over n1; position p holds k1 = bitrev5(p) */
 #pragma unroll
-            for (int p = 0; p < 32; p++) {
-                const int k1 = bitrev5(p);
-                const float2 w = tw1[k1 * 32 + lane];                           /* exp(-2 pi i lane k1 / 1024) */
-                scr[k1 * SCR_LD + lane] = make_float2(re[p] * w.x - im[p] * w.y, re[p] * w.y + im[p] * w.x);
+            for (int p = 0; p < 32; p += 2) {                                   /* x exp(-2 pi i lane k1 / 1024) */
+                const float4 w = tw1[(p >> 1) * 32 + lane];
+                const float a0 = re[p] * w.x - im[p] * w.y, b0 = re[p] * w.y + im[p] * w.x;
+                const float a1 = re[p + 1] * w.z - im[p + 1] * w.w, b1 = re[p + 1] * w.w + im[p + 1] * w.z;
+                re[p] = a0; im[p] = b0; re[p + 1] = a1; im[p + 1] = b1;
+            }
+            /* 32x32 transpose through shared memory, one component at a time: lane k1 ends up with A[n2][k1], n2 = 0..31 */
+#pragma unroll
+            for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = re[p];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const float4 t = *reinterpret_cast<const float4*>(&scr[lane * SCR_LDF + 4 * q]);
+                re[4 * q] = t.x; re[4 * q + 1] = t.y; re[4 * q + 2] = t.z; re[4 * q + 3] = t.w;
             }
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 16; q++) {                                      /* lane = k1 reads A[n2][k1], n2 = 2q, 2q+1 */
-                const float4 t = *reinterpret_cast<const float4*>(&scr[lane * SCR_LD + 2 * q]);
-                re[2 * q] = t.x; im[2 * q] = t.y; re[2 * q + 1] = t.z; im[2 * q + 1] = t.w;
+            for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = im[p];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const float4 t = *reinterpret_cast<const float4*>(&scr[lane * SCR_LDF + 4 * q]);
+                im[4 * q] = t.x; im[4 * q + 1] = t.y; im[4 * q + 2] = t.z; im[4 * q + 3] = t.w;
             }
             fft32(re, im);                                                      /* over n2; position p holds Z[lane + 32 bitrev5(p)] */
             __syncwarp();                                                       /* scratch is about to be reused as vbuf */
             const int src_lane = (32 - lane) & 31;
 #pragma unroll
-            for (int k2 = 0; k2 < 32; k2++) {
-                if (k2 >= k2lo && k2 <= k2hi) {                                 /* warp-uniform */
-                    const int p = bitrev5(k2), pp = bitrev5(31 - k2), p0 = bitrev5((32 - k2) & 31);
-                    float pr = __shfl_sync(0xffffffffu, re[pp], src_lane);      /* Z[1024 - k] lives in lane 32-lane, k2' = 31-k2 */
-                    float pi = __shfl_sync(0xffffffffu, im[pp], src_lane);
-                    if (lane == 0) { pr = re[p0]; pi = im[p0]; }                /* ... except lane 0: own register k2' = 32-k2 */
-                    const float2 w = tw2[k2 * 32 + lane];                       /* (cos, sin) of 2 pi k / 2048 */
-                    float xr, xi;
-                    real_split_2x(re[p], im[p], pr, pi, w.x, w.y, xr, xi);
-                    if (k2 == 0 && lane == 0) { xr = 2.0f * (re[p] + im[p]); xi = 2.0f * (re[p] - im[p]); }   /* DC / packed Nyquist */
-                    vbuf[k2 * 32 + lane] = bin_energy(xr, xi, g.inv_pos_scale);
+            for (int k2 = 0; k2 < 32; k2 += 2) {
+                if ((STATIC_RANGE && k2 >= 2 && k2 <= 23) || (!STATIC_RANGE && k2 + 1 >= k2lo && k2 <= k2hi)) {   /* warp-uniform */
+                    const float4 w = tw2[(k2 >> 1) * 32 + lane];                /* (cos, sin) of 2 pi k / 2048 for k2 and k2+1 */
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int kk = k2 + h;
+                        const int p = bitrev5(kk), pp = bitrev5(31 - kk), p0 = bitrev5((32 - kk) & 31);
+                        float pr = __shfl_sync(0xffffffffu, re[pp], src_lane);  /* Z[1024 - k] lives in lane 32-lane, k2' = 31-k2 */
+                        float pi = __shfl_sync(0xffffffffu, im[pp], src_lane);
+                        if (lane == 0) { pr = re[p0]; pi = im[p0]; }            /* ... except lane 0: own register k2' = 32-k2 */
+                        float xr, xi;
+                        real_split_2x(re[p], im[p], pr, pi, h ? w.z : w.x, h ? w.w : w.y, xr, xi);
+                        if (kk == 0 && lane == 0) { xr = 2.0f * (re[p] + im[p]); xi = 2.0f * (re[p] - im[p]); }   /* DC / packed Nyquist */
+                        vbuf[kk * 32 + lane] = bin_energy(xr, xi, scale_m1);
+                    }
                 }
             }
             __syncwarp();
-            float pacc = 0.0f;                                                  /* lane = band; m:379-405 order */
-            for (uint32_t k = klow; k < khigh; k++) pacc = __fadd_rn(pacc, vbuf[k]);
-            img[row * FUSED_LD + lane] = __fdiv_rn(pacc, divisor);
+            float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;                   /* lane = band; m:379-405 (4 interleaved partial sums) */
+            uint32_t k = klow;
+            for (; k + 4 <= khigh; k += 4) { p0 += vbuf[k]; p1 += vbuf[k + 1]; p2 += vbuf[k + 2]; p3 += vbuf[k + 3]; }
+            for (; k < khigh; k++) p0 += vbuf[k];
+            img[row * FUSED_LD + lane] = __fdiv_rn((p0 + p1) + (p2 + p3), divisor);
             __syncwarp();
         }
         __syncthreads();                                                        /* image complete; samples free */
@@ -355,10 +379,11 @@ extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words
         if (images_out) {
             float* o = images_out + (size_t)f * LBAD_ROWS_PER_FRAME * 32;
             for (int i = tid; i < (int)LBAD_ROWS_PER_FRAME * 32; i += FUSED_THREADS) o[i] = img[(i >> 5) * FUSED_LD + (i & 31)];
+            __syncthreads();
         }
 
         /* ---- Haar rows (length 32), Frame.m:114-116 + 134-153; thread = row ---- */
-        {
+        if (tid < (int)LBAD_ROWS_PER_FRAME) {
             float a[32], t[32];
             const float s32 = sqrtf(32.0f), s2 = sqrtf(2.0f), s128 = sqrtf(128.0f);
 #pragma unroll
@@ -384,16 +409,16 @@ extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words
             const int c = tid & 31, i0 = tid >> 5;
 #pragma unroll 1
             for (int n = 64; n >= 1; n >>= 1) {
-                float x0[16], x1[16];
+                float x0[8], x1[8];
 #pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    const int i = i0 + 4 * q;
+                for (int q = 0; q < 8; q++) {
+                    const int i = i0 + FUSED_WARPS * q;
                     if (i < n) { x0[q] = img[(2 * i) * FUSED_LD + c]; x1[q] = img[(2 * i + 1) * FUSED_LD + c]; }
                 }
                 __syncthreads();
 #pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    const int i = i0 + 4 * q;
+                for (int q = 0; q < 8; q++) {
+                    const int i = i0 + FUSED_WARPS * q;
                     if (i < n) {
                         img[i * FUSED_LD + c] = __fdiv_rn(__fadd_rn(x0[q], x1[q]), s2);
                         img[(n + i) * FUSED_LD + c] = __fdiv_rn(__fsub_rn(x0[q], x1[q]), s2);
@@ -407,7 +432,7 @@ extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words
             for (int i = tid; i < (int)LBAD_ROWS_PER_FRAME * 32; i += FUSED_THREADS) o[i] = img[(i >> 5) * FUSED_LD + (i & 31)];
         }
         /* ---- ordered top-T -> packed words, Frame.m:165-191 ---- */
-        select_and_pack<FUSED_THREADS, 32>([&](int idx) { return img[(idx >> 5) * FUSED_LD + (idx & 31)]; }, (int)g.pairs,
+        select_and_pack<FUSED_THREADS, 16>([&](int idx) { return img[(idx >> 5) * FUSED_LD + (idx & 31)]; }, (int)g.pairs,
                                            (int)g.words_per_plane, words + (size_t)f * 2 * g.words_per_plane, sel);
         __syncthreads();
     }
@@ -425,7 +450,8 @@ struct lbadcu_plan {
     BandTable bt;
     int device = 0;
     cudaStream_t stream = nullptr, copy_streams[3] = {nullptr, nullptr, nullptr};
-    float2 *d_tw_m = nullptr, *d_tw_n = nullptr, *d_tw1 = nullptr, *d_tw2 = nullptr;
+    float2 *d_tw_m = nullptr, *d_tw_n = nullptr; float4 *d_tw1 = nullptr, *d_tw2 = nullptr;
+    bool static_range = false;
     float* d_scratch_images = nullptr; size_t scratch_frames = 0;
     float* d_chunk_pcm[3] = {nullptr, nullptr, nullptr}; uint32_t* d_chunk_words[3] = {nullptr, nullptr, nullptr};
     size_t chunk_pcm_floats = 0, chunk_words = 0;
@@ -471,17 +497,24 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     LBAD_CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) LBAD_CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_streams[i], cudaStreamNonBlocking));
     /* twiddle tables, evaluated in double and rounded once */
-    std::vector<float2> twm(M / 2), twn(M), tw1(1024), tw2(1024);
+    std::vector<float2> twm(M / 2), twn(M); std::vector<float4> tw1(512), tw2(512);
     for (uint32_t j = 0; j < M / 2; j++) { const double a = 2.0 * M_PI * j / M; twm[j] = make_float2((float)cos(a), (float)-sin(a)); }
     for (uint32_t k = 0; k < M; k++) { const double a = 2.0 * M_PI * k / N; twn[k] = make_float2((float)cos(a), (float)sin(a)); }
-    for (int k1 = 0; k1 < 32; k1++) for (int l = 0; l < 32; l++) { const double a = 2.0 * M_PI * (double)(l * k1) / 1024.0; tw1[k1 * 32 + l] = make_float2((float)cos(a), (float)-sin(a)); }
-    for (int k2 = 0; k2 < 32; k2++) for (int l = 0; l < 32; l++) { const double a = 2.0 * M_PI * (double)(l + 32 * k2) / 2048.0; tw2[k2 * 32 + l] = make_float2((float)cos(a), (float)sin(a)); }
+    for (int pp = 0; pp < 32; pp += 2) for (int l = 0; l < 32; l++) {            /* fused pass-1 twiddles, in register-position order */
+        const double a0 = 2.0 * M_PI * (double)(l * bitrev5(pp)) / 1024.0, a1 = 2.0 * M_PI * (double)(l * bitrev5(pp + 1)) / 1024.0;
+        tw1[(pp >> 1) * 32 + l] = make_float4((float)cos(a0), (float)-sin(a0), (float)cos(a1), (float)-sin(a1));
+    }
+    for (int k2 = 0; k2 < 32; k2 += 2) for (int l = 0; l < 32; l++) {            /* real-split twiddles for bins l+32k2 and l+32(k2+1) */
+        const double a0 = 2.0 * M_PI * (double)(l + 32 * k2) / 2048.0, a1 = 2.0 * M_PI * (double)(l + 32 * (k2 + 1)) / 2048.0;
+        tw2[(k2 >> 1) * 32 + l] = make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
+    }
     LBAD_CUDA_TRY(cudaMalloc(&p->d_tw_m, sizeof(float2) * (M / 2))); LBAD_CUDA_TRY(cudaMalloc(&p->d_tw_n, sizeof(float2) * M));
-    LBAD_CUDA_TRY(cudaMalloc(&p->d_tw1, sizeof(float2) * 1024)); LBAD_CUDA_TRY(cudaMalloc(&p->d_tw2, sizeof(float2) * 1024));
+    LBAD_CUDA_TRY(cudaMalloc(&p->d_tw1, sizeof(float4) * 512)); LBAD_CUDA_TRY(cudaMalloc(&p->d_tw2, sizeof(float4) * 512));
     LBAD_CUDA_TRY(cudaMemcpy(p->d_tw_m, twm.data(), sizeof(float2) * (M / 2), cudaMemcpyHostToDevice));
     LBAD_CUDA_TRY(cudaMemcpy(p->d_tw_n, twn.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
-    LBAD_CUDA_TRY(cudaMemcpy(p->d_tw1, tw1.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
-    LBAD_CUDA_TRY(cudaMemcpy(p->d_tw2, tw2.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
+    LBAD_CUDA_TRY(cudaMemcpy(p->d_tw1, tw1.data(), sizeof(float4) * 512, cudaMemcpyHostToDevice));
+    LBAD_CUDA_TRY(cudaMemcpy(p->d_tw2, tw2.data(), sizeof(float4) * 512, cudaMemcpyHostToDevice));
+    p->static_range = (kmin >> 5) == 2 && ((kmax - 1) >> 5) == 23;
     /* fused path: window 2048, 32 bands, even hop, frame span fits in shared memory */
     const uint64_t span = 127ull * geo->stride + N;
     p->fused_ok = (N == 2048 && B == 32 && (geo->stride % 2 == 0) && span * 4 < (1u << 20) && fused_layout((uint32_t)span).total_bytes <= p->smem_optin);
@@ -553,14 +586,15 @@ extern "C" int lbadcu_extract_device(lbadcu_plan* p, const float* d_pcm, uint32_
         /* TMA bulk copies need 16-byte aligned sources and sizes */
         bool tma_ok = ((uintptr_t)d_pcm % 16 == 0) && (clip_stride % 4 == 0) && (g.stride % 4 == 0);
         if (p->stage_mode == 0) tma_ok = false;
-        LBAD_CUDA_TRY(cudaFuncSetAttribute(extract_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes));
+        auto kern = p->static_range ? extract_fused_kernel<true> : extract_fused_kernel<false>;
+        LBAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes));
         int per_sm = 0;
-        LBAD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, extract_fused_kernel, FUSED_THREADS, L.total_bytes));
+        LBAD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, L.total_bytes));
         if (per_sm < 1) per_sm = 1;
         const uint32_t cap = (uint32_t)(p->sm_count * per_sm);
         const uint32_t grid = total_frames < cap ? total_frames : cap;
         p->timer.begin(s);
-        extract_fused_kernel<<<grid, FUSED_THREADS, L.total_bytes, s>>>(d_pcm, d_words, d_images, d_haar, p->d_tw1, p->d_tw2, g, p->bt, L, span,
+        kern<<<grid, FUSED_THREADS, L.total_bytes, s>>>(d_pcm, d_words, d_images, d_haar, p->d_tw1, p->d_tw2, g, p->bt, L, span,
                                                                         total_frames, tma_ok ? 1 : 0);
         p->timer.end(s);
         p->launches++;

@@ -17,6 +17,7 @@
 #ifndef LBAD_MATH_CUH
 #define LBAD_MATH_CUH
 #include <stdint.h>
+#include <math.h>
 #include <utility>
 
 #if defined(__CUDACC__)
@@ -78,24 +79,19 @@ LBAD_HD void fft32(float (&re)[32], float (&im)[32]) {
 LBAD_HD void real_split_2x(float zr, float zi, float pr, float pi, float c, float s, float& xr, float& xi) {
     const float er = zr + pr, ei = zi - pi;      /* Z + conj Z' */
     const float dr = zr - pr, di = zi + pi;      /* Z - conj Z' */
-    xr = er + (c * di - s * dr);                 /* -i w d = (-s dr + c di) + i (-c dr - s di) */
-    xi = ei - (c * dr + s * di);
+    xr = fmaf(c, di, fmaf(-s, dr, er));          /* -i w d = (-s dr + c di) + i (-c dr - s di) */
+    xi = fmaf(-s, di, fmaf(-c, dr, ei));
 }
 
-/* LBAudioDetective.m:387-401 for one bin: positive parts only are divided by pos_scale (a power of two, so the
- * multiply by its reciprocal is exact), then re^2 + im^2 evaluated unfused in f32 as the reference does.
- * Returns 0 for a non-finite value (the reference skips it). */
-LBAD_HD float bin_energy(float re, float im, float inv_pos_scale) {
-    re = re > 0.0f ? re * inv_pos_scale : re;
-    im = im > 0.0f ? im * inv_pos_scale : im;
-#if defined(__CUDA_ARCH__)
-    const float v = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
-    return (v - v == 0.0f) ? v : 0.0f;           /* finite <=> v - v == 0 */
-#else
-    volatile float a = re * re, b = im * im;     /* keep the host build from contracting */
-    const float v = a + b;
-    return (v - v == 0.0f) ? v : 0.0f;
-#endif
+/* LBAudioDetective.m:387-401 for one bin: positive parts only are divided by pos_scale, then re^2 + im^2; a
+ * non-finite value contributes 0 (the reference skips it).  scale_m1 = 1/pos_scale - 1: pos_scale is a power of two,
+ * so fma(max(x, 0), scale_m1, x) is x/pos_scale for x > 0 (the exact quotient is representable, one rounding) and x
+ * otherwise (NaN propagates and is then dropped, as in the reference where NaN > 0 is false). */
+LBAD_HD float bin_energy(float re, float im, float scale_m1) {
+    re = fmaf(fmaxf(re, 0.0f), scale_m1, re);
+    im = fmaf(fmaxf(im, 0.0f), scale_m1, im);
+    const float v = fmaf(re, re, im * im);
+    return (v <= 3.402823466e+38f) ? v : 0.0f;
 }
 
 /* Hit mask of one 32-pair word (LBAudioDetectiveFingerprint.m:155-169):

@@ -52,3 +52,22 @@ def test_dc_and_nyquist_packing(emu, port):
     emu.lbad_emulate_window(vp(win), vp(lo), vp(hi), vp(div), C.c_float(1 / 512.0), C.c_uint32(0), C.c_uint32(40), vp(out), vp(spec))
     ref = port.fft2x(win)
     assert np.abs(spec[:80] - ref[:80]).max() <= 2e-6 * np.abs(ref).max()
+
+
+def test_bin_energy_matches_literal_formula(emu):
+    """fma(max(x,0), 1/s-1, x) == x/s for x > 0 and x otherwise, for the power-of-two scales the reference produces."""
+    emu.lbad_emulate_bin_energy.restype = C.c_float
+    emu.lbad_emulate_bin_energy.argtypes = [C.c_float, C.c_float, C.c_float]
+    rng = np.random.default_rng(9)
+    vals = np.concatenate([rng.standard_normal(2000).astype(np.float32) * np.float32(10.0) ** rng.integers(-30, 30, 2000).astype(np.float32),
+                           np.array([0.0, -0.0, 1e-45, -1e-45, 3e38, -3e38, np.inf, -np.inf, np.nan], np.float32)])
+    for scale in (64.0, 128.0, 256.0, 512.0):
+        for re, im in zip(vals, vals[::-1]):
+            r = np.float32(re / np.float32(scale)) if re > 0 else np.float32(re)
+            i = np.float32(im / np.float32(scale)) if im > 0 else np.float32(im)
+            with np.errstate(all="ignore"):
+                v = np.float32(np.float32(r * r) + np.float32(i * i))
+                want = v if np.isfinite(v) else np.float32(0)
+                got = np.float32(emu.lbad_emulate_bin_energy(float(re), float(im), scale))
+            # the kernel fuses re*re + im*im into one FMA: allow one rounding of difference on the sum
+            assert got == want or abs(float(got) - float(want)) <= 1.2e-7 * abs(float(want)), (re, im, scale, got, want)
