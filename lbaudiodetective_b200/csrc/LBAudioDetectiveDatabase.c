@@ -18,7 +18,7 @@ LBAudioDetectiveDatabaseRef LBAudioDetectiveDatabaseNew(UInt32 inSubfingerprintL
     LBAudioDetectiveDatabaseRef d = calloc(1, sizeof *d);
     if (!d) return NULL;
     d->subfingerprintLength = inSubfingerprintLength; d->W = W;
-    if (lbadcu_db_create(W, &d->db) != LBAD_OK) { free(d); return NULL; }
+    if (lbadcu_db_create(W, (inSubfingerprintLength + 1) / 2, &d->db) != LBAD_OK) { free(d); return NULL; }
     return d;
 }
 

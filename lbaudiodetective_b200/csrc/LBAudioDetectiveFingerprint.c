@@ -144,9 +144,9 @@ static void die_no_device(const char* what, int code) {
 }
 
 /* score = CompareToFingerprint(fp1, fp2, range) on the GPU: fp1 becomes a one-clip database, fp2 the single query */
-static Float32 gpu_compare(const UInt32* w1, UInt32 c1, const UInt32* w2, UInt32 c2, UInt32 W, UInt32 pairs) {
+static Float32 gpu_compare(const UInt32* w1, UInt32 c1, const UInt32* w2, UInt32 c2, UInt32 W, UInt32 pairs, UInt32 pairs_full) {
     lbadcu_db* db = NULL;
-    int e = lbadcu_db_create(W, &db);
+    int e = lbadcu_db_create(W, pairs_full, &db);
     if (e != LBAD_OK) die_no_device("LBAudioDetectiveFingerprintCompareToFingerprint", e);
     Float32 score = 0.0f; UInt32 idx = 0;
     UInt32 dummy[16] = {0};
@@ -167,7 +167,7 @@ Float32 LBAudioDetectiveFingerprintCompareToFingerprint(LBAudioDetectiveFingerpr
                 (unsigned)fp1->subfingerprintLength, (unsigned)fp2->subfingerprintLength);
         return 0.0f;
     }
-    return gpu_compare(fp1->words, fp1->subfingerprintCount, fp2->words, fp2->subfingerprintCount, W, lbad_pairs_for_range(inRange, L));
+    return gpu_compare(fp1->words, fp1->subfingerprintCount, fp2->words, fp2->subfingerprintCount, W, lbad_pairs_for_range(inRange, L), (L + 1) / 2);
 }
 
 /* FP.m:151-176 */
@@ -179,7 +179,7 @@ Float32 LBAudioDetectiveFingerprintCompareSubfingerprints(LBAudioDetectiveFinger
     UInt32 w1[16], w2[16];
     lbad_pack_booleans(s1, n, W, w1);
     lbad_pack_booleans(s2, n, W, w2);
-    return gpu_compare(w1, 1, w2, 1, W, (lim + 1) / 2);
+    return gpu_compare(w1, 1, w2, 1, W, (lim + 1) / 2, (L + 1) / 2);
 }
 
 /* ---- additions ---- */

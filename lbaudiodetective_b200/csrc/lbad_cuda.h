@@ -61,7 +61,8 @@ int  lbadcu_transform_images_host(lbadcu_plan* p, const float* h_images, uint32_
 
 /* ---- search ---- */
 typedef struct lbadcu_db lbadcu_db;
-int  lbadcu_db_create(uint32_t words_per_plane, lbadcu_db** out);
+/* pairs_full = ceil(L/2): pairs every stored subfingerprint carries */
+int  lbadcu_db_create(uint32_t words_per_plane, uint32_t pairs_full, lbadcu_db** out);
 void lbadcu_db_destroy(lbadcu_db* db);
 uint32_t lbadcu_db_clips(const lbadcu_db* db);
 uint64_t lbadcu_db_subfps(const lbadcu_db* db);

@@ -49,21 +49,59 @@ struct TopK {
     }
 };
 
-/* hits/possible as f32, exactly the IEEE quotient (FP.m:171-175); possible == 0 -> 0 because c_rcp[0] == 0 and hits == 0 */
+/* small non-negative integer -> float without the (quarter-rate, XU-pipe) I2F: 0x4B000000 is 2^23 */
+__device__ __forceinline__ float small_uint_to_float(uint32_t v) { return __int_as_float(0x4B000000u | v) - 8388608.0f; }
+
+/* hits/possible as f32, exactly the IEEE quotient (FP.m:171-175); possible == 0 -> 0 because rcp == 0 and hits == 0 */
 __device__ __forceinline__ float ratio_exact(uint32_t hits, float fposs, float rcp) {
-    const float fh = (float)hits;
+    const float fh = small_uint_to_float(hits);
     const float q0 = __fmul_rn(fh, rcp);
     const float rem = fmaf(-q0, fposs, fh);
     return fmaf(rem, rcp, q0);
 }
 
+/* sum / count as the IEEE quotient for count <= 16 and sum in {0} U [2^-8, 16] (verified exhaustively over every
+ * float in [0, 64]: the multiply + two-FMA form only misrounds below 1e-37); larger counts use the divide */
+template <int CQ>
+__device__ __forceinline__ float mean_exact(float sum) {
+    if (CQ > 16) return __fdiv_rn(sum, (float)CQ);
+    constexpr float b = (float)CQ, r = 1.0f / (float)CQ;
+    const float q0 = __fmul_rn(sum, r);
+    const float rem = fmaf(-q0, b, sum);
+    return fmaf(rem, r, q0);
+}
+
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return r;
+}
+/* hit_word() of lbad_math.cuh as exactly two LOP3: u = (p1|m1) & ~(p1^p2) [0xA4], h = u & ~(m1^m2) [0x90] */
+__device__ __forceinline__ uint32_t hit_word2(uint32_t p1, uint32_t m1, uint32_t p2, uint32_t m2) {
+    return lop3<0x90>(lop3<0xA4>(p1, m1, p2), m1, m2);
+}
+
+/* per database subfingerprint: (float)possible and RN(1/possible) over the FULL length — what every unmasked compare needs */
+template <int W>
+__global__ void meta_kernel(const uint32_t* __restrict__ db, float2* __restrict__ meta, const uint64_t first, const uint64_t count) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t* src = db + (first + i) * 2 * W;
+        uint32_t possible = 0;
+#pragma unroll
+        for (int w = 0; w < W; w++) possible += __popc(src[w] | src[W + w]);
+        meta[first + i] = make_float2((float)possible, c_rcp[possible]);
+    }
+}
+
 /* Fast path: every clip in the database has at least CQ subfingerprints, so the clip is always fp1 (FP.m:123-131:
- * no swap when counts are equal).  For each database subfingerprint j the CQ query subfingerprints i are compared
- * and added to the running sum of offset o = j - i, held in a CQ-deep shift register; offset o completes at j = o+CQ-1. */
+ * no swap when counts are equal).  Offset-outer / query-subfingerprint-inner, exactly the reference's loop nest; the
+ * database words and their (possible, 1/possible) are warp-uniform broadcast loads, the CQ query subfingerprints
+ * live in registers. */
 template <int W, int CQ, bool MASKED>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32)
-search_fast_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ offsets, const uint32_t n_clips, const uint32_t clip_base,
-                   const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t pairs, const int k,
+search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ meta, const uint32_t* __restrict__ offsets, const uint32_t n_clips,
+                   const uint32_t clip_base, const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t pairs, const int k,
                    const uint32_t n_qgroups, const uint32_t clips_per_chunk, float* __restrict__ part_sc, uint32_t* __restrict__ part_id,
                    float* __restrict__ all_scores, const uint32_t total_warps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -86,57 +124,50 @@ search_fast_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__
         }
     const uint32_t c_begin = chunk * clips_per_chunk;
     const uint32_t c_end = min(n_clips, c_begin + clips_per_chunk);
+    float worst = top.worst();
     for (uint32_t c = c_begin; c < c_end; c++) {
         const uint32_t s0 = offsets[c], c1 = offsets[c + 1] - s0;            /* warp-uniform */
-        float acc[CQ];
-#pragma unroll
-        for (int i = 0; i < CQ; i++) acc[i] = 0.0f;
         float best = 0.0f;                                                    /* FP.m:133 */
-        const uint32_t last_off = c1 - CQ;                                    /* offsets 0..c1-CQ, FP.m:136 */
-        for (uint32_t j = 0; j < c1; j++) {
-            uint32_t p1[W], m1[W];
-            const uint32_t* src = db + ((size_t)s0 + j) * 2 * W;
-            if (W % 4 == 0) {
+        for (uint32_t o = 0; o + CQ <= c1; o++) {                             /* FP.m:136 */
+            float sum = 0.0f;
 #pragma unroll
-                for (int w = 0; w < W; w += 4) {
-                    const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + w)), b = __ldg(reinterpret_cast<const uint4*>(src + W + w));
-                    p1[w] = a.x; p1[w + 1] = a.y; p1[w + 2] = a.z; p1[w + 3] = a.w; m1[w] = b.x; m1[w + 1] = b.y; m1[w + 2] = b.z; m1[w + 3] = b.w;
+            for (int i = 0; i < CQ; i++) {                                    /* FP.m:139-142 */
+                const uint32_t* src = db + ((size_t)s0 + o + i) * 2 * W;
+                uint32_t p1[W], m1[W];
+                if (W % 4 == 0) {
+#pragma unroll
+                    for (int w = 0; w < W; w += 4) {
+                        const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + w)), b = __ldg(reinterpret_cast<const uint4*>(src + W + w));
+                        p1[w] = a.x; p1[w + 1] = a.y; p1[w + 2] = a.z; p1[w + 3] = a.w; m1[w] = b.x; m1[w + 1] = b.y; m1[w + 2] = b.z; m1[w + 3] = b.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < W; w += 2) {
+                        const uint2 a = __ldg(reinterpret_cast<const uint2*>(src + w)), b = __ldg(reinterpret_cast<const uint2*>(src + W + w));
+                        p1[w] = a.x; p1[w + 1] = a.y; m1[w] = b.x; m1[w + 1] = b.y;
+                    }
                 }
-            } else {
+                float fposs, rcp;
+                if (MASKED) {
+                    uint32_t possible = 0;
 #pragma unroll
-                for (int w = 0; w < W; w += 2) {
-                    const uint2 a = __ldg(reinterpret_cast<const uint2*>(src + w)), b = __ldg(reinterpret_cast<const uint2*>(src + W + w));
-                    p1[w] = a.x; p1[w + 1] = a.y; m1[w] = b.x; m1[w + 1] = b.y;
+                    for (int w = 0; w < W; w++) { p1[w] &= mask.w[w]; m1[w] &= mask.w[w]; possible += __popc(p1[w] | m1[w]); }   /* FP.m:159-160 */
+                    fposs = (float)possible; rcp = c_rcp[possible];
+                } else {
+                    const float2 mt = __ldg(meta + (size_t)s0 + o + i);
+                    fposs = mt.x; rcp = mt.y;
                 }
-            }
-            uint32_t possible = 0;
+                uint32_t hits = 0;
 #pragma unroll
-            for (int w = 0; w < W; w++) {
-                if (MASKED) { p1[w] &= mask.w[w]; m1[w] &= mask.w[w]; }
-                possible += __popc(p1[w] | m1[w]);                            /* FP.m:159-160, warp-uniform */
+                for (int w = 0; w < W; w++) hits += __popc(hit_word2(p1[w], m1[w], qp[i][w], qm[i][w]));   /* FP.m:162-167 */
+                sum = __fadd_rn(sum, ratio_exact(hits, fposs, rcp));
             }
-            const float fposs = (float)possible, rcp = c_rcp[possible];
-#pragma unroll
-            for (int i = 0; i < CQ; i++) {
-                /* term i of offset o = j - i; skip offsets outside [0, c1-CQ] (warp-uniform test) */
-                if (j >= (uint32_t)i && j - i <= last_off) {
-                    uint32_t hits = 0;
-#pragma unroll
-                    for (int w = 0; w < W; w++) hits += __popc(hit_word(p1[w], m1[w], qp[i][w], qm[i][w]));   /* FP.m:162-167 */
-                    acc[i] = __fadd_rn(acc[i], ratio_exact(hits, fposs, rcp));  /* FP.m:139-142, increasing i per offset */
-                }
-            }
-            if (j >= (uint32_t)(CQ - 1)) {                                     /* offset j-CQ+1 is complete */
-                const float mean = __fdiv_rn(acc[CQ - 1], (float)CQ);          /* FP.m:144 */
-                best = (best < mean) ? mean : best;                            /* Apple MAX */
-            }
-#pragma unroll
-            for (int i = CQ - 1; i > 0; i--) acc[i] = acc[i - 1];
-            acc[0] = 0.0f;
+            const float mean = mean_exact<CQ>(sum);                            /* FP.m:144 */
+            best = (best < mean) ? mean : best;                                /* Apple MAX */
         }
         if (qvalid) {
             if (all_scores) all_scores[(size_t)q * n_clips + c] = best;
-            if (best > top.worst()) top.insert(best, clip_base + c);
+            if (best > worst) { top.insert(best, clip_base + c); worst = top.worst(); }
         }
     }
     if (qvalid) for (int r = 0; r < k; r++) {
@@ -248,7 +279,7 @@ using namespace lbad;
 struct lbadcu_db {
     int device = 0; uint32_t W = 4;
     cudaStream_t stream = nullptr;
-    uint32_t* d_words = nullptr; size_t cap_subfps = 0, n_subfps = 0;
+    uint32_t* d_words = nullptr; float2* d_meta = nullptr; size_t cap_subfps = 0, n_subfps = 0; uint32_t pairs_full = 0;
     std::vector<uint32_t> h_offsets{0};
     uint32_t* d_offsets = nullptr; size_t d_offsets_cap = 0; bool offsets_dirty = true;
     uint32_t min_count = 0xffffffffu, max_count = 0, base = 0;
@@ -265,11 +296,11 @@ static int upload_rcp() {
     return LBAD_OK;
 }
 
-extern "C" int lbadcu_db_create(uint32_t W, lbadcu_db** out) {
+extern "C" int lbadcu_db_create(uint32_t W, uint32_t pairs_full, lbadcu_db** out) {
     *out = nullptr;
-    if (W != 2 && W != 4 && W != 8) return LBAD_ERR_ARG;
+    if ((W != 2 && W != 4 && W != 8) || pairs_full == 0 || pairs_full > 32 * W) return LBAD_ERR_ARG;
     if (lbadcu_device_available() != LBAD_OK) { set_error("no CUDA device available (this library has no CPU fallback)"); return LBAD_ERR_NODEVICE; }
-    lbadcu_db* db = new lbadcu_db(); db->W = W;
+    lbadcu_db* db = new lbadcu_db(); db->W = W; db->pairs_full = pairs_full;
     LBAD_CUDA_TRY(cudaGetDevice(&db->device));
     cudaDeviceProp prop; LBAD_CUDA_TRY(cudaGetDeviceProperties(&prop, db->device));
     db->sm_count = prop.multiProcessorCount; db->smem_optin = prop.sharedMemPerBlockOptin;
@@ -284,7 +315,7 @@ extern "C" void lbadcu_db_destroy(lbadcu_db* db) {
     cudaSetDevice(db->device);
     cudaStreamSynchronize(db->stream);
     db->timer.clear();
-    cudaFree(db->d_words); cudaFree(db->d_offsets); cudaFree(db->d_part_sc); cudaFree(db->d_part_id);
+    cudaFree(db->d_words); cudaFree(db->d_meta); cudaFree(db->d_offsets); cudaFree(db->d_part_sc); cudaFree(db->d_part_id);
     cudaStreamDestroy(db->stream);
     delete db;
 }
@@ -310,14 +341,25 @@ extern "C" int lbadcu_db_append(lbadcu_db* db, const uint32_t* words, int on_dev
     if (db->n_subfps + add > 0xfffffff0ull) return LBAD_ERR_ARG;
     if (db->n_subfps + add > db->cap_subfps) {
         size_t cap = std::max<size_t>(db->cap_subfps * 2, db->n_subfps + add);
-        uint32_t* nw = nullptr;
-        LBAD_CUDA_TRY(cudaMalloc(&nw, cap * 2 * db->W * sizeof(uint32_t)));
-        if (db->n_subfps) LBAD_CUDA_TRY(cudaMemcpyAsync(nw, db->d_words, db->n_subfps * 2 * db->W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, db->stream));
+        uint32_t* nw = nullptr; float2* nm = nullptr;
+        LBAD_CUDA_TRY(cudaMalloc(&nw, cap * 2 * db->W * sizeof(uint32_t))); LBAD_CUDA_TRY(cudaMalloc(&nm, cap * sizeof(float2)));
+        if (db->n_subfps) {
+            LBAD_CUDA_TRY(cudaMemcpyAsync(nw, db->d_words, db->n_subfps * 2 * db->W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, db->stream));
+            LBAD_CUDA_TRY(cudaMemcpyAsync(nm, db->d_meta, db->n_subfps * sizeof(float2), cudaMemcpyDeviceToDevice, db->stream));
+        }
         LBAD_CUDA_TRY(cudaStreamSynchronize(db->stream));
-        cudaFree(db->d_words); db->d_words = nw; db->cap_subfps = cap;
+        cudaFree(db->d_words); cudaFree(db->d_meta); db->d_words = nw; db->d_meta = nm; db->cap_subfps = cap;
     }
     if (add) LBAD_CUDA_TRY(cudaMemcpyAsync(db->d_words + db->n_subfps * 2 * db->W, words, add * 2 * db->W * sizeof(uint32_t),
                                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, db->stream));
+    if (add) {
+        const unsigned blocks = (unsigned)std::min<uint64_t>((add + 255) / 256, 4096);
+        if (db->W == 2) meta_kernel<2><<<blocks, 256, 0, db->stream>>>(db->d_words, db->d_meta, db->n_subfps, add);
+        else if (db->W == 4) meta_kernel<4><<<blocks, 256, 0, db->stream>>>(db->d_words, db->d_meta, db->n_subfps, add);
+        else meta_kernel<8><<<blocks, 256, 0, db->stream>>>(db->d_words, db->d_meta, db->n_subfps, add);
+        db->launches++;
+        LBAD_CUDA_TRY(cudaGetLastError());
+    }
     LBAD_CUDA_TRY(cudaStreamSynchronize(db->stream));
     db->h_offsets.reserve(db->h_offsets.size() + n_clips);
     for (uint32_t c = 0; c < n_clips; c++) {
@@ -345,11 +387,11 @@ static void launch_fast(lbadcu_db* db, bool masked, uint32_t blocks, size_t smem
     const uint32_t n_clips = lbadcu_db_clips(db);
     if (masked) {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        search_fast_kernel<W, CQ, true><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
+        search_fast_kernel<W, CQ, true><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
                                                                                 db->d_part_sc, db->d_part_id, d_all, total_warps);
     } else {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        search_fast_kernel<W, CQ, false><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
+        search_fast_kernel<W, CQ, false><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
                                                                                  db->d_part_sc, db->d_part_id, d_all, total_warps);
     }
 }
@@ -394,8 +436,8 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
     }
     const uint32_t total_warps = n_chunks * n_qgroups;
     const uint32_t blocks = (total_warps + SEARCH_WARPS - 1) / SEARCH_WARPS;
-    const bool fast = n_clips > 0 && db->min_count >= cq && (cq == 1 || cq == 6);
-    const bool masked = pairs < 32 * W;       /* words beyond L are zero already; a mask is only needed for a shorter range */
+    const bool fast = n_clips > 0 && db->min_count >= cq && cq >= 1 && cq <= 6;
+    const bool masked = pairs < db->pairs_full;       /* words beyond L are zero already; a mask is only needed for a shorter range */
     const size_t smem_fast = (size_t)SEARCH_WARPS * 2 * k * 32 * 4;
     const size_t smem_gen = (size_t)SEARCH_WARPS * ((size_t)2 * k * 32 + (size_t)cq * 2 * W * 32) * 4;
     if (!fast && smem_gen > db->smem_optin) return LBAD_ERR_ARG;
@@ -403,9 +445,10 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
 #define LBAD_FAST(WW, CC) launch_fast<WW, CC>(db, masked, blocks, smem_fast, s, d_q, n_q, pairs, (int)k, n_qgroups, cpc, d_all, total_warps)
 #define LBAD_GEN(WW) launch_generic<WW>(db, blocks, smem_gen, s, d_q, n_q, cq, pairs, (int)k, n_qgroups, cpc, d_all, total_warps)
     if (fast) {
-        if (W == 2) { if (cq == 1) LBAD_FAST(2, 1); else LBAD_FAST(2, 6); }
-        else if (W == 4) { if (cq == 1) LBAD_FAST(4, 1); else LBAD_FAST(4, 6); }
-        else { if (cq == 1) LBAD_FAST(8, 1); else LBAD_FAST(8, 6); }
+#define LBAD_FAST_W(WW) switch (cq) { case 1: LBAD_FAST(WW, 1); break; case 2: LBAD_FAST(WW, 2); break; case 3: LBAD_FAST(WW, 3); break; \
+                                      case 4: LBAD_FAST(WW, 4); break; case 5: LBAD_FAST(WW, 5); break; default: LBAD_FAST(WW, 6); break; }
+        if (W == 2) { LBAD_FAST_W(2) } else if (W == 4) { LBAD_FAST_W(4) } else { LBAD_FAST_W(8) }
+#undef LBAD_FAST_W
     } else {
         if (W == 2) LBAD_GEN(2); else if (W == 4) LBAD_GEN(4); else LBAD_GEN(8);
     }
