@@ -28,25 +28,24 @@ extern "C" void lbad_emulate_window(const float* win, const uint32_t* klow, cons
         }
         init = true;
     }
-    static float re[32][32], im[32][32];            /* [lane][register] */
+    static float2 z[32][32];                        /* [lane][register] */
     std::vector<float> scr(32 * SCR_LDF), vbuf(1024, 0.0f);
     const float scale_m1 = inv_pos_scale - 1.0f;
     for (int lane = 0; lane < 32; lane++) {
-        for (int n1 = 0; n1 < 32; n1++) { re[lane][n1] = win[2 * (32 * n1 + lane)]; im[lane][n1] = win[2 * (32 * n1 + lane) + 1]; }
-        fft32(re[lane], im[lane]);
+        for (int n1 = 0; n1 < 32; n1++) z[lane][n1] = make_float2(win[2 * (32 * n1 + lane)], win[2 * (32 * n1 + lane) + 1]);
+        fft32(z[lane]);
         for (int p = 0; p < 32; p += 2) {
             const float* w = tw1[(p >> 1) * 32 + lane];
-            const float a0 = re[lane][p] * w[0] - im[lane][p] * w[1], b0 = re[lane][p] * w[1] + im[lane][p] * w[0];
-            const float a1 = re[lane][p + 1] * w[2] - im[lane][p + 1] * w[3], b1 = re[lane][p + 1] * w[3] + im[lane][p + 1] * w[2];
-            re[lane][p] = a0; im[lane][p] = b0; re[lane][p + 1] = a1; im[lane][p + 1] = b1;
+            float2* zz = z[lane];
+            zz[p] = make_float2(zz[p].x * w[0] - zz[p].y * w[1], zz[p].x * w[1] + zz[p].y * w[0]);
+            zz[p + 1] = make_float2(zz[p + 1].x * w[2] - zz[p + 1].y * w[3], zz[p + 1].x * w[3] + zz[p + 1].y * w[2]);
         }
     }
     for (int comp = 0; comp < 2; comp++) {          /* one component at a time, as in the kernel */
-        float (*x)[32] = comp ? im : re;
-        for (int lane = 0; lane < 32; lane++) for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = x[lane][p];
-        for (int lane = 0; lane < 32; lane++) for (int q = 0; q < 8; q++) for (int j = 0; j < 4; j++) x[lane][4 * q + j] = scr[lane * SCR_LDF + 4 * q + j];
+        for (int lane = 0; lane < 32; lane++) for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = comp ? z[lane][p].y : z[lane][p].x;
+        for (int lane = 0; lane < 32; lane++) for (int q = 0; q < 8; q++) for (int j = 0; j < 4; j++) (comp ? z[lane][4 * q + j].y : z[lane][4 * q + j].x) = scr[lane * SCR_LDF + 4 * q + j];
     }
-    for (int lane = 0; lane < 32; lane++) fft32(re[lane], im[lane]);
+    for (int lane = 0; lane < 32; lane++) fft32(z[lane]);
     const int k2lo = (int)(kmin >> 5), k2hi = (int)((kmax - 1) >> 5);
     for (int lane = 0; lane < 32; lane++) {
         const int src_lane = (32 - lane) & 31;
@@ -56,32 +55,46 @@ extern "C" void lbad_emulate_window(const float* win, const uint32_t* klow, cons
                 for (int h = 0; h < 2; h++) {
                     const int kk = k2 + h;
                     const int p = bitrev5(kk), pp = bitrev5(31 - kk), p0 = bitrev5((32 - kk) & 31);
-                    float pr = re[src_lane][pp], pi = im[src_lane][pp];      /* __shfl_sync */
-                    if (lane == 0) { pr = re[lane][p0]; pi = im[lane][p0]; }
+                    float2 pz = z[src_lane][pp];                             /* __shfl_sync */
+                    if (lane == 0) pz = z[lane][p0];
                     float xr, xi;
-                    real_split_2x(re[lane][p], im[lane][p], pr, pi, h ? w[2] : w[0], h ? w[3] : w[1], xr, xi);
-                    if (kk == 0 && lane == 0) { xr = 2.0f * (re[lane][p] + im[lane][p]); xi = 2.0f * (re[lane][p] - im[lane][p]); }
+                    real_split_2x(z[lane][p], pz, h ? w[2] : w[0], h ? w[3] : w[1], xr, xi);
+                    if (kk == 0 && lane == 0) { xr = 2.0f * (z[lane][p].x + z[lane][p].y); xi = 2.0f * (z[lane][p].x - z[lane][p].y); }
                     if (out_spec) { out_spec[2 * (kk * 32 + lane)] = xr; out_spec[2 * (kk * 32 + lane) + 1] = xi; }
                     vbuf[kk * 32 + lane] = bin_energy(xr, xi, scale_m1);
                 }
             }
         }
     }
+    /* band sums as in the kernel: two lanes per band, halves combined by the xor-1 shuffle */
+    auto seg_sum = [&](uint32_t a, uint32_t b) {
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        for (; a + 4 <= b; a += 4) { s0 += vbuf[a]; s1 += vbuf[a + 1]; s2 += vbuf[a + 2]; s3 += vbuf[a + 3]; }
+        if (a + 2 <= b) { s0 += vbuf[a]; s1 += vbuf[a + 1]; a += 2; }
+        if (a < b) s2 += vbuf[a];
+        return (s0 + s1) + (s2 + s3);
+    };
+    float sa[32], sb[32];
     for (int lane = 0; lane < 32; lane++) {
-        float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
-        uint32_t k = klow[lane];
-        for (; k + 4 <= khigh[lane]; k += 4) { p0 += vbuf[k]; p1 += vbuf[k + 1]; p2 += vbuf[k + 2]; p3 += vbuf[k + 3]; }
-        for (; k < khigh[lane]; k++) p0 += vbuf[k];
-        out_bands[lane] = ((p0 + p1) + (p2 + p3)) / divisor[lane];
+        const int b0 = lane >> 1, b1 = 16 + (lane >> 1);
+        const uint32_t l0 = klow[b0], h0 = khigh[b0], m0 = l0 + (h0 - l0 + 1) / 2;
+        const uint32_t l1 = klow[b1], h1 = khigh[b1], m1 = l1 + (h1 - l1 + 1) / 2;
+        sa[lane] = seg_sum((lane & 1) ? m0 : l0, (lane & 1) ? h0 : m0);
+        sb[lane] = seg_sum((lane & 1) ? m1 : l1, (lane & 1) ? h1 : m1);
+    }
+    for (int lane = 0; lane < 32; lane++) {
+        const int my_band = (lane >> 1) + ((lane & 1) ? 16 : 0);
+        const float a2 = sa[lane] + sa[lane ^ 1], b2 = sb[lane] + sb[lane ^ 1];
+        out_bands[my_band] = ((lane & 1) ? b2 : a2) / divisor[my_band];
     }
 }
 
 /* bare 32-point DFT in natural order, for a direct unit test of fft32 + bitrev5 */
 extern "C" void lbad_emulate_fft32(const float* in_re, const float* in_im, float* out_re, float* out_im) {
-    float re[32], im[32];
-    memcpy(re, in_re, sizeof re); memcpy(im, in_im, sizeof im);
-    fft32(re, im);
-    for (int p = 0; p < 32; p++) { out_re[bitrev5(p)] = re[p]; out_im[bitrev5(p)] = im[p]; }
+    float2 z[32];
+    for (int i = 0; i < 32; i++) z[i] = make_float2(in_re[i], in_im[i]);
+    fft32(z);
+    for (int p = 0; p < 32; p++) { out_re[bitrev5(p)] = z[p].x; out_im[bitrev5(p)] = z[p].y; }
 }
 
 /* bin_energy against the reference's literal formulation (LBAudioDetective.m:387-401), for the unit test */

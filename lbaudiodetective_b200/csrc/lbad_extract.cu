@@ -58,15 +58,19 @@ struct SelectSmem {
     uint32_t surv_key[256];
     uint32_t surv_idx[256];              /* flat index | sign code << 16 (1: v > 0, 2: v < 0) */
     uint32_t words[16];
-    uint32_t nsurv;
-    uint32_t pad[3];
+    uint32_t nsurv, nbucket, threshold;
+    uint32_t pad[1];
 };
 
 /* Ordered top-T by |v| (stable: lower flat index first on ties) -> packed sign planes.
  * THREADS threads, each owning E consecutive flat indices [tid*E, tid*E+E); elem(idx) returns the coefficient.
- * Must be called by all threads of the CTA.  out: 2*W words (global). */
+ * Must be called by all threads of the CTA.  out: 2*W words (global).  bucket: shared scratch for THREADS*E keys.
+ *
+ * The T-th largest key (|v| as an integer) is found by bisection on its bits: the 8 exponent bits by every thread
+ * over its own keys, then — since only the keys sharing that exponent are still undecided — the 23 mantissa bits by
+ * warp 0 alone over the compacted bucket, without block-wide barriers. */
 template <int THREADS, int E, class Elem>
-__device__ __forceinline__ void select_and_pack(Elem elem, const int T, const int W, uint32_t* __restrict__ out, SelectSmem& sm) {
+__device__ __forceinline__ void select_and_pack(Elem elem, const int T, const int W, uint32_t* __restrict__ out, SelectSmem& sm, uint32_t* bucket) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t key[E];
     uint32_t pos = 0, neg = 0;           /* sign bits of my E elements (E <= 32) */
@@ -79,11 +83,11 @@ __device__ __forceinline__ void select_and_pack(Elem elem, const int T, const in
     }
     if (tid < 32) sm.counters[tid] = 0;
     if (tid < 16) sm.words[tid] = 0;
-    if (tid == 0) sm.nsurv = 0;
+    if (tid == 0) { sm.nsurv = 0; sm.nbucket = 0; }
     __syncthreads();
-    /* largest threshold with count(key >= threshold) >= T, one bit at a time */
+    /* largest exponent-aligned threshold with count(key >= threshold) >= T */
     uint32_t thr = 0;
-    for (int bit = 30; bit >= 0; --bit) {
+    for (int bit = 30; bit >= 23; --bit) {
         const uint32_t cand = thr | (1u << bit);
         uint32_t c = 0;
 #pragma unroll
@@ -93,6 +97,37 @@ __device__ __forceinline__ void select_and_pack(Elem elem, const int T, const in
         __syncthreads();
         if (sm.counters[bit] >= (uint32_t)T) thr = cand;
     }
+    /* keys in [thr, thr + 2^23) are undecided; keys above are certainly selected */
+    {
+        const uint32_t hi = thr + (1u << 23);
+        uint32_t above = 0, mine = 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) { above += key[e] >= hi; mine += (key[e] >= thr && key[e] < hi); }
+        const uint32_t wa = __reduce_add_sync(0xffffffffu, above);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        uint32_t base = 0;
+        if (lane == 31) { base = atomicAdd(&sm.nbucket, incl); if (wa) atomicAdd(&sm.counters[22], wa); }
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+        for (int e = 0; e < E; e++) if (key[e] >= thr && key[e] < hi) bucket[base++] = key[e];
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const uint32_t nb = sm.nbucket, need = (uint32_t)T - sm.counters[22];      /* rank of the threshold inside the bucket, >= 1 */
+        uint32_t t2 = thr;
+        for (int bit = 22; bit >= 0; --bit) {
+            const uint32_t cand = t2 | (1u << bit);
+            uint32_t c = 0;
+            for (uint32_t i = lane; i < nb; i += 32) c += (bucket[i] >= cand) ? 1u : 0u;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c >= need) t2 = cand;
+        }
+        if (lane == 0) sm.threshold = t2;
+    }
+    __syncthreads();
+    thr = sm.threshold;
     /* strictly greater: all survive; equal: the first (T - n_gt) in flat-index order survive */
     uint32_t ngt = 0, neq = 0;
 #pragma unroll
@@ -191,7 +226,7 @@ bands_generic_kernel(const float* __restrict__ pcm, float* __restrict__ images, 
                 xr = 2.0f * (z0.x + z0.y); xi = 2.0f * (z0.x - z0.y);
             } else {
                 const float2 zk = z[__brev(k) >> sh], zp = z[__brev(M - k) >> sh], tw = tw_n[k];   /* tw = (cos, sin) */
-                real_split_2x(zk.x, zk.y, zp.x, zp.y, tw.x, tw.y, xr, xi);
+                real_split_2x(zk, zp, tw.x, tw.y, xr, xi);
             }
             v[k] = bin_energy(xr, xi, g.inv_pos_scale - 1.0f);                         /* m:387-401 */
         }
@@ -228,12 +263,21 @@ haar_select_kernel(const float* __restrict__ images, float* __restrict__ haar_ou
         __syncthreads();
         if (haar_out) for (int i = tid; i < R * B; i += HS_THREADS) haar_out[(size_t)f * R * B + i] = a[(i / B) * LD + (i % B)];
         select_and_pack<HS_THREADS, (R * B) / HS_THREADS>([&](int idx) { return a[(idx / B) * LD + (idx % B)]; }, T, W,
-                                                          words + (size_t)f * 2 * W, sel);
+                                                          words + (size_t)f * 2 * W, sel, reinterpret_cast<uint32_t*>(tmp));
         __syncthreads();
     }
 }
 
 /* -------------------------------------------------------------------------------------------- fused path ---- */
+
+/* sum of v[a..b) with four interleaved partial sums */
+__device__ __forceinline__ float seg_sum(const float* __restrict__ v, uint32_t a, const uint32_t b) {
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    for (; a + 4 <= b; a += 4) { s0 += v[a]; s1 += v[a + 1]; s2 += v[a + 2]; s3 += v[a + 3]; }
+    if (a + 2 <= b) { s0 += v[a]; s1 += v[a + 1]; a += 2; }
+    if (a < b) s2 += v[a];
+    return (s0 + s1) + (s2 + s3);
+}
 
 constexpr int FUSED_WARPS = 8;
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;
@@ -281,8 +325,17 @@ extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words
     if (tid == 0 && use_tma) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
 
-    const uint32_t klow = bt.klow[lane], khigh = bt.khigh[lane];
-    const float divisor = bt.divisor[lane];
+    /* round 0 covers bands 0..15, round 1 bands 16..31; lanes 2b and 2b+1 split band b (resp. 16+b) in halves */
+    uint32_t ra0, rb0, ra1, rb1;
+    {
+        const int b0 = lane >> 1, b1 = 16 + (lane >> 1);
+        const uint32_t l0 = bt.klow[b0], h0 = bt.khigh[b0], m0 = l0 + (h0 - l0 + 1) / 2;
+        const uint32_t l1 = bt.klow[b1], h1 = bt.khigh[b1], m1 = l1 + (h1 - l1 + 1) / 2;
+        ra0 = (lane & 1) ? m0 : l0; rb0 = (lane & 1) ? h0 : m0;
+        ra1 = (lane & 1) ? m1 : l1; rb1 = (lane & 1) ? h1 : m1;
+    }
+    const int my_band = (lane >> 1) + ((lane & 1) ? 16 : 0);
+    const float divisor = bt.divisor[my_band];
     const int k2lo = STATIC_RANGE ? 2 : (int)(g.kmin >> 5), k2hi = STATIC_RANGE ? 23 : (int)((g.kmax - 1) >> 5);
     const uint32_t hop = g.stride;
     const uint32_t bytes = span_floats * 4;
@@ -309,39 +362,36 @@ extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words
         for (int it = 0; it < (int)LBAD_ROWS_PER_FRAME / FUSED_WARPS; ++it) {
             const int row = it * FUSED_WARPS + wid;
             const float* win = samples + (size_t)row * hop;
-            float re[32], im[32];
+            float2 z[32];
 #pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) {                                   /* vDSP_ctoz (m:353): z[n] = x[2n] + i x[2n+1] */
-                const float2 t = *reinterpret_cast<const float2*>(win + 2 * (32 * n1 + lane));
-                re[n1] = t.x; im[n1] = t.y;
-            }
-            fft32(re, im);                                                      /* over n1; position p holds k1 = bitrev5(p) */
+            for (int n1 = 0; n1 < 32; n1++)                                     /* vDSP_ctoz (m:353): z[n] = x[2n] + i x[2n+1] */
+                z[n1] = *reinterpret_cast<const float2*>(win + 2 * (32 * n1 + lane));
+            fft32(z);                                                           /* over n1; position p holds k1 = bitrev5(p) */
 #pragma unroll
             for (int p = 0; p < 32; p += 2) {                                   /* x exp(-2 pi i lane k1 / 1024) */
                 const float4 w = tw1[(p >> 1) * 32 + lane];
-                const float a0 = re[p] * w.x - im[p] * w.y, b0 = re[p] * w.y + im[p] * w.x;
-                const float a1 = re[p + 1] * w.z - im[p + 1] * w.w, b1 = re[p + 1] * w.w + im[p + 1] * w.z;
-                re[p] = a0; im[p] = b0; re[p + 1] = a1; im[p + 1] = b1;
+                z[p] = make_float2(z[p].x * w.x - z[p].y * w.y, z[p].x * w.y + z[p].y * w.x);
+                z[p + 1] = make_float2(z[p + 1].x * w.z - z[p + 1].y * w.w, z[p + 1].x * w.w + z[p + 1].y * w.z);
             }
             /* 32x32 transpose through shared memory, one component at a time: lane k1 ends up with A[n2][k1], n2 = 0..31 */
 #pragma unroll
-            for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = re[p];
+            for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = z[p].x;
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const float4 t = *reinterpret_cast<const float4*>(&scr[lane * SCR_LDF + 4 * q]);
-                re[4 * q] = t.x; re[4 * q + 1] = t.y; re[4 * q + 2] = t.z; re[4 * q + 3] = t.w;
+                z[4 * q].x = t.x; z[4 * q + 1].x = t.y; z[4 * q + 2].x = t.z; z[4 * q + 3].x = t.w;
             }
             __syncwarp();
 #pragma unroll
-            for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = im[p];
+            for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = z[p].y;
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const float4 t = *reinterpret_cast<const float4*>(&scr[lane * SCR_LDF + 4 * q]);
-                im[4 * q] = t.x; im[4 * q + 1] = t.y; im[4 * q + 2] = t.z; im[4 * q + 3] = t.w;
+                z[4 * q].y = t.x; z[4 * q + 1].y = t.y; z[4 * q + 2].y = t.z; z[4 * q + 3].y = t.w;
             }
-            fft32(re, im);                                                      /* over n2; position p holds Z[lane + 32 bitrev5(p)] */
+            fft32(z);                                                           /* over n2; position p holds Z[lane + 32 bitrev5(p)] */
             __syncwarp();                                                       /* scratch is about to be reused as vbuf */
             const int src_lane = (32 - lane) & 31;
 #pragma unroll
@@ -352,22 +402,23 @@ extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words
                     for (int h = 0; h < 2; h++) {
                         const int kk = k2 + h;
                         const int p = bitrev5(kk), pp = bitrev5(31 - kk), p0 = bitrev5((32 - kk) & 31);
-                        float pr = __shfl_sync(0xffffffffu, re[pp], src_lane);  /* Z[1024 - k] lives in lane 32-lane, k2' = 31-k2 */
-                        float pi = __shfl_sync(0xffffffffu, im[pp], src_lane);
-                        if (lane == 0) { pr = re[p0]; pi = im[p0]; }            /* ... except lane 0: own register k2' = 32-k2 */
+                        float2 pz;                                              /* Z[1024 - k] lives in lane 32-lane, k2' = 31-k2 */
+                        pz.x = __shfl_sync(0xffffffffu, z[pp].x, src_lane);
+                        pz.y = __shfl_sync(0xffffffffu, z[pp].y, src_lane);
+                        if (lane == 0) pz = z[p0];                              /* ... except lane 0: own register k2' = 32-k2 */
                         float xr, xi;
-                        real_split_2x(re[p], im[p], pr, pi, h ? w.z : w.x, h ? w.w : w.y, xr, xi);
-                        if (kk == 0 && lane == 0) { xr = 2.0f * (re[p] + im[p]); xi = 2.0f * (re[p] - im[p]); }   /* DC / packed Nyquist */
+                        real_split_2x(z[p], pz, h ? w.z : w.x, h ? w.w : w.y, xr, xi);
+                        if (kk == 0 && lane == 0) { xr = 2.0f * (z[p].x + z[p].y); xi = 2.0f * (z[p].x - z[p].y); }   /* DC / packed Nyquist */
                         vbuf[kk * 32 + lane] = bin_energy(xr, xi, scale_m1);
                     }
                 }
             }
             __syncwarp();
-            float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;                   /* lane = band; m:379-405 (4 interleaved partial sums) */
-            uint32_t k = klow;
-            for (; k + 4 <= khigh; k += 4) { p0 += vbuf[k]; p1 += vbuf[k + 1]; p2 += vbuf[k + 2]; p3 += vbuf[k + 3]; }
-            for (; k < khigh; k++) p0 += vbuf[k];
-            img[row * FUSED_LD + lane] = __fdiv_rn((p0 + p1) + (p2 + p3), divisor);
+            /* band sums, m:379-405: two lanes per band (each sums half of the band's bins), 16 bands per round */
+            float sa = seg_sum(vbuf, ra0, rb0), sb = seg_sum(vbuf, ra1, rb1);
+            sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+            sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+            img[row * FUSED_LD + my_band] = __fdiv_rn((lane & 1) ? sb : sa, divisor);     /* even lane: band lane/2, odd lane: band 16 + lane/2 */
             __syncwarp();
         }
         __syncthreads();                                                        /* image complete; samples free */
@@ -433,7 +484,8 @@ extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words
         }
         /* ---- ordered top-T -> packed words, Frame.m:165-191 ---- */
         select_and_pack<FUSED_THREADS, 16>([&](int idx) { return img[(idx >> 5) * FUSED_LD + (idx & 31)]; }, (int)g.pairs,
-                                           (int)g.words_per_plane, words + (size_t)f * 2 * g.words_per_plane, sel);
+                                           (int)g.words_per_plane, words + (size_t)f * 2 * g.words_per_plane, sel,
+                                           reinterpret_cast<uint32_t*>(smem + L.off_scratch));      /* transpose scratch is idle in the tail */
         __syncthreads();
     }
 }

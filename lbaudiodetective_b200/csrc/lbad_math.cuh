@@ -40,47 +40,73 @@ LBAD_HD constexpr float cos32(int m) {
 }
 LBAD_HD constexpr float sin32(int m) { return m <= 8 ? cos32(8 - m) : cos32(m - 8); }
 
-/* one radix-2 DIF butterfly of a 32-point transform: half-span H, block start S, offset J within the half-block */
+#if !defined(__CUDACC__)
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#endif
+
+/* Packed FP32x2 arithmetic: on sm_100a one FADD2 / FFMA2 instruction per (re, im) pair — half the issue slots of the
+ * scalar form, same IEEE result per component; on the host (lane emulator) plain component-wise code. */
+LBAD_HD float2 add2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+LBAD_HD float2 fma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+
+/* one radix-2 DIF butterfly of a 32-point transform: half-span H, block start S, offset J within the half-block.
+ * z[] holds (re, im) pairs; the sum (and the difference when its twiddle is 1) is one packed instruction. */
 template <int H, int S, int J>
-LBAD_HD void fft32_butterfly(float (&re)[32], float (&im)[32]) {
+LBAD_HD void fft32_butterfly(float2 (&z)[32], const float2 neg1) {
     constexpr int a = S + J, b = S + J + H;
     constexpr int m = J * (16 / H);              /* twiddle exp(-2 pi i m / 32), 0 <= m < 16 */
     constexpr float kS2 = 0.70710678118654752f;
-    const float ar = re[a], ai = im[a], br = re[b], bi = im[b];
-    re[a] = ar + br; im[a] = ai + bi;
-    const float dr = ar - br, di = ai - bi;
-    if constexpr (m == 0)       { re[b] = dr; im[b] = di; }
-    else if constexpr (m == 8)  { re[b] = di; im[b] = -dr; }                               /* x (-i) */
-    else if constexpr (m == 4)  { re[b] = (dr + di) * kS2; im[b] = (di - dr) * kS2; }      /* x (1-i)/sqrt2 */
-    else if constexpr (m == 12) { re[b] = (di - dr) * kS2; im[b] = (dr + di) * (-kS2); }   /* x (-1-i)/sqrt2 */
+    const float2 za = z[a], zb = z[b];
+    z[a] = add2(za, zb);
+    if constexpr (m == 0) { z[b] = fma2(zb, neg1, za); }                                    /* za - zb, exactly */
     else {
-        constexpr float c = cos32(m), s = sin32(m);                                        /* x (c - i s) */
-        re[b] = dr * c + di * s;
-        im[b] = di * c - dr * s;
+        const float dr = za.x - zb.x, di = za.y - zb.y;
+        if constexpr (m == 8)       { z[b] = make_float2(di, -dr); }                                         /* x (-i) */
+        else if constexpr (m == 4)  { z[b] = make_float2((dr + di) * kS2, (di - dr) * kS2); }                /* x (1-i)/sqrt2 */
+        else if constexpr (m == 12) { z[b] = make_float2((di - dr) * kS2, (dr + di) * (-kS2)); }             /* x (-1-i)/sqrt2 */
+        else {
+            constexpr float c = cos32(m), s = sin32(m);                                                      /* x (c - i s) */
+            z[b] = make_float2(dr * c + di * s, di * c - dr * s);
+        }
     }
 }
 
 template <int H, int... I>
-LBAD_HD void fft32_stage(float (&re)[32], float (&im)[32], std::integer_sequence<int, I...>) {
-    (fft32_butterfly<H, (I / H) * 2 * H, I % H>(re, im), ...);
+LBAD_HD void fft32_stage(float2 (&z)[32], const float2 neg1, std::integer_sequence<int, I...>) {
+    (fft32_butterfly<H, (I / H) * 2 * H, I % H>(z, neg1), ...);
 }
 
 /* in-place forward 32-point DFT (e^{-i theta}); output index of register position p is bitrev5(p) */
-LBAD_HD void fft32(float (&re)[32], float (&im)[32]) {
+LBAD_HD void fft32(float2 (&z)[32]) {
+    const float2 neg1 = make_float2(-1.0f, -1.0f);
     using seq = std::make_integer_sequence<int, 16>;
-    fft32_stage<16>(re, im, seq{});
-    fft32_stage<8>(re, im, seq{});
-    fft32_stage<4>(re, im, seq{});
-    fft32_stage<2>(re, im, seq{});
-    fft32_stage<1>(re, im, seq{});
+    fft32_stage<16>(z, neg1, seq{});
+    fft32_stage<8>(z, neg1, seq{});
+    fft32_stage<4>(z, neg1, seq{});
+    fft32_stage<2>(z, neg1, seq{});
+    fft32_stage<1>(z, neg1, seq{});
 }
 
-/* 2 X[k] from Z[k] = (zr, zi) and Z[M-k] = (pr, pi), with w = exp(-2 pi i k / N) = (c, -s) given as c, s */
-LBAD_HD void real_split_2x(float zr, float zi, float pr, float pi, float c, float s, float& xr, float& xi) {
-    const float er = zr + pr, ei = zi - pi;      /* Z + conj Z' */
-    const float dr = zr - pr, di = zi + pi;      /* Z - conj Z' */
-    xr = fmaf(c, di, fmaf(-s, dr, er));          /* -i w d = (-s dr + c di) + i (-c dr - s di) */
-    xi = fmaf(-s, di, fmaf(-c, dr, ei));
+/* 2 X[k] from Z[k] = z and Z[M-k] = p, with w = exp(-2 pi i k / N) = (c, -s) given as c, s */
+LBAD_HD void real_split_2x(float2 z, float2 p, float c, float s, float& xr, float& xi) {
+    const float2 e = fma2(p, make_float2(1.0f, -1.0f), z);     /* Z + conj Z' */
+    const float2 d = fma2(p, make_float2(-1.0f, 1.0f), z);     /* Z - conj Z' */
+    xr = fmaf(c, d.y, fmaf(-s, d.x, e.x));                     /* -i w d = (-s dr + c di) + i (-c dr - s di) */
+    xi = fmaf(-s, d.y, fmaf(-c, d.x, e.y));
 }
 
 /* LBAudioDetective.m:387-401 for one bin: positive parts only are divided by pos_scale, then re^2 + im^2; a
