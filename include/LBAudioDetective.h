@@ -97,16 +97,18 @@ LBAD_API OSStatus LBAudioDetectiveProcessPCMBatch(LBAudioDetectiveRef inDetectiv
 LBAD_API OSStatus LBAudioDetectiveProcessPCMBatchDevice(LBAudioDetectiveRef inDetective, const Float32* inDeviceSamples, UInt32 inNumberOfClips, UInt64 inFramesPerClip, UInt64 inClipStride, UInt32* outDeviceWords, void* inStream);
 /* Stage dump for parity tests, one clip from host memory: outImages / outHaar are [subfp][128][B] floats (spectral
  * images before / after the Haar transform), outBooleans is [subfp][L]; any may be NULL.  inUseFusedKernel selects
- * the fused fast path (only valid for window 2048 / 32 pitch steps) or the generic two-kernel path. */
+ * the register-FFT fast path (only valid for window 2048 / 32 pitch steps) or the generic shared-memory-FFT path. */
 LBAD_API OSStatus LBAudioDetectiveProcessPCMStages(LBAudioDetectiveRef inDetective, const Float32* inSamples, UInt64 inNumberFrames, Float32* outImages, Float32* outHaar, Boolean* outBooleans, Boolean inUseFusedKernel);
 /* Haar transform (Frame.m:113-153) + ordered top-t sign extraction (Frame.m:165-191) of inCount host images
  * [128][B]; outHaar [inCount][128][B] and outBooleans [inCount][L] may be NULL. */
 LBAD_API OSStatus LBAudioDetectiveTransformImages(LBAudioDetectiveRef inDetective, const Float32* inImages, UInt32 inCount, Float32* outHaar, Boolean* outBooleans);
 /* Kernels launched by this detective since creation (for bench.py's gpu_launches). */
 LBAD_API UInt64 LBAudioDetectiveGetKernelLaunchCount(LBAudioDetectiveRef inDetective);
-/* Average device time in ms of the dominant extraction kernel over the launches since the last call with
- * inReset != 0 (CUDA events on the launching stream); returns the number of launches measured. */
+/* Total device time in ms of the dominant extraction kernel (FFT + band energies) over the launches since the last
+ * call with inReset != 0 (CUDA events on the launching stream); returns the number of launches measured. */
 LBAD_API UInt32 LBAudioDetectiveGetKernelTiming(LBAudioDetectiveRef inDetective, Boolean inEnable, Boolean inReset, Float64* outTotalMilliseconds);
+/* Same for the second kernel of the path (Haar transform + ordered top-t + packing). */
+LBAD_API UInt32 LBAudioDetectiveGetTransformKernelTiming(LBAudioDetectiveRef inDetective, Boolean inEnable, Boolean inReset, Float64* outTotalMilliseconds);
 
 LBAD_EXTERN_C_END
 #endif

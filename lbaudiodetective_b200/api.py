@@ -68,6 +68,7 @@ def load_library(build_if_missing: bool = True):
         "LBAudioDetectiveTransformImages": (C.c_int32, [vp, vp, u32, vp, vp]),
         "LBAudioDetectiveGetKernelLaunchCount": (u64, [vp]),
         "LBAudioDetectiveGetKernelTiming": (u32, [vp, u8, u8, P(f64)]),
+        "LBAudioDetectiveGetTransformKernelTiming": (u32, [vp, u8, u8, P(f64)]),
         "LBAudioDetectiveFingerprintNew": (vp, [u32]),
         "LBAudioDetectiveFingerprintDispose": (None, [vp]),
         "LBAudioDetectiveFingerprintCopy": (vp, [vp]),
@@ -344,9 +345,11 @@ class Detective:
     def kernel_launches(self):
         return int(self._L.LBAudioDetectiveGetKernelLaunchCount(self.ref))
 
-    def kernel_timing(self, enable=True, reset=True):
+    def kernel_timing(self, enable=True, reset=True, transform=False):
+        """(launches, total ms) of the FFT + band-energy kernel, or of the Haar/select/pack kernel with transform=True."""
         ms = C.c_double(0.0)
-        n = self._L.LBAudioDetectiveGetKernelTiming(self.ref, 1 if enable else 0, 1 if reset else 0, C.byref(ms))
+        fn = self._L.LBAudioDetectiveGetTransformKernelTiming if transform else self._L.LBAudioDetectiveGetKernelTiming
+        n = fn(self.ref, 1 if enable else 0, 1 if reset else 0, C.byref(ms))
         return int(n), float(ms.value)
 
 

@@ -279,5 +279,11 @@ UInt64 LBAudioDetectiveGetKernelLaunchCount(LBAudioDetectiveRef d) {
 UInt32 LBAudioDetectiveGetKernelTiming(LBAudioDetectiveRef d, Boolean inEnable, Boolean inReset, Float64* outTotalMilliseconds) {
     if (outTotalMilliseconds) *outTotalMilliseconds = 0.0;
     if (!d || ensure_plan(d) != noErr) return 0;
-    return lbadcu_plan_timing(d->plan, inEnable, inReset, outTotalMilliseconds);
+    return lbadcu_plan_timing(d->plan, 0, inEnable, inReset, outTotalMilliseconds);
+}
+
+UInt32 LBAudioDetectiveGetTransformKernelTiming(LBAudioDetectiveRef d, Boolean inEnable, Boolean inReset, Float64* outTotalMilliseconds) {
+    if (outTotalMilliseconds) *outTotalMilliseconds = 0.0;
+    if (!d || ensure_plan(d) != noErr) return 0;
+    return lbadcu_plan_timing(d->plan, 1, inEnable, inReset, outTotalMilliseconds);
 }

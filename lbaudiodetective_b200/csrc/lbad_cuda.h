@@ -45,7 +45,8 @@ void lbadcu_plan_destroy(lbadcu_plan* p);
 int  lbadcu_plan_fused_supported(const lbadcu_plan* p);
 void* lbadcu_plan_stream(lbadcu_plan* p);
 uint64_t lbadcu_plan_launches(const lbadcu_plan* p);
-uint32_t lbadcu_plan_timing(lbadcu_plan* p, int enable, int reset, double* total_ms);
+/* which = 0: FFT + band-energy kernel (the dominant one), 1: Haar / select / pack kernel */
+uint32_t lbadcu_plan_timing(lbadcu_plan* p, int which, int enable, int reset, double* total_ms);
 
 /* Extraction over DEVICE-resident PCM.  Clip c starts at d_pcm + c*clip_stride and has clip_len samples; every
  * clip yields frames = ((clip_len - N)/hop)/128 subfingerprints.  d_words: [clip][frame][2*W].

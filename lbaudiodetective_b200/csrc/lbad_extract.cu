@@ -279,6 +279,18 @@ __device__ __forceinline__ float seg_sum(const float* __restrict__ v, uint32_t a
     return (s0 + s1) + (s2 + s3);
 }
 
+/* same sum with a compile-time bound on the length: fully unrolled, predicated, no loop-carried control flow */
+template <int L>
+__device__ __forceinline__ float seg_sum_static(const float* __restrict__ v, const uint32_t a, const uint32_t len) {
+    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        if ((uint32_t)i < len) { if (i & 1) s1 += v[a + i]; else s0 += v[a + i]; }
+    }
+    return s0 + s1;
+}
+constexpr int STATIC_HALF0 = 9, STATIC_HALF1 = 25;     /* longest half-band of bands 0..15 / 16..31 in the reference-default table */
+
 constexpr int FUSED_WARPS = 8;
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;
 constexpr int FUSED_LD = 33;                 /* image row stride (floats) */
@@ -286,7 +298,7 @@ constexpr int SCR_LDF = 36;                  /* transpose scratch row stride (fl
 
 struct FusedSmemLayout {
     uint32_t samples_bytes, total_bytes;
-    uint32_t off_scratch, off_tw1, off_tw2, off_img, off_sel, off_bar;
+    uint32_t off_scratch, off_tw1, off_tw2, off_bar;
 };
 static FusedSmemLayout fused_layout(uint32_t span_floats) {
     FusedSmemLayout L;
@@ -295,8 +307,6 @@ static FusedSmemLayout fused_layout(uint32_t span_floats) {
     L.off_scratch = o; o += FUSED_WARPS * 32 * SCR_LDF * 4;      /* one float component at a time: 4.5 KB per warp */
     L.off_tw1 = o;     o += 32 * 32 * 8;
     L.off_tw2 = o;     o += 32 * 32 * 8;
-    L.off_img = o;     o += LBAD_ROWS_PER_FRAME * FUSED_LD * 4;
-    L.off_sel = o;     o += (sizeof(SelectSmem) + 15) & ~15u;
     L.off_bar = o;     o += 16;
     L.total_bytes = o;
     return L;
@@ -306,16 +316,13 @@ static FusedSmemLayout fused_layout(uint32_t span_floats) {
  * real split are k2 = 2..23 at compile time; otherwise the range is a (warp-uniform) run-time value. */
 template <bool STATIC_RANGE>
 __global__ void __launch_bounds__(FUSED_THREADS, 2)
-extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words, float* __restrict__ images_out,
-                     float* __restrict__ haar_out, const float4* __restrict__ g_tw1, const float4* __restrict__ g_tw2,
-                     const Geo g, const BandTable bt, const FusedSmemLayout L, const uint32_t span_floats,
-                     const uint32_t total_frames, const int use_tma) {
+bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, const float4* __restrict__ g_tw1, const float4* __restrict__ g_tw2,
+                   const Geo g, const BandTable bt, const FusedSmemLayout L, const uint32_t span_floats,
+                   const uint32_t total_frames, const int use_tma, const uint32_t frame0) {
     extern __shared__ __align__(128) unsigned char smem[];
     float*  samples = reinterpret_cast<float*>(smem);
     float4* tw1 = reinterpret_cast<float4*>(smem + L.off_tw1);     /* [p/2][lane]: twiddles of register positions p, p+1 */
     float4* tw2 = reinterpret_cast<float4*>(smem + L.off_tw2);     /* [k2/2][lane]: (cos, sin) of bins lane+32k2, lane+32(k2+1) */
-    float*  img = reinterpret_cast<float*>(smem + L.off_img);
-    SelectSmem& sel = *reinterpret_cast<SelectSmem*>(smem + L.off_sel);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     float* scr = reinterpret_cast<float*>(smem + L.off_scratch) + wid * (32 * SCR_LDF);
@@ -341,14 +348,14 @@ extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words
     const uint32_t bytes = span_floats * 4;
     const float scale_m1 = g.inv_pos_scale - 1.0f;
 
-    auto frame_src = [&](uint32_t f) -> const float* {
+    auto frame_src = [&](uint32_t fl) -> const float* {                        /* fl: frame index inside this launch's slab */
+        const uint32_t f = frame0 + fl;
         const uint32_t clip = f / g.frames_per_clip, fr = f % g.frames_per_clip;
         return pcm + (uint64_t)clip * g.clip_stride + (uint64_t)fr * LBAD_ROWS_PER_FRAME * hop;   /* m:262-290 */
     };
 
     uint32_t f = blockIdx.x, parity = 0;
     if (f < total_frames && use_tma && tid == 0) { mbar_arrive_expect_tx(bar, bytes); bulk_copy_g2s(samples, frame_src(f), bytes, bar); }
-
     for (; f < total_frames; f += gridDim.x) {
         if (use_tma) { mbar_wait(bar, parity); parity ^= 1; }
         else {
@@ -415,64 +422,91 @@ extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words
             }
             __syncwarp();
             /* band sums, m:379-405: two lanes per band (each sums half of the band's bins), 16 bands per round */
-            float sa = seg_sum(vbuf, ra0, rb0), sb = seg_sum(vbuf, ra1, rb1);
+            float sa, sb;
+            if (STATIC_RANGE) { sa = seg_sum_static<STATIC_HALF0>(vbuf, ra0, rb0 - ra0); sb = seg_sum_static<STATIC_HALF1>(vbuf, ra1, rb1 - ra1); }
+            else              { sa = seg_sum(vbuf, ra0, rb0); sb = seg_sum(vbuf, ra1, rb1); }
             sa += __shfl_xor_sync(0xffffffffu, sa, 1);
             sb += __shfl_xor_sync(0xffffffffu, sb, 1);
-            img[row * FUSED_LD + my_band] = __fdiv_rn((lane & 1) ? sb : sa, divisor);     /* even lane: band lane/2, odd lane: band 16 + lane/2 */
+            /* even lane: band lane/2, odd lane: band 16 + lane/2; the 32 lanes fill one 128-byte line of the image row */
+            images[((size_t)f * LBAD_ROWS_PER_FRAME + row) * 32 + my_band] = __fdiv_rn((lane & 1) ? sb : sa, divisor);
             __syncwarp();
         }
-        __syncthreads();                                                        /* image complete; samples free */
-
+        __syncthreads();                                                        /* every warp is done with the samples */
         const uint32_t fnext = f + gridDim.x;
-        if (use_tma && tid == 0 && fnext < total_frames) {                      /* next frame's load overlaps the tail */
-            mbar_arrive_expect_tx(bar, bytes); bulk_copy_g2s(samples, frame_src(fnext), bytes, bar);
-        }
-        if (images_out) {
-            float* o = images_out + (size_t)f * LBAD_ROWS_PER_FRAME * 32;
-            for (int i = tid; i < (int)LBAD_ROWS_PER_FRAME * 32; i += FUSED_THREADS) o[i] = img[(i >> 5) * FUSED_LD + (i & 31)];
-            __syncthreads();
-        }
+        if (use_tma && tid == 0 && fnext < total_frames) { mbar_arrive_expect_tx(bar, bytes); bulk_copy_g2s(samples, frame_src(fnext), bytes, bar); }
+    }
+}
 
+/* One CTA per spectral image (128 x 32): Haar rows + columns (Frame.m:113-153), ordered top-T and packing (Frame.m:165-191)
+ * entirely in shared memory.  Small footprint (about 19 KB), so several CTAs share an SM and hide each other's barriers. */
+constexpr int HS32_THREADS = 256;
+constexpr int HS32_LD = 33;
+
+/* x / c for a compile-time constant c with r = RN(1/c): multiply + two FMAs give the IEEE quotient for every finite x with
+ * |x| >= 2^-100 or x == 0 (exhaustively checked on the host for c = sqrtf(2), sqrtf(32), sqrtf(128)); the rare rest divides. */
+__device__ __forceinline__ float div_const(const float x, const float c, const float r) {
+    const float q0 = __fmul_rn(x, r);
+    const float q = fmaf(fmaf(-q0, c, x), r, q0);
+    const float ax = fabsf(x);
+    return ((ax >= 7.9e-31f && ax <= 1.0e37f) || ax == 0.0f) ? q : __fdiv_rn(x, c);
+}
+
+__global__ void __launch_bounds__(HS32_THREADS, 3)
+haar_select32_kernel(const float* __restrict__ images, float* __restrict__ haar_out, uint32_t* __restrict__ words,
+                     const int T, const int W, const uint32_t total_frames) {
+    __shared__ __align__(16) float img[LBAD_ROWS_PER_FRAME * HS32_LD];
+    __shared__ SelectSmem sel;
+    const int tid = threadIdx.x;
+    const float s2 = sqrtf(2.0f), s32 = sqrtf(32.0f), s128 = sqrtf(128.0f);
+    const float r2 = 1.0f / s2, r32 = 1.0f / s32, r128 = 1.0f / s128;
+    for (uint32_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
+        const float4* src = reinterpret_cast<const float4*>(images + (size_t)f * LBAD_ROWS_PER_FRAME * 32);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {                                           /* 1024 float4 = one image */
+            const int i = tid + HS32_THREADS * j;
+            const float4 v = __ldg(src + i);
+            float* d = img + (i >> 3) * HS32_LD + (i & 7) * 4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        __syncthreads();
         /* ---- Haar rows (length 32), Frame.m:114-116 + 134-153; thread = row ---- */
         if (tid < (int)LBAD_ROWS_PER_FRAME) {
             float a[32], t[32];
-            const float s32 = sqrtf(32.0f), s2 = sqrtf(2.0f), s128 = sqrtf(128.0f);
 #pragma unroll
-            for (int c = 0; c < 32; c++) a[c] = __fdiv_rn(img[tid * FUSED_LD + c], s32);
+            for (int c = 0; c < 32; c++) a[c] = div_const(img[tid * HS32_LD + c], s32, r32);
 #pragma unroll
             for (int n = 16; n >= 1; n >>= 1) {
 #pragma unroll
                 for (int i = 0; i < n; i++) {
-                    t[i] = __fdiv_rn(__fadd_rn(a[2 * i], a[2 * i + 1]), s2);
-                    t[n + i] = __fdiv_rn(__fsub_rn(a[2 * i], a[2 * i + 1]), s2);
+                    t[i] = div_const(__fadd_rn(a[2 * i], a[2 * i + 1]), s2, r2);
+                    t[n + i] = div_const(__fsub_rn(a[2 * i], a[2 * i + 1]), s2, r2);
                 }
 #pragma unroll
                 for (int i = 0; i < 2 * n; i++) a[i] = t[i];
             }
             /* the column pass starts by dividing every element by sqrtf(128) (Frame.m:137-139): fold it into the write-back */
 #pragma unroll
-            for (int c = 0; c < 32; c++) img[tid * FUSED_LD + c] = __fdiv_rn(a[c], s128);
+            for (int c = 0; c < 32; c++) img[tid * HS32_LD + c] = div_const(a[c], s128, r128);
         }
         __syncthreads();
         /* ---- Haar columns (length 128), Frame.m:118-131; each level: read pairs, barrier, write ---- */
         {
-            const float s2 = sqrtf(2.0f);
             const int c = tid & 31, i0 = tid >> 5;
 #pragma unroll 1
             for (int n = 64; n >= 1; n >>= 1) {
                 float x0[8], x1[8];
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
-                    const int i = i0 + FUSED_WARPS * q;
-                    if (i < n) { x0[q] = img[(2 * i) * FUSED_LD + c]; x1[q] = img[(2 * i + 1) * FUSED_LD + c]; }
+                    const int i = i0 + 8 * q;
+                    if (i < n) { x0[q] = img[(2 * i) * HS32_LD + c]; x1[q] = img[(2 * i + 1) * HS32_LD + c]; }
                 }
                 __syncthreads();
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
-                    const int i = i0 + FUSED_WARPS * q;
+                    const int i = i0 + 8 * q;
                     if (i < n) {
-                        img[i * FUSED_LD + c] = __fdiv_rn(__fadd_rn(x0[q], x1[q]), s2);
-                        img[(n + i) * FUSED_LD + c] = __fdiv_rn(__fsub_rn(x0[q], x1[q]), s2);
+                        img[i * HS32_LD + c] = div_const(__fadd_rn(x0[q], x1[q]), s2, r2);
+                        img[(n + i) * HS32_LD + c] = div_const(__fsub_rn(x0[q], x1[q]), s2, r2);
                     }
                 }
                 __syncthreads();
@@ -480,12 +514,11 @@ extract_fused_kernel(const float* __restrict__ pcm, uint32_t* __restrict__ words
         }
         if (haar_out) {
             float* o = haar_out + (size_t)f * LBAD_ROWS_PER_FRAME * 32;
-            for (int i = tid; i < (int)LBAD_ROWS_PER_FRAME * 32; i += FUSED_THREADS) o[i] = img[(i >> 5) * FUSED_LD + (i & 31)];
+            for (int i = tid; i < (int)LBAD_ROWS_PER_FRAME * 32; i += HS32_THREADS) o[i] = img[(i >> 5) * HS32_LD + (i & 31)];
         }
-        /* ---- ordered top-T -> packed words, Frame.m:165-191 ---- */
-        select_and_pack<FUSED_THREADS, 16>([&](int idx) { return img[(idx >> 5) * FUSED_LD + (idx & 31)]; }, (int)g.pairs,
-                                           (int)g.words_per_plane, words + (size_t)f * 2 * g.words_per_plane, sel,
-                                           reinterpret_cast<uint32_t*>(smem + L.off_scratch));      /* transpose scratch is idle in the tail */
+        /* ---- ordered top-T -> packed words, Frame.m:165-191; once the keys are in registers the image doubles as the bucket ---- */
+        select_and_pack<HS32_THREADS, 16>([&](int idx) { return img[(idx >> 5) * HS32_LD + (idx & 31)]; }, T, W,
+                                          words + (size_t)f * 2 * W, sel, reinterpret_cast<uint32_t*>(img));
         __syncthreads();
     }
 }
@@ -509,7 +542,7 @@ struct lbadcu_plan {
     size_t chunk_pcm_floats = 0, chunk_words = 0;
     bool fused_ok = false; int sm_count = 0; size_t smem_optin = 0;
     uint64_t launches = 0;
-    LaunchTimer timer;
+    LaunchTimer timer, timer2;      /* FFT+bands kernel / Haar+select kernel */
     int stage_mode = -1;      /* -1 auto, 0 plain loads, 1 TMA (env LBAD_STAGE=ldg|tma) */
 };
 
@@ -567,6 +600,10 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     LBAD_CUDA_TRY(cudaMemcpy(p->d_tw1, tw1.data(), sizeof(float4) * 512, cudaMemcpyHostToDevice));
     LBAD_CUDA_TRY(cudaMemcpy(p->d_tw2, tw2.data(), sizeof(float4) * 512, cudaMemcpyHostToDevice));
     p->static_range = (kmin >> 5) == 2 && ((kmax - 1) >> 5) == 23;
+    for (uint32_t b = 0; b < B && b < 32; b++) {
+        const uint32_t half = (geo->khigh[b] - geo->klow[b] + 1) / 2;
+        if (half > (uint32_t)(b < 16 ? STATIC_HALF0 : STATIC_HALF1)) p->static_range = false;
+    }
     /* fused path: window 2048, 32 bands, even hop, frame span fits in shared memory */
     const uint64_t span = 127ull * geo->stride + N;
     p->fused_ok = (N == 2048 && B == 32 && (geo->stride % 2 == 0) && span * 4 < (1u << 20) && fused_layout((uint32_t)span).total_bytes <= p->smem_optin);
@@ -580,7 +617,7 @@ extern "C" void lbadcu_plan_destroy(lbadcu_plan* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     cudaStreamSynchronize(p->stream);
-    p->timer.clear();
+    p->timer.clear(); p->timer2.clear();
     cudaFree(p->d_tw_m); cudaFree(p->d_tw_n); cudaFree(p->d_tw1); cudaFree(p->d_tw2); cudaFree(p->d_scratch_images);
     for (int i = 0; i < 3; i++) { cudaFree(p->d_chunk_pcm[i]); cudaFree(p->d_chunk_words[i]); if (p->copy_streams[i]) cudaStreamDestroy(p->copy_streams[i]); }
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -590,9 +627,10 @@ extern "C" void lbadcu_plan_destroy(lbadcu_plan* p) {
 extern "C" int lbadcu_plan_fused_supported(const lbadcu_plan* p) { return p->fused_ok ? 1 : 0; }
 extern "C" void* lbadcu_plan_stream(lbadcu_plan* p) { return p->stream; }
 extern "C" uint64_t lbadcu_plan_launches(const lbadcu_plan* p) { return p->launches; }
-extern "C" uint32_t lbadcu_plan_timing(lbadcu_plan* p, int enable, int reset, double* total_ms) {
-    uint32_t n = p->timer.collect(total_ms, reset != 0);
-    p->timer.enabled = enable != 0;
+extern "C" uint32_t lbadcu_plan_timing(lbadcu_plan* p, int which, int enable, int reset, double* total_ms) {
+    LaunchTimer& t = which ? p->timer2 : p->timer;      /* 0: FFT + band-energy kernel (dominant), 1: Haar / select / pack kernel */
+    uint32_t n = t.collect(total_ms, reset != 0);
+    t.enabled = enable != 0;
     return n;
 }
 
@@ -633,24 +671,44 @@ extern "C" int lbadcu_extract_device(lbadcu_plan* p, const float* d_pcm, uint32_
     const bool fused = mode == 1 ? true : mode == 2 ? false : p->fused_ok;
     if (fused && !p->fused_ok) return LBAD_ERR_ARG;
     if (fused) {
+        /* fast path: FFT + bands kernel -> spectral images (global, L2-friendly 16 KB each) -> Haar/select/pack kernel */
         const uint32_t span = 127u * g.stride + g.window;
         const FusedSmemLayout L = fused_layout(span);
         /* TMA bulk copies need 16-byte aligned sources and sizes */
         bool tma_ok = ((uintptr_t)d_pcm % 16 == 0) && (clip_stride % 4 == 0) && (g.stride % 4 == 0);
         if (p->stage_mode == 0) tma_ok = false;
-        auto kern = p->static_range ? extract_fused_kernel<true> : extract_fused_kernel<false>;
+        auto kern = p->static_range ? bands_fused_kernel<true> : bands_fused_kernel<false>;
         LBAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes));
         int per_sm = 0;
         LBAD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, L.total_bytes));
         if (per_sm < 1) per_sm = 1;
         const uint32_t cap = (uint32_t)(p->sm_count * per_sm);
-        const uint32_t grid = total_frames < cap ? total_frames : cap;
-        p->timer.begin(s);
-        kern<<<grid, FUSED_THREADS, L.total_bytes, s>>>(d_pcm, d_words, d_images, d_haar, p->d_tw1, p->d_tw2, g, p->bt, L, span,
-                                                                        total_frames, tma_ok ? 1 : 0);
-        p->timer.end(s);
-        p->launches++;
-        LBAD_CUDA_TRY(cudaGetLastError());
+        const uint32_t slab_frames = d_images ? total_frames : (total_frames < (1u << 18) ? total_frames : (1u << 18));   /* <= 4 GB of images */
+        if (!d_images && p->scratch_frames < slab_frames) {
+            LBAD_CUDA_TRY(cudaStreamSynchronize(s));
+            cudaFree(p->d_scratch_images); p->d_scratch_images = nullptr; p->scratch_frames = 0;
+            LBAD_CUDA_TRY(cudaMalloc(&p->d_scratch_images, (size_t)slab_frames * LBAD_ROWS_PER_FRAME * LBAD_MAX_BANDS * sizeof(float)));
+            p->scratch_frames = slab_frames;
+        }
+        for (uint32_t f0 = 0; f0 < total_frames; f0 += slab_frames) {
+            const uint32_t nf = total_frames - f0 < slab_frames ? total_frames - f0 : slab_frames;
+            float* imgs = d_images ? d_images : p->d_scratch_images;
+            /* a slab starts at frame f0 of the flattened (clip, frame) order: hand the kernel a view that starts there */
+            Geo gs = g;
+            const uint32_t grid = nf < cap ? nf : cap;
+            p->timer.begin(s);
+            kern<<<grid, FUSED_THREADS, L.total_bytes, s>>>(d_pcm, imgs, p->d_tw1, p->d_tw2, gs, p->bt, L, span, nf, tma_ok ? 1 : 0, f0);
+            p->timer.end(s);
+            p->launches++;
+            LBAD_CUDA_TRY(cudaGetLastError());
+            const uint32_t grid2 = nf < (uint32_t)p->sm_count * 6 ? nf : (uint32_t)p->sm_count * 6;
+            p->timer2.begin(s);
+            haar_select32_kernel<<<grid2, HS32_THREADS, 0, s>>>(imgs, d_haar ? d_haar + (size_t)f0 * LBAD_ROWS_PER_FRAME * 32 : nullptr,
+                                                                d_words + (size_t)f0 * 2 * g.words_per_plane, (int)g.pairs, (int)g.words_per_plane, nf);
+            p->timer2.end(s);
+            p->launches++;
+            LBAD_CUDA_TRY(cudaGetLastError());
+        }
         return LBAD_OK;
     }
     /* generic: bands -> (scratch) images -> Haar/select, in slabs of frames when no dump buffer was given */

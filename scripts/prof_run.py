@@ -18,9 +18,13 @@ if a.what in ("both", "extract"):
     d = lb.Detective(); n, L = a.clips, 165360
     x = torch.empty((n, L), dtype=torch.float32, device="cuda"); lb.synthesize_device(x.data_ptr(), n, L, L, stream=s.cuda_stream)
     w = torch.zeros((n, 19, 8), dtype=torch.int32, device="cuda")
+    d.process_batch_device(x.data_ptr(), n, L, L, w.data_ptr(), s.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(a.reps):
         d.process_batch_device(x.data_ptr(), n, L, L, w.data_ptr(), s.cuda_stream)
-    torch.cuda.synchronize()
+    e1.record(); torch.cuda.synchronize()
+    print("extract: %d clips, %.3f ms per pass, %.1f audio-hours/s" % (n, e0.elapsed_time(e1) / a.reps, n * L / 5512.0 / 3600.0 / (e0.elapsed_time(e1) / a.reps * 1e-3)))
 if a.what in ("both", "search"):
     db = lb.Database(200); n = a.db_clips
     codes = torch.empty((n, 19, 8), dtype=torch.int32, device="cuda"); lb.random_codes_device(codes.data_ptr(), n * 19, 200, seed=5, stream=s.cuda_stream); torch.cuda.synchronize()
