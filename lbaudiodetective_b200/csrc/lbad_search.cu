@@ -94,25 +94,38 @@ __global__ void meta_kernel(const uint32_t* __restrict__ db, float2* __restrict_
     }
 }
 
-/* Fast path: every clip in the database has at least CQ subfingerprints, so the clip is always fp1 (FP.m:123-131:
- * no swap when counts are equal).  Offset-outer / query-subfingerprint-inner, exactly the reference's loop nest; the
- * database words and their (possible, 1/possible) are warp-uniform broadcast loads, the CQ query subfingerprints
- * live in registers. */
+constexpr int STAGE_SUBFPS = 128;          /* database subfingerprints staged in shared memory per tile (whole clips only) */
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+/* Fast path: every clip in the database has between CQ and STAGE_SUBFPS subfingerprints, so the clip is always fp1
+ * (FP.m:123-131: no swap when counts are equal).  Offset-outer / query-subfingerprint-inner, exactly the reference's loop
+ * nest.  The four warps of a CTA work on the SAME clips with different query groups: tiles of whole clips (words and
+ * (possible, 1/possible)) are brought into shared memory by cp.async, double buffered, and read back as warp-uniform
+ * broadcast loads; the CQ query subfingerprints live in registers. */
 template <int W, int CQ, bool MASKED>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32)
 search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ meta, const uint32_t* __restrict__ offsets, const uint32_t n_clips,
                    const uint32_t clip_base, const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t pairs, const int k,
                    const uint32_t n_qgroups, const uint32_t clips_per_chunk, float* __restrict__ part_sc, uint32_t* __restrict__ part_id,
-                   float* __restrict__ all_scores, const uint32_t total_warps) {
+                   float* __restrict__ all_scores, const uint32_t groups_per_chunk) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t gw = blockIdx.x * SEARCH_WARPS + wid;
-    if (gw >= total_warps) return;
-    const uint32_t qg = gw % n_qgroups, chunk = gw / n_qgroups;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t chunk = blockIdx.x / groups_per_chunk, qg = (blockIdx.x % groups_per_chunk) * SEARCH_WARPS + wid;
     const uint32_t q = qg * 32 + lane;
-    const bool qvalid = q < n_q;
+    const bool qvalid = qg < n_qgroups && q < n_q;
     TopK top{reinterpret_cast<float*>(smem_raw) + (size_t)wid * 2 * k * 32, reinterpret_cast<uint32_t*>(smem_raw) + (size_t)wid * 2 * k * 32 + (size_t)k * 32, k, lane};
     top.init();
+    /* staging buffers after the top-k lists: [2][STAGE_SUBFPS][2W] words, then [2][STAGE_SUBFPS] float2 */
+    uint32_t* st_words = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)SEARCH_WARPS * 2 * k * 32;
+    float2* st_meta = reinterpret_cast<float2*>(st_words + 2 * STAGE_SUBFPS * 2 * W);
     const PairMask<W> mask = make_mask<W>(pairs);
     uint32_t qp[CQ][W], qm[CQ][W];
 #pragma unroll
@@ -125,50 +138,80 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
     const uint32_t c_begin = chunk * clips_per_chunk;
     const uint32_t c_end = min(n_clips, c_begin + clips_per_chunk);
     float worst = top.worst();
-    for (uint32_t c = c_begin; c < c_end; c++) {
-        const uint32_t s0 = offsets[c], c1 = offsets[c + 1] - s0;            /* warp-uniform */
-        float best = 0.0f;                                                    /* FP.m:133 */
-        for (uint32_t o = 0; o + CQ <= c1; o++) {                             /* FP.m:136 */
-            float sum = 0.0f;
+
+    /* tile = clips [c0, c1) whose subfingerprints [s_lo, s_hi) fit the staging buffer; every thread computes the same bounds */
+    auto tile_end = [&](uint32_t c0) -> uint32_t {
+        const uint32_t s_lo = offsets[c0];
+        uint32_t c1 = c0;
+        while (c1 < c_end && offsets[c1 + 1] - s_lo <= (uint32_t)STAGE_SUBFPS) c1++;
+        return c1;
+    };
+    auto issue_tile = [&](uint32_t c0, uint32_t c1, int buf) {
+        const uint32_t s_lo = offsets[c0], n_sub = offsets[c1] - s_lo;
+        const uint4* src = reinterpret_cast<const uint4*>(db + (size_t)s_lo * 2 * W);
+        uint4* dst = reinterpret_cast<uint4*>(st_words + (size_t)buf * STAGE_SUBFPS * 2 * W);
+        for (uint32_t i = tid; i < n_sub * (2 * W / 4); i += SEARCH_WARPS * 32) cp_async16(dst + i, src + i);
+        if (!MASKED) for (uint32_t i = tid; i < n_sub; i += SEARCH_WARPS * 32) cp_async8(st_meta + (size_t)buf * STAGE_SUBFPS + i, meta + (size_t)s_lo + i);
+        cp_async_commit();
+    };
+
+    uint32_t c0 = c_begin, c1 = c_begin < c_end ? tile_end(c_begin) : c_begin;
+    int buf = 0;
+    if (c0 < c_end) issue_tile(c0, c1, 0);
+    while (c0 < c_end) {
+        cp_async_wait_all();
+        __syncthreads();                                                       /* tile `buf` has landed; everyone is done with the other buffer */
+        const uint32_t n0 = c1, n1 = n0 < c_end ? tile_end(n0) : n0;
+        if (n0 < c_end) issue_tile(n0, n1, buf ^ 1);                           /* prefetch the next tile while this one is compared */
+        const uint32_t s_lo = offsets[c0];
+        const uint32_t* tw = st_words + (size_t)buf * STAGE_SUBFPS * 2 * W;
+        const float2* tm = st_meta + (size_t)buf * STAGE_SUBFPS;
+        if (qg < n_qgroups) for (uint32_t c = c0; c < c1; c++) {
+            const uint32_t s0 = offsets[c] - s_lo, cnt = offsets[c + 1] - offsets[c];      /* warp-uniform */
+            float best = 0.0f;                                                /* FP.m:133 */
+            for (uint32_t o = 0; o + CQ <= cnt; o++) {                        /* FP.m:136 */
+                float sum = 0.0f;
 #pragma unroll
-            for (int i = 0; i < CQ; i++) {                                    /* FP.m:139-142 */
-                const uint32_t* src = db + ((size_t)s0 + o + i) * 2 * W;
-                uint32_t p1[W], m1[W];
-                if (W % 4 == 0) {
+                for (int i = 0; i < CQ; i++) {                                /* FP.m:139-142 */
+                    const uint32_t* src = tw + (size_t)(s0 + o + i) * 2 * W;
+                    uint32_t p1[W], m1[W];
+                    if (W % 4 == 0) {
 #pragma unroll
-                    for (int w = 0; w < W; w += 4) {
-                        const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + w)), b = __ldg(reinterpret_cast<const uint4*>(src + W + w));
-                        p1[w] = a.x; p1[w + 1] = a.y; p1[w + 2] = a.z; p1[w + 3] = a.w; m1[w] = b.x; m1[w + 1] = b.y; m1[w + 2] = b.z; m1[w + 3] = b.w;
+                        for (int w = 0; w < W; w += 4) {
+                            const uint4 a = *reinterpret_cast<const uint4*>(src + w), b = *reinterpret_cast<const uint4*>(src + W + w);
+                            p1[w] = a.x; p1[w + 1] = a.y; p1[w + 2] = a.z; p1[w + 3] = a.w; m1[w] = b.x; m1[w + 1] = b.y; m1[w + 2] = b.z; m1[w + 3] = b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < W; w += 2) {
+                            const uint2 a = *reinterpret_cast<const uint2*>(src + w), b = *reinterpret_cast<const uint2*>(src + W + w);
+                            p1[w] = a.x; p1[w + 1] = a.y; m1[w] = b.x; m1[w + 1] = b.y;
+                        }
                     }
-                } else {
+                    float fposs, rcp;
+                    if (MASKED) {
+                        uint32_t possible = 0;
 #pragma unroll
-                    for (int w = 0; w < W; w += 2) {
-                        const uint2 a = __ldg(reinterpret_cast<const uint2*>(src + w)), b = __ldg(reinterpret_cast<const uint2*>(src + W + w));
-                        p1[w] = a.x; p1[w + 1] = a.y; m1[w] = b.x; m1[w + 1] = b.y;
+                        for (int w = 0; w < W; w++) { p1[w] &= mask.w[w]; m1[w] &= mask.w[w]; possible += __popc(p1[w] | m1[w]); }   /* FP.m:159-160 */
+                        fposs = (float)possible; rcp = c_rcp[possible];
+                    } else {
+                        const float2 mt = tm[s0 + o + i];
+                        fposs = mt.x; rcp = mt.y;
                     }
-                }
-                float fposs, rcp;
-                if (MASKED) {
-                    uint32_t possible = 0;
+                    uint32_t hits = 0;
 #pragma unroll
-                    for (int w = 0; w < W; w++) { p1[w] &= mask.w[w]; m1[w] &= mask.w[w]; possible += __popc(p1[w] | m1[w]); }   /* FP.m:159-160 */
-                    fposs = (float)possible; rcp = c_rcp[possible];
-                } else {
-                    const float2 mt = __ldg(meta + (size_t)s0 + o + i);
-                    fposs = mt.x; rcp = mt.y;
+                    for (int w = 0; w < W; w++) hits += __popc(hit_word2(p1[w], m1[w], qp[i][w], qm[i][w]));   /* FP.m:162-167 */
+                    sum = __fadd_rn(sum, ratio_exact(hits, fposs, rcp));
                 }
-                uint32_t hits = 0;
-#pragma unroll
-                for (int w = 0; w < W; w++) hits += __popc(hit_word2(p1[w], m1[w], qp[i][w], qm[i][w]));   /* FP.m:162-167 */
-                sum = __fadd_rn(sum, ratio_exact(hits, fposs, rcp));
+                const float mean = mean_exact<CQ>(sum);                        /* FP.m:144 */
+                best = (best < mean) ? mean : best;                            /* Apple MAX */
             }
-            const float mean = mean_exact<CQ>(sum);                            /* FP.m:144 */
-            best = (best < mean) ? mean : best;                                /* Apple MAX */
+            if (qvalid) {
+                if (all_scores) all_scores[(size_t)q * n_clips + c] = best;
+                if (best > worst) { top.insert(best, clip_base + c); worst = top.worst(); }
+            }
         }
-        if (qvalid) {
-            if (all_scores) all_scores[(size_t)q * n_clips + c] = best;
-            if (best > worst) { top.insert(best, clip_base + c); worst = top.worst(); }
-        }
+        c0 = n0; c1 = n1; buf ^= 1;
     }
     if (qvalid) for (int r = 0; r < k; r++) {
         part_sc[((size_t)chunk * n_q + q) * k + r] = top.sc[r * 32 + lane];
@@ -382,9 +425,12 @@ extern "C" uint64_t lbadcu_db_compares_per_query(const lbadcu_db* db, uint32_t c
 }
 
 template <int W, int CQ>
-static void launch_fast(lbadcu_db* db, bool masked, uint32_t blocks, size_t smem, cudaStream_t s, const uint32_t* d_q, uint32_t n_q, uint32_t pairs, int k,
-                        uint32_t n_qgroups, uint32_t cpc, float* d_all, uint32_t total_warps) {
+static void launch_fast(lbadcu_db* db, bool masked, uint32_t n_chunks, size_t smem_topk, cudaStream_t s, const uint32_t* d_q, uint32_t n_q, uint32_t pairs, int k,
+                        uint32_t n_qgroups, uint32_t cpc, float* d_all) {
     const uint32_t n_clips = lbadcu_db_clips(db);
+    const uint32_t total_warps = (n_qgroups + SEARCH_WARPS - 1) / SEARCH_WARPS;      /* = CTAs per clip chunk (passed in the last kernel argument) */
+    const uint32_t blocks = n_chunks * total_warps;
+    const size_t smem = smem_topk + (size_t)2 * STAGE_SUBFPS * (2 * W * sizeof(uint32_t) + sizeof(float2));
     if (masked) {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         search_fast_kernel<W, CQ, true><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
@@ -436,13 +482,13 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
     }
     const uint32_t total_warps = n_chunks * n_qgroups;
     const uint32_t blocks = (total_warps + SEARCH_WARPS - 1) / SEARCH_WARPS;
-    const bool fast = n_clips > 0 && db->min_count >= cq && cq >= 1 && cq <= 6;
+    const bool fast = n_clips > 0 && db->min_count >= cq && db->max_count <= (uint32_t)STAGE_SUBFPS && cq >= 1 && cq <= 6;
     const bool masked = pairs < db->pairs_full;       /* words beyond L are zero already; a mask is only needed for a shorter range */
     const size_t smem_fast = (size_t)SEARCH_WARPS * 2 * k * 32 * 4;
     const size_t smem_gen = (size_t)SEARCH_WARPS * ((size_t)2 * k * 32 + (size_t)cq * 2 * W * 32) * 4;
     if (!fast && smem_gen > db->smem_optin) return LBAD_ERR_ARG;
     db->timer.begin(s);
-#define LBAD_FAST(WW, CC) launch_fast<WW, CC>(db, masked, blocks, smem_fast, s, d_q, n_q, pairs, (int)k, n_qgroups, cpc, d_all, total_warps)
+#define LBAD_FAST(WW, CC) launch_fast<WW, CC>(db, masked, n_chunks, smem_fast, s, d_q, n_q, pairs, (int)k, n_qgroups, cpc, d_all)
 #define LBAD_GEN(WW) launch_generic<WW>(db, blocks, smem_gen, s, d_q, n_q, cq, pairs, (int)k, n_qgroups, cpc, d_all, total_warps)
     if (fast) {
 #define LBAD_FAST_W(WW) switch (cq) { case 1: LBAD_FAST(WW, 1); break; case 2: LBAD_FAST(WW, 2); break; case 3: LBAD_FAST(WW, 3); break; \
