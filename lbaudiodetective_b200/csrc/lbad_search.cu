@@ -82,6 +82,21 @@ __device__ __forceinline__ uint32_t hit_word2(uint32_t p1, uint32_t m1, uint32_t
     return lop3<0x90>(lop3<0xA4>(p1, m1, p2), m1, m2);
 }
 
+/* popcount of the W hit words with a carry-save adder per group of three words (x ^ y ^ z has the ones, maj(x, y, z) the
+ * twos): POPC is a quarter-rate XU-pipe instruction and the search kernel is bound by it, LOP3 is not. */
+template <int W>
+__device__ __forceinline__ uint32_t popc_words(const uint32_t (&h)[W]) {
+    uint32_t ones = 0, twos = 0;
+#pragma unroll
+    for (int w = 0; w + 3 <= W; w += 3) {
+        ones += __popc(lop3<0x96>(h[w], h[w + 1], h[w + 2]));
+        twos += __popc(lop3<0xE8>(h[w], h[w + 1], h[w + 2]));
+    }
+#pragma unroll
+    for (int w = (W / 3) * 3; w < W; w++) ones += __popc(h[w]);
+    return ones + 2 * twos;
+}
+
 /* per database subfingerprint: (float)possible and RN(1/possible) over the FULL length — what every unmasked compare needs */
 template <int W>
 __global__ void meta_kernel(const uint32_t* __restrict__ db, float2* __restrict__ meta, const uint64_t first, const uint64_t count) {
@@ -198,10 +213,10 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
                         const float2 mt = tm[s0 + o + i];
                         fposs = mt.x; rcp = mt.y;
                     }
-                    uint32_t hits = 0;
+                    uint32_t h[W];
 #pragma unroll
-                    for (int w = 0; w < W; w++) hits += __popc(hit_word2(p1[w], m1[w], qp[i][w], qm[i][w]));   /* FP.m:162-167 */
-                    sum = __fadd_rn(sum, ratio_exact(hits, fposs, rcp));
+                    for (int w = 0; w < W; w++) h[w] = hit_word2(p1[w], m1[w], qp[i][w], qm[i][w]);            /* FP.m:162-167 */
+                    sum = __fadd_rn(sum, ratio_exact(popc_words<W>(h), fposs, rcp));
                 }
                 const float mean = mean_exact<CQ>(sum);                        /* FP.m:144 */
                 best = (best < mean) ? mean : best;                            /* Apple MAX */
