@@ -437,10 +437,14 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
     }
 }
 
-/* One CTA per spectral image (128 x 32): Haar rows + columns (Frame.m:113-153), ordered top-T and packing (Frame.m:165-191)
- * entirely in shared memory.  Small footprint (about 19 KB), so several CTAs share an SM and hide each other's barriers. */
+/* ------------------------------------------------------------------------------------- Haar + select, 128 x 32 ---- */
+
+/* One CTA per spectral image (128 x 32): Haar rows + columns (Frame.m:113-153), ordered top-T and packing (Frame.m:165-191).
+ * The Haar transform is warp-local — every level runs in registers or through warp shuffles — so the whole image needs ONE block
+ * barrier (between the row and the column pass); the coefficients never go back to shared memory: each thread keeps its 16 and
+ * the selection works on registers.  About 27 KB of shared memory and 64 registers: four CTAs per SM hide each other's barriers. */
 constexpr int HS32_THREADS = 256;
-constexpr int HS32_LD = 33;
+constexpr int HS32_LDT = 132;                /* column-major image, imgT[col * 132 + row]: LDS.128-aligned and conflict-free */
 
 /* x / c for a compile-time constant c with r = RN(1/c): multiply + two FMAs give the IEEE quotient for every finite x with
  * |x| >= 2^-100 or x == 0 (exhaustively checked on the host for c = sqrtf(2), sqrtf(32), sqrtf(128)); the rare rest divides. */
@@ -451,74 +455,217 @@ __device__ __forceinline__ float div_const(const float x, const float c, const f
     return ((ax >= 7.9e-31f && ax <= 1.0e37f) || ax == 0.0f) ? q : __fdiv_rn(x, c);
 }
 
-__global__ void __launch_bounds__(HS32_THREADS, 3)
+/* four levels of the ordered Haar pyramid (Frame.m:143-152) on 16 consecutive elements held in registers:
+ * d1[i] = level-1 difference of pair i (8), d2 (4), d3 (2), d4 (1) and the remaining sum s4 */
+__device__ __forceinline__ void haar16(const float (&x)[16], float (&d1)[8], float (&d2)[4], float (&d3)[2], float& d4, float& s4,
+                                       const float s2, const float r2) {
+    float s1[8], t2[4], t3[2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { s1[i] = div_const(__fadd_rn(x[2 * i], x[2 * i + 1]), s2, r2); d1[i] = div_const(__fsub_rn(x[2 * i], x[2 * i + 1]), s2, r2); }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { t2[i] = div_const(__fadd_rn(s1[2 * i], s1[2 * i + 1]), s2, r2); d2[i] = div_const(__fsub_rn(s1[2 * i], s1[2 * i + 1]), s2, r2); }
+#pragma unroll
+    for (int i = 0; i < 2; i++) { t3[i] = div_const(__fadd_rn(t2[2 * i], t2[2 * i + 1]), s2, r2); d3[i] = div_const(__fsub_rn(t2[2 * i], t2[2 * i + 1]), s2, r2); }
+    s4 = div_const(__fadd_rn(t3[0], t3[1]), s2, r2);
+    d4 = div_const(__fsub_rn(t3[0], t3[1]), s2, r2);
+}
+
+struct Select32Smem {
+    uint32_t hist[HS32_THREADS / 32][256];   /* per-warp histograms of the 8 exponent bits */
+    uint32_t warp_tot[HS32_THREADS / 32];
+    uint32_t surv_key[256];
+    uint32_t surv_idx[256];                  /* flat index | sign code << 16 (bit 16: v > 0, bit 17: v < 0) */
+    uint32_t words[16];
+    uint32_t nsurv, nbucket, threshold, expo, above, n_gt, n_eq, cut;
+    uint32_t steps[16];
+};
+
+__global__ void __launch_bounds__(HS32_THREADS, 4)
 haar_select32_kernel(const float* __restrict__ images, float* __restrict__ haar_out, uint32_t* __restrict__ words,
                      const int T, const int W, const uint32_t total_frames) {
-    __shared__ __align__(16) float img[LBAD_ROWS_PER_FRAME * HS32_LD];
-    __shared__ SelectSmem sel;
-    const int tid = threadIdx.x;
+    __shared__ __align__(16) float imgT[32 * HS32_LDT];      /* also the bucket of undecided keys once the columns are in registers */
+    __shared__ Select32Smem sm;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float s2 = sqrtf(2.0f), s32 = sqrtf(32.0f), s128 = sqrtf(128.0f);
     const float r2 = 1.0f / s2, r32 = 1.0f / s32, r128 = 1.0f / s128;
+    uint32_t* bucket = reinterpret_cast<uint32_t*>(imgT);
+
     for (uint32_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
-        const float4* src = reinterpret_cast<const float4*>(images + (size_t)f * LBAD_ROWS_PER_FRAME * 32);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {                                           /* 1024 float4 = one image */
-            const int i = tid + HS32_THREADS * j;
-            const float4 v = __ldg(src + i);
-            float* d = img + (i >> 3) * HS32_LD + (i & 7) * 4;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
-        __syncthreads();
-        /* ---- Haar rows (length 32), Frame.m:114-116 + 134-153; thread = row ---- */
-        if (tid < (int)LBAD_ROWS_PER_FRAME) {
-            float a[32], t[32];
-#pragma unroll
-            for (int c = 0; c < 32; c++) a[c] = div_const(img[tid * HS32_LD + c], s32, r32);
-#pragma unroll
-            for (int n = 16; n >= 1; n >>= 1) {
-#pragma unroll
-                for (int i = 0; i < n; i++) {
-                    t[i] = div_const(__fadd_rn(a[2 * i], a[2 * i + 1]), s2, r2);
-                    t[n + i] = div_const(__fsub_rn(a[2 * i], a[2 * i + 1]), s2, r2);
-                }
-#pragma unroll
-                for (int i = 0; i < 2 * n; i++) a[i] = t[i];
-            }
-            /* the column pass starts by dividing every element by sqrtf(128) (Frame.m:137-139): fold it into the write-back */
-#pragma unroll
-            for (int c = 0; c < 32; c++) img[tid * HS32_LD + c] = div_const(a[c], s128, r128);
-        }
-        __syncthreads();
-        /* ---- Haar columns (length 128), Frame.m:118-131; each level: read pairs, barrier, write ---- */
+        /* ---- rows (length 32, Frame.m:114-116): warp w owns rows 16w..16w+15, two lanes per row, 16 elements each ---- */
         {
-            const int c = tid & 31, i0 = tid >> 5;
-#pragma unroll 1
-            for (int n = 64; n >= 1; n >>= 1) {
-                float x0[8], x1[8];
+            const int row = 16 * wid + (lane >> 1), half = lane & 1;
+            const float4* src = reinterpret_cast<const float4*>(images + ((size_t)f * LBAD_ROWS_PER_FRAME + row) * 32 + half * 16);
+            float x[16], d1[8], d2[4], d3[2], d4, s4;
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int i = i0 + 8 * q;
-                    if (i < n) { x0[q] = img[(2 * i) * HS32_LD + c]; x1[q] = img[(2 * i + 1) * HS32_LD + c]; }
-                }
-                __syncthreads();
+            for (int j = 0; j < 4; j++) { const float4 v = __ldg(src + j); x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int i = i0 + 8 * q;
-                    if (i < n) {
-                        img[i * HS32_LD + c] = div_const(__fadd_rn(x0[q], x1[q]), s2, r2);
-                        img[(n + i) * HS32_LD + c] = div_const(__fsub_rn(x0[q], x1[q]), s2, r2);
-                    }
-                }
-                __syncthreads();
-            }
+            for (int j = 0; j < 16; j++) x[j] = div_const(x[j], s32, r32);                   /* Frame.m:137-139 */
+            haar16(x, d1, d2, d3, d4, s4, s2, r2);
+            const float other = __shfl_xor_sync(0xffffffffu, s4, 1);                           /* level 5 joins the two halves */
+            const float top = half ? div_const(__fsub_rn(other, s4), s2, r2) : div_const(__fadd_rn(s4, other), s2, r2);
+            /* ordered output positions; the column pass starts by dividing by sqrtf(128) (Frame.m:137-139): folded into the store */
+            float* dst = imgT + row;
+#pragma unroll
+            for (int i = 0; i < 8; i++) dst[(16 + 8 * half + i) * HS32_LDT] = div_const(d1[i], s128, r128);
+#pragma unroll
+            for (int i = 0; i < 4; i++) dst[(8 + 4 * half + i) * HS32_LDT] = div_const(d2[i], s128, r128);
+#pragma unroll
+            for (int i = 0; i < 2; i++) dst[(4 + 2 * half + i) * HS32_LDT] = div_const(d3[i], s128, r128);
+            dst[(2 + half) * HS32_LDT] = div_const(d4, s128, r128);
+            dst[half * HS32_LDT] = div_const(top, s128, r128);
         }
+        __syncthreads();
+        /* ---- columns (length 128, Frame.m:118-131): warp w owns columns 4w..4w+3, eight lanes per column, 16 rows each ---- */
+        const int cl = lane & 3, g = lane >> 2, col = 4 * wid + cl;
+        float coef[16];
+        {
+            float x[16], d1[8], d2[4], d3[2], d4, s4;
+            const float4* src = reinterpret_cast<const float4*>(imgT + col * HS32_LDT + 16 * g);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const float4 v = src[j]; x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
+            haar16(x, d1, d2, d3, d4, s4, s2, r2);
+            /* levels 5-7 across the eight lanes of the column: the lane with the lower g keeps the sum, the other the difference */
+            float p = __shfl_xor_sync(0xffffffffu, s4, 4);
+            const float s5 = div_const(__fadd_rn(s4, p), s2, r2), d5 = div_const(__fsub_rn(p, s4), s2, r2);
+            p = __shfl_xor_sync(0xffffffffu, s5, 8);
+            const float s6 = div_const(__fadd_rn(s5, p), s2, r2), d6 = div_const(__fsub_rn(p, s5), s2, r2);
+            p = __shfl_xor_sync(0xffffffffu, s6, 16);
+            const float s7 = div_const(__fadd_rn(s6, p), s2, r2), d7 = div_const(__fsub_rn(p, s6), s2, r2);
+#pragma unroll
+            for (int i = 0; i < 8; i++) coef[i] = d1[i];
+#pragma unroll
+            for (int i = 0; i < 4; i++) coef[8 + i] = d2[i];
+            coef[12] = d3[0]; coef[13] = d3[1]; coef[14] = d4;
+            coef[15] = (g & 1) ? d5 : (g & 2) ? d6 : (g & 4) ? d7 : s7;
+        }
+        /* row position of each of my coefficients in the ordered output (flat index = 32 * position + column) */
+        const uint32_t pos_last = (g & 1) ? 4 + (g >> 1) : (g & 2) ? 2 + (g >> 2) : (g & 4) ? 1 : 0;
+        auto flat_idx = [&](int e) -> uint32_t {
+            const uint32_t pos = e < 8 ? 64 + 8 * g + e : e < 12 ? 32 + 4 * g + (e - 8) : e < 14 ? 16 + 2 * g + (e - 12) : e == 14 ? 8 + g : pos_last;
+            return pos * 32 + col;
+        };
         if (haar_out) {
             float* o = haar_out + (size_t)f * LBAD_ROWS_PER_FRAME * 32;
-            for (int i = tid; i < (int)LBAD_ROWS_PER_FRAME * 32; i += HS32_THREADS) o[i] = img[(i >> 5) * HS32_LD + (i & 31)];
+#pragma unroll
+            for (int e = 0; e < 16; e++) o[flat_idx(e)] = coef[e];
         }
-        /* ---- ordered top-T -> packed words, Frame.m:165-191; once the keys are in registers the image doubles as the bucket ---- */
-        select_and_pack<HS32_THREADS, 16>([&](int idx) { return img[(idx >> 5) * HS32_LD + (idx & 31)]; }, T, W,
-                                          words + (size_t)f * 2 * W, sel, reinterpret_cast<uint32_t*>(img));
+
+        /* ---- ordered top-T (Frame.m:165-191): threshold = T-th largest |v| as an integer key ---- */
+        uint32_t key[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) key[e] = __float_as_uint(coef[e]) & 0x7fffffffu;
+#pragma unroll
+        for (int j = 0; j < 8; j++) sm.hist[wid][lane + 32 * j] = 0;
+        if (tid < 16) { sm.words[tid] = 0; sm.steps[tid] = 0; }
+        if (tid == 0) { sm.nsurv = 0; sm.nbucket = 0; sm.n_gt = 0; sm.n_eq = 0; }
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 16; e++) atomicAdd(&sm.hist[wid][key[e] >> 23], 1u);
+        __syncthreads();                                     /* also: every warp has read its columns, imgT may become the bucket */
+        {
+            /* thread t owns exponent bin t: suffix sums S[t] = #keys with exponent >= t; the threshold's exponent is the largest t with S[t] >= T */
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < HS32_THREADS / 32; w++) tot += sm.hist[w][tid];
+            uint32_t suf = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_down_sync(0xffffffffu, suf, d); if (lane + d < 32) suf += o; }
+            if (lane == 0) sm.warp_tot[wid] = suf;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < HS32_THREADS / 32; w++) if (w > wid) suf += sm.warp_tot[w];
+            if (suf >= (uint32_t)T && suf - tot < (uint32_t)T) { sm.expo = (uint32_t)tid; sm.above = suf - tot; }
+        }
+        __syncthreads();
+        const uint32_t expo = sm.expo;
+        {
+            /* compact the keys that share the threshold's exponent: only their mantissas are still undecided */
+            uint32_t mine = 0;
+#pragma unroll
+            for (int e = 0; e < 16; e++) mine += (key[e] >> 23) == expo;
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+            uint32_t base = 0;
+            if (lane == 31 && incl) base = atomicAdd(&sm.nbucket, incl);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+            for (int e = 0; e < 16; e++) if ((key[e] >> 23) == expo) bucket[base++] = key[e];
+        }
+        __syncthreads();
+        if (wid == 0) {
+            const uint32_t nb = sm.nbucket, need = (uint32_t)T - sm.above;      /* rank of the threshold inside the bucket, >= 1 */
+            uint32_t t2 = expo << 23;
+            for (int bit = 22; bit >= 0; --bit) {
+                const uint32_t cand = t2 | (1u << bit);
+                uint32_t c = 0;
+                for (uint32_t i = lane; i < nb; i += 32) c += (bucket[i] >= cand) ? 1u : 0u;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c >= need) t2 = cand;
+            }
+            if (lane == 0) sm.threshold = t2;
+        }
+        __syncthreads();
+        const uint32_t thr = sm.threshold;
+        {
+            uint32_t ngt = 0, neq = 0;
+#pragma unroll
+            for (int e = 0; e < 16; e++) { ngt += key[e] > thr; neq += key[e] == thr; }
+            ngt = __reduce_add_sync(0xffffffffu, ngt); neq = __reduce_add_sync(0xffffffffu, neq);
+            if (lane == 0) { if (ngt) atomicAdd(&sm.n_gt, ngt); if (neq) atomicAdd(&sm.n_eq, neq); }
+        }
+        __syncthreads();
+        const uint32_t need_eq = (uint32_t)T - sm.n_gt;                            /* >= 1 ties to take, lowest flat index first (Q9) */
+        uint32_t cut = 0xffffffffu;
+        if (sm.n_eq > need_eq) {                                                   /* block-uniform; rare (exact magnitude ties at the threshold) */
+            /* smallest cut with #(ties with flat index < cut) >= need_eq, by bisection on the 13 index bits */
+            uint32_t m = 0;
+            for (int bit = 12; bit >= 0; --bit) {
+                const uint32_t cand = m | (1u << bit);
+                uint32_t c = 0;
+#pragma unroll
+                for (int e = 0; e < 16; e++) c += (key[e] == thr && flat_idx(e) < cand) ? 1u : 0u;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (lane == 0 && c) atomicAdd(&sm.steps[bit], c);
+                __syncthreads();
+                if (sm.steps[bit] < need_eq) m = cand;
+            }
+            cut = m + 1;
+        }
+        {
+            uint32_t take = 0;
+#pragma unroll
+            for (int e = 0; e < 16; e++) take |= (uint32_t)(key[e] > thr || (key[e] == thr && flat_idx(e) < cut)) << e;
+            const uint32_t mine = __popc(take);
+            uint32_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+            uint32_t base = 0;
+            if (lane == 31 && incl) base = atomicAdd(&sm.nsurv, incl);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+            for (int e = 0; e < 16; e++) if ((take >> e) & 1u) {
+                if (base < 256u) {
+                    sm.surv_key[base] = key[e];
+                    sm.surv_idx[base] = flat_idx(e) | ((coef[e] > 0.0f ? 1u : 0u) << 16) | ((coef[e] < 0.0f ? 1u : 0u) << 17);
+                }
+                base++;
+            }
+        }
+        __syncthreads();
+        /* rank by counting: survivor j precedes s iff key_j > key_s, or equal keys and idx_j < idx_s */
+        for (int s = tid; s < T; s += HS32_THREADS) {
+            const uint32_t ks = sm.surv_key[s], is = sm.surv_idx[s], idx = is & 0xffffu;
+            uint32_t rank = 0;
+            for (int j = 0; j < T; j++) {
+                const uint32_t kj = sm.surv_key[j], ij = sm.surv_idx[j] & 0xffffu;
+                rank += (kj > ks || (kj == ks && ij < idx)) ? 1u : 0u;
+            }
+            if (is & (1u << 16)) atomicOr(&sm.words[rank >> 5], 1u << (rank & 31));
+            if (is & (1u << 17)) atomicOr(&sm.words[W + (rank >> 5)], 1u << (rank & 31));
+        }
+        __syncthreads();
+        if (tid < 2 * W) words[(size_t)f * 2 * W + tid] = sm.words[tid];
         __syncthreads();
     }
 }
@@ -701,7 +848,7 @@ extern "C" int lbadcu_extract_device(lbadcu_plan* p, const float* d_pcm, uint32_
             p->timer.end(s);
             p->launches++;
             LBAD_CUDA_TRY(cudaGetLastError());
-            const uint32_t grid2 = nf < (uint32_t)p->sm_count * 6 ? nf : (uint32_t)p->sm_count * 6;
+            const uint32_t grid2 = nf < (uint32_t)p->sm_count * 8 ? nf : (uint32_t)p->sm_count * 8;
             p->timer2.begin(s);
             haar_select32_kernel<<<grid2, HS32_THREADS, 0, s>>>(imgs, d_haar ? d_haar + (size_t)f0 * LBAD_ROWS_PER_FRAME * 32 : nullptr,
                                                                 d_words + (size_t)f0 * 2 * g.words_per_plane, (int)g.pairs, (int)g.words_per_plane, nf);
