@@ -212,7 +212,13 @@ def main():
     algo_bytes = n_clips * ALGO_BYTES_PER_CLIP
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     flops = n_clips * WINDOWS_PER_CLIP * FLOP_PER_WINDOW
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+    traffic = None
+    try:        # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch's clip count
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = tj["traffic_bytes_per_launch"] * n_clips / tj["clips_per_launch"] / 1e9
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
                 "peak_source": peak_src, "kernel": "bands_fused_kernel (FFT + band energies)", "kernel_ms": kernel_ms, "second_kernel": "haar_select32_kernel", "second_kernel_ms": kernel2_ms_total / max(n_timed2, 1), "algorithmic_bytes_per_launch": algo_bytes,
                 "note": "FP32-issue bound, not HBM bound (235 flop per new PCM byte, SURVEY.md §8d); fp32 figures alongside",
                 "fp32_tflops_algorithmic": flops / (kernel_ms * 1e-3) / 1e12, "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12}

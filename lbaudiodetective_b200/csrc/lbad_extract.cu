@@ -364,10 +364,9 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
             __syncthreads();
         }
 
-        /* ---- 16 windows per warp: FFT -> bands -> image row ---- */
+        /* ---- the frame's 128 windows, round-robin over the warps: FFT -> bands -> image row ---- */
 #pragma unroll 1
-        for (int it = 0; it < (int)LBAD_ROWS_PER_FRAME / FUSED_WARPS; ++it) {
-            const int row = it * FUSED_WARPS + wid;
+        for (int row = wid; row < (int)LBAD_ROWS_PER_FRAME; row += FUSED_WARPS) {
             const float* win = samples + (size_t)row * hop;
             float2 z[32];
 #pragma unroll
