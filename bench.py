@@ -151,6 +151,17 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    try:        # keep the pinned staging buffers of this rank on the NUMA node of its GPU (matters once 8 ranks upload at once)
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1}
+        if cpus:
+            os.sched_setaffinity(0, cpus & set(os.sched_getaffinity(0)) or cpus)
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lb.load_library(build_if_missing=False)          # the bench must run the in-tree CUDA library, never a fallback
@@ -243,7 +254,18 @@ def main():
         assert np.array_equal(host_words.numpy()[:: max(1, n_clips // 64)].view(np.uint32), w)
         e2e = {"value": hours_per_gpu_step * world * args.steps / dt, "unit": "audio-hours/s", "h2d_bytes_per_step": n_clips * CLIP_LEN * 4,
                "d2h_bytes_per_step": n_clips * SUBFPS * 32, "ms_per_step": 1e3 * dt / args.steps, "api": "LBAudioDetectiveProcessPCMBatch (pinned host buffers)"}
-        del host_pcm, host_words
+        # extra: the same clips as signed 16-bit PCM through LBAudioDetectiveProcessPCMBatchInt16 (half the PCIe bytes; not the headline)
+        host_i16 = torch.empty((n_clips, CLIP_LEN), dtype=torch.int16, pin_memory=True)
+        host_i16.copy_((pcm * 32767.0).round().clamp_(-32768, 32767).to(torch.int16)); torch.cuda.synchronize()
+        det.process_batch_int16_ptr(host_i16.data_ptr(), n_clips, CLIP_LEN, CLIP_LEN, host_words.data_ptr())
+        barrier(); t0 = time.perf_counter()
+        for _ in range(args.steps):
+            det.process_batch_int16_ptr(host_i16.data_ptr(), n_clips, CLIP_LEN, CLIP_LEN, host_words.data_ptr())
+        torch.cuda.synchronize(); dt16 = max_over_ranks(time.perf_counter() - t0)
+        e2e["int16_pcm"] = {"value": hours_per_gpu_step * world * args.steps / dt16, "unit": "audio-hours/s", "h2d_bytes_per_step": n_clips * CLIP_LEN * 2,
+                            "ms_per_step": 1e3 * dt16 / args.steps, "api": "LBAudioDetectiveProcessPCMBatchInt16 (extension; pinned host buffers)"}
+        e2e["pcie_gbs"] = n_clips * CLIP_LEN * 4 / dt * args.steps / 1e9
+        del host_pcm, host_words, host_i16
     del pcm
     torch.cuda.empty_cache()
 

@@ -92,6 +92,9 @@ LBAD_API OSStatus LBAudioDetectiveGetBandTable(LBAudioDetectiveRef inDetective, 
  * clip starts (host memory; chunks are copied and processed on overlapping streams).  outWords receives
  * [clip][subfingerprint][2*W] packed words (see LBAudioDetectiveFingerprint.h), W = PackedWordsPerPlane(L). */
 LBAD_API OSStatus LBAudioDetectiveProcessPCMBatch(LBAudioDetectiveRef inDetective, const Float32* inSamples, UInt32 inNumberOfClips, UInt64 inFramesPerClip, UInt64 inClipStride, UInt32* outWords);
+/* Same for signed 16-bit PCM (the reference's recording format, essay p.VI ff.): half the bytes cross PCIe; samples are converted on
+ * the device as x / 32768, exactly what a float32 client format would have delivered. */
+LBAD_API OSStatus LBAudioDetectiveProcessPCMBatchInt16(LBAudioDetectiveRef inDetective, const SInt16* inSamples, UInt32 inNumberOfClips, UInt64 inFramesPerClip, UInt64 inClipStride, UInt32* outWords);
 /* Same, but inSamples and outWords are DEVICE pointers on the detective's device and the work is enqueued on
  * inStream (a cudaStream_t, NULL = the detective's own stream) without synchronising. */
 LBAD_API OSStatus LBAudioDetectiveProcessPCMBatchDevice(LBAudioDetectiveRef inDetective, const Float32* inDeviceSamples, UInt32 inNumberOfClips, UInt64 inFramesPerClip, UInt64 inClipStride, UInt32* outDeviceWords, void* inStream);
@@ -102,6 +105,21 @@ LBAD_API OSStatus LBAudioDetectiveProcessPCMStages(LBAudioDetectiveRef inDetecti
 /* Haar transform (Frame.m:113-153) + ordered top-t sign extraction (Frame.m:165-191) of inCount host images
  * [128][B]; outHaar [inCount][128][B] and outBooleans [inCount][L] may be NULL. */
 LBAD_API OSStatus LBAudioDetectiveTransformImages(LBAudioDetectiveRef inDetective, const Float32* inImages, UInt32 inCount, Float32* outHaar, Boolean* outBooleans);
+/* ---- streaming extraction (addition): the recording use case of the essay (p.23-24) without the whole-clip requirement ---- */
+typedef struct LBAudioDetectiveStream *LBAudioDetectiveStreamRef;
+/* Borrows inDetective (which must outlive the stream and keep its window / stride / subfingerprint length); NULL if its
+ * configuration is unsupported. */
+LBAD_API LBAudioDetectiveStreamRef LBAudioDetectiveStreamNew(LBAudioDetectiveRef inDetective);
+LBAD_API OSStatus LBAudioDetectiveStreamDispose(LBAudioDetectiveStreamRef inStream);
+/* Appends PCM; every frame that the one-shot LBAudioDetectiveProcessPCM would produce for the samples appended so far is
+ * extracted (on the GPU) and added to the stream's fingerprint — after any sequence of appends the fingerprint equals the one-shot
+ * result on the concatenation. */
+LBAD_API OSStatus LBAudioDetectiveStreamAppend(LBAudioDetectiveStreamRef inStream, const Float32* inSamples, UInt64 inNumberFrames);
+/* The growing fingerprint, owned by the stream (copy it to keep it past Dispose). */
+LBAD_API LBAudioDetectiveFingerprintRef LBAudioDetectiveStreamGetFingerprint(LBAudioDetectiveStreamRef inStream);
+/* Samples buffered and not yet covered by an emitted subfingerprint. */
+LBAD_API UInt64 LBAudioDetectiveStreamGetNumberOfPendingFrames(LBAudioDetectiveStreamRef inStream);
+
 /* Kernels launched by this detective since creation (for bench.py's gpu_launches). */
 LBAD_API UInt64 LBAudioDetectiveGetKernelLaunchCount(LBAudioDetectiveRef inDetective);
 /* Total device time in ms of the dominant extraction kernel (FFT + band energies) over the launches since the last

@@ -10,6 +10,7 @@
 
 #if !defined(__MACTYPES__) && !defined(LBAD_HAVE_APPLE_TYPES)
 typedef uint8_t  UInt8;
+typedef int16_t  SInt16;
 typedef uint32_t UInt32;
 typedef int32_t  SInt32;
 typedef uint64_t UInt64;

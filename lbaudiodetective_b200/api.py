@@ -63,9 +63,15 @@ def load_library(build_if_missing: bool = True):
         "LBAudioDetectiveGetNumberOfSubfingerprintsForLength": (u64, [vp, u64]),
         "LBAudioDetectiveGetBandTable": (C.c_int32, [vp, vp, vp, vp]),
         "LBAudioDetectiveProcessPCMBatch": (C.c_int32, [vp, vp, u32, u64, u64, vp]),
+        "LBAudioDetectiveProcessPCMBatchInt16": (C.c_int32, [vp, vp, u32, u64, u64, vp]),
         "LBAudioDetectiveProcessPCMBatchDevice": (C.c_int32, [vp, vp, u32, u64, u64, vp, vp]),
         "LBAudioDetectiveProcessPCMStages": (C.c_int32, [vp, vp, u64, vp, vp, vp, u8]),
         "LBAudioDetectiveTransformImages": (C.c_int32, [vp, vp, u32, vp, vp]),
+        "LBAudioDetectiveStreamNew": (vp, [vp]),
+        "LBAudioDetectiveStreamDispose": (C.c_int32, [vp]),
+        "LBAudioDetectiveStreamAppend": (C.c_int32, [vp, vp, u64]),
+        "LBAudioDetectiveStreamGetFingerprint": (vp, [vp]),
+        "LBAudioDetectiveStreamGetNumberOfPendingFrames": (u64, [vp]),
         "LBAudioDetectiveGetKernelLaunchCount": (u64, [vp]),
         "LBAudioDetectiveGetKernelTiming": (u32, [vp, u8, u8, P(f64)]),
         "LBAudioDetectiveGetTransformKernelTiming": (u32, [vp, u8, u8, P(f64)]),
@@ -322,6 +328,17 @@ class Detective:
         _check(self._L.LBAudioDetectiveProcessPCMBatch(self.ref, _ptr(pcm2d), n_clips, clip_len, clip_len, _ptr(out_words)), "LBAudioDetectiveProcessPCMBatch")
         return out_words
 
+    def process_batch_int16(self, pcm2d):
+        """Host [clips][samples] int16 -> packed words (converted on the device as x / 32768)."""
+        pcm2d = np.ascontiguousarray(pcm2d, dtype=np.int16); n_clips, clip_len = pcm2d.shape
+        n = self.subfingerprints_for_length(clip_len); W = words_per_plane(self.subfingerprint_length)
+        out = np.zeros((n_clips, n, 2 * W), np.uint32)
+        _check(self._L.LBAudioDetectiveProcessPCMBatchInt16(self.ref, _ptr(pcm2d), n_clips, clip_len, clip_len, _ptr(out)), "LBAudioDetectiveProcessPCMBatchInt16")
+        return out
+
+    def process_batch_int16_ptr(self, host_ptr, n_clips, clip_len, clip_stride, out_ptr):
+        _check(self._L.LBAudioDetectiveProcessPCMBatchInt16(self.ref, host_ptr, n_clips, clip_len, clip_stride, out_ptr), "LBAudioDetectiveProcessPCMBatchInt16")
+
     def process_batch_ptr(self, host_ptr, n_clips, clip_len, clip_stride, out_ptr):
         _check(self._L.LBAudioDetectiveProcessPCMBatch(self.ref, host_ptr, n_clips, clip_len, clip_stride, out_ptr), "LBAudioDetectiveProcessPCMBatch")
 
@@ -351,6 +368,38 @@ class Detective:
         fn = self._L.LBAudioDetectiveGetTransformKernelTiming if transform else self._L.LBAudioDetectiveGetKernelTiming
         n = fn(self.ref, 1 if enable else 0, 1 if reset else 0, C.byref(ms))
         return int(n), float(ms.value)
+
+
+class Stream:
+    """LBAudioDetectiveStreamRef: append PCM, subfingerprints appear as frames complete."""
+
+    def __init__(self, detective):
+        self._L = lib(); self.detective = detective
+        self.ref = self._L.LBAudioDetectiveStreamNew(detective.ref)
+        if not self.ref:
+            raise LBADError(ARGUMENT_INVALID, "LBAudioDetectiveStreamNew")
+
+    def dispose(self):
+        if self.ref:
+            self._L.LBAudioDetectiveStreamDispose(self.ref); self.ref = None
+
+    def __del__(self):
+        try:
+            self.dispose()
+        except Exception:
+            pass
+
+    def append(self, pcm):
+        pcm = _f32(pcm)
+        _check(self._L.LBAudioDetectiveStreamAppend(self.ref, _ptr(pcm), pcm.size), "LBAudioDetectiveStreamAppend")
+
+    def fingerprint(self):
+        """A copy of the stream's fingerprint so far."""
+        return Fingerprint(_ref=self._L.LBAudioDetectiveFingerprintCopy(self._L.LBAudioDetectiveStreamGetFingerprint(self.ref)))
+
+    @property
+    def pending(self):
+        return int(self._L.LBAudioDetectiveStreamGetNumberOfPendingFrames(self.ref))
 
 
 class Database:

@@ -233,6 +233,14 @@ OSStatus LBAudioDetectiveProcessPCMBatch(LBAudioDetectiveRef d, const Float32* i
     return lbad_status(lbadcu_extract_host(d->plan, inSamples, nClips, framesPerClip, clipStride, outWords, NULL, NULL, 0));
 }
 
+OSStatus LBAudioDetectiveProcessPCMBatchInt16(LBAudioDetectiveRef d, const SInt16* inSamples, UInt32 nClips, UInt64 framesPerClip, UInt64 clipStride, UInt32* outWords) {
+    if (!d || !inSamples || !outWords || nClips == 0 || clipStride < framesPerClip) return kLBAudioDetectiveArgumentInvalid;
+    OSStatus e = ensure_plan(d);
+    if (e != noErr) return e;
+    if (framesPerClip < d->windowSize) return kLBAudioDetectiveArgumentInvalid;
+    return lbad_status(lbadcu_extract_host_i16(d->plan, inSamples, nClips, framesPerClip, clipStride, outWords));
+}
+
 OSStatus LBAudioDetectiveProcessPCMBatchDevice(LBAudioDetectiveRef d, const Float32* dSamples, UInt32 nClips, UInt64 framesPerClip, UInt64 clipStride, UInt32* dWords, void* stream) {
     if (!d || !dSamples || !dWords || nClips == 0 || clipStride < framesPerClip) return kLBAudioDetectiveArgumentInvalid;
     OSStatus e = ensure_plan(d);
@@ -287,3 +295,66 @@ UInt32 LBAudioDetectiveGetTransformKernelTiming(LBAudioDetectiveRef d, Boolean i
     if (!d || ensure_plan(d) != noErr) return 0;
     return lbadcu_plan_timing(d->plan, 1, inEnable, inReset, outTotalMilliseconds);
 }
+
+/* ---- streaming extraction (addition): append PCM, a subfingerprint is emitted for every completed frame ---- */
+
+struct LBAudioDetectiveStream {
+    LBAudioDetectiveRef detective;              /* borrowed: configuration + device plan */
+    LBAudioDetectiveFingerprintRef fingerprint; /* grows as frames complete */
+    Float32* pending;                           /* samples from the start of the first frame not yet emitted */
+    UInt64 pendingCount, pendingCapacity;
+    UInt64 totalFrames;                         /* samples appended so far */
+    UInt64 emitted;                             /* subfingerprints emitted so far */
+    UInt32 window, stride, sublen;              /* geometry frozen at creation */
+};
+
+LBAudioDetectiveStreamRef LBAudioDetectiveStreamNew(LBAudioDetectiveRef d) {
+    if (!d || LBAudioDetectiveCheckConfiguration(d) != noErr) return NULL;
+    LBAudioDetectiveStreamRef s = calloc(1, sizeof *s);
+    if (!s) return NULL;
+    s->detective = d; s->window = d->windowSize; s->stride = d->analysisStride; s->sublen = d->subfingerprintLength;
+    s->fingerprint = LBAudioDetectiveFingerprintNew(0);
+    UInt32 L = s->sublen;
+    LBAudioDetectiveFingerprintSetSubfingerprintLength(s->fingerprint, &L);
+    return s;
+}
+
+OSStatus LBAudioDetectiveStreamDispose(LBAudioDetectiveStreamRef s) {
+    if (!s) return kLBAudioDetectiveArgumentInvalid;
+    LBAudioDetectiveFingerprintDispose(s->fingerprint);
+    free(s->pending); free(s);
+    return noErr;
+}
+
+OSStatus LBAudioDetectiveStreamAppend(LBAudioDetectiveStreamRef s, const Float32* inSamples, UInt64 inNumberFrames) {
+    if (!s || (!inSamples && inNumberFrames)) return kLBAudioDetectiveArgumentInvalid;
+    LBAudioDetectiveRef d = s->detective;
+    if (d->windowSize != s->window || d->analysisStride != s->stride || d->subfingerprintLength != s->sublen) return kLBAudioDetectiveArgumentInvalid;
+    if (s->pendingCount + inNumberFrames > s->pendingCapacity) {
+        UInt64 cap = s->pendingCapacity ? s->pendingCapacity * 2 : 65536;
+        while (cap < s->pendingCount + inNumberFrames) cap *= 2;
+        Float32* p = realloc(s->pending, cap * sizeof(Float32));
+        if (!p) return kLBAudioDetectiveArgumentInvalid;
+        s->pending = p; s->pendingCapacity = cap;
+    }
+    memcpy(s->pending + s->pendingCount, inSamples, inNumberFrames * sizeof(Float32));
+    s->pendingCount += inNumberFrames; s->totalFrames += inNumberFrames;
+    /* frames the one-shot path would produce for everything appended so far (m:250-255), minus those already emitted;
+     * the pending buffer starts at sample 128*stride*emitted, so processing it as one clip yields exactly the new ones */
+    UInt64 available = LBAudioDetectiveGetNumberOfSubfingerprintsForLength(d, s->totalFrames);
+    if (available <= s->emitted) return noErr;
+    UInt64 fresh = available - s->emitted;
+    LBAudioDetectiveFingerprintRef part = NULL;
+    OSStatus e = LBAudioDetectiveProcessPCM(d, s->pending, s->pendingCount, &part);
+    if (e == noErr && part->subfingerprintCount != fresh) e = kLBAudioDetectiveDeviceError;
+    if (e == noErr) e = lbad_fingerprint_append_packed(s->fingerprint, part->words, part->subfingerprintCount);
+    LBAudioDetectiveFingerprintDispose(part);
+    if (e != noErr) return e;
+    UInt64 consumed = fresh * kLBAudioDetectiveDefaultNumberOfRowsPerFrame * s->stride;
+    memmove(s->pending, s->pending + consumed, (s->pendingCount - consumed) * sizeof(Float32));
+    s->pendingCount -= consumed; s->emitted = available;
+    return noErr;
+}
+
+LBAudioDetectiveFingerprintRef LBAudioDetectiveStreamGetFingerprint(LBAudioDetectiveStreamRef s) { return s ? s->fingerprint : NULL; }
+UInt64 LBAudioDetectiveStreamGetNumberOfPendingFrames(LBAudioDetectiveStreamRef s) { return s ? s->pendingCount : 0; }

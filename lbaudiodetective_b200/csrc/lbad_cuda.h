@@ -57,6 +57,8 @@ int  lbadcu_extract_device(lbadcu_plan* p, const float* d_pcm, uint32_t n_clips,
 /* Host-memory front end: uploads in chunks on two streams, runs the kernels, downloads the packed words. */
 int  lbadcu_extract_host(lbadcu_plan* p, const float* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
                          uint32_t* h_words, float* h_images, float* h_haar, int mode);
+/* same for signed 16-bit PCM (uploaded as 2 bytes per sample, converted on the device as x / 32768) */
+int  lbadcu_extract_host_i16(lbadcu_plan* p, const int16_t* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride, uint32_t* h_words);
 /* Haar + top-t + pack on device images [count][128][B] (generic kernel). */
 int  lbadcu_transform_images_host(lbadcu_plan* p, const float* h_images, uint32_t count, float* h_haar, uint32_t* h_words);
 

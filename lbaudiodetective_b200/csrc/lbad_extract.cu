@@ -293,7 +293,6 @@ constexpr int STATIC_HALF0 = 9, STATIC_HALF1 = 25;     /* longest half-band of b
 
 constexpr int FUSED_WARPS = 8;
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;
-constexpr int FUSED_LD = 33;                 /* image row stride (floats) */
 constexpr int SCR_LDF = 36;                  /* transpose scratch row stride (floats): LDS.128-aligned and conflict-free */
 
 struct FusedSmemLayout {
@@ -683,7 +682,8 @@ struct lbadcu_plan {
     cudaStream_t stream = nullptr, copy_streams[3] = {nullptr, nullptr, nullptr};
     float2 *d_tw_m = nullptr, *d_tw_n = nullptr; float4 *d_tw1 = nullptr, *d_tw2 = nullptr;
     bool static_range = false;
-    float* d_scratch_images = nullptr; size_t scratch_frames = 0;
+    float* d_scratch[4] = {nullptr, nullptr, nullptr, nullptr}; size_t scratch_frames[4] = {0, 0, 0, 0};   /* spectral images: slot 0 for device-API calls, 1..3 for the host pipeline's chunk buffers */
+    int16_t* d_chunk_i16[3] = {nullptr, nullptr, nullptr}; size_t chunk_i16 = 0;
     float* d_chunk_pcm[3] = {nullptr, nullptr, nullptr}; uint32_t* d_chunk_words[3] = {nullptr, nullptr, nullptr};
     size_t chunk_pcm_floats = 0, chunk_words = 0;
     bool fused_ok = false; int sm_count = 0; size_t smem_optin = 0;
@@ -764,7 +764,7 @@ extern "C" void lbadcu_plan_destroy(lbadcu_plan* p) {
     cudaSetDevice(p->device);
     cudaStreamSynchronize(p->stream);
     p->timer.clear(); p->timer2.clear();
-    cudaFree(p->d_tw_m); cudaFree(p->d_tw_n); cudaFree(p->d_tw1); cudaFree(p->d_tw2); cudaFree(p->d_scratch_images);
+    cudaFree(p->d_tw_m); cudaFree(p->d_tw_n); cudaFree(p->d_tw1); cudaFree(p->d_tw2); for (int i = 0; i < 4; i++) cudaFree(p->d_scratch[i]); for (int i = 0; i < 3; i++) cudaFree(p->d_chunk_i16[i]);
     for (int i = 0; i < 3; i++) { cudaFree(p->d_chunk_pcm[i]); cudaFree(p->d_chunk_words[i]); if (p->copy_streams[i]) cudaStreamDestroy(p->copy_streams[i]); }
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -802,8 +802,17 @@ static int haar_select_dispatch(lbadcu_plan* p, const float* d_images, float* d_
     return LBAD_ERR_ARG;
 }
 
+static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
+                               uint32_t* d_words, float* d_images, float* d_haar, int mode, void* stream, int slot);
+
 extern "C" int lbadcu_extract_device(lbadcu_plan* p, const float* d_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
                                      uint32_t* d_words, float* d_images, float* d_haar, int mode, void* stream) {
+    return extract_device_slot(p, d_pcm, n_clips, clip_len, clip_stride, d_words, d_images, d_haar, mode, stream, 0);
+}
+
+/* slot: which scratch buffer holds the spectral images between the two kernels — concurrent streams must not share one */
+static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
+                               uint32_t* d_words, float* d_images, float* d_haar, int mode, void* stream, int slot) {
     if (!p || !d_pcm || !d_words) return LBAD_ERR_ARG;
     if (clip_len < p->g.window) return LBAD_ERR_ARG;
     LBAD_CUDA_TRY(cudaSetDevice(p->device));
@@ -830,15 +839,15 @@ extern "C" int lbadcu_extract_device(lbadcu_plan* p, const float* d_pcm, uint32_
         if (per_sm < 1) per_sm = 1;
         const uint32_t cap = (uint32_t)(p->sm_count * per_sm);
         const uint32_t slab_frames = d_images ? total_frames : (total_frames < (1u << 18) ? total_frames : (1u << 18));   /* <= 4 GB of images */
-        if (!d_images && p->scratch_frames < slab_frames) {
+        if (!d_images && p->scratch_frames[slot] < slab_frames) {
             LBAD_CUDA_TRY(cudaStreamSynchronize(s));
-            cudaFree(p->d_scratch_images); p->d_scratch_images = nullptr; p->scratch_frames = 0;
-            LBAD_CUDA_TRY(cudaMalloc(&p->d_scratch_images, (size_t)slab_frames * LBAD_ROWS_PER_FRAME * LBAD_MAX_BANDS * sizeof(float)));
-            p->scratch_frames = slab_frames;
+            cudaFree(p->d_scratch[slot]); p->d_scratch[slot] = nullptr; p->scratch_frames[slot] = 0;
+            LBAD_CUDA_TRY(cudaMalloc(&p->d_scratch[slot], (size_t)slab_frames * LBAD_ROWS_PER_FRAME * 32 * sizeof(float)));
+            p->scratch_frames[slot] = slab_frames;
         }
         for (uint32_t f0 = 0; f0 < total_frames; f0 += slab_frames) {
             const uint32_t nf = total_frames - f0 < slab_frames ? total_frames - f0 : slab_frames;
-            float* imgs = d_images ? d_images : p->d_scratch_images;
+            float* imgs = d_images ? d_images : p->d_scratch[slot];
             /* a slab starts at frame f0 of the flattened (clip, frame) order: hand the kernel a view that starts there */
             Geo gs = g;
             const uint32_t grid = nf < cap ? nf : cap;
@@ -866,18 +875,18 @@ extern "C" int lbadcu_extract_device(lbadcu_plan* p, const float* d_pcm, uint32_
         const uint64_t want_clips = 8192 / frames_per_clip ? 8192 / frames_per_clip : 1;      /* ~8192 frames (128 MB at B=32) per slab */
         clips_per_slab = (uint32_t)(want_clips < n_clips ? want_clips : n_clips);
         const size_t need = (size_t)clips_per_slab * frames_per_clip;
-        if (p->scratch_frames < need) {
+        if (p->scratch_frames[slot] < need * 2) {                         /* sized for 64 bands: twice the 32-band frame size */
             LBAD_CUDA_TRY(cudaStreamSynchronize(s));
-            cudaFree(p->d_scratch_images); p->d_scratch_images = nullptr; p->scratch_frames = 0;
-            LBAD_CUDA_TRY(cudaMalloc(&p->d_scratch_images, need * LBAD_ROWS_PER_FRAME * LBAD_MAX_BANDS * sizeof(float)));
-            p->scratch_frames = need;
+            cudaFree(p->d_scratch[slot]); p->d_scratch[slot] = nullptr; p->scratch_frames[slot] = 0;
+            LBAD_CUDA_TRY(cudaMalloc(&p->d_scratch[slot], need * 2 * LBAD_ROWS_PER_FRAME * 32 * sizeof(float)));
+            p->scratch_frames[slot] = need * 2;
         }
     }
     for (uint32_t c0 = 0; c0 < n_clips; c0 += clips_per_slab) {
         const uint32_t nc = (n_clips - c0) < clips_per_slab ? (n_clips - c0) : clips_per_slab;
         const uint32_t nf = (uint32_t)(nc * frames_per_clip);
         const uint64_t nw = (uint64_t)nf * LBAD_ROWS_PER_FRAME;
-        float* imgs = d_images ? d_images + (size_t)c0 * frames_per_clip * LBAD_ROWS_PER_FRAME * g.bands : p->d_scratch_images;
+        float* imgs = d_images ? d_images + (size_t)c0 * frames_per_clip * LBAD_ROWS_PER_FRAME * g.bands : p->d_scratch[slot];
         const uint64_t want = (nw + GEN_WARPS - 1) / GEN_WARPS;
         const uint32_t grid = (uint32_t)(want < (uint64_t)p->sm_count * 16 ? want : (uint64_t)p->sm_count * 16);
         p->timer.begin(s);
@@ -909,32 +918,43 @@ extern "C" int lbadcu_transform_images_host(lbadcu_plan* p, const float* h_image
     return e;
 }
 
+__global__ void i16_to_f32_kernel(const int16_t* __restrict__ in, float* __restrict__ out, const size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (float)in[i] * (1.0f / 32768.0f);
+}
+
 /* Host-memory front end.  Clips are processed in chunks on three streams so that the H2D copy of chunk i+1, the
- * kernels of chunk i and the D2H of chunk i-1 overlap (they do when the caller's buffers are pinned). */
-extern "C" int lbadcu_extract_host(lbadcu_plan* p, const float* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
-                                   uint32_t* h_words, float* h_images, float* h_haar, int mode) {
-    if (!p || !h_pcm || !h_words || n_clips == 0) return LBAD_ERR_ARG;
+ * kernels of chunk i and the D2H of chunk i-1 overlap (they do when the caller's buffers are pinned).  Each chunk
+ * buffer has its own spectral-image scratch (slots 1..3), because the streams run concurrently.
+ * sample_bytes: 4 = float32 PCM, 2 = signed 16-bit PCM (converted on the device as x / 32768, which is exact). */
+static int extract_host_impl(lbadcu_plan* p, const void* h_pcm_v, int sample_bytes, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
+                             uint32_t* h_words, float* h_images, float* h_haar, int mode) {
+    if (!p || !h_pcm_v || !h_words || n_clips == 0) return LBAD_ERR_ARG;
     if (clip_len < p->g.window) return LBAD_ERR_ARG;
     LBAD_CUDA_TRY(cudaSetDevice(p->device));
+    const char* h_pcm = static_cast<const char*>(h_pcm_v);
     const uint64_t frames_per_clip = ((clip_len - p->g.window) / p->g.stride) / LBAD_ROWS_PER_FRAME;
     if (frames_per_clip == 0) return LBAD_OK;
     const size_t words_per_clip = (size_t)frames_per_clip * 2 * p->g.words_per_plane;
     const size_t img_per_clip = (size_t)frames_per_clip * LBAD_ROWS_PER_FRAME * p->g.bands;
-    const uint64_t clip_pad = (clip_len + 3) & ~3ull;                  /* device clip stride: keeps every clip 16-byte aligned */
-    uint64_t clips_per_chunk = (48ull << 20) / clip_pad;                /* ~192 MB of PCM per chunk */
+    const uint64_t clip_pad = (clip_len + 7) & ~7ull;                  /* device clip stride: keeps every clip 16-byte aligned in both sample formats */
+    uint64_t clips_per_chunk = (48ull << 20) / clip_pad;                /* ~192 MB of float PCM per chunk */
     if (clips_per_chunk < 1) clips_per_chunk = 1;
     if (clips_per_chunk > n_clips) clips_per_chunk = n_clips;
     const size_t need_pcm = (size_t)clips_per_chunk * clip_pad, need_words = (size_t)clips_per_chunk * words_per_clip;
     const int nbuf = n_clips > clips_per_chunk ? 3 : 1;
-    if (p->chunk_pcm_floats < need_pcm || p->chunk_words < need_words) {
-        for (int i = 0; i < 3; i++) { cudaFree(p->d_chunk_pcm[i]); cudaFree(p->d_chunk_words[i]); p->d_chunk_pcm[i] = nullptr; p->d_chunk_words[i] = nullptr; }
-        p->chunk_pcm_floats = p->chunk_words = 0;
+    if (p->chunk_pcm_floats < need_pcm || p->chunk_words < need_words || (sample_bytes == 2 && p->chunk_i16 < need_pcm)) {
+        for (int i = 0; i < 3; i++) {
+            cudaFree(p->d_chunk_pcm[i]); cudaFree(p->d_chunk_words[i]); cudaFree(p->d_chunk_i16[i]);
+            p->d_chunk_pcm[i] = nullptr; p->d_chunk_words[i] = nullptr; p->d_chunk_i16[i] = nullptr;
+        }
+        p->chunk_pcm_floats = p->chunk_words = p->chunk_i16 = 0;
     }
     for (int i = 0; i < nbuf; i++) {
         if (!p->d_chunk_pcm[i]) LBAD_CUDA_TRY(cudaMalloc(&p->d_chunk_pcm[i], need_pcm * sizeof(float)));
         if (!p->d_chunk_words[i]) LBAD_CUDA_TRY(cudaMalloc(&p->d_chunk_words[i], need_words * sizeof(uint32_t)));
+        if (sample_bytes == 2 && !p->d_chunk_i16[i]) LBAD_CUDA_TRY(cudaMalloc(&p->d_chunk_i16[i], need_pcm * sizeof(int16_t)));
     }
-    p->chunk_pcm_floats = need_pcm; p->chunk_words = need_words;
+    p->chunk_pcm_floats = need_pcm; p->chunk_words = need_words; if (sample_bytes == 2) p->chunk_i16 = need_pcm;
     float *d_img = nullptr, *d_haar = nullptr;
     if (h_images) LBAD_CUDA_TRY(cudaMalloc(&d_img, (size_t)clips_per_chunk * img_per_clip * sizeof(float)));
     if (h_haar) LBAD_CUDA_TRY(cudaMalloc(&d_haar, (size_t)clips_per_chunk * img_per_clip * sizeof(float)));
@@ -944,10 +964,16 @@ extern "C" int lbadcu_extract_host(lbadcu_plan* p, const float* h_pcm, uint32_t 
         const uint32_t nc = (uint32_t)((n_clips - c0) < clips_per_chunk ? (n_clips - c0) : clips_per_chunk);
         const int b = (int)(chunk % (uint32_t)nbuf);
         cudaStream_t s = nbuf == 1 ? p->stream : p->copy_streams[b];
-        if (clip_stride == clip_pad) LBAD_CUDA_TRY(cudaMemcpyAsync(p->d_chunk_pcm[b], h_pcm + c0 * clip_stride, (size_t)nc * clip_pad * sizeof(float), cudaMemcpyHostToDevice, s));
-        else LBAD_CUDA_TRY(cudaMemcpy2DAsync(p->d_chunk_pcm[b], clip_pad * sizeof(float), h_pcm + c0 * clip_stride, clip_stride * sizeof(float),
-                                             clip_len * sizeof(float), nc, cudaMemcpyHostToDevice, s));
-        rc = lbadcu_extract_device(p, p->d_chunk_pcm[b], nc, clip_len, clip_pad, p->d_chunk_words[b], d_img, d_haar, mode, s);
+        void* d_in = sample_bytes == 2 ? static_cast<void*>(p->d_chunk_i16[b]) : static_cast<void*>(p->d_chunk_pcm[b]);
+        const char* src = h_pcm + c0 * clip_stride * sample_bytes;
+        if (clip_stride == clip_pad) LBAD_CUDA_TRY(cudaMemcpyAsync(d_in, src, (size_t)nc * clip_pad * sample_bytes, cudaMemcpyHostToDevice, s));
+        else LBAD_CUDA_TRY(cudaMemcpy2DAsync(d_in, clip_pad * sample_bytes, src, clip_stride * sample_bytes, clip_len * sample_bytes, nc, cudaMemcpyHostToDevice, s));
+        if (sample_bytes == 2) {
+            i16_to_f32_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->d_chunk_i16[b], p->d_chunk_pcm[b], (size_t)nc * clip_pad);
+            p->launches++;
+            LBAD_CUDA_TRY(cudaGetLastError());
+        }
+        rc = extract_device_slot(p, p->d_chunk_pcm[b], nc, clip_len, clip_pad, p->d_chunk_words[b], d_img, d_haar, mode, s, 1 + b);
         if (rc != LBAD_OK) break;
         LBAD_CUDA_TRY(cudaMemcpyAsync(h_words + c0 * words_per_clip, p->d_chunk_words[b], (size_t)nc * words_per_clip * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         if (h_images) LBAD_CUDA_TRY(cudaMemcpyAsync(h_images + c0 * img_per_clip, d_img, (size_t)nc * img_per_clip * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -958,4 +984,13 @@ extern "C" int lbadcu_extract_host(lbadcu_plan* p, const float* h_pcm, uint32_t 
     LBAD_CUDA_TRY(cudaStreamSynchronize(p->stream));
     cudaFree(d_img); cudaFree(d_haar);
     return rc;
+}
+
+extern "C" int lbadcu_extract_host(lbadcu_plan* p, const float* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
+                                   uint32_t* h_words, float* h_images, float* h_haar, int mode) {
+    return extract_host_impl(p, h_pcm, 4, n_clips, clip_len, clip_stride, h_words, h_images, h_haar, mode);
+}
+
+extern "C" int lbadcu_extract_host_i16(lbadcu_plan* p, const int16_t* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride, uint32_t* h_words) {
+    return extract_host_impl(p, h_pcm, 2, n_clips, clip_len, clip_stride, h_words, nullptr, nullptr, 0);
 }

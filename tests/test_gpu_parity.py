@@ -187,6 +187,33 @@ def test_device_resident_batch(lb, port):
     assert d.kernel_launches >= 2
 
 
+def test_int16_batch_equals_float_batch(lb, port):
+    """Signed 16-bit PCM uploaded as 2 bytes per sample and converted on the device (x / 32768, exact) gives the same words."""
+    d = lb.Detective()
+    f = np.stack([port.synth_clip(80 + i, 55120) for i in range(4)])
+    i16 = np.clip(np.round(f * 32767.0), -32768, 32767).astype(np.int16)
+    assert np.array_equal(d.process_batch_int16(i16), d.process_batch(i16.astype(np.float32) / np.float32(32768.0)))
+    odd = np.ascontiguousarray(i16[:, :55003])
+    assert np.array_equal(d.process_batch_int16(odd), d.process_batch(odd.astype(np.float32) / np.float32(32768.0)))
+
+
+def test_streaming_equals_one_shot(lb, port):
+    """Any chunking of the PCM gives the one-shot fingerprint at every prefix (frame emission follows m:250-255 exactly)."""
+    d = lb.Detective(); pcm = port.synth_clip(90, 100000); rng = np.random.default_rng(15)
+    s = lb.Stream(d); pos = 0
+    while pos < len(pcm):
+        n = int(rng.choice([1, 63, 64, 1000, 8192, 10175, 10176, 20000])); n = min(n, len(pcm) - pos)
+        s.append(pcm[pos:pos + n]); pos += n
+        want = d.subfingerprints_for_length(pos)
+        fp = s.fingerprint()
+        assert fp.count == want and s.pending == pos - want * 8192
+        if n >= 8192 and want:
+            assert fp.equal(d.process_pcm(pcm[:pos]))
+    assert s.fingerprint().equal(d.process_pcm(pcm)) and s.fingerprint().count == 11
+    s2 = lb.Stream(d); s2.append(pcm[:10239]); assert s2.fingerprint().count == 0
+    s2.append(pcm[10239:10240]); assert s2.fingerprint().count == 1          # exactly the reference's threshold: 128*64 + 2048 samples
+
+
 # --------------------------------------------------------------------- matching ----
 
 def test_compare_toy_vectors(lb, kat):
