@@ -99,14 +99,19 @@ __device__ __forceinline__ uint32_t popc_words(const uint32_t (&h)[W]) {
 
 /* per database subfingerprint: (float)possible and RN(1/possible) over the FULL length — what every unmasked compare needs */
 template <int W>
-__global__ void meta_kernel(const uint32_t* __restrict__ db, float2* __restrict__ meta, const uint64_t first, const uint64_t count) {
+__global__ void meta_kernel(const uint32_t* __restrict__ db, float2* __restrict__ meta, const uint64_t first, const uint64_t count,
+                            const uint32_t pairs_full, uint32_t* __restrict__ irregular) {
+    uint32_t bad = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t* src = db + (first + i) * 2 * W;
-        uint32_t possible = 0;
+        uint32_t possible = 0, both = 0;
 #pragma unroll
-        for (int w = 0; w < W; w++) possible += __popc(src[w] | src[W + w]);
+        for (int w = 0; w < W; w++) { possible += __popc(src[w] | src[W + w]); both |= src[w] & src[W + w]; }
         meta[first + i] = make_float2((float)possible, c_rcp[possible]);
+        bad += (possible != pairs_full || both != 0) ? 1u : 0u;
     }
+    bad = __reduce_add_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(irregular, bad);
 }
 
 constexpr int STAGE_SUBFPS = 128;          /* database subfingerprints staged in shared memory per tile (whole clips only) */
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
 search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ meta, const uint32_t* __restrict__ offsets, const uint32_t n_clips,
                    const uint32_t clip_base, const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t pairs, const int k,
                    const uint32_t n_qgroups, const uint32_t clips_per_chunk, float* __restrict__ part_sc, uint32_t* __restrict__ part_id,
-                   float* __restrict__ all_scores, const uint32_t groups_per_chunk) {
+                   float* __restrict__ all_scores, const uint32_t groups_per_chunk, const int db_regular) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t chunk = blockIdx.x / groups_per_chunk, qg = (blockIdx.x % groups_per_chunk) * SEARCH_WARPS + wid;
@@ -153,6 +158,23 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
     const uint32_t c_begin = chunk * clips_per_chunk;
     const uint32_t c_end = min(n_clips, c_begin + clips_per_chunk);
     float worst = top.worst();
+    /* "Regular" codes: every one of the first `pairs` ranks carries exactly one sign bit, which is what extraction produces whenever
+     * the selected coefficients are non-zero.  Then M = ~P on those ranks, possible = pairs, and a pair hits iff the P bits agree:
+     * one LOP3 per word instead of two, no M plane, no per-subfingerprint (possible, 1/possible).  The database side is checked
+     * when it is appended (db_regular), the query side here; a warp takes the short form only if all of its queries qualify. */
+    bool regular = false;
+    if (!MASKED && db_regular) {
+        bool mine = true;
+#pragma unroll
+        for (int i = 0; i < CQ; i++) {
+            uint32_t both = 0, cover = 0;
+#pragma unroll
+            for (int w = 0; w < W; w++) { both |= qp[i][w] & qm[i][w]; cover += __popc(qp[i][w] | qm[i][w]); }
+            mine = mine && both == 0 && cover == pairs;
+        }
+        regular = __all_sync(0xffffffffu, mine || !qvalid);
+    }
+    const float reg_fposs = (float)pairs, reg_rcp = c_rcp[pairs <= 256 ? pairs : 0];
 
     /* tile = clips [c0, c1) whose subfingerprints [s_lo, s_hi) fit the staging buffer; every thread computes the same bounds */
     auto tile_end = [&](uint32_t c0) -> uint32_t {
@@ -184,7 +206,32 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
         if (qg < n_qgroups) for (uint32_t c = c0; c < c1; c++) {
             const uint32_t s0 = offsets[c] - s_lo, cnt = offsets[c + 1] - offsets[c];      /* warp-uniform */
             float best = 0.0f;                                                /* FP.m:133 */
-            for (uint32_t o = 0; o + CQ <= cnt; o++) {                        /* FP.m:136 */
+            if (regular) for (uint32_t o = 0; o + CQ <= cnt; o++) {            /* FP.m:136, short form */
+                float sum = 0.0f;
+#pragma unroll
+                for (int i = 0; i < CQ; i++) {
+                    const uint32_t* src = tw + (size_t)(s0 + o + i) * 2 * W;
+                    uint32_t h[W];
+                    if (W % 4 == 0) {
+#pragma unroll
+                        for (int w = 0; w < W; w += 4) {
+                            const uint4 a = *reinterpret_cast<const uint4*>(src + w);
+                            h[w] = lop3<0xC3>(a.x, qp[i][w], 0u) & mask.w[w]; h[w + 1] = lop3<0xC3>(a.y, qp[i][w + 1], 0u) & mask.w[w + 1];
+                            h[w + 2] = lop3<0xC3>(a.z, qp[i][w + 2], 0u) & mask.w[w + 2]; h[w + 3] = lop3<0xC3>(a.w, qp[i][w + 3], 0u) & mask.w[w + 3];
+                        }
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < W; w += 2) {
+                            const uint2 a = *reinterpret_cast<const uint2*>(src + w);
+                            h[w] = lop3<0xC3>(a.x, qp[i][w], 0u) & mask.w[w]; h[w + 1] = lop3<0xC3>(a.y, qp[i][w + 1], 0u) & mask.w[w + 1];
+                        }
+                    }
+                    sum = __fadd_rn(sum, ratio_exact(popc_words<W>(h), reg_fposs, reg_rcp));
+                }
+                const float mean = mean_exact<CQ>(sum);
+                best = (best < mean) ? mean : best;
+            }
+            else for (uint32_t o = 0; o + CQ <= cnt; o++) {                   /* FP.m:136 */
                 float sum = 0.0f;
 #pragma unroll
                 for (int i = 0; i < CQ; i++) {                                /* FP.m:139-142 */
@@ -341,6 +388,7 @@ struct lbadcu_db {
     std::vector<uint32_t> h_offsets{0};
     uint32_t* d_offsets = nullptr; size_t d_offsets_cap = 0; bool offsets_dirty = true;
     uint32_t min_count = 0xffffffffu, max_count = 0, base = 0;
+    bool regular = true; uint32_t* d_irregular = nullptr;    /* device counter of subfingerprints that are not "one sign bit per rank" */
     float* d_part_sc = nullptr; uint32_t* d_part_id = nullptr; size_t part_cap = 0;
     int sm_count = 0; size_t smem_optin = 0;
     uint64_t launches = 0;
@@ -373,7 +421,7 @@ extern "C" void lbadcu_db_destroy(lbadcu_db* db) {
     cudaSetDevice(db->device);
     cudaStreamSynchronize(db->stream);
     db->timer.clear();
-    cudaFree(db->d_words); cudaFree(db->d_meta); cudaFree(db->d_offsets); cudaFree(db->d_part_sc); cudaFree(db->d_part_id);
+    cudaFree(db->d_words); cudaFree(db->d_meta); cudaFree(db->d_irregular); cudaFree(db->d_offsets); cudaFree(db->d_part_sc); cudaFree(db->d_part_id);
     cudaStreamDestroy(db->stream);
     delete db;
 }
@@ -412,11 +460,16 @@ extern "C" int lbadcu_db_append(lbadcu_db* db, const uint32_t* words, int on_dev
                                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, db->stream));
     if (add) {
         const unsigned blocks = (unsigned)std::min<uint64_t>((add + 255) / 256, 4096);
-        if (db->W == 2) meta_kernel<2><<<blocks, 256, 0, db->stream>>>(db->d_words, db->d_meta, db->n_subfps, add);
-        else if (db->W == 4) meta_kernel<4><<<blocks, 256, 0, db->stream>>>(db->d_words, db->d_meta, db->n_subfps, add);
-        else meta_kernel<8><<<blocks, 256, 0, db->stream>>>(db->d_words, db->d_meta, db->n_subfps, add);
+        if (!db->d_irregular) { LBAD_CUDA_TRY(cudaMalloc(&db->d_irregular, sizeof(uint32_t))); LBAD_CUDA_TRY(cudaMemsetAsync(db->d_irregular, 0, sizeof(uint32_t), db->stream)); }
+        if (db->W == 2) meta_kernel<2><<<blocks, 256, 0, db->stream>>>(db->d_words, db->d_meta, db->n_subfps, add, db->pairs_full, db->d_irregular);
+        else if (db->W == 4) meta_kernel<4><<<blocks, 256, 0, db->stream>>>(db->d_words, db->d_meta, db->n_subfps, add, db->pairs_full, db->d_irregular);
+        else meta_kernel<8><<<blocks, 256, 0, db->stream>>>(db->d_words, db->d_meta, db->n_subfps, add, db->pairs_full, db->d_irregular);
         db->launches++;
         LBAD_CUDA_TRY(cudaGetLastError());
+        uint32_t irregular = 0;
+        LBAD_CUDA_TRY(cudaMemcpyAsync(&irregular, db->d_irregular, sizeof(uint32_t), cudaMemcpyDeviceToHost, db->stream));
+        LBAD_CUDA_TRY(cudaStreamSynchronize(db->stream));
+        db->regular = irregular == 0;
     }
     LBAD_CUDA_TRY(cudaStreamSynchronize(db->stream));
     db->h_offsets.reserve(db->h_offsets.size() + n_clips);
@@ -449,11 +502,11 @@ static void launch_fast(lbadcu_db* db, bool masked, uint32_t n_chunks, size_t sm
     if (masked) {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         search_fast_kernel<W, CQ, true><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
-                                                                                db->d_part_sc, db->d_part_id, d_all, total_warps);
+                                                                                db->d_part_sc, db->d_part_id, d_all, total_warps, db->regular ? 1 : 0);
     } else {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         search_fast_kernel<W, CQ, false><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
-                                                                                 db->d_part_sc, db->d_part_id, d_all, total_warps);
+                                                                                 db->d_part_sc, db->d_part_id, d_all, total_warps, db->regular ? 1 : 0);
     }
 }
 

@@ -283,6 +283,34 @@ def test_search_scores_and_topk_bit_exact(lb, checker, L, q_count, db_count, rng
     assert db.compares_per_query(q_count) == n_db * (abs(db_count - q_count) + 1) * min(db_count, q_count)
 
 
+@pytest.mark.parametrize("L,q_count,db_count", [(200, 6, 19), (200, 1, 5), (100, 3, 7), (400, 2, 9)])
+def test_search_regular_codes_short_form(lb, checker, L, q_count, db_count):
+    """Databases in which every rank carries exactly one sign bit take the kernel's short form (one LOP3 per word, no M plane);
+    warps whose queries do not all qualify fall back to the general form inside the same launch.  Both must be bit-exact."""
+    rng = np.random.default_rng(300 + L + q_count)
+    n_db, n_q, k = 500, 70, 7
+    dbb = rank_sign_codes(rng, n_db, db_count, L)                          # regular: exactly one of (P, M) per rank
+    qb = rank_sign_codes(rng, n_q, q_count, L)
+    for q in range(0, n_q, 2):
+        c = int(rng.integers(0, n_db)); o = int(rng.integers(0, db_count - q_count + 1))
+        qb[q] = dbb[c, o:o + q_count]; flip = rng.random((q_count, L // 2)) < 0.05
+        qb[q, :, 0::2] ^= flip.astype(np.uint8); qb[q, :, 1::2] ^= flip.astype(np.uint8)     # sign flips keep the codes regular
+    qb[40:, 0, 6] = 0; qb[40:, 0, 7] = 0                                    # queries 40.. get a '00' rank: their warps take the general form
+    qb[69, 0, 10] = 1; qb[69, 0, 11] = 1                                    # and one illegal '11'
+    db = lb.Database(L); db.add_packed(lb.pack_booleans(dbb))
+    sc, idx, full = db.search_packed(lb.pack_booleans(qb), k, all_scores=True)
+    want, _ = checker.search(dbb, qb, L)
+    assert np.array_equal(full, want)
+    order = np.lexsort((np.arange(n_db)[None, :].repeat(n_q, 0), -want.astype(np.float64)), axis=1)[:, :k]
+    assert np.array_equal(idx, order.astype(np.uint32)) and np.array_equal(sc, np.take_along_axis(want, order, axis=1))
+    # an irregular database (one '00' rank somewhere) must give the same answers through the general form
+    dbb2 = dbb.copy(); dbb2[123, 2, 0] = 0; dbb2[123, 2, 1] = 0
+    db2 = lb.Database(L); db2.add_packed(lb.pack_booleans(dbb2))
+    _, _, full2 = db2.search_packed(lb.pack_booleans(qb), k, all_scores=True)
+    want2, _ = checker.search(dbb2, qb, L)
+    assert np.array_equal(full2, want2)
+
+
 def test_search_ragged_database_and_fingerprint_api(lb, checker):
     rng = np.random.default_rng(12); L = 200
     counts = rng.integers(0, 25, size=120)
