@@ -174,7 +174,9 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
         }
         regular = __all_sync(0xffffffffu, mine || !qvalid);
     }
-    const float reg_fposs = (float)pairs, reg_rcp = c_rcp[pairs <= 256 ? pairs : 0];
+    float* ratio_tab = reinterpret_cast<float*>(st_meta + 2 * STAGE_SUBFPS);        /* [pairs + 1]: (float)h / (float)pairs */
+    for (uint32_t h = tid; h <= pairs; h += SEARCH_WARPS * 32) ratio_tab[h] = pairs ? __fdiv_rn((float)h, (float)pairs) : 0.0f;
+    /* (visible to every warp after the first __syncthreads of the tile loop) */
 
     /* tile = clips [c0, c1) whose subfingerprints [s_lo, s_hi) fit the staging buffer; every thread computes the same bounds */
     auto tile_end = [&](uint32_t c0) -> uint32_t {
@@ -216,17 +218,17 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
 #pragma unroll
                         for (int w = 0; w < W; w += 4) {
                             const uint4 a = *reinterpret_cast<const uint4*>(src + w);
-                            h[w] = lop3<0xC3>(a.x, qp[i][w], 0u) & mask.w[w]; h[w + 1] = lop3<0xC3>(a.y, qp[i][w + 1], 0u) & mask.w[w + 1];
-                            h[w + 2] = lop3<0xC3>(a.z, qp[i][w + 2], 0u) & mask.w[w + 2]; h[w + 3] = lop3<0xC3>(a.w, qp[i][w + 3], 0u) & mask.w[w + 3];
+                            h[w] = lop3<0x82>(a.x, qp[i][w], mask.w[w]); h[w + 1] = lop3<0x82>(a.y, qp[i][w + 1], mask.w[w + 1]);      /* ~(a ^ b) & mask */
+                            h[w + 2] = lop3<0x82>(a.z, qp[i][w + 2], mask.w[w + 2]); h[w + 3] = lop3<0x82>(a.w, qp[i][w + 3], mask.w[w + 3]);
                         }
                     } else {
 #pragma unroll
                         for (int w = 0; w < W; w += 2) {
                             const uint2 a = *reinterpret_cast<const uint2*>(src + w);
-                            h[w] = lop3<0xC3>(a.x, qp[i][w], 0u) & mask.w[w]; h[w + 1] = lop3<0xC3>(a.y, qp[i][w + 1], 0u) & mask.w[w + 1];
+                            h[w] = lop3<0x82>(a.x, qp[i][w], mask.w[w]); h[w + 1] = lop3<0x82>(a.y, qp[i][w + 1], mask.w[w + 1]);
                         }
                     }
-                    sum = __fadd_rn(sum, ratio_exact(popc_words<W>(h), reg_fposs, reg_rcp));
+                    sum = __fadd_rn(sum, ratio_tab[popc_words<W>(h)]);          /* hits / pairs, tabulated with the IEEE divide */
                 }
                 const float mean = mean_exact<CQ>(sum);
                 best = (best < mean) ? mean : best;
@@ -498,7 +500,7 @@ static void launch_fast(lbadcu_db* db, bool masked, uint32_t n_chunks, size_t sm
     const uint32_t n_clips = lbadcu_db_clips(db);
     const uint32_t total_warps = (n_qgroups + SEARCH_WARPS - 1) / SEARCH_WARPS;      /* = CTAs per clip chunk (passed in the last kernel argument) */
     const uint32_t blocks = n_chunks * total_warps;
-    const size_t smem = smem_topk + (size_t)2 * STAGE_SUBFPS * (2 * W * sizeof(uint32_t) + sizeof(float2));
+    const size_t smem = smem_topk + (size_t)2 * STAGE_SUBFPS * (2 * W * sizeof(uint32_t) + sizeof(float2)) + 260 * sizeof(float);
     if (masked) {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         search_fast_kernel<W, CQ, true><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
