@@ -690,6 +690,7 @@ struct lbadcu_plan {
     uint64_t launches = 0;
     LaunchTimer timer, timer2;      /* FFT+bands kernel / Haar+select kernel */
     int stage_mode = -1;      /* -1 auto, 0 plain loads, 1 TMA (env LBAD_STAGE=ldg|tma) */
+    uint32_t slab_frames_cap = 1u << 18;
 };
 
 extern "C" const char* lbadcu_last_error(void) { return g_err; }
@@ -755,6 +756,7 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     p->fused_ok = (N == 2048 && B == 32 && (geo->stride % 2 == 0) && span * 4 < (1u << 20) && fused_layout((uint32_t)span).total_bytes <= p->smem_optin);
     const char* st = getenv("LBAD_STAGE");
     p->stage_mode = st ? (strcmp(st, "tma") == 0 ? 1 : strcmp(st, "ldg") == 0 ? 0 : -1) : -1;
+    if (const char* sf = getenv("LBAD_SLAB_FRAMES")) { const unsigned long v = strtoul(sf, nullptr, 10); if (v >= 1 && v <= (1u << 18)) p->slab_frames_cap = (uint32_t)v; }
     *out = p;
     return LBAD_OK;
 }
@@ -838,7 +840,8 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
         LBAD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, L.total_bytes));
         if (per_sm < 1) per_sm = 1;
         const uint32_t cap = (uint32_t)(p->sm_count * per_sm);
-        const uint32_t slab_frames = d_images ? total_frames : (total_frames < (1u << 18) ? total_frames : (1u << 18));   /* <= 4 GB of images */
+        const uint32_t slab_cap = p->slab_frames_cap;                     /* <= 4 GB of images per slab (LBAD_SLAB_FRAMES overrides, for tests) */
+        const uint32_t slab_frames = d_images ? total_frames : (total_frames < slab_cap ? total_frames : slab_cap);
         if (!d_images && p->scratch_frames[slot] < slab_frames) {
             LBAD_CUDA_TRY(cudaStreamSynchronize(s));
             cudaFree(p->d_scratch[slot]); p->d_scratch[slot] = nullptr; p->scratch_frames[slot] = 0;

@@ -170,6 +170,17 @@ def test_batch_equals_single(lb, port):
         assert np.array_equal(w2[i], d.process_pcm(odd[i]).packed())
 
 
+def test_slabs_and_staging_variants_agree(lb, port, monkeypatch):
+    """The image scratch is processed in slabs of frames and the samples are staged by TMA or by plain loads: same words either way."""
+    pcm = np.stack([port.synth_clip(120 + i, 82680) for i in range(6)])      # 9 frames per clip, 54 frames
+    want = lb.Detective().process_batch(pcm)
+    monkeypatch.setenv("LBAD_SLAB_FRAMES", "7")                              # slabs that cut through clips
+    assert np.array_equal(lb.Detective().process_batch(pcm), want)
+    monkeypatch.delenv("LBAD_SLAB_FRAMES")
+    monkeypatch.setenv("LBAD_STAGE", "ldg")
+    assert np.array_equal(lb.Detective().process_batch(pcm), want)
+
+
 def test_device_resident_batch(lb, port):
     import torch
     d = lb.Detective(); n, clip_len = 64, 165360
