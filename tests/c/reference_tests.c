@@ -1,0 +1,103 @@
+/*
+ * reference_tests.c — the reference's XCTest suite (LBAudioDetectiveTests/LBAudioDetectiveTests.m) re-stated in C against
+ * the drop-in library: same API calls, same argument order (archive first, query second, range 0), with the bundled .caf
+ * recordings replaced by synthetic "birds" handed over as float32 PCM (decoding is out of scope).
+ *
+ *   testFingerprintingWithEqualBirds      Tests.m:53-117  (suffix _eql : crop of the archive clip)       -> asserted here
+ *   testFingerprintingWithDifferentBirds  (suffix _dif : another recording)                              -> printed only, as upstream
+ *   testFingerprintingWithBlurredBirds    (suffix _blu1/_blu2 : crop + 1.58 % / 3.16 % noise)            -> asserted here
+ *   testFingerprintVersatility            Tests.m:119-139                                                -> asserted
+ *   testFingerprintComparison             Tests.m:141-155                                                -> asserted
+ *
+ * Build: cc -std=gnu11 -Iinclude tests/c/reference_tests.c -Llbaudiodetective_b200 -lLBAudioDetectiveCUDA -lm
+ * Exit status 0 = all assertions hold; 77 = no CUDA device (skipped).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "LBAudioDetective.h"
+#include "LBAudioDetectiveSupport.h"
+
+#define BIRDS 10
+#define ARCHIVE_SAMPLES 49608   /* 9 s at 5512 Hz, like the archive clips */
+#define CROP_SAMPLES 22048      /* 4 s, like the cropped clips */
+#define CROP_START (8192 * 2)   /* crops start on a frame boundary of the archive clip */
+
+static unsigned long long rng_state;
+static double rnd(void) { rng_state = rng_state * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(rng_state >> 40) / 16777216.0; }
+
+/* a "bird": a few chirping partials plus a little noise */
+static void make_bird(int bird, int take, Float32* out, int n) {
+    rng_state = 1000003ULL * (unsigned long long)(bird + 1) + 77ULL * (unsigned long long)take;
+    double f[3], df[3], rate[3];
+    for (int p = 0; p < 3; p++) { f[p] = 400.0 + 1400.0 * rnd(); df[p] = 100.0 + 300.0 * rnd(); rate[p] = 2.0 + 6.0 * rnd(); }
+    for (int i = 0; i < n; i++) {
+        double t = i / 5512.0, v = 0.0;
+        for (int p = 0; p < 3; p++) v += 0.25 * sin(2.0 * M_PI * (f[p] * t + df[p] / (2.0 * M_PI * rate[p]) * sin(2.0 * M_PI * rate[p] * t)));
+        out[i] = (Float32)(v + 0.05 * (rnd() - 0.5));
+    }
+}
+
+static int failures = 0;
+#define CHECK(cond, ...) do { if (!(cond)) { failures++; fprintf(stderr, "FAILED %s:%d: ", __FILE__, __LINE__); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } } while (0)
+
+/* Tests.m:53-117: every archive bird against every cropped bird; returns how many birds were identified */
+static int fingerprinting_with_suffix(LBAudioDetectiveRef detective, Float32 archive[BIRDS][ARCHIVE_SAMPLES], Float32 (*cropped)[CROP_SAMPLES], const char* suffix) {
+    int identified = 0;
+    printf("%-6s", suffix);
+    for (int original = 0; original < BIRDS; original++) {
+        Float32 bestMatch = 0.0f; int bestBird = -1;
+        for (int sequence = 0; sequence < BIRDS; sequence++) {
+            Float32 match = 0.0f;
+            OSStatus error = LBAudioDetectiveComparePCM(detective, archive[original], ARCHIVE_SAMPLES, cropped[sequence], CROP_SAMPLES, 0, &match);
+            CHECK(error == noErr, "LBAudioDetectiveComparePCM returned %d", (int)error);
+            if (match > bestMatch) { bestMatch = match; bestBird = sequence; }          /* Tests.m:72-75 */
+        }
+        printf(" %d:%d(%.3f)", original, bestBird, bestMatch);
+        identified += bestBird == original;
+    }
+    printf("  -> %d/%d identified\n", identified, BIRDS);
+    return identified;
+}
+
+int main(void) {
+    if (!LBAudioDetectiveSupportDeviceAvailable()) { fprintf(stderr, "no CUDA device: skipped\n"); return 77; }
+    static Float32 archive[BIRDS][ARCHIVE_SAMPLES], eql[BIRDS][CROP_SAMPLES], dif[BIRDS][CROP_SAMPLES], blu1[BIRDS][CROP_SAMPLES], blu2[BIRDS][CROP_SAMPLES];
+    for (int b = 0; b < BIRDS; b++) {
+        make_bird(b, 0, archive[b], ARCHIVE_SAMPLES);
+        memcpy(eql[b], archive[b] + CROP_START, sizeof eql[b]);
+        make_bird(b, 1, dif[b], CROP_SAMPLES);
+        rng_state = 4242 + b;
+        for (int i = 0; i < CROP_SAMPLES; i++) { blu1[b][i] = eql[b][i] + (Float32)(0.0158 * 2.0 * (rnd() - 0.5)); blu2[b][i] = eql[b][i] + (Float32)(0.0316 * 2.0 * (rnd() - 0.5)); }
+    }
+    LBAudioDetectiveRef detective = LBAudioDetectiveNew();                                 /* Tests.m:42 */
+    CHECK(detective != NULL, "LBAudioDetectiveNew");
+    CHECK(LBAudioDetectiveGetWindowSize(detective) == 2048 && LBAudioDetectiveGetAnalysisStride(detective) == 64 &&
+          LBAudioDetectiveGetNumberOfPitchSteps(detective) == 32 && LBAudioDetectiveGetSubfingerprintLength(detective) == 200, "defaults");
+
+    CHECK(fingerprinting_with_suffix(detective, archive, eql, "_eql") == BIRDS, "a crop of the archive clip must identify its bird");
+    fingerprinting_with_suffix(detective, archive, dif, "_dif");                            /* upstream asserts nothing here either */
+    CHECK(fingerprinting_with_suffix(detective, archive, blu1, "_blu1") == BIRDS, "1.58 %% noise must not break identification");
+    CHECK(fingerprinting_with_suffix(detective, archive, blu2, "_blu2") == BIRDS, "3.16 %% noise must not break identification");
+
+    /* Tests.m:119-139: two detective instances produce equal fingerprints */
+    for (int i = 0; i < 3; i++) {
+        LBAudioDetectiveRef detective2 = LBAudioDetectiveNew();
+        LBAudioDetectiveFingerprintRef fingerprint1 = NULL, fingerprint2 = NULL;
+        CHECK(LBAudioDetectiveProcessPCM(detective, archive[0], ARCHIVE_SAMPLES, &fingerprint1) == noErr, "ProcessPCM");
+        CHECK(LBAudioDetectiveProcessPCM(detective2, archive[0], ARCHIVE_SAMPLES, &fingerprint2) == noErr, "ProcessPCM");
+        CHECK(LBAudioDetectiveFingerprintEqualToFingerprint(fingerprint1, fingerprint2), "Fingerprints should be equal");
+        CHECK(LBAudioDetectiveFingerprintGetNumberOfSubfingerprints(fingerprint1) == 5 && LBAudioDetectiveFingerprintGetSubfingerprintLength(fingerprint1) == 200, "5 x 200");
+        /* Tests.m:141-155: a copy equals the original; a fingerprint matches itself completely */
+        LBAudioDetectiveFingerprintRef copy = LBAudioDetectiveFingerprintCopy(fingerprint1);
+        CHECK(LBAudioDetectiveFingerprintEqualToFingerprint(fingerprint1, copy), "Fingerprints should be equal");
+        CHECK(LBAudioDetectiveFingerprintCompareToFingerprint(fingerprint1, copy, 200) == 1.0f, "self match is 1.0");
+        LBAudioDetectiveFingerprintDispose(copy); LBAudioDetectiveFingerprintDispose(fingerprint1); LBAudioDetectiveFingerprintDispose(fingerprint2);
+        CHECK(LBAudioDetectiveDispose(detective2) == noErr, "Dispose");
+    }
+    CHECK(LBAudioDetectiveDispose(detective) == noErr, "Dispose");                          /* Tests.m:46 */
+    CHECK(LBAudioDetectiveDispose(NULL) == kLBAudioDetectiveArgumentInvalid, "Dispose(NULL)");
+    printf(failures ? "%d FAILURES\n" : "all reference tests passed\n", failures);
+    return failures ? 1 : 0;
+}
