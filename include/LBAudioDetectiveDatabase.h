@@ -49,6 +49,10 @@ LBAD_API OSStatus LBAudioDetectiveDatabaseSearchDevice(LBAudioDetectiveDatabaseR
  * ordered (score desc, clip index asc) — the result equals a single-GPU search over the union.  Host memory. */
 LBAD_API OSStatus LBAudioDetectiveDatabaseMergeTopK(const Float32* inScores, const UInt32* inClipIndices, UInt32 inNumberOfLists, UInt32 inNumberOfQueries, UInt32 inK,
                                                    Float32* outScores, UInt32* outClipIndices);
+/* Persistence: packed binary file (header: L, W, clip count, per-clip subfingerprint counts; body: the bit planes), so that a
+ * database is reloaded without re-extracting.  Load returns NULL on a missing / malformed file or without a CUDA device. */
+LBAD_API OSStatus LBAudioDetectiveDatabaseSave(LBAudioDetectiveDatabaseRef inDatabase, const char* inPath);
+LBAD_API LBAudioDetectiveDatabaseRef LBAudioDetectiveDatabaseLoad(const char* inPath);
 /* Number of CompareSubfingerprints evaluations one search performs (for compares/s). */
 LBAD_API UInt64 LBAudioDetectiveDatabaseComparesPerQuery(LBAudioDetectiveDatabaseRef inDatabase, UInt32 inQueryCount);
 LBAD_API UInt64 LBAudioDetectiveDatabaseGetKernelLaunchCount(LBAudioDetectiveDatabaseRef inDatabase);

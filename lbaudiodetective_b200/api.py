@@ -103,6 +103,8 @@ def load_library(build_if_missing: bool = True):
         "LBAudioDetectiveDatabaseSearch": (C.c_int32, [vp, P(vp), u32, u32, u32, vp, vp]),
         "LBAudioDetectiveDatabaseSearchDevice": (C.c_int32, [vp, vp, u32, u32, u32, u32, vp, vp, vp]),
         "LBAudioDetectiveDatabaseMergeTopK": (C.c_int32, [vp, vp, u32, u32, u32, vp, vp]),
+        "LBAudioDetectiveDatabaseSave": (C.c_int32, [vp, C.c_char_p]),
+        "LBAudioDetectiveDatabaseLoad": (vp, [C.c_char_p]),
         "LBAudioDetectiveDatabaseComparesPerQuery": (u64, [vp, u32]),
         "LBAudioDetectiveDatabaseGetKernelLaunchCount": (u64, [vp]),
         "LBAudioDetectiveDatabaseGetKernelTiming": (u32, [vp, u8, u8, P(f64)]),
@@ -405,12 +407,20 @@ class Stream:
 class Database:
     """LBAudioDetectiveDatabaseRef (include/LBAudioDetectiveDatabase.h)."""
 
-    def __init__(self, subfingerprint_length=200):
+    def __init__(self, subfingerprint_length=200, _ref=None):
         self._L = lib()
         self.L = subfingerprint_length
-        self.ref = self._L.LBAudioDetectiveDatabaseNew(subfingerprint_length)
+        self.ref = _ref if _ref is not None else self._L.LBAudioDetectiveDatabaseNew(subfingerprint_length)
         if not self.ref:
             raise LBADError(DEVICE_UNAVAILABLE, "LBAudioDetectiveDatabaseNew")
+
+    def save(self, path):
+        _check(self._L.LBAudioDetectiveDatabaseSave(self.ref, os.fsencode(path)), "DatabaseSave")
+
+    @staticmethod
+    def load(path, subfingerprint_length=200):
+        ref = lib().LBAudioDetectiveDatabaseLoad(os.fsencode(path))
+        return Database(subfingerprint_length, _ref=ref) if ref else None
 
     def dispose(self):
         if self.ref:

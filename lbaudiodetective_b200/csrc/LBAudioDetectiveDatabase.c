@@ -3,6 +3,7 @@
  * Marshals packed fingerprints into the CUDA layer (lbad_search.cu); no match arithmetic happens here.
  */
 #include "lbad_host.h"
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -97,4 +98,49 @@ UInt64 LBAudioDetectiveDatabaseGetKernelLaunchCount(LBAudioDetectiveDatabaseRef 
 UInt32 LBAudioDetectiveDatabaseGetKernelTiming(LBAudioDetectiveDatabaseRef d, Boolean inEnable, Boolean inReset, Float64* outTotalMilliseconds) {
     if (outTotalMilliseconds) *outTotalMilliseconds = 0.0;
     return d ? lbadcu_db_timing(d->db, inEnable, inReset, outTotalMilliseconds) : 0;
+}
+
+/* ---- persistence: a packed binary file, so that a database can be reloaded without re-extracting ----
+ * little-endian: char magic[8] = "LBADDB1\0"; u32 L; u32 W; u32 clips; u32 reserved; u64 subfingerprints;
+ *                u32 counts[clips]; u32 words[subfingerprints][2*W]  (P plane then M plane per subfingerprint) */
+static const char kMagic[8] = {'L', 'B', 'A', 'D', 'D', 'B', '1', '\0'};
+
+OSStatus LBAudioDetectiveDatabaseSave(LBAudioDetectiveDatabaseRef d, const char* inPath) {
+    if (!d || !inPath) return kLBAudioDetectiveArgumentInvalid;
+    UInt32 clips = lbadcu_db_clips(d->db); UInt64 subfps = lbadcu_db_subfps(d->db);
+    UInt32* counts = malloc(((size_t)clips ? clips : 1) * sizeof(UInt32));
+    UInt32* words = malloc(((size_t)subfps ? subfps : 1) * 2 * d->W * sizeof(UInt32));
+    if (!counts || !words) { free(counts); free(words); return kLBAudioDetectiveArgumentInvalid; }
+    OSStatus e = lbad_status(lbadcu_db_download(d->db, words, counts));
+    FILE* f = e == noErr ? fopen(inPath, "wb") : NULL;
+    if (e == noErr && !f) e = kLBAudioDetectiveArgumentInvalid;
+    if (f) {
+        UInt32 hdr[4] = {d->subfingerprintLength, d->W, clips, 0};
+        int ok = fwrite(kMagic, 1, 8, f) == 8 && fwrite(hdr, sizeof(UInt32), 4, f) == 4 && fwrite(&subfps, sizeof(UInt64), 1, f) == 1 &&
+                 fwrite(counts, sizeof(UInt32), clips, f) == clips && fwrite(words, sizeof(UInt32), (size_t)subfps * 2 * d->W, f) == (size_t)subfps * 2 * d->W;
+        if (fclose(f) != 0 || !ok) e = kLBAudioDetectiveArgumentInvalid;
+    }
+    free(counts); free(words);
+    return e;
+}
+
+LBAudioDetectiveDatabaseRef LBAudioDetectiveDatabaseLoad(const char* inPath) {
+    FILE* f = inPath ? fopen(inPath, "rb") : NULL;
+    if (!f) return NULL;
+    char magic[8]; UInt32 hdr[4]; UInt64 subfps = 0;
+    LBAudioDetectiveDatabaseRef d = NULL; UInt32* counts = NULL; UInt32* words = NULL;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kMagic, 8) != 0 || fread(hdr, sizeof(UInt32), 4, f) != 4 || fread(&subfps, sizeof(UInt64), 1, f) != 1) goto done;
+    if (lbad_words_per_plane(hdr[0]) != hdr[1] || hdr[1] == 0) goto done;
+    counts = malloc(((size_t)hdr[2] ? hdr[2] : 1) * sizeof(UInt32));
+    words = malloc(((size_t)subfps ? subfps : 1) * 2 * hdr[1] * sizeof(UInt32));
+    if (!counts || !words) goto done;
+    if (fread(counts, sizeof(UInt32), hdr[2], f) != hdr[2] || fread(words, sizeof(UInt32), (size_t)subfps * 2 * hdr[1], f) != (size_t)subfps * 2 * hdr[1]) goto done;
+    UInt64 total = 0;
+    for (UInt32 c = 0; c < hdr[2]; c++) total += counts[c];
+    if (total != subfps) goto done;
+    d = LBAudioDetectiveDatabaseNew(hdr[0]);
+    if (d && hdr[2] && lbadcu_db_append(d->db, words, 0, hdr[2], counts, 0) != LBAD_OK) { LBAudioDetectiveDatabaseDispose(d); d = NULL; }
+done:
+    fclose(f); free(counts); free(words);
+    return d;
 }

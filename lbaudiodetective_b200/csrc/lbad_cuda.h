@@ -77,6 +77,7 @@ uint64_t lbadcu_db_launches(const lbadcu_db* db);
 uint32_t lbadcu_db_timing(lbadcu_db* db, int enable, int reset, double* total_ms);
 /* counts == NULL -> uniform_count for every clip; words on host or device */
 int  lbadcu_db_append(lbadcu_db* db, const uint32_t* words, int words_on_device, uint32_t n_clips, const uint32_t* counts, uint32_t uniform_count);
+int  lbadcu_db_download(lbadcu_db* db, uint32_t* h_words, uint32_t* h_counts);
 /* pairs = number of (P,M) bit pairs compared = ceil(min(range, L)/2).  Outputs [q][k]; d_all optional [q][clips]. */
 int  lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_qwords, uint32_t n_q, uint32_t q_count, uint32_t pairs, uint32_t k,
                              float* d_scores, uint32_t* d_idx, float* d_all, void* stream);

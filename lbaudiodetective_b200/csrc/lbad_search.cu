@@ -484,6 +484,18 @@ extern "C" int lbadcu_db_append(lbadcu_db* db, const uint32_t* words, int on_dev
     return LBAD_OK;
 }
 
+/* copies the packed words and the per-clip counts back to the host (for persisting a database) */
+extern "C" int lbadcu_db_download(lbadcu_db* db, uint32_t* h_words, uint32_t* h_counts) {
+    if (!db) return LBAD_ERR_ARG;
+    LBAD_CUDA_TRY(cudaSetDevice(db->device));
+    if (h_words && db->n_subfps) {
+        LBAD_CUDA_TRY(cudaMemcpyAsync(h_words, db->d_words, db->n_subfps * 2 * db->W * sizeof(uint32_t), cudaMemcpyDeviceToHost, db->stream));
+        LBAD_CUDA_TRY(cudaStreamSynchronize(db->stream));
+    }
+    if (h_counts) for (size_t c = 0; c + 1 < db->h_offsets.size(); c++) h_counts[c] = db->h_offsets[c + 1] - db->h_offsets[c];
+    return LBAD_OK;
+}
+
 extern "C" uint64_t lbadcu_db_compares_per_query(const lbadcu_db* db, uint32_t cq) {
     uint64_t total = 0;
     for (size_t c = 0; c + 1 < db->h_offsets.size(); c++) {

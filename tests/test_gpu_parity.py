@@ -11,6 +11,8 @@ Tolerances (BASELINE.json north_star):
   * everything downstream of identical inputs — Haar given images, bits given coefficients, scores and top-k given
     bits — bit-exact.
 """
+import os
+
 import numpy as np
 import pytest
 from oracle.oracle import Cfg
@@ -338,6 +340,22 @@ def test_search_ragged_database_and_fingerprint_api(lb, checker):
         assert np.array_equal(idx[qi], (order + 5000).astype(np.uint32))
         assert np.array_equal(sc[qi], want[order])
     assert sc[0, 0] == 1.0 and idx[0, 0] == 5000 + int(np.argmax(counts))
+
+
+def test_database_save_load_round_trip(lb, tmp_path):
+    rng = np.random.default_rng(16); L = 200
+    counts = rng.integers(0, 25, size=60)
+    words = lb.pack_booleans(rank_sign_codes(rng, 1, int(counts.sum()), L)[0])
+    db = lb.Database(L); db.add_packed(words, counts=counts)
+    path = tmp_path / "birds.lbaddb"; db.save(path)
+    assert os.path.getsize(path) == 8 + 16 + 8 + 4 * 60 + 32 * int(counts.sum())
+    db2 = lb.Database.load(path, L)
+    assert db2.clips == 60 and db2.subfingerprints == int(counts.sum())
+    q = lb.pack_booleans(rank_sign_codes(rng, 5, 6, L))
+    a = db.search_packed(q, k=4, all_scores=True); b = db2.search_packed(q, k=4, all_scores=True)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    open(path, "r+b").write(b"XXXX")
+    assert lb.Database.load(path, L) is None and lb.Database.load(tmp_path / "missing", L) is None
 
 
 def test_topk_with_fewer_clips_than_k(lb):
