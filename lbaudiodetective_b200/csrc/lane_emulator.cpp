@@ -1,6 +1,6 @@
 /*
  * lane_emulator.cpp — TEST SUPPORT (host only, g++): runs the fused kernel's per-window warp procedure
- * (lbad_extract.cu: extract_fused_kernel, "16 windows per warp" loop) lane by lane on the CPU, using the very same
+ * (lbad_extract.cu: bands_fused_kernel<R>, the per-warp window loop) lane by lane on the CPU, using the very same
  * lbad_math.cuh functions and the same index expressions, with shared memory and shuffles replaced by arrays.
  * It lets the register/shared-memory index algebra of the kernel be checked against the oracle without a GPU
  * (tests/test_lane_emulation.py).  It is not part of libLBAudioDetectiveCUDA.so and never ships.
@@ -12,27 +12,30 @@
 
 using namespace lbad;
 
-extern "C" void lbad_emulate_window(const float* win, const uint32_t* klow, const uint32_t* khigh, const float* divisor,
-                                    float inv_pos_scale, uint32_t kmin, uint32_t kmax, float* out_bands, float* out_spec /* 2048 floats or NULL */) {
-    constexpr int SCR_LDF = 36;
+/* One warp iteration of bands_fused_kernel<R, false>: S = 32/R windows of N = 64 R samples, window s starting at pcm + s*hop.
+ * out_bands: [S][32]; out_spec (optional): [S][N] interleaved 2X[k] for the bins the kernel computes. */
+template <int R>
+static void emulate_windows(const float* pcm, int hop, const uint32_t* klow, const uint32_t* khigh, const float* divisor,
+                            float inv_pos_scale, uint32_t kmin, uint32_t kmax, float* out_bands, float* out_spec) {
+    constexpr int SCR_LDF = 36, S = 32 / R, M = 32 * R, N = 2 * M;
     static float tw1[512][4], tw2[512][4];
-    static bool init = false;
-    if (!init) {                                   /* same tables as lbadcu_plan_create */
+    {                                              /* same tables as lbadcu_plan_create */
         for (int pp = 0; pp < 32; pp += 2) for (int l = 0; l < 32; l++) {
-            const double a0 = 2.0 * M_PI * (double)(l * bitrev5(pp)) / 1024.0, a1 = 2.0 * M_PI * (double)(l * bitrev5(pp + 1)) / 1024.0;
+            const double a0 = 2.0 * M_PI * (double)((l % R) * bitrev5(pp)) / (double)M, a1 = 2.0 * M_PI * (double)((l % R) * bitrev5(pp + 1)) / (double)M;
             float* t = tw1[(pp >> 1) * 32 + l]; t[0] = (float)cos(a0); t[1] = (float)-sin(a0); t[2] = (float)cos(a1); t[3] = (float)-sin(a1);
         }
         for (int k2 = 0; k2 < 32; k2 += 2) for (int l = 0; l < 32; l++) {
-            const double a0 = 2.0 * M_PI * (double)(l + 32 * k2) / 2048.0, a1 = 2.0 * M_PI * (double)(l + 32 * (k2 + 1)) / 2048.0;
+            const double a0 = 2.0 * M_PI * (double)(l + 32 * k2) / (double)N, a1 = 2.0 * M_PI * (double)(l + 32 * (k2 + 1)) / (double)N;
             float* t = tw2[(k2 >> 1) * 32 + l]; t[0] = (float)cos(a0); t[1] = (float)sin(a0); t[2] = (float)cos(a1); t[3] = (float)sin(a1);
         }
-        init = true;
     }
     static float2 z[32][32];                        /* [lane][register] */
     std::vector<float> scr(32 * SCR_LDF), vbuf(1024, 0.0f);
     const float scale_m1 = inv_pos_scale - 1.0f;
     for (int lane = 0; lane < 32; lane++) {
-        for (int n1 = 0; n1 < 32; n1++) z[lane][n1] = make_float2(win[2 * (32 * n1 + lane)], win[2 * (32 * n1 + lane) + 1]);
+        const int my_win = lane / R, n2 = lane % R;
+        const float* win = pcm + (size_t)my_win * hop;
+        for (int n1 = 0; n1 < 32; n1++) z[lane][n1] = make_float2(win[2 * (R * n1 + n2)], win[2 * (R * n1 + n2) + 1]);
         fft32(z[lane]);
         for (int p = 0; p < 32; p += 2) {
             const float* w = tw1[(p >> 1) * 32 + lane];
@@ -45,48 +48,66 @@ extern "C" void lbad_emulate_window(const float* win, const uint32_t* klow, cons
         for (int lane = 0; lane < 32; lane++) for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = comp ? z[lane][p].y : z[lane][p].x;
         for (int lane = 0; lane < 32; lane++) for (int q = 0; q < 8; q++) for (int j = 0; j < 4; j++) (comp ? z[lane][4 * q + j].y : z[lane][4 * q + j].x) = scr[lane * SCR_LDF + 4 * q + j];
     }
-    for (int lane = 0; lane < 32; lane++) fft32(z[lane]);
+    for (int lane = 0; lane < 32; lane++) fft32_tail<R>(z[lane]);
     const int k2lo = (int)(kmin >> 5), k2hi = (int)((kmax - 1) >> 5);
     for (int lane = 0; lane < 32; lane++) {
         const int src_lane = (32 - lane) & 31;
-        for (int k2 = 0; k2 < 32; k2 += 2) {
+        for (int k2 = 0; k2 < R; k2 += 2) {
             if (k2 + 1 >= k2lo && k2 <= k2hi) {
                 const float* w = tw2[(k2 >> 1) * 32 + lane];
                 for (int h = 0; h < 2; h++) {
                     const int kk = k2 + h;
-                    const int p = bitrev5(kk), pp = bitrev5(31 - kk), p0 = bitrev5((32 - kk) & 31);
-                    float2 pz = z[src_lane][pp];                             /* __shfl_sync */
-                    if (lane == 0) pz = z[lane][p0];
-                    float xr, xi;
-                    real_split_2x(z[lane][p], pz, h ? w[2] : w[0], h ? w[3] : w[1], xr, xi);
-                    if (kk == 0 && lane == 0) { xr = 2.0f * (z[lane][p].x + z[lane][p].y); xi = 2.0f * (z[lane][p].x - z[lane][p].y); }
-                    if (out_spec) { out_spec[2 * (kk * 32 + lane)] = xr; out_spec[2 * (kk * 32 + lane) + 1] = xi; }
-                    vbuf[kk * 32 + lane] = bin_energy(xr, xi, scale_m1);
+                    for (int s = 0; s < S; s++) {
+                        const int p = s * R + bitrevR<R>(kk), pp = s * R + bitrevR<R>(R - 1 - kk), p0 = s * R + bitrevR<R>((R - kk) % R);
+                        float2 pz = z[src_lane][pp];                         /* __shfl_sync */
+                        if (lane == 0) pz = z[lane][p0];
+                        float xr, xi;
+                        real_split_2x(z[lane][p], pz, h ? w[2] : w[0], h ? w[3] : w[1], xr, xi);
+                        if (kk == 0 && lane == 0) { xr = 2.0f * (z[lane][p].x + z[lane][p].y); xi = 2.0f * (z[lane][p].x - z[lane][p].y); }
+                        if (out_spec) { out_spec[(size_t)s * N + 2 * (kk * 32 + lane)] = xr; out_spec[(size_t)s * N + 2 * (kk * 32 + lane) + 1] = xi; }
+                        vbuf[s * M + kk * 32 + lane] = bin_energy(xr, xi, scale_m1);
+                    }
                 }
             }
         }
     }
     /* band sums as in the kernel: two lanes per band, halves combined by the xor-1 shuffle */
-    auto seg_sum = [&](uint32_t a, uint32_t b) {
-        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-        for (; a + 4 <= b; a += 4) { s0 += vbuf[a]; s1 += vbuf[a + 1]; s2 += vbuf[a + 2]; s3 += vbuf[a + 3]; }
-        if (a + 2 <= b) { s0 += vbuf[a]; s1 += vbuf[a + 1]; a += 2; }
-        if (a < b) s2 += vbuf[a];
-        return (s0 + s1) + (s2 + s3);
-    };
-    float sa[32], sb[32];
-    for (int lane = 0; lane < 32; lane++) {
-        const int b0 = lane >> 1, b1 = 16 + (lane >> 1);
-        const uint32_t l0 = klow[b0], h0 = khigh[b0], m0 = l0 + (h0 - l0 + 1) / 2;
-        const uint32_t l1 = klow[b1], h1 = khigh[b1], m1 = l1 + (h1 - l1 + 1) / 2;
-        sa[lane] = seg_sum((lane & 1) ? m0 : l0, (lane & 1) ? h0 : m0);
-        sb[lane] = seg_sum((lane & 1) ? m1 : l1, (lane & 1) ? h1 : m1);
+    for (int s = 0; s < S; s++) {
+        const float* v = vbuf.data() + s * M;
+        auto seg_sum = [&](uint32_t a, uint32_t b) {
+            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+            for (; a + 4 <= b; a += 4) { s0 += v[a]; s1 += v[a + 1]; s2 += v[a + 2]; s3 += v[a + 3]; }
+            if (a + 2 <= b) { s0 += v[a]; s1 += v[a + 1]; a += 2; }
+            if (a < b) s2 += v[a];
+            return (s0 + s1) + (s2 + s3);
+        };
+        float sa[32], sb[32];
+        for (int lane = 0; lane < 32; lane++) {
+            const int b0 = lane >> 1, b1 = 16 + (lane >> 1);
+            const uint32_t l0 = klow[b0], h0 = khigh[b0], m0 = l0 + (h0 - l0 + 1) / 2;
+            const uint32_t l1 = klow[b1], h1 = khigh[b1], m1 = l1 + (h1 - l1 + 1) / 2;
+            sa[lane] = seg_sum((lane & 1) ? m0 : l0, (lane & 1) ? h0 : m0);
+            sb[lane] = seg_sum((lane & 1) ? m1 : l1, (lane & 1) ? h1 : m1);
+        }
+        for (int lane = 0; lane < 32; lane++) {
+            const int my_band = (lane >> 1) + ((lane & 1) ? 16 : 0);
+            const float a2 = sa[lane] + sa[lane ^ 1], b2 = sb[lane] + sb[lane ^ 1];
+            out_bands[s * 32 + my_band] = ((lane & 1) ? b2 : a2) / divisor[my_band];
+        }
     }
-    for (int lane = 0; lane < 32; lane++) {
-        const int my_band = (lane >> 1) + ((lane & 1) ? 16 : 0);
-        const float a2 = sa[lane] + sa[lane ^ 1], b2 = sb[lane] + sb[lane ^ 1];
-        out_bands[my_band] = ((lane & 1) ? b2 : a2) / divisor[my_band];
-    }
+}
+
+extern "C" void lbad_emulate_windows(int R, const float* pcm, int hop, const uint32_t* klow, const uint32_t* khigh, const float* divisor,
+                                     float inv_pos_scale, uint32_t kmin, uint32_t kmax, float* out_bands, float* out_spec) {
+    if (R == 32) emulate_windows<32>(pcm, hop, klow, khigh, divisor, inv_pos_scale, kmin, kmax, out_bands, out_spec);
+    else if (R == 16) emulate_windows<16>(pcm, hop, klow, khigh, divisor, inv_pos_scale, kmin, kmax, out_bands, out_spec);
+    else if (R == 8) emulate_windows<8>(pcm, hop, klow, khigh, divisor, inv_pos_scale, kmin, kmax, out_bands, out_spec);
+    else if (R == 4) emulate_windows<4>(pcm, hop, klow, khigh, divisor, inv_pos_scale, kmin, kmax, out_bands, out_spec);
+}
+
+extern "C" void lbad_emulate_window(const float* win, const uint32_t* klow, const uint32_t* khigh, const float* divisor,
+                                    float inv_pos_scale, uint32_t kmin, uint32_t kmax, float* out_bands, float* out_spec /* 2048 floats or NULL */) {
+    emulate_windows<32>(win, 0, klow, khigh, divisor, inv_pos_scale, kmin, kmax, out_bands, out_spec);
 }
 
 /* bare 32-point DFT in natural order, for a direct unit test of fft32 + bitrev5 */

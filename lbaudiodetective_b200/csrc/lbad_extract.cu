@@ -311,13 +311,17 @@ static FusedSmemLayout fused_layout(uint32_t span_floats) {
     return L;
 }
 
-/* STATIC_RANGE: the band table is the reference-default one (bins [86, 759)), so the rows of 32 bins that need the
- * real split are k2 = 2..23 at compile time; otherwise the range is a (warp-uniform) run-time value. */
-template <bool STATIC_RANGE>
+/* R: lanes per window in pass 1 = points of the pass-2 DFT; window = 64 R samples, 32/R windows per warp (see lbad_math.cuh).
+ * STATIC_RANGE (R = 32 only): the band table is the reference-default one (bins [86, 759)), so the rows of 32 bins that need
+ * the real split are k2 = 2..23 at compile time; otherwise the range is a (warp-uniform) run-time value. */
+template <int R, bool STATIC_RANGE>
 __global__ void __launch_bounds__(FUSED_THREADS, 2)
 bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, const float4* __restrict__ g_tw1, const float4* __restrict__ g_tw2,
                    const Geo g, const BandTable bt, const FusedSmemLayout L, const uint32_t span_floats,
                    const uint32_t total_frames, const int use_tma, const uint32_t frame0) {
+    static_assert(!STATIC_RANGE || R == 32, "the compile-time band rows belong to the 2048-sample window");
+    constexpr int S = 32 / R;                                /* windows per warp */
+    constexpr int M = 32 * R;                                /* complex points per window = bins of the half spectrum */
     extern __shared__ __align__(128) unsigned char smem[];
     float*  samples = reinterpret_cast<float*>(smem);
     float4* tw1 = reinterpret_cast<float4*>(smem + L.off_tw1);     /* [p/2][lane]: twiddles of register positions p, p+1 */
@@ -325,7 +329,7 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     float* scr = reinterpret_cast<float*>(smem + L.off_scratch) + wid * (32 * SCR_LDF);
-    float* vbuf = scr;                                       /* band scratch (1024 floats) aliases the transpose scratch */
+    float* vbuf = scr;                                       /* band scratch (S x M = 1024 floats) aliases the transpose scratch */
 
     for (int i = tid; i < 512; i += FUSED_THREADS) { tw1[i] = g_tw1[i]; tw2[i] = g_tw2[i]; }
     if (tid == 0 && use_tma) { mbar_init(bar, 1); mbar_fence_init(); }
@@ -346,6 +350,7 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
     const uint32_t hop = g.stride;
     const uint32_t bytes = span_floats * 4;
     const float scale_m1 = g.inv_pos_scale - 1.0f;
+    const int my_win = lane / R, n2 = lane % R;              /* pass 1: which of the warp's windows this lane loads, and its column */
 
     auto frame_src = [&](uint32_t fl) -> const float* {                        /* fl: frame index inside this launch's slab */
         const uint32_t f = frame0 + fl;
@@ -355,6 +360,7 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
 
     uint32_t f = blockIdx.x, parity = 0;
     if (f < total_frames && use_tma && tid == 0) { mbar_arrive_expect_tx(bar, bytes); bulk_copy_g2s(samples, frame_src(f), bytes, bar); }
+
     for (; f < total_frames; f += gridDim.x) {
         if (use_tma) { mbar_wait(bar, parity); parity ^= 1; }
         else {
@@ -363,22 +369,22 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
             __syncthreads();
         }
 
-        /* ---- the frame's 128 windows, round-robin over the warps: FFT -> bands -> image row ---- */
+        /* ---- the frame's 128 windows, S at a time per warp, round-robin over the warps: FFT -> bands -> image rows ---- */
 #pragma unroll 1
-        for (int row = wid; row < (int)LBAD_ROWS_PER_FRAME; row += FUSED_WARPS) {
-            const float* win = samples + (size_t)row * hop;
+        for (int row0 = wid * S; row0 < (int)LBAD_ROWS_PER_FRAME; row0 += FUSED_WARPS * S) {
+            const float* win = samples + (size_t)(row0 + my_win) * hop;
             float2 z[32];
 #pragma unroll
-            for (int n1 = 0; n1 < 32; n1++)                                     /* vDSP_ctoz (m:353): z[n] = x[2n] + i x[2n+1] */
-                z[n1] = *reinterpret_cast<const float2*>(win + 2 * (32 * n1 + lane));
+            for (int n1 = 0; n1 < 32; n1++)                                     /* vDSP_ctoz (m:353): z[n] = x[2n] + i x[2n+1], n = R n1 + n2 */
+                z[n1] = *reinterpret_cast<const float2*>(win + 2 * (R * n1 + n2));
             fft32(z);                                                           /* over n1; position p holds k1 = bitrev5(p) */
 #pragma unroll
-            for (int p = 0; p < 32; p += 2) {                                   /* x exp(-2 pi i lane k1 / 1024) */
+            for (int p = 0; p < 32; p += 2) {                                   /* x exp(-2 pi i n2 k1 / M) */
                 const float4 w = tw1[(p >> 1) * 32 + lane];
                 z[p] = make_float2(z[p].x * w.x - z[p].y * w.y, z[p].x * w.y + z[p].y * w.x);
                 z[p + 1] = make_float2(z[p + 1].x * w.z - z[p + 1].y * w.w, z[p + 1].x * w.w + z[p + 1].y * w.z);
             }
-            /* 32x32 transpose through shared memory, one component at a time: lane k1 ends up with A[n2][k1], n2 = 0..31 */
+            /* 32x32 transpose through shared memory, one component at a time: lane k1 ends up with A_s[n2][k1] in register s R + n2 */
 #pragma unroll
             for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = z[p].x;
             __syncwarp();
@@ -396,37 +402,44 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                 const float4 t = *reinterpret_cast<const float4*>(&scr[lane * SCR_LDF + 4 * q]);
                 z[4 * q].y = t.x; z[4 * q + 1].y = t.y; z[4 * q + 2].y = t.z; z[4 * q + 3].y = t.w;
             }
-            fft32(z);                                                           /* over n2; position p holds Z[lane + 32 bitrev5(p)] */
+            fft32_tail<R>(z);                                                   /* over n2, per window; position s R + q holds Z_s[lane + 32 bitrevR(q)] */
             __syncwarp();                                                       /* scratch is about to be reused as vbuf */
             const int src_lane = (32 - lane) & 31;
 #pragma unroll
-            for (int k2 = 0; k2 < 32; k2 += 2) {
+            for (int k2 = 0; k2 < R; k2 += 2) {
                 if ((STATIC_RANGE && k2 >= 2 && k2 <= 23) || (!STATIC_RANGE && k2 + 1 >= k2lo && k2 <= k2hi)) {   /* warp-uniform */
-                    const float4 w = tw2[(k2 >> 1) * 32 + lane];                /* (cos, sin) of 2 pi k / 2048 for k2 and k2+1 */
+                    const float4 w = tw2[(k2 >> 1) * 32 + lane];                /* (cos, sin) of 2 pi k / N for k2 and k2+1 */
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const int kk = k2 + h;
-                        const int p = bitrev5(kk), pp = bitrev5(31 - kk), p0 = bitrev5((32 - kk) & 31);
-                        float2 pz;                                              /* Z[1024 - k] lives in lane 32-lane, k2' = 31-k2 */
-                        pz.x = __shfl_sync(0xffffffffu, z[pp].x, src_lane);
-                        pz.y = __shfl_sync(0xffffffffu, z[pp].y, src_lane);
-                        if (lane == 0) pz = z[p0];                              /* ... except lane 0: own register k2' = 32-k2 */
-                        float xr, xi;
-                        real_split_2x(z[p], pz, h ? w.z : w.x, h ? w.w : w.y, xr, xi);
-                        if (kk == 0 && lane == 0) { xr = 2.0f * (z[p].x + z[p].y); xi = 2.0f * (z[p].x - z[p].y); }   /* DC / packed Nyquist */
-                        vbuf[kk * 32 + lane] = bin_energy(xr, xi, scale_m1);
+#pragma unroll
+                        for (int s = 0; s < S; s++) {
+                            const int p = s * R + bitrevR<R>(kk), pp = s * R + bitrevR<R>(R - 1 - kk), p0 = s * R + bitrevR<R>((R - kk) % R);
+                            float2 pz;                                          /* Z[M - k] lives in lane 32-lane, k2' = R-1-k2 */
+                            pz.x = __shfl_sync(0xffffffffu, z[pp].x, src_lane);
+                            pz.y = __shfl_sync(0xffffffffu, z[pp].y, src_lane);
+                            if (lane == 0) pz = z[p0];                          /* ... except lane 0: own register k2' = R-k2 */
+                            float xr, xi;
+                            real_split_2x(z[p], pz, h ? w.z : w.x, h ? w.w : w.y, xr, xi);
+                            if (kk == 0 && lane == 0) { xr = 2.0f * (z[p].x + z[p].y); xi = 2.0f * (z[p].x - z[p].y); }   /* DC / packed Nyquist */
+                            vbuf[s * M + kk * 32 + lane] = bin_energy(xr, xi, scale_m1);
+                        }
                     }
                 }
             }
             __syncwarp();
             /* band sums, m:379-405: two lanes per band (each sums half of the band's bins), 16 bands per round */
-            float sa, sb;
-            if (STATIC_RANGE) { sa = seg_sum_static<STATIC_HALF0>(vbuf, ra0, rb0 - ra0); sb = seg_sum_static<STATIC_HALF1>(vbuf, ra1, rb1 - ra1); }
-            else              { sa = seg_sum(vbuf, ra0, rb0); sb = seg_sum(vbuf, ra1, rb1); }
-            sa += __shfl_xor_sync(0xffffffffu, sa, 1);
-            sb += __shfl_xor_sync(0xffffffffu, sb, 1);
-            /* even lane: band lane/2, odd lane: band 16 + lane/2; the 32 lanes fill one 128-byte line of the image row */
-            images[((size_t)f * LBAD_ROWS_PER_FRAME + row) * 32 + my_band] = __fdiv_rn((lane & 1) ? sb : sa, divisor);
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const float* v = vbuf + s * M;
+                float sa, sb;
+                if (STATIC_RANGE) { sa = seg_sum_static<STATIC_HALF0>(v, ra0, rb0 - ra0); sb = seg_sum_static<STATIC_HALF1>(v, ra1, rb1 - ra1); }
+                else              { sa = seg_sum(v, ra0, rb0); sb = seg_sum(v, ra1, rb1); }
+                sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+                sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+                /* even lane: band lane/2, odd lane: band 16 + lane/2; the 32 lanes fill one 128-byte line of the image row */
+                images[((size_t)f * LBAD_ROWS_PER_FRAME + row0 + s) * 32 + my_band] = __fdiv_rn((lane & 1) ? sb : sa, divisor);
+            }
             __syncwarp();
         }
         __syncthreads();                                                        /* every warp is done with the samples */
@@ -732,12 +745,13 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     std::vector<float2> twm(M / 2), twn(M); std::vector<float4> tw1(512), tw2(512);
     for (uint32_t j = 0; j < M / 2; j++) { const double a = 2.0 * M_PI * j / M; twm[j] = make_float2((float)cos(a), (float)-sin(a)); }
     for (uint32_t k = 0; k < M; k++) { const double a = 2.0 * M_PI * k / N; twn[k] = make_float2((float)cos(a), (float)sin(a)); }
-    for (int pp = 0; pp < 32; pp += 2) for (int l = 0; l < 32; l++) {            /* fused pass-1 twiddles, in register-position order */
-        const double a0 = 2.0 * M_PI * (double)(l * bitrev5(pp)) / 1024.0, a1 = 2.0 * M_PI * (double)(l * bitrev5(pp + 1)) / 1024.0;
+    const int Rr = (int)(N / 64);                                                 /* lanes per window in the register-FFT kernel (N = 64 R) */
+    for (int pp = 0; pp < 32; pp += 2) for (int l = 0; l < 32; l++) {            /* pass-1 twiddles exp(-2 pi i n2 k1 / M), n2 = lane % R, in register-position order */
+        const double a0 = 2.0 * M_PI * (double)((l % Rr) * bitrev5(pp)) / (double)M, a1 = 2.0 * M_PI * (double)((l % Rr) * bitrev5(pp + 1)) / (double)M;
         tw1[(pp >> 1) * 32 + l] = make_float4((float)cos(a0), (float)-sin(a0), (float)cos(a1), (float)-sin(a1));
     }
-    for (int k2 = 0; k2 < 32; k2 += 2) for (int l = 0; l < 32; l++) {            /* real-split twiddles for bins l+32k2 and l+32(k2+1) */
-        const double a0 = 2.0 * M_PI * (double)(l + 32 * k2) / 2048.0, a1 = 2.0 * M_PI * (double)(l + 32 * (k2 + 1)) / 2048.0;
+    for (int k2 = 0; k2 < 32; k2 += 2) for (int l = 0; l < 32; l++) {            /* real-split twiddles for bins l+32k2 and l+32(k2+1) (rows k2 < R are used) */
+        const double a0 = 2.0 * M_PI * (double)(l + 32 * k2) / (double)N, a1 = 2.0 * M_PI * (double)(l + 32 * (k2 + 1)) / (double)N;
         tw2[(k2 >> 1) * 32 + l] = make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
     }
     LBAD_CUDA_TRY(cudaMalloc(&p->d_tw_m, sizeof(float2) * (M / 2))); LBAD_CUDA_TRY(cudaMalloc(&p->d_tw_n, sizeof(float2) * M));
@@ -746,14 +760,15 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     LBAD_CUDA_TRY(cudaMemcpy(p->d_tw_n, twn.data(), sizeof(float2) * M, cudaMemcpyHostToDevice));
     LBAD_CUDA_TRY(cudaMemcpy(p->d_tw1, tw1.data(), sizeof(float4) * 512, cudaMemcpyHostToDevice));
     LBAD_CUDA_TRY(cudaMemcpy(p->d_tw2, tw2.data(), sizeof(float4) * 512, cudaMemcpyHostToDevice));
-    p->static_range = (kmin >> 5) == 2 && ((kmax - 1) >> 5) == 23;
+    p->static_range = N == 2048 && (kmin >> 5) == 2 && ((kmax - 1) >> 5) == 23;
     for (uint32_t b = 0; b < B && b < 32; b++) {
         const uint32_t half = (geo->khigh[b] - geo->klow[b] + 1) / 2;
         if (half > (uint32_t)(b < 16 ? STATIC_HALF0 : STATIC_HALF1)) p->static_range = false;
     }
     /* fused path: window 2048, 32 bands, even hop, frame span fits in shared memory */
     const uint64_t span = 127ull * geo->stride + N;
-    p->fused_ok = (N == 2048 && B == 32 && (geo->stride % 2 == 0) && span * 4 < (1u << 20) && fused_layout((uint32_t)span).total_bytes <= p->smem_optin);
+    p->fused_ok = ((N == 2048 || N == 1024 || N == 512 || N == 256) && B == 32 && (geo->stride % 2 == 0) && span * 4 < (1u << 20) &&
+                   fused_layout((uint32_t)span).total_bytes <= p->smem_optin);
     const char* st = getenv("LBAD_STAGE");
     p->stage_mode = st ? (strcmp(st, "tma") == 0 ? 1 : strcmp(st, "ldg") == 0 ? 0 : -1) : -1;
     if (const char* sf = getenv("LBAD_SLAB_FRAMES")) { const unsigned long v = strtoul(sf, nullptr, 10); if (v >= 1 && v <= (1u << 18)) p->slab_frames_cap = (uint32_t)v; }
@@ -834,7 +849,8 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
         /* TMA bulk copies need 16-byte aligned sources and sizes */
         bool tma_ok = ((uintptr_t)d_pcm % 16 == 0) && (clip_stride % 4 == 0) && (g.stride % 4 == 0);
         if (p->stage_mode == 0) tma_ok = false;
-        auto kern = p->static_range ? bands_fused_kernel<true> : bands_fused_kernel<false>;
+        auto kern = p->static_range ? bands_fused_kernel<32, true> : g.window == 2048 ? bands_fused_kernel<32, false> : g.window == 1024 ? bands_fused_kernel<16, false>
+                  : g.window == 512 ? bands_fused_kernel<8, false> : bands_fused_kernel<4, false>;
         LBAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes));
         int per_sm = 0;
         LBAD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, L.total_bytes));

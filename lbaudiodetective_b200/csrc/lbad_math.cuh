@@ -3,6 +3,11 @@
  * that the exact same functions run inside the CUDA kernels (lbad_extract.cu, lbad_search.cu) and inside the
  * host-side lane emulator used by the CPU unit tests (tests/test_lane_emulation.py -> csrc/lane_emulator.cpp).
  *
+ * Windows shorter than 2048 use the same network with several windows per warp: a window of N = 64 R samples (R = 32, 16, 8, 4)
+ * is M = 32 R complex points, n = R n1 + n2, k = k1 + 32 k2; 32/R windows sit side by side in the lanes for pass 1 (lane = window
+ * * R + n2, the in-lane 32-point DFT over n1 is unchanged), the same 32 x 32 transpose follows, and pass 2 is fft32_tail<R>: one
+ * R-point DFT per window in every lane.
+ *
  * Layout of the 2048-point real FFT used by the fused kernel (one warp per window):
  *   z[n] = x[2n] + i x[2n+1], n < 1024 = 32 x 32.   n = 32 n1 + n2,  k = k1 + 32 k2.
  *   pass 1: lane n2 holds z[32 n1 + n2] (n1 = register index) and does a 32-point DFT over n1 -> A[n2][k1]
@@ -90,16 +95,24 @@ LBAD_HD void fft32_stage(float2 (&z)[32], const float2 neg1, std::integer_sequen
     (fft32_butterfly<H, (I / H) * 2 * H, I % H>(z, neg1), ...);
 }
 
-/* in-place forward 32-point DFT (e^{-i theta}); output index of register position p is bitrev5(p) */
-LBAD_HD void fft32(float2 (&z)[32]) {
+/* The last log2(R) stages of the 32-point DIF network: 32/R independent forward R-point DFTs, one on every aligned block of R
+ * register positions (R = 32: the whole 32-point DFT).  Inside a block, position q holds output index bitrev over log2(R) bits. */
+template <int R>
+LBAD_HD void fft32_tail(float2 (&z)[32]) {
     const float2 neg1 = make_float2(-1.0f, -1.0f);
     using seq = std::make_integer_sequence<int, 16>;
-    fft32_stage<16>(z, neg1, seq{});
-    fft32_stage<8>(z, neg1, seq{});
-    fft32_stage<4>(z, neg1, seq{});
-    fft32_stage<2>(z, neg1, seq{});
-    fft32_stage<1>(z, neg1, seq{});
+    if constexpr (R >= 32) fft32_stage<16>(z, neg1, seq{});
+    if constexpr (R >= 16) fft32_stage<8>(z, neg1, seq{});
+    if constexpr (R >= 8) fft32_stage<4>(z, neg1, seq{});
+    if constexpr (R >= 4) fft32_stage<2>(z, neg1, seq{});
+    if constexpr (R >= 2) fft32_stage<1>(z, neg1, seq{});
 }
+/* in-place forward 32-point DFT (e^{-i theta}); output index of register position p is bitrev5(p) */
+LBAD_HD void fft32(float2 (&z)[32]) { fft32_tail<32>(z); }
+
+LBAD_HD constexpr int log2c(int v) { return v <= 1 ? 0 : 1 + log2c(v >> 1); }
+/* bit reversal over log2(R) bits */
+template <int R> LBAD_HD constexpr int bitrevR(int q) { return bitrev5(q) >> (5 - log2c(R)); }
 
 /* 2 X[k] from Z[k] = z and Z[M-k] = p, with w = exp(-2 pi i k / N) = (c, -s) given as c, s */
 LBAD_HD void real_split_2x(float2 z, float2 p, float c, float s, float& xr, float& xi) {

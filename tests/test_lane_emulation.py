@@ -45,6 +45,25 @@ def test_window_pipeline_matches_oracle(emu, port):
         assert (np.abs(out - ref_bands) / np.abs(ref_bands)).max() < 1e-4
 
 
+@pytest.mark.parametrize("window", [2048, 1024, 512, 256])
+def test_multi_window_warp_matches_oracle(emu, port, window):
+    """bands_fused_kernel<R>: 32/R windows of 64 R samples side by side in one warp — same index algebra, checked for every R."""
+    R = window // 64; S = 32 // R
+    cfg = Cfg.default(window=window); idx, lo, hi = port.band_table(cfg); div = (idx[1:] - idx[:-1]).astype(np.float32)
+    pcm = port.synth_clip(4, 30000)
+    for start in (0, 64 * 7, 64 * 100):
+        seg = np.ascontiguousarray(pcm[start:start + 64 * (S - 1) + window])
+        out = np.zeros((S, 32), np.float32); spec = np.zeros((S, window), np.float32)
+        emu.lbad_emulate_windows(C.c_int(R), vp(seg), C.c_int(64), vp(lo), vp(hi), vp(div), C.c_float(4.0 / window), C.c_uint32(int(lo.min())), C.c_uint32(int(hi.max())), vp(out), vp(spec))
+        for s in range(S):
+            win = seg[64 * s: 64 * s + window]
+            ref_spec = port.fft2x(win).reshape(-1, 2); k = np.arange(lo.min(), hi.max())
+            assert np.abs(spec[s].reshape(-1, 2)[k] - ref_spec[k]).max() <= 2e-6 * np.abs(ref_spec).max(), (window, s)
+            ref_bands = port.band_energies(cfg, seg[64 * s:], 1)[0]
+            floor = 1e-9 * np.abs(ref_bands).max()
+            assert (np.abs(out[s] - ref_bands) <= 3e-4 * np.abs(ref_bands) + floor).all(), (window, s)
+
+
 def test_dc_and_nyquist_packing(emu, port):
     """bin 0 carries 2X[0] in re and 2X[N/2] in im (vDSP packing)."""
     rng = np.random.default_rng(5); win = rng.standard_normal(2048).astype(np.float32)
