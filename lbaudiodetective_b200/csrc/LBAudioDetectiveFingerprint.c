@@ -143,16 +143,11 @@ static void die_no_device(const char* what, int code) {
     abort();
 }
 
-/* score = CompareToFingerprint(fp1, fp2, range) on the GPU: fp1 becomes a one-clip database, fp2 the single query */
+/* score = CompareToFingerprint(fp1, fp2, range) on the GPU (compare_pair_kernel, cached per-thread context) */
 static Float32 gpu_compare(const UInt32* w1, UInt32 c1, const UInt32* w2, UInt32 c2, UInt32 W, UInt32 pairs, UInt32 pairs_full) {
-    lbadcu_db* db = NULL;
-    int e = lbadcu_db_create(W, pairs_full, &db);
-    if (e != LBAD_OK) die_no_device("LBAudioDetectiveFingerprintCompareToFingerprint", e);
-    Float32 score = 0.0f; UInt32 idx = 0;
-    UInt32 dummy[16] = {0};
-    e = lbadcu_db_append(db, c1 ? w1 : dummy, 0, 1, &c1, 0);
-    if (e == LBAD_OK) e = lbadcu_db_search_host(db, c2 ? w2 : dummy, 1, c2, pairs, 1, &score, &idx, NULL);
-    lbadcu_db_destroy(db);
+    (void)pairs_full;
+    Float32 score = 0.0f;
+    int e = lbadcu_compare_pair(W, pairs, w1, c1, w2, c2, &score);
     if (e != LBAD_OK) die_no_device("LBAudioDetectiveFingerprintCompareToFingerprint", e);
     return score;
 }

@@ -21,6 +21,7 @@
 #include "lbad_math.cuh"
 #include <vector>
 #include <algorithm>
+#include <string.h>
 
 namespace lbad {
 
@@ -344,6 +345,43 @@ search_generic_kernel(const uint32_t* __restrict__ db, const uint32_t* __restric
     }
 }
 
+/* One pair of fingerprints, LBAudioDetectiveFingerprintCompareToFingerprint (FP.m:119-149) as written: swap so that fp1 has more
+ * subfingerprints, then for every time offset the f32 mean of CompareSubfingerprints over fp2's subfingerprints, and the maximum.
+ * The offsets are spread over the threads of one CTA; the maximum of non-NaN means does not depend on the order, and the only NaN
+ * (0/0 when fp2 is empty) leaves the match at 0, as Apple's MAX does. */
+template <int W>
+__global__ void __launch_bounds__(128)
+compare_pair_kernel(const uint32_t* __restrict__ wa, const uint32_t ca, const uint32_t* __restrict__ wb, const uint32_t cb, const uint32_t pairs,
+                    float* __restrict__ out) {
+    const bool swap = ca < cb;                                                  /* FP.m:123-131 */
+    const uint32_t* w1 = swap ? wb : wa; const uint32_t* w2 = swap ? wa : wb;
+    const uint32_t c1 = swap ? cb : ca, c2 = swap ? ca : cb;
+    const PairMask<W> mask = make_mask<W>(pairs);
+    float best = 0.0f;                                                          /* FP.m:133 */
+    if (c2 > 0) for (uint32_t o = threadIdx.x; o + c2 <= c1; o += blockDim.x) {  /* FP.m:136 */
+        float sum = 0.0f;
+        for (uint32_t i = 0; i < c2; i++) {                                     /* FP.m:139-142 */
+            const uint32_t* s1 = w1 + (size_t)(o + i) * 2 * W; const uint32_t* s2 = w2 + (size_t)i * 2 * W;
+            uint32_t hits = 0, possible = 0;
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                const uint32_t p1 = s1[w] & mask.w[w], m1 = s1[W + w] & mask.w[w];
+                possible += __popc(p1 | m1);                                    /* FP.m:159-160 */
+                hits += __popc(hit_word(p1, m1, s2[w] & mask.w[w], s2[W + w] & mask.w[w]));   /* FP.m:162-167 */
+            }
+            sum = __fadd_rn(sum, possible ? __fdiv_rn((float)hits, (float)possible) : 0.0f);   /* FP.m:171-175 */
+        }
+        const float mean = __fdiv_rn(sum, (float)c2);                           /* FP.m:144 */
+        best = (best < mean) ? mean : best;
+    }
+    __shared__ float red[4];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, d));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) *out = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+}
+
 /* (score desc, clip index asc) strict order; a is "better" than b */
 __device__ __forceinline__ bool better(float sa, uint32_t ia, float sb, uint32_t ib) { return sa > sb || (sa == sb && ia < ib); }
 
@@ -625,5 +663,58 @@ extern "C" int lbadcu_merge_topk_host(const float* h_sc, const uint32_t* h_id, u
     LBAD_CUDA_TRY(cudaGetLastError());
     LBAD_CUDA_TRY(cudaMemcpy(o_sc, d_o, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost)); LBAD_CUDA_TRY(cudaMemcpy(o_id, d_oi, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost));
     cudaFree(d_sc); cudaFree(d_id); cudaFree(d_o); cudaFree(d_oi);
+    return LBAD_OK;
+}
+
+/* Pairwise compare with a cached per-thread context (stream, pinned staging, device buffers): the drop-in
+ * LBAudioDetectiveFingerprintCompareToFingerprint is called in tight loops by the reference's own tests, so it must not pay for
+ * allocations.  One H2D copy, one kernel, one 4-byte D2H copy. */
+namespace {
+struct PairCtx {
+    int device = -1; cudaStream_t stream = nullptr;
+    uint32_t* h_stage = nullptr; uint32_t* d_words = nullptr; size_t cap_words = 0;
+    float* d_score = nullptr; float* h_score = nullptr;
+    void release() {
+        if (device < 0) return;
+        cudaSetDevice(device);
+        if (stream) cudaStreamDestroy(stream);
+        cudaFreeHost(h_stage); cudaFree(d_words); cudaFree(d_score); cudaFreeHost(h_score);
+        *this = PairCtx();
+    }
+    ~PairCtx() { /* process teardown: the CUDA context may already be gone; leave the buffers to the driver */ }
+};
+thread_local PairCtx g_pair;
+}
+
+extern "C" int lbadcu_compare_pair(uint32_t W, uint32_t pairs, const uint32_t* w1, uint32_t c1, const uint32_t* w2, uint32_t c2, float* out) {
+    if ((W != 2 && W != 4 && W != 8) || !out || (c1 && !w1) || (c2 && !w2)) return LBAD_ERR_ARG;
+    if (lbadcu_device_available() != LBAD_OK) { set_error("no CUDA device available (this library has no CPU fallback)"); return LBAD_ERR_NODEVICE; }
+    int dev = 0; LBAD_CUDA_TRY(cudaGetDevice(&dev));
+    PairCtx& c = g_pair;
+    if (c.device != dev) {
+        c.release();
+        c.device = dev;
+        LBAD_CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        LBAD_CUDA_TRY(cudaMalloc(&c.d_score, sizeof(float))); LBAD_CUDA_TRY(cudaHostAlloc(&c.h_score, sizeof(float), cudaHostAllocDefault));
+    }
+    const size_t n1 = (size_t)c1 * 2 * W, n2 = (size_t)c2 * 2 * W, need = n1 + n2 ? n1 + n2 : 1;
+    if (c.cap_words < need) {
+        LBAD_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        cudaFreeHost(c.h_stage); cudaFree(c.d_words); c.h_stage = nullptr; c.d_words = nullptr; c.cap_words = 0;
+        const size_t cap = need < 4096 ? 4096 : need * 2;
+        LBAD_CUDA_TRY(cudaHostAlloc(&c.h_stage, cap * sizeof(uint32_t), cudaHostAllocDefault)); LBAD_CUDA_TRY(cudaMalloc(&c.d_words, cap * sizeof(uint32_t)));
+        c.cap_words = cap;
+    }
+    if (n1) memcpy(c.h_stage, w1, n1 * sizeof(uint32_t));
+    if (n2) memcpy(c.h_stage + n1, w2, n2 * sizeof(uint32_t));
+    if (n1 + n2) LBAD_CUDA_TRY(cudaMemcpyAsync(c.d_words, c.h_stage, (n1 + n2) * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+    if (pairs > 32 * W) pairs = 32 * W;
+    if (W == 2) compare_pair_kernel<2><<<1, 128, 0, c.stream>>>(c.d_words, c1, c.d_words + n1, c2, pairs, c.d_score);
+    else if (W == 4) compare_pair_kernel<4><<<1, 128, 0, c.stream>>>(c.d_words, c1, c.d_words + n1, c2, pairs, c.d_score);
+    else compare_pair_kernel<8><<<1, 128, 0, c.stream>>>(c.d_words, c1, c.d_words + n1, c2, pairs, c.d_score);
+    LBAD_CUDA_TRY(cudaGetLastError());
+    LBAD_CUDA_TRY(cudaMemcpyAsync(c.h_score, c.d_score, sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+    LBAD_CUDA_TRY(cudaStreamSynchronize(c.stream));
+    *out = *c.h_score;
     return LBAD_OK;
 }

@@ -34,4 +34,15 @@ if a.what in ("both", "search"):
         db.search_device(q.data_ptr(), a.queries, 6, 10, sc.data_ptr(), ix.data_ptr(), stream=s.cuda_stream)
     torch.cuda.synchronize()
     assert (ix[:, 0].cpu().numpy() == np.arange(a.queries)).all()
+
+if a.what == "latency":
+    import time
+    from oracle.oracle import Port
+    p = Port(); x = p.synth_clip(0, 55120); y = p.synth_clip(1, 55120)
+    d = lb.Detective(); fa = d.process_pcm(x); fb = d.process_pcm(y)
+    for name, fn in (("ProcessPCM(10 s clip)", lambda: d.process_pcm(x)), ("CompareToFingerprint(6 x 6)", lambda: fa.compare(fb, 200)),
+                     ("ComparePCM(2 x 10 s)", lambda: d.compare_pcm(x, y, 0))):
+        fn(); t0 = time.perf_counter()
+        for _ in range(200): fn()
+        print("%-30s %.1f us per call" % (name, (time.perf_counter() - t0) / 200 * 1e6))
 print("prof_run done")
