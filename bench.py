@@ -147,7 +147,7 @@ def main():
     import torch
     import torch.distributed as dist
     import lbaudiodetective_b200 as lb
-    from lbaudiodetective_b200.dist import shard_range, gather_topk
+    from lbaudiodetective_b200.dist import shard_range, gather_and_merge_topk_device
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -291,10 +291,10 @@ def main():
         del codes
         d_sc = torch.empty((args.queries, 10), dtype=torch.float32, device="cuda"); d_idx = torch.empty((args.queries, 10), dtype=torch.int32, device="cuda")
         def search_step():
+            # per-GPU top-k on the shard, ONE NCCL all-gather of the [query][k] lists, device merge, then the result to the host
             db.search_device(qw.data_ptr(), args.queries, 6, 10, d_sc.data_ptr(), d_idx.data_ptr(), stream=stream)
-            torch.cuda.synchronize()
-            gs, gi = gather_topk(d_sc.cpu().numpy(), d_idx.cpu().numpy().view(np.uint32))
-            return lb.merge_topk(gs, gi) if world > 1 else (gs[0], gi[0])
+            m_sc, m_id = gather_and_merge_topk_device(d_sc, d_idx, stream)
+            return m_sc.cpu().numpy(), m_id.cpu().numpy().view(np.uint32)
         for _ in range(2):
             sc, idx = search_step()
         db.kernel_timing(enable=True, reset=True)

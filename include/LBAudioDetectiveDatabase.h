@@ -49,6 +49,9 @@ LBAD_API OSStatus LBAudioDetectiveDatabaseSearchDevice(LBAudioDetectiveDatabaseR
  * ordered (score desc, clip index asc) — the result equals a single-GPU search over the union.  Host memory. */
 LBAD_API OSStatus LBAudioDetectiveDatabaseMergeTopK(const Float32* inScores, const UInt32* inClipIndices, UInt32 inNumberOfLists, UInt32 inNumberOfQueries, UInt32 inK,
                                                    Float32* outScores, UInt32* outClipIndices);
+/* Same with every buffer on the device (e.g. straight out of an NCCL all-gather), enqueued on inStream without synchronising. */
+LBAD_API OSStatus LBAudioDetectiveDatabaseMergeTopKDevice(const Float32* inDeviceScores, const UInt32* inDeviceClipIndices, UInt32 inNumberOfLists, UInt32 inNumberOfQueries, UInt32 inK,
+                                                         Float32* outDeviceScores, UInt32* outDeviceClipIndices, void* inStream);
 /* Persistence: packed binary file (header: L, W, clip count, per-clip subfingerprint counts; body: the bit planes), so that a
  * database is reloaded without re-extracting.  Load returns NULL on a missing / malformed file or without a CUDA device. */
 LBAD_API OSStatus LBAudioDetectiveDatabaseSave(LBAudioDetectiveDatabaseRef inDatabase, const char* inPath);

@@ -103,6 +103,7 @@ def load_library(build_if_missing: bool = True):
         "LBAudioDetectiveDatabaseSearch": (C.c_int32, [vp, P(vp), u32, u32, u32, vp, vp]),
         "LBAudioDetectiveDatabaseSearchDevice": (C.c_int32, [vp, vp, u32, u32, u32, u32, vp, vp, vp]),
         "LBAudioDetectiveDatabaseMergeTopK": (C.c_int32, [vp, vp, u32, u32, u32, vp, vp]),
+        "LBAudioDetectiveDatabaseMergeTopKDevice": (C.c_int32, [vp, vp, u32, u32, u32, vp, vp, vp]),
         "LBAudioDetectiveDatabaseSave": (C.c_int32, [vp, C.c_char_p]),
         "LBAudioDetectiveDatabaseLoad": (vp, [C.c_char_p]),
         "LBAudioDetectiveDatabaseComparesPerQuery": (u64, [vp, u32]),
@@ -493,6 +494,10 @@ def merge_topk(scores, indices):
     os_ = np.zeros((n_q, k), np.float32); oi = np.zeros((n_q, k), np.uint32)
     _check(lib().LBAudioDetectiveDatabaseMergeTopK(_ptr(s), _ptr(i), n_lists, n_q, k, _ptr(os_), _ptr(oi)), "DatabaseMergeTopK")
     return os_, oi
+
+
+def merge_topk_device(d_scores_ptr, d_idx_ptr, n_lists, n_q, k, d_out_scores_ptr, d_out_idx_ptr, stream=None):
+    _check(lib().LBAudioDetectiveDatabaseMergeTopKDevice(d_scores_ptr, d_idx_ptr, n_lists, n_q, k, d_out_scores_ptr, d_out_idx_ptr, stream), "DatabaseMergeTopKDevice")
 
 
 def synthesize_device(d_out_ptr, n_clips, clip_len, clip_stride, first_clip_id=0, base_seed=0x1BAD5EED, sample_rate=5512.0, stream=None):

@@ -93,6 +93,10 @@ OSStatus LBAudioDetectiveDatabaseMergeTopK(const Float32* inScores, const UInt32
     return lbad_status(lbadcu_merge_topk_host(inScores, inClipIndices, nLists, nQ, inK, outScores, outClipIndices));
 }
 
+OSStatus LBAudioDetectiveDatabaseMergeTopKDevice(const Float32* dScores, const UInt32* dIdx, UInt32 nLists, UInt32 nQ, UInt32 inK, Float32* dOutScores, UInt32* dOutIdx, void* stream) {
+    return lbad_status(lbadcu_merge_topk_device(dScores, dIdx, nLists, nQ, inK, dOutScores, dOutIdx, stream));
+}
+
 UInt64 LBAudioDetectiveDatabaseComparesPerQuery(LBAudioDetectiveDatabaseRef d, UInt32 qCount) { return d ? lbadcu_db_compares_per_query(d->db, qCount) : 0; }
 UInt64 LBAudioDetectiveDatabaseGetKernelLaunchCount(LBAudioDetectiveDatabaseRef d) { return d ? lbadcu_db_launches(d->db) : 0; }
 UInt32 LBAudioDetectiveDatabaseGetKernelTiming(LBAudioDetectiveDatabaseRef d, Boolean inEnable, Boolean inReset, Float64* outTotalMilliseconds) {

@@ -20,6 +20,18 @@ void set_error(const char* fmt, ...);
         }                                                                                           \
     } while (0)
 
+/* cudaMalloc with scope lifetime, so that an early error return does not leak */
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, (n ? n : 1) * sizeof(T)); }
+    ~DevBuf() { if (p) cudaFree(p); }
+    operator T*() const { return p; }
+};
+
 /* Device time of selected launches, measured with CUDA events on the launching stream. */
 struct LaunchTimer {
     bool enabled = false;

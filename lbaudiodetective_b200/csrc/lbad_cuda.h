@@ -87,6 +87,7 @@ uint64_t lbadcu_db_compares_per_query(const lbadcu_db* db, uint32_t q_count);
 /* merges [list][q][k] top-k lists (host memory) with the device merge kernel; order (score desc, index asc) */
 int  lbadcu_merge_topk_host(const float* h_sc, const uint32_t* h_id, uint32_t n_lists, uint32_t n_q, uint32_t k, float* o_sc, uint32_t* o_id);
 
+int  lbadcu_merge_topk_device(const float* d_sc, const uint32_t* d_id, uint32_t n_lists, uint32_t n_q, uint32_t k, float* d_o_sc, uint32_t* d_o_id, void* stream);
 /* one pair, LBAudioDetectiveFingerprintCompareToFingerprint(fp1, fp2) with pairs = ceil(min(range, L)/2); cached per-thread context */
 int  lbadcu_compare_pair(uint32_t words_per_plane, uint32_t pairs, const uint32_t* w1, uint32_t c1, const uint32_t* w2, uint32_t c2, float* out);
 

@@ -924,16 +924,15 @@ extern "C" int lbadcu_transform_images_host(lbadcu_plan* p, const float* h_image
     if (!p || !h_images || count == 0) return LBAD_ERR_ARG;
     LBAD_CUDA_TRY(cudaSetDevice(p->device));
     const size_t n = (size_t)count * LBAD_ROWS_PER_FRAME * p->g.bands, nw = (size_t)count * 2 * p->g.words_per_plane;
-    float *d_img = nullptr, *d_haar = nullptr; uint32_t* d_words = nullptr;
-    LBAD_CUDA_TRY(cudaMalloc(&d_img, n * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&d_haar, n * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&d_words, nw * sizeof(uint32_t)));
+    DevBuf<float> d_img, d_haar; DevBuf<uint32_t> d_words;
+    LBAD_CUDA_TRY(d_img.alloc(n)); LBAD_CUDA_TRY(d_haar.alloc(n)); LBAD_CUDA_TRY(d_words.alloc(nw));
     LBAD_CUDA_TRY(cudaMemcpyAsync(d_img, h_images, n * sizeof(float), cudaMemcpyHostToDevice, p->stream));
     int e = haar_select_dispatch(p, d_img, d_haar, d_words, count, p->stream);
     if (e == LBAD_OK) {
         if (h_haar) LBAD_CUDA_TRY(cudaMemcpyAsync(h_haar, d_haar, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
         if (h_words) LBAD_CUDA_TRY(cudaMemcpyAsync(h_words, d_words, nw * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));
-        LBAD_CUDA_TRY(cudaStreamSynchronize(p->stream));
     }
-    cudaFree(d_img); cudaFree(d_haar); cudaFree(d_words);
+    LBAD_CUDA_TRY(cudaStreamSynchronize(p->stream));
     return e;
 }
 
@@ -974,9 +973,9 @@ static int extract_host_impl(lbadcu_plan* p, const void* h_pcm_v, int sample_byt
         if (sample_bytes == 2 && !p->d_chunk_i16[i]) LBAD_CUDA_TRY(cudaMalloc(&p->d_chunk_i16[i], need_pcm * sizeof(int16_t)));
     }
     p->chunk_pcm_floats = need_pcm; p->chunk_words = need_words; if (sample_bytes == 2) p->chunk_i16 = need_pcm;
-    float *d_img = nullptr, *d_haar = nullptr;
-    if (h_images) LBAD_CUDA_TRY(cudaMalloc(&d_img, (size_t)clips_per_chunk * img_per_clip * sizeof(float)));
-    if (h_haar) LBAD_CUDA_TRY(cudaMalloc(&d_haar, (size_t)clips_per_chunk * img_per_clip * sizeof(float)));
+    DevBuf<float> d_img, d_haar;
+    if (h_images) LBAD_CUDA_TRY(d_img.alloc((size_t)clips_per_chunk * img_per_clip));
+    if (h_haar) LBAD_CUDA_TRY(d_haar.alloc((size_t)clips_per_chunk * img_per_clip));
     int rc = LBAD_OK;
     uint32_t chunk = 0;
     for (uint64_t c0 = 0; c0 < n_clips && rc == LBAD_OK; c0 += clips_per_chunk, chunk++) {
@@ -1001,7 +1000,6 @@ static int extract_host_impl(lbadcu_plan* p, const void* h_pcm_v, int sample_byt
     }
     for (int i = 0; i < 3; i++) LBAD_CUDA_TRY(cudaStreamSynchronize(p->copy_streams[i]));
     LBAD_CUDA_TRY(cudaStreamSynchronize(p->stream));
-    cudaFree(d_img); cudaFree(d_haar);
     return rc;
 }
 

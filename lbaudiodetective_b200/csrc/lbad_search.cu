@@ -635,19 +635,17 @@ extern "C" int lbadcu_db_search_host(lbadcu_db* db, const uint32_t* h_q, uint32_
     LBAD_CUDA_TRY(cudaSetDevice(db->device));
     const uint32_t W = db->W, n_clips = lbadcu_db_clips(db);
     const size_t qn = (size_t)n_q * cq * 2 * W;
-    uint32_t* d_q = nullptr; float* d_sc = nullptr; uint32_t* d_id = nullptr; float* d_all = nullptr;
-    LBAD_CUDA_TRY(cudaMalloc(&d_q, (qn ? qn : 1) * sizeof(uint32_t)));
-    LBAD_CUDA_TRY(cudaMalloc(&d_sc, (size_t)n_q * k * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&d_id, (size_t)n_q * k * sizeof(uint32_t)));
-    if (h_all && n_clips) LBAD_CUDA_TRY(cudaMalloc(&d_all, (size_t)n_q * n_clips * sizeof(float)));
+    DevBuf<uint32_t> d_q, d_id; DevBuf<float> d_sc, d_all;
+    LBAD_CUDA_TRY(d_q.alloc(qn)); LBAD_CUDA_TRY(d_sc.alloc((size_t)n_q * k)); LBAD_CUDA_TRY(d_id.alloc((size_t)n_q * k));
+    if (h_all && n_clips) LBAD_CUDA_TRY(d_all.alloc((size_t)n_q * n_clips));
     if (qn) LBAD_CUDA_TRY(cudaMemcpyAsync(d_q, h_q, qn * sizeof(uint32_t), cudaMemcpyHostToDevice, db->stream));
     int e = lbadcu_db_search_device(db, d_q, n_q, cq, pairs, k, d_sc, d_id, d_all, db->stream);
     if (e == LBAD_OK) {
         LBAD_CUDA_TRY(cudaMemcpyAsync(h_scores, d_sc, (size_t)n_q * k * sizeof(float), cudaMemcpyDeviceToHost, db->stream));
         LBAD_CUDA_TRY(cudaMemcpyAsync(h_idx, d_id, (size_t)n_q * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, db->stream));
-        if (d_all) LBAD_CUDA_TRY(cudaMemcpyAsync(h_all, d_all, (size_t)n_q * n_clips * sizeof(float), cudaMemcpyDeviceToHost, db->stream));
-        LBAD_CUDA_TRY(cudaStreamSynchronize(db->stream));
+        if (d_all.p) LBAD_CUDA_TRY(cudaMemcpyAsync(h_all, d_all, (size_t)n_q * n_clips * sizeof(float), cudaMemcpyDeviceToHost, db->stream));
     }
-    cudaFree(d_q); cudaFree(d_sc); cudaFree(d_id); cudaFree(d_all);
+    LBAD_CUDA_TRY(cudaStreamSynchronize(db->stream));
     return e;
 }
 
@@ -656,13 +654,20 @@ extern "C" int lbadcu_merge_topk_host(const float* h_sc, const uint32_t* h_id, u
     if (!h_sc || !h_id || !o_sc || !o_id || n_lists == 0 || n_q == 0 || k == 0) return LBAD_ERR_ARG;
     if (lbadcu_device_available() != LBAD_OK) { set_error("no CUDA device available (this library has no CPU fallback)"); return LBAD_ERR_NODEVICE; }
     const size_t n = (size_t)n_lists * n_q * k;
-    float *d_sc = nullptr, *d_o = nullptr; uint32_t *d_id = nullptr, *d_oi = nullptr;
-    LBAD_CUDA_TRY(cudaMalloc(&d_sc, n * 4)); LBAD_CUDA_TRY(cudaMalloc(&d_id, n * 4)); LBAD_CUDA_TRY(cudaMalloc(&d_o, (size_t)n_q * k * 4)); LBAD_CUDA_TRY(cudaMalloc(&d_oi, (size_t)n_q * k * 4));
+    DevBuf<float> d_sc, d_o; DevBuf<uint32_t> d_id, d_oi;
+    LBAD_CUDA_TRY(d_sc.alloc(n)); LBAD_CUDA_TRY(d_id.alloc(n)); LBAD_CUDA_TRY(d_o.alloc((size_t)n_q * k)); LBAD_CUDA_TRY(d_oi.alloc((size_t)n_q * k));
     LBAD_CUDA_TRY(cudaMemcpy(d_sc, h_sc, n * 4, cudaMemcpyHostToDevice)); LBAD_CUDA_TRY(cudaMemcpy(d_id, h_id, n * 4, cudaMemcpyHostToDevice));
     merge_topk_kernel<<<(n_q + 3) / 4, 128>>>(d_sc, d_id, n_lists, n_q, (int)k, d_o, d_oi);
     LBAD_CUDA_TRY(cudaGetLastError());
     LBAD_CUDA_TRY(cudaMemcpy(o_sc, d_o, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost)); LBAD_CUDA_TRY(cudaMemcpy(o_id, d_oi, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost));
-    cudaFree(d_sc); cudaFree(d_id); cudaFree(d_o); cudaFree(d_oi);
+    return LBAD_OK;
+}
+
+/* same merge on lists that already live on the device (e.g. the output of an NCCL all-gather), enqueued on the caller's stream */
+extern "C" int lbadcu_merge_topk_device(const float* d_sc, const uint32_t* d_id, uint32_t n_lists, uint32_t n_q, uint32_t k, float* d_o_sc, uint32_t* d_o_id, void* stream) {
+    if (!d_sc || !d_id || !d_o_sc || !d_o_id || n_lists == 0 || n_q == 0 || k == 0) return LBAD_ERR_ARG;
+    merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_sc, d_id, n_lists, n_q, (int)k, d_o_sc, d_o_id);
+    LBAD_CUDA_TRY(cudaGetLastError());
     return LBAD_OK;
 }
 
