@@ -95,6 +95,29 @@ def test_process_pcm_against_oracle(lb, checker):
     assert mism / total <= BIT_MISMATCH_BUDGET
 
 
+def test_bit_mismatch_rate_on_a_large_sample(lb, checker):
+    """The 0.1 % budget measured where it means something: 120 x 30 s clips (2,280 subfingerprints, 456,000 Booleans) plus quiet,
+    loud and tonal variants, against the oracle run on all host threads."""
+    cfg = Cfg.default(); d = lb.Detective()
+    base = np.stack([checker.synth_clip(500 + i, 165360) for i in range(120)])
+    t = np.arange(165360) / 5512.0
+    variants = {"chirp+tone+noise": base,
+                "x 1e-3 (quiet)": (base[:24] * np.float32(1e-3)).astype(np.float32),
+                "x 30 (clipped range exceeded)": (base[:24] * np.float32(30.0)).astype(np.float32),
+                "two pure tones, no noise": np.stack([(0.5 * np.sin(2 * np.pi * (440.0 + 7 * i) * t) + 0.3 * np.sin(2 * np.pi * (1234.5 + 3 * i) * t)).astype(np.float32) for i in range(12)])}
+    worst = 0.0
+    for name, pcm in variants.items():
+        want, _ = checker.extract_batch(cfg, pcm, threads=os.cpu_count() or 1)
+        got = lb.unpack_words(d.process_batch(pcm), 200)
+        assert got.shape == want.shape
+        rate = mismatch_rate(got, want)
+        per_sub = (got != want).reshape(-1, 200).any(axis=1).mean()
+        print("%-32s %8d Booleans, mismatch rate %.2e (%.2f %% of subfingerprints touched)" % (name, want.size, rate, 100 * per_sub))
+        if "pure tones" not in name:
+            worst = max(worst, rate)
+    assert worst <= BIT_MISMATCH_BUDGET
+
+
 def test_transform_images_bit_exact(lb, checker, config1):
     """Given identical spectral images, Haar (IEEE divides, same order) and the ordered top-t are bit-exact."""
     d = lb.Detective()
