@@ -65,7 +65,7 @@ static void emulate_windows(const float* pcm, int hop, const uint32_t* klow, con
                         real_split_2x(z[lane][p], pz, h ? w[2] : w[0], h ? w[3] : w[1], xr, xi);
                         if (kk == 0 && lane == 0) { xr = 2.0f * (z[lane][p].x + z[lane][p].y); xi = 2.0f * (z[lane][p].x - z[lane][p].y); }
                         if (out_spec) { out_spec[(size_t)s * N + 2 * (kk * 32 + lane)] = xr; out_spec[(size_t)s * N + 2 * (kk * 32 + lane) + 1] = xi; }
-                        vbuf[s * M + kk * 32 + lane] = bin_energy(xr, xi, scale_m1);
+                        vbuf[s * M + kk * 32 + lane] = bin_energy_raw(xr, xi, scale_m1);
                     }
                 }
             }
@@ -92,7 +92,9 @@ static void emulate_windows(const float* pcm, int hop, const uint32_t* klow, con
         for (int lane = 0; lane < 32; lane++) {
             const int my_band = (lane >> 1) + ((lane & 1) ? 16 : 0);
             const float a2 = sa[lane] + sa[lane ^ 1], b2 = sb[lane] + sb[lane ^ 1];
-            out_bands[s * 32 + my_band] = ((lane & 1) ? b2 : a2) / divisor[my_band];
+            float tot = (lane & 1) ? b2 : a2;
+            if (!(tot <= 3.402823466e+38f)) { tot = 0.0f; for (uint32_t k = klow[my_band]; k < khigh[my_band]; k++) if (v[k] <= 3.402823466e+38f) tot += v[k]; }
+            out_bands[s * 32 + my_band] = tot / divisor[my_band];
         }
     }
 }

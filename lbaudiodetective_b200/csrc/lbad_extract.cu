@@ -422,7 +422,7 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                             float xr, xi;
                             real_split_2x(z[p], pz, h ? w.z : w.x, h ? w.w : w.y, xr, xi);
                             if (kk == 0 && lane == 0) { xr = 2.0f * (z[p].x + z[p].y); xi = 2.0f * (z[p].x - z[p].y); }   /* DC / packed Nyquist */
-                            vbuf[s * M + kk * 32 + lane] = bin_energy(xr, xi, scale_m1);
+                            vbuf[s * M + kk * 32 + lane] = bin_energy_raw(xr, xi, scale_m1);      /* finiteness is checked on the band sum */
                         }
                     }
                 }
@@ -437,8 +437,13 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                 else              { sa = seg_sum(v, ra0, rb0); sb = seg_sum(v, ra1, rb1); }
                 sa += __shfl_xor_sync(0xffffffffu, sa, 1);
                 sb += __shfl_xor_sync(0xffffffffu, sb, 1);
-                /* even lane: band lane/2, odd lane: band 16 + lane/2; the 32 lanes fill one 128-byte line of the image row */
-                images[((size_t)f * LBAD_ROWS_PER_FRAME + row0 + s) * 32 + my_band] = __fdiv_rn((lane & 1) ? sb : sa, divisor);
+                float tot = (lane & 1) ? sb : sa;                              /* even lane: band lane/2, odd lane: band 16 + lane/2 */
+                if (!(tot <= 3.402823466e+38f)) {                               /* a non-finite term (m:398-401 skips it): re-sum this band filtered */
+                    tot = 0.0f;
+                    for (uint32_t k = bt.klow[my_band]; k < bt.khigh[my_band]; k++) { const float e = v[k]; if (e <= 3.402823466e+38f) tot += e; }
+                }
+                /* the 32 lanes fill one 128-byte line of the image row */
+                images[((size_t)f * LBAD_ROWS_PER_FRAME + row0 + s) * 32 + my_band] = __fdiv_rn(tot, divisor);
             }
             __syncwarp();
         }

@@ -133,6 +133,13 @@ LBAD_HD float bin_energy(float re, float im, float scale_m1) {
     return (v <= 3.402823466e+38f) ? v : 0.0f;
 }
 
+/* The same without the finiteness filter, for callers that check the band sum instead: every term is >= 0, so a band sum is finite
+ * exactly when all of its terms are, and only a non-finite sum (never seen on real audio) needs the filtered re-summation. */
+LBAD_HD float bin_energy_raw(float re, float im, float scale_m1) {
+    const float2 g = fma2(make_float2(fmaxf(re, 0.0f), fmaxf(im, 0.0f)), make_float2(scale_m1, scale_m1), make_float2(re, im));
+    return fmaf(g.x, g.x, g.y * g.y);
+}
+
 /* Hit mask of one 32-pair word (LBAudioDetectiveFingerprint.m:155-169):
  * pairs where fp1 has a bit set (P1|M1) and both bits agree with fp2. */
 LBAD_HD uint32_t hit_word(uint32_t p1, uint32_t m1, uint32_t p2, uint32_t m2) {
