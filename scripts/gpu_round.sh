@@ -8,6 +8,6 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/b
 timeout 600 python bench.py --steps 5 --warmup 3 --microbench > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 cat gpurun_out/bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/bench_under_ncu.log 2>&1; echo "launch list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"bands_fused|haar_select32" -s 2 -c 2 -f -o gpurun_out/prof_extract python scripts/prof_run.py --what extract --clips 10000 --reps 2 > gpurun_out/ncu_extract.log 2>&1; echo "ncu extract rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:bands_fused -s 1 -c 1 -f -o gpurun_out/prof_extract python scripts/prof_run.py --what extract --clips 10000 --reps 2 > gpurun_out/ncu_extract.log 2>&1; echo "ncu bands rc=$?"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:haar_select32 -s 1 -c 1 -f -o gpurun_out/prof_select python scripts/prof_run.py --what extract --clips 10000 --reps 2 > gpurun_out/ncu_extract.log 2>&1; echo "ncu extract rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:search_fast -s 1 -c 1 -f -o gpurun_out/prof_search python scripts/prof_run.py --what search --db-clips 1000000 > gpurun_out/ncu_search.log 2>&1; echo "ncu search rc=$?"
 ls -la gpurun_out
