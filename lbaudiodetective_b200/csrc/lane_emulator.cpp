@@ -44,12 +44,47 @@ static void emulate_windows(const float* pcm, int hop, const uint32_t* klow, con
             zz[p + 1] = make_float2(zz[p + 1].x * w[2] - zz[p + 1].y * w[3], zz[p + 1].x * w[3] + zz[p + 1].y * w[2]);
         }
     }
+    static float zx[32][32], zy[32][32];            /* [lane][position]: the transposed components, as the kernel's 128-bit loads deliver them */
     for (int comp = 0; comp < 2; comp++) {          /* one component at a time, as in the kernel */
         for (int lane = 0; lane < 32; lane++) for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = comp ? z[lane][p].y : z[lane][p].x;
-        for (int lane = 0; lane < 32; lane++) for (int q = 0; q < 8; q++) for (int j = 0; j < 4; j++) (comp ? z[lane][4 * q + j].y : z[lane][4 * q + j].x) = scr[lane * SCR_LDF + 4 * q + j];
+        for (int lane = 0; lane < 32; lane++) for (int q = 0; q < 8; q++) for (int j = 0; j < 4; j++) (comp ? zy[lane][4 * q + j] : zx[lane][4 * q + j]) = scr[lane * SCR_LDF + 4 * q + j];
     }
-    for (int lane = 0; lane < 32; lane++) fft32_tail<R>(z[lane]);
+    for (int lane = 0; lane < 32; lane++) fft32_tail_soa<R>(zx[lane], zy[lane], z[lane]);
     const int k2lo = (int)(kmin >> 5), k2hi = (int)((kmax - 1) >> 5);
+    if constexpr (R == 32) {                        /* mirrored rows share one evaluation of the real split (see the kernel) */
+        auto row_needed = [&](int r) -> bool { return r >= k2lo && r <= k2hi; };
+        auto spec_out = [&](int k, float xr, float xi) { if (out_spec) { out_spec[2 * k] = xr; out_spec[2 * k + 1] = xi; } };
+        for (int lane = 0; lane < 32; lane++) {
+            const int src_lane = (32 - lane) & 31;
+            for (int k2 = 0; k2 < 16; k2++) {
+                const bool need_lo = row_needed(k2), need_hi = row_needed(31 - k2) || (k2 > 0 && row_needed(32 - k2));
+                if (need_lo || need_hi) {
+                    const float* w = tw2[(k2 >> 1) * 32 + lane];
+                    const float c = (k2 & 1) ? w[2] : w[0], sn = (k2 & 1) ? w[3] : w[1];
+                    const int p = bitrev5(k2), pp = bitrev5(31 - k2), p0 = bitrev5((32 - k2) % 32);
+                    float2 pz = z[src_lane][pp];                             /* __shfl_sync */
+                    if (lane == 0) pz = z[lane][p0];
+                    const int k = k2 * 32 + lane;
+                    if (need_hi) {
+                        float2 lo, hi;
+                        real_split_pair_2x(z[lane][p], pz, c, sn, lo, hi);
+                        if (k2 == 0 && lane == 0) { lo.x = 2.0f * (z[lane][p].x + z[lane][p].y); lo.y = 2.0f * (z[lane][p].x - z[lane][p].y); }
+                        if (need_lo) { vbuf[k] = bin_energy_raw(lo.x, lo.y, scale_m1); spec_out(k, lo.x, lo.y); }
+                        if (k2 > 0 || lane > 0) { vbuf[1024 - k] = bin_energy_raw_conj(hi.x, hi.y, scale_m1); spec_out(1024 - k, hi.x, -hi.y); }
+                    } else {
+                        float xr, xi;
+                        real_split_2x(z[lane][p], pz, c, sn, xr, xi);
+                        if (k2 == 0 && lane == 0) { xr = 2.0f * (z[lane][p].x + z[lane][p].y); xi = 2.0f * (z[lane][p].x - z[lane][p].y); }
+                        vbuf[k] = bin_energy_raw(xr, xi, scale_m1); spec_out(k, xr, xi);
+                    }
+                }
+            }
+            if (row_needed(16) && lane == 0) {
+                const float xr = 2.0f * z[lane][bitrev5(16)].x, xi = -2.0f * z[lane][bitrev5(16)].y;
+                vbuf[512] = bin_energy_raw(xr, xi, scale_m1); spec_out(512, xr, xi);
+            }
+        }
+    } else
     for (int lane = 0; lane < 32; lane++) {
         const int src_lane = (32 - lane) & 31;
         for (int k2 = 0; k2 < R; k2 += 2) {

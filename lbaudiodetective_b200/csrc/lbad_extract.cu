@@ -384,14 +384,15 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                 z[p] = make_float2(z[p].x * w.x - z[p].y * w.y, z[p].x * w.y + z[p].y * w.x);
                 z[p + 1] = make_float2(z[p + 1].x * w.z - z[p + 1].y * w.w, z[p + 1].x * w.w + z[p + 1].y * w.z);
             }
-            /* 32x32 transpose through shared memory, one component at a time: lane k1 ends up with A_s[n2][k1] in register s R + n2 */
+            /* 32x32 transpose through shared memory, one component at a time: lane k1 ends up with A_s[n2][k1] at position s R + n2 */
+            float zx[32], zy[32];
 #pragma unroll
             for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = z[p].x;
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const float4 t = *reinterpret_cast<const float4*>(&scr[lane * SCR_LDF + 4 * q]);
-                z[4 * q].x = t.x; z[4 * q + 1].x = t.y; z[4 * q + 2].x = t.z; z[4 * q + 3].x = t.w;
+                zx[4 * q] = t.x; zx[4 * q + 1] = t.y; zx[4 * q + 2] = t.z; zx[4 * q + 3] = t.w;
             }
             __syncwarp();
 #pragma unroll
@@ -400,29 +401,63 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const float4 t = *reinterpret_cast<const float4*>(&scr[lane * SCR_LDF + 4 * q]);
-                z[4 * q].y = t.x; z[4 * q + 1].y = t.y; z[4 * q + 2].y = t.z; z[4 * q + 3].y = t.w;
+                zy[4 * q] = t.x; zy[4 * q + 1] = t.y; zy[4 * q + 2] = t.z; zy[4 * q + 3] = t.w;
             }
-            fft32_tail<R>(z);                                                   /* over n2, per window; position s R + q holds Z_s[lane + 32 bitrevR(q)] */
+            fft32_tail_soa<R>(zx, zy, z);                                       /* over n2, per window; position s R + q holds Z_s[lane + 32 bitrevR(q)] */
             __syncwarp();                                                       /* scratch is about to be reused as vbuf */
             const int src_lane = (32 - lane) & 31;
+            if constexpr (R == 32) {
+                /* rows k2 and 31 - k2 are mirror images (bin k of lane l <-> bin 1024 - k of lane 32 - l): one evaluation of the
+                 * real split yields both, and the lane that did it stores both energies.  Lane 0 is its own mirror one row up
+                 * (k = 32 k2 <-> 32 (32 - k2)), so its row 16 (bin 512, self-mirrored) is done separately below. */
+                auto row_needed = [&](int r) -> bool { return STATIC_RANGE ? (r >= 2 && r <= 23) : (r >= k2lo && r <= k2hi); };
 #pragma unroll
-            for (int k2 = 0; k2 < R; k2 += 2) {
-                if ((STATIC_RANGE && k2 >= 2 && k2 <= 23) || (!STATIC_RANGE && k2 + 1 >= k2lo && k2 <= k2hi)) {   /* warp-uniform */
-                    const float4 w = tw2[(k2 >> 1) * 32 + lane];                /* (cos, sin) of 2 pi k / N for k2 and k2+1 */
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int kk = k2 + h;
-#pragma unroll
-                        for (int s = 0; s < S; s++) {
-                            const int p = s * R + bitrevR<R>(kk), pp = s * R + bitrevR<R>(R - 1 - kk), p0 = s * R + bitrevR<R>((R - kk) % R);
-                            float2 pz;                                          /* Z[M - k] lives in lane 32-lane, k2' = R-1-k2 */
-                            pz.x = __shfl_sync(0xffffffffu, z[pp].x, src_lane);
-                            pz.y = __shfl_sync(0xffffffffu, z[pp].y, src_lane);
-                            if (lane == 0) pz = z[p0];                          /* ... except lane 0: own register k2' = R-k2 */
+                for (int k2 = 0; k2 < 16; k2++) {
+                    const bool need_lo = row_needed(k2), need_hi = row_needed(31 - k2) || (k2 > 0 && row_needed(32 - k2));   /* warp-uniform */
+                    if (need_lo || need_hi) {
+                        const float4 w = tw2[(k2 >> 1) * 32 + lane];            /* (cos, sin) of 2 pi k / N for rows k2 & ~1 and k2 | 1 */
+                        const float c = (k2 & 1) ? w.z : w.x, sn = (k2 & 1) ? w.w : w.y;
+                        const int p = bitrev5(k2), pp = bitrev5(31 - k2), p0 = bitrev5((32 - k2) % 32);
+                        float2 pz;                                              /* Z[1024 - k] lives in lane 32 - lane, row 31 - k2 */
+                        pz.x = __shfl_sync(0xffffffffu, z[pp].x, src_lane);
+                        pz.y = __shfl_sync(0xffffffffu, z[pp].y, src_lane);
+                        if (lane == 0) pz = z[p0];                              /* ... except lane 0: own register, row 32 - k2 */
+                        const int k = k2 * 32 + lane;
+                        if (need_hi) {
+                            float2 lo, hi;
+                            real_split_pair_2x(z[p], pz, c, sn, lo, hi);
+                            if (k2 == 0 && lane == 0) { lo.x = 2.0f * (z[p].x + z[p].y); lo.y = 2.0f * (z[p].x - z[p].y); }       /* DC / packed Nyquist */
+                            if (need_lo) vbuf[k] = bin_energy_raw(lo.x, lo.y, scale_m1);                                     /* finiteness is checked on the band sum */
+                            if (k2 > 0 || lane > 0) vbuf[1024 - k] = bin_energy_raw_conj(hi.x, hi.y, scale_m1);
+                        } else {
                             float xr, xi;
-                            real_split_2x(z[p], pz, h ? w.z : w.x, h ? w.w : w.y, xr, xi);
-                            if (kk == 0 && lane == 0) { xr = 2.0f * (z[p].x + z[p].y); xi = 2.0f * (z[p].x - z[p].y); }   /* DC / packed Nyquist */
-                            vbuf[s * M + kk * 32 + lane] = bin_energy_raw(xr, xi, scale_m1);      /* finiteness is checked on the band sum */
+                            real_split_2x(z[p], pz, c, sn, xr, xi);
+                            if (k2 == 0 && lane == 0) { xr = 2.0f * (z[p].x + z[p].y); xi = 2.0f * (z[p].x - z[p].y); }
+                            vbuf[k] = bin_energy_raw(xr, xi, scale_m1);
+                        }
+                    }
+                }
+                if (row_needed(16) && lane == 0) vbuf[512] = bin_energy_raw(2.0f * z[bitrev5(16)].x, -2.0f * z[bitrev5(16)].y, scale_m1);   /* w = -i, partner = itself */
+            } else {
+    #pragma unroll
+                for (int k2 = 0; k2 < R; k2 += 2) {
+                    if ((STATIC_RANGE && k2 >= 2 && k2 <= 23) || (!STATIC_RANGE && k2 + 1 >= k2lo && k2 <= k2hi)) {   /* warp-uniform */
+                        const float4 w = tw2[(k2 >> 1) * 32 + lane];                /* (cos, sin) of 2 pi k / N for k2 and k2+1 */
+    #pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int kk = k2 + h;
+    #pragma unroll
+                            for (int s = 0; s < S; s++) {
+                                const int p = s * R + bitrevR<R>(kk), pp = s * R + bitrevR<R>(R - 1 - kk), p0 = s * R + bitrevR<R>((R - kk) % R);
+                                float2 pz;                                          /* Z[M - k] lives in lane 32-lane, k2' = R-1-k2 */
+                                pz.x = __shfl_sync(0xffffffffu, z[pp].x, src_lane);
+                                pz.y = __shfl_sync(0xffffffffu, z[pp].y, src_lane);
+                                if (lane == 0) pz = z[p0];                          /* ... except lane 0: own register k2' = R-k2 */
+                                float xr, xi;
+                                real_split_2x(z[p], pz, h ? w.z : w.x, h ? w.w : w.y, xr, xi);
+                                if (kk == 0 && lane == 0) { xr = 2.0f * (z[p].x + z[p].y); xi = 2.0f * (z[p].x - z[p].y); }   /* DC / packed Nyquist */
+                                vbuf[s * M + kk * 32 + lane] = bin_energy_raw(xr, xi, scale_m1);      /* finiteness is checked on the band sum */
+                            }
                         }
                     }
                 }

@@ -37,14 +37,6 @@ LBAD_HD constexpr int bitrev5(int p) {
     return ((p & 1) << 4) | ((p & 2) << 2) | (p & 4) | ((p & 8) >> 2) | ((p & 16) >> 4);
 }
 
-/* cos / sin of 2*pi*m/32 for m in [0, 16) */
-LBAD_HD constexpr float cos32(int m) {
-    return m == 0 ? 1.0f : m == 1 ? 0.98078528040323043f : m == 2 ? 0.92387953251128674f : m == 3 ? 0.83146961230254524f
-         : m == 4 ? 0.70710678118654752f : m == 5 ? 0.55557023301960218f : m == 6 ? 0.38268343236508977f : m == 7 ? 0.19509032201612825f
-         : m == 8 ? 0.0f : -cos32(16 - m);
-}
-LBAD_HD constexpr float sin32(int m) { return m <= 8 ? cos32(8 - m) : cos32(m - 8); }
-
 #if !defined(__CUDACC__)
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
@@ -68,51 +60,93 @@ LBAD_HD float2 fma2(float2 a, float2 b, float2 c) {
 #endif
 }
 
-/* one radix-2 DIF butterfly of a 32-point transform: half-span H, block start S, offset J within the half-block.
- * z[] holds (re, im) pairs; the sum (and the difference when its twiddle is 1) is one packed instruction. */
-template <int H, int S, int J>
-LBAD_HD void fft32_butterfly(float2 (&z)[32], const float2 neg1) {
-    constexpr int a = S + J, b = S + J + H;
-    constexpr int m = J * (16 / H);              /* twiddle exp(-2 pi i m / 32), 0 <= m < 16 */
-    constexpr float kS2 = 0.70710678118654752f;
-    const float2 za = z[a], zb = z[b];
-    z[a] = add2(za, zb);
-    if constexpr (m == 0) { z[b] = fma2(zb, neg1, za); }                                    /* za - zb, exactly */
-    else {
-        const float dr = za.x - zb.x, di = za.y - zb.y;
-        if constexpr (m == 8)       { z[b] = make_float2(di, -dr); }                                         /* x (-i) */
-        else if constexpr (m == 4)  { z[b] = make_float2((dr + di) * kS2, (di - dr) * kS2); }                /* x (1-i)/sqrt2 */
-        else if constexpr (m == 12) { z[b] = make_float2((di - dr) * kS2, (dr + di) * (-kS2)); }             /* x (-1-i)/sqrt2 */
-        else {
-            constexpr float c = cos32(m), s = sin32(m);                                                      /* x (c - i s) */
-            z[b] = make_float2(dr * c + di * s, di * c - dr * s);
-        }
+/* cos(2 pi m / 32), m = 0..8, to double precision; the remaining angles follow by symmetry */
+LBAD_HD constexpr double cos32d(int m) {
+    return m == 0 ? 1.0 : m == 1 ? 0.98078528040323044913 : m == 2 ? 0.92387953251128675613 : m == 3 ? 0.83146961230254523708
+         : m == 4 ? 0.70710678118654752440 : m == 5 ? 0.55557023301960222474 : m == 6 ? 0.38268343236508977173 : m == 7 ? 0.19509032201612826785
+         : m == 8 ? 0.0 : -cos32d(16 - m);
+}
+LBAD_HD constexpr double sin32d(int m) { return m <= 8 ? cos32d(8 - m) : cos32d(m - 8); }
+
+/* One radix-2 decimation-in-time butterfly, twiddle first: (A, B) <- (A + w B, A - w B), w = exp(-2 pi i M / 32), 0 <= M < 16.
+ * z[] holds (re, im) pairs.  The general twiddle is applied in the Linzer-Feig form: with w = c - i s and t = s / c,
+ * w B = c (B.x + t B.y, B.y - t B.x), so the product costs two FMAs and its scale c rides on the two packed FMAs that
+ * form A +- (...) — six FMA-pipe slots per butterfly instead of eight.  Where |s| > |c| the same is done with s factored
+ * out (cotangent form), so the stored ratio never exceeds 1 in magnitude.  The scale is a literal: FFMA2 takes it as a
+ * broadcast immediate. */
+template <int M, int PA, int PB>
+LBAD_HD void dit_butterfly(float2 (&z)[32]) {
+    const float2 A = z[PA], B = z[PB];
+    if constexpr (M == 0) {
+        z[PA] = add2(A, B);
+        z[PB] = fma2(B, make_float2(-1.0f, -1.0f), A);
+    } else if constexpr (M == 8) {                                  /* w = -i: w B = (B.y, -B.x) */
+        z[PA] = make_float2(A.x + B.y, A.y - B.x);
+        z[PB] = make_float2(A.x - B.y, A.y + B.x);
+    } else {
+        constexpr double c = cos32d(M), s = sin32d(M);
+        constexpr bool tan_form = (c < 0 ? -c : c) >= (s < 0 ? -s : s);
+        constexpr float scale = (float)(tan_form ? c : s);
+        float2 u;
+        if constexpr (M == 4) u = make_float2(B.x + B.y, B.y - B.x);                  /* t = 1 */
+        else if constexpr (M == 12) u = make_float2(B.x - B.y, B.y + B.x);            /* t = -1 */
+        else if constexpr (tan_form) { constexpr float t = (float)(s / c); u = make_float2(fmaf(t, B.y, B.x), fmaf(-t, B.x, B.y)); }
+        else                         { constexpr float t = (float)(c / s); u = make_float2(fmaf(t, B.x, B.y), fmaf(t, B.y, -B.x)); }
+        z[PA] = fma2(u, make_float2(scale, scale), A);
+        z[PB] = fma2(u, make_float2(-scale, -scale), A);
     }
 }
-
-template <int H, int... I>
-LBAD_HD void fft32_stage(float2 (&z)[32], const float2 neg1, std::integer_sequence<int, I...>) {
-    (fft32_butterfly<H, (I / H) * 2 * H, I % H>(z, neg1), ...);
-}
-
-/* The last log2(R) stages of the 32-point DIF network: 32/R independent forward R-point DFTs, one on every aligned block of R
- * register positions (R = 32: the whole 32-point DFT).  Inside a block, position q holds output index bitrev over log2(R) bits. */
-template <int R>
-LBAD_HD void fft32_tail(float2 (&z)[32]) {
-    const float2 neg1 = make_float2(-1.0f, -1.0f);
-    using seq = std::make_integer_sequence<int, 16>;
-    if constexpr (R >= 32) fft32_stage<16>(z, neg1, seq{});
-    if constexpr (R >= 16) fft32_stage<8>(z, neg1, seq{});
-    if constexpr (R >= 8) fft32_stage<4>(z, neg1, seq{});
-    if constexpr (R >= 4) fft32_stage<2>(z, neg1, seq{});
-    if constexpr (R >= 2) fft32_stage<1>(z, neg1, seq{});
-}
-/* in-place forward 32-point DFT (e^{-i theta}); output index of register position p is bitrev5(p) */
-LBAD_HD void fft32(float2 (&z)[32]) { fft32_tail<32>(z); }
 
 LBAD_HD constexpr int log2c(int v) { return v <= 1 ? 0 : 1 + log2c(v >> 1); }
 /* bit reversal over log2(R) bits */
 template <int R> LBAD_HD constexpr int bitrevR(int q) { return bitrev5(q) >> (5 - log2c(R)); }
+
+/* stage with logical half-span HALF of the R-point transforms living on the aligned blocks of R register positions:
+ * logical index i of a block sits at position bitrevR(i), so the input is read in natural order and output k ends up at bitrevR(k) */
+template <int R, int HALF, int... I>
+LBAD_HD void dit_stage(float2 (&z)[32], std::integer_sequence<int, I...>) {
+    /* butterfly I of the 16 in this stage: block of R positions (I / (R/2)), within it logical pair (a, a + HALF) */
+    (dit_butterfly<((I % (R / 2)) % HALF) * (16 / HALF),
+                   (I / (R / 2)) * R + bitrevR<R>(((I % (R / 2)) / HALF) * 2 * HALF + (I % (R / 2)) % HALF),
+                   (I / (R / 2)) * R + bitrevR<R>(((I % (R / 2)) / HALF) * 2 * HALF + (I % (R / 2)) % HALF + HALF)>(z), ...);
+}
+
+/* 32/R independent forward R-point DFTs (e^{-i theta}), one on every aligned block of R register positions (R = 32: one 32-point
+ * DFT).  Inside a block the input is in natural order and position q ends up holding output index bitrevR(q). */
+template <int R>
+LBAD_HD void fft32_tail(float2 (&z)[32]) {
+    using seq = std::make_integer_sequence<int, 16>;
+    if constexpr (R >= 2) dit_stage<R, 1>(z, seq{});
+    if constexpr (R >= 4) dit_stage<R, 2>(z, seq{});
+    if constexpr (R >= 8) dit_stage<R, 4>(z, seq{});
+    if constexpr (R >= 16) dit_stage<R, 8>(z, seq{});
+    if constexpr (R >= 32) dit_stage<R, 16>(z, seq{});
+}
+/* The same transforms with the input given as separate real and imaginary arrays (what the component-wise shared-memory
+ * transposition delivers, four consecutive positions per 128-bit load): the first stage, whose twiddles are all 1, is done in
+ * scalar adds that write the (re, im) register pairs directly, so no moves are needed to assemble pairs for the packed stages. */
+template <int R, int... I>
+LBAD_HD void dit_first_stage_soa(const float (&zx)[32], const float (&zy)[32], float2 (&z)[32], std::integer_sequence<int, I...>) {
+    ((z[(I / (R / 2)) * R + bitrevR<R>(2 * (I % (R / 2)))] =
+          make_float2(zx[(I / (R / 2)) * R + bitrevR<R>(2 * (I % (R / 2)))] + zx[(I / (R / 2)) * R + bitrevR<R>(2 * (I % (R / 2)) + 1)],
+                      zy[(I / (R / 2)) * R + bitrevR<R>(2 * (I % (R / 2)))] + zy[(I / (R / 2)) * R + bitrevR<R>(2 * (I % (R / 2)) + 1)]),
+      z[(I / (R / 2)) * R + bitrevR<R>(2 * (I % (R / 2)) + 1)] =
+          make_float2(zx[(I / (R / 2)) * R + bitrevR<R>(2 * (I % (R / 2)))] - zx[(I / (R / 2)) * R + bitrevR<R>(2 * (I % (R / 2)) + 1)],
+                      zy[(I / (R / 2)) * R + bitrevR<R>(2 * (I % (R / 2)))] - zy[(I / (R / 2)) * R + bitrevR<R>(2 * (I % (R / 2)) + 1)])), ...);
+}
+template <int R>
+LBAD_HD void fft32_tail_soa(const float (&zx)[32], const float (&zy)[32], float2 (&z)[32]) {
+    using seq = std::make_integer_sequence<int, 16>;
+    static_assert(R >= 2, "at least one stage");
+    dit_first_stage_soa<R>(zx, zy, z, seq{});
+    if constexpr (R >= 4) dit_stage<R, 2>(z, seq{});
+    if constexpr (R >= 8) dit_stage<R, 4>(z, seq{});
+    if constexpr (R >= 16) dit_stage<R, 8>(z, seq{});
+    if constexpr (R >= 32) dit_stage<R, 16>(z, seq{});
+}
+/* in-place forward 32-point DFT (e^{-i theta}); output index of register position p is bitrev5(p) */
+LBAD_HD void fft32(float2 (&z)[32]) { fft32_tail<32>(z); }
+
 
 /* 2 X[k] from Z[k] = z and Z[M-k] = p, with w = exp(-2 pi i k / N) = (c, -s) given as c, s */
 LBAD_HD void real_split_2x(float2 z, float2 p, float c, float s, float& xr, float& xi) {
@@ -120,6 +154,19 @@ LBAD_HD void real_split_2x(float2 z, float2 p, float c, float s, float& xr, floa
     const float2 d = fma2(p, make_float2(-1.0f, 1.0f), z);     /* Z - conj Z' */
     xr = fmaf(c, d.y, fmaf(-s, d.x, e.x));                     /* -i w d = (-s dr + c di) + i (-c dr - s di) */
     xi = fmaf(-s, d.y, fmaf(-c, d.x, e.y));
+}
+
+/* Both members of a mirrored pair of bins from one evaluation: with Z[k] = z and Z[M-k] = p (w as above),
+ * lo = 2 X[k] and hi = conj(2 X[M-k]): the sum e = z + conj p and the rotated difference g = -i w (z - conj p) are shared,
+ * 2 X[k] = e + g and 2 X[M-k] = conj(e - g).  g is kept as (Re g, -Im g) so that both results are one packed FMA. */
+LBAD_HD void real_split_pair_2x(float2 z, float2 p, float c, float s, float2& lo, float2& hi) {
+    const float2 e = fma2(p, make_float2(1.0f, -1.0f), z);
+    const float2 d = fma2(p, make_float2(-1.0f, 1.0f), z);
+    float2 g;
+    g.x = fmaf(c, d.y, -(s * d.x));
+    g.y = fmaf(s, d.y, c * d.x);
+    lo = fma2(g, make_float2(1.0f, -1.0f), e);
+    hi = fma2(g, make_float2(-1.0f, 1.0f), e);
 }
 
 /* LBAudioDetective.m:387-401 for one bin: positive parts only are divided by pos_scale, then re^2 + im^2; a
@@ -137,6 +184,13 @@ LBAD_HD float bin_energy(float re, float im, float scale_m1) {
  * exactly when all of its terms are, and only a non-finite sum (never seen on real audio) needs the filtered re-summation. */
 LBAD_HD float bin_energy_raw(float re, float im, float scale_m1) {
     const float2 g = fma2(make_float2(fmaxf(re, 0.0f), fmaxf(im, 0.0f)), make_float2(scale_m1, scale_m1), make_float2(re, im));
+    return fmaf(g.x, g.x, g.y * g.y);
+}
+
+/* bin_energy_raw of the conjugate: the energy of (re, -im) given (re, im) — the positive-part scaling applies to -im, i.e. to
+ * the negative part of im */
+LBAD_HD float bin_energy_raw_conj(float re, float im, float scale_m1) {
+    const float2 g = fma2(make_float2(fmaxf(re, 0.0f), fminf(im, 0.0f)), make_float2(scale_m1, scale_m1), make_float2(re, im));
     return fmaf(g.x, g.x, g.y * g.y);
 }
 
