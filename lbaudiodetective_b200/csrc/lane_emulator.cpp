@@ -26,7 +26,12 @@ static void emulate_windows(const float* pcm, int hop, const uint32_t* klow, con
         }
         for (int k2 = 0; k2 < 32; k2 += 2) for (int l = 0; l < 32; l++) {
             const double a0 = 2.0 * M_PI * (double)(l + 32 * k2) / (double)N, a1 = 2.0 * M_PI * (double)(l + 32 * (k2 + 1)) / (double)N;
-            float* t = tw2[(k2 >> 1) * 32 + l]; t[0] = (float)cos(a0); t[1] = (float)sin(a0); t[2] = (float)cos(a1); t[3] = (float)sin(a1);
+            if (R == 32) {
+                float* t = &tw2[0][0] + 2 * (k2 * 32 + l); t[0] = (float)cos(a0); t[1] = (float)sin(a0);
+                t = &tw2[0][0] + 2 * ((k2 + 1) * 32 + l); t[0] = (float)cos(a1); t[1] = (float)sin(a1);
+            } else {
+                float* t = tw2[(k2 >> 1) * 32 + l]; t[0] = (float)cos(a0); t[1] = (float)sin(a0); t[2] = (float)cos(a1); t[3] = (float)sin(a1);
+            }
         }
     }
     static float2 z[32][32];                        /* [lane][register] */
@@ -35,8 +40,15 @@ static void emulate_windows(const float* pcm, int hop, const uint32_t* klow, con
     for (int lane = 0; lane < 32; lane++) {
         const int my_win = lane / R, n2 = lane % R;
         const float* win = pcm + (size_t)my_win * hop;
-        for (int n1 = 0; n1 < 32; n1++) z[lane][n1] = make_float2(win[2 * (R * n1 + n2)], win[2 * (R * n1 + n2) + 1]);
-        fft32(z[lane]);
+        if constexpr (R == 32) {                    /* the kernel's carried scheme: E = dft16 of the even n1 (odd n1 of the window one hop earlier), O = dft16 of the odd n1 */
+            float2 ev[16], od[16];
+            for (int m = 0; m < 16; m++) { ev[m] = make_float2(win[2 * (32 * (2 * m) + lane)], win[2 * (32 * (2 * m) + lane) + 1]); od[m] = make_float2(win[2 * (32 * (2 * m + 1) + lane)], win[2 * (32 * (2 * m + 1) + lane) + 1]); }
+            dft16(ev); dft16(od);
+            dit32_combine(ev, od, z[lane]);
+        } else {
+            for (int n1 = 0; n1 < 32; n1++) z[lane][n1] = make_float2(win[2 * (R * n1 + n2)], win[2 * (R * n1 + n2) + 1]);
+            fft32(z[lane]);
+        }
         for (int p = 0; p < 32; p += 2) {
             const float* w = tw1[(p >> 1) * 32 + lane];
             float2* zz = z[lane];
@@ -59,8 +71,8 @@ static void emulate_windows(const float* pcm, int hop, const uint32_t* klow, con
             for (int k2 = 0; k2 < 16; k2++) {
                 const bool need_lo = row_needed(k2), need_hi = row_needed(31 - k2) || (k2 > 0 && row_needed(32 - k2));
                 if (need_lo || need_hi) {
-                    const float* w = tw2[(k2 >> 1) * 32 + lane];
-                    const float c = (k2 & 1) ? w[2] : w[0], sn = (k2 & 1) ? w[3] : w[1];
+                    const float* w = &tw2[0][0] + 2 * (k2 * 32 + lane);       /* R == 32: float2 [k2][lane] */
+                    const float c = w[0], sn = w[1];
                     const int p = bitrev5(k2), pp = bitrev5(31 - k2), p0 = bitrev5((32 - k2) % 32);
                     float2 pz = z[src_lane][pp];                             /* __shfl_sync */
                     if (lane == 0) pz = z[lane][p0];

@@ -314,18 +314,19 @@ static FusedSmemLayout fused_layout(uint32_t span_floats) {
 /* R: lanes per window in pass 1 = points of the pass-2 DFT; window = 64 R samples, 32/R windows per warp (see lbad_math.cuh).
  * STATIC_RANGE (R = 32 only): the band table is the reference-default one (bins [86, 759)), so the rows of 32 bins that need
  * the real split are k2 = 2..23 at compile time; otherwise the range is a (warp-uniform) run-time value. */
-template <int R, bool STATIC_RANGE>
+template <int R, bool STATIC_RANGE, bool CARRY>
 __global__ void __launch_bounds__(FUSED_THREADS, 2)
 bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, const float4* __restrict__ g_tw1, const float4* __restrict__ g_tw2,
                    const Geo g, const BandTable bt, const FusedSmemLayout L, const uint32_t span_floats,
                    const uint32_t total_frames, const int use_tma, const uint32_t frame0) {
     static_assert(!STATIC_RANGE || R == 32, "the compile-time band rows belong to the 2048-sample window");
+    static_assert(!CARRY || R == 32, "half transforms are carried between windows only in the one-window-per-warp layout");
     constexpr int S = 32 / R;                                /* windows per warp */
     constexpr int M = 32 * R;                                /* complex points per window = bins of the half spectrum */
     extern __shared__ __align__(128) unsigned char smem[];
     float*  samples = reinterpret_cast<float*>(smem);
     float4* tw1 = reinterpret_cast<float4*>(smem + L.off_tw1);     /* [p/2][lane]: twiddles of register positions p, p+1 */
-    float4* tw2 = reinterpret_cast<float4*>(smem + L.off_tw2);     /* [k2/2][lane]: (cos, sin) of bins lane+32k2, lane+32(k2+1) */
+    float4* tw2 = reinterpret_cast<float4*>(smem + L.off_tw2);     /* R < 32: [k2/2][lane]: (cos, sin) of bins lane+32k2, lane+32(k2+1); R == 32: float2 [k2][lane] */
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     float* scr = reinterpret_cast<float*>(smem + L.off_scratch) + wid * (32 * SCR_LDF);
@@ -370,14 +371,34 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
         }
 
         /* ---- the frame's 128 windows, S at a time per warp, round-robin over the warps: FFT -> bands -> image rows ---- */
+        constexpr int ITERS = (int)LBAD_ROWS_PER_FRAME / (FUSED_WARPS * S);
+        /* CARRY (R == 32 and hop == 64 samples): a warp takes ITERS CONSECUTIVE windows, one hop = one n1 step apart, so the
+         * 16-point transform of a window's odd-n1 inputs is carried over as the even-n1 transform of the next window (dft16 /
+         * dit32_combine in lbad_math.cuh): half the sample loads and 48 instead of 80 butterflies in pass 1. */
+        float2 carry[16];
+        auto half_transform = [&](const float* w, float2 (&h)[16]) {             /* inputs z[32 n1 + lane], n1 = 1, 3, .., 31 of the window at w */
+#pragma unroll
+            for (int m = 0; m < 16; m++) h[m] = *reinterpret_cast<const float2*>(w + 2 * (32 * (2 * m + 1) + lane));
+            dft16(h);
+        };
+        if constexpr (CARRY) half_transform(samples + (size_t)(wid * ITERS) * hop - hop, carry);     /* even n1 of the first window = odd n1 of the one before */
 #pragma unroll 1
-        for (int row0 = wid * S; row0 < (int)LBAD_ROWS_PER_FRAME; row0 += FUSED_WARPS * S) {
+        for (int it = 0; it < ITERS; it++) {
+            const int row0 = CARRY ? wid * ITERS + it : (wid + it * FUSED_WARPS) * S;
             const float* win = samples + (size_t)(row0 + my_win) * hop;
             float2 z[32];
+            if constexpr (CARRY) {
+                float2 odd[16];
+                half_transform(win, odd);
+                dit32_combine(carry, odd, z);                                   /* over n1; position p holds k1 = bitrev5(p) */
 #pragma unroll
-            for (int n1 = 0; n1 < 32; n1++)                                     /* vDSP_ctoz (m:353): z[n] = x[2n] + i x[2n+1], n = R n1 + n2 */
-                z[n1] = *reinterpret_cast<const float2*>(win + 2 * (R * n1 + n2));
-            fft32(z);                                                           /* over n1; position p holds k1 = bitrev5(p) */
+                for (int m = 0; m < 16; m++) carry[m] = odd[m];
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < 32; n1++)                                 /* vDSP_ctoz (m:353): z[n] = x[2n] + i x[2n+1], n = R n1 + n2 */
+                    z[n1] = *reinterpret_cast<const float2*>(win + 2 * (R * n1 + n2));
+                fft32(z);                                                       /* over n1; position p holds k1 = bitrev5(p) */
+            }
 #pragma unroll
             for (int p = 0; p < 32; p += 2) {                                   /* x exp(-2 pi i n2 k1 / M) */
                 const float4 w = tw1[(p >> 1) * 32 + lane];
@@ -415,8 +436,8 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                 for (int k2 = 0; k2 < 16; k2++) {
                     const bool need_lo = row_needed(k2), need_hi = row_needed(31 - k2) || (k2 > 0 && row_needed(32 - k2));   /* warp-uniform */
                     if (need_lo || need_hi) {
-                        const float4 w = tw2[(k2 >> 1) * 32 + lane];            /* (cos, sin) of 2 pi k / N for rows k2 & ~1 and k2 | 1 */
-                        const float c = (k2 & 1) ? w.z : w.x, sn = (k2 & 1) ? w.w : w.y;
+                        const float2 w = reinterpret_cast<const float2*>(tw2)[k2 * 32 + lane];   /* (cos, sin) of 2 pi k / N, k = lane + 32 k2: one conflict-free LDS.64 */
+                        const float c = w.x, sn = w.y;
                         const int p = bitrev5(k2), pp = bitrev5(31 - k2), p0 = bitrev5((32 - k2) % 32);
                         float2 pz;                                              /* Z[1024 - k] lives in lane 32 - lane, row 31 - k2 */
                         pz.x = __shfl_sync(0xffffffffu, z[pp].x, src_lane);
@@ -792,7 +813,10 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     }
     for (int k2 = 0; k2 < 32; k2 += 2) for (int l = 0; l < 32; l++) {            /* real-split twiddles for bins l+32k2 and l+32(k2+1) (rows k2 < R are used) */
         const double a0 = 2.0 * M_PI * (double)(l + 32 * k2) / (double)N, a1 = 2.0 * M_PI * (double)(l + 32 * (k2 + 1)) / (double)N;
-        tw2[(k2 >> 1) * 32 + l] = make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
+        if (Rr == 32) {                                                           /* one (cos, sin) per row and lane, read as 64-bit words */
+            float2* t2 = reinterpret_cast<float2*>(tw2.data());
+            t2[k2 * 32 + l] = make_float2((float)cos(a0), (float)sin(a0)); t2[(k2 + 1) * 32 + l] = make_float2((float)cos(a1), (float)sin(a1));
+        } else tw2[(k2 >> 1) * 32 + l] = make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
     }
     LBAD_CUDA_TRY(cudaMalloc(&p->d_tw_m, sizeof(float2) * (M / 2))); LBAD_CUDA_TRY(cudaMalloc(&p->d_tw_n, sizeof(float2) * M));
     LBAD_CUDA_TRY(cudaMalloc(&p->d_tw1, sizeof(float4) * 512)); LBAD_CUDA_TRY(cudaMalloc(&p->d_tw2, sizeof(float4) * 512));
@@ -889,8 +913,10 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
         /* TMA bulk copies need 16-byte aligned sources and sizes */
         bool tma_ok = ((uintptr_t)d_pcm % 16 == 0) && (clip_stride % 4 == 0) && (g.stride % 4 == 0);
         if (p->stage_mode == 0) tma_ok = false;
-        auto kern = p->static_range ? bands_fused_kernel<32, true> : g.window == 2048 ? bands_fused_kernel<32, false> : g.window == 1024 ? bands_fused_kernel<16, false>
-                  : g.window == 512 ? bands_fused_kernel<8, false> : bands_fused_kernel<4, false>;
+        const bool carry = g.window == 2048 && g.stride == 64;           /* consecutive windows one pass-1 input apart: half transforms are shared */
+        auto kern = carry ? (p->static_range ? bands_fused_kernel<32, true, true> : bands_fused_kernel<32, false, true>)
+                  : g.window == 2048 ? bands_fused_kernel<32, false, false> : g.window == 1024 ? bands_fused_kernel<16, false, false>
+                  : g.window == 512 ? bands_fused_kernel<8, false, false> : bands_fused_kernel<4, false, false>;
         LBAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes));
         int per_sm = 0;
         LBAD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, L.total_bytes));

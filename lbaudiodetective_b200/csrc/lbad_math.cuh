@@ -74,15 +74,14 @@ LBAD_HD constexpr double sin32d(int m) { return m <= 8 ? cos32d(8 - m) : cos32d(
  * form A +- (...) — six FMA-pipe slots per butterfly instead of eight.  Where |s| > |c| the same is done with s factored
  * out (cotangent form), so the stored ratio never exceeds 1 in magnitude.  The scale is a literal: FFMA2 takes it as a
  * broadcast immediate. */
-template <int M, int PA, int PB>
-LBAD_HD void dit_butterfly(float2 (&z)[32]) {
-    const float2 A = z[PA], B = z[PB];
+template <int M>
+LBAD_HD void dit_bfly(const float2 A, const float2 B, float2& X, float2& Y) {
     if constexpr (M == 0) {
-        z[PA] = add2(A, B);
-        z[PB] = fma2(B, make_float2(-1.0f, -1.0f), A);
+        X = add2(A, B);
+        Y = fma2(B, make_float2(-1.0f, -1.0f), A);
     } else if constexpr (M == 8) {                                  /* w = -i: w B = (B.y, -B.x) */
-        z[PA] = make_float2(A.x + B.y, A.y - B.x);
-        z[PB] = make_float2(A.x - B.y, A.y + B.x);
+        X = make_float2(A.x + B.y, A.y - B.x);
+        Y = make_float2(A.x - B.y, A.y + B.x);
     } else {
         constexpr double c = cos32d(M), s = sin32d(M);
         constexpr bool tan_form = (c < 0 ? -c : c) >= (s < 0 ? -s : s);
@@ -92,10 +91,12 @@ LBAD_HD void dit_butterfly(float2 (&z)[32]) {
         else if constexpr (M == 12) u = make_float2(B.x - B.y, B.y + B.x);            /* t = -1 */
         else if constexpr (tan_form) { constexpr float t = (float)(s / c); u = make_float2(fmaf(t, B.y, B.x), fmaf(-t, B.x, B.y)); }
         else                         { constexpr float t = (float)(c / s); u = make_float2(fmaf(t, B.x, B.y), fmaf(t, B.y, -B.x)); }
-        z[PA] = fma2(u, make_float2(scale, scale), A);
-        z[PB] = fma2(u, make_float2(-scale, -scale), A);
+        X = fma2(u, make_float2(scale, scale), A);
+        Y = fma2(u, make_float2(-scale, -scale), A);
     }
 }
+template <int M, int PA, int PB>
+LBAD_HD void dit_butterfly(float2 (&z)[32]) { dit_bfly<M>(z[PA], z[PB], z[PA], z[PB]); }
 
 LBAD_HD constexpr int log2c(int v) { return v <= 1 ? 0 : 1 + log2c(v >> 1); }
 /* bit reversal over log2(R) bits */
@@ -122,6 +123,29 @@ LBAD_HD void fft32_tail(float2 (&z)[32]) {
     if constexpr (R >= 16) dit_stage<R, 8>(z, seq{});
     if constexpr (R >= 32) dit_stage<R, 16>(z, seq{});
 }
+/* The 32-point transform of a hop-N/32 sliding window in two halves.  The decimation-in-time split X[k] = E[k] + W^k O[k],
+ * X[k+16] = E[k] - W^k O[k] has E = DFT16 of the even-indexed inputs and O = DFT16 of the odd-indexed ones; when consecutive
+ * windows are one input apart, the odd inputs of window w ARE the even inputs of window w + 1, so O of one window is carried
+ * over as E of the next (same values, same arithmetic — nothing is approximated) and each window costs one 16-point transform
+ * plus the combining stage.  dft16: natural order in, output k at position bitrev4(k).  dit32_combine: position q of e / o holds
+ * E / O[bitrev4(q)]; output index k1 lands at position bitrev5(k1) of z, the convention of fft32. */
+template <int HALF, int... I>
+LBAD_HD void dft16_stage(float2 (&h)[16], std::integer_sequence<int, I...>) {
+    (dit_bfly<(I % HALF) * (16 / HALF)>(h[bitrevR<16>((I / HALF) * 2 * HALF + I % HALF)], h[bitrevR<16>((I / HALF) * 2 * HALF + I % HALF + HALF)],
+                                        h[bitrevR<16>((I / HALF) * 2 * HALF + I % HALF)], h[bitrevR<16>((I / HALF) * 2 * HALF + I % HALF + HALF)]), ...);
+}
+LBAD_HD void dft16(float2 (&h)[16]) {
+    using seq = std::make_integer_sequence<int, 8>;
+    dft16_stage<1>(h, seq{}); dft16_stage<2>(h, seq{}); dft16_stage<4>(h, seq{}); dft16_stage<8>(h, seq{});
+}
+template <int... Q>
+LBAD_HD void dit32_combine_impl(const float2 (&e)[16], const float2 (&o)[16], float2 (&z)[32], std::integer_sequence<int, Q...>) {
+    (dit_bfly<bitrevR<16>(Q)>(e[Q], o[Q], z[2 * Q], z[2 * Q + 1]), ...);
+}
+LBAD_HD void dit32_combine(const float2 (&e)[16], const float2 (&o)[16], float2 (&z)[32]) {
+    dit32_combine_impl(e, o, z, std::make_integer_sequence<int, 16>{});
+}
+
 /* The same transforms with the input given as separate real and imaginary arrays (what the component-wise shared-memory
  * transposition delivers, four consecutive positions per 128-bit load): the first stage, whose twiddles are all 1, is done in
  * scalar adds that write the (re, im) register pairs directly, so no moves are needed to assemble pairs for the packed stages. */

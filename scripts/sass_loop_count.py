@@ -15,17 +15,19 @@ for line in txt.splitlines():
 for name, ins in funcs.items():
     if pat not in name:
         continue
-    best = None
+    loops = []
     for addr, text in ins:
         m = re.search(r"\bBRA\b.*?(0x[0-9a-f]+)", text)
         if m:
             tgt = int(m.group(1), 16)
-            if tgt <= addr and (best is None or addr - tgt > best[1] - best[0]):
-                best = (tgt, addr)
-    print("== %s: %d instructions, largest loop [%#x, %#x]" % (name, len(ins), best[0], best[1]))
-    body = [t for a, t in ins if best[0] <= a <= best[1]]
-    ops = collections.Counter()
-    for t in body:
-        m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_]+)", t); ops[m.group(2) if m else "?"] += 1
-    print("   loop body: %d instructions" % len(body))
-    print("   " + ", ".join("%s %d" % kv for kv in ops.most_common(20)))
+            if tgt <= addr:
+                loops.append((tgt, addr))
+    loops.sort(key=lambda l: l[0] - l[1])
+    print("== %s: %d instructions" % (name, len(ins)))
+    for lo, hi in loops[:3]:                      # the three largest loops (outer frame loop, window loop, ...)
+        body = [t for a, t in ins if lo <= a <= hi]
+        ops = collections.Counter()
+        for t in body:
+            m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_]+)", t); ops[m.group(2) if m else "?"] += 1
+        print("   loop [%#x, %#x]: %d instructions" % (lo, hi, len(body)))
+        print("      " + ", ".join("%s %d" % kv for kv in ops.most_common(20)))
