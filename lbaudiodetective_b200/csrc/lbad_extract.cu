@@ -520,96 +520,151 @@ constexpr int HS32_LDT = 132;                /* column-major image, imgT[col * 1
 
 /* x / c for a compile-time constant c with r = RN(1/c): multiply + two FMAs give the IEEE quotient for every finite x with
  * |x| >= 2^-100 or x == 0 (exhaustively checked on the host for c = sqrtf(2), sqrtf(32), sqrtf(128)); the rare rest divides. */
+constexpr uint32_t DIVC_LO = 0x0d802b1eu, DIVC_HI = 0x7cf0bdc2u;          /* bit patterns of 7.9e-31f and 1.0e37f */
 __device__ __forceinline__ float div_const(const float x, const float c, const float r) {
     const float q0 = __fmul_rn(x, r);
     const float q = fmaf(fmaf(-q0, c, x), r, q0);
     const float ax = fabsf(x);
     return ((ax >= 7.9e-31f && ax <= 1.0e37f) || ax == 0.0f) ? q : __fdiv_rn(x, c);
 }
+/* The range of the dividends seen so far, kept as integers: lo = min(|x| bits - 1) (so that zero never counts as small),
+ * hi = max(|x| bits).  FAST mode divides by the short form unconditionally and only records the range; the caller checks it once
+ * per image (block-wide) and redoes the image with the checked form if anything fell outside — which real spectra never do. */
+struct DivRange { uint32_t lo = 0xffffffffu, hi = 0u; __device__ __forceinline__ bool bad() const { return lo < DIVC_LO - 1u || hi > DIVC_HI; } };
+template <bool FAST>
+__device__ __forceinline__ float div_c(const float x, const float c, const float r, DivRange& rg) {
+    if constexpr (!FAST) return div_const(x, c, r);
+    else {
+        const float q0 = __fmul_rn(x, r);
+        const uint32_t u = __float_as_uint(x) & 0x7fffffffu;
+        rg.lo = min(rg.lo, u - 1u); rg.hi = max(rg.hi, u);
+        return fmaf(fmaf(-q0, c, x), r, q0);
+    }
+}
 
 /* four levels of the ordered Haar pyramid (Frame.m:143-152) on 16 consecutive elements held in registers:
  * d1[i] = level-1 difference of pair i (8), d2 (4), d3 (2), d4 (1) and the remaining sum s4 */
+template <bool FAST>
 __device__ __forceinline__ void haar16(const float (&x)[16], float (&d1)[8], float (&d2)[4], float (&d3)[2], float& d4, float& s4,
-                                       const float s2, const float r2) {
+                                       const float s2, const float r2, DivRange& rg) {
     float s1[8], t2[4], t3[2];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { s1[i] = div_const(__fadd_rn(x[2 * i], x[2 * i + 1]), s2, r2); d1[i] = div_const(__fsub_rn(x[2 * i], x[2 * i + 1]), s2, r2); }
+    for (int i = 0; i < 8; i++) { s1[i] = div_c<FAST>(__fadd_rn(x[2 * i], x[2 * i + 1]), s2, r2, rg); d1[i] = div_c<FAST>(__fsub_rn(x[2 * i], x[2 * i + 1]), s2, r2, rg); }
 #pragma unroll
-    for (int i = 0; i < 4; i++) { t2[i] = div_const(__fadd_rn(s1[2 * i], s1[2 * i + 1]), s2, r2); d2[i] = div_const(__fsub_rn(s1[2 * i], s1[2 * i + 1]), s2, r2); }
+    for (int i = 0; i < 4; i++) { t2[i] = div_c<FAST>(__fadd_rn(s1[2 * i], s1[2 * i + 1]), s2, r2, rg); d2[i] = div_c<FAST>(__fsub_rn(s1[2 * i], s1[2 * i + 1]), s2, r2, rg); }
 #pragma unroll
-    for (int i = 0; i < 2; i++) { t3[i] = div_const(__fadd_rn(t2[2 * i], t2[2 * i + 1]), s2, r2); d3[i] = div_const(__fsub_rn(t2[2 * i], t2[2 * i + 1]), s2, r2); }
-    s4 = div_const(__fadd_rn(t3[0], t3[1]), s2, r2);
-    d4 = div_const(__fsub_rn(t3[0], t3[1]), s2, r2);
+    for (int i = 0; i < 2; i++) { t3[i] = div_c<FAST>(__fadd_rn(t2[2 * i], t2[2 * i + 1]), s2, r2, rg); d3[i] = div_c<FAST>(__fsub_rn(t2[2 * i], t2[2 * i + 1]), s2, r2, rg); }
+    s4 = div_c<FAST>(__fadd_rn(t3[0], t3[1]), s2, r2, rg);
+    d4 = div_c<FAST>(__fsub_rn(t3[0], t3[1]), s2, r2, rg);
 }
 
 struct Select32Smem {
     uint32_t hist[HS32_THREADS / 32][256];   /* per-warp histograms of the 8 exponent bits */
     uint32_t warp_tot[HS32_THREADS / 32];
-    uint32_t surv_key[256];
+    __align__(16) uint32_t surv_key[256];
     uint32_t surv_idx[256];                  /* flat index | sign code << 16 (bit 16: v > 0, bit 17: v < 0) */
     uint32_t words[16];
-    uint32_t nsurv, nbucket, threshold, expo, above, n_gt, n_eq, cut;
+    uint32_t nsurv, nbucket, threshold, expo, above, n_gt, n_eq, rank_sum;
     uint32_t steps[16];
 };
 
+/* Rows (length 32, Frame.m:114-116) of one 128 x 32 image into the column-major tile imgT, with the column pass's leading division
+ * by sqrtf(128) (Frame.m:137-139) folded into the store: warp w owns rows 16w..16w+15, two lanes per row, 16 elements each. */
+template <bool FAST>
+__device__ __forceinline__ void haar32_rows(const float* __restrict__ img, float* __restrict__ imgT, DivRange& rg) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float s2 = sqrtf(2.0f), s32 = sqrtf(32.0f), s128 = sqrtf(128.0f);
+    const float r2 = 1.0f / s2, r32 = 1.0f / s32, r128 = 1.0f / s128;
+    const int row = 16 * wid + (lane >> 1), half = lane & 1;
+    const float4* src = reinterpret_cast<const float4*>(img + (size_t)row * 32 + half * 16);
+    float x[16], d1[8], d2[4], d3[2], d4, s4;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const float4 v = __ldg(src + j); x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = div_c<FAST>(x[j], s32, r32, rg);                   /* Frame.m:137-139 */
+    haar16<FAST>(x, d1, d2, d3, d4, s4, s2, r2, rg);
+    const float other = __shfl_xor_sync(0xffffffffu, s4, 1);                                /* level 5 joins the two halves */
+    const float top = half ? div_c<FAST>(__fsub_rn(other, s4), s2, r2, rg) : div_c<FAST>(__fadd_rn(s4, other), s2, r2, rg);
+    float* dst = imgT + row;                                                                /* ordered output positions */
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[(16 + 8 * half + i) * HS32_LDT] = div_c<FAST>(d1[i], s128, r128, rg);
+#pragma unroll
+    for (int i = 0; i < 4; i++) dst[(8 + 4 * half + i) * HS32_LDT] = div_c<FAST>(d2[i], s128, r128, rg);
+#pragma unroll
+    for (int i = 0; i < 2; i++) dst[(4 + 2 * half + i) * HS32_LDT] = div_c<FAST>(d3[i], s128, r128, rg);
+    dst[(2 + half) * HS32_LDT] = div_c<FAST>(d4, s128, r128, rg);
+    dst[half * HS32_LDT] = div_c<FAST>(top, s128, r128, rg);
+}
+
+/* Columns (length 128, Frame.m:118-131): warp w owns columns 4w..4w+3, eight lanes per column, 16 rows each; four levels in
+ * registers and three by shuffles.  The thread keeps its 16 coefficients (coef), whose flat indices are given by haar32_flat_idx. */
+template <bool FAST>
+__device__ __forceinline__ void haar32_cols(const float* __restrict__ imgT, float (&coef)[16], DivRange& rg) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float s2 = sqrtf(2.0f), r2 = 1.0f / s2;
+    const int cl = lane & 3, g = lane >> 2, col = 4 * wid + cl;
+    float x[16], d1[8], d2[4], d3[2], d4, s4;
+    const float4* src = reinterpret_cast<const float4*>(imgT + col * HS32_LDT + 16 * g);
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const float4 v = src[j]; x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
+    haar16<FAST>(x, d1, d2, d3, d4, s4, s2, r2, rg);
+    /* levels 5-7 across the eight lanes of the column: the lane with the lower g keeps the sum, the other the difference */
+    float p = __shfl_xor_sync(0xffffffffu, s4, 4);
+    const float s5 = div_c<FAST>(__fadd_rn(s4, p), s2, r2, rg), d5 = div_c<FAST>(__fsub_rn(p, s4), s2, r2, rg);
+    p = __shfl_xor_sync(0xffffffffu, s5, 8);
+    const float s6 = div_c<FAST>(__fadd_rn(s5, p), s2, r2, rg), d6 = div_c<FAST>(__fsub_rn(p, s5), s2, r2, rg);
+    p = __shfl_xor_sync(0xffffffffu, s6, 16);
+    const float s7 = div_c<FAST>(__fadd_rn(s6, p), s2, r2, rg), d7 = div_c<FAST>(__fsub_rn(p, s6), s2, r2, rg);
+#pragma unroll
+    for (int i = 0; i < 8; i++) coef[i] = d1[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) coef[8 + i] = d2[i];
+    coef[12] = d3[0]; coef[13] = d3[1]; coef[14] = d4;
+    coef[15] = (g & 1) ? d5 : (g & 2) ? d6 : (g & 4) ? d7 : s7;
+}
+
+/* One CTA per spectral image (128 x 32): Haar rows + columns (Frame.m:113-153), ordered top-T and packing (Frame.m:165-191).
+ * The Haar transform is warp-local — every level runs in registers or through warp shuffles — so the whole image needs ONE block
+ * barrier (between the row and the column pass); the coefficients never go back to shared memory: each thread keeps its 16 and
+ * the selection works on registers.  About 27 KB of shared memory and 64 registers: four CTAs per SM hide each other's barriers. */
 __global__ void __launch_bounds__(HS32_THREADS, 4)
 haar_select32_kernel(const float* __restrict__ images, float* __restrict__ haar_out, uint32_t* __restrict__ words,
                      const int T, const int W, const uint32_t total_frames) {
     __shared__ __align__(16) float imgT[32 * HS32_LDT];      /* also the bucket of undecided keys once the columns are in registers */
     __shared__ Select32Smem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const float s2 = sqrtf(2.0f), s32 = sqrtf(32.0f), s128 = sqrtf(128.0f);
-    const float r2 = 1.0f / s2, r32 = 1.0f / s32, r128 = 1.0f / s128;
     uint32_t* bucket = reinterpret_cast<uint32_t*>(imgT);
+    const int T4 = (T + 3) & ~3;
 
     for (uint32_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
-        /* ---- rows (length 32, Frame.m:114-116): warp w owns rows 16w..16w+15, two lanes per row, 16 elements each ---- */
-        {
-            const int row = 16 * wid + (lane >> 1), half = lane & 1;
-            const float4* src = reinterpret_cast<const float4*>(images + ((size_t)f * LBAD_ROWS_PER_FRAME + row) * 32 + half * 16);
-            float x[16], d1[8], d2[4], d3[2], d4, s4;
-#pragma unroll
-            for (int j = 0; j < 4; j++) { const float4 v = __ldg(src + j); x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
-#pragma unroll
-            for (int j = 0; j < 16; j++) x[j] = div_const(x[j], s32, r32);                   /* Frame.m:137-139 */
-            haar16(x, d1, d2, d3, d4, s4, s2, r2);
-            const float other = __shfl_xor_sync(0xffffffffu, s4, 1);                           /* level 5 joins the two halves */
-            const float top = half ? div_const(__fsub_rn(other, s4), s2, r2) : div_const(__fadd_rn(s4, other), s2, r2);
-            /* ordered output positions; the column pass starts by dividing by sqrtf(128) (Frame.m:137-139): folded into the store */
-            float* dst = imgT + row;
-#pragma unroll
-            for (int i = 0; i < 8; i++) dst[(16 + 8 * half + i) * HS32_LDT] = div_const(d1[i], s128, r128);
-#pragma unroll
-            for (int i = 0; i < 4; i++) dst[(8 + 4 * half + i) * HS32_LDT] = div_const(d2[i], s128, r128);
-#pragma unroll
-            for (int i = 0; i < 2; i++) dst[(4 + 2 * half + i) * HS32_LDT] = div_const(d3[i], s128, r128);
-            dst[(2 + half) * HS32_LDT] = div_const(d4, s128, r128);
-            dst[half * HS32_LDT] = div_const(top, s128, r128);
-        }
-        __syncthreads();
-        /* ---- columns (length 128, Frame.m:118-131): warp w owns columns 4w..4w+3, eight lanes per column, 16 rows each ---- */
-        const int cl = lane & 3, g = lane >> 2, col = 4 * wid + cl;
+        const float* img = images + (size_t)f * LBAD_ROWS_PER_FRAME * 32;
         float coef[16];
-        {
-            float x[16], d1[8], d2[4], d3[2], d4, s4;
-            const float4* src = reinterpret_cast<const float4*>(imgT + col * HS32_LDT + 16 * g);
+        uint32_t key[16];
+        DivRange rg;
+        haar32_rows<true>(img, imgT, rg);
+        __syncthreads();
+        haar32_cols<true>(imgT, coef, rg);
+        auto histogram = [&]() {                             /* per-warp histograms of the exponents of my 16 keys */
 #pragma unroll
-            for (int j = 0; j < 4; j++) { const float4 v = src[j]; x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
-            haar16(x, d1, d2, d3, d4, s4, s2, r2);
-            /* levels 5-7 across the eight lanes of the column: the lane with the lower g keeps the sum, the other the difference */
-            float p = __shfl_xor_sync(0xffffffffu, s4, 4);
-            const float s5 = div_const(__fadd_rn(s4, p), s2, r2), d5 = div_const(__fsub_rn(p, s4), s2, r2);
-            p = __shfl_xor_sync(0xffffffffu, s5, 8);
-            const float s6 = div_const(__fadd_rn(s5, p), s2, r2), d6 = div_const(__fsub_rn(p, s5), s2, r2);
-            p = __shfl_xor_sync(0xffffffffu, s6, 16);
-            const float s7 = div_const(__fadd_rn(s6, p), s2, r2), d7 = div_const(__fsub_rn(p, s6), s2, r2);
+            for (int e = 0; e < 16; e++) key[e] = __float_as_uint(coef[e]) & 0x7fffffffu;
 #pragma unroll
-            for (int i = 0; i < 8; i++) coef[i] = d1[i];
+            for (int j = 0; j < 8; j++) sm.hist[wid][lane + 32 * j] = 0;
+            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; i++) coef[8 + i] = d2[i];
-            coef[12] = d3[0]; coef[13] = d3[1]; coef[14] = d4;
-            coef[15] = (g & 1) ? d5 : (g & 2) ? d6 : (g & 4) ? d7 : s7;
+            for (int e = 0; e < 16; e++) atomicAdd(&sm.hist[wid][key[e] >> 23], 1u);
+        };
+        histogram();
+        if (tid < 16) sm.words[tid] = 0;
+        if (tid == 0) { sm.nsurv = 0; sm.nbucket = 0; sm.rank_sum = 0; }
+        if (__syncthreads_or(rg.bad())) {                    /* a dividend outside the range of the short division: redo the image with checked divisions */
+            haar32_rows<false>(img, imgT, rg);
+            __syncthreads();
+            haar32_cols<false>(imgT, coef, rg);
+            histogram();
+            __syncthreads();
         }
+        /* from here on every warp has read its columns: imgT may become the bucket */
+        const int cl = lane & 3, g = lane >> 2, col = 4 * wid + cl;
         /* row position of each of my coefficients in the ordered output (flat index = 32 * position + column) */
         const uint32_t pos_last = (g & 1) ? 4 + (g >> 1) : (g & 2) ? 2 + (g >> 2) : (g & 4) ? 1 : 0;
         auto flat_idx = [&](int e) -> uint32_t {
@@ -623,17 +678,6 @@ haar_select32_kernel(const float* __restrict__ images, float* __restrict__ haar_
         }
 
         /* ---- ordered top-T (Frame.m:165-191): threshold = T-th largest |v| as an integer key ---- */
-        uint32_t key[16];
-#pragma unroll
-        for (int e = 0; e < 16; e++) key[e] = __float_as_uint(coef[e]) & 0x7fffffffu;
-#pragma unroll
-        for (int j = 0; j < 8; j++) sm.hist[wid][lane + 32 * j] = 0;
-        if (tid < 16) { sm.words[tid] = 0; sm.steps[tid] = 0; }
-        if (tid == 0) { sm.nsurv = 0; sm.nbucket = 0; sm.n_gt = 0; sm.n_eq = 0; }
-        __syncwarp();
-#pragma unroll
-        for (int e = 0; e < 16; e++) atomicAdd(&sm.hist[wid][key[e] >> 23], 1u);
-        __syncthreads();                                     /* also: every warp has read its columns, imgT may become the bucket */
         {
             /* thread t owns exponent bin t: suffix sums S[t] = #keys with exponent >= t; the threshold's exponent is the largest t with S[t] >= T */
             uint32_t tot = 0;
@@ -675,22 +719,21 @@ haar_select32_kernel(const float* __restrict__ images, float* __restrict__ haar_
                 c = __reduce_add_sync(0xffffffffu, c);
                 if (c >= need) t2 = cand;
             }
-            if (lane == 0) sm.threshold = t2;
+            /* keys above the threshold all survive; of those equal to it, the first (T - n_gt) in flat-index order (Q9) */
+            uint32_t gt = 0, eq = 0;
+            for (uint32_t i = lane; i < nb; i += 32) { const uint32_t b = bucket[i]; gt += b > t2; eq += b == t2; }
+            gt = __reduce_add_sync(0xffffffffu, gt); eq = __reduce_add_sync(0xffffffffu, eq);
+            if (lane == 0) { sm.threshold = t2; sm.n_gt = sm.above + gt; sm.n_eq = eq; }
+            for (int i = T + lane; i < T4; i += 32) sm.surv_key[i] = 0;         /* padding of the 128-bit loads of the ranking */
         }
         __syncthreads();
         const uint32_t thr = sm.threshold;
-        {
-            uint32_t ngt = 0, neq = 0;
-#pragma unroll
-            for (int e = 0; e < 16; e++) { ngt += key[e] > thr; neq += key[e] == thr; }
-            ngt = __reduce_add_sync(0xffffffffu, ngt); neq = __reduce_add_sync(0xffffffffu, neq);
-            if (lane == 0) { if (ngt) atomicAdd(&sm.n_gt, ngt); if (neq) atomicAdd(&sm.n_eq, neq); }
-        }
-        __syncthreads();
         const uint32_t need_eq = (uint32_t)T - sm.n_gt;                            /* >= 1 ties to take, lowest flat index first (Q9) */
         uint32_t cut = 0xffffffffu;
         if (sm.n_eq > need_eq) {                                                   /* block-uniform; rare (exact magnitude ties at the threshold) */
             /* smallest cut with #(ties with flat index < cut) >= need_eq, by bisection on the 13 index bits */
+            if (tid < 16) sm.steps[tid] = 0;
+            __syncthreads();
             uint32_t m = 0;
             for (int bit = 12; bit >= 0; --bit) {
                 const uint32_t cand = m | (1u << bit);
@@ -704,37 +747,49 @@ haar_select32_kernel(const float* __restrict__ images, float* __restrict__ haar_
             }
             cut = m + 1;
         }
-        {
-            uint32_t take = 0;
+        /* survivors take a slot each (any order: their rank is computed below from key and index) */
 #pragma unroll
-            for (int e = 0; e < 16; e++) take |= (uint32_t)(key[e] > thr || (key[e] == thr && flat_idx(e) < cut)) << e;
-            const uint32_t mine = __popc(take);
-            uint32_t incl = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-            uint32_t base = 0;
-            if (lane == 31 && incl) base = atomicAdd(&sm.nsurv, incl);
-            base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
-#pragma unroll
-            for (int e = 0; e < 16; e++) if ((take >> e) & 1u) {
-                if (base < 256u) {
-                    sm.surv_key[base] = key[e];
-                    sm.surv_idx[base] = flat_idx(e) | ((coef[e] > 0.0f ? 1u : 0u) << 16) | ((coef[e] < 0.0f ? 1u : 0u) << 17);
+        for (int e = 0; e < 16; e++) {
+            if (key[e] >= thr) {
+                if (key[e] > thr || flat_idx(e) < cut) {
+                    const uint32_t slot = atomicAdd(&sm.nsurv, 1u);
+                    if (slot < 256u) {
+                        sm.surv_key[slot] = key[e];
+                        sm.surv_idx[slot] = flat_idx(e) | ((coef[e] > 0.0f ? 1u : 0u) << 16) | ((coef[e] < 0.0f ? 1u : 0u) << 17);
+                    }
                 }
-                base++;
             }
         }
         __syncthreads();
-        /* rank by counting: survivor j precedes s iff key_j > key_s, or equal keys and idx_j < idx_s */
-        for (int s = tid; s < T; s += HS32_THREADS) {
-            const uint32_t ks = sm.surv_key[s], is = sm.surv_idx[s], idx = is & 0xffffu;
-            uint32_t rank = 0;
-            for (int j = 0; j < T; j++) {
-                const uint32_t kj = sm.surv_key[j], ij = sm.surv_idx[j] & 0xffffu;
-                rank += (kj > ks || (kj == ks && ij < idx)) ? 1u : 0u;
+        /* rank by counting.  Fast form: rank = #keys greater than mine, four keys per 128-bit load; it is a permutation exactly when
+         * no two survivors have equal keys, which the sum of the ranks tells (ties share the lower rank, so the sum falls short). */
+        uint32_t my_rank = 0, my_is = 0;
+        if (tid < T) {
+            const uint32_t ks = sm.surv_key[tid];
+            my_is = sm.surv_idx[tid];
+            for (int j = 0; j < T4; j += 4) {
+                const uint4 k4 = *reinterpret_cast<const uint4*>(&sm.surv_key[j]);
+                my_rank += (k4.x > ks) + (k4.y > ks) + (k4.z > ks) + (k4.w > ks);
             }
-            if (is & (1u << 16)) atomicOr(&sm.words[rank >> 5], 1u << (rank & 31));
-            if (is & (1u << 17)) atomicOr(&sm.words[W + (rank >> 5)], 1u << (rank & 31));
+        }
+        {
+            const uint32_t rs = __reduce_add_sync(0xffffffffu, my_rank);
+            if (lane == 0 && rs) atomicAdd(&sm.rank_sum, rs);
+        }
+        __syncthreads();
+        if (sm.rank_sum != (uint32_t)(T * (T - 1) / 2)) {                         /* equal keys among the survivors: the index breaks the tie (Q9) */
+            if (tid < T) {
+                const uint32_t ks = sm.surv_key[tid], idx = my_is & 0xffffu;
+                my_rank = 0;
+                for (int j = 0; j < T; j++) {
+                    const uint32_t kj = sm.surv_key[j], ij = sm.surv_idx[j] & 0xffffu;
+                    my_rank += (kj > ks || (kj == ks && ij < idx)) ? 1u : 0u;
+                }
+            }
+        }
+        if (tid < T) {
+            if (my_is & (1u << 16)) atomicOr(&sm.words[my_rank >> 5], 1u << (my_rank & 31));
+            if (my_is & (1u << 17)) atomicOr(&sm.words[W + (my_rank >> 5)], 1u << (my_rank & 31));
         }
         __syncthreads();
         if (tid < 2 * W) words[(size_t)f * 2 * W + tid] = sm.words[tid];
@@ -764,6 +819,7 @@ struct lbadcu_plan {
     uint64_t launches = 0;
     LaunchTimer timer, timer2;      /* FFT+bands kernel / Haar+select kernel */
     int stage_mode = -1;      /* -1 auto, 0 plain loads, 1 TMA (env LBAD_STAGE=ldg|tma) */
+    bool transform_generic = false;      /* env LBAD_TRANSFORM=generic: lbadcu_transform_images_host uses the any-geometry Haar/select kernel */
     uint32_t slab_frames_cap = 1u << 18;
 };
 
@@ -835,6 +891,7 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
                    fused_layout((uint32_t)span).total_bytes <= p->smem_optin);
     const char* st = getenv("LBAD_STAGE");
     p->stage_mode = st ? (strcmp(st, "tma") == 0 ? 1 : strcmp(st, "ldg") == 0 ? 0 : -1) : -1;
+    if (const char* tf = getenv("LBAD_TRANSFORM")) p->transform_generic = strcmp(tf, "generic") == 0;
     if (const char* sf = getenv("LBAD_SLAB_FRAMES")) { const unsigned long v = strtoul(sf, nullptr, 10); if (v >= 1 && v <= (1u << 18)) p->slab_frames_cap = (uint32_t)v; }
     *out = p;
     return LBAD_OK;
@@ -993,7 +1050,14 @@ extern "C" int lbadcu_transform_images_host(lbadcu_plan* p, const float* h_image
     DevBuf<float> d_img, d_haar; DevBuf<uint32_t> d_words;
     LBAD_CUDA_TRY(d_img.alloc(n)); LBAD_CUDA_TRY(d_haar.alloc(n)); LBAD_CUDA_TRY(d_words.alloc(nw));
     LBAD_CUDA_TRY(cudaMemcpyAsync(d_img, h_images, n * sizeof(float), cudaMemcpyHostToDevice, p->stream));
-    int e = haar_select_dispatch(p, d_img, d_haar, d_words, count, p->stream);
+    /* the kernel the extraction path itself would run on these images: the register kernel for 32 bands (LBAD_TRANSFORM=generic forces the other) */
+    int e = LBAD_OK;
+    if (p->g.bands == 32 && !p->transform_generic) {
+        const uint32_t grid2 = count < (uint32_t)p->sm_count * 8 ? count : (uint32_t)p->sm_count * 8;
+        haar_select32_kernel<<<grid2, HS32_THREADS, 0, p->stream>>>(d_img, d_haar, d_words, (int)p->g.pairs, (int)p->g.words_per_plane, count);
+        p->launches++;
+        LBAD_CUDA_TRY(cudaGetLastError());
+    } else e = haar_select_dispatch(p, d_img, d_haar, d_words, count, p->stream);
     if (e == LBAD_OK) {
         if (h_haar) LBAD_CUDA_TRY(cudaMemcpyAsync(h_haar, d_haar, n * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
         if (h_words) LBAD_CUDA_TRY(cudaMemcpyAsync(h_words, d_words, nw * sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream));

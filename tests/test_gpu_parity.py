@@ -118,13 +118,21 @@ def test_bit_mismatch_rate_on_a_large_sample(lb, checker):
     assert worst <= BIT_MISMATCH_BUDGET
 
 
-def test_transform_images_bit_exact(lb, checker, config1):
-    """Given identical spectral images, Haar (IEEE divides, same order) and the ordered top-t are bit-exact."""
+@pytest.mark.parametrize("kernel", ["register", "generic"])
+def test_transform_images_bit_exact(lb, checker, config1, kernel, monkeypatch):
+    """Given identical spectral images, Haar (IEEE divides, same order) and the ordered top-t are bit-exact — in the register kernel
+    the batch path runs for 32 bands (haar_select32_kernel) and in the any-geometry one; the images include magnitudes outside the
+    range of the short constant division (the register kernel then redoes the image with checked divisions), ties and silence."""
+    if kernel == "generic":
+        monkeypatch.setenv("LBAD_TRANSFORM", "generic")
     d = lb.Detective()
     rng = np.random.default_rng(7)
     images = np.concatenate([config1["images"][0], (rng.random((4, 128, 32)) ** 4 * 50).astype(np.float32)])
     ties = np.zeros((1, 128, 32), np.float32); ties[0, 5, 3] = 2.0; ties[0, 6, 3] = -2.0; ties[0, 100, 31] = 2.0; ties[0, 64:, :8] = 1.0
-    images = np.concatenate([images, ties, np.zeros((1, 128, 32), np.float32)])
+    tiny = (rng.random((2, 128, 32)).astype(np.float32) * np.float32(1e-30)); tiny[1] *= np.float32(1e-8)          # below 2^-100, down to denormals
+    huge = (rng.random((1, 128, 32)).astype(np.float32) * np.float32(3e37))
+    mixed = (rng.random((1, 128, 32)) ** 4 * 50).astype(np.float32); mixed[0, 17, 5] = np.float32(1e-36); mixed[0, 90, 30] = np.float32(2e37)
+    images = np.concatenate([images, ties, tiny, huge, mixed, np.zeros((1, 128, 32), np.float32)])
     haar, bits = d.transform_images(images)
     for i in range(images.shape[0]):
         want_h = checker.haar(images[i])
@@ -133,8 +141,11 @@ def test_transform_images_bit_exact(lb, checker, config1):
     assert bits[-1].sum() == 0                                            # silence: every coefficient is zero -> no bit set
 
 
-def test_bits_from_coefficients_with_exact_ties(lb, checker):
+@pytest.mark.parametrize("kernel", ["register", "generic"])
+def test_bits_from_coefficients_with_exact_ties(lb, checker, kernel, monkeypatch):
     """Top-t on coefficient sets full of exact magnitude ties: the stable order (lower flat index first) must hold."""
+    if kernel == "generic":
+        monkeypatch.setenv("LBAD_TRANSFORM", "generic")
     d = lb.Detective(); rng = np.random.default_rng(8)
     # images whose Haar transform is easy to control: a constant image has a single non-zero coefficient; use small integers instead
     images = rng.integers(0, 3, size=(6, 128, 32)).astype(np.float32)
