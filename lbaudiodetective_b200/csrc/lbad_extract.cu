@@ -558,8 +558,30 @@ __device__ __forceinline__ void haar16(const float (&x)[16], float (&d1)[8], flo
     d4 = div_c<FAST>(__fsub_rn(t3[0], t3[1]), s2, r2, rg);
 }
 
+/* Suffix search in a 256-bin histogram, done redundantly by every warp (no broadcast, no barrier): bin = the largest b with
+ * S[b] = sum_{j >= b} hist[j] >= need, above = S[b + 1], count = hist[b].  Requires 1 <= need <= S[0]. */
+__device__ __forceinline__ void warp_find_bin256(const uint32_t* __restrict__ hist, const uint32_t need, uint32_t& bin, uint32_t& above, uint32_t& count) {
+    const int lane = threadIdx.x & 31;
+    const uint4 a = *reinterpret_cast<const uint4*>(hist + 8 * lane), b = *reinterpret_cast<const uint4*>(hist + 8 * lane + 4);
+    const uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const uint32_t tot = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+    uint32_t suf = tot;                                      /* inclusive suffix over the lanes */
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_down_sync(0xffffffffu, suf, d); if (lane + d < 32) suf += o; }
+    uint32_t run = suf - tot, mybin = 0, myabove = 0, mycount = 0;
+    const bool here = suf >= need && run < need;             /* true in exactly one lane */
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+        if (run < need && run + c[j] >= need) { mybin = 8u * lane + j; myabove = run; mycount = c[j]; }
+        run += c[j];
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
+    bin = __shfl_sync(0xffffffffu, mybin, src); above = __shfl_sync(0xffffffffu, myabove, src); count = __shfl_sync(0xffffffffu, mycount, src);
+}
+
 struct Select32Smem {
     uint32_t hist[HS32_THREADS / 32][256];   /* per-warp histograms of the 8 exponent bits */
+    __align__(16) uint32_t digit_hist[3][256];   /* mantissa bits 22..15, 14..7, 6..0 of the keys that are still candidates for the threshold */
     uint32_t warp_tot[HS32_THREADS / 32];
     __align__(16) uint32_t surv_key[256];
     uint32_t surv_idx[256];                  /* flat index | sign code << 16 (bit 16: v > 0, bit 17: v < 0) */
@@ -656,6 +678,9 @@ haar_select32_kernel(const float* __restrict__ images, float* __restrict__ haar_
         histogram();
         if (tid < 16) sm.words[tid] = 0;
         if (tid == 0) { sm.nsurv = 0; sm.nbucket = 0; sm.rank_sum = 0; }
+#pragma unroll
+        for (int j = 0; j < 3; j++) sm.digit_hist[j][tid] = 0;
+        for (int i = T + tid; i < T4; i += HS32_THREADS) sm.surv_key[i] = 0;     /* padding of the 128-bit loads of the ranking */
         if (__syncthreads_or(rg.bad())) {                    /* a dividend outside the range of the short division: redo the image with checked divisions */
             haar32_rows<false>(img, imgT, rg);
             __syncthreads();
@@ -709,28 +734,29 @@ haar_select32_kernel(const float* __restrict__ images, float* __restrict__ haar_
             for (int e = 0; e < 16; e++) if ((key[e] >> 23) == expo) bucket[base++] = key[e];
         }
         __syncthreads();
-        if (wid == 0) {
-            const uint32_t nb = sm.nbucket, need = (uint32_t)T - sm.above;      /* rank of the threshold inside the bucket, >= 1 */
-            uint32_t t2 = expo << 23;
-            for (int bit = 22; bit >= 0; --bit) {
-                const uint32_t cand = t2 | (1u << bit);
-                uint32_t c = 0;
-                for (uint32_t i = lane; i < nb; i += 32) c += (bucket[i] >= cand) ? 1u : 0u;
-                c = __reduce_add_sync(0xffffffffu, c);
-                if (c >= need) t2 = cand;
-            }
-            /* keys above the threshold all survive; of those equal to it, the first (T - n_gt) in flat-index order (Q9) */
-            uint32_t gt = 0, eq = 0;
-            for (uint32_t i = lane; i < nb; i += 32) { const uint32_t b = bucket[i]; gt += b > t2; eq += b == t2; }
-            gt = __reduce_add_sync(0xffffffffu, gt); eq = __reduce_add_sync(0xffffffffu, eq);
-            if (lane == 0) { sm.threshold = t2; sm.n_gt = sm.above + gt; sm.n_eq = eq; }
-            for (int i = T + lane; i < T4; i += 32) sm.surv_key[i] = 0;         /* padding of the 128-bit loads of the ranking */
+        /* the remaining 23 bits of the threshold, 8 + 8 + 7 at a time: all threads histogram the digit of the bucket keys that still
+         * match, then EVERY warp finds the digit's bin for itself — three short phases instead of a 23-step bisection by one warp */
+        const uint32_t nb = sm.nbucket;
+        uint32_t need = (uint32_t)T - sm.above, thr = expo << 23, n_eq;           /* need: rank of the threshold among the candidates, >= 1 */
+        {
+            uint32_t d, above;
+            for (uint32_t i = tid; i < nb; i += HS32_THREADS) atomicAdd(&sm.digit_hist[0][(bucket[i] >> 15) & 255u], 1u);
+            __syncthreads();
+            warp_find_bin256(sm.digit_hist[0], need, d, above, n_eq);
+            thr |= d << 15; need -= above;
+            for (uint32_t i = tid; i < nb; i += HS32_THREADS) { const uint32_t k = bucket[i]; if ((k >> 15) == (thr >> 15)) atomicAdd(&sm.digit_hist[1][(k >> 7) & 255u], 1u); }
+            __syncthreads();
+            warp_find_bin256(sm.digit_hist[1], need, d, above, n_eq);
+            thr |= d << 7; need -= above;
+            for (uint32_t i = tid; i < nb; i += HS32_THREADS) { const uint32_t k = bucket[i]; if ((k >> 7) == (thr >> 7)) atomicAdd(&sm.digit_hist[2][k & 127u], 1u); }
+            __syncthreads();
+            warp_find_bin256(sm.digit_hist[2], need, d, above, n_eq);
+            thr |= d; need -= above;
         }
-        __syncthreads();
-        const uint32_t thr = sm.threshold;
-        const uint32_t need_eq = (uint32_t)T - sm.n_gt;                            /* >= 1 ties to take, lowest flat index first (Q9) */
+        /* keys above the threshold all survive; of the n_eq equal to it, the first need_eq in flat-index order (Q9) */
+        const uint32_t need_eq = need;
         uint32_t cut = 0xffffffffu;
-        if (sm.n_eq > need_eq) {                                                   /* block-uniform; rare (exact magnitude ties at the threshold) */
+        if (n_eq > need_eq) {                                                      /* block-uniform; rare (exact magnitude ties at the threshold) */
             /* smallest cut with #(ties with flat index < cut) >= need_eq, by bisection on the 13 index bits */
             if (tid < 16) sm.steps[tid] = 0;
             __syncthreads();
