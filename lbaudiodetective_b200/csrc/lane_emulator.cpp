@@ -40,20 +40,29 @@ static void emulate_windows(const float* pcm, int hop, const uint32_t* klow, con
     for (int lane = 0; lane < 32; lane++) {
         const int my_win = lane / R, n2 = lane % R;
         const float* win = pcm + (size_t)my_win * hop;
-        if constexpr (R == 32) {                    /* the kernel's carried scheme: E = dft16 of the even n1 (odd n1 of the window one hop earlier), O = dft16 of the odd n1 */
+        if constexpr (R == 32) {
+            /* the kernel's carried scheme: P = dft16(odd n1) x twiddle is what a window computes; P of the even n1 is the carried P of the
+             * window one hop earlier; z[k1] tw[k1] = Pe + W^k1 Po, z[k1+16] tw[k1+16] = (Pe - W^k1 Po) exp(-2 pi i 16 n2 / M) */
             float2 ev[16], od[16];
             for (int m = 0; m < 16; m++) { ev[m] = make_float2(win[2 * (32 * (2 * m) + lane)], win[2 * (32 * (2 * m) + lane) + 1]); od[m] = make_float2(win[2 * (32 * (2 * m + 1) + lane)], win[2 * (32 * (2 * m + 1) + lane) + 1]); }
             dft16(ev); dft16(od);
+            for (int q = 0; q < 16; q++) {
+                const double a = 2.0 * M_PI * (double)(lane * bitrevR<16>(q)) / (double)M; const float tx = (float)cos(a), ty = (float)-sin(a);
+                ev[q] = make_float2(ev[q].x * tx - ev[q].y * ty, ev[q].x * ty + ev[q].y * tx);
+                od[q] = make_float2(od[q].x * tx - od[q].y * ty, od[q].x * ty + od[q].y * tx);
+            }
             dit32_combine(ev, od, z[lane]);
+            const double ao = 2.0 * M_PI * (double)(16 * lane) / (double)M; const float omx = (float)cos(ao), omy = (float)-sin(ao);
+            for (int q = 0; q < 16; q++) { float2& v = z[lane][2 * q + 1]; v = make_float2(v.x * omx - v.y * omy, v.x * omy + v.y * omx); }
         } else {
             for (int n1 = 0; n1 < 32; n1++) z[lane][n1] = make_float2(win[2 * (R * n1 + n2)], win[2 * (R * n1 + n2) + 1]);
             fft32(z[lane]);
-        }
-        for (int p = 0; p < 32; p += 2) {
-            const float* w = tw1[(p >> 1) * 32 + lane];
-            float2* zz = z[lane];
-            zz[p] = make_float2(zz[p].x * w[0] - zz[p].y * w[1], zz[p].x * w[1] + zz[p].y * w[0]);
-            zz[p + 1] = make_float2(zz[p + 1].x * w[2] - zz[p + 1].y * w[3], zz[p + 1].x * w[3] + zz[p + 1].y * w[2]);
+            for (int p = 0; p < 32; p += 2) {
+                const float* w = tw1[(p >> 1) * 32 + lane];
+                float2* zz = z[lane];
+                zz[p] = make_float2(zz[p].x * w[0] - zz[p].y * w[1], zz[p].x * w[1] + zz[p].y * w[0]);
+                zz[p + 1] = make_float2(zz[p + 1].x * w[2] - zz[p + 1].y * w[3], zz[p + 1].x * w[3] + zz[p + 1].y * w[2]);
+            }
         }
     }
     static float zx[32][32], zy[32][32];            /* [lane][position]: the transposed components, as the kernel's 128-bit loads deliver them */

@@ -376,10 +376,19 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
          * 16-point transform of a window's odd-n1 inputs is carried over as the even-n1 transform of the next window (dft16 /
          * dit32_combine in lbad_math.cuh): half the sample loads and 48 instead of 80 butterflies in pass 1. */
         float2 carry[16];
+        const float2* tw1h = reinterpret_cast<const float2*>(tw1);               /* CARRY: [q][lane] = exp(-2 pi i n2 k1 / M), k1 = bitrev4(q); row 16 = exp(-2 pi i 16 n2 / M) */
+        /* The pass-1 twiddle exp(-2 pi i n2 k1 / M) does not depend on the window either, so what is carried is P = O x twiddle:
+         * z[k1] x tw[k1] = P_prev[k1] + W^k1 P[k1], and z[k1+16] x tw[k1+16] = (P_prev[k1] - W^k1 P[k1]) x exp(-2 pi i 16 n2 / M) —
+         * 16 table entries per window instead of 32 (the kernel is bound by shared-memory wavefronts), the same number of products. */
         auto half_transform = [&](const float* w, float2 (&h)[16]) {             /* inputs z[32 n1 + lane], n1 = 1, 3, .., 31 of the window at w */
 #pragma unroll
             for (int m = 0; m < 16; m++) h[m] = *reinterpret_cast<const float2*>(w + 2 * (32 * (2 * m + 1) + lane));
             dft16(h);
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const float2 t = tw1h[q * 32 + lane];
+                h[q] = make_float2(h[q].x * t.x - h[q].y * t.y, h[q].x * t.y + h[q].y * t.x);
+            }
         };
         if constexpr (CARRY) half_transform(samples + (size_t)(wid * ITERS) * hop - hop, carry);     /* even n1 of the first window = odd n1 of the one before */
 #pragma unroll 1
@@ -390,20 +399,24 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
             if constexpr (CARRY) {
                 float2 odd[16];
                 half_transform(win, odd);
-                dit32_combine(carry, odd, z);                                   /* over n1; position p holds k1 = bitrev5(p) */
+                dit32_combine(carry, odd, z);                                   /* over n1; position p holds k1 = bitrev5(p), already twiddled for even p */
+                const float2 om = tw1h[16 * 32 + lane];
 #pragma unroll
-                for (int m = 0; m < 16; m++) carry[m] = odd[m];
+                for (int q = 0; q < 16; q++) {
+                    z[2 * q + 1] = make_float2(z[2 * q + 1].x * om.x - z[2 * q + 1].y * om.y, z[2 * q + 1].x * om.y + z[2 * q + 1].y * om.x);
+                    carry[q] = odd[q];
+                }
             } else {
 #pragma unroll
                 for (int n1 = 0; n1 < 32; n1++)                                 /* vDSP_ctoz (m:353): z[n] = x[2n] + i x[2n+1], n = R n1 + n2 */
                     z[n1] = *reinterpret_cast<const float2*>(win + 2 * (R * n1 + n2));
                 fft32(z);                                                       /* over n1; position p holds k1 = bitrev5(p) */
-            }
 #pragma unroll
-            for (int p = 0; p < 32; p += 2) {                                   /* x exp(-2 pi i n2 k1 / M) */
-                const float4 w = tw1[(p >> 1) * 32 + lane];
-                z[p] = make_float2(z[p].x * w.x - z[p].y * w.y, z[p].x * w.y + z[p].y * w.x);
-                z[p + 1] = make_float2(z[p + 1].x * w.z - z[p + 1].y * w.w, z[p + 1].x * w.w + z[p + 1].y * w.z);
+                for (int p = 0; p < 32; p += 2) {                               /* x exp(-2 pi i n2 k1 / M) */
+                    const float4 w = tw1[(p >> 1) * 32 + lane];
+                    z[p] = make_float2(z[p].x * w.x - z[p].y * w.y, z[p].x * w.y + z[p].y * w.x);
+                    z[p + 1] = make_float2(z[p + 1].x * w.z - z[p + 1].y * w.w, z[p + 1].x * w.w + z[p + 1].y * w.z);
+                }
             }
             /* 32x32 transpose through shared memory, one component at a time: lane k1 ends up with A_s[n2][k1] at position s R + n2 */
             float zx[32], zy[32];
@@ -892,6 +905,11 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     for (int pp = 0; pp < 32; pp += 2) for (int l = 0; l < 32; l++) {            /* pass-1 twiddles exp(-2 pi i n2 k1 / M), n2 = lane % R, in register-position order */
         const double a0 = 2.0 * M_PI * (double)((l % Rr) * bitrev5(pp)) / (double)M, a1 = 2.0 * M_PI * (double)((l % Rr) * bitrev5(pp + 1)) / (double)M;
         tw1[(pp >> 1) * 32 + l] = make_float4((float)cos(a0), (float)-sin(a0), (float)cos(a1), (float)-sin(a1));
+    }
+    if (N == 2048 && geo->stride == 64) {                                         /* the carried-transform kernel: one (cos, -sin) per k1 < 16 and lane, then the lane's exp(-2 pi i 16 n2 / M) */
+        float2* t1 = reinterpret_cast<float2*>(tw1.data());
+        for (int q = 0; q < 16; q++) for (int l = 0; l < 32; l++) { const double a = 2.0 * M_PI * (double)(l * bitrevR<16>(q)) / (double)M; t1[q * 32 + l] = make_float2((float)cos(a), (float)-sin(a)); }
+        for (int l = 0; l < 32; l++) { const double a = 2.0 * M_PI * (double)(16 * l) / (double)M; t1[16 * 32 + l] = make_float2((float)cos(a), (float)-sin(a)); }
     }
     for (int k2 = 0; k2 < 32; k2 += 2) for (int l = 0; l < 32; l++) {            /* real-split twiddles for bins l+32k2 and l+32(k2+1) (rows k2 < R are used) */
         const double a0 = 2.0 * M_PI * (double)(l + 32 * k2) / (double)N, a1 = 2.0 * M_PI * (double)(l + 32 * (k2 + 1)) / (double)N;
