@@ -35,12 +35,13 @@ def load_library(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise FileNotFoundError(LIB_PATH + " is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    path = os.environ.get("LBAD_LIBRARY") or LIB_PATH      # LBAD_LIBRARY: another build of the same CUDA library (kernel A/B experiments, build.py --variant)
+    if not os.path.exists(path):
+        if not build_if_missing or path != LIB_PATH:
+            raise FileNotFoundError(path + " is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
         from . import build as _b
         _b.build()
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, u32, u64, f32, f64, u8 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float, C.c_double, C.c_ubyte
     P = C.POINTER
     sig = {
@@ -60,6 +61,11 @@ def load_library(build_if_missing: bool = True):
         "LBAudioDetectiveProcessPCM": (C.c_int32, [vp, vp, u64, P(vp)]),
         "LBAudioDetectiveComparePCM": (C.c_int32, [vp, vp, u64, vp, u64, u32, P(f32)]),
         "LBAudioDetectiveCheckConfiguration": (C.c_int32, [vp]),
+        "LBAudioDetectiveGetRecordingSampleRate": (f64, [vp]),
+        "LBAudioDetectiveGetResampledLength": (u64, [vp, u64]),
+        "LBAudioDetectiveResamplePCM": (C.c_int32, [vp, vp, u64, vp]),
+        "LBAudioDetectiveProcessRecordedPCM": (C.c_int32, [vp, vp, u64, P(vp)]),
+        "LBAudioDetectiveProcessRecordedPCMBatchDevice": (C.c_int32, [vp, vp, u32, u64, u64, vp, vp]),
         "LBAudioDetectiveGetNumberOfSubfingerprintsForLength": (u64, [vp, u64]),
         "LBAudioDetectiveGetBandTable": (C.c_int32, [vp, vp, vp, vp]),
         "LBAudioDetectiveProcessPCMBatch": (C.c_int32, [vp, vp, u32, u64, u64, vp]),
@@ -297,6 +303,29 @@ class Detective:
     def set_window_size(self, v): return int(self._L.LBAudioDetectiveSetWindowSize(self.ref, v))
     def set_analysis_stride(self, v): return int(self._L.LBAudioDetectiveSetAnalysisStride(self.ref, v))
     def check_configuration(self): return int(self._L.LBAudioDetectiveCheckConfiguration(self.ref))
+
+    # ---- recording-rate front end (include/LBAudioDetectiveResample.h) ----
+    def set_recording_rate(self, v): return int(self._L.LBAudioDetectiveSetRecordingSampleRate(self.ref, v))
+
+    @property
+    def recording_rate(self): return float(self._L.LBAudioDetectiveGetRecordingSampleRate(self.ref))
+
+    def resampled_length(self, n): return int(self._L.LBAudioDetectiveGetResampledLength(self.ref, n))
+
+    def resample(self, pcm):
+        pcm = _f32(pcm); out = np.zeros(self.resampled_length(len(pcm)), np.float32)
+        _check(self._L.LBAudioDetectiveResamplePCM(self.ref, _ptr(pcm), len(pcm), _ptr(out)), "LBAudioDetectiveResamplePCM")
+        return out
+
+    def process_recorded_pcm(self, pcm):
+        pcm = _f32(pcm); ref = C.c_void_p()
+        st = self._L.LBAudioDetectiveProcessRecordedPCM(self.ref, _ptr(pcm), len(pcm), C.byref(ref))
+        fp = Fingerprint(_ref=ref.value) if ref.value else None
+        _check(st, "LBAudioDetectiveProcessRecordedPCM")
+        return fp
+
+    def process_recorded_batch_device(self, d_pcm_ptr, n_clips, clip_len, clip_stride, d_words_ptr, stream=None):
+        _check(self._L.LBAudioDetectiveProcessRecordedPCMBatchDevice(self.ref, d_pcm_ptr, n_clips, clip_len, clip_stride, d_words_ptr, stream), "LBAudioDetectiveProcessRecordedPCMBatchDevice")
 
     def subfingerprints_for_length(self, n):
         return int(self._L.LBAudioDetectiveGetNumberOfSubfingerprintsForLength(self.ref, n))

@@ -9,13 +9,13 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libLBAudioDetectiveCUDA.so")
 OBJ = os.path.join(PKG, "build")
 
-CU = ["lbad_extract.cu", "lbad_search.cu", "lbad_synth.cu"]
-C = ["LBAudioDetective.c", "LBAudioDetectiveFingerprint.c", "LBAudioDetectiveDatabase.c", "lbad_support.c"]
+CU = ["lbad_extract.cu", "lbad_search.cu", "lbad_synth.cu", "lbad_resample.cu"]
+C = ["LBAudioDetective.c", "LBAudioDetectiveFingerprint.c", "LBAudioDetectiveDatabase.c", "lbad_support.c", "lbad_resample_design.c"]
 HDRS = ["lbad_cuda.h", "lbad_common.cuh", "lbad_math.cuh", "lbad_host.h"]
 
 NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-diag-suppress", "186"]
-CC_FLAGS = ["-std=gnu11", "-O2", "-fPIC", "-Wall", "-Wextra", "-fvisibility=hidden"]
+CC_FLAGS = ["-std=gnu11", "-O2", "-fPIC", "-Wall", "-Wextra", "-fvisibility=hidden", "-ffp-contract=off"]
 
 
 def _nvcc():
@@ -27,6 +27,23 @@ def _stale(target, deps):
         return True
     t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build_variant(name: str, defines) -> str:
+    """Kernel A/B experiments: the same sources with extra -D flags, linked into scripts/_bin/libvariant_<name>.so (never the shipped
+    library; bench.py loads one when LBAD_LIBRARY points at it)."""
+    out_dir = os.path.join(PKG, "..", "scripts", "_bin"); os.makedirs(out_dir, exist_ok=True)
+    obj_dir = os.path.join(out_dir, "obj_" + name); os.makedirs(obj_dir, exist_ok=True)
+    objs = []
+    for s in CU:
+        o = os.path.join(obj_dir, s + ".o"); objs.append(o)
+        subprocess.run([_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, s), "-o", o], check=True)
+    for s in C:
+        o = os.path.join(obj_dir, s + ".o"); objs.append(o)
+        subprocess.run([os.environ.get("CC", "gcc")] + CC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o], check=True)
+    lib = os.path.join(out_dir, "libvariant_%s.so" % name)
+    subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-lm"], check=True)
+    return lib
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -59,4 +76,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:          # python build.py --variant NAME -DFOO=1 -DBAR=2
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a[2:] for a in sys.argv[i + 2:] if a.startswith("-D")]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

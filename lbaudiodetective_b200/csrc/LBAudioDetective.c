@@ -29,8 +29,14 @@ struct LBAudioDetective {
     UInt32 pitchStepCount;
     lbadcu_plan* plan;          /* built lazily; any setter invalidates it */
     UInt64 launchesBefore;      /* launches of plans that were since destroyed */
+    Float64 recordingSampleRate;        /* rate of the PCM given to the ...Recorded... entry points (LBAudioDetectiveResample.h) */
+    lbadcu_resampler* resampler;        /* built lazily for (recordingSampleRate, processing rate) */
+    Float32* dResampled; UInt64 dResampledCapacity;     /* device scratch of ProcessRecordedPCMBatchDevice */
 };
 
+static void invalidate_resampler(LBAudioDetectiveRef d) {
+    if (d->resampler) { d->launchesBefore += lbadcu_resampler_launches(d->resampler); lbadcu_resampler_destroy(d->resampler); d->resampler = NULL; }
+}
 static void invalidate_plan(LBAudioDetectiveRef d) {
     if (d->plan) { d->launchesBefore += lbadcu_plan_launches(d->plan); lbadcu_plan_destroy(d->plan); d->plan = NULL; }
 }
@@ -44,6 +50,7 @@ LBAudioDetectiveRef LBAudioDetectiveNew(void) {
     LBAudioDetectiveSetWindowSize(d, kLBAudioDetectiveDefaultWindowSize);     /* return value ignored, as upstream (m:85) */
     d->analysisStride = kLBAudioDetectiveDefaultAnalysisStride;
     d->pitchStepCount = kLBAudioDetectiveDefaultNumberOfPitchSteps;
+    d->recordingSampleRate = 44100.0;
     return d;
 }
 
@@ -51,6 +58,8 @@ LBAudioDetectiveRef LBAudioDetectiveNew(void) {
 OSStatus LBAudioDetectiveDispose(LBAudioDetectiveRef d) {
     if (d == NULL) return kLBAudioDetectiveArgumentInvalid;
     invalidate_plan(d);
+    invalidate_resampler(d);
+    if (d->dResampled) lbadcu_device_free(d->dResampled);
     free(d);
     return noErr;
 }
@@ -79,11 +88,17 @@ UInt32 LBAudioDetectiveGetWindowSize(LBAudioDetectiveRef d) { return d->windowSi
 UInt32 LBAudioDetectiveGetAnalysisStride(LBAudioDetectiveRef d) { return d->analysisStride; }
 
 /* h:143 — declared upstream, never defined */
-OSStatus LBAudioDetectiveSetRecordingSampleRate(LBAudioDetectiveRef d, Float64 inSampleRate) { (void)d; (void)inSampleRate; return noErr; }
+/* h:143 (declared upstream, never defined): here the rate of the PCM handed to the ...Recorded... entry points */
+OSStatus LBAudioDetectiveSetRecordingSampleRate(LBAudioDetectiveRef d, Float64 inSampleRate) {
+    if (!d || !(inSampleRate > 0.0)) return kLBAudioDetectiveArgumentInvalid;
+    d->recordingSampleRate = inSampleRate; invalidate_resampler(d);
+    return noErr;
+}
+Float64 LBAudioDetectiveGetRecordingSampleRate(LBAudioDetectiveRef d) { return d ? d->recordingSampleRate : 0.0; }
 
 /* m:156-160 */
 OSStatus LBAudioDetectiveSetProcessingSampleRate(LBAudioDetectiveRef d, Float64 inSampleRate) {
-    d->processingFormat.mSampleRate = inSampleRate; invalidate_plan(d);
+    d->processingFormat.mSampleRate = inSampleRate; invalidate_plan(d); invalidate_resampler(d);
     return noErr;
 }
 /* m:162-166 */
@@ -279,9 +294,78 @@ OSStatus LBAudioDetectiveTransformImages(LBAudioDetectiveRef d, const Float32* i
     return e;
 }
 
+/* ---- recording-rate front end (include/LBAudioDetectiveResample.h; replaces the ExtAudioFile client-format conversion, m:229 / m:275) ---- */
+
+static OSStatus ensure_resampler(LBAudioDetectiveRef d) {
+    if (d->resampler) return noErr;
+    lbadcu_resample_design des;
+    if (lbad_resample_design_create(d->recordingSampleRate, d->processingFormat.mSampleRate, &des) != LBAD_OK) return kLBAudioDetectiveArgumentInvalid;
+    OSStatus e = lbad_status(lbadcu_resampler_create(&des, &d->resampler));
+    lbad_resample_design_free(&des);
+    return e;
+}
+
+UInt64 LBAudioDetectiveGetResampledLength(LBAudioDetectiveRef d, UInt64 inNumberFrames) {
+    if (!d) return 0;
+    return lbad_resample_out_len(d->recordingSampleRate, d->processingFormat.mSampleRate, inNumberFrames);
+}
+
+OSStatus LBAudioDetectiveResamplePCM(LBAudioDetectiveRef d, const Float32* inSamples, UInt64 inNumberFrames, Float32* outSamples) {
+    if (!d || !inSamples || !outSamples) return kLBAudioDetectiveArgumentInvalid;
+    OSStatus e = ensure_resampler(d);
+    if (e != noErr) return e;
+    return lbad_status(lbadcu_resample_host(d->resampler, inSamples, inNumberFrames, outSamples, LBAudioDetectiveGetResampledLength(d, inNumberFrames)));
+}
+
+OSStatus LBAudioDetectiveProcessRecordedPCMBatchDevice(LBAudioDetectiveRef d, const Float32* dSamples, UInt32 nClips, UInt64 framesPerClip, UInt64 clipStride, UInt32* dWords, void* stream) {
+    if (!d || !dSamples || !dWords || nClips == 0 || clipStride < framesPerClip) return kLBAudioDetectiveArgumentInvalid;
+    OSStatus e = ensure_plan(d);
+    if (e == noErr) e = ensure_resampler(d);
+    if (e != noErr) return e;
+    const UInt64 outLen = LBAudioDetectiveGetResampledLength(d, framesPerClip);
+    if (outLen < d->windowSize) return kLBAudioDetectiveArgumentInvalid;
+    const UInt64 outStride = (outLen + 3) & ~(UInt64)3;                            /* keeps every clip 16-byte aligned for the bulk copies of the FFT kernel */
+    if (d->dResampledCapacity < outStride * nClips) {
+        if (d->dResampled) lbadcu_device_free(d->dResampled);
+        d->dResampled = NULL; d->dResampledCapacity = 0;
+        e = lbad_status(lbadcu_device_alloc_floats(outStride * nClips, &d->dResampled));
+        if (e != noErr) return e;
+        d->dResampledCapacity = outStride * nClips;
+    }
+    if (!stream) stream = lbadcu_plan_stream(d->plan);                            /* both kernels on one stream: the extraction follows the conversion */
+    e = lbad_status(lbadcu_resample_device(d->resampler, dSamples, nClips, framesPerClip, clipStride, d->dResampled, outLen, outStride, stream));
+    if (e != noErr) return e;
+    return lbad_status(lbadcu_extract_device(d->plan, d->dResampled, nClips, outLen, outStride, dWords, NULL, NULL, 0, stream));
+}
+
+OSStatus LBAudioDetectiveProcessRecordedPCM(LBAudioDetectiveRef d, const Float32* inSamples, UInt64 inNumberFrames, LBAudioDetectiveFingerprintRef* outFingerprint) {
+    if (!d || !outFingerprint) return kLBAudioDetectiveArgumentInvalid;
+    *outFingerprint = NULL;
+    if (!inSamples) return kLBAudioDetectiveArgumentInvalid;
+    OSStatus e = ensure_plan(d);
+    if (e == noErr) e = ensure_resampler(d);
+    if (e != noErr) return e;
+    LBAudioDetectiveFingerprintRef fp = LBAudioDetectiveFingerprintNew(0);
+    UInt32 L = d->subfingerprintLength;
+    LBAudioDetectiveFingerprintSetSubfingerprintLength(fp, &L);
+    *outFingerprint = fp;
+    const UInt64 outLen = LBAudioDetectiveGetResampledLength(d, inNumberFrames);
+    if (outLen < d->windowSize) return kLBAudioDetectiveArgumentInvalid;
+    const UInt64 count = LBAudioDetectiveGetNumberOfSubfingerprintsForLength(d, outLen);
+    if (count == 0) return noErr;
+    if (count > 0x7fffffffu) return kLBAudioDetectiveArgumentInvalid;
+    const UInt32 W = lbad_words_per_plane(L);
+    UInt32* words = malloc((size_t)count * 2 * W * sizeof(UInt32));
+    if (!words) return kLBAudioDetectiveArgumentInvalid;
+    e = lbad_status(lbadcu_process_recorded_host(d->plan, d->resampler, inSamples, inNumberFrames, outLen, words, (size_t)count * 2 * W));
+    if (e == noErr) e = lbad_fingerprint_append_packed(fp, words, (UInt32)count);
+    free(words);
+    return e;
+}
+
 UInt64 LBAudioDetectiveGetKernelLaunchCount(LBAudioDetectiveRef d) {
     if (!d) return 0;
-    return d->launchesBefore + (d->plan ? lbadcu_plan_launches(d->plan) : 0);
+    return d->launchesBefore + (d->plan ? lbadcu_plan_launches(d->plan) : 0) + (d->resampler ? lbadcu_resampler_launches(d->resampler) : 0);
 }
 
 UInt32 LBAudioDetectiveGetKernelTiming(LBAudioDetectiveRef d, Boolean inEnable, Boolean inReset, Float64* outTotalMilliseconds) {

@@ -62,6 +62,32 @@ int  lbadcu_extract_host_i16(lbadcu_plan* p, const int16_t* h_pcm, uint32_t n_cl
 /* Haar + top-t + pack on device images [count][128][B] (generic kernel). */
 int  lbadcu_transform_images_host(lbadcu_plan* p, const float* h_images, uint32_t count, float* h_haar, uint32_t* h_words);
 
+/* ---- recording-rate -> processing-rate conversion (include/LBAudioDetectiveResample.h) ---- */
+#define LBAD_RS_PHASES 64u
+typedef struct {
+    double in_rate, out_rate, rho2;  /* rho2 = in_rate / (out_rate * D) */
+    uint32_t D, H1, T1;              /* integer pre-decimation; stage-1 half length and taps (T1 = 2 H1 + 1; unused when D = 1) */
+    uint32_t H2, T2;                 /* stage-2 half length and taps (T2 = 2 H2) */
+    float* g;                        /* [T1] */
+    float* hc;                       /* [LBAD_RS_PHASES + 1][T2] */
+} lbadcu_resample_design;
+/* host-side filter design (lbad_resample_design.c) */
+int  lbad_resample_design_create(double in_rate, double out_rate, lbadcu_resample_design* d);
+void lbad_resample_design_free(lbadcu_resample_design* d);
+uint64_t lbad_resample_out_len(double in_rate, double out_rate, uint64_t n_in);
+typedef struct lbadcu_resampler lbadcu_resampler;
+int  lbadcu_resampler_create(const lbadcu_resample_design* d, lbadcu_resampler** out);
+void lbadcu_resampler_destroy(lbadcu_resampler* r);
+uint64_t lbadcu_resampler_launches(const lbadcu_resampler* r);
+/* clips of in_len recorded samples, in_stride apart -> out_len samples each, out_stride apart (device pointers) */
+int  lbadcu_resample_device(lbadcu_resampler* r, const float* d_in, uint32_t n_clips, uint64_t in_len, uint64_t in_stride,
+                            float* d_out, uint64_t out_len, uint64_t out_stride, void* stream);
+int  lbadcu_resample_host(lbadcu_resampler* r, const float* h_in, uint64_t n_in, float* h_out, uint64_t n_out);
+/* one recorded clip from host memory: upload, convert, extract, download n_words packed words — nothing but the words returns to the host */
+int  lbadcu_process_recorded_host(lbadcu_plan* p, lbadcu_resampler* r, const float* h_in, uint64_t n_in, uint64_t out_len, uint32_t* h_words, size_t n_words);
+int  lbadcu_device_alloc_floats(uint64_t n, float** out);
+void lbadcu_device_free(void* p);
+
 /* ---- search ---- */
 typedef struct lbadcu_db lbadcu_db;
 /* pairs_full = ceil(L/2): pairs every stored subfingerprint carries */

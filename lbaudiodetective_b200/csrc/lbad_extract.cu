@@ -391,7 +391,11 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
             }
         };
         if constexpr (CARRY) half_transform(samples + (size_t)(wid * ITERS) * hop - hop, carry);     /* even n1 of the first window = odd n1 of the one before */
-#pragma unroll 1
+#ifndef LBAD_WINDOW_UNROLL
+#define LBAD_WINDOW_UNROLL 1
+#endif
+        constexpr int WINDOW_UNROLL = LBAD_WINDOW_UNROLL;                       /* A/B knob (build.py --variant) */
+#pragma unroll WINDOW_UNROLL
         for (int it = 0; it < ITERS; it++) {
             const int row0 = CARRY ? wid * ITERS + it : (wid + it * FUSED_WARPS) * S;
             const float* win = samples + (size_t)(row0 + my_win) * hop;

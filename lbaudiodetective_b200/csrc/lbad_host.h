@@ -3,6 +3,7 @@
 #define LBAD_HOST_H
 #include "../../include/LBAudioDetective.h"
 #include "../../include/LBAudioDetectiveDatabase.h"
+#include "../../include/LBAudioDetectiveResample.h"
 #include "lbad_cuda.h"
 
 /* Fingerprint object (replaces struct LBAudioDetectiveFingerprint, LBAudioDetectiveFingerprint.m:10-14).

@@ -398,3 +398,70 @@ void lbad_synth_add_noise(uint64_t seed, int64_t n, double amplitude, float* io)
         io[i] = (float)v;
     }
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Recording-rate -> processing-rate conversion.  The reference delegates this to ExtAudioFile's client format
+ * (LBAudioDetective.m:229, m:275 — Apple's converter, closed), so there is nothing of the reference to restate: this is the
+ * scalar restatement of the DEFINITION in include/LBAudioDetectiveResample.h, written from that text (PARITY UNPINNED against
+ * Apple; the CUDA kernel is checked against this bit for bit, and this against scipy / analytic tones in tests/).
+ * ------------------------------------------------------------------------------------------------------------------- */
+static double rs_i0(double x) {
+    double s = 1.0, t = 1.0;
+    for (int k = 1; k < 200; k++) { t *= (0.5 * x / k) * (0.5 * x / k); s += t; if (t < 1e-20 * s) break; }
+    return s;
+}
+static double rs_kaiser(double x, double beta) { return fabs(x) >= 1.0 ? 0.0 : rs_i0(beta * sqrt(1.0 - x * x)) / rs_i0(beta); }
+static double rs_sinc(double x) { return x == 0.0 ? 1.0 : sin(M_PI * x) / (M_PI * x); }
+
+uint64_t lbad_oracle_resampled_length(double in_rate, double out_rate, uint64_t n_in) {
+    return (uint64_t)floor((double)n_in * out_rate / in_rate + 1e-9);
+}
+
+/* out must hold lbad_oracle_resampled_length() samples; returns that count (0 on unsupported rates) */
+uint64_t lbad_oracle_resample(double in_rate, double out_rate, const float* x, int64_t n_in, float* out) {
+    if (!(out_rate > 0.0) || !(in_rate >= out_rate)) return 0;
+    const double rho = in_rate / out_rate;
+    int64_t D = (int64_t)floor(rho / 2.0); if (D < 1) D = 1;
+    const double rho2 = rho / (double)D;
+    const int64_t H1 = 6 * D, T1 = 2 * H1 + 1;
+    float* g = NULL;
+    if (D > 1) {                                                     /* stage-1 taps */
+        g = malloc(T1 * sizeof(float)); double* t = malloc(T1 * sizeof(double)); double sum = 0.0;
+        for (int64_t i = 0; i < T1; i++) { const double u = (double)(i - H1); t[i] = rs_sinc(u / (double)D) / (double)D * rs_kaiser(u / (double)(H1 + 1), 8.0); sum += t[i]; }
+        for (int64_t i = 0; i < T1; i++) g[i] = (float)(t[i] / sum);
+        free(t);
+    }
+    const double gamma = 0.97 / rho2;
+    const int64_t H2 = (int64_t)ceil(10.0 / gamma), T2 = 2 * H2;
+    float* hc = malloc((size_t)(65 * T2) * sizeof(float)); double* row = malloc(T2 * sizeof(double));
+    for (int p = 0; p <= 64; p++) {                                  /* coarse-phase rows of stage 2 */
+        double sum = 0.0;
+        for (int64_t i = 0; i < T2; i++) {
+            const double u = (double)(i - H2 + 1) - (double)p / 64.0;
+            row[i] = fabs(u) < (double)H2 ? gamma * rs_sinc(gamma * u) * rs_kaiser(u / (double)H2, 9.0) : 0.0;
+            sum += row[i];
+        }
+        for (int64_t i = 0; i < T2; i++) hc[(size_t)p * T2 + i] = (float)(row[i] / sum);
+    }
+    free(row);
+    const uint64_t n_out = lbad_oracle_resampled_length(in_rate, out_rate, (uint64_t)n_in);
+    for (uint64_t m = 0; m < n_out; m++) {
+        const double pos = (double)m * rho2, fl = floor(pos), fp = (pos - fl) * 64.0;
+        const int p = (int)fp; const float a = (float)(fp - (double)p);
+        const int64_t i0 = (int64_t)fl;
+        float s0 = 0.0f, s1 = 0.0f;
+        for (int64_t i = 0; i < T2; i++) {
+            const int64_t n = i0 + i - H2 + 1;                       /* index into the stage-1 sequence */
+            float y;
+            if (D > 1) {
+                y = 0.0f;
+                for (int64_t t = 0; t < T1; t++) { const int64_t k = D * n + t - H1; y = fmaf(g[t], (k >= 0 && k < n_in) ? x[k] : 0.0f, y); }
+            } else y = (n >= 0 && n < n_in) ? x[n] : 0.0f;
+            s0 = fmaf(hc[(size_t)p * T2 + i], y, s0);
+            s1 = fmaf(hc[(size_t)(p + 1) * T2 + i], y, s1);
+        }
+        out[m] = fmaf(a, s1 - s0, s0);
+    }
+    free(g); free(hc);
+    return n_out;
+}

@@ -47,6 +47,11 @@ double   lbad_oracle_extract_batch(const lbad_oracle_cfg* c, const float* pcm, u
 double   lbad_oracle_search(const uint8_t* db_bits, uint32_t n_db, uint32_t db_count, const uint8_t* q_bits, uint32_t n_q, uint32_t q_count,
                             uint32_t L, uint32_t range, uint32_t threads, float* scores);
 
+/* recording-rate -> processing-rate conversion as DEFINED in include/LBAudioDetectiveResample.h (the reference leaves it to
+ * ExtAudioFile, m:229 / m:275); out holds lbad_oracle_resampled_length() samples */
+uint64_t lbad_oracle_resampled_length(double in_rate, double out_rate, uint64_t n_in);
+uint64_t lbad_oracle_resample(double in_rate, double out_rate, const float* x, int64_t n_in, float* out);
+
 /* deterministic synthetic PCM: chirp + tone + uniform noise, double arithmetic, f32 out */
 void     lbad_synth_clip(uint64_t base_seed, uint64_t clip_id, int64_t n, double sample_rate, float* out);
 void     lbad_synth_add_noise(uint64_t seed, int64_t n, double amplitude, float* io);

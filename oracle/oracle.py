@@ -69,6 +69,16 @@ class Port:
         L.lbad_oracle_extract_batch.restype = C.c_double
         L.lbad_oracle_search.restype = C.c_double
         L.lbad_oracle_subfp_count.restype = C.c_uint64
+        L.lbad_oracle_resample.restype = C.c_uint64
+        L.lbad_oracle_resampled_length.restype = C.c_uint64
+
+    def resample(self, x, in_rate, out_rate=5512.0):
+        """include/LBAudioDetectiveResample.h, scalar restatement (the reference leaves this step to ExtAudioFile)."""
+        x = _f32(x); n = int(self.lib.lbad_oracle_resampled_length(C.c_double(in_rate), C.c_double(out_rate), C.c_uint64(len(x))))
+        out = np.zeros(n, np.float32)
+        got = self.lib.lbad_oracle_resample(C.c_double(in_rate), C.c_double(out_rate), _p(x, C.c_float), C.c_int64(len(x)), _p(out, C.c_float))
+        assert got == n
+        return out
 
     def band_table(self, cfg, nframes=None):
         B = cfg.bands

@@ -35,6 +35,19 @@ if a.what in ("both", "search"):
     torch.cuda.synchronize()
     assert (ix[:, 0].cpu().numpy() == np.arange(a.queries)).all()
 
+if a.what == "resample":
+    # recording-rate front end: 30 s clips at 44.1 kHz, resampled and fingerprinted on the device
+    d = lb.Detective(); n, L = a.clips, 30 * 44100
+    x = torch.empty((n, L), dtype=torch.float32, device="cuda"); lb.synthesize_device(x.data_ptr(), n, L, L, sample_rate=44100.0, stream=s.cuda_stream)
+    w = torch.zeros((n, 19, 8), dtype=torch.int32, device="cuda")
+    d.process_recorded_batch_device(x.data_ptr(), n, L, L, w.data_ptr(), s.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        d.process_recorded_batch_device(x.data_ptr(), n, L, L, w.data_ptr(), s.cuda_stream)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.reps
+    print("resample + extract: %d clips of 30 s at 44.1 kHz, %.3f ms per pass, %.1f audio-hours/s, %.0f GB/s of recorded PCM" % (n, ms, n * 30.0 / 3600.0 / (ms * 1e-3), n * L * 4 / (ms * 1e-3) / 1e9))
 if a.what == "latency":
     import time
     from oracle.oracle import Port
