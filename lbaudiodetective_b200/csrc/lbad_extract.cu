@@ -537,24 +537,31 @@ constexpr int HS32_LDT = 132;                /* column-major image, imgT[col * 1
 
 /* x / c for a compile-time constant c with r = RN(1/c): multiply + two FMAs give the IEEE quotient for every finite x with
  * |x| >= 2^-100 or x == 0 (exhaustively checked on the host for c = sqrtf(2), sqrtf(32), sqrtf(128)); the rare rest divides. */
-constexpr uint32_t DIVC_LO = 0x0d802b1eu, DIVC_HI = 0x7cf0bdc2u;          /* bit patterns of 7.9e-31f and 1.0e37f */
+constexpr uint32_t DIVC_LO = 0x0d802f51u, DIVC_HI_IMAGE = 0x7c70bdc2u;    /* bit patterns of 7.9e-31f and 1.0e37f / 2 */
 __device__ __forceinline__ float div_const(const float x, const float c, const float r) {
     const float q0 = __fmul_rn(x, r);
     const float q = fmaf(fmaf(-q0, c, x), r, q0);
     const float ax = fabsf(x);
     return ((ax >= 7.9e-31f && ax <= 1.0e37f) || ax == 0.0f) ? q : __fdiv_rn(x, c);
 }
-/* The range of the dividends seen so far, kept as integers: lo = min(|x| bits - 1) (so that zero never counts as small),
- * hi = max(|x| bits).  FAST mode divides by the short form unconditionally and only records the range; the caller checks it once
- * per image (block-wide) and redoes the image with the checked form if anything fell outside — which real spectra never do. */
-struct DivRange { uint32_t lo = 0xffffffffu, hi = 0u; __device__ __forceinline__ bool bad() const { return lo < DIVC_LO - 1u || hi > DIVC_HI; } };
+/* The range of the dividends seen so far, kept as integers: lo = min(|x| bits - 1) over every dividend (so that zero never counts
+ * as small); hi = max(|x| bits) over the IMAGE VALUES only — every dividend of the transform is a sum or difference of two values
+ * that are themselves bounded by the largest image value M (each level divides by sqrt 2 what the previous one at most doubled, and
+ * the leading divisions by sqrt 32 / sqrt 128 undo the five / seven levels), so |dividend| <= 2 M and M <= 1e37 / 2 is enough.
+ * FAST mode divides by the short form unconditionally and only records the range; the caller checks it once per image (block-wide)
+ * and redoes the image with the checked form if anything fell outside — which real spectra never do. */
+struct DivRange {
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    __device__ __forceinline__ void image_value(const float x) { hi = max(hi, __float_as_uint(x) & 0x7fffffffu); }
+    __device__ __forceinline__ bool bad() const { return lo < DIVC_LO - 1u || hi > DIVC_HI_IMAGE; }
+};
 template <bool FAST>
 __device__ __forceinline__ float div_c(const float x, const float c, const float r, DivRange& rg) {
     if constexpr (!FAST) return div_const(x, c, r);
     else {
         const float q0 = __fmul_rn(x, r);
         const uint32_t u = __float_as_uint(x) & 0x7fffffffu;
-        rg.lo = min(rg.lo, u - 1u); rg.hi = max(rg.hi, u);
+        rg.lo = min(rg.lo, u - 1u);
         return fmaf(fmaf(-q0, c, x), r, q0);
     }
 }
@@ -620,7 +627,7 @@ __device__ __forceinline__ void haar32_rows(const float* __restrict__ img, float
 #pragma unroll
     for (int j = 0; j < 4; j++) { const float4 v = __ldg(src + j); x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
 #pragma unroll
-    for (int j = 0; j < 16; j++) x[j] = div_c<FAST>(x[j], s32, r32, rg);                   /* Frame.m:137-139 */
+    for (int j = 0; j < 16; j++) { if constexpr (FAST) rg.image_value(x[j]); x[j] = div_c<FAST>(x[j], s32, r32, rg); }   /* Frame.m:137-139 */
     haar16<FAST>(x, d1, d2, d3, d4, s4, s2, r2, rg);
     const float other = __shfl_xor_sync(0xffffffffu, s4, 1);                                /* level 5 joins the two halves */
     const float top = half ? div_c<FAST>(__fsub_rn(other, s4), s2, r2, rg) : div_c<FAST>(__fadd_rn(s4, other), s2, r2, rg);

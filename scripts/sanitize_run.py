@@ -18,5 +18,13 @@ db = lb.Database(200); db.add_packed(w)
 sc, idx, full = db.search_packed(w[:, 1:5], k=2, all_scores=True)      # generic (cq = 4 -> fast), masked below
 sc2, idx2 = db.search_packed(w[:, :6], k=3, rng=77)
 sc3, idx3 = db.search_packed(np.concatenate([w[:1], w[:1]], axis=1)[:, :9], k=2)   # query longer than the clips -> generic kernel
+# Haar/select register kernel incl. its checked-division and tie paths; recording-rate front end (D = 4 fast path and a generic rate)
+rng = np.random.default_rng(3)
+imgs = np.concatenate([(rng.random((2, 128, 32)) ** 4 * 50).astype(np.float32), (rng.random((1, 128, 32)) * 1e-36).astype(np.float32),
+                       rng.integers(0, 3, size=(1, 128, 32)).astype(np.float32)])
+th, tb = d.transform_images(imgs)
+hi = p.synth_clip(9, 3 * 44100, 44100.0)
+r1 = d.resample(hi); fr = d.process_recorded_pcm(hi)
+d3 = lb.Detective(); d3.set_recording_rate(16000.0); r2 = d3.resample(p.synth_clip(9, 2 * 16000, 16000.0))
 f0 = lb.Fingerprint(200); f0.add_packed(w[0]); f1 = lb.Fingerprint(200); f1.add_packed(w[1])
-print("ok", w.shape, (bits != bits2).sum(), b3.shape, sc[:, 0], f0.compare(f1, 200), lb.merge_topk(np.stack([sc, sc]), np.stack([idx, idx + 10]))[1][0])
+print("ok", tb.shape, r1.shape, r2.shape, fr.count, w.shape, (bits != bits2).sum(), b3.shape, sc[:, 0], f0.compare(f1, 200), lb.merge_topk(np.stack([sc, sc]), np.stack([idx, idx + 10]))[1][0])
