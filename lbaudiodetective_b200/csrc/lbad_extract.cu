@@ -8,15 +8,15 @@
  *   2-D standard Haar                 LBAudioDetectiveFrame.m:113-153
  *   ordered top-t sign bits           LBAudioDetectiveFrame.m:165-191, truncation LBAudioDetective.m:321-328
  *
- * Two paths:
- *   fused   (window 2048, 32 bands, even hop, frame span fits shared memory): ONE kernel, persistent CTAs, one frame
- *           (= one subfingerprint) per CTA iteration.  The frame's 127*hop+2048 samples are brought into shared
- *           memory once by a 1-D TMA bulk copy (cp.async.bulk + mbarrier), so every PCM sample is read from HBM
- *           once; each warp runs a 2048-point real FFT per window entirely in registers (2 x radix-32 with one
- *           shared-memory transpose), bins the bands, and the CTA then does Haar + top-t + packing in shared
- *           memory and writes 2*W words.
- *   generic (any supported geometry): bands kernel (one warp per window, shared-memory radix-2 FFT) -> images in
- *           global memory -> Haar/select kernel (one CTA per frame).  Also the on-device cross-check of the fused path.
+ * Two paths, each two kernels (spectral images in between, 16 KB per subfingerprint, L2-friendly):
+ *   fast    (window 2048/1024/512/256, 32 bands, even hop, frame span fits shared memory):
+ *           bands_fused_kernel — persistent CTAs, one frame (= one subfingerprint) per CTA iteration.  The frame's 127*hop+window
+ *           samples are brought into shared memory once by a 1-D TMA bulk copy (cp.async.bulk + mbarrier), so every PCM sample is
+ *           read from HBM once; each warp runs the real FFT of a window entirely in registers (2 x radix-32 decimation in time with
+ *           one shared-memory transpose; at hop 64 the first pass is shared between consecutive windows) and bins the bands.
+ *           haar_select32_kernel — one CTA per image: warp-local Haar, radix selection of the t-th magnitude, ranking, packing.
+ *   generic (any supported geometry): bands_generic_kernel (one warp per window, shared-memory radix-2 FFT) and
+ *           haar_select_kernel<B>.  Also the on-device cross-check of the fast path (the two FFTs are independent implementations).
  */
 #include "lbad_common.cuh"
 #include "lbad_math.cuh"
@@ -610,7 +610,7 @@ struct Select32Smem {
     __align__(16) uint32_t surv_key[256];
     uint32_t surv_idx[256];                  /* flat index | sign code << 16 (bit 16: v > 0, bit 17: v < 0) */
     uint32_t words[16];
-    uint32_t nsurv, nbucket, threshold, expo, above, n_gt, n_eq, rank_sum;
+    uint32_t nsurv, nbucket, expo, above, rank_sum;
     uint32_t steps[16];
 };
 

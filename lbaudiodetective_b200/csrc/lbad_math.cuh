@@ -16,8 +16,10 @@
  *   pass 2: 32-point DFT over n2 -> Z[k1 + 32 k2] in lane k1
  *   split : 2 X[k] = (Z[k] + conj Z[1024-k]) - i exp(-2 pi i k / 2048) (Z[k] - conj Z[1024-k])
  * which is vDSP_fft_zrip's output convention (x2, e^{-i theta}) as the reference consumes it (LBAudioDetective.m:353-355).
- * The in-register 32-point DFT is a fully unrolled radix-2 DIF; register position p ends up holding output
- * index bitrev5(p), and callers account for that permutation at compile time.
+ * The in-register 32-point DFT is a fully unrolled radix-2 decimation in time with Linzer-Feig (FMA-fused) butterflies; the input is
+ * read in natural order, register position p ends up holding output index bitrev5(p), and callers account for that permutation at
+ * compile time.  At the reference's hop of 64 samples pass 1 is further split into two 16-point halves of which one is carried over
+ * from the previous window (dft16 / dit32_combine below).
  */
 #ifndef LBAD_MATH_CUH
 #define LBAD_MATH_CUH
