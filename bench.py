@@ -163,6 +163,7 @@ def main():
     except Exception:
         pass
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line and nothing else (NCCL_DEBUG=VERSION/INFO would print there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lb.load_library(build_if_missing=False)          # the bench must run the in-tree CUDA library, never a fallback
     if not lb.device_available():
@@ -310,6 +311,15 @@ def main():
                   "queries": args.queries, "db_clips": args.db_clips, "k": 10, "scaling": "strong", "workload": "configs[3]: 1,000 x 6-subfp queries vs 1M x 19-subfp clips, 14 offsets",
                   "gpu_launches": db.kernel_launches}
 
+    if search is not None and rank == 0 and "popc_gops_measured" in roofline:
+        # the search is POPC-bound — 4 POPC per compare (one per 32-pair word) against the measured lane-POPC rate;
+        # HBM only sees the database once per 128 queries
+        per_gpu = search["kernel_compares_per_s_per_gpu"]
+        bound = roofline["popc_gops_measured"] * 1e9 / 4.0
+        db_bytes = (args.db_clips / world) * SUBFPS * (32 + 8)
+        search["roofline"] = {"bound": "int-pipe (POPC)", "achieved": per_gpu, "peak": bound, "unit": "compares/s per GPU", "frac": per_gpu / bound,
+                              "note": "peak = measured lane-POPC rate / 4 POPC per compare; the kernel needs 3 (carry-save adder), so frac can exceed 1",
+                              "hbm_gbs": db_bytes * ((args.queries + 127) // 128) / (search["kernel_ms"] * 1e-3) / 1e9, "hbm_frac": db_bytes * ((args.queries + 127) // 128) / (search["kernel_ms"] * 1e-3) / 1e9 / hbm_peak}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -176,7 +176,10 @@ def test_config5_sweep_against_golden(lb, sweep):
 
 def test_other_geometry_against_oracle(lb, checker):
     cases = [dict(window=256, stride=64), dict(stride=128, sample_rate=8000.0), dict(bands=16, sublen=64), dict(stride=50), dict(bands=64, sublen=512),
-             dict(stride=2), dict(window=1024, stride=1000)]
+             dict(stride=2), dict(window=1024, stride=1000),
+             # window 2048 at hop 64 with other band tables: the carried-transform kernel with run-time band rows (rows above 23, rows below 2,
+             # rows needed only as mirror images)
+             dict(sample_rate=6000.0), dict(sample_rate=4100.0), dict(sample_rate=4800.0), dict(sample_rate=8000.0), dict(sample_rate=22050.0)]
     mism = total = 0
     for kw in cases:
         cfg = Cfg.default(**kw); d = lb.Detective()
