@@ -216,6 +216,22 @@ def test_edge_cases(lb, port):
     assert st == lb.ARGUMENT_INVALID
 
 
+def test_non_finite_samples_against_oracle(lb, checker):
+    """A NaN or Inf sample poisons every window that contains it: all of that window's bins are non-finite, are skipped (m:398-401,
+    SURVEY.md Q6) and its image row is zero; the other windows are untouched.  Same bits as the oracle."""
+    cfg = Cfg.default(); d = lb.Detective()
+    pcm = checker.synth_clip(70, 55120).copy()
+    pcm[12345] = np.nan; pcm[30000] = np.inf; pcm[30001] = -np.inf
+    want = checker.process(cfg, pcm)
+    got = d.process_pcm(pcm).booleans()
+    assert got.shape == want.shape
+    assert (got != want).mean() <= BIT_MISMATCH_BUDGET
+    img, _, _ = d.process_stages(pcm, fused=True)
+    first = (12345 - 2048) // 64 + 1; last = 12345 // 64                     # windows containing sample 12345
+    rows = img.reshape(-1, 32)
+    assert (rows[first:last + 1] == 0).all() and (rows[first - 1] != 0).any() and (rows[last + 1] != 0).any()
+
+
 def test_batch_equals_single(lb, port):
     d = lb.Detective()
     pcm = np.stack([port.synth_clip(70 + i, 55120) for i in range(5)])
