@@ -268,6 +268,333 @@ haar_select_kernel(const float* __restrict__ images, float* __restrict__ haar_ou
     }
 }
 
+/* ------------------------------------------------------------------------------------- Haar + select, 128 x 32 ---- */
+
+/* One CTA per spectral image (128 x 32): Haar rows + columns (Frame.m:113-153), ordered top-T and packing (Frame.m:165-191).
+ * The Haar transform is warp-local — every level runs in registers or through warp shuffles — so the whole image needs ONE block
+ * barrier (between the row and the column pass); the coefficients never go back to shared memory: each thread keeps its 16 and
+ * the selection works on registers.  About 27 KB of shared memory and 64 registers: four CTAs per SM hide each other's barriers. */
+constexpr int HS32_THREADS = 256;
+constexpr int HS32_LDT = 132;                /* column-major image, imgT[col * 132 + row]: LDS.128-aligned and conflict-free */
+
+/* x / c for a compile-time constant c with r = RN(1/c): multiply + two FMAs give the IEEE quotient for every finite x with
+ * |x| >= 2^-100 or x == 0 (exhaustively checked on the host for c = sqrtf(2), sqrtf(32), sqrtf(128)); the rare rest divides. */
+constexpr uint32_t DIVC_LO = 0x0d802f51u, DIVC_HI_IMAGE = 0x7c70bdc2u;    /* bit patterns of 7.9e-31f and 1.0e37f / 2 */
+__device__ __forceinline__ float div_const(const float x, const float c, const float r) {
+    const float q0 = __fmul_rn(x, r);
+    const float q = fmaf(fmaf(-q0, c, x), r, q0);
+    const float ax = fabsf(x);
+    return ((ax >= 7.9e-31f && ax <= 1.0e37f) || ax == 0.0f) ? q : __fdiv_rn(x, c);
+}
+/* The range of the dividends seen so far, kept as integers: lo = min(|x| bits - 1) over every dividend (so that zero never counts
+ * as small); hi = max(|x| bits) over the IMAGE VALUES only — every dividend of the transform is a sum or difference of two values
+ * that are themselves bounded by the largest image value M (each level divides by sqrt 2 what the previous one at most doubled, and
+ * the leading divisions by sqrt 32 / sqrt 128 undo the five / seven levels), so |dividend| <= 2 M and M <= 1e37 / 2 is enough.
+ * FAST mode divides by the short form unconditionally and only records the range; the caller checks it once per image (block-wide)
+ * and redoes the image with the checked form if anything fell outside — which real spectra never do. */
+struct DivRange {
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    __device__ __forceinline__ void image_value(const float x) { hi = max(hi, __float_as_uint(x) & 0x7fffffffu); }
+    __device__ __forceinline__ bool bad() const { return lo < DIVC_LO - 1u || hi > DIVC_HI_IMAGE; }
+};
+template <bool FAST>
+__device__ __forceinline__ float div_c(const float x, const float c, const float r, DivRange& rg) {
+    if constexpr (!FAST) return div_const(x, c, r);
+    else {
+        const float q0 = __fmul_rn(x, r);
+        const uint32_t u = __float_as_uint(x) & 0x7fffffffu;
+        rg.lo = min(rg.lo, u - 1u);
+        return fmaf(fmaf(-q0, c, x), r, q0);
+    }
+}
+
+/* four levels of the ordered Haar pyramid (Frame.m:143-152) on 16 consecutive elements held in registers:
+ * d1[i] = level-1 difference of pair i (8), d2 (4), d3 (2), d4 (1) and the remaining sum s4 */
+template <bool FAST>
+__device__ __forceinline__ void haar16(const float (&x)[16], float (&d1)[8], float (&d2)[4], float (&d3)[2], float& d4, float& s4,
+                                       const float s2, const float r2, DivRange& rg) {
+    float s1[8], t2[4], t3[2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { s1[i] = div_c<FAST>(__fadd_rn(x[2 * i], x[2 * i + 1]), s2, r2, rg); d1[i] = div_c<FAST>(__fsub_rn(x[2 * i], x[2 * i + 1]), s2, r2, rg); }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { t2[i] = div_c<FAST>(__fadd_rn(s1[2 * i], s1[2 * i + 1]), s2, r2, rg); d2[i] = div_c<FAST>(__fsub_rn(s1[2 * i], s1[2 * i + 1]), s2, r2, rg); }
+#pragma unroll
+    for (int i = 0; i < 2; i++) { t3[i] = div_c<FAST>(__fadd_rn(t2[2 * i], t2[2 * i + 1]), s2, r2, rg); d3[i] = div_c<FAST>(__fsub_rn(t2[2 * i], t2[2 * i + 1]), s2, r2, rg); }
+    s4 = div_c<FAST>(__fadd_rn(t3[0], t3[1]), s2, r2, rg);
+    d4 = div_c<FAST>(__fsub_rn(t3[0], t3[1]), s2, r2, rg);
+}
+
+/* Suffix search in a 256-bin histogram, done redundantly by every warp (no broadcast, no barrier): bin = the largest b with
+ * S[b] = sum_{j >= b} hist[j] >= need, above = S[b + 1], count = hist[b].  Requires 1 <= need <= S[0]. */
+__device__ __forceinline__ void warp_find_bin256(const uint32_t* __restrict__ hist, const uint32_t need, uint32_t& bin, uint32_t& above, uint32_t& count) {
+    const int lane = threadIdx.x & 31;
+    const uint4 a = *reinterpret_cast<const uint4*>(hist + 8 * lane), b = *reinterpret_cast<const uint4*>(hist + 8 * lane + 4);
+    const uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const uint32_t tot = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
+    uint32_t suf = tot;                                      /* inclusive suffix over the lanes */
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_down_sync(0xffffffffu, suf, d); if (lane + d < 32) suf += o; }
+    uint32_t run = suf - tot, mybin = 0, myabove = 0, mycount = 0;
+    const bool here = suf >= need && run < need;             /* true in exactly one lane */
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+        if (run < need && run + c[j] >= need) { mybin = 8u * lane + j; myabove = run; mycount = c[j]; }
+        run += c[j];
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
+    bin = __shfl_sync(0xffffffffu, mybin, src); above = __shfl_sync(0xffffffffu, myabove, src); count = __shfl_sync(0xffffffffu, mycount, src);
+}
+
+struct Select32Smem {
+    uint32_t hist[HS32_THREADS / 32][256];   /* per-warp histograms of the 8 exponent bits */
+    __align__(16) uint32_t digit_hist[3][256];   /* mantissa bits 22..15, 14..7, 6..0 of the keys that are still candidates for the threshold */
+    uint32_t warp_tot[HS32_THREADS / 32];
+    __align__(16) uint32_t surv_key[256];
+    uint32_t surv_idx[256];                  /* flat index | sign code << 16 (bit 16: v > 0, bit 17: v < 0) */
+    uint32_t words[16];
+    uint32_t nsurv, nbucket, expo, above, rank_sum;
+    uint32_t steps[16];
+};
+
+/* Rows (length 32, Frame.m:114-116) of one 128 x 32 image into the column-major tile imgT, with the column pass's leading division
+ * by sqrtf(128) (Frame.m:137-139) folded into the store: warp w owns rows 16w..16w+15, two lanes per row, 16 elements each. */
+template <bool FAST, int SRC_LD>     /* SRC_LD = 0: img is in global memory (rows of 32 floats); otherwise a shared-memory image with rows SRC_LD floats apart */
+__device__ __forceinline__ void haar32_rows(const float* __restrict__ img, float* __restrict__ imgT, DivRange& rg) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float s2 = sqrtf(2.0f), s32 = sqrtf(32.0f), s128 = sqrtf(128.0f);
+    const float r2 = 1.0f / s2, r32 = 1.0f / s32, r128 = 1.0f / s128;
+    const int row = 16 * wid + (lane >> 1), half = lane & 1;
+    const float4* src = reinterpret_cast<const float4*>(img + (size_t)row * (SRC_LD ? SRC_LD : 32) + half * 16);
+    float x[16], d1[8], d2[4], d3[2], d4, s4;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const float4 v = SRC_LD ? src[j] : __ldg(src + j); x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
+#pragma unroll
+    for (int j = 0; j < 16; j++) { if constexpr (FAST) rg.image_value(x[j]); x[j] = div_c<FAST>(x[j], s32, r32, rg); }   /* Frame.m:137-139 */
+    haar16<FAST>(x, d1, d2, d3, d4, s4, s2, r2, rg);
+    const float other = __shfl_xor_sync(0xffffffffu, s4, 1);                                /* level 5 joins the two halves */
+    const float top = half ? div_c<FAST>(__fsub_rn(other, s4), s2, r2, rg) : div_c<FAST>(__fadd_rn(s4, other), s2, r2, rg);
+    float* dst = imgT + row;                                                                /* ordered output positions */
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[(16 + 8 * half + i) * HS32_LDT] = div_c<FAST>(d1[i], s128, r128, rg);
+#pragma unroll
+    for (int i = 0; i < 4; i++) dst[(8 + 4 * half + i) * HS32_LDT] = div_c<FAST>(d2[i], s128, r128, rg);
+#pragma unroll
+    for (int i = 0; i < 2; i++) dst[(4 + 2 * half + i) * HS32_LDT] = div_c<FAST>(d3[i], s128, r128, rg);
+    dst[(2 + half) * HS32_LDT] = div_c<FAST>(d4, s128, r128, rg);
+    dst[half * HS32_LDT] = div_c<FAST>(top, s128, r128, rg);
+}
+
+/* Columns (length 128, Frame.m:118-131): warp w owns columns 4w..4w+3, eight lanes per column, 16 rows each; four levels in
+ * registers and three by shuffles.  The thread keeps its 16 coefficients (coef), whose flat indices are given by haar32_flat_idx. */
+template <bool FAST>
+__device__ __forceinline__ void haar32_cols(const float* __restrict__ imgT, float (&coef)[16], DivRange& rg) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const float s2 = sqrtf(2.0f), r2 = 1.0f / s2;
+    const int cl = lane & 3, g = lane >> 2, col = 4 * wid + cl;
+    float x[16], d1[8], d2[4], d3[2], d4, s4;
+    const float4* src = reinterpret_cast<const float4*>(imgT + col * HS32_LDT + 16 * g);
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const float4 v = src[j]; x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
+    haar16<FAST>(x, d1, d2, d3, d4, s4, s2, r2, rg);
+    /* levels 5-7 across the eight lanes of the column: the lane with the lower g keeps the sum, the other the difference */
+    float p = __shfl_xor_sync(0xffffffffu, s4, 4);
+    const float s5 = div_c<FAST>(__fadd_rn(s4, p), s2, r2, rg), d5 = div_c<FAST>(__fsub_rn(p, s4), s2, r2, rg);
+    p = __shfl_xor_sync(0xffffffffu, s5, 8);
+    const float s6 = div_c<FAST>(__fadd_rn(s5, p), s2, r2, rg), d6 = div_c<FAST>(__fsub_rn(p, s5), s2, r2, rg);
+    p = __shfl_xor_sync(0xffffffffu, s6, 16);
+    const float s7 = div_c<FAST>(__fadd_rn(s6, p), s2, r2, rg), d7 = div_c<FAST>(__fsub_rn(p, s6), s2, r2, rg);
+#pragma unroll
+    for (int i = 0; i < 8; i++) coef[i] = d1[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) coef[8 + i] = d2[i];
+    coef[12] = d3[0]; coef[13] = d3[1]; coef[14] = d4;
+    coef[15] = (g & 1) ? d5 : (g & 2) ? d6 : (g & 4) ? d7 : s7;
+}
+
+/* One spectral image (128 x 32) by the 256 threads of a CTA: Haar rows + columns (Frame.m:113-153), ordered top-T and packing
+ * (Frame.m:165-191); writes the 2 W packed words of the subfingerprint to `words`.  The Haar transform is warp-local — every level
+ * runs in registers or through warp shuffles — so the image needs ONE block barrier (between the row and the column pass); the
+ * coefficients never go back to shared memory: each thread keeps its 16 and the selection works on registers.  imgT (32 x HS32_LDT
+ * floats, 16-byte aligned) and sm are the caller's shared memory; the call ends with a block barrier after the last use of both. */
+template <int SRC_LD>
+__device__ __forceinline__ void haar_select32_image(const float* __restrict__ img, float* __restrict__ imgT, Select32Smem& sm,
+                                                    float* __restrict__ haar_out, uint32_t* __restrict__ words, const int T, const int W) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t* bucket = reinterpret_cast<uint32_t*>(imgT);     /* imgT doubles as the bucket of undecided keys once the columns are in registers */
+    const int T4 = (T + 3) & ~3;
+    float coef[16];
+    uint32_t key[16];
+    DivRange rg;
+    haar32_rows<true, SRC_LD>(img, imgT, rg);
+    __syncthreads();
+    haar32_cols<true>(imgT, coef, rg);
+    auto histogram = [&]() {                             /* per-warp histograms of the exponents of my 16 keys */
+#pragma unroll
+        for (int e = 0; e < 16; e++) key[e] = __float_as_uint(coef[e]) & 0x7fffffffu;
+#pragma unroll
+        for (int j = 0; j < 8; j++) sm.hist[wid][lane + 32 * j] = 0;
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 16; e++) atomicAdd(&sm.hist[wid][key[e] >> 23], 1u);
+    };
+    histogram();
+    if (tid < 16) sm.words[tid] = 0;
+    if (tid == 0) { sm.nsurv = 0; sm.nbucket = 0; sm.rank_sum = 0; }
+#pragma unroll
+    for (int j = 0; j < 3; j++) sm.digit_hist[j][tid] = 0;
+    for (int i = T + tid; i < T4; i += HS32_THREADS) sm.surv_key[i] = 0;     /* padding of the 128-bit loads of the ranking */
+    if (__syncthreads_or(rg.bad())) {                    /* a dividend outside the range of the short division: redo the image with checked divisions */
+        haar32_rows<false, SRC_LD>(img, imgT, rg);
+        __syncthreads();
+        haar32_cols<false>(imgT, coef, rg);
+        histogram();
+        __syncthreads();
+    }
+    /* from here on every warp has read its columns: imgT may become the bucket */
+    const int cl = lane & 3, g = lane >> 2, col = 4 * wid + cl;
+    /* row position of each of my coefficients in the ordered output (flat index = 32 * position + column) */
+    const uint32_t pos_last = (g & 1) ? 4 + (g >> 1) : (g & 2) ? 2 + (g >> 2) : (g & 4) ? 1 : 0;
+    auto flat_idx = [&](int e) -> uint32_t {
+        const uint32_t pos = e < 8 ? 64 + 8 * g + e : e < 12 ? 32 + 4 * g + (e - 8) : e < 14 ? 16 + 2 * g + (e - 12) : e == 14 ? 8 + g : pos_last;
+        return pos * 32 + col;
+    };
+    if (haar_out) {
+        float* o = haar_out;
+#pragma unroll
+        for (int e = 0; e < 16; e++) o[flat_idx(e)] = coef[e];
+    }
+
+    /* ---- ordered top-T (Frame.m:165-191): threshold = T-th largest |v| as an integer key ---- */
+    {
+        /* thread t owns exponent bin t: suffix sums S[t] = #keys with exponent >= t; the threshold's exponent is the largest t with S[t] >= T */
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < HS32_THREADS / 32; w++) tot += sm.hist[w][tid];
+        uint32_t suf = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_down_sync(0xffffffffu, suf, d); if (lane + d < 32) suf += o; }
+        if (lane == 0) sm.warp_tot[wid] = suf;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < HS32_THREADS / 32; w++) if (w > wid) suf += sm.warp_tot[w];
+        if (suf >= (uint32_t)T && suf - tot < (uint32_t)T) { sm.expo = (uint32_t)tid; sm.above = suf - tot; }
+    }
+    __syncthreads();
+    const uint32_t expo = sm.expo;
+    {
+        /* compact the keys that share the threshold's exponent: only their mantissas are still undecided */
+        uint32_t mine = 0;
+#pragma unroll
+        for (int e = 0; e < 16; e++) mine += (key[e] >> 23) == expo;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        uint32_t base = 0;
+        if (lane == 31 && incl) base = atomicAdd(&sm.nbucket, incl);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+        for (int e = 0; e < 16; e++) if ((key[e] >> 23) == expo) bucket[base++] = key[e];
+    }
+    __syncthreads();
+    /* the remaining 23 bits of the threshold, 8 + 8 + 7 at a time: all threads histogram the digit of the bucket keys that still
+     * match, then EVERY warp finds the digit's bin for itself — three short phases instead of a 23-step bisection by one warp */
+    const uint32_t nb = sm.nbucket;
+    uint32_t need = (uint32_t)T - sm.above, thr = expo << 23, n_eq;           /* need: rank of the threshold among the candidates, >= 1 */
+    {
+        uint32_t d, above;
+        for (uint32_t i = tid; i < nb; i += HS32_THREADS) atomicAdd(&sm.digit_hist[0][(bucket[i] >> 15) & 255u], 1u);
+        __syncthreads();
+        warp_find_bin256(sm.digit_hist[0], need, d, above, n_eq);
+        thr |= d << 15; need -= above;
+        for (uint32_t i = tid; i < nb; i += HS32_THREADS) { const uint32_t k = bucket[i]; if ((k >> 15) == (thr >> 15)) atomicAdd(&sm.digit_hist[1][(k >> 7) & 255u], 1u); }
+        __syncthreads();
+        warp_find_bin256(sm.digit_hist[1], need, d, above, n_eq);
+        thr |= d << 7; need -= above;
+        for (uint32_t i = tid; i < nb; i += HS32_THREADS) { const uint32_t k = bucket[i]; if ((k >> 7) == (thr >> 7)) atomicAdd(&sm.digit_hist[2][k & 127u], 1u); }
+        __syncthreads();
+        warp_find_bin256(sm.digit_hist[2], need, d, above, n_eq);
+        thr |= d; need -= above;
+    }
+    /* keys above the threshold all survive; of the n_eq equal to it, the first need_eq in flat-index order (Q9) */
+    const uint32_t need_eq = need;
+    uint32_t cut = 0xffffffffu;
+    if (n_eq > need_eq) {                                                      /* block-uniform; rare (exact magnitude ties at the threshold) */
+        /* smallest cut with #(ties with flat index < cut) >= need_eq, by bisection on the 13 index bits */
+        if (tid < 16) sm.steps[tid] = 0;
+        __syncthreads();
+        uint32_t m = 0;
+        for (int bit = 12; bit >= 0; --bit) {
+            const uint32_t cand = m | (1u << bit);
+            uint32_t c = 0;
+#pragma unroll
+            for (int e = 0; e < 16; e++) c += (key[e] == thr && flat_idx(e) < cand) ? 1u : 0u;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0 && c) atomicAdd(&sm.steps[bit], c);
+            __syncthreads();
+            if (sm.steps[bit] < need_eq) m = cand;
+        }
+        cut = m + 1;
+    }
+    /* survivors take a slot each (any order: their rank is computed below from key and index) */
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        if (key[e] >= thr) {
+            if (key[e] > thr || flat_idx(e) < cut) {
+                const uint32_t slot = atomicAdd(&sm.nsurv, 1u);
+                if (slot < 256u) {
+                    sm.surv_key[slot] = key[e];
+                    sm.surv_idx[slot] = flat_idx(e) | ((coef[e] > 0.0f ? 1u : 0u) << 16) | ((coef[e] < 0.0f ? 1u : 0u) << 17);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    /* rank by counting.  Fast form: rank = #keys greater than mine, four keys per 128-bit load; it is a permutation exactly when
+     * no two survivors have equal keys, which the sum of the ranks tells (ties share the lower rank, so the sum falls short). */
+    uint32_t my_rank = 0, my_is = 0;
+    if (tid < T) {
+        const uint32_t ks = sm.surv_key[tid];
+        my_is = sm.surv_idx[tid];
+        for (int j = 0; j < T4; j += 4) {
+            const uint4 k4 = *reinterpret_cast<const uint4*>(&sm.surv_key[j]);
+            my_rank += (k4.x > ks) + (k4.y > ks) + (k4.z > ks) + (k4.w > ks);
+        }
+    }
+    {
+        const uint32_t rs = __reduce_add_sync(0xffffffffu, my_rank);
+        if (lane == 0 && rs) atomicAdd(&sm.rank_sum, rs);
+    }
+    __syncthreads();
+    if (sm.rank_sum != (uint32_t)(T * (T - 1) / 2)) {                         /* equal keys among the survivors: the index breaks the tie (Q9) */
+        if (tid < T) {
+            const uint32_t ks = sm.surv_key[tid], idx = my_is & 0xffffu;
+            my_rank = 0;
+            for (int j = 0; j < T; j++) {
+                const uint32_t kj = sm.surv_key[j], ij = sm.surv_idx[j] & 0xffffu;
+                my_rank += (kj > ks || (kj == ks && ij < idx)) ? 1u : 0u;
+            }
+        }
+    }
+    if (tid < T) {
+        if (my_is & (1u << 16)) atomicOr(&sm.words[my_rank >> 5], 1u << (my_rank & 31));
+        if (my_is & (1u << 17)) atomicOr(&sm.words[W + (my_rank >> 5)], 1u << (my_rank & 31));
+    }
+    __syncthreads();
+    if (tid < 2 * W) words[tid] = sm.words[tid];
+    __syncthreads();
+}
+
+/* One CTA per spectral image; about 30 KB of shared memory and 64 registers: four CTAs per SM hide each other's barriers. */
+__global__ void __launch_bounds__(HS32_THREADS, 4)
+haar_select32_kernel(const float* __restrict__ images, float* __restrict__ haar_out, uint32_t* __restrict__ words,
+                     const int T, const int W, const uint32_t total_frames) {
+    __shared__ __align__(16) float imgT[32 * HS32_LDT];
+    __shared__ Select32Smem sm;
+    for (uint32_t f = blockIdx.x; f < total_frames; f += gridDim.x)
+        haar_select32_image<0>(images + (size_t)f * LBAD_ROWS_PER_FRAME * 32, imgT, sm, haar_out ? haar_out + (size_t)f * LBAD_ROWS_PER_FRAME * 32 : nullptr,
+                               words + (size_t)f * 2 * W, T, W);
+}
+
 /* -------------------------------------------------------------------------------------------- fused path ---- */
 
 /* sum of v[a..b) with four interleaved partial sums */
@@ -523,327 +850,6 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
         __syncthreads();                                                        /* every warp is done with the samples */
         const uint32_t fnext = f + gridDim.x;
         if (use_tma && tid == 0 && fnext < total_frames) { mbar_arrive_expect_tx(bar, bytes); bulk_copy_g2s(samples, frame_src(fnext), bytes, bar); }
-    }
-}
-
-/* ------------------------------------------------------------------------------------- Haar + select, 128 x 32 ---- */
-
-/* One CTA per spectral image (128 x 32): Haar rows + columns (Frame.m:113-153), ordered top-T and packing (Frame.m:165-191).
- * The Haar transform is warp-local — every level runs in registers or through warp shuffles — so the whole image needs ONE block
- * barrier (between the row and the column pass); the coefficients never go back to shared memory: each thread keeps its 16 and
- * the selection works on registers.  About 27 KB of shared memory and 64 registers: four CTAs per SM hide each other's barriers. */
-constexpr int HS32_THREADS = 256;
-constexpr int HS32_LDT = 132;                /* column-major image, imgT[col * 132 + row]: LDS.128-aligned and conflict-free */
-
-/* x / c for a compile-time constant c with r = RN(1/c): multiply + two FMAs give the IEEE quotient for every finite x with
- * |x| >= 2^-100 or x == 0 (exhaustively checked on the host for c = sqrtf(2), sqrtf(32), sqrtf(128)); the rare rest divides. */
-constexpr uint32_t DIVC_LO = 0x0d802f51u, DIVC_HI_IMAGE = 0x7c70bdc2u;    /* bit patterns of 7.9e-31f and 1.0e37f / 2 */
-__device__ __forceinline__ float div_const(const float x, const float c, const float r) {
-    const float q0 = __fmul_rn(x, r);
-    const float q = fmaf(fmaf(-q0, c, x), r, q0);
-    const float ax = fabsf(x);
-    return ((ax >= 7.9e-31f && ax <= 1.0e37f) || ax == 0.0f) ? q : __fdiv_rn(x, c);
-}
-/* The range of the dividends seen so far, kept as integers: lo = min(|x| bits - 1) over every dividend (so that zero never counts
- * as small); hi = max(|x| bits) over the IMAGE VALUES only — every dividend of the transform is a sum or difference of two values
- * that are themselves bounded by the largest image value M (each level divides by sqrt 2 what the previous one at most doubled, and
- * the leading divisions by sqrt 32 / sqrt 128 undo the five / seven levels), so |dividend| <= 2 M and M <= 1e37 / 2 is enough.
- * FAST mode divides by the short form unconditionally and only records the range; the caller checks it once per image (block-wide)
- * and redoes the image with the checked form if anything fell outside — which real spectra never do. */
-struct DivRange {
-    uint32_t lo = 0xffffffffu, hi = 0u;
-    __device__ __forceinline__ void image_value(const float x) { hi = max(hi, __float_as_uint(x) & 0x7fffffffu); }
-    __device__ __forceinline__ bool bad() const { return lo < DIVC_LO - 1u || hi > DIVC_HI_IMAGE; }
-};
-template <bool FAST>
-__device__ __forceinline__ float div_c(const float x, const float c, const float r, DivRange& rg) {
-    if constexpr (!FAST) return div_const(x, c, r);
-    else {
-        const float q0 = __fmul_rn(x, r);
-        const uint32_t u = __float_as_uint(x) & 0x7fffffffu;
-        rg.lo = min(rg.lo, u - 1u);
-        return fmaf(fmaf(-q0, c, x), r, q0);
-    }
-}
-
-/* four levels of the ordered Haar pyramid (Frame.m:143-152) on 16 consecutive elements held in registers:
- * d1[i] = level-1 difference of pair i (8), d2 (4), d3 (2), d4 (1) and the remaining sum s4 */
-template <bool FAST>
-__device__ __forceinline__ void haar16(const float (&x)[16], float (&d1)[8], float (&d2)[4], float (&d3)[2], float& d4, float& s4,
-                                       const float s2, const float r2, DivRange& rg) {
-    float s1[8], t2[4], t3[2];
-#pragma unroll
-    for (int i = 0; i < 8; i++) { s1[i] = div_c<FAST>(__fadd_rn(x[2 * i], x[2 * i + 1]), s2, r2, rg); d1[i] = div_c<FAST>(__fsub_rn(x[2 * i], x[2 * i + 1]), s2, r2, rg); }
-#pragma unroll
-    for (int i = 0; i < 4; i++) { t2[i] = div_c<FAST>(__fadd_rn(s1[2 * i], s1[2 * i + 1]), s2, r2, rg); d2[i] = div_c<FAST>(__fsub_rn(s1[2 * i], s1[2 * i + 1]), s2, r2, rg); }
-#pragma unroll
-    for (int i = 0; i < 2; i++) { t3[i] = div_c<FAST>(__fadd_rn(t2[2 * i], t2[2 * i + 1]), s2, r2, rg); d3[i] = div_c<FAST>(__fsub_rn(t2[2 * i], t2[2 * i + 1]), s2, r2, rg); }
-    s4 = div_c<FAST>(__fadd_rn(t3[0], t3[1]), s2, r2, rg);
-    d4 = div_c<FAST>(__fsub_rn(t3[0], t3[1]), s2, r2, rg);
-}
-
-/* Suffix search in a 256-bin histogram, done redundantly by every warp (no broadcast, no barrier): bin = the largest b with
- * S[b] = sum_{j >= b} hist[j] >= need, above = S[b + 1], count = hist[b].  Requires 1 <= need <= S[0]. */
-__device__ __forceinline__ void warp_find_bin256(const uint32_t* __restrict__ hist, const uint32_t need, uint32_t& bin, uint32_t& above, uint32_t& count) {
-    const int lane = threadIdx.x & 31;
-    const uint4 a = *reinterpret_cast<const uint4*>(hist + 8 * lane), b = *reinterpret_cast<const uint4*>(hist + 8 * lane + 4);
-    const uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    const uint32_t tot = ((c[0] + c[1]) + (c[2] + c[3])) + ((c[4] + c[5]) + (c[6] + c[7]));
-    uint32_t suf = tot;                                      /* inclusive suffix over the lanes */
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_down_sync(0xffffffffu, suf, d); if (lane + d < 32) suf += o; }
-    uint32_t run = suf - tot, mybin = 0, myabove = 0, mycount = 0;
-    const bool here = suf >= need && run < need;             /* true in exactly one lane */
-#pragma unroll
-    for (int j = 7; j >= 0; --j) {
-        if (run < need && run + c[j] >= need) { mybin = 8u * lane + j; myabove = run; mycount = c[j]; }
-        run += c[j];
-    }
-    const int src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
-    bin = __shfl_sync(0xffffffffu, mybin, src); above = __shfl_sync(0xffffffffu, myabove, src); count = __shfl_sync(0xffffffffu, mycount, src);
-}
-
-struct Select32Smem {
-    uint32_t hist[HS32_THREADS / 32][256];   /* per-warp histograms of the 8 exponent bits */
-    __align__(16) uint32_t digit_hist[3][256];   /* mantissa bits 22..15, 14..7, 6..0 of the keys that are still candidates for the threshold */
-    uint32_t warp_tot[HS32_THREADS / 32];
-    __align__(16) uint32_t surv_key[256];
-    uint32_t surv_idx[256];                  /* flat index | sign code << 16 (bit 16: v > 0, bit 17: v < 0) */
-    uint32_t words[16];
-    uint32_t nsurv, nbucket, expo, above, rank_sum;
-    uint32_t steps[16];
-};
-
-/* Rows (length 32, Frame.m:114-116) of one 128 x 32 image into the column-major tile imgT, with the column pass's leading division
- * by sqrtf(128) (Frame.m:137-139) folded into the store: warp w owns rows 16w..16w+15, two lanes per row, 16 elements each. */
-template <bool FAST>
-__device__ __forceinline__ void haar32_rows(const float* __restrict__ img, float* __restrict__ imgT, DivRange& rg) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const float s2 = sqrtf(2.0f), s32 = sqrtf(32.0f), s128 = sqrtf(128.0f);
-    const float r2 = 1.0f / s2, r32 = 1.0f / s32, r128 = 1.0f / s128;
-    const int row = 16 * wid + (lane >> 1), half = lane & 1;
-    const float4* src = reinterpret_cast<const float4*>(img + (size_t)row * 32 + half * 16);
-    float x[16], d1[8], d2[4], d3[2], d4, s4;
-#pragma unroll
-    for (int j = 0; j < 4; j++) { const float4 v = __ldg(src + j); x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
-#pragma unroll
-    for (int j = 0; j < 16; j++) { if constexpr (FAST) rg.image_value(x[j]); x[j] = div_c<FAST>(x[j], s32, r32, rg); }   /* Frame.m:137-139 */
-    haar16<FAST>(x, d1, d2, d3, d4, s4, s2, r2, rg);
-    const float other = __shfl_xor_sync(0xffffffffu, s4, 1);                                /* level 5 joins the two halves */
-    const float top = half ? div_c<FAST>(__fsub_rn(other, s4), s2, r2, rg) : div_c<FAST>(__fadd_rn(s4, other), s2, r2, rg);
-    float* dst = imgT + row;                                                                /* ordered output positions */
-#pragma unroll
-    for (int i = 0; i < 8; i++) dst[(16 + 8 * half + i) * HS32_LDT] = div_c<FAST>(d1[i], s128, r128, rg);
-#pragma unroll
-    for (int i = 0; i < 4; i++) dst[(8 + 4 * half + i) * HS32_LDT] = div_c<FAST>(d2[i], s128, r128, rg);
-#pragma unroll
-    for (int i = 0; i < 2; i++) dst[(4 + 2 * half + i) * HS32_LDT] = div_c<FAST>(d3[i], s128, r128, rg);
-    dst[(2 + half) * HS32_LDT] = div_c<FAST>(d4, s128, r128, rg);
-    dst[half * HS32_LDT] = div_c<FAST>(top, s128, r128, rg);
-}
-
-/* Columns (length 128, Frame.m:118-131): warp w owns columns 4w..4w+3, eight lanes per column, 16 rows each; four levels in
- * registers and three by shuffles.  The thread keeps its 16 coefficients (coef), whose flat indices are given by haar32_flat_idx. */
-template <bool FAST>
-__device__ __forceinline__ void haar32_cols(const float* __restrict__ imgT, float (&coef)[16], DivRange& rg) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const float s2 = sqrtf(2.0f), r2 = 1.0f / s2;
-    const int cl = lane & 3, g = lane >> 2, col = 4 * wid + cl;
-    float x[16], d1[8], d2[4], d3[2], d4, s4;
-    const float4* src = reinterpret_cast<const float4*>(imgT + col * HS32_LDT + 16 * g);
-#pragma unroll
-    for (int j = 0; j < 4; j++) { const float4 v = src[j]; x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w; }
-    haar16<FAST>(x, d1, d2, d3, d4, s4, s2, r2, rg);
-    /* levels 5-7 across the eight lanes of the column: the lane with the lower g keeps the sum, the other the difference */
-    float p = __shfl_xor_sync(0xffffffffu, s4, 4);
-    const float s5 = div_c<FAST>(__fadd_rn(s4, p), s2, r2, rg), d5 = div_c<FAST>(__fsub_rn(p, s4), s2, r2, rg);
-    p = __shfl_xor_sync(0xffffffffu, s5, 8);
-    const float s6 = div_c<FAST>(__fadd_rn(s5, p), s2, r2, rg), d6 = div_c<FAST>(__fsub_rn(p, s5), s2, r2, rg);
-    p = __shfl_xor_sync(0xffffffffu, s6, 16);
-    const float s7 = div_c<FAST>(__fadd_rn(s6, p), s2, r2, rg), d7 = div_c<FAST>(__fsub_rn(p, s6), s2, r2, rg);
-#pragma unroll
-    for (int i = 0; i < 8; i++) coef[i] = d1[i];
-#pragma unroll
-    for (int i = 0; i < 4; i++) coef[8 + i] = d2[i];
-    coef[12] = d3[0]; coef[13] = d3[1]; coef[14] = d4;
-    coef[15] = (g & 1) ? d5 : (g & 2) ? d6 : (g & 4) ? d7 : s7;
-}
-
-/* One CTA per spectral image (128 x 32): Haar rows + columns (Frame.m:113-153), ordered top-T and packing (Frame.m:165-191).
- * The Haar transform is warp-local — every level runs in registers or through warp shuffles — so the whole image needs ONE block
- * barrier (between the row and the column pass); the coefficients never go back to shared memory: each thread keeps its 16 and
- * the selection works on registers.  About 27 KB of shared memory and 64 registers: four CTAs per SM hide each other's barriers. */
-__global__ void __launch_bounds__(HS32_THREADS, 4)
-haar_select32_kernel(const float* __restrict__ images, float* __restrict__ haar_out, uint32_t* __restrict__ words,
-                     const int T, const int W, const uint32_t total_frames) {
-    __shared__ __align__(16) float imgT[32 * HS32_LDT];      /* also the bucket of undecided keys once the columns are in registers */
-    __shared__ Select32Smem sm;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    uint32_t* bucket = reinterpret_cast<uint32_t*>(imgT);
-    const int T4 = (T + 3) & ~3;
-
-    for (uint32_t f = blockIdx.x; f < total_frames; f += gridDim.x) {
-        const float* img = images + (size_t)f * LBAD_ROWS_PER_FRAME * 32;
-        float coef[16];
-        uint32_t key[16];
-        DivRange rg;
-        haar32_rows<true>(img, imgT, rg);
-        __syncthreads();
-        haar32_cols<true>(imgT, coef, rg);
-        auto histogram = [&]() {                             /* per-warp histograms of the exponents of my 16 keys */
-#pragma unroll
-            for (int e = 0; e < 16; e++) key[e] = __float_as_uint(coef[e]) & 0x7fffffffu;
-#pragma unroll
-            for (int j = 0; j < 8; j++) sm.hist[wid][lane + 32 * j] = 0;
-            __syncwarp();
-#pragma unroll
-            for (int e = 0; e < 16; e++) atomicAdd(&sm.hist[wid][key[e] >> 23], 1u);
-        };
-        histogram();
-        if (tid < 16) sm.words[tid] = 0;
-        if (tid == 0) { sm.nsurv = 0; sm.nbucket = 0; sm.rank_sum = 0; }
-#pragma unroll
-        for (int j = 0; j < 3; j++) sm.digit_hist[j][tid] = 0;
-        for (int i = T + tid; i < T4; i += HS32_THREADS) sm.surv_key[i] = 0;     /* padding of the 128-bit loads of the ranking */
-        if (__syncthreads_or(rg.bad())) {                    /* a dividend outside the range of the short division: redo the image with checked divisions */
-            haar32_rows<false>(img, imgT, rg);
-            __syncthreads();
-            haar32_cols<false>(imgT, coef, rg);
-            histogram();
-            __syncthreads();
-        }
-        /* from here on every warp has read its columns: imgT may become the bucket */
-        const int cl = lane & 3, g = lane >> 2, col = 4 * wid + cl;
-        /* row position of each of my coefficients in the ordered output (flat index = 32 * position + column) */
-        const uint32_t pos_last = (g & 1) ? 4 + (g >> 1) : (g & 2) ? 2 + (g >> 2) : (g & 4) ? 1 : 0;
-        auto flat_idx = [&](int e) -> uint32_t {
-            const uint32_t pos = e < 8 ? 64 + 8 * g + e : e < 12 ? 32 + 4 * g + (e - 8) : e < 14 ? 16 + 2 * g + (e - 12) : e == 14 ? 8 + g : pos_last;
-            return pos * 32 + col;
-        };
-        if (haar_out) {
-            float* o = haar_out + (size_t)f * LBAD_ROWS_PER_FRAME * 32;
-#pragma unroll
-            for (int e = 0; e < 16; e++) o[flat_idx(e)] = coef[e];
-        }
-
-        /* ---- ordered top-T (Frame.m:165-191): threshold = T-th largest |v| as an integer key ---- */
-        {
-            /* thread t owns exponent bin t: suffix sums S[t] = #keys with exponent >= t; the threshold's exponent is the largest t with S[t] >= T */
-            uint32_t tot = 0;
-#pragma unroll
-            for (int w = 0; w < HS32_THREADS / 32; w++) tot += sm.hist[w][tid];
-            uint32_t suf = tot;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_down_sync(0xffffffffu, suf, d); if (lane + d < 32) suf += o; }
-            if (lane == 0) sm.warp_tot[wid] = suf;
-            __syncthreads();
-#pragma unroll
-            for (int w = 0; w < HS32_THREADS / 32; w++) if (w > wid) suf += sm.warp_tot[w];
-            if (suf >= (uint32_t)T && suf - tot < (uint32_t)T) { sm.expo = (uint32_t)tid; sm.above = suf - tot; }
-        }
-        __syncthreads();
-        const uint32_t expo = sm.expo;
-        {
-            /* compact the keys that share the threshold's exponent: only their mantissas are still undecided */
-            uint32_t mine = 0;
-#pragma unroll
-            for (int e = 0; e < 16; e++) mine += (key[e] >> 23) == expo;
-            uint32_t incl = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-            uint32_t base = 0;
-            if (lane == 31 && incl) base = atomicAdd(&sm.nbucket, incl);
-            base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
-#pragma unroll
-            for (int e = 0; e < 16; e++) if ((key[e] >> 23) == expo) bucket[base++] = key[e];
-        }
-        __syncthreads();
-        /* the remaining 23 bits of the threshold, 8 + 8 + 7 at a time: all threads histogram the digit of the bucket keys that still
-         * match, then EVERY warp finds the digit's bin for itself — three short phases instead of a 23-step bisection by one warp */
-        const uint32_t nb = sm.nbucket;
-        uint32_t need = (uint32_t)T - sm.above, thr = expo << 23, n_eq;           /* need: rank of the threshold among the candidates, >= 1 */
-        {
-            uint32_t d, above;
-            for (uint32_t i = tid; i < nb; i += HS32_THREADS) atomicAdd(&sm.digit_hist[0][(bucket[i] >> 15) & 255u], 1u);
-            __syncthreads();
-            warp_find_bin256(sm.digit_hist[0], need, d, above, n_eq);
-            thr |= d << 15; need -= above;
-            for (uint32_t i = tid; i < nb; i += HS32_THREADS) { const uint32_t k = bucket[i]; if ((k >> 15) == (thr >> 15)) atomicAdd(&sm.digit_hist[1][(k >> 7) & 255u], 1u); }
-            __syncthreads();
-            warp_find_bin256(sm.digit_hist[1], need, d, above, n_eq);
-            thr |= d << 7; need -= above;
-            for (uint32_t i = tid; i < nb; i += HS32_THREADS) { const uint32_t k = bucket[i]; if ((k >> 7) == (thr >> 7)) atomicAdd(&sm.digit_hist[2][k & 127u], 1u); }
-            __syncthreads();
-            warp_find_bin256(sm.digit_hist[2], need, d, above, n_eq);
-            thr |= d; need -= above;
-        }
-        /* keys above the threshold all survive; of the n_eq equal to it, the first need_eq in flat-index order (Q9) */
-        const uint32_t need_eq = need;
-        uint32_t cut = 0xffffffffu;
-        if (n_eq > need_eq) {                                                      /* block-uniform; rare (exact magnitude ties at the threshold) */
-            /* smallest cut with #(ties with flat index < cut) >= need_eq, by bisection on the 13 index bits */
-            if (tid < 16) sm.steps[tid] = 0;
-            __syncthreads();
-            uint32_t m = 0;
-            for (int bit = 12; bit >= 0; --bit) {
-                const uint32_t cand = m | (1u << bit);
-                uint32_t c = 0;
-#pragma unroll
-                for (int e = 0; e < 16; e++) c += (key[e] == thr && flat_idx(e) < cand) ? 1u : 0u;
-                c = __reduce_add_sync(0xffffffffu, c);
-                if (lane == 0 && c) atomicAdd(&sm.steps[bit], c);
-                __syncthreads();
-                if (sm.steps[bit] < need_eq) m = cand;
-            }
-            cut = m + 1;
-        }
-        /* survivors take a slot each (any order: their rank is computed below from key and index) */
-#pragma unroll
-        for (int e = 0; e < 16; e++) {
-            if (key[e] >= thr) {
-                if (key[e] > thr || flat_idx(e) < cut) {
-                    const uint32_t slot = atomicAdd(&sm.nsurv, 1u);
-                    if (slot < 256u) {
-                        sm.surv_key[slot] = key[e];
-                        sm.surv_idx[slot] = flat_idx(e) | ((coef[e] > 0.0f ? 1u : 0u) << 16) | ((coef[e] < 0.0f ? 1u : 0u) << 17);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        /* rank by counting.  Fast form: rank = #keys greater than mine, four keys per 128-bit load; it is a permutation exactly when
-         * no two survivors have equal keys, which the sum of the ranks tells (ties share the lower rank, so the sum falls short). */
-        uint32_t my_rank = 0, my_is = 0;
-        if (tid < T) {
-            const uint32_t ks = sm.surv_key[tid];
-            my_is = sm.surv_idx[tid];
-            for (int j = 0; j < T4; j += 4) {
-                const uint4 k4 = *reinterpret_cast<const uint4*>(&sm.surv_key[j]);
-                my_rank += (k4.x > ks) + (k4.y > ks) + (k4.z > ks) + (k4.w > ks);
-            }
-        }
-        {
-            const uint32_t rs = __reduce_add_sync(0xffffffffu, my_rank);
-            if (lane == 0 && rs) atomicAdd(&sm.rank_sum, rs);
-        }
-        __syncthreads();
-        if (sm.rank_sum != (uint32_t)(T * (T - 1) / 2)) {                         /* equal keys among the survivors: the index breaks the tie (Q9) */
-            if (tid < T) {
-                const uint32_t ks = sm.surv_key[tid], idx = my_is & 0xffffu;
-                my_rank = 0;
-                for (int j = 0; j < T; j++) {
-                    const uint32_t kj = sm.surv_key[j], ij = sm.surv_idx[j] & 0xffffu;
-                    my_rank += (kj > ks || (kj == ks && ij < idx)) ? 1u : 0u;
-                }
-            }
-        }
-        if (tid < T) {
-            if (my_is & (1u << 16)) atomicOr(&sm.words[my_rank >> 5], 1u << (my_rank & 31));
-            if (my_is & (1u << 17)) atomicOr(&sm.words[W + (my_rank >> 5)], 1u << (my_rank & 31));
-        }
-        __syncthreads();
-        if (tid < 2 * W) words[(size_t)f * 2 * W + tid] = sm.words[tid];
-        __syncthreads();
     }
 }
 
