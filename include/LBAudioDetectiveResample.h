@@ -13,7 +13,8 @@
  *             m rho2 = i0 + phi (i0 integer, 0 <= phi < 1),  p = floor(64 phi),  a = 64 phi - p,
  *             Hc[p][i] = gamma sinc(gamma u) kaiser_9(u / H2) for |u| < H2 (else 0),  u = i - H2 + 1 - p / 64,
  *             gamma = 0.97 / rho2,  H2 = ceil(10 / gamma);  every row normalised to sum 1
- *   tables in double rounded once to float32; sums are float32 FMA chains in increasing tap order; m rho2 in double;
+ *   tables in double rounded once to float32; sums are float32 FMA chains — stage 2 in increasing tap order, stage 1 in polyphase order
+ *   (t = p, p + D, p + 2 D, ... for p = 0 .. D - 1, the order in which a de-interleaved input is consumed); m rho2 in double;
  *   outFrames = floor(inFrames * outRate / inRate + 1e-9).
  * For 44.1 kHz -> 5512 Hz: D = 4 (49 taps), rho2 = 2.00018, 42 taps.  The cutoff sits at 0.97 of the output Nyquist because the band
  * table only reads 231-2043 Hz: the response is flat there (error <= 1.2e-3 at 2043 Hz) and everything that could alias

@@ -20,6 +20,7 @@ struct ResampleParams {
     double rho2;
     uint64_t in_len, in_stride, out_len, out_stride;
     uint32_t tiles_per_clip, ny_max, nx_max;
+    uint32_t nip, xs_floats;         /* D = 4: floats per polyphase plane of the staged input; floats reserved for the staged input */
 };
 
 /* The stage-1 taps for D = 4 depend on nothing but D (sinc((t - 24) / 4) / 4 under a Kaiser window), so one constant copy serves every
@@ -36,7 +37,7 @@ resample_kernel(const float* __restrict__ in, float* __restrict__ out, const flo
                 const uint64_t total_tiles, const int vec_ok) {
     extern __shared__ __align__(16) float rs_smem[];
     float* xs = rs_smem;                                       /* [nx_max], 16-byte aligned */
-    float* y1s = xs + ((P.nx_max + 3) & ~3u);                  /* [ny_max + 4] */
+    float* y1s = xs + P.xs_floats;                             /* [ny_max + 4] */
     float* gs = y1s + ((P.ny_max + 4 + 3) & ~3u);              /* [T1] */
     float* hcs = gs + ((P.T1 + 3) & ~3u);                      /* [PHASES + 1][T2P], rows padded to T2P = a multiple of 4 floats (zeros) */
     const uint32_t T2 = T2C ? (uint32_t)T2C : P.T2;
@@ -55,30 +56,43 @@ resample_kernel(const float* __restrict__ in, float* __restrict__ out, const flo
         __syncthreads();                                        /* the previous tile's readers are done with the shared tiles (first pass: the tables are in place) */
         if (P.D > 1) {
             const int64_t x_lo = (int64_t)P.D * y_lo - (int64_t)P.H1;
-            const uint32_t nx = P.D * (ny - 1) + P.T1, nx4 = (nx + 3) & ~3u;
-            if (D4 && vec_ok && x_lo >= 0 && (uint64_t)x_lo + nx4 <= P.in_len) {       /* interior tile, x_lo is a multiple of 4 */
-                const float4* s4 = reinterpret_cast<const float4*>(src + x_lo);
-                float4* d4 = reinterpret_cast<float4*>(xs);
-                for (uint32_t i = tid; i < nx4 / 4; i += RS_THREADS) d4[i] = __ldg(s4 + i);
+            const uint32_t nx = P.D * (ny - 1) + P.T1;
+            if constexpr (D4) {
+                /* the input tile is staged de-interleaved into its four polyphase planes xp[p][i] = x[x_lo + 4 i + p] (x_lo is a multiple
+                 * of 4): a thread then produces FOUR consecutive stage-1 outputs from four 128-bit loads per plane, 16 loads for 196 FMAs,
+                 * instead of 13 loads per output — stage 1 was bound by shared-memory wavefronts */
+                const uint32_t ni = (nx + 3) / 4, nip = P.nip;                              /* plane length used / allocated (multiple of 4 floats, >= ny_max + 16) */
+                if (vec_ok && x_lo >= 0 && (uint64_t)x_lo + 4ull * ni <= P.in_len) {
+                    const float4* s4 = reinterpret_cast<const float4*>(src + x_lo);
+                    for (uint32_t i = tid; i < ni; i += RS_THREADS) { const float4 v = __ldg(s4 + i); xs[i] = v.x; xs[nip + i] = v.y; xs[2 * nip + i] = v.z; xs[3 * nip + i] = v.w; }
+                } else {
+                    for (uint32_t i = tid; i < 4 * ni; i += RS_THREADS) { const int64_t k = x_lo + i; xs[(i & 3) * nip + (i >> 2)] = (k >= 0 && (uint64_t)k < P.in_len) ? __ldg(src + k) : 0.0f; }
+                }
+                __syncthreads();
+                for (uint32_t j0 = 4 * tid; j0 < ny; j0 += 4 * RS_THREADS) {             /* stage 1: outputs j0 .. j0 + 3 */
+                    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+                    for (int pl = 0; pl < 4; pl++) {
+                        const float4* x4 = reinterpret_cast<const float4*>(xs + pl * nip) + (j0 >> 2);
+                        const float4 q0 = x4[0], q1 = x4[1], q2 = x4[2], q3 = x4[3];
+                        const float v[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+                        for (int m = 0; m < (pl == 0 ? 13 : 12); m++) {                   /* tap t = 4 m + pl multiplies plane sample (output + m) */
+                            const float c = c_g_d4[4 * m + pl];
+                            a0 = fmaf(c, v[m], a0); a1 = fmaf(c, v[m + 1], a1); a2 = fmaf(c, v[m + 2], a2); a3 = fmaf(c, v[m + 3], a3);
+                        }
+                    }
+                    *reinterpret_cast<float4*>(y1s + j0) = make_float4(a0, a1, a2, a3);    /* y1s has room for the up to three outputs past ny */
+                }
             } else {
                 for (uint32_t i = tid; i < nx; i += RS_THREADS) { const int64_t k = x_lo + i; xs[i] = (k >= 0 && (uint64_t)k < P.in_len) ? __ldg(src + k) : 0.0f; }
-            }
-            __syncthreads();
-            for (uint32_t j = tid; j < ny; j += RS_THREADS) {   /* stage 1 */
-                float acc = 0.0f;
-                if constexpr (D4) {
-                    const float4* x4 = reinterpret_cast<const float4*>(xs) + j;
-#pragma unroll
-                    for (int q = 0; q < 12; q++) {
-                        const float4 v = x4[q];
-                        acc = fmaf(c_g_d4[4 * q], v.x, acc); acc = fmaf(c_g_d4[4 * q + 1], v.y, acc); acc = fmaf(c_g_d4[4 * q + 2], v.z, acc); acc = fmaf(c_g_d4[4 * q + 3], v.w, acc);
-                    }
-                    acc = fmaf(c_g_d4[48], xs[4 * j + 48], acc);
-                } else {
+                __syncthreads();
+                for (uint32_t j = tid; j < ny; j += RS_THREADS) {   /* stage 1, taps in polyphase order: p outer, t = D m + p */
+                    float acc = 0.0f;
                     const float* x = xs + (size_t)P.D * j;
-                    for (uint32_t t = 0; t < P.T1; t++) acc = fmaf(gs[t], x[t], acc);
+                    for (uint32_t pl = 0; pl < P.D; pl++) for (uint32_t t = pl; t < P.T1; t += P.D) acc = fmaf(gs[t], x[t], acc);
+                    y1s[j] = acc;
                 }
-                y1s[j] = acc;
             }
         } else {
             for (uint32_t i = tid; i < ny; i += RS_THREADS) { const int64_t k = y_lo + i; y1s[i] = (k >= 0 && (uint64_t)k < P.in_len) ? __ldg(src + k) : 0.0f; }
@@ -145,9 +159,11 @@ extern "C" int lbadcu_resampler_create(const lbadcu_resample_design* d, lbadcu_r
     P.D = d->D; P.H1 = d->H1; P.T1 = d->D > 1 ? d->T1 : 0; P.H2 = d->H2; P.T2 = d->T2; P.rho2 = d->rho2;
     P.ny_max = (uint32_t)floor(RS_THREADS * d->rho2) + 2 * d->H2 + 2;
     P.nx_max = d->D > 1 ? d->D * (P.ny_max - 1) + d->T1 : 0;
+    P.nip = (P.nx_max / 4 + 8) & ~3u;
+    P.xs_floats = (d->D == 4 && d->T1 == 49) ? 4 * P.nip : ((P.nx_max + 3) & ~3u);
     const size_t nhc = (size_t)(RS_PHASES + 1) * d->T2;
     /* shared layout: input tile, stage-1 tile (+4: the 64-bit sample loads of stage 2 may read up to three floats past it), taps, padded coarse-phase rows */
-    r->smem_base = (((size_t)P.nx_max + 3) & ~3u) + (((size_t)P.ny_max + 4 + 3) & ~3u) + (((size_t)P.T1 + 3) & ~3u) + (size_t)(RS_PHASES + 1) * ((d->T2 + 3) & ~3u);
+    r->smem_base = (size_t)P.xs_floats + (((size_t)P.ny_max + 4 + 3) & ~3u) + (((size_t)P.T1 + 3) & ~3u) + (size_t)(RS_PHASES + 1) * ((d->T2 + 3) & ~3u);
     if (r->smem_base * sizeof(float) > prop.sharedMemPerBlockOptin) { delete r; set_error("resampler: the filters for this rate pair do not fit in shared memory"); return LBAD_ERR_ARG; }
     LBAD_CUDA_TRY(cudaMalloc(&r->d_hc, nhc * sizeof(float)));
     LBAD_CUDA_TRY(cudaMemcpy(r->d_hc, d->hc, nhc * sizeof(float), cudaMemcpyHostToDevice));

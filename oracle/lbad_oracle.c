@@ -454,8 +454,9 @@ uint64_t lbad_oracle_resample(double in_rate, double out_rate, const float* x, i
             const int64_t n = i0 + i - H2 + 1;                       /* index into the stage-1 sequence */
             float y;
             if (D > 1) {
-                y = 0.0f;
-                for (int64_t t = 0; t < T1; t++) { const int64_t k = D * n + t - H1; y = fmaf(g[t], (k >= 0 && k < n_in) ? x[k] : 0.0f, y); }
+                y = 0.0f;                                            /* taps in polyphase order: t = p, p + D, p + 2 D, ... for p = 0 .. D - 1 */
+                for (int64_t p = 0; p < D; p++)
+                    for (int64_t t = p; t < T1; t += D) { const int64_t k = D * n + t - H1; y = fmaf(g[t], (k >= 0 && k < n_in) ? x[k] : 0.0f, y); }
             } else y = (n >= 0 && n < n_in) ? x[n] : 0.0f;
             s0 = fmaf(hc[(size_t)p * T2 + i], y, s0);
             s1 = fmaf(hc[(size_t)(p + 1) * T2 + i], y, s1);
