@@ -25,6 +25,8 @@
 #include <string.h>
 #include <stdlib.h>
 #include <vector>
+#include <mutex>
+#include <utility>
 
 namespace lbad {
 
@@ -39,6 +41,7 @@ void set_error(const char* fmt, ...) {
 struct BandTable {                       /* by-value kernel parameter */
     uint32_t klow[LBAD_MAX_BANDS];
     uint32_t khigh[LBAD_MAX_BANDS];
+    uint32_t split[LBAD_MAX_BANDS];      /* register-FFT kernel: the two lanes of band b sum [klow, split) and [split, khigh) */
     float    divisor[LBAD_MAX_BANDS];
 };
 
@@ -667,8 +670,8 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
     uint32_t ra0, rb0, ra1, rb1;
     {
         const int b0 = lane >> 1, b1 = 16 + (lane >> 1);
-        const uint32_t l0 = bt.klow[b0], h0 = bt.khigh[b0], m0 = l0 + (h0 - l0 + 1) / 2;
-        const uint32_t l1 = bt.klow[b1], h1 = bt.khigh[b1], m1 = l1 + (h1 - l1 + 1) / 2;
+        const uint32_t l0 = bt.klow[b0], h0 = bt.khigh[b0], m0 = bt.split[b0];
+        const uint32_t l1 = bt.klow[b1], h1 = bt.khigh[b1], m1 = bt.split[b1];
         ra0 = (lane & 1) ? m0 : l0; rb0 = (lane & 1) ? h0 : m0;
         ra1 = (lane & 1) ? m1 : l1; rb1 = (lane & 1) ? h1 : m1;
     }
@@ -890,6 +893,49 @@ extern "C" int lbadcu_device_available(void) {
 
 static uint32_t ilog2(uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l; }
 
+/* Where the two lanes of a band split it.  In round r (bands 16 r .. 16 r + 15) step i of the band sums has lane (b, h) read the
+ * energy at start(b, h) + i; the shared-memory wavefronts of that instruction are the largest number of lanes whose addresses share
+ * a bank.  With every band cut in the middle the 34 loads of the reference-default table take 77 wavefronts; moving the cuts (both
+ * parts still at most lmax long) so that fewer starts coincide mod 32 brings them to about 50.  Deterministic annealing, some
+ * milliseconds, once per plan. */
+static uint32_t band_sum_wavefronts(const uint32_t* lo, const uint32_t* hi, const uint32_t* split, int r, uint32_t lmax) {
+    uint32_t total = 0;
+    for (uint32_t i = 0; i < lmax; i++) {
+        uint32_t cnt[32] = {0}, worst = 0;
+        for (int b = 16 * r; b < 16 * r + 16; b++) {
+            if (i < split[b] - lo[b]) { const uint32_t c = ++cnt[(lo[b] + i) & 31]; worst = c > worst ? c : worst; }
+            if (i < hi[b] - split[b]) { const uint32_t c = ++cnt[(split[b] + i) & 31]; worst = c > worst ? c : worst; }
+        }
+        total += worst;
+    }
+    return total;
+}
+static void optimise_band_splits(const uint32_t* lo, const uint32_t* hi, uint32_t* split, const uint32_t lmax0, const uint32_t lmax1) {
+    for (int r = 0; r < 2; r++) {
+        const uint32_t lmax = r ? lmax1 : lmax0;
+        uint32_t cur[32], best[32];
+        for (int b = 0; b < 32; b++) cur[b] = best[b] = split[b];
+        uint32_t cw = band_sum_wavefronts(lo, hi, cur, r, lmax), bw = cw;
+        uint64_t rng = 0x9E3779B97F4A7C15ull + (uint64_t)r;
+        double T = 2.0;
+        for (int it = 0; it < 40000; it++) {
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+            const int b = 16 * r + (int)((rng >> 33) % 16);
+            const uint32_t smin = hi[b] > lo[b] + lmax ? hi[b] - lmax : lo[b], smax = lo[b] + lmax < hi[b] ? lo[b] + lmax : hi[b];
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+            const uint32_t s = smin + (uint32_t)((rng >> 33) % (smax - smin + 1)), old = cur[b];
+            cur[b] = s;
+            const uint32_t w = band_sum_wavefronts(lo, hi, cur, r, lmax);
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+            const double u = (double)(rng >> 11) * (1.0 / 9007199254740992.0);
+            if (w <= cw || u < exp(((double)cw - (double)w) / T)) cw = w; else cur[b] = old;
+            if (cw < bw) { bw = cw; for (int k = 16 * r; k < 16 * r + 16; k++) best[k] = cur[k]; }
+            T = T * 0.9999 > 0.05 ? T * 0.9999 : 0.05;
+        }
+        for (int b = 16 * r; b < 16 * r + 16; b++) split[b] = best[b];
+    }
+}
+
 extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out) {
     *out = nullptr;
     if (lbadcu_device_available() != LBAD_OK) { set_error("no CUDA device available (this library has no CPU fallback)"); return LBAD_ERR_NODEVICE; }
@@ -942,9 +988,23 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     LBAD_CUDA_TRY(cudaMemcpy(p->d_tw1, tw1.data(), sizeof(float4) * 512, cudaMemcpyHostToDevice));
     LBAD_CUDA_TRY(cudaMemcpy(p->d_tw2, tw2.data(), sizeof(float4) * 512, cudaMemcpyHostToDevice));
     p->static_range = N == 2048 && (kmin >> 5) == 2 && ((kmax - 1) >> 5) == 23;
+    for (uint32_t b = 0; b < LBAD_MAX_BANDS; b++) p->bt.split[b] = p->bt.klow[b] + (p->bt.khigh[b] - p->bt.klow[b] + 1) / 2;
     for (uint32_t b = 0; b < B && b < 32; b++) {
         const uint32_t half = (geo->khigh[b] - geo->klow[b] + 1) / 2;
         if (half > (uint32_t)(b < 16 ? STATIC_HALF0 : STATIC_HALF1)) p->static_range = false;
+    }
+    if (p->static_range && B == 32) {                                             /* (the run-time-range variants sum with plain loops: any cut would do, the middle stays) */
+        static std::mutex cache_mutex; static std::vector<std::pair<std::vector<uint32_t>, std::vector<uint32_t>>> cache;      /* band table -> cuts */
+        std::vector<uint32_t> key(p->bt.klow, p->bt.klow + 32); key.insert(key.end(), p->bt.khigh, p->bt.khigh + 32);
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        const std::vector<uint32_t>* hit = nullptr;
+        for (auto& e : cache) if (e.first == key) hit = &e.second;
+        if (!hit) {
+            std::vector<uint32_t> sp(p->bt.split, p->bt.split + 32);
+            optimise_band_splits(p->bt.klow, p->bt.khigh, sp.data(), STATIC_HALF0, STATIC_HALF1);
+            cache.emplace_back(key, sp); hit = &cache.back().second;
+        }
+        for (int b = 0; b < 32; b++) p->bt.split[b] = (*hit)[b];
     }
     /* fused path: window 2048, 32 bands, even hop, frame span fits in shared memory */
     const uint64_t span = 127ull * geo->stride + N;
