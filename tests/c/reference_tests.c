@@ -8,6 +8,8 @@
  *   testFingerprintingWithBlurredBirds    (suffix _blu1/_blu2 : crop + 1.58 % / 3.16 % noise)            -> asserted here
  *   testFingerprintVersatility            Tests.m:119-139                                                -> asserted
  *   testFingerprintComparison             Tests.m:141-155                                                -> asserted
+ *   (addition) the same identification from 44.1 kHz PCM, the rate of the bundled recordings, through the recording-rate entry
+ *   points that stand in for ExtAudioFile's client-format conversion (LBAudioDetective.m:229)             -> asserted
  *
  * Build: cc -std=gnu11 -Iinclude tests/c/reference_tests.c -Llbaudiodetective_b200 -lLBAudioDetectiveCUDA -lm
  * Exit status 0 = all assertions hold; 77 = no CUDA device (skipped).
@@ -17,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "LBAudioDetective.h"
+#include "LBAudioDetectiveResample.h"
 #include "LBAudioDetectiveSupport.h"
 
 #define BIRDS 10
@@ -27,17 +30,19 @@
 static unsigned long long rng_state;
 static double rnd(void) { rng_state = rng_state * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(rng_state >> 40) / 16777216.0; }
 
-/* a "bird": a few chirping partials plus a little noise */
-static void make_bird(int bird, int take, Float32* out, int n) {
+/* a "bird": a few chirping partials plus a little noise, sampled at sampleRate */
+static void make_bird_at(int bird, int take, Float32* out, int n, double sampleRate) {
     rng_state = 1000003ULL * (unsigned long long)(bird + 1) + 77ULL * (unsigned long long)take;
     double f[3], df[3], rate[3];
     for (int p = 0; p < 3; p++) { f[p] = 400.0 + 1400.0 * rnd(); df[p] = 100.0 + 300.0 * rnd(); rate[p] = 2.0 + 6.0 * rnd(); }
     for (int i = 0; i < n; i++) {
-        double t = i / 5512.0, v = 0.0;
+        double t = i / sampleRate, v = 0.0;
         for (int p = 0; p < 3; p++) v += 0.25 * sin(2.0 * M_PI * (f[p] * t + df[p] / (2.0 * M_PI * rate[p]) * sin(2.0 * M_PI * rate[p] * t)));
         out[i] = (Float32)(v + 0.05 * (rnd() - 0.5));
     }
 }
+
+static void make_bird(int bird, int take, Float32* out, int n) { make_bird_at(bird, take, out, n, 5512.0); }
 
 static int failures = 0;
 #define CHECK(cond, ...) do { if (!(cond)) { failures++; fprintf(stderr, "FAILED %s:%d: ", __FILE__, __LINE__); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } } while (0)
@@ -95,6 +100,37 @@ int main(void) {
         CHECK(LBAudioDetectiveFingerprintCompareToFingerprint(fingerprint1, copy, 200) == 1.0f, "self match is 1.0");
         LBAudioDetectiveFingerprintDispose(copy); LBAudioDetectiveFingerprintDispose(fingerprint1); LBAudioDetectiveFingerprintDispose(fingerprint2);
         CHECK(LBAudioDetectiveDispose(detective2) == noErr, "Dispose");
+    }
+    /* the bundled recordings are 44.1 kHz files which ExtAudioFile converts while reading (m:229): here the caller hands over PCM at that
+     * rate and the library converts on the GPU; archive = 9 s, query = its first 4 s.  (The comparison slides by whole subfingerprints,
+     * i.e. by 8192 processing-rate samples = 65541.9 recorded samples: a crop that starts further in cannot be cut on a frame boundary of
+     * the archive, and these sparse synthetic birds lose the match within a hundredth of a sample of misalignment.) */
+    {
+        enum { HI_ARCHIVE = 9 * 44100, HI_CROP = 4 * 44100, HI_START = 0 };
+        static Float32 hi[HI_ARCHIVE];
+        LBAudioDetectiveFingerprintRef fa[BIRDS], fc[BIRDS];
+        CHECK(LBAudioDetectiveSetRecordingSampleRate(detective, 44100.0) == noErr, "SetRecordingSampleRate");
+        CHECK(LBAudioDetectiveGetResampledLength(detective, HI_ARCHIVE) == ARCHIVE_SAMPLES, "9 s stay 9 s");
+        for (int b = 0; b < BIRDS; b++) {
+            make_bird_at(b, 0, hi, HI_ARCHIVE, 44100.0);
+            CHECK(LBAudioDetectiveProcessRecordedPCM(detective, hi, HI_ARCHIVE, &fa[b]) == noErr, "ProcessRecordedPCM");
+            CHECK(LBAudioDetectiveProcessRecordedPCM(detective, hi + HI_START, HI_CROP, &fc[b]) == noErr, "ProcessRecordedPCM");
+            CHECK(LBAudioDetectiveFingerprintGetNumberOfSubfingerprints(fa[b]) == 5 && LBAudioDetectiveFingerprintGetNumberOfSubfingerprints(fc[b]) == 2, "5 and 2 subfingerprints");
+        }
+        int identified = 0;
+        printf("%-6s", "_44k");
+        for (int original = 0; original < BIRDS; original++) {
+            Float32 bestMatch = 0.0f; int bestBird = -1;
+            for (int sequence = 0; sequence < BIRDS; sequence++) {
+                const Float32 match = LBAudioDetectiveFingerprintCompareToFingerprint(fa[original], fc[sequence], 200);
+                if (match > bestMatch) { bestMatch = match; bestBird = sequence; }
+            }
+            printf(" %d:%d(%.3f)", original, bestBird, bestMatch);
+            identified += bestBird == original;
+        }
+        printf("  -> %d/%d identified\n", identified, BIRDS);
+        CHECK(identified == BIRDS, "a crop of a 44.1 kHz recording must identify its bird");
+        for (int b = 0; b < BIRDS; b++) { LBAudioDetectiveFingerprintDispose(fa[b]); LBAudioDetectiveFingerprintDispose(fc[b]); }
     }
     CHECK(LBAudioDetectiveDispose(detective) == noErr, "Dispose");                          /* Tests.m:46 */
     CHECK(LBAudioDetectiveDispose(NULL) == kLBAudioDetectiveArgumentInvalid, "Dispose(NULL)");
