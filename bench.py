@@ -101,6 +101,23 @@ def cpu_search_baseline(chk, threads, n_db=20000, n_q=4):
     return n_db * n_q * 84 / secs
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """stdout carries ONE JSON line: anything a library prints there (NCCL's version banner, for one) goes to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the same path, same metric, all host threads.
     Each step fingerprints a bounded sample (args.ref_clips x 30 s) of the config-2 workload."""
@@ -123,7 +140,7 @@ def run_reference(args):
                                             "clip_seconds": 30, "window": 2048, "stride": 64, "bands": 32, "subfingerprint_length": 200},
             "cpu_baseline": {"value": value, "unit": "audio-hours/s", "cores": threads, "kind": chk.kind, "sample": sample},
             "e2e": {"value": value, "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -141,6 +158,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--microbench", action="store_true", help="also measure the FP32 / POPC / LOP3 pipe rates (roofline context)")
     args = ap.parse_args()
+    guard_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -163,7 +181,6 @@ def main():
     except Exception:
         pass
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line and nothing else (NCCL_DEBUG=VERSION/INFO would print there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lb.load_library(build_if_missing=False)          # the bench must run the in-tree CUDA library, never a fallback
     if not lb.device_available():
@@ -337,7 +354,7 @@ def main():
                        "clips_per_gpu": n_clips, "clip_seconds": 30, "window": 2048, "stride": 64, "bands": 32, "subfingerprint_length": 200,
                        "l2_policy": "inputs (%.1f GB per GPU) larger than L2" % (n_clips * CLIP_LEN * 4 / 1e9)},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "search": search}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
