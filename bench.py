@@ -230,7 +230,9 @@ def main():
     gpu_launches = det.kernel_launches - launches0
     hours_per_gpu_step = n_clips * CLIP_LEN / SR / 3600.0
     value = hours_per_gpu_step * world * args.steps / (ms_total * 1e-3)
-    kernel_ms = kernel_ms_total / max(n_timed, 1)
+    # per STEP, not per launch: a step of more than 2^18 frames runs the two kernels once per slab (config 3 at full size: 9 slabs)
+    kernel_ms = kernel_ms_total / args.steps
+    kernel2_ms = kernel2_ms_total / args.steps
 
     # ---- sanity on the timed output: structure of the words (never the thing measured) ----
     w = words[:: max(1, n_clips // 64)].cpu().numpy().view(np.uint32)
@@ -248,7 +250,7 @@ def main():
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
-                "peak_source": peak_src, "kernel": "bands_fused_kernel (FFT + band energies)", "kernel_ms": kernel_ms, "second_kernel": "haar_select32_kernel", "second_kernel_ms": kernel2_ms_total / max(n_timed2, 1), "algorithmic_bytes_per_launch": algo_bytes,
+                "peak_source": peak_src, "kernel": "bands_fused_kernel (FFT + band energies)", "kernel_ms": kernel_ms, "second_kernel": "haar_select32_kernel", "second_kernel_ms": kernel2_ms, "launches_per_step": n_timed // max(args.steps, 1), "algorithmic_bytes_per_launch": algo_bytes,
                 "note": "FP32-issue bound, not HBM bound (235 flop per new PCM byte, SURVEY.md §8d); fp32 figures alongside",
                 "fp32_tflops_algorithmic": flops / (kernel_ms * 1e-3) / 1e12, "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12}
     if args.microbench and rank == 0:

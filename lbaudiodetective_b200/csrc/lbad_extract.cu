@@ -786,10 +786,12 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                         const float2 w = reinterpret_cast<const float2*>(tw2)[k2 * 32 + lane];   /* (cos, sin) of 2 pi k / N, k = lane + 32 k2: one conflict-free LDS.64 */
                         const float c = w.x, sn = w.y;
                         const int p = bitrev5(k2), pp = bitrev5(31 - k2), p0 = bitrev5((32 - k2) % 32);
-                        float2 pz;                                              /* Z[1024 - k] lives in lane 32 - lane, row 31 - k2 */
-                        pz.x = __shfl_sync(0xffffffffu, z[pp].x, src_lane);
-                        pz.y = __shfl_sync(0xffffffffu, z[pp].y, src_lane);
-                        if (lane == 0) pz = z[p0];                              /* ... except lane 0: own register, row 32 - k2 */
+                        /* Z[1024 - k] lives in lane 32 - lane, row 31 - k2 ... except for lane 0: own register, row 32 - k2.  Lane 0 is
+                         * read by nobody but itself, so it offers that register and the exception costs nothing after the shuffle. */
+                        const float2 offer = lane == 0 ? z[p0] : z[pp];
+                        float2 pz;
+                        pz.x = __shfl_sync(0xffffffffu, offer.x, src_lane);
+                        pz.y = __shfl_sync(0xffffffffu, offer.y, src_lane);
                         const int k = k2 * 32 + lane;
                         if (need_hi) {
                             float2 lo, hi;
@@ -817,10 +819,10 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
     #pragma unroll
                             for (int s = 0; s < S; s++) {
                                 const int p = s * R + bitrevR<R>(kk), pp = s * R + bitrevR<R>(R - 1 - kk), p0 = s * R + bitrevR<R>((R - kk) % R);
-                                float2 pz;                                          /* Z[M - k] lives in lane 32-lane, k2' = R-1-k2 */
-                                pz.x = __shfl_sync(0xffffffffu, z[pp].x, src_lane);
-                                pz.y = __shfl_sync(0xffffffffu, z[pp].y, src_lane);
-                                if (lane == 0) pz = z[p0];                          /* ... except lane 0: own register k2' = R-k2 */
+                                const float2 offer = lane == 0 ? z[p0] : z[pp];     /* Z[M - k] lives in lane 32-lane, k2' = R-1-k2 ... except lane 0: own register k2' = R-k2 */
+                                float2 pz;
+                                pz.x = __shfl_sync(0xffffffffu, offer.x, src_lane);
+                                pz.y = __shfl_sync(0xffffffffu, offer.y, src_lane);
                                 float xr, xi;
                                 real_split_2x(z[p], pz, h ? w.z : w.x, h ? w.w : w.y, xr, xi);
                                 if (kk == 0 && lane == 0) { xr = 2.0f * (z[p].x + z[p].y); xi = 2.0f * (z[p].x - z[p].y); }   /* DC / packed Nyquist */
