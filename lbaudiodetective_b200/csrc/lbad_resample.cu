@@ -2,24 +2,25 @@
  * lbad_resample.cu — recording-rate -> processing-rate conversion on the device (sm_100a), the step ExtAudioFile's client
  * format performs in the reference (LBAudioDetective.m:229, m:275; AudioToolbox itself is out of scope).  The conversion is
  * the two-stage band-limited decimator defined in include/LBAudioDetectiveResample.h; the tables are designed on the host
- * (lbad_resample_design.c) and this file evaluates them: one CTA per tile of 256 output samples of one clip, the input span of
+ * (lbad_resample_design.c) and this file evaluates them: one CTA (128 threads) per tile of 128 or 256 output samples of one clip, the input span of
  * the tile staged once in shared memory (every recorded sample is read from HBM once per tile it touches; neighbouring tiles
  * overlap by the filter length, served by L2), stage 1 into a second shared tile, stage 2 from there.  Sums are float32 FMA
  * chains in increasing tap order, so the result equals oracle/lbad_oracle.c bit for bit.
  */
 #include "lbad_common.cuh"
 #include <math.h>
+#include <type_traits>
 
 namespace lbad {
 
-constexpr int RS_THREADS = 256;              /* = output samples per tile */
+constexpr int RS_THREADS = 128;              /* a tile is RS_THREADS x OPT output samples (OPT = outputs per thread in stage 2) */
 constexpr int RS_PHASES = LBAD_RS_PHASES;
 
 struct ResampleParams {
     uint32_t D, H1, T1, H2, T2;
     double rho2;
     uint64_t in_len, in_stride, out_len, out_stride;
-    uint32_t tiles_per_clip, ny_max, nx_max;
+    uint32_t tiles_per_clip, ny_max, nx_max, tile;      /* tile: output samples per CTA iteration */
     uint32_t nip, xs_floats;         /* D = 4: floats per polyphase plane of the staged input; floats reserved for the staged input */
 };
 
@@ -30,15 +31,19 @@ __constant__ float c_g_d4[49];
 /* D4: integer decimation by 4 with the 49-tap stage-1 filter — the 44.1 kHz case.  The tile's input starts on a multiple of 4
  * samples, so thread j reads its 49 inputs as twelve conflict-free 128-bit shared loads plus one scalar.  T2C: the number of
  * stage-2 taps when known at compile time (42 for 44.1 kHz -> 5512 Hz), 0 = run-time.  vec_ok: the clips start on 16-byte
- * boundaries, so interior tiles are staged with 128-bit loads. */
-template <bool D4, int T2C>
+ * boundaries, so interior tiles are staged with 128-bit loads.  OPT: outputs per thread in stage 2.  OPT = 2 (rho2 in [2, 3), T2C
+ * given) pairs outputs m, m + 1: while consecutive outputs sit exactly two stage-1 samples apart — all but one step in 1 / frac(rho2)
+ * — a thread reads the 44 samples its two outputs share as twelve 128-bit loads and, while both outputs use the same coarse phase,
+ * one set of coefficient rows: 35 instead of 64 shared-memory wavefronts per 32 outputs (stage 2 was what bound the kernel).  The
+ * FMA chain of every output is the one of the single-output form, so the result does not change by a bit. */
+template <bool D4, int T2C, int OPT>
 __global__ void __launch_bounds__(RS_THREADS)
 resample_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ g, const float* __restrict__ hc, const ResampleParams P,
                 const uint64_t total_tiles, const int vec_ok) {
     extern __shared__ __align__(16) float rs_smem[];
     float* xs = rs_smem;                                       /* [nx_max], 16-byte aligned */
     float* y1s = xs + P.xs_floats;                             /* [ny_max + 4] */
-    float* gs = y1s + ((P.ny_max + 4 + 3) & ~3u);              /* [T1] */
+    float* gs = y1s + ((P.ny_max + 8 + 3) & ~3u);              /* [T1] */
     float* hcs = gs + ((P.T1 + 3) & ~3u);                      /* [PHASES + 1][T2P], rows padded to T2P = a multiple of 4 floats (zeros) */
     const uint32_t T2 = T2C ? (uint32_t)T2C : P.T2;
     const uint32_t T2P = (T2 + 3) & ~3u;
@@ -47,8 +52,9 @@ resample_kernel(const float* __restrict__ in, float* __restrict__ out, const flo
     for (uint32_t i = tid; i < (RS_PHASES + 1) * T2P; i += RS_THREADS) { const uint32_t r = i / T2P, c = i % T2P; hcs[i] = c < T2 ? __ldg(hc + r * T2 + c) : 0.0f; }
     for (uint32_t tile = blockIdx.x; tile < (uint32_t)total_tiles; tile += gridDim.x) {      /* the host keeps total_tiles and out_len below 2^31 */
         const uint32_t clip = tile / P.tiles_per_clip;
-        const uint32_t m0 = (tile % P.tiles_per_clip) * RS_THREADS;
-        const uint32_t m1 = (m0 + RS_THREADS < (uint32_t)P.out_len) ? m0 + RS_THREADS : (uint32_t)P.out_len;
+        constexpr uint32_t TILE = RS_THREADS * OPT;
+        const uint32_t m0 = (tile % P.tiles_per_clip) * TILE;
+        const uint32_t m1 = (m0 + TILE < (uint32_t)P.out_len) ? m0 + TILE : (uint32_t)P.out_len;
         const int64_t i0_lo = (int64_t)floor((double)m0 * P.rho2), i0_hi = (int64_t)floor((double)(m1 - 1) * P.rho2);
         const int64_t y_lo = i0_lo - (int64_t)P.H2 + 1, y_hi = i0_hi + (int64_t)P.H2;
         const uint32_t ny = (uint32_t)(y_hi - y_lo + 1);
@@ -59,9 +65,9 @@ resample_kernel(const float* __restrict__ in, float* __restrict__ out, const flo
             const uint32_t nx = P.D * (ny - 1) + P.T1;
             if constexpr (D4) {
                 /* the input tile is staged de-interleaved into its four polyphase planes xp[p][i] = x[x_lo + 4 i + p] (x_lo is a multiple
-                 * of 4): a thread then produces FOUR consecutive stage-1 outputs from four 128-bit loads per plane, 16 loads for 196 FMAs,
+                 * of 4): a thread then produces EIGHT consecutive stage-1 outputs from five 128-bit loads per plane, 20 loads for 392 FMAs,
                  * instead of 13 loads per output — stage 1 was bound by shared-memory wavefronts */
-                const uint32_t ni = (nx + 3) / 4, nip = P.nip;                              /* plane length used / allocated (multiple of 4 floats, >= ny_max + 16) */
+                const uint32_t ni = (nx + 3) / 4, nip = P.nip;                              /* plane length used / allocated (multiple of 4 floats, >= ny_max + 24) */
                 if (vec_ok && x_lo >= 0 && (uint64_t)x_lo + 4ull * ni <= P.in_len) {
                     const float4* s4 = reinterpret_cast<const float4*>(src + x_lo);
                     for (uint32_t i = tid; i < ni; i += RS_THREADS) { const float4 v = __ldg(s4 + i); xs[i] = v.x; xs[nip + i] = v.y; xs[2 * nip + i] = v.z; xs[3 * nip + i] = v.w; }
@@ -69,20 +75,23 @@ resample_kernel(const float* __restrict__ in, float* __restrict__ out, const flo
                     for (uint32_t i = tid; i < 4 * ni; i += RS_THREADS) { const int64_t k = x_lo + i; xs[(i & 3) * nip + (i >> 2)] = (k >= 0 && (uint64_t)k < P.in_len) ? __ldg(src + k) : 0.0f; }
                 }
                 __syncthreads();
-                for (uint32_t j0 = 4 * tid; j0 < ny; j0 += 4 * RS_THREADS) {             /* stage 1: outputs j0 .. j0 + 3 */
-                    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                for (uint32_t j0 = 8 * tid; j0 < ny; j0 += 8 * RS_THREADS) {             /* stage 1: outputs j0 .. j0 + 7 */
+                    float acc[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                     for (int pl = 0; pl < 4; pl++) {
                         const float4* x4 = reinterpret_cast<const float4*>(xs + pl * nip) + (j0 >> 2);
-                        const float4 q0 = x4[0], q1 = x4[1], q2 = x4[2], q3 = x4[3];
-                        const float v[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+                        float v[20];
+#pragma unroll
+                        for (int q = 0; q < 5; q++) { const float4 t = x4[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
 #pragma unroll
                         for (int m = 0; m < (pl == 0 ? 13 : 12); m++) {                   /* tap t = 4 m + pl multiplies plane sample (output + m) */
                             const float c = c_g_d4[4 * m + pl];
-                            a0 = fmaf(c, v[m], a0); a1 = fmaf(c, v[m + 1], a1); a2 = fmaf(c, v[m + 2], a2); a3 = fmaf(c, v[m + 3], a3);
+#pragma unroll
+                            for (int o = 0; o < 8; o++) acc[o] = fmaf(c, v[m + o], acc[o]);
                         }
                     }
-                    *reinterpret_cast<float4*>(y1s + j0) = make_float4(a0, a1, a2, a3);    /* y1s has room for the up to three outputs past ny */
+                    *reinterpret_cast<float4*>(y1s + j0) = make_float4(acc[0], acc[1], acc[2], acc[3]);      /* y1s has room for the up to seven outputs past ny */
+                    *reinterpret_cast<float4*>(y1s + j0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
                 }
             } else {
                 for (uint32_t i = tid; i < nx; i += RS_THREADS) { const int64_t k = x_lo + i; xs[i] = (k >= 0 && (uint64_t)k < P.in_len) ? __ldg(src + k) : 0.0f; }
@@ -98,8 +107,8 @@ resample_kernel(const float* __restrict__ in, float* __restrict__ out, const flo
             for (uint32_t i = tid; i < ny; i += RS_THREADS) { const int64_t k = y_lo + i; y1s[i] = (k >= 0 && (uint64_t)k < P.in_len) ? __ldg(src + k) : 0.0f; }
         }
         __syncthreads();
-        const uint32_t m = m0 + tid;
-        if (m < m1) {                                           /* stage 2: position in the stage-1 sequence, coarse phase, interpolation weight */
+        /* stage 2 for one output: position in the stage-1 sequence, coarse phase, interpolation weight */
+        auto single_output = [&](const uint32_t m) {
             const double pos = (double)m * P.rho2;
             const double fl = floor(pos);
             const double fp = (pos - fl) * (double)RS_PHASES;
@@ -130,6 +139,66 @@ resample_kernel(const float* __restrict__ in, float* __restrict__ out, const flo
                 for (uint32_t q = 0; q < quads; q++) { const float2 a2 = y2[2 * q], b2 = y2[2 * q + 1]; taps4(q, a2.x, a2.y, b2.x, b2.y); }
             }
             out[(uint64_t)clip * P.out_stride + m] = fmaf(a, s1 - s0, s0);
+        };
+        if constexpr (OPT == 1) {
+            if (m0 + tid < m1) single_output(m0 + tid);
+        } else {
+            static_assert(OPT == 2 && T2C > 0, "the paired form needs the tap count at compile time");
+            const int lane = tid & 31;
+            const uint32_t ma = m0 + 2 * tid, mb = ma + 1;
+            const double pos_a = (double)ma * P.rho2, pos_b = (double)mb * P.rho2;
+            const double fl_a = floor(pos_a), fl_b = floor(pos_b);
+            const double fp_a = (pos_a - fl_a) * (double)RS_PHASES, fp_b = (pos_b - fl_b) * (double)RS_PHASES;
+            const int p_a = (int)fp_a, p_b = (int)fp_b;
+            const int yb = (int)((int64_t)fl_a - (int64_t)P.H2 + 1 - y_lo), yb_b = (int)((int64_t)fl_b - (int64_t)P.H2 + 1 - y_lo);
+            const int yb0 = __shfl_sync(0xffffffffu, yb, 0);
+            /* the paired form: every output of the warp exists and every step inside the warp's 64 outputs is exactly two samples */
+            if (__all_sync(0xffffffffu, mb < m1 && yb == yb0 + 4 * lane && yb_b == yb + 2)) {
+                const bool same = __all_sync(0xffffffffu, p_a == p_b) != 0;              /* one set of coefficient rows serves both outputs */
+                const float4* y4 = reinterpret_cast<const float4*>(y1s + (yb & ~3));
+                float w[48];                                    /* stage-1 samples (yb & ~3) .. + 47; taps use w[r .. r + 43], r = yb & 3 (warp-uniform) */
+#pragma unroll
+                for (int q = 0; q < 12; q++) { const float4 v = y4[q]; w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+                const float4* h0a = reinterpret_cast<const float4*>(hcs + (size_t)p_a * T2P);
+                const float4* h1a = reinterpret_cast<const float4*>(hcs + (size_t)(p_a + 1) * T2P);
+                const float4* h0b = reinterpret_cast<const float4*>(hcs + (size_t)p_b * T2P);
+                const float4* h1b = reinterpret_cast<const float4*>(hcs + (size_t)(p_b + 1) * T2P);
+                float sa0 = 0.0f, sa1 = 0.0f, sb0 = 0.0f, sb1 = 0.0f;
+                auto chains = [&](auto rc, auto sc) {
+                    constexpr int r = decltype(rc)::value;
+                    constexpr bool SAME = decltype(sc)::value;  /* both outputs on one coarse phase: b reads a's coefficient registers */
+#pragma unroll
+                    for (int q = 0; q < (T2C + 3) / 4; q++) {
+                        const float4 ca0 = h0a[q], ca1 = h1a[q];
+                        const float4 cb0 = SAME ? ca0 : h0b[q], cb1 = SAME ? ca1 : h1b[q];
+                        const float a0[4] = {ca0.x, ca0.y, ca0.z, ca0.w}, a1[4] = {ca1.x, ca1.y, ca1.z, ca1.w};
+                        const float b0[4] = {cb0.x, cb0.y, cb0.z, cb0.w}, b1[4] = {cb1.x, cb1.y, cb1.z, cb1.w};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int i = 4 * q + j;
+                            if (i < T2C) {                      /* the padded taps have zero coefficients but must not enter the chain */
+                                sa0 = fmaf(a0[j], w[r + i], sa0); sa1 = fmaf(a1[j], w[r + i], sa1);
+                                sb0 = fmaf(b0[j], w[r + 2 + i], sb0); sb1 = fmaf(b1[j], w[r + 2 + i], sb1);
+                            }
+                        }
+                    }
+                };
+                auto by_alignment = [&](auto sc) {
+                    switch (yb0 & 3) {                          /* warp-uniform */
+                        case 0: chains(std::integral_constant<int, 0>{}, sc); break;
+                        case 1: chains(std::integral_constant<int, 1>{}, sc); break;
+                        case 2: chains(std::integral_constant<int, 2>{}, sc); break;
+                        default: chains(std::integral_constant<int, 3>{}, sc); break;
+                    }
+                };
+                if (same) by_alignment(std::true_type{}); else by_alignment(std::false_type{});
+                float* o = out + (uint64_t)clip * P.out_stride + ma;
+                o[0] = fmaf((float)(fp_a - (double)p_a), sa1 - sa0, sa0);
+                o[1] = fmaf((float)(fp_b - (double)p_b), sb1 - sb0, sb0);
+            } else {
+                if (ma < m1) single_output(ma);
+                if (mb < m1) single_output(mb);
+            }
         }
     }
 }
@@ -157,13 +226,15 @@ extern "C" int lbadcu_resampler_create(const lbadcu_resample_design* d, lbadcu_r
     r->sm_count = prop.multiProcessorCount;
     ResampleParams& P = r->P;
     P.D = d->D; P.H1 = d->H1; P.T1 = d->D > 1 ? d->T1 : 0; P.H2 = d->H2; P.T2 = d->T2; P.rho2 = d->rho2;
-    P.ny_max = (uint32_t)floor(RS_THREADS * d->rho2) + 2 * d->H2 + 2;
+    /* two outputs per thread in stage 2 (tiles of 512) where the paired form applies: the 49-tap D = 4 first stage, 42 taps, rho2 in [2, 3) */
+    P.tile = (d->D == 4 && d->T1 == 49 && d->T2 == 42 && d->rho2 >= 2.0 && d->rho2 < 3.0) ? 2 * RS_THREADS : RS_THREADS;
+    P.ny_max = (uint32_t)floor(P.tile * d->rho2) + 2 * d->H2 + 2;
     P.nx_max = d->D > 1 ? d->D * (P.ny_max - 1) + d->T1 : 0;
-    P.nip = (P.nx_max / 4 + 8) & ~3u;
+    P.nip = (P.nx_max / 4 + 12 + 3) & ~3u;          /* >= ny_max + 24: the five 128-bit loads of the last thread's eight outputs stay inside the plane */
     P.xs_floats = (d->D == 4 && d->T1 == 49) ? 4 * P.nip : ((P.nx_max + 3) & ~3u);
     const size_t nhc = (size_t)(RS_PHASES + 1) * d->T2;
-    /* shared layout: input tile, stage-1 tile (+4: the 64-bit sample loads of stage 2 may read up to three floats past it), taps, padded coarse-phase rows */
-    r->smem_base = (size_t)P.xs_floats + (((size_t)P.ny_max + 4 + 3) & ~3u) + (((size_t)P.T1 + 3) & ~3u) + (size_t)(RS_PHASES + 1) * ((d->T2 + 3) & ~3u);
+    /* shared layout: input tile, stage-1 tile (+8: the 64- and 128-bit sample loads of stage 2 may read up to seven floats past it), taps, padded coarse-phase rows */
+    r->smem_base = (size_t)P.xs_floats + (((size_t)P.ny_max + 8 + 3) & ~3u) + (((size_t)P.T1 + 3) & ~3u) + (size_t)(RS_PHASES + 1) * ((d->T2 + 3) & ~3u);
     if (r->smem_base * sizeof(float) > prop.sharedMemPerBlockOptin) { delete r; set_error("resampler: the filters for this rate pair do not fit in shared memory"); return LBAD_ERR_ARG; }
     LBAD_CUDA_TRY(cudaMalloc(&r->d_hc, nhc * sizeof(float)));
     LBAD_CUDA_TRY(cudaMemcpy(r->d_hc, d->hc, nhc * sizeof(float), cudaMemcpyHostToDevice));
@@ -193,12 +264,12 @@ extern "C" int lbadcu_resample_device(lbadcu_resampler* r, const float* d_in, ui
     cudaStream_t s = stream ? (cudaStream_t)stream : r->stream;
     ResampleParams P = r->P;
     P.in_len = in_len; P.in_stride = in_stride; P.out_len = out_len; P.out_stride = out_stride;
-    P.tiles_per_clip = (uint32_t)((out_len + RS_THREADS - 1) / RS_THREADS);
+    P.tiles_per_clip = (uint32_t)((out_len + P.tile - 1) / P.tile);
     const uint64_t total = (uint64_t)P.tiles_per_clip * n_clips;
     if (out_len >= (1ull << 31) || total >= (1ull << 31)) return LBAD_ERR_ARG;
     const size_t smem = r->smem_base * sizeof(float);
     const bool d4 = P.D == 4 && P.T1 == 49;
-    auto kern = d4 ? (P.T2 == 42 ? resample_kernel<true, 42> : resample_kernel<true, 0>) : resample_kernel<false, 0>;
+    auto kern = d4 ? (P.tile == 2 * RS_THREADS ? resample_kernel<true, 42, 2> : P.T2 == 42 ? resample_kernel<true, 42, 1> : resample_kernel<true, 0, 1>) : resample_kernel<false, 0, 1>;
     const int vec_ok = ((uintptr_t)d_in % 16 == 0) && (in_stride % 4 == 0);
     LBAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;

@@ -23,7 +23,7 @@ rng = np.random.default_rng(3)
 imgs = np.concatenate([(rng.random((2, 128, 32)) ** 4 * 50).astype(np.float32), (rng.random((1, 128, 32)) * 1e-36).astype(np.float32),
                        rng.integers(0, 3, size=(1, 128, 32)).astype(np.float32)])
 th, tb = d.transform_images(imgs)
-hi = p.synth_clip(9, 3 * 44100, 44100.0)
+hi = p.synth_clip(9, 3 * 44100 + 1234, 44100.0)          # not a whole number of tiles or pairs
 r1 = d.resample(hi); fr = d.process_recorded_pcm(hi)
 d3 = lb.Detective(); d3.set_recording_rate(16000.0); r2 = d3.resample(p.synth_clip(9, 2 * 16000, 16000.0))
 f0 = lb.Fingerprint(200); f0.add_packed(w[0]); f1 = lb.Fingerprint(200); f1.add_packed(w[1])

@@ -70,6 +70,23 @@ def test_kernel_equals_oracle_bit_for_bit(lb, port, fs):
 
 
 @pytest.mark.gpu
+def test_kernel_44k_tile_edges_and_long_clip(lb, port):
+    """The 44.1 kHz kernel pairs outputs in tiles of 512: lengths around the tile and pair boundaries (odd tails, a single output),
+    and a clip long enough for every irregular step (three instead of two stage-1 samples, once per 5,512 outputs) and every coarse-phase
+    step (once per 86 outputs) to fall on each side of a pair."""
+    d = lb.Detective()
+    rng = np.random.default_rng(44)
+    for n_out in (1, 2, 3, 511, 512, 513, 1023, 1024, 1025, 1537):
+        n = int(np.ceil(n_out * FS / OUT)) + 1
+        x = (0.3 * rng.standard_normal(n)).astype(np.float32)
+        got = d.resample(x); want = port.resample(x, FS)
+        assert len(want) in (n_out, n_out + 1) and np.array_equal(got, want), n_out
+    x = (0.3 * rng.standard_normal(11 * 44100 + 5)).astype(np.float32)
+    got = d.resample(x); want = port.resample(x, FS)
+    assert len(want) > 60000 and np.array_equal(got, want)
+
+
+@pytest.mark.gpu
 def test_process_recorded_pcm_equals_process_of_resampled(lb, port):
     """One call from 44.1 kHz PCM = resample + LBAudioDetectiveProcessPCM, without the host round trip."""
     hi = port.synth_clip(21, 8 * 44100, 44100.0)
