@@ -36,6 +36,12 @@ __constant__ float c_g_d4[49];
  * — a thread reads the 44 samples its two outputs share as twelve 128-bit loads and, while both outputs use the same coarse phase,
  * one set of coefficient rows: 35 instead of 64 shared-memory wavefronts per 32 outputs (stage 2 was what bound the kernel).  The
  * FMA chain of every output is the one of the single-output form, so the result does not change by a bit. */
+/* Where 128-bit group I of a polyphase plane is kept: a thread's eight stage-1 outputs start two groups after its neighbour's, so the
+ * eight lanes of a 128-bit access phase read groups s, s + 2, .., s + 14 — every bank twice.  Exchanging odd and even groups in every
+ * second block of eight puts the groups that are eight apart on different banks: conflict-free for any s. */
+__device__ __forceinline__ uint32_t plane_quad(const uint32_t I) { return I ^ ((I >> 3) & 1u); }
+__device__ __forceinline__ uint32_t plane_pos(const uint32_t i) { return i ^ (((i >> 5) & 1u) << 2); }      /* the same for float index i = 4 I + c */
+
 template <bool D4, int T2C, int OPT>
 __global__ void __launch_bounds__(RS_THREADS)
 resample_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ g, const float* __restrict__ hc, const ResampleParams P,
@@ -70,19 +76,19 @@ resample_kernel(const float* __restrict__ in, float* __restrict__ out, const flo
                 const uint32_t ni = (nx + 3) / 4, nip = P.nip;                              /* plane length used / allocated (multiple of 4 floats, >= ny_max + 24) */
                 if (vec_ok && x_lo >= 0 && (uint64_t)x_lo + 4ull * ni <= P.in_len) {
                     const float4* s4 = reinterpret_cast<const float4*>(src + x_lo);
-                    for (uint32_t i = tid; i < ni; i += RS_THREADS) { const float4 v = __ldg(s4 + i); xs[i] = v.x; xs[nip + i] = v.y; xs[2 * nip + i] = v.z; xs[3 * nip + i] = v.w; }
+                    for (uint32_t i = tid; i < ni; i += RS_THREADS) { const float4 v = __ldg(s4 + i); const uint32_t j = plane_pos(i); xs[j] = v.x; xs[nip + j] = v.y; xs[2 * nip + j] = v.z; xs[3 * nip + j] = v.w; }
                 } else {
-                    for (uint32_t i = tid; i < 4 * ni; i += RS_THREADS) { const int64_t k = x_lo + i; xs[(i & 3) * nip + (i >> 2)] = (k >= 0 && (uint64_t)k < P.in_len) ? __ldg(src + k) : 0.0f; }
+                    for (uint32_t i = tid; i < 4 * ni; i += RS_THREADS) { const int64_t k = x_lo + i; xs[(i & 3) * nip + plane_pos(i >> 2)] = (k >= 0 && (uint64_t)k < P.in_len) ? __ldg(src + k) : 0.0f; }
                 }
                 __syncthreads();
                 for (uint32_t j0 = 8 * tid; j0 < ny; j0 += 8 * RS_THREADS) {             /* stage 1: outputs j0 .. j0 + 7 */
                     float acc[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                     for (int pl = 0; pl < 4; pl++) {
-                        const float4* x4 = reinterpret_cast<const float4*>(xs + pl * nip) + (j0 >> 2);
+                        const float4* x4 = reinterpret_cast<const float4*>(xs + pl * nip);
                         float v[20];
 #pragma unroll
-                        for (int q = 0; q < 5; q++) { const float4 t = x4[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+                        for (int q = 0; q < 5; q++) { const float4 t = x4[plane_quad((j0 >> 2) + q)]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
 #pragma unroll
                         for (int m = 0; m < (pl == 0 ? 13 : 12); m++) {                   /* tap t = 4 m + pl multiplies plane sample (output + m) */
                             const float c = c_g_d4[4 * m + pl];
