@@ -466,9 +466,11 @@ def test_extract_then_search_end_to_end(lb, port):
 
 
 def test_full_size_properties(lb):
-    """BASELINE config-2 shaped work at reduced clip count: determinism and structure of 2,000 x 30 s clips on device."""
+    """BASELINE config 2 at full size — 10,000 x 30 s clips resident on the device — through size-independent properties:
+    the same PCM gives the same words wherever it is scheduled, the pass is idempotent, every subfingerprint has the structure
+    the reference's construction implies, and excerpts of database clips find their clip."""
     import torch
-    d = lb.Detective(); n, clip_len = 2000, 165360
+    d = lb.Detective(); n, clip_len = 10000, 165360
     x = torch.empty((n, clip_len), dtype=torch.float32, device="cuda")
     lb.synthesize_device(x.data_ptr(), n // 2, clip_len, clip_len, first_clip_id=0)
     x[n // 2:] = x[:n // 2]                                                 # second half duplicates the first
@@ -487,3 +489,33 @@ def test_full_size_properties(lb):
     db = lb.Database(200); db.add_packed_device(out.data_ptr(), n // 2, 19)
     sc, idx = db.search_packed(w[5:n // 2:97, 4:10], k=1)                   # 6-subfp excerpts of database clips
     assert np.array_equal(idx[:, 0], np.arange(5, n // 2, 97).astype(np.uint32)) and (sc == 1.0).all()
+
+
+def test_full_size_search_sharded_equals_whole(lb):
+    """BASELINE config 4 at full size — 1,000 six-subfingerprint queries against 1,000,000 clips of 19 — through properties that do
+    not need the oracle: every query finds the clip it was cut from with score exactly 1, and the database split into eight shards
+    (the 8-GPU layout: per-shard top-k with global clip ids, then the merge kernel) returns what the whole database returns, bit for bit."""
+    import torch
+    n_db, n_q, c, k = 1000000, 1000, 19, 10
+    codes = torch.empty((n_db, c, 8), dtype=torch.int32, device="cuda")
+    lb.random_codes_device(codes.data_ptr(), n_db * c, 200, seed=4242); torch.cuda.synchronize()
+    g = torch.Generator().manual_seed(9)
+    src = torch.randint(0, n_db, (n_q,), generator=g); off = torch.randint(0, c - 6 + 1, (n_q,), generator=g)
+    q = torch.stack([codes[int(a), int(o):int(o) + 6] for a, o in zip(src, off)]).contiguous()
+    whole = lb.Database(200); whole.add_packed_device(codes.data_ptr(), n_db, c)
+    sc = torch.empty((n_q, k), dtype=torch.float32, device="cuda"); ix = torch.empty((n_q, k), dtype=torch.int32, device="cuda")
+    whole.search_device(q.data_ptr(), n_q, 6, k, sc.data_ptr(), ix.data_ptr()); torch.cuda.synchronize()
+    sc_w, ix_w = sc.cpu().numpy(), ix.cpu().numpy().view(np.uint32)
+    assert np.array_equal(ix_w[:, 0], src.numpy().astype(np.uint32)) and (sc_w[:, 0] == 1.0).all()
+    assert (np.diff(sc_w, axis=1) <= 0).all() and (sc_w[:, 1] < 1.0).all()
+    del whole
+    shards = 8; per = n_db // shards
+    s_sc = torch.empty((shards, n_q, k), dtype=torch.float32, device="cuda"); s_ix = torch.empty((shards, n_q, k), dtype=torch.int32, device="cuda")
+    for r in range(shards):
+        db = lb.Database(200); db.set_clip_index_base(r * per)
+        db.add_packed_device(codes[r * per:(r + 1) * per].data_ptr(), per, c)
+        db.search_device(q.data_ptr(), n_q, 6, k, s_sc[r].data_ptr(), s_ix[r].data_ptr()); torch.cuda.synchronize()
+        del db
+    m_sc = torch.empty((n_q, k), dtype=torch.float32, device="cuda"); m_ix = torch.empty((n_q, k), dtype=torch.int32, device="cuda")
+    lb.merge_topk_device(s_sc.data_ptr(), s_ix.data_ptr(), shards, n_q, k, m_sc.data_ptr(), m_ix.data_ptr()); torch.cuda.synchronize()
+    assert np.array_equal(m_ix.cpu().numpy().view(np.uint32), ix_w) and np.array_equal(m_sc.cpu().numpy(), sc_w)
