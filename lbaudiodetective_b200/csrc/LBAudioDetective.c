@@ -87,7 +87,6 @@ UInt32 LBAudioDetectiveGetSubfingerprintLength(LBAudioDetectiveRef d) { return d
 UInt32 LBAudioDetectiveGetWindowSize(LBAudioDetectiveRef d) { return d->windowSize; }
 UInt32 LBAudioDetectiveGetAnalysisStride(LBAudioDetectiveRef d) { return d->analysisStride; }
 
-/* h:143 — declared upstream, never defined */
 /* h:143 (declared upstream, never defined): here the rate of the PCM handed to the ...Recorded... entry points */
 OSStatus LBAudioDetectiveSetRecordingSampleRate(LBAudioDetectiveRef d, Float64 inSampleRate) {
     if (!d || !(inSampleRate > 0.0)) return kLBAudioDetectiveArgumentInvalid;
@@ -231,6 +230,16 @@ OSStatus LBAudioDetectiveProcessPCM(LBAudioDetectiveRef d, const Float32* inSamp
 OSStatus LBAudioDetectiveComparePCM(LBAudioDetectiveRef d, const Float32* s1, UInt64 n1, const Float32* s2, UInt64 n2, UInt32 inComparisonRange, Float32* outMatch) {
     if (!d) return kLBAudioDetectiveArgumentInvalid;
     if (inComparisonRange == 0) inComparisonRange = d->subfingerprintLength;     /* m:443-445 */
+    /* the usual case — both clips yield subfingerprints — runs as one device pipeline: upload, fingerprint, compare, four bytes back.
+     * Same arithmetic as the three steps below (the same kernels on the same words), without their host round trips. */
+    if (s1 && s2 && ensure_plan(d) == noErr && LBAudioDetectiveGetNumberOfSubfingerprintsForLength(d, n1) >= 1 &&
+        LBAudioDetectiveGetNumberOfSubfingerprintsForLength(d, n2) >= 1 && LBAudioDetectiveGetNumberOfSubfingerprintsForLength(d, n1) +
+        LBAudioDetectiveGetNumberOfSubfingerprintsForLength(d, n2) <= 0x7fffffffu) {
+        Float32 match = 0.0f;
+        OSStatus e = lbad_status(lbadcu_compare_pcm_host(d->plan, s1, n1, s2, n2, lbad_pairs_for_range(inComparisonRange, d->subfingerprintLength), &match));
+        if (e == noErr && outMatch) *outMatch = match;                           /* m:456-458 */
+        return e;
+    }
     LBAudioDetectiveFingerprintRef fp1 = NULL, fp2 = NULL;
     OSStatus error = LBAudioDetectiveProcessPCM(d, s1, n1, &fp1);                /* m:449 */
     if (error == noErr) error = LBAudioDetectiveProcessPCM(d, s2, n2, &fp2);     /* m:453 */

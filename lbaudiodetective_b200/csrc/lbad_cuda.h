@@ -116,6 +116,12 @@ int  lbadcu_merge_topk_host(const float* h_sc, const uint32_t* h_id, uint32_t n_
 int  lbadcu_merge_topk_device(const float* d_sc, const uint32_t* d_id, uint32_t n_lists, uint32_t n_q, uint32_t k, float* d_o_sc, uint32_t* d_o_id, void* stream);
 /* one pair, LBAudioDetectiveFingerprintCompareToFingerprint(fp1, fp2) with pairs = ceil(min(range, L)/2); cached per-thread context */
 int  lbadcu_compare_pair(uint32_t words_per_plane, uint32_t pairs, const uint32_t* w1, uint32_t c1, const uint32_t* w2, uint32_t c2, float* out);
+/* the same on packed words that are already on the device; the score stays on the device (d_out) — no synchronisation */
+int  lbadcu_compare_pair_device(uint32_t words_per_plane, uint32_t pairs, const uint32_t* d_w1, uint32_t c1, const uint32_t* d_w2, uint32_t c2, float* d_out, void* stream);
+/* LBAudioDetectiveCompareAudioURLs as ONE device pipeline (LBAudioDetective.m:442-464): both clips uploaded, fingerprinted (as one
+ * two-clip batch when their lengths agree) and compared without the words ever visiting the host; one synchronisation.  Both clips
+ * must yield at least one subfingerprint. */
+int  lbadcu_compare_pcm_host(lbadcu_plan* p, const float* h1, uint64_t n1, const float* h2, uint64_t n2, uint32_t pairs, float* out);
 
 /* ---- synthetic PCM on the device (bench support; same formula as the host generator, device libm) ---- */
 int  lbadcu_synth_device(float* d_out, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride, uint64_t first_clip_id,

@@ -882,6 +882,7 @@ struct lbadcu_plan {
     int stage_mode = -1;      /* -1 auto, 0 plain loads, 1 TMA (env LBAD_STAGE=ldg|tma) */
     bool transform_generic = false;      /* env LBAD_TRANSFORM=generic: lbadcu_transform_images_host uses the any-geometry Haar/select kernel */
     uint32_t slab_frames_cap = 1u << 18;
+    float *d_score = nullptr, *h_score = nullptr;      /* lbadcu_compare_pcm_host: the match on the device and its pinned landing place */
 };
 
 extern "C" const char* lbadcu_last_error(void) { return g_err; }
@@ -1028,6 +1029,7 @@ extern "C" void lbadcu_plan_destroy(lbadcu_plan* p) {
     cudaFree(p->d_tw_m); cudaFree(p->d_tw_n); cudaFree(p->d_tw1); cudaFree(p->d_tw2); for (int i = 0; i < 4; i++) cudaFree(p->d_scratch[i]); for (int i = 0; i < 3; i++) cudaFree(p->d_chunk_i16[i]);
     for (int i = 0; i < 3; i++) { cudaFree(p->d_chunk_pcm[i]); cudaFree(p->d_chunk_words[i]); if (p->copy_streams[i]) cudaStreamDestroy(p->copy_streams[i]); }
     if (p->stream) cudaStreamDestroy(p->stream);
+    cudaFree(p->d_score); cudaFreeHost(p->h_score);
     delete p;
 }
 
@@ -1263,4 +1265,47 @@ extern "C" int lbadcu_extract_host(lbadcu_plan* p, const float* h_pcm, uint32_t 
 
 extern "C" int lbadcu_extract_host_i16(lbadcu_plan* p, const int16_t* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride, uint32_t* h_words) {
     return extract_host_impl(p, h_pcm, 2, n_clips, clip_len, clip_stride, h_words, nullptr, nullptr, 0);
+}
+
+/* LBAudioDetectiveCompareAudioURLs (m:442-464) without a host round trip between its three steps: both clips go up on the plan's
+ * stream, are fingerprinted there — as one two-clip batch when the lengths agree, so the two clips' frames run side by side — and
+ * compare_pair_kernel reads the packed words where the extraction left them.  One synchronisation, four bytes come back. */
+extern "C" int lbadcu_compare_pcm_host(lbadcu_plan* p, const float* h1, uint64_t n1, const float* h2, uint64_t n2, uint32_t pairs, float* out) {
+    if (!p || !h1 || !h2 || !out) return LBAD_ERR_ARG;
+    if (n1 < p->g.window || n2 < p->g.window) return LBAD_ERR_ARG;
+    LBAD_CUDA_TRY(cudaSetDevice(p->device));
+    const uint64_t f1 = ((n1 - p->g.window) / p->g.stride) / LBAD_ROWS_PER_FRAME, f2 = ((n2 - p->g.window) / p->g.stride) / LBAD_ROWS_PER_FRAME;   /* m:250-255 */
+    if (f1 == 0 || f2 == 0 || f1 + f2 > 0x7fffffffull) return LBAD_ERR_ARG;
+    const uint64_t pad1 = (n1 + 7) & ~7ull, pad2 = (n2 + 7) & ~7ull;
+    const size_t W2 = 2 * (size_t)p->g.words_per_plane, need_pcm = (size_t)(pad1 + pad2), need_words = (size_t)(f1 + f2) * W2;
+    if (p->chunk_pcm_floats < need_pcm || p->chunk_words < need_words || !p->d_chunk_pcm[0] || !p->d_chunk_words[0]) {
+        for (int i = 0; i < 3; i++) {                                    /* the chunk buffers are shared with the batch front end: same sizes for all three */
+            LBAD_CUDA_TRY(cudaStreamSynchronize(p->copy_streams[i]));
+            cudaFree(p->d_chunk_pcm[i]); cudaFree(p->d_chunk_words[i]); cudaFree(p->d_chunk_i16[i]);
+            p->d_chunk_pcm[i] = nullptr; p->d_chunk_words[i] = nullptr; p->d_chunk_i16[i] = nullptr;
+        }
+        LBAD_CUDA_TRY(cudaStreamSynchronize(p->stream));
+        p->chunk_pcm_floats = p->chunk_words = p->chunk_i16 = 0;
+        LBAD_CUDA_TRY(cudaMalloc(&p->d_chunk_pcm[0], need_pcm * sizeof(float)));
+        LBAD_CUDA_TRY(cudaMalloc(&p->d_chunk_words[0], need_words * sizeof(uint32_t)));
+        p->chunk_pcm_floats = need_pcm; p->chunk_words = need_words;
+    }
+    if (!p->d_score) { LBAD_CUDA_TRY(cudaMalloc(&p->d_score, sizeof(float))); LBAD_CUDA_TRY(cudaHostAlloc(&p->h_score, sizeof(float), cudaHostAllocDefault)); }
+    cudaStream_t s = p->stream;
+    float* d1 = p->d_chunk_pcm[0]; float* d2 = d1 + pad1;
+    uint32_t* w1 = p->d_chunk_words[0]; uint32_t* w2 = w1 + f1 * W2;
+    LBAD_CUDA_TRY(cudaMemcpyAsync(d1, h1, n1 * sizeof(float), cudaMemcpyHostToDevice, s));
+    LBAD_CUDA_TRY(cudaMemcpyAsync(d2, h2, n2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc;
+    if (n1 == n2) rc = extract_device_slot(p, d1, 2, n1, pad1, w1, nullptr, nullptr, 0, s, 1);
+    else {
+        rc = extract_device_slot(p, d1, 1, n1, pad1, w1, nullptr, nullptr, 0, s, 1);
+        if (rc == LBAD_OK) rc = extract_device_slot(p, d2, 1, n2, pad2, w2, nullptr, nullptr, 0, s, 1);
+    }
+    if (rc == LBAD_OK) { rc = lbadcu_compare_pair_device(p->g.words_per_plane, pairs, w1, (uint32_t)f1, w2, (uint32_t)f2, p->d_score, s); p->launches++; }
+    if (rc != LBAD_OK) { cudaStreamSynchronize(s); return rc; }
+    LBAD_CUDA_TRY(cudaMemcpyAsync(p->h_score, p->d_score, sizeof(float), cudaMemcpyDeviceToHost, s));
+    LBAD_CUDA_TRY(cudaStreamSynchronize(s));
+    *out = *p->h_score;
+    return LBAD_OK;
 }

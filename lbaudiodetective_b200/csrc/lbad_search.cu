@@ -691,6 +691,17 @@ struct PairCtx {
 thread_local PairCtx g_pair;
 }
 
+extern "C" int lbadcu_compare_pair_device(uint32_t W, uint32_t pairs, const uint32_t* d_w1, uint32_t c1, const uint32_t* d_w2, uint32_t c2, float* d_out, void* stream) {
+    if ((W != 2 && W != 4 && W != 8) || !d_out || (c1 && !d_w1) || (c2 && !d_w2)) return LBAD_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (pairs > 32 * W) pairs = 32 * W;
+    if (W == 2) compare_pair_kernel<2><<<1, 128, 0, s>>>(d_w1, c1, d_w2, c2, pairs, d_out);
+    else if (W == 4) compare_pair_kernel<4><<<1, 128, 0, s>>>(d_w1, c1, d_w2, c2, pairs, d_out);
+    else compare_pair_kernel<8><<<1, 128, 0, s>>>(d_w1, c1, d_w2, c2, pairs, d_out);
+    LBAD_CUDA_TRY(cudaGetLastError());
+    return LBAD_OK;
+}
+
 extern "C" int lbadcu_compare_pair(uint32_t W, uint32_t pairs, const uint32_t* w1, uint32_t c1, const uint32_t* w2, uint32_t c2, float* out) {
     if ((W != 2 && W != 4 && W != 8) || !out || (c1 && !w1) || (c2 && !w2)) return LBAD_ERR_ARG;
     if (lbadcu_device_available() != LBAD_OK) { set_error("no CUDA device available (this library has no CPU fallback)"); return LBAD_ERR_NODEVICE; }

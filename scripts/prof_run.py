@@ -58,4 +58,9 @@ if a.what == "latency":
         fn(); t0 = time.perf_counter()
         for _ in range(200): fn()
         print("%-30s %.1f us per call" % (name, (time.perf_counter() - t0) / 200 * 1e6))
+    # what the two kernels themselves take for one 10 s clip (6 frames: the GPU is all but empty, so this is latency, not throughput)
+    d.kernel_timing(enable=True, reset=True); d.kernel_timing(enable=True, reset=True, transform=True)
+    for _ in range(50): d.process_pcm(x)
+    n1, ms1 = d.kernel_timing(enable=False, reset=True); n2, ms2 = d.kernel_timing(enable=False, reset=True, transform=True)
+    print("kernels for one 10 s clip: FFT + bands %.1f us, Haar/select %.1f us" % (1e3 * ms1 / max(n1, 1), 1e3 * ms2 / max(n2, 1)))
 print("prof_run done")

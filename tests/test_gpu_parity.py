@@ -343,6 +343,28 @@ def test_compare_pcm_config1(lb, config1):
     assert np.float32(f0.compare(f1, 100)) == config1["score_01_r100"]
 
 
+def test_compare_pcm_equals_its_three_steps(lb, port):
+    """LBAudioDetectiveComparePCM runs upload, fingerprinting and comparison as one device pipeline (one two-clip batch when the lengths
+    agree): the match must be the one of ProcessPCM twice + CompareToFingerprint (LBAudioDetective.m:442-464), bit for bit, for either
+    argument order, any range, growing and shrinking clips, and with the batch entry point used in between (they share device buffers)."""
+    d = lb.Detective()
+    clips = {n: port.synth_clip(300 + i, n) for i, n in enumerate((55120, 55121, 165360, 16536, 12288, 400000))}
+    fps = {n: d.process_pcm(x) for n, x in clips.items()}
+    for a, b in ((55120, 55120), (55120, 55121), (55120, 165360), (165360, 55120), (16536, 165360), (12288, 16536), (400000, 55120), (55120, 16536)):
+        for rng in (0, 200, 100, 7, 1000):
+            want = np.float32(fps[a].compare(fps[b], rng if rng else 200))
+            assert np.float32(d.compare_pcm(clips[a], clips[b], rng)) == want, (a, b, rng)
+        if a == 165360:
+            w = d.process_batch(np.stack([clips[55120], clips[55121][:55120]]))
+            assert np.array_equal(w[0], fps[55120].packed())
+    assert np.float32(d.compare_pcm(clips[55120], clips[55120], 0)) == 1.0
+    # a clip too short for one subfingerprint takes the step-by-step route: compared with an empty fingerprint the match is 0 (FP.m:133)
+    assert d.compare_pcm(clips[55120], clips[55120][:9000], 0) == 0.0
+    d2 = lb.Detective(); d2.set_window_size(1024); d2.set_subfingerprint_length(100)
+    f = [d2.process_pcm(clips[n]) for n in (55120, 165360)]
+    assert np.float32(d2.compare_pcm(clips[55120], clips[165360], 0)) == np.float32(f[0].compare(f[1], 100))
+
+
 def rank_sign_codes(rng, n, count, L):
     sign = rng.integers(0, 2, size=(n, count, L // 2))
     out = np.zeros((n, count, L), np.uint8); out[..., 0::2] = sign == 0; out[..., 1::2] = sign == 1
