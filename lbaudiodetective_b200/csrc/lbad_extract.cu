@@ -644,13 +644,19 @@ static FusedSmemLayout fused_layout(uint32_t span_floats) {
 /* R: lanes per window in pass 1 = points of the pass-2 DFT; window = 64 R samples, 32/R windows per warp (see lbad_math.cuh).
  * STATIC_RANGE (R = 32 only): the band table is the reference-default one (bins [86, 759)), so the rows of 32 bins that need
  * the real split are k2 = 2..23 at compile time; otherwise the range is a (warp-uniform) run-time value. */
-template <int R, bool STATIC_RANGE, bool CARRY>
+/* SUBS: CTA iterations per frame.  1 for throughput (a frame per iteration: every warp carries its half transform over 16 windows).
+ * 8 for latency, when a call brings fewer frames than half the CTAs the device holds (a single clip, LBAudioDetectiveProcessPCM):
+ * a frame is then spread over eight CTAs of 16 windows, two per warp — same windows, same arithmetic (a carried half transform and a
+ * recomputed one are the same instructions on the same samples), one eighth of the serial chain. */
+template <int R, bool STATIC_RANGE, bool CARRY, int SUBS = 1>
 __global__ void __launch_bounds__(FUSED_THREADS, 2)
 bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, const float4* __restrict__ g_tw1, const float4* __restrict__ g_tw2,
                    const Geo g, const BandTable bt, const FusedSmemLayout L, const uint32_t span_floats,
                    const uint32_t total_frames, const int use_tma, const uint32_t frame0) {
     static_assert(!STATIC_RANGE || R == 32, "the compile-time band rows belong to the 2048-sample window");
     static_assert(!CARRY || R == 32, "half transforms are carried between windows only in the one-window-per-warp layout");
+    static_assert(SUBS == 1 || CARRY, "frames are split between CTAs only in the carried layout");
+    constexpr uint32_t UNIT_ROWS = LBAD_ROWS_PER_FRAME / SUBS;      /* windows per CTA iteration */
     constexpr int S = 32 / R;                                /* windows per warp */
     constexpr int M = 32 * R;                                /* complex points per window = bins of the half spectrum */
     extern __shared__ __align__(128) unsigned char smem[];
@@ -683,10 +689,10 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
     const float scale_m1 = g.inv_pos_scale - 1.0f;
     const int my_win = lane / R, n2 = lane % R;              /* pass 1: which of the warp's windows this lane loads, and its column */
 
-    auto frame_src = [&](uint32_t fl) -> const float* {                        /* fl: frame index inside this launch's slab */
-        const uint32_t f = frame0 + fl;
+    auto frame_src = [&](uint32_t ul) -> const float* {                        /* ul: unit (frame x SUBS + part) index inside this launch's slab */
+        const uint32_t f = frame0 + ul / SUBS, part = ul % SUBS;
         const uint32_t clip = f / g.frames_per_clip, fr = f % g.frames_per_clip;
-        return pcm + (uint64_t)clip * g.clip_stride + (uint64_t)fr * LBAD_ROWS_PER_FRAME * hop;   /* m:262-290 */
+        return pcm + (uint64_t)clip * g.clip_stride + ((uint64_t)fr * LBAD_ROWS_PER_FRAME + part * UNIT_ROWS) * hop;   /* m:262-290 */
     };
 
     uint32_t f = blockIdx.x, parity = 0;
@@ -701,7 +707,7 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
         }
 
         /* ---- the frame's 128 windows, S at a time per warp, round-robin over the warps: FFT -> bands -> image rows ---- */
-        constexpr int ITERS = (int)LBAD_ROWS_PER_FRAME / (FUSED_WARPS * S);
+        constexpr int ITERS = (int)UNIT_ROWS / (FUSED_WARPS * S);
         /* CARRY (R == 32 and hop == 64 samples): a warp takes ITERS CONSECUTIVE windows, one hop = one n1 step apart, so the
          * 16-point transform of a window's odd-n1 inputs is carried over as the even-n1 transform of the next window (dft16 /
          * dit32_combine in lbad_math.cuh): half the sample loads and 48 instead of 80 butterflies in pass 1. */
@@ -848,7 +854,7 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                     for (uint32_t k = bt.klow[my_band]; k < bt.khigh[my_band]; k++) { const float e = v[k]; if (e <= 3.402823466e+38f) tot += e; }
                 }
                 /* the 32 lanes fill one 128-byte line of the image row */
-                images[((size_t)f * LBAD_ROWS_PER_FRAME + row0 + s) * 32 + my_band] = __fdiv_rn(tot, divisor);
+                images[((size_t)f * UNIT_ROWS + row0 + s) * 32 + my_band] = __fdiv_rn(tot, divisor);      /* f counts units: unit f holds rows [f UNIT_ROWS, (f + 1) UNIT_ROWS) of the slab */
             }
             __syncwarp();
         }
@@ -882,6 +888,7 @@ struct lbadcu_plan {
     int stage_mode = -1;      /* -1 auto, 0 plain loads, 1 TMA (env LBAD_STAGE=ldg|tma) */
     bool transform_generic = false;      /* env LBAD_TRANSFORM=generic: lbadcu_transform_images_host uses the any-geometry Haar/select kernel */
     uint32_t slab_frames_cap = 1u << 18;
+    int force_subs = 0;                  /* env LBAD_SUBFRAMES=1|8: pin the CTA iterations per frame (tests); 0 = by frame count */
     float *d_score = nullptr, *h_score = nullptr;      /* lbadcu_compare_pcm_host: the match on the device and its pinned landing place */
 };
 
@@ -1015,6 +1022,7 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
                    fused_layout((uint32_t)span).total_bytes <= p->smem_optin);
     const char* st = getenv("LBAD_STAGE");
     p->stage_mode = st ? (strcmp(st, "tma") == 0 ? 1 : strcmp(st, "ldg") == 0 ? 0 : -1) : -1;
+    if (const char* sb = getenv("LBAD_SUBFRAMES")) p->force_subs = atoi(sb) == 8 ? 8 : atoi(sb) == 1 ? 1 : 0;
     if (const char* tf = getenv("LBAD_TRANSFORM")) p->transform_generic = strcmp(tf, "generic") == 0;
     if (const char* sf = getenv("LBAD_SLAB_FRAMES")) { const unsigned long v = strtoul(sf, nullptr, 10); if (v >= 1 && v <= (1u << 18)) p->slab_frames_cap = (uint32_t)v; }
     *out = p;
@@ -1090,13 +1098,16 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
     if (fused && !p->fused_ok) return LBAD_ERR_ARG;
     if (fused) {
         /* fast path: FFT + bands kernel -> spectral images (global, L2-friendly 16 KB each) -> Haar/select/pack kernel */
-        const uint32_t span = 127u * g.stride + g.window;
+        const bool carry = g.window == 2048 && g.stride == 64;           /* consecutive windows one pass-1 input apart: half transforms are shared */
+        /* few frames (a single clip): eight CTAs per frame, so the call's latency is two windows per warp instead of sixteen */
+        const uint32_t subs = !carry ? 1u : p->force_subs ? (uint32_t)p->force_subs : (total_frames <= (uint32_t)p->sm_count ? 8u : 1u);
+        const uint32_t span = (LBAD_ROWS_PER_FRAME / subs - 1u) * g.stride + g.window;
         const FusedSmemLayout L = fused_layout(span);
         /* TMA bulk copies need 16-byte aligned sources and sizes */
         bool tma_ok = ((uintptr_t)d_pcm % 16 == 0) && (clip_stride % 4 == 0) && (g.stride % 4 == 0);
         if (p->stage_mode == 0) tma_ok = false;
-        const bool carry = g.window == 2048 && g.stride == 64;           /* consecutive windows one pass-1 input apart: half transforms are shared */
-        auto kern = carry ? (p->static_range ? bands_fused_kernel<32, true, true> : bands_fused_kernel<32, false, true>)
+        auto kern = carry ? (subs == 8 ? (p->static_range ? bands_fused_kernel<32, true, true, 8> : bands_fused_kernel<32, false, true, 8>)
+                                       : (p->static_range ? bands_fused_kernel<32, true, true> : bands_fused_kernel<32, false, true>))
                   : g.window == 2048 ? bands_fused_kernel<32, false, false> : g.window == 1024 ? bands_fused_kernel<16, false, false>
                   : g.window == 512 ? bands_fused_kernel<8, false, false> : bands_fused_kernel<4, false, false>;
         LBAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes));
@@ -1117,9 +1128,10 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
             float* imgs = d_images ? d_images : p->d_scratch[slot];
             /* a slab starts at frame f0 of the flattened (clip, frame) order: hand the kernel a view that starts there */
             Geo gs = g;
-            const uint32_t grid = nf < cap ? nf : cap;
+            const uint32_t units = nf * subs;
+            const uint32_t grid = units < cap ? units : cap;
             p->timer.begin(s);
-            kern<<<grid, FUSED_THREADS, L.total_bytes, s>>>(d_pcm, imgs, p->d_tw1, p->d_tw2, gs, p->bt, L, span, nf, tma_ok ? 1 : 0, f0);
+            kern<<<grid, FUSED_THREADS, L.total_bytes, s>>>(d_pcm, imgs, p->d_tw1, p->d_tw2, gs, p->bt, L, span, units, tma_ok ? 1 : 0, f0);
             p->timer.end(s);
             p->launches++;
             LBAD_CUDA_TRY(cudaGetLastError());

@@ -257,6 +257,30 @@ def test_slabs_and_staging_variants_agree(lb, port, monkeypatch):
     assert np.array_equal(lb.Detective().process_batch(pcm), want)
 
 
+def test_frames_split_between_ctas_agree(lb, port, monkeypatch):
+    """Calls that bring few frames (a single clip) spread each frame over eight CTAs of 16 windows, big batches give a CTA a whole
+    frame: the same spectral images, bit for bit — both ways forced on the same input, by TMA and by plain loads, and as it happens by
+    itself (one clip alone against the clip inside a batch of 200 frames)."""
+    x = port.synth_clip(77, 165360)
+    out = {}
+    for subs in ("1", "8"):
+        monkeypatch.setenv("LBAD_SUBFRAMES", subs)
+        img, haar, bits = lb.Detective().process_stages(x, fused=True)
+        monkeypatch.setenv("LBAD_STAGE", "ldg")
+        img2, _, bits2 = lb.Detective().process_stages(x[:165001], fused=True)       # odd length: plain-load staging, 19 frames all the same
+        monkeypatch.delenv("LBAD_STAGE")
+        out[subs] = (img, bits, img2, bits2)
+    monkeypatch.delenv("LBAD_SUBFRAMES")
+    assert out["1"][0].shape == (19, 128, 32)
+    for a, b in zip(out["1"], out["8"]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(out["1"][0], out["1"][2])
+    pcm = np.stack([port.synth_clip(500 + i, 82680) for i in range(23)])     # 207 frames: a frame per CTA
+    d = lb.Detective(); batch = d.process_batch(pcm)
+    for i in (0, 11, 22):
+        assert np.array_equal(d.process_pcm(pcm[i]).packed(), batch[i])      # 9 frames: eight CTAs per frame
+
+
 def test_device_resident_batch(lb, port):
     import torch
     d = lb.Detective(); n, clip_len = 64, 165360
