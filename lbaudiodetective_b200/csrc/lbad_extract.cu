@@ -888,6 +888,7 @@ struct lbadcu_plan {
     int stage_mode = -1;      /* -1 auto, 0 plain loads, 1 TMA (env LBAD_STAGE=ldg|tma) */
     bool transform_generic = false;      /* env LBAD_TRANSFORM=generic: lbadcu_transform_images_host uses the any-geometry Haar/select kernel */
     uint32_t slab_frames_cap = 1u << 18;
+    struct { const void* fn; uint32_t smem; int per_sm; } occ_cache[8] = {};      /* per kernel variant: opt-in shared memory set, resident CTAs per SM */
     int force_subs = 0;                  /* env LBAD_SUBFRAMES=1|8: pin the CTA iterations per frame (tests); 0 = by frame count */
     float *d_score = nullptr, *h_score = nullptr;      /* lbadcu_compare_pcm_host: the match on the device and its pinned landing place */
 };
@@ -1110,10 +1111,15 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
                                        : (p->static_range ? bands_fused_kernel<32, true, true> : bands_fused_kernel<32, false, true>))
                   : g.window == 2048 ? bands_fused_kernel<32, false, false> : g.window == 1024 ? bands_fused_kernel<16, false, false>
                   : g.window == 512 ? bands_fused_kernel<8, false, false> : bands_fused_kernel<4, false, false>;
-        LBAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total_bytes));
         int per_sm = 0;
-        LBAD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, L.total_bytes));
-        if (per_sm < 1) per_sm = 1;
+        for (auto& c : p->occ_cache) if (c.fn == (const void*)kern && c.smem == L.total_bytes) per_sm = c.per_sm;
+        if (!per_sm) {                                                    /* first launch of this variant with this footprint */
+            /* the attribute is a ceiling shared by every plan of the process: raise it to the device's limit once, never lower it */
+            LBAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_optin));
+            LBAD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, L.total_bytes));
+            if (per_sm < 1) per_sm = 1;
+            for (auto& c : p->occ_cache) if (!c.fn) { c.fn = (const void*)kern; c.smem = L.total_bytes; c.per_sm = per_sm; break; }
+        }
         const uint32_t cap = (uint32_t)(p->sm_count * per_sm);
         const uint32_t slab_cap = p->slab_frames_cap;                     /* <= 4 GB of images per slab (LBAD_SLAB_FRAMES overrides, for tests) */
         const uint32_t slab_frames = d_images ? total_frames : (total_frames < slab_cap ? total_frames : slab_cap);
@@ -1265,7 +1271,7 @@ static int extract_host_impl(lbadcu_plan* p, const void* h_pcm_v, int sample_byt
         if (h_haar) LBAD_CUDA_TRY(cudaMemcpyAsync(h_haar + c0 * img_per_clip, d_haar, (size_t)nc * img_per_clip * sizeof(float), cudaMemcpyDeviceToHost, s));
         if (h_images || h_haar) LBAD_CUDA_TRY(cudaStreamSynchronize(s));      /* the dump buffers are shared between chunks */
     }
-    for (int i = 0; i < 3; i++) LBAD_CUDA_TRY(cudaStreamSynchronize(p->copy_streams[i]));
+    if (nbuf > 1) { for (int i = 0; i < 3; i++) LBAD_CUDA_TRY(cudaStreamSynchronize(p->copy_streams[i])); }      /* one chunk: everything ran on the plan's stream */
     LBAD_CUDA_TRY(cudaStreamSynchronize(p->stream));
     return rc;
 }
