@@ -385,20 +385,123 @@ compare_pair_kernel(const uint32_t* __restrict__ wa, const uint32_t ca, const ui
 /* (score desc, clip index asc) strict order; a is "better" than b */
 __device__ __forceinline__ bool better(float sa, uint32_t ia, float sb, uint32_t ib) { return sa > sb || (sa == sb && ia < ib); }
 
-/* One warp per query: k-way merge of n_lists partial top-k lists [list][q][k] by repeated selection. */
+/* Few queries (at most FEW_MAX_Q — the server-style "identify one recording" call): lane = database clip instead of lane = query, so
+ * that every lane works when there is one query.  A lane walks its clip once; subfingerprint j of the clip meets query subfingerprints
+ * i = 0 .. cq - 1 and feeds the running sums of the offsets o = j - i, which therefore receive their terms in the order i = 0, 1, ..
+ * of FP.m:139-142 (a ring of cq partial sums; offset j - cq + 1 completes at step j).  Same arithmetic as the other search kernels:
+ * IEEE hits / possible, sequential f32 sum, IEEE mean, Apple MAX.  The warp keeps ONE top-k list per query (entry r in lane r): a batch
+ * of 32 scores is tested against the list's last entry with one ballot and the few that pass are inserted by shuffles. */
+constexpr uint32_t FEW_MAX_Q = 16, FEW_MAX_CQ = 6;
+template <int W>
+__global__ void __launch_bounds__(SEARCH_WARPS * 32)
+search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ offsets, const uint32_t n_clips, const uint32_t clip_base,
+                  const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t cq, const uint32_t pairs, const int k,
+                  const uint32_t clips_per_warp, float* __restrict__ part_sc, uint32_t* __restrict__ part_id, float* __restrict__ all_scores,
+                  const uint32_t total_warps) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5);
+    if (gw >= total_warps) return;
+    const uint32_t c_begin = gw * clips_per_warp, c_end = min(n_clips, c_begin + clips_per_warp);      /* clips_per_warp is a multiple of 32 */
+    const PairMask<W> mask = make_mask<W>(pairs);
+    const float fcq = (float)cq;
+    for (uint32_t q = 0; q < n_q; q++) {
+        uint32_t qw[FEW_MAX_CQ][2 * W];
+#pragma unroll
+        for (uint32_t i = 0; i < FEW_MAX_CQ; i++)
+#pragma unroll
+            for (int w = 0; w < 2 * W; w++) qw[i][w] = i < cq ? (__ldg(qwords + ((size_t)q * cq + i) * 2 * W + w) & mask.w[w % W]) : 0u;
+        float tsc = -1.0f; uint32_t tid = EMPTY_IDX;                           /* lane r < k: entry r of the warp's list, best first */
+        for (uint32_t c0 = c_begin; c0 < c_end; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const bool valid = c < c_end;
+            float best = 0.0f;                                                  /* FP.m:133 */
+            if (valid) {
+                const uint32_t s0 = offsets[c], cd = offsets[c + 1] - s0;     /* cd >= cq: the database side is fp1 (FP.m:123) */
+                float ring[FEW_MAX_CQ];
+#pragma unroll
+                for (uint32_t i = 0; i < FEW_MAX_CQ; i++) ring[i] = 0.0f;
+                for (uint32_t j = 0; j < cd; j++) {
+                    const uint32_t* src = db + ((size_t)s0 + j) * 2 * W;
+                    uint32_t dp[W], dm[W], cover[W];
+#pragma unroll
+                    for (int w = 0; w < W; w += 4) {                            /* subfingerprints are 8 W bytes apart: 16-byte aligned planes for W = 4, 8 */
+                        if constexpr (W >= 4) {
+                            const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + w)), b = __ldg(reinterpret_cast<const uint4*>(src + W + w));
+                            dp[w] = a.x; dp[w + 1] = a.y; dp[w + 2] = a.z; dp[w + 3] = a.w; dm[w] = b.x; dm[w + 1] = b.y; dm[w + 2] = b.z; dm[w + 3] = b.w;
+                        } else {
+                            const uint2 a = __ldg(reinterpret_cast<const uint2*>(src)), b = __ldg(reinterpret_cast<const uint2*>(src + W));
+                            dp[0] = a.x; dp[1] = a.y; dm[0] = b.x; dm[1] = b.y;
+                        }
+                    }
+#pragma unroll
+                    for (int w = 0; w < W; w++) { dp[w] &= mask.w[w]; dm[w] &= mask.w[w]; cover[w] = dp[w] | dm[w]; }
+                    const uint32_t possible = popc_words<W>(cover);            /* FP.m:159-160 */
+                    const float fposs = small_uint_to_float(possible), rcp = possible ? __frcp_rn(fposs) : 0.0f;
+                    float r[FEW_MAX_CQ];
+#pragma unroll
+                    for (uint32_t i = 0; i < FEW_MAX_CQ; i++) {
+                        r[i] = 0.0f;
+                        if (i < cq) {                                           /* warp-uniform */
+                            uint32_t h[W];
+#pragma unroll
+                            for (int w = 0; w < W; w++) h[w] = hit_word2(dp[w], dm[w], qw[i][w], qw[i][W + w]);  /* FP.m:162-167 */
+                            r[i] = ratio_exact(popc_words<W>(h), fposs, rcp);   /* FP.m:171-175 */
+                        }
+                    }
+                    /* offset j - i gets its term number i: in decreasing i, so that ring[i - 1] is still the sum of terms 0 .. i - 1 */
+#pragma unroll
+                    for (int i = (int)FEW_MAX_CQ - 1; i >= 1; i--) ring[i] = __fadd_rn(ring[i - 1], r[i]);
+                    ring[0] = __fadd_rn(0.0f, r[0]);
+                    if (j + 1 >= cq) {                                          /* offset j - cq + 1 is complete (FP.m:144) */
+                        float sum = ring[0];
+#pragma unroll
+                        for (uint32_t i = 1; i < FEW_MAX_CQ; i++) sum = (i + 1 == cq) ? ring[i] : sum;
+                        const float mean = __fdiv_rn(sum, fcq);
+                        best = (best < mean) ? mean : best;
+                    }
+                }
+                if (all_scores) all_scores[(size_t)q * n_clips + c] = best;
+            }
+            /* into the warp's list: first those that beat its last entry, one at a time */
+            const uint32_t cid = clip_base + c;
+            const float last_sc = __shfl_sync(0xffffffffu, tsc, k - 1); const uint32_t last_id = __shfl_sync(0xffffffffu, tid, k - 1);
+            uint32_t pass = __ballot_sync(0xffffffffu, valid && (last_id == EMPTY_IDX || better(best, cid, last_sc, last_id)));
+            while (pass) {
+                const int src = __ffs(pass) - 1; pass &= pass - 1;
+                const float cs = __shfl_sync(0xffffffffu, best, src); const uint32_t ci = __shfl_sync(0xffffffffu, cid, src);
+                const bool ahead = lane < k && tid != EMPTY_IDX && better(tsc, tid, cs, ci);      /* entries that stay in front of the newcomer: a prefix */
+                const int pos = __popc(__ballot_sync(0xffffffffu, ahead));
+                const float up_sc = __shfl_up_sync(0xffffffffu, tsc, 1); const uint32_t up_id = __shfl_up_sync(0xffffffffu, tid, 1);
+                if (lane < k) { if (lane > pos) { tsc = up_sc; tid = up_id; } else if (lane == pos) { tsc = cs; tid = ci; } }
+            }
+        }
+        if (lane < k) { part_sc[((size_t)gw * n_q + q) * k + lane] = tsc; part_id[((size_t)gw * n_q + q) * k + lane] = tid; }
+    }
+}
+
+/* One warp per (group of lists, query): k-way merge of the partial top-k lists [list][q][k] of the group by repeated selection into
+ * out[group][q][k].  group_size >= n_lists is the plain merge (one group); a search with few queries cuts the database into thousands
+ * of chunks to fill the device, and merges their lists in two levels (groups of MERGE_GROUP, then the groups) instead of letting one
+ * warp walk all of them.  The order (score desc, clip asc) is strict and every clip sits in exactly one list, so the top k of the
+ * groups' top k are the top k of everything. */
+constexpr uint32_t MERGE_GROUP = 64;
 __global__ void __launch_bounds__(128)
 merge_topk_kernel(const float* __restrict__ part_sc, const uint32_t* __restrict__ part_id, const uint32_t n_lists, const uint32_t n_q, const int k,
-                  float* __restrict__ out_sc, uint32_t* __restrict__ out_id) {
+                  float* __restrict__ out_sc, uint32_t* __restrict__ out_id, const uint32_t group_size) {
     const int lane = threadIdx.x & 31;
-    const uint32_t q = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (q >= n_q) return;
-    const uint32_t n_cand = n_lists * (uint32_t)k;
+    const uint32_t wq = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const uint32_t n_groups = (n_lists + group_size - 1) / group_size;
+    if (wq >= n_q * n_groups) return;
+    const uint32_t grp = wq / n_q, q = wq % n_q;
+    const uint32_t list0 = grp * group_size, lists = (n_lists - list0 < group_size) ? n_lists - list0 : group_size;
+    const uint32_t n_cand = lists * (uint32_t)k;
+    float* o_sc = out_sc + ((size_t)grp * n_q + q) * k; uint32_t* o_id = out_id + ((size_t)grp * n_q + q) * k;
     float last_s = INFINITY; uint32_t last_i = 0;                              /* everything is "after" (+inf, 0) */
     bool first = true;
     for (int r = 0; r < k; r++) {
         float bs = -2.0f; uint32_t bi = EMPTY_IDX; bool have = false;
         for (uint32_t t = lane; t < n_cand; t += 32) {
-            const uint32_t list = t / k, slot = t % k;
+            const uint32_t list = list0 + t / k, slot = t % k;
             const float s = part_sc[((size_t)list * n_q + q) * k + slot]; const uint32_t i = part_id[((size_t)list * n_q + q) * k + slot];
             if (i == EMPTY_IDX) continue;
             if (!first && !better(last_s, last_i, s, i)) continue;             /* already emitted */
@@ -410,7 +513,7 @@ merge_topk_kernel(const float* __restrict__ part_sc, const uint32_t* __restrict_
             const bool oh = __shfl_xor_sync(0xffffffffu, have ? 1 : 0, d) != 0;
             if (oh && (!have || better(os, oi, bs, bi))) { bs = os; bi = oi; have = true; }
         }
-        if (lane == 0) { out_sc[(size_t)q * k + r] = have ? bs : -1.0f; out_id[(size_t)q * k + r] = have ? bi : EMPTY_IDX; }
+        if (lane == 0) { o_sc[r] = have ? bs : -1.0f; o_id[r] = have ? bi : EMPTY_IDX; }
         if (have) { last_s = bs; last_i = bi; first = false; } else { last_s = -INFINITY; last_i = EMPTY_IDX; first = false; }
     }
 }
@@ -588,12 +691,16 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
         db->offsets_dirty = false;
     }
     const uint32_t n_qgroups = (n_q + 31) / 32;
+    const bool fast = n_clips > 0 && db->min_count >= cq && db->max_count <= (uint32_t)STAGE_SUBFPS && cq >= 1 && cq <= 6;
+    const bool few = fast && n_q <= FEW_MAX_Q && k <= 32;                 /* lane = clip: every lane works even for ONE query */
     uint32_t n_chunks = ((uint32_t)db->sm_count * 32 + n_qgroups - 1) / n_qgroups;       /* ~32 warps per SM */
+    if (few) n_chunks = std::min<uint32_t>((n_clips + 31) / 32, (uint32_t)db->sm_count * 32);      /* one list per warp, 32 clips per step */
     if (n_chunks > n_clips) n_chunks = n_clips;
     if (n_chunks < 1) n_chunks = 1;
-    const uint32_t cpc = n_clips ? (n_clips + n_chunks - 1) / n_chunks : 1;
+    uint32_t cpc = n_clips ? (n_clips + n_chunks - 1) / n_chunks : 1;
+    if (few) cpc = (cpc + 31) & ~31u;
     n_chunks = n_clips ? (n_clips + cpc - 1) / cpc : 1;
-    const size_t need = (size_t)n_chunks * n_q * k;
+    const size_t need = ((size_t)n_chunks + (n_chunks + MERGE_GROUP - 1) / MERGE_GROUP) * n_q * k;      /* chunk lists + (two-level merge) group lists */
     if (db->part_cap < need) {
         LBAD_CUDA_TRY(cudaStreamSynchronize(s));
         cudaFree(db->d_part_sc); cudaFree(db->d_part_id); db->d_part_sc = nullptr; db->d_part_id = nullptr;
@@ -602,7 +709,6 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
     }
     const uint32_t total_warps = n_chunks * n_qgroups;
     const uint32_t blocks = (total_warps + SEARCH_WARPS - 1) / SEARCH_WARPS;
-    const bool fast = n_clips > 0 && db->min_count >= cq && db->max_count <= (uint32_t)STAGE_SUBFPS && cq >= 1 && cq <= 6;
     const bool masked = pairs < db->pairs_full;       /* words beyond L are zero already; a mask is only needed for a shorter range */
     const size_t smem_fast = (size_t)SEARCH_WARPS * 2 * k * 32 * 4;
     const size_t smem_gen = (size_t)SEARCH_WARPS * ((size_t)2 * k * 32 + (size_t)cq * 2 * W * 32) * 4;
@@ -610,7 +716,12 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
     db->timer.begin(s);
 #define LBAD_FAST(WW, CC) launch_fast<WW, CC>(db, masked, n_chunks, smem_fast, s, d_q, n_q, pairs, (int)k, n_qgroups, cpc, d_all)
 #define LBAD_GEN(WW) launch_generic<WW>(db, blocks, smem_gen, s, d_q, n_q, cq, pairs, (int)k, n_qgroups, cpc, d_all, total_warps)
-    if (fast) {
+    if (few) {
+        const uint32_t fblocks = (n_chunks + SEARCH_WARPS - 1) / SEARCH_WARPS;
+        if (W == 2) search_few_kernel<2><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, d_all, n_chunks);
+        else if (W == 4) search_few_kernel<4><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, d_all, n_chunks);
+        else search_few_kernel<8><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, d_all, n_chunks);
+    } else if (fast) {
 #define LBAD_FAST_W(WW) switch (cq) { case 1: LBAD_FAST(WW, 1); break; case 2: LBAD_FAST(WW, 2); break; case 3: LBAD_FAST(WW, 3); break; \
                                       case 4: LBAD_FAST(WW, 4); break; case 5: LBAD_FAST(WW, 5); break; default: LBAD_FAST(WW, 6); break; }
         if (W == 2) { LBAD_FAST_W(2) } else if (W == 4) { LBAD_FAST_W(4) } else { LBAD_FAST_W(8) }
@@ -623,8 +734,17 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
     db->timer.end(s);
     db->launches++;
     LBAD_CUDA_TRY(cudaGetLastError());
-    merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_chunks, n_q, (int)k, d_scores, d_idx);
-    db->launches++;
+    if (n_chunks > 2 * MERGE_GROUP) {
+        /* many chunks (few queries): their lists are merged group by group, then the groups — behind the chunk lists in the same buffer */
+        const uint32_t n_groups = (n_chunks + MERGE_GROUP - 1) / MERGE_GROUP;
+        float* g_sc = db->d_part_sc + (size_t)n_chunks * n_q * k; uint32_t* g_id = db->d_part_id + (size_t)n_chunks * n_q * k;
+        merge_topk_kernel<<<(n_q * n_groups + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_chunks, n_q, (int)k, g_sc, g_id, MERGE_GROUP);
+        merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(g_sc, g_id, n_groups, n_q, (int)k, d_scores, d_idx, n_groups);
+        db->launches += 2;
+    } else {
+        merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_chunks, n_q, (int)k, d_scores, d_idx, n_chunks);
+        db->launches++;
+    }
     LBAD_CUDA_TRY(cudaGetLastError());
     return LBAD_OK;
 }
@@ -657,7 +777,7 @@ extern "C" int lbadcu_merge_topk_host(const float* h_sc, const uint32_t* h_id, u
     DevBuf<float> d_sc, d_o; DevBuf<uint32_t> d_id, d_oi;
     LBAD_CUDA_TRY(d_sc.alloc(n)); LBAD_CUDA_TRY(d_id.alloc(n)); LBAD_CUDA_TRY(d_o.alloc((size_t)n_q * k)); LBAD_CUDA_TRY(d_oi.alloc((size_t)n_q * k));
     LBAD_CUDA_TRY(cudaMemcpy(d_sc, h_sc, n * 4, cudaMemcpyHostToDevice)); LBAD_CUDA_TRY(cudaMemcpy(d_id, h_id, n * 4, cudaMemcpyHostToDevice));
-    merge_topk_kernel<<<(n_q + 3) / 4, 128>>>(d_sc, d_id, n_lists, n_q, (int)k, d_o, d_oi);
+    merge_topk_kernel<<<(n_q + 3) / 4, 128>>>(d_sc, d_id, n_lists, n_q, (int)k, d_o, d_oi, n_lists);
     LBAD_CUDA_TRY(cudaGetLastError());
     LBAD_CUDA_TRY(cudaMemcpy(o_sc, d_o, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost)); LBAD_CUDA_TRY(cudaMemcpy(o_id, d_oi, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost));
     return LBAD_OK;
@@ -666,7 +786,7 @@ extern "C" int lbadcu_merge_topk_host(const float* h_sc, const uint32_t* h_id, u
 /* same merge on lists that already live on the device (e.g. the output of an NCCL all-gather), enqueued on the caller's stream */
 extern "C" int lbadcu_merge_topk_device(const float* d_sc, const uint32_t* d_id, uint32_t n_lists, uint32_t n_q, uint32_t k, float* d_o_sc, uint32_t* d_o_id, void* stream) {
     if (!d_sc || !d_id || !d_o_sc || !d_o_id || n_lists == 0 || n_q == 0 || k == 0) return LBAD_ERR_ARG;
-    merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_sc, d_id, n_lists, n_q, (int)k, d_o_sc, d_o_id);
+    merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_sc, d_id, n_lists, n_q, (int)k, d_o_sc, d_o_id, n_lists);
     LBAD_CUDA_TRY(cudaGetLastError());
     return LBAD_OK;
 }

@@ -416,6 +416,38 @@ def test_search_scores_and_topk_bit_exact(lb, checker, L, q_count, db_count, rng
     assert db.compares_per_query(q_count) == n_db * (abs(db_count - q_count) + 1) * min(db_count, q_count)
 
 
+@pytest.mark.parametrize("L,q_count,db_count,rng_len,n_q", [(200, 6, 19, 0, 1), (200, 6, 19, 77, 5), (200, 1, 5, 0, 16), (100, 3, 7, 0, 2), (100, 1, 5, 31, 7),
+                                                             (400, 6, 19, 300, 3), (400, 2, 9, 0, 16), (200, 6, 6, 0, 4), (200, 4, 40, 0, 2)])
+def test_few_query_kernel_bit_exact(lb, checker, L, q_count, db_count, rng_len, n_q):
+    """Up to 16 queries run with lane = clip (search_few_kernel): the whole score matrix and the top-k must equal the oracle's, for
+    every word count (L = 100 / 200 / 400), shortened ranges, irregular codes ('00' and '11' ranks on either side) and ragged clips."""
+    rng = np.random.default_rng(700 + L + q_count + db_count + rng_len + n_q)
+    n_db, k = 777, 10
+    dbb = rank_sign_codes(rng, n_db, db_count, L)
+    qb = rank_sign_codes(rng, n_q, q_count, L)
+    for q in range(0, n_q, 2):
+        c = int(rng.integers(0, n_db)); o = int(rng.integers(0, db_count - q_count + 1))
+        qb[q] = dbb[c, o:o + q_count]; flip = rng.random(qb[q].shape) < 0.02; qb[q] = np.where(flip, 1 - qb[q], qb[q])
+    dbb[5, 1, 0:2] = 0; dbb[6, 0, 2:4] = 1; dbb[7, :, :] = 0                  # '00', '11', an all-zero clip (possible = 0 everywhere)
+    qb[-1, 0, 4:6] = 0
+    db = lb.Database(L); db.add_packed(lb.pack_booleans(dbb))
+    sc, idx, full = db.search_packed(lb.pack_booleans(qb), k, rng=rng_len, all_scores=True)
+    want, _ = checker.search(dbb, qb, rng_len if rng_len else L)
+    assert np.array_equal(full, want)
+    order = np.lexsort((np.arange(n_db)[None, :].repeat(n_q, 0), -want.astype(np.float64)), axis=1)[:, :k]
+    assert np.array_equal(idx, order.astype(np.uint32)) and np.array_equal(sc, np.take_along_axis(want, order, axis=1))
+    # ragged: clips of different lengths (all at least as long as the query) through the fingerprint API
+    if q_count <= 4:
+        db2 = lb.Database(L); counts = rng.integers(q_count, q_count + 9, 50)
+        fps = [rank_sign_codes(rng, 1, int(c), L)[0] for c in counts]
+        for f in fps: db2.add_fingerprint(lb.Fingerprint.from_booleans(f))
+        qf = lb.Fingerprint.from_booleans(fps[17][:q_count])
+        sc2, idx2 = db2.search([qf], k=5)
+        want2 = np.array([np.float32(checker.compare_fp(f, fps[17][:q_count], L)) for f in fps])
+        o2 = np.lexsort((np.arange(50), -want2.astype(np.float64)))[:5]
+        assert np.array_equal(idx2[0], o2.astype(np.uint32)) and np.array_equal(sc2[0], want2[o2]) and idx2[0, 0] == 17
+
+
 @pytest.mark.parametrize("L,q_count,db_count", [(200, 6, 19), (200, 1, 5), (100, 3, 7), (400, 2, 9)])
 def test_search_regular_codes_short_form(lb, checker, L, q_count, db_count):
     """Databases in which every rank carries exactly one sign bit take the kernel's short form (one LOP3 per word, no M plane);
@@ -483,6 +515,20 @@ def test_topk_with_fewer_clips_than_k(lb):
     db.add_packed(lb.pack_booleans(rank_sign_codes(rng, 3, 6, 200)))
     sc, idx = db.search_packed(lb.pack_booleans(rank_sign_codes(rng, 2, 6, 200)), k=8)
     assert (idx[:, 3:] == 0xFFFFFFFF).all() and (sc[:, 3:] == -1).all() and (idx[:, :3] < 3).all()
+
+
+def test_few_queries_many_chunks_two_level_merge(lb):
+    """One to three queries cut the database into thousands of chunks (to fill the device) whose lists are merged in two levels:
+    the top-k must be the first k of the full score matrix ordered (score desc, clip asc), ties included."""
+    rng = np.random.default_rng(21); n_db = 20000
+    words = lb.pack_booleans(rank_sign_codes(rng, n_db, 7, 200))
+    db = lb.Database(200); db.add_packed(words)
+    for n_q in (1, 3):
+        q = words[rng.integers(0, n_db, n_q), 1:5]
+        sc, idx, full = db.search_packed(q, k=10, all_scores=True)
+        o = np.lexsort((np.broadcast_to(np.arange(n_db), full.shape), -full.astype(np.float64)), axis=1)[:, :10]
+        assert np.array_equal(idx, o.astype(np.uint32)) and np.array_equal(sc, np.take_along_axis(full, o, 1))
+        assert (sc[:, 0] == 1.0).all()
 
 
 def test_merge_topk_equals_single_list(lb):
