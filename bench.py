@@ -330,6 +330,17 @@ def main():
                   "queries": args.queries, "db_clips": args.db_clips, "k": 10, "scaling": "strong", "workload": "configs[3]: 1,000 x 6-subfp queries vs 1M x 19-subfp clips, 14 offsets",
                   "gpu_launches": db.kernel_launches}
 
+    if search is not None and world == 1:
+        # the server-style call: ONE query against the whole database (lane-per-clip kernel + two-level merge), device-timed
+        for _ in range(2):
+            db.search_device(qw.data_ptr(), 1, 6, 10, d_sc.data_ptr(), d_idx.data_ptr(), stream=stream)
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(10):
+            db.search_device(qw.data_ptr(), 1, 6, 10, d_sc.data_ptr(), d_idx.data_ptr(), stream=stream)
+        q1.record(); torch.cuda.synchronize()
+        assert int(d_idx[0, 0].item()) == int(q_src[0]) and float(d_sc[0, 0].item()) == 1.0
+        search["single_query_ms"] = q0.elapsed_time(q1) / 10
     if search is not None and rank == 0 and "popc_gops_measured" in roofline:
         # the search is POPC-bound — 4 POPC per compare (one per 32-pair word) against the measured lane-POPC rate;
         # HBM only sees the database once per 128 queries
@@ -350,12 +361,29 @@ def main():
         cpu = {"value": v, "unit": "audio-hours/s", "cores": threads, "kind": chk.kind,
                "sample": "%d x 30 s clips of the same synthetic workload (%.1f s of wall time); float32 FFT stands in for vDSP" % (args.ref_clips, secs),
                "search_compares_per_s": cpu_search_baseline(chk, threads)}
+    # ---- configs[0] (the reference's own headline call): compare two 10 s clips through the compare-audio path, one call at a time ----
+    config1 = None
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle as o
+        chk = o.best(); cfg = o.Cfg.default()
+        a, b = chk.synth_clip(0, 55120), chk.synth_clip(1, 55120)
+        det.compare_pcm(a, b, 0)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            got = det.compare_pcm(a, b, 0)
+        gpu_us = (time.perf_counter() - t0) / 200 * 1e6
+        t0 = time.perf_counter()
+        for _ in range(3):
+            want = chk.compare_pcm(cfg, a, b, 0)
+        cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+        config1 = {"workload": "configs[0]: compare two synthetic 10 s clips through the compare-audio path (LBAudioDetectiveComparePCM), one call at a time, host buffers",
+                   "us_per_call": gpu_us, "match": got, "reference_ms_per_call": cpu_ms, "reference_match": want, "reference_kind": chk.kind, "reference_cores": 1}
     line = {"metric": "audio-hours/s fingerprinted", "value": value, "unit": "audio-hours/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: batch fingerprint extraction of %d synthetic 30 s clips per GPU (FFT+band-energy kernel, then Haar+top-t+pack kernel)" % n_clips,
                        "clips_per_gpu": n_clips, "clip_seconds": 30, "window": 2048, "stride": 64, "bands": 32, "subfingerprint_length": 200,
                        "l2_policy": "inputs (%.1f GB per GPU) larger than L2" % (n_clips * CLIP_LEN * 4 / 1e9)},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "search": search}
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "search": search, "config1": config1}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -26,5 +26,10 @@ th, tb = d.transform_images(imgs)
 hi = p.synth_clip(9, 3 * 44100 + 1234, 44100.0)          # not a whole number of tiles or pairs
 r1 = d.resample(hi); fr = d.process_recorded_pcm(hi)
 d3 = lb.Detective(); d3.set_recording_rate(16000.0); r2 = d3.resample(p.synth_clip(9, 2 * 16000, 16000.0))
+# compare-audio as one device pipeline (equal and unequal lengths); few-query search (lane = clip) with the two-level merge of its chunk lists
+m1 = d.compare_pcm(pcm[0], pcm[1], 0); m2 = d.compare_pcm(pcm[0], pcm[1][:30000], 0)
+big = lb.Database(200); big.add_packed(np.tile(w, (1500, 1, 1)))            # 4,500 clips -> 141 chunk lists
+sc4, idx4 = big.search_packed(w[:1, :6], k=3); sc5, idx5 = big.search_packed(w[:, 1:4], k=10)
+assert idx4[0, 0] == 0 and sc4[0, 0] == 1.0 and m1 > 0.0
 f0 = lb.Fingerprint(200); f0.add_packed(w[0]); f1 = lb.Fingerprint(200); f1.add_packed(w[1])
 print("ok", tb.shape, r1.shape, r2.shape, fr.count, w.shape, (bits != bits2).sum(), b3.shape, sc[:, 0], f0.compare(f1, 200), lb.merge_topk(np.stack([sc, sc]), np.stack([idx, idx + 10]))[1][0])
