@@ -136,10 +136,13 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
 search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ meta, const uint32_t* __restrict__ offsets, const uint32_t n_clips,
                    const uint32_t clip_base, const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t pairs, const int k,
                    const uint32_t n_qgroups, const uint32_t clips_per_chunk, float* __restrict__ part_sc, uint32_t* __restrict__ part_id,
-                   float* __restrict__ all_scores, const uint32_t groups_per_chunk, const int db_regular) {
+                   float* __restrict__ all_scores, const uint32_t groups_per_chunk, const int db_regular, const uint32_t rep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t chunk = blockIdx.x / groups_per_chunk, qg = (blockIdx.x % groups_per_chunk) * SEARCH_WARPS + wid;
+    /* rep > 1 (one or two query groups, i.e. at most 64 queries): the warps a CTA would leave idle take a share of the tile's clips —
+     * warp wid serves query group wid % n_qgroups on the clips c0 + sub, c0 + sub + rep, .. (sub = wid / n_qgroups) and keeps its own list */
+    const uint32_t chunk = blockIdx.x / groups_per_chunk;
+    const uint32_t qg = rep > 1 ? (uint32_t)wid % n_qgroups : (blockIdx.x % groups_per_chunk) * SEARCH_WARPS + wid, sub = rep > 1 ? (uint32_t)wid / n_qgroups : 0u;
     const uint32_t q = qg * 32 + lane;
     const bool qvalid = qg < n_qgroups && q < n_q;
     TopK top{reinterpret_cast<float*>(smem_raw) + (size_t)wid * 2 * k * 32, reinterpret_cast<uint32_t*>(smem_raw) + (size_t)wid * 2 * k * 32 + (size_t)k * 32, k, lane};
@@ -206,7 +209,7 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
         const uint32_t s_lo = offsets[c0];
         const uint32_t* tw = st_words + (size_t)buf * STAGE_SUBFPS * 2 * W;
         const float2* tm = st_meta + (size_t)buf * STAGE_SUBFPS;
-        if (qg < n_qgroups) for (uint32_t c = c0; c < c1; c++) {
+        if (qg < n_qgroups) for (uint32_t c = c0 + sub; c < c1; c += rep) {
             const uint32_t s0 = offsets[c] - s_lo, cnt = offsets[c + 1] - offsets[c];      /* warp-uniform */
             float best = 0.0f;                                                /* FP.m:133 */
             if (regular) for (uint32_t o = 0; o + CQ <= cnt; o++) {            /* FP.m:136, short form */
@@ -279,8 +282,8 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
         c0 = n0; c1 = n1; buf ^= 1;
     }
     if (qvalid) for (int r = 0; r < k; r++) {
-        part_sc[((size_t)chunk * n_q + q) * k + r] = top.sc[r * 32 + lane];
-        part_id[((size_t)chunk * n_q + q) * k + r] = top.id[r * 32 + lane];
+        part_sc[(((size_t)chunk * rep + sub) * n_q + q) * k + r] = top.sc[r * 32 + lane];
+        part_id[(((size_t)chunk * rep + sub) * n_q + q) * k + r] = top.id[r * 32 + lane];
     }
 }
 
@@ -649,7 +652,7 @@ extern "C" uint64_t lbadcu_db_compares_per_query(const lbadcu_db* db, uint32_t c
 
 template <int W, int CQ>
 static void launch_fast(lbadcu_db* db, bool masked, uint32_t n_chunks, size_t smem_topk, cudaStream_t s, const uint32_t* d_q, uint32_t n_q, uint32_t pairs, int k,
-                        uint32_t n_qgroups, uint32_t cpc, float* d_all) {
+                        uint32_t n_qgroups, uint32_t cpc, float* d_all, uint32_t rep) {
     const uint32_t n_clips = lbadcu_db_clips(db);
     const uint32_t total_warps = (n_qgroups + SEARCH_WARPS - 1) / SEARCH_WARPS;      /* = CTAs per clip chunk (passed in the last kernel argument) */
     const uint32_t blocks = n_chunks * total_warps;
@@ -657,11 +660,11 @@ static void launch_fast(lbadcu_db* db, bool masked, uint32_t n_chunks, size_t sm
     if (masked) {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         search_fast_kernel<W, CQ, true><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
-                                                                                db->d_part_sc, db->d_part_id, d_all, total_warps, db->regular ? 1 : 0);
+                                                                                db->d_part_sc, db->d_part_id, d_all, total_warps, db->regular ? 1 : 0, rep);
     } else {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         search_fast_kernel<W, CQ, false><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
-                                                                                 db->d_part_sc, db->d_part_id, d_all, total_warps, db->regular ? 1 : 0);
+                                                                                 db->d_part_sc, db->d_part_id, d_all, total_warps, db->regular ? 1 : 0, rep);
     }
 }
 
@@ -700,7 +703,9 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
     uint32_t cpc = n_clips ? (n_clips + n_chunks - 1) / n_chunks : 1;
     if (few) cpc = (cpc + 31) & ~31u;
     n_chunks = n_clips ? (n_clips + cpc - 1) / cpc : 1;
-    const size_t need = ((size_t)n_chunks + (n_chunks + MERGE_GROUP - 1) / MERGE_GROUP) * n_q * k;      /* chunk lists + (two-level merge) group lists */
+    const uint32_t rep = (fast && !few && n_qgroups <= 2) ? (uint32_t)SEARCH_WARPS / n_qgroups : 1u;      /* search_fast_kernel: lists per chunk */
+    const uint32_t n_lists = n_chunks * rep;
+    const size_t need = ((size_t)n_lists + (n_lists + MERGE_GROUP - 1) / MERGE_GROUP) * n_q * k;      /* chunk lists + (two-level merge) group lists */
     if (db->part_cap < need) {
         LBAD_CUDA_TRY(cudaStreamSynchronize(s));
         cudaFree(db->d_part_sc); cudaFree(db->d_part_id); db->d_part_sc = nullptr; db->d_part_id = nullptr;
@@ -714,7 +719,7 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
     const size_t smem_gen = (size_t)SEARCH_WARPS * ((size_t)2 * k * 32 + (size_t)cq * 2 * W * 32) * 4;
     if (!fast && smem_gen > db->smem_optin) return LBAD_ERR_ARG;
     db->timer.begin(s);
-#define LBAD_FAST(WW, CC) launch_fast<WW, CC>(db, masked, n_chunks, smem_fast, s, d_q, n_q, pairs, (int)k, n_qgroups, cpc, d_all)
+#define LBAD_FAST(WW, CC) launch_fast<WW, CC>(db, masked, n_chunks, smem_fast, s, d_q, n_q, pairs, (int)k, n_qgroups, cpc, d_all, rep)
 #define LBAD_GEN(WW) launch_generic<WW>(db, blocks, smem_gen, s, d_q, n_q, cq, pairs, (int)k, n_qgroups, cpc, d_all, total_warps)
     if (few) {
         const uint32_t fblocks = (n_chunks + SEARCH_WARPS - 1) / SEARCH_WARPS;
@@ -734,15 +739,15 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
     db->timer.end(s);
     db->launches++;
     LBAD_CUDA_TRY(cudaGetLastError());
-    if (n_chunks > 2 * MERGE_GROUP) {
-        /* many chunks (few queries): their lists are merged group by group, then the groups — behind the chunk lists in the same buffer */
-        const uint32_t n_groups = (n_chunks + MERGE_GROUP - 1) / MERGE_GROUP;
-        float* g_sc = db->d_part_sc + (size_t)n_chunks * n_q * k; uint32_t* g_id = db->d_part_id + (size_t)n_chunks * n_q * k;
-        merge_topk_kernel<<<(n_q * n_groups + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_chunks, n_q, (int)k, g_sc, g_id, MERGE_GROUP);
+    if (n_lists > 2 * MERGE_GROUP) {
+        /* many lists (few queries): merged group by group, then the groups — behind the chunk lists in the same buffer */
+        const uint32_t n_groups = (n_lists + MERGE_GROUP - 1) / MERGE_GROUP;
+        float* g_sc = db->d_part_sc + (size_t)n_lists * n_q * k; uint32_t* g_id = db->d_part_id + (size_t)n_lists * n_q * k;
+        merge_topk_kernel<<<(n_q * n_groups + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_lists, n_q, (int)k, g_sc, g_id, MERGE_GROUP);
         merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(g_sc, g_id, n_groups, n_q, (int)k, d_scores, d_idx, n_groups);
         db->launches += 2;
     } else {
-        merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_chunks, n_q, (int)k, d_scores, d_idx, n_chunks);
+        merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_lists, n_q, (int)k, d_scores, d_idx, n_lists);
         db->launches++;
     }
     LBAD_CUDA_TRY(cudaGetLastError());
