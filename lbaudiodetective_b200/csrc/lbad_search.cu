@@ -394,7 +394,7 @@ __device__ __forceinline__ bool better(float sa, uint32_t ia, float sb, uint32_t
  * of FP.m:139-142 (a ring of cq partial sums; offset j - cq + 1 completes at step j).  Same arithmetic as the other search kernels:
  * IEEE hits / possible, sequential f32 sum, IEEE mean, Apple MAX.  The warp keeps ONE top-k list per query (entry r in lane r): a batch
  * of 32 scores is tested against the list's last entry with one ballot and the few that pass are inserted by shuffles. */
-constexpr uint32_t FEW_MAX_Q = 16, FEW_MAX_CQ = 6;
+constexpr uint32_t FEW_MAX_Q = 8, FEW_MAX_CQ = 6;       /* beyond 8 queries the query-per-lane kernel (32 queries at the price of one) is the faster one */
 template <int W>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32)
 search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ offsets, const uint32_t n_clips, const uint32_t clip_base,
