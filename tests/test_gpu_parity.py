@@ -275,6 +275,14 @@ def test_frames_split_between_ctas_agree(lb, port, monkeypatch):
     for a, b in zip(out["1"], out["8"]):
         assert np.array_equal(a, b)
     assert np.array_equal(out["1"][0], out["1"][2])
+    # the same with a band table whose rows are only known at run time (another processing rate)
+    y = port.synth_clip(78, 60000, 6000.0); alt = {}
+    for subs in ("1", "8"):
+        monkeypatch.setenv("LBAD_SUBFRAMES", subs)
+        d6 = lb.Detective(); d6.set_sample_rate(6000.0)
+        alt[subs] = d6.process_stages(y, fused=True)
+    monkeypatch.delenv("LBAD_SUBFRAMES")
+    assert alt["1"][0].shape[0] == 7 and np.array_equal(alt["1"][0], alt["8"][0]) and np.array_equal(alt["1"][2], alt["8"][2])
     pcm = np.stack([port.synth_clip(500 + i, 82680) for i in range(23)])     # 207 frames: a frame per CTA
     d = lb.Detective(); batch = d.process_batch(pcm)
     for i in (0, 11, 22):
