@@ -423,19 +423,27 @@ search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
                 float ring[FEW_MAX_CQ];
 #pragma unroll
                 for (uint32_t i = 0; i < FEW_MAX_CQ; i++) ring[i] = 0.0f;
-                for (uint32_t j = 0; j < cd; j++) {
+                /* the words of subfingerprint j + 1 are requested before subfingerprint j is compared: the kernel waits on memory, not on arithmetic */
+                auto load_words = [&](const uint32_t j, uint32_t (&p)[W], uint32_t (&m)[W]) {
                     const uint32_t* src = db + ((size_t)s0 + j) * 2 * W;
+                    if constexpr (W >= 4) {                                     /* subfingerprints are 8 W bytes apart: 16-byte aligned planes for W = 4, 8 */
+#pragma unroll
+                        for (int w = 0; w < W; w += 4) {
+                            const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + w)), b = __ldg(reinterpret_cast<const uint4*>(src + W + w));
+                            p[w] = a.x; p[w + 1] = a.y; p[w + 2] = a.z; p[w + 3] = a.w; m[w] = b.x; m[w + 1] = b.y; m[w + 2] = b.z; m[w + 3] = b.w;
+                        }
+                    } else {
+                        const uint2 a = __ldg(reinterpret_cast<const uint2*>(src)), b = __ldg(reinterpret_cast<const uint2*>(src + W));
+                        p[0] = a.x; p[1] = a.y; m[0] = b.x; m[1] = b.y;
+                    }
+                };
+                uint32_t np[W], nm[W];
+                if (cd) load_words(0, np, nm);
+                for (uint32_t j = 0; j < cd; j++) {
                     uint32_t dp[W], dm[W], cover[W];
 #pragma unroll
-                    for (int w = 0; w < W; w += 4) {                            /* subfingerprints are 8 W bytes apart: 16-byte aligned planes for W = 4, 8 */
-                        if constexpr (W >= 4) {
-                            const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + w)), b = __ldg(reinterpret_cast<const uint4*>(src + W + w));
-                            dp[w] = a.x; dp[w + 1] = a.y; dp[w + 2] = a.z; dp[w + 3] = a.w; dm[w] = b.x; dm[w + 1] = b.y; dm[w + 2] = b.z; dm[w + 3] = b.w;
-                        } else {
-                            const uint2 a = __ldg(reinterpret_cast<const uint2*>(src)), b = __ldg(reinterpret_cast<const uint2*>(src + W));
-                            dp[0] = a.x; dp[1] = a.y; dm[0] = b.x; dm[1] = b.y;
-                        }
-                    }
+                    for (int w = 0; w < W; w++) { dp[w] = np[w]; dm[w] = nm[w]; }
+                    if (j + 1 < cd) load_words(j + 1, np, nm);
 #pragma unroll
                     for (int w = 0; w < W; w++) { dp[w] &= mask.w[w]; dm[w] &= mask.w[w]; cover[w] = dp[w] | dm[w]; }
                     const uint32_t possible = popc_words<W>(cover);            /* FP.m:159-160 */
