@@ -407,12 +407,17 @@ search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
     const uint32_t c_begin = gw * clips_per_warp, c_end = min(n_clips, c_begin + clips_per_warp);      /* clips_per_warp is a multiple of 32 */
     const PairMask<W> mask = make_mask<W>(pairs);
     const float fcq = (float)cq;
+    __shared__ __align__(16) uint32_t q_smem[SEARCH_WARPS][FEW_MAX_CQ][2 * W];
+    uint32_t (*qw)[2 * W] = q_smem[threadIdx.x >> 5];
     for (uint32_t q = 0; q < n_q; q++) {
-        uint32_t qw[FEW_MAX_CQ][2 * W];
-#pragma unroll
-        for (uint32_t i = 0; i < FEW_MAX_CQ; i++)
-#pragma unroll
-            for (int w = 0; w < 2 * W; w++) qw[i][w] = i < cq ? (__ldg(qwords + ((size_t)q * cq + i) * 2 * W + w) & mask.w[w % W]) : 0u;
+        /* the query's words sit in shared memory (one copy per warp, read back as broadcasts): in registers they would cost the kernel,
+         * which waits on memory, a third of its resident warps */
+        __syncwarp();
+        for (uint32_t t = lane; t < FEW_MAX_CQ * 2 * W; t += 32) {
+            const uint32_t i = t / (2 * W), w = t % (2 * W);
+            qw[i][w] = i < cq ? (__ldg(qwords + ((size_t)q * cq + i) * 2 * W + w) & mask.w[w % W]) : 0u;
+        }
+        __syncwarp();
         float tsc = -1.0f; uint32_t tid = EMPTY_IDX;                           /* lane r < k: entry r of the warp's list, best first */
         for (uint32_t c0 = c_begin; c0 < c_end; c0 += 32) {
             const uint32_t c = c0 + lane;
