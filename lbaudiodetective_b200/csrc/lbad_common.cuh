@@ -32,6 +32,17 @@ struct DevBuf {
     operator T*() const { return p; }
 };
 
+/* A half-built object on the error paths of a create function: destroyed on scope exit unless released */
+template <class T>
+struct Guard {
+    T* p; void (*destroy)(T*);
+    Guard(T* p_, void (*d)(T*)) : p(p_), destroy(d) {}
+    Guard(const Guard&) = delete;
+    Guard& operator=(const Guard&) = delete;
+    ~Guard() { if (p) destroy(p); }
+    T* release() { T* r = p; p = nullptr; return r; }
+};
+
 /* Device time of selected launches, measured with CUDA events on the launching stream. */
 struct LaunchTimer {
     bool enabled = false;

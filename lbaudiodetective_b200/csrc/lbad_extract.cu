@@ -960,6 +960,7 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     }
     if (kmin >= kmax) { kmin = 0; kmax = 1; }
     lbadcu_plan* p = new lbadcu_plan();
+    Guard<lbadcu_plan> guard(p, lbadcu_plan_destroy);                            /* the CUDA calls below return on failure */
     p->geo = *geo;
     LBAD_CUDA_TRY(cudaGetDevice(&p->device));
     cudaDeviceProp prop; LBAD_CUDA_TRY(cudaGetDeviceProperties(&prop, p->device));
@@ -1026,14 +1027,14 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     if (const char* sb = getenv("LBAD_SUBFRAMES")) p->force_subs = atoi(sb) == 8 ? 8 : atoi(sb) == 1 ? 1 : 0;
     if (const char* tf = getenv("LBAD_TRANSFORM")) p->transform_generic = strcmp(tf, "generic") == 0;
     if (const char* sf = getenv("LBAD_SLAB_FRAMES")) { const unsigned long v = strtoul(sf, nullptr, 10); if (v >= 1 && v <= (1u << 18)) p->slab_frames_cap = (uint32_t)v; }
-    *out = p;
+    *out = guard.release();
     return LBAD_OK;
 }
 
 extern "C" void lbadcu_plan_destroy(lbadcu_plan* p) {
     if (!p) return;
     cudaSetDevice(p->device);
-    cudaStreamSynchronize(p->stream);
+    if (p->stream) cudaStreamSynchronize(p->stream);
     p->timer.clear(); p->timer2.clear();
     cudaFree(p->d_tw_m); cudaFree(p->d_tw_n); cudaFree(p->d_tw1); cudaFree(p->d_tw2); for (int i = 0; i < 4; i++) cudaFree(p->d_scratch[i]); for (int i = 0; i < 3; i++) cudaFree(p->d_chunk_i16[i]);
     for (int i = 0; i < 3; i++) { cudaFree(p->d_chunk_pcm[i]); cudaFree(p->d_chunk_words[i]); if (p->copy_streams[i]) cudaStreamDestroy(p->copy_streams[i]); }

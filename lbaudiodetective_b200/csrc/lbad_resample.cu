@@ -227,6 +227,7 @@ extern "C" int lbadcu_resampler_create(const lbadcu_resample_design* d, lbadcu_r
     if (lbadcu_device_available() != LBAD_OK) { set_error("no CUDA device available (this library has no CPU fallback)"); return LBAD_ERR_NODEVICE; }
     if (!d || !d->hc || d->T2 == 0 || (d->D > 1 && !d->g)) return LBAD_ERR_ARG;
     lbadcu_resampler* r = new lbadcu_resampler();
+    Guard<lbadcu_resampler> guard(r, lbadcu_resampler_destroy);
     LBAD_CUDA_TRY(cudaGetDevice(&r->device));
     cudaDeviceProp prop; LBAD_CUDA_TRY(cudaGetDeviceProperties(&prop, r->device));
     r->sm_count = prop.multiProcessorCount;
@@ -241,14 +242,14 @@ extern "C" int lbadcu_resampler_create(const lbadcu_resample_design* d, lbadcu_r
     const size_t nhc = (size_t)(RS_PHASES + 1) * d->T2;
     /* shared layout: input tile, stage-1 tile (+8: the 64- and 128-bit sample loads of stage 2 may read up to seven floats past it), taps, padded coarse-phase rows */
     r->smem_base = (size_t)P.xs_floats + (((size_t)P.ny_max + 8 + 3) & ~3u) + (((size_t)P.T1 + 3) & ~3u) + (size_t)(RS_PHASES + 1) * ((d->T2 + 3) & ~3u);
-    if (r->smem_base * sizeof(float) > prop.sharedMemPerBlockOptin) { delete r; set_error("resampler: the filters for this rate pair do not fit in shared memory"); return LBAD_ERR_ARG; }
+    if (r->smem_base * sizeof(float) > prop.sharedMemPerBlockOptin) { set_error("resampler: the filters for this rate pair do not fit in shared memory"); return LBAD_ERR_ARG; }
     LBAD_CUDA_TRY(cudaMalloc(&r->d_hc, nhc * sizeof(float)));
     LBAD_CUDA_TRY(cudaMemcpy(r->d_hc, d->hc, nhc * sizeof(float), cudaMemcpyHostToDevice));
     LBAD_CUDA_TRY(cudaMalloc(&r->d_g, (P.T1 ? P.T1 : 1) * sizeof(float)));
     if (P.T1) LBAD_CUDA_TRY(cudaMemcpy(r->d_g, d->g, P.T1 * sizeof(float), cudaMemcpyHostToDevice));
     if (P.D == 4 && P.T1 == 49) LBAD_CUDA_TRY(cudaMemcpyToSymbol(c_g_d4, d->g, 49 * sizeof(float)));      /* the same 49 values whoever writes them */
     LBAD_CUDA_TRY(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
-    *out = r;
+    *out = guard.release();
     return LBAD_OK;
 }
 

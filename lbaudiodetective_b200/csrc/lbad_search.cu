@@ -566,22 +566,23 @@ extern "C" int lbadcu_db_create(uint32_t W, uint32_t pairs_full, lbadcu_db** out
     if ((W != 2 && W != 4 && W != 8) || pairs_full == 0 || pairs_full > 32 * W) return LBAD_ERR_ARG;
     if (lbadcu_device_available() != LBAD_OK) { set_error("no CUDA device available (this library has no CPU fallback)"); return LBAD_ERR_NODEVICE; }
     lbadcu_db* db = new lbadcu_db(); db->W = W; db->pairs_full = pairs_full;
+    Guard<lbadcu_db> guard(db, lbadcu_db_destroy);
     LBAD_CUDA_TRY(cudaGetDevice(&db->device));
     cudaDeviceProp prop; LBAD_CUDA_TRY(cudaGetDeviceProperties(&prop, db->device));
     db->sm_count = prop.multiProcessorCount; db->smem_optin = prop.sharedMemPerBlockOptin;
     LBAD_CUDA_TRY(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
     int e = upload_rcp(); if (e != LBAD_OK) return e;       /* per device; cheap enough to repeat per database */
-    *out = db;
+    *out = guard.release();
     return LBAD_OK;
 }
 
 extern "C" void lbadcu_db_destroy(lbadcu_db* db) {
     if (!db) return;
     cudaSetDevice(db->device);
-    cudaStreamSynchronize(db->stream);
+    if (db->stream) cudaStreamSynchronize(db->stream);
     db->timer.clear();
     cudaFree(db->d_words); cudaFree(db->d_meta); cudaFree(db->d_irregular); cudaFree(db->d_offsets); cudaFree(db->d_part_sc); cudaFree(db->d_part_id);
-    cudaStreamDestroy(db->stream);
+    if (db->stream) cudaStreamDestroy(db->stream);
     delete db;
 }
 
