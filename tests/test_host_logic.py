@@ -181,3 +181,8 @@ def test_no_gpu_means_loud_failure(lb):
         lb.Database(200)
     with pytest.raises(lb.LBADError):
         lb.microbench()
+    with pytest.raises(lb.LBADError) as err:                                  # the compare-audio pipeline has no CPU route either
+        d.compare_pcm(np.zeros(55120, np.float32), np.zeros(55120, np.float32), 0)
+    assert "-7001" in str(err.value)
+    with pytest.raises(lb.LBADError):
+        d.resample(np.zeros(44100, np.float32))
