@@ -156,7 +156,8 @@ def main():
     ap.add_argument("--no-search", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--microbench", action="store_true", help="also measure the FP32 / POPC / LOP3 pipe rates (roofline context)")
+    ap.add_argument("--microbench", action="store_true", help="(default; kept for old command lines) measure the FP32 / POPC / LOP3 pipe rates the rooflines are quoted against")
+    ap.add_argument("--no-microbench", action="store_true", help="skip the pipe-rate measurement (a fraction of a second)")
     args = ap.parse_args()
     guard_stdout()
     if args.impl == "reference":
@@ -253,7 +254,7 @@ def main():
                 "peak_source": peak_src, "kernel": "bands_fused_kernel (FFT + band energies)", "kernel_ms": kernel_ms, "second_kernel": "haar_select32_kernel", "second_kernel_ms": kernel2_ms, "launches_per_step": n_timed // max(args.steps, 1), "algorithmic_bytes_per_launch": algo_bytes,
                 "note": "FP32-issue bound, not HBM bound (235 flop per new PCM byte, SURVEY.md §8d); fp32 figures alongside",
                 "fp32_tflops_algorithmic": flops / (kernel_ms * 1e-3) / 1e12, "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12}
-    if args.microbench and rank == 0:
+    if not args.no_microbench and rank == 0:
         mb = lb.microbench(); roofline["fp32_peak_tflops_measured"] = mb["fp32_tflops"]; roofline["fp32_frac_of_measured"] = roofline["fp32_tflops_algorithmic"] / mb["fp32_tflops"]
         roofline["popc_gops_measured"] = mb["popc_gops"]; roofline["lop3_gops_measured"] = mb["lop3_gops"]
 
