@@ -49,11 +49,3 @@ def gather_and_merge_topk_device(d_scores, d_idx, stream=None):
                           stream if stream is not None else torch.cuda.current_stream().cuda_stream)
     return m_sc, m_id
 
-
-def merge_reference(scores: np.ndarray, indices: np.ndarray):
-    """numpy statement of the merge order (score desc, clip index asc) — used by tests to check the device merge."""
-    n_lists, n_q, k = scores.shape
-    s = scores.transpose(1, 0, 2).reshape(n_q, -1); i = indices.transpose(1, 0, 2).reshape(n_q, -1)
-    valid_last = np.where(i == 0xFFFFFFFF, 1, 0)
-    o = np.lexsort((i, -s.astype(np.float64), valid_last), axis=1)[:, :k]
-    return np.take_along_axis(s, o, 1), np.take_along_axis(i, o, 1)

@@ -19,10 +19,20 @@ def test_shard_range_partitions_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
+def merge_reference(scores, indices):
+    """numpy statement of the merge order (score desc, clip index asc, empty slots last) — the checker of this CPU test only; the
+    product merges on the device (LBAudioDetectiveDatabaseMergeTopK[Device])."""
+    n_lists, n_q, k = scores.shape
+    s = scores.transpose(1, 0, 2).reshape(n_q, -1); i = indices.transpose(1, 0, 2).reshape(n_q, -1)
+    valid_last = np.where(i == 0xFFFFFFFF, 1, 0)
+    o = np.lexsort((i, -s.astype(np.float64), valid_last), axis=1)[:, :k]
+    return np.take_along_axis(s, o, 1), np.take_along_axis(i, o, 1)
+
+
 def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
-    from lbaudiodetective_b200.dist import shard_range, gather_topk, merge_reference
+    from lbaudiodetective_b200.dist import shard_range, gather_topk
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     rng = np.random.default_rng(5)                     # same "database scores" on every rank
     n_clips, n_q, k = 1001, 13, 10
