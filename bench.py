@@ -363,6 +363,7 @@ def main():
                "sample": "%d x 30 s clips of the same synthetic workload (%.1f s of wall time); float32 FFT stands in for vDSP" % (args.ref_clips, secs),
                "search_compares_per_s": cpu_search_baseline(chk, threads)}
     # ---- configs[0] (the reference's own headline call): compare two 10 s clips through the compare-audio path, one call at a time ----
+    # (part of the cpu_baseline leg, skipped with --no-cpu: the oracle generates the two clips and is the timed CPU baseline, nothing else)
     config1 = None
     if world == 1 and not args.no_cpu:
         from oracle import oracle as o
