@@ -50,8 +50,9 @@ LBAD_API UInt32 LBAudioDetectiveGetSubfingerprintLength(LBAudioDetectiveRef inDe
 LBAD_API UInt32 LBAudioDetectiveGetWindowSize(LBAudioDetectiveRef inDetective);
 /* h:118, m:149-151 */
 LBAD_API UInt32 LBAudioDetectiveGetAnalysisStride(LBAudioDetectiveRef inDetective);
-/* h:143: declared upstream but never defined (recording was removed); defined here as a no-op returning noErr
- * so that code referencing the symbol links. */
+/* h:143: declared upstream but never defined (recording was removed).  Defined here: it sets the rate of the PCM handed to the
+ * ...Recorded... entry points of LBAudioDetectiveResample.h (default 44100.0) and invalidates the cached resampler; rates that are
+ * not positive return kLBAudioDetectiveArgumentInvalid. */
 LBAD_API OSStatus LBAudioDetectiveSetRecordingSampleRate(LBAudioDetectiveRef inDetective, Float64 inSampleRate);
 /* h:154, m:156-160 */
 LBAD_API OSStatus LBAudioDetectiveSetProcessingSampleRate(LBAudioDetectiveRef inDetective, Float64 inSampleRate);
@@ -102,6 +103,10 @@ LBAD_API OSStatus LBAudioDetectiveProcessPCMBatchDevice(LBAudioDetectiveRef inDe
  * images before / after the Haar transform), outBooleans is [subfp][L]; any may be NULL.  inUseFusedKernel selects
  * the register-FFT fast path (only valid for window 2048 / 32 pitch steps) or the generic shared-memory-FFT path. */
 LBAD_API OSStatus LBAudioDetectiveProcessPCMStages(LBAudioDetectiveRef inDetective, const Float32* inSamples, UInt64 inNumberFrames, Float32* outImages, Float32* outHaar, Boolean* outBooleans, Boolean inUseFusedKernel);
+/* Stage dump of a batch (layout of LBAudioDetectiveProcessPCMBatch): outWords [clip][subfp][2*W] (required), outImages / outHaar
+ * [clip][subfp][128][B] (either may be NULL).  The same kernels as the batch entry point, chunk by chunk. */
+LBAD_API OSStatus LBAudioDetectiveProcessPCMBatchStages(LBAudioDetectiveRef inDetective, const Float32* inSamples, UInt32 inNumberOfClips, UInt64 inFramesPerClip, UInt64 inClipStride,
+                                                       UInt32* outWords, Float32* outImages, Float32* outHaar, Boolean inUseFusedKernel);
 /* Haar transform (Frame.m:113-153) + ordered top-t sign extraction (Frame.m:165-191) of inCount host images
  * [128][B]; outHaar [inCount][128][B] and outBooleans [inCount][L] may be NULL. */
 LBAD_API OSStatus LBAudioDetectiveTransformImages(LBAudioDetectiveRef inDetective, const Float32* inImages, UInt32 inCount, Float32* outHaar, Boolean* outBooleans);

@@ -72,6 +72,7 @@ def load_library(build_if_missing: bool = True):
         "LBAudioDetectiveProcessPCMBatchInt16": (C.c_int32, [vp, vp, u32, u64, u64, vp]),
         "LBAudioDetectiveProcessPCMBatchDevice": (C.c_int32, [vp, vp, u32, u64, u64, vp, vp]),
         "LBAudioDetectiveProcessPCMStages": (C.c_int32, [vp, vp, u64, vp, vp, vp, u8]),
+        "LBAudioDetectiveProcessPCMBatchStages": (C.c_int32, [vp, vp, u32, u64, u64, vp, vp, vp, u8]),
         "LBAudioDetectiveTransformImages": (C.c_int32, [vp, vp, u32, vp, vp]),
         "LBAudioDetectiveStreamNew": (vp, [vp]),
         "LBAudioDetectiveStreamDispose": (C.c_int32, [vp]),
@@ -383,6 +384,16 @@ class Detective:
         img = np.zeros((n, ROWS_PER_FRAME, B), np.float32); haar = np.zeros_like(img); bits = np.zeros((n, L), np.uint8)
         _check(self._L.LBAudioDetectiveProcessPCMStages(self.ref, _ptr(pcm), pcm.size, _ptr(img), _ptr(haar), _ptr(bits), 1 if fused else 0), "LBAudioDetectiveProcessPCMStages")
         return img, haar, bits
+
+    def process_batch_stages(self, pcm2d, fused=True, images=True, haar=True):
+        """Host [clips][samples] -> (words [clips][subfps][2W], images, haar [clips][subfps][128][B]) through the batch kernels."""
+        pcm2d = _f32(pcm2d); n_clips, clip_len = pcm2d.shape
+        n = self.subfingerprints_for_length(clip_len); W = words_per_plane(self.subfingerprint_length); B = self.pitch_steps
+        words = np.zeros((n_clips, n, 2 * W), np.uint32)
+        img = np.zeros((n_clips, n, ROWS_PER_FRAME, B), np.float32) if images else None
+        hr = np.zeros((n_clips, n, ROWS_PER_FRAME, B), np.float32) if haar else None
+        _check(self._L.LBAudioDetectiveProcessPCMBatchStages(self.ref, _ptr(pcm2d), n_clips, clip_len, clip_len, _ptr(words), _ptr(img), _ptr(hr), 1 if fused else 0), "LBAudioDetectiveProcessPCMBatchStages")
+        return words, img, hr
 
     def transform_images(self, images):
         images = _f32(images); n = images.shape[0]

@@ -290,6 +290,16 @@ OSStatus LBAudioDetectiveProcessPCMStages(LBAudioDetectiveRef d, const Float32* 
     return e;
 }
 
+OSStatus LBAudioDetectiveProcessPCMBatchStages(LBAudioDetectiveRef d, const Float32* inSamples, UInt32 nClips, UInt64 framesPerClip, UInt64 clipStride,
+                                               UInt32* outWords, Float32* outImages, Float32* outHaar, Boolean useFused) {
+    if (!d || !inSamples || !outWords || nClips == 0 || clipStride < framesPerClip) return kLBAudioDetectiveArgumentInvalid;
+    OSStatus e = ensure_plan(d);
+    if (e != noErr) return e;
+    if (framesPerClip < d->windowSize) return kLBAudioDetectiveArgumentInvalid;
+    if (useFused && !lbadcu_plan_fused_supported(d->plan)) return kLBAudioDetectiveArgumentInvalid;
+    return lbad_status(lbadcu_extract_host(d->plan, inSamples, nClips, framesPerClip, clipStride, outWords, outImages, outHaar, useFused ? 1 : 2));
+}
+
 OSStatus LBAudioDetectiveTransformImages(LBAudioDetectiveRef d, const Float32* inImages, UInt32 inCount, Float32* outHaar, Boolean* outBooleans) {
     if (!d || !inImages || inCount == 0) return kLBAudioDetectiveArgumentInvalid;
     OSStatus e = ensure_plan(d);

@@ -1258,7 +1258,9 @@ static int extract_host_impl(lbadcu_plan* p, const void* h_pcm_v, int sample_byt
         cudaStream_t s = nbuf == 1 ? p->stream : p->copy_streams[b];
         void* d_in = sample_bytes == 2 ? static_cast<void*>(p->d_chunk_i16[b]) : static_cast<void*>(p->d_chunk_pcm[b]);
         const char* src = h_pcm + c0 * clip_stride * sample_bytes;
-        if (clip_stride == clip_pad) LBAD_CUDA_TRY(cudaMemcpyAsync(d_in, src, (size_t)nc * clip_pad * sample_bytes, cudaMemcpyHostToDevice, s));
+        /* one contiguous copy when the host layout already has the device stride — up to the last clip's last SAMPLE, not its padded end:
+         * the caller's buffer may end there */
+        if (clip_stride == clip_pad) LBAD_CUDA_TRY(cudaMemcpyAsync(d_in, src, ((size_t)(nc - 1) * clip_pad + clip_len) * sample_bytes, cudaMemcpyHostToDevice, s));
         else LBAD_CUDA_TRY(cudaMemcpy2DAsync(d_in, clip_pad * sample_bytes, src, clip_stride * sample_bytes, clip_len * sample_bytes, nc, cudaMemcpyHostToDevice, s));
         if (sample_bytes == 2) {
             i16_to_f32_kernel<<<p->sm_count * 8, 256, 0, s>>>(p->d_chunk_i16[b], p->d_chunk_pcm[b], (size_t)nc * clip_pad);

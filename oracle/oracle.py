@@ -187,7 +187,14 @@ class Ref(Port):
         return os.path.exists(REF_SO) or os.path.isdir(REFERENCE_SRC)
 
     def set_fft_mode(self, mode):
-        self.ref.lbad_shim_set_fft_mode(C.c_int(1 if mode == "f32" else 0))
+        """"f64": the parity definition (exact DFT rounded once); "fast": the tuned single-precision FFT of the timing baseline;
+        "f32": round 1's radix-2 Stockham stand-in (kept for comparison)."""
+        self.ref.lbad_shim_set_fft_mode(C.c_int({"f64": 0, "f32": 1, "fast": 2}[mode]))
+
+    def fft_us_per_window(self, n=2048, mode="fast", reps=20000):
+        """Cost of one vDSP_ctoz + vDSP_fft_zrip + vDSP_ztoc (m:353-355) through the shim, in microseconds."""
+        self.ref.lbad_ref_time_fft.restype = C.c_double
+        return float(self.ref.lbad_ref_time_fft(C.c_uint32(n), C.c_int({"f64": 0, "f32": 1, "fast": 2}[mode]), C.c_uint32(reps))) * 1e6
 
     def band_energies(self, cfg, pcm, n_windows):
         pcm = _f32(pcm); out = np.zeros((n_windows, cfg.bands), np.float32)
@@ -237,12 +244,24 @@ class Ref(Port):
         return float(out.value)
 
     def _extract_batch(self, cfg, pcm2d, n_clips, clip_len, threads, bits, n, fft_f32):
-        self.set_fft_mode("f32" if fft_f32 else "f64")
+        self.set_fft_mode(fft_f32 if isinstance(fft_f32, str) else ("fast" if fft_f32 else "f64"))
         try:
             return self.ref.lbad_ref_extract_batch(C.byref(cfg), _p(pcm2d, C.c_float), C.c_uint32(n_clips), C.c_int64(clip_len), C.c_uint32(threads),
                                                    _p(bits, C.c_uint8) if bits is not None else None, C.c_uint32(max(n, 1)), None)
         finally:
             self.set_fft_mode("f64")
+
+    def extract_batch_stages(self, cfg, pcm2d, threads=1, images=True, haar=True):
+        """(bits, images, haar, seconds) of a whole batch through the reference's own internals (f64 FFT definition), threaded."""
+        pcm2d = _f32(pcm2d); n_clips, clip_len = pcm2d.shape; n = subfp_count(cfg, clip_len)
+        bits = np.zeros((n_clips, max(n, 1), cfg.sublen), np.uint8)
+        img = np.zeros((n_clips, max(n, 1), ROWS_PER_FRAME, cfg.bands), np.float32) if images else None
+        hr = np.zeros((n_clips, max(n, 1), ROWS_PER_FRAME, cfg.bands), np.float32) if haar else None
+        self.ref.lbad_ref_extract_batch_stages.restype = C.c_double
+        self.set_fft_mode("f64")
+        secs = self.ref.lbad_ref_extract_batch_stages(C.byref(cfg), _p(pcm2d, C.c_float), C.c_uint32(n_clips), C.c_int64(clip_len), C.c_uint32(threads), C.c_uint32(max(n, 1)),
+                                                      _p(img, C.c_float) if images else None, _p(hr, C.c_float) if haar else None, _p(bits, C.c_uint8))
+        return bits[:, :n], (img[:, :n] if images else None), (hr[:, :n] if haar else None), float(secs)
 
     def search(self, db_bits, q_bits, rng, threads=1):
         db = _u8(db_bits); q = _u8(q_bits)

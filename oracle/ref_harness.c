@@ -8,6 +8,7 @@
  */
 #include <Foundation/Foundation.h>
 #include <AudioToolbox/AudioToolbox.h>
+#include <Accelerate/Accelerate.h>
 #include <pthread.h>
 #include <time.h>
 #include "LBAudioDetective.h"
@@ -171,6 +172,34 @@ int lbad_ref_set_window_size_status(UInt32 n) {
 
 /* ------------------------------------------------------------------ timing ---- */
 
+static double now_s(void);
+void lbad_shim_set_fft_mode(int mode);
+int lbad_shim_get_fft_mode(void);
+
+/* seconds per window of the three vDSP calls the reference makes (LBAudioDetective.m:353-355), in the given shim mode */
+double lbad_ref_time_fft(UInt32 n, int mode, UInt32 reps) {
+    UInt32 log2n = 0; while ((1u << log2n) < n) log2n++;
+    FFTSetup setup = vDSP_create_fftsetup(log2n, FFT_RADIX2);
+    float* x = malloc(sizeof(float) * n); float* re = malloc(sizeof(float) * n / 2); float* im = malloc(sizeof(float) * n / 2);
+    for (UInt32 i = 0; i < n; i++) x[i] = (float)((i * 2654435761u) >> 8) / 16777216.0f - 0.5f;
+    COMPLEX_SPLIT A = { re, im };
+    int old = lbad_shim_get_fft_mode(); lbad_shim_set_fft_mode(mode);
+    volatile float sink = 0;
+    double t0 = now_s();
+    for (UInt32 r = 0; r < reps; r++) {
+        x[r % n] += 1e-3f;
+        vDSP_ctoz((COMPLEX*)x, 2, &A, 1, n / 2);
+        vDSP_fft_zrip(setup, &A, 1, log2n, FFT_FORWARD);
+        vDSP_ztoc(&A, 1, (COMPLEX*)x, 2, n / 2);
+        sink += x[7];
+        for (UInt32 i = 0; i < 8; i++) x[(r * 8 + i) % n] *= 1e-3f;      /* keep the values bounded */
+    }
+    double dt = (now_s() - t0) / reps;
+    lbad_shim_set_fft_mode(old);
+    vDSP_destroy_fftsetup(setup); free(x); free(re); free(im);
+    return dt;
+}
+
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 typedef struct {
@@ -208,6 +237,38 @@ double lbad_ref_extract_batch(const lbad_ref_cfg* cfg, const float* pcm, UInt32 
         jobs[t] = (extract_job){ cfg, pcm, clip_len, (UInt32)((UInt64)n_clips * t / threads), (UInt32)((UInt64)n_clips * (t + 1) / threads),
                                  out_bits, max_subfps_per_clip, out_counts, L };
         pthread_create(&th[t], NULL, extract_worker, &jobs[t]);
+    }
+    for (UInt32 t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    return now_s() - t0;
+}
+
+/* Stage dumps of a whole batch on `threads` host threads, every clip through lbad_ref_process_pcm_direct (the reference's own
+ * ComputeFrequencies / FrameSetRow / SynthesizeFingerprint; Q14-safe at every window size): out_images and out_haar are
+ * [n_clips][subfps_per_clip][128][bands] (either may be NULL), out_bits [n_clips][subfps_per_clip][sublen].  Returns wall seconds. */
+typedef struct { const lbad_ref_cfg* cfg; const float* pcm; SInt64 clip_len; UInt32 first, last, per_clip, bands, L; float* img; float* haar; Boolean* bits; } stage_job;
+
+static void* stage_worker(void* p) {
+    stage_job* j = p;
+    const size_t fsz = (size_t)128 * j->bands;
+    for (UInt32 c = j->first; c < j->last; c++) {
+        UInt32 cnt = 0, L = 0;
+        lbad_ref_process_pcm_direct(j->cfg, j->pcm + (size_t)c * j->clip_len, j->clip_len, j->bits + (size_t)c * j->per_clip * j->L, j->per_clip, &cnt, &L,
+                                    j->img ? j->img + (size_t)c * j->per_clip * fsz : NULL, j->haar ? j->haar + (size_t)c * j->per_clip * fsz : NULL);
+    }
+    return NULL;
+}
+
+double lbad_ref_extract_batch_stages(const lbad_ref_cfg* cfg, const float* pcm, UInt32 n_clips, SInt64 clip_len, UInt32 threads,
+                                     UInt32 subfps_per_clip, float* out_images, float* out_haar, Boolean* out_bits) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    if (threads > n_clips) threads = n_clips ? n_clips : 1;
+    pthread_t th[256]; stage_job jobs[256];
+    double t0 = now_s();
+    for (UInt32 t = 0; t < threads; t++) {
+        jobs[t] = (stage_job){ cfg, pcm, clip_len, (UInt32)((UInt64)n_clips * t / threads), (UInt32)((UInt64)n_clips * (t + 1) / threads), subfps_per_clip,
+                               cfg->bands ? cfg->bands : 32, cfg->sublen ? cfg->sublen : 200, out_images, out_haar, out_bits };
+        pthread_create(&th[t], NULL, stage_worker, &jobs[t]);
     }
     for (UInt32 t = 0; t < threads; t++) pthread_join(th[t], NULL);
     return now_s() - t0;

@@ -9,9 +9,13 @@
  *     realp[0], Nyquist packed into imagp[0].  Two interchangeable kernels:
  *       mode 0 "f64"  (default, used for parity): the DFT evaluated in double precision and rounded once
  *                     to float — the centre of the "within f32 rounding" ball both vDSP and the GPU live in;
- *       mode 1 "f32"  (used for the CPU timing baseline): a float Stockham radix-2 FFT with table
- *                     twiddles, comparable in cost to a production single-precision FFT.
- *     Select with lbad_shim_set_fft_mode() or the LBAD_SHIM_FFT=f64|f32 environment variable.
+ *       mode 1 "f32"  a float Stockham radix-2 FFT with table twiddles (round 1's timing stand-in; kept for
+ *                     comparison — it costs about 12 us per 2048-point window);
+ *       mode 2 "fast" (used for the CPU timing baseline, bench.py --impl reference and cpu_baseline): a
+ *                     single-precision four-step FFT (32 x R points, split re/im arrays, every loop a
+ *                     contiguous SIMD loop; AVX-512 / AVX2 clones picked at load time) — what a tuned vDSP
+ *                     costs, so that the GPU/CPU ratio is not inflated by a slow stand-in.
+ *     Select with lbad_shim_set_fft_mode() or the LBAD_SHIM_FFT=f64|f32|fast environment variable.
  *   - AudioToolbox ExtAudioFile*: a memory-backed "file".  The NSURL* the reference passes around is a
  *     pointer to {const float* samples; int64 count}; Read copies from a cursor, Seek sets the cursor
  *     (LBAudioDetective.m:224-237,275,288).  Decode/resample is out of scope.
@@ -30,15 +34,20 @@ struct LBADShimFFTSetup {
     float*   twf;        /* same in float — f32 kernel */
     double*  wa; double* wb;   /* f64 ping-pong, N/2 complex each */
     float*   fa; float*  fb;   /* f32 ping-pong */
+    struct LBADFastFFT* fast;  /* mode 2 tables and scratch */
 };
+struct LBADFastFFT;
+static struct LBADFastFFT* fast_new(size_t n);
+static void fast_free(struct LBADFastFFT* f);
+static void fast_zrip(struct LBADFastFFT* f, float* re, float* im);
 
 static int g_fft_mode = -1;
 
-void lbad_shim_set_fft_mode(int mode) { g_fft_mode = mode ? 1 : 0; }
+void lbad_shim_set_fft_mode(int mode) { g_fft_mode = mode == 2 ? 2 : mode ? 1 : 0; }
 int lbad_shim_get_fft_mode(void) {
     if (g_fft_mode < 0) {
         const char* e = getenv("LBAD_SHIM_FFT");
-        g_fft_mode = (e && strcmp(e, "f32") == 0) ? 1 : 0;
+        g_fft_mode = (e && strcmp(e, "f32") == 0) ? 1 : (e && strcmp(e, "fast") == 0) ? 2 : 0;
     }
     return g_fft_mode;
 }
@@ -58,22 +67,33 @@ FFTSetup vDSP_create_fftsetup(vDSP_Length log2n, FFTRadix radix) {
     }
     s->wa = malloc(2 * h * sizeof(double)); s->wb = malloc(2 * h * sizeof(double));
     s->fa = malloc(2 * h * sizeof(float));  s->fb = malloc(2 * h * sizeof(float));
+    s->fast = fast_new(s->n);
     return s;
 }
 
 void vDSP_destroy_fftsetup(FFTSetup s) {
     if (!s) return;   /* the reference destroys a NULL setup on its first SetWindowSize (LBAudioDetective.m:179) */
-    free(s->twd); free(s->twf); free(s->wa); free(s->wb); free(s->fa); free(s->fb); free(s);
+    fast_free(s->fast); free(s->twd); free(s->twf); free(s->wa); free(s->wb); free(s->fa); free(s->fb); free(s);
 }
 
 void vDSP_ctoz(const DSPComplex* C, vDSP_Stride IC, const DSPSplitComplex* Z, vDSP_Stride IZ, vDSP_Length N) {
     /* IC is in floats (2 = contiguous complex), as in vDSP */
     const float* c = (const float*)C;
+    if (IC == 2 && IZ == 1) {            /* the reference's call (m:353): contiguous pairs -> split arrays, a SIMD de-interleave */
+        float* restrict zr = Z->realp; float* restrict zi = Z->imagp; const float* restrict cc = c;
+        for (vDSP_Length i = 0; i < N; i++) { zr[i] = cc[2*i]; zi[i] = cc[2*i + 1]; }
+        return;
+    }
     for (vDSP_Length i = 0; i < N; i++) { Z->realp[i*IZ] = c[i*IC]; Z->imagp[i*IZ] = c[i*IC + 1]; }
 }
 
 void vDSP_ztoc(const DSPSplitComplex* Z, vDSP_Stride IZ, DSPComplex* C, vDSP_Stride IC, vDSP_Length N) {
     float* c = (float*)C;
+    if (IC == 2 && IZ == 1) {            /* m:355 */
+        const float* restrict zr = Z->realp; const float* restrict zi = Z->imagp; float* restrict cc = c;
+        for (vDSP_Length i = 0; i < N; i++) { cc[2*i] = zr[i]; cc[2*i + 1] = zi[i]; }
+        return;
+    }
     for (vDSP_Length i = 0; i < N; i++) { c[i*IC] = Z->realp[i*IZ]; c[i*IC + 1] = Z->imagp[i*IZ]; }
 }
 
@@ -103,10 +123,124 @@ static T* NAME(T* x, T* y, size_t M, const T* tw) {                             
 STOCKHAM(double, stockham_f64)
 STOCKHAM(float,  stockham_f32)
 
+
+/* ---- mode 2: four-step single-precision FFT --------------------------------------------------------------
+ * M = N/2 complex points z[n] = x[2n] + i x[2n+1] (what vDSP_ctoz left in realp/imagp), M = 32 R, R = 4 .. 32:
+ *   n = R n1 + n2, k = k1 + 32 k2
+ *   step 1: 32-point DFT over n1 for every column n2            (rows of R floats: contiguous SIMD loops)
+ *   twiddle by exp(-2 pi i n2 k1 / M), transposed to [n2][k1]
+ *   step 2: R-point DFT over n2 for every column k1             (rows of 32 floats)
+ *   -> Z[k1 + 32 k2] sits at [k2][k1], i.e. in natural order
+ *   real split: 2 X[k] = (Z[k] + conj Z[M-k]) - i e^{-2 pi i k / N} (Z[k] - conj Z[M-k])
+ * The row transforms are radix-2 decimation in frequency, in place; they leave output index bitrev(r) in row r,
+ * which the following step undoes through its row addressing.  Split real / imaginary arrays throughout. */
+#if defined(__x86_64__) && defined(__GNUC__)
+#define LBAD_CLONES __attribute__((target_clones("avx512f", "avx2,fma", "default")))
+#else
+#define LBAD_CLONES
+#endif
+
+struct LBADFastFFT {
+    unsigned M, R, logR;
+    float *ar, *ai, *br, *bi;          /* [32][R] and [R][32] work arrays, 64-byte aligned */
+    float *t1c, *t1s;                  /* step-1 row twiddles: stage s, butterfly j -> cos, sin of 2 pi j 2^s / 32 */
+    float *t2c, *t2s;                  /* step-2 row twiddles for R points */
+    float *twc, *tws;                  /* inter-step twiddles in the order they are applied: [bitrev5 row r -> k1][n2] */
+    float *sc, *ss;                    /* real-split twiddles cos, sin(2 pi k / N), k < M */
+    float *zr, *zi;                    /* spectrum of the complex transform, natural order, M + 1 entries (Z[M] = Z[0]) */
+};
+
+static unsigned bitrev_n(unsigned v, unsigned bits) { unsigned r = 0; for (unsigned b = 0; b < bits; b++) r |= ((v >> b) & 1u) << (bits - 1 - b); return r; }
+static float* alloc64(size_t n) { void* p = NULL; if (posix_memalign(&p, 64, (n * sizeof(float) + 63) & ~(size_t)63) != 0) return NULL; return p; }
+
+static struct LBADFastFFT* fast_new(size_t n) {
+    if (n < 256 || n > 2048 || (n & (n - 1))) return NULL;
+    struct LBADFastFFT* f = calloc(1, sizeof *f);
+    f->M = (unsigned)n / 2; f->R = f->M / 32; f->logR = 0; while ((1u << f->logR) < f->R) f->logR++;
+    unsigned M = f->M, R = f->R;
+    f->ar = alloc64(M); f->ai = alloc64(M); f->br = alloc64(M); f->bi = alloc64(M);
+    f->t1c = alloc64(16 * 5); f->t1s = alloc64(16 * 5); f->t2c = alloc64(16 * 5); f->t2s = alloc64(16 * 5);
+    f->twc = alloc64(M); f->tws = alloc64(M); f->sc = alloc64(M); f->ss = alloc64(M); f->zr = alloc64(M + 16); f->zi = alloc64(M + 16);
+    for (unsigned st = 0; st < 5; st++) for (unsigned j = 0; j < 16; j++) {
+        double a1 = 2.0 * M_PI * (double)((j << st) % 32) / 32.0, a2 = 2.0 * M_PI * (double)((j << st) % R) / (double)R;
+        f->t1c[st * 16 + j] = (float)cos(a1); f->t1s[st * 16 + j] = (float)sin(a1);
+        f->t2c[st * 16 + j] = (float)cos(a2); f->t2s[st * 16 + j] = (float)sin(a2);
+    }
+    for (unsigned r = 0; r < 32; r++) for (unsigned n2 = 0; n2 < R; n2++) {
+        double a = 2.0 * M_PI * (double)(bitrev_n(r, 5) * n2) / (double)M;
+        f->twc[r * R + n2] = (float)cos(a); f->tws[r * R + n2] = (float)sin(a);
+    }
+    for (unsigned k = 0; k < M; k++) { double a = 2.0 * M_PI * (double)k / (double)n; f->sc[k] = (float)cos(a); f->ss[k] = (float)sin(a); }
+    return f;
+}
+static void fast_free(struct LBADFastFFT* f) {
+    if (!f) return;
+    free(f->ar); free(f->ai); free(f->br); free(f->bi); free(f->t1c); free(f->t1s); free(f->t2c); free(f->t2s);
+    free(f->twc); free(f->tws); free(f->sc); free(f->ss); free(f->zr); free(f->zi); free(f);
+}
+
+/* in-place radix-2 DIF over `rows` rows of `cols` floats (forward, e^{-i theta}); row r ends up holding output bitrev(r) */
+LBAD_CLONES
+static void rows_dif(float* restrict xr, float* restrict xi, unsigned rows, unsigned cols, const float* restrict tc, const float* restrict ts) {
+    unsigned st = 0;
+    for (unsigned half = rows / 2; half >= 1; half >>= 1, st++) {
+        for (unsigned b = 0; b < rows; b += 2 * half) {
+            for (unsigned j = 0; j < half; j++) {
+                const float c = tc[st * 16 + j], s = ts[st * 16 + j];      /* w = c - i s */
+                float* restrict pr = xr + (size_t)(b + j) * cols; float* restrict pi = xi + (size_t)(b + j) * cols;
+                float* restrict qr = xr + (size_t)(b + j + half) * cols; float* restrict qi = xi + (size_t)(b + j + half) * cols;
+                for (unsigned q = 0; q < cols; q++) {
+                    const float ar = pr[q], ai = pi[q], cr = qr[q], ci = qi[q];
+                    const float dr = ar - cr, di = ai - ci;
+                    pr[q] = ar + cr; pi[q] = ai + ci;
+                    qr[q] = dr * c + di * s; qi[q] = di * c - dr * s;
+                }
+            }
+        }
+    }
+}
+
+LBAD_CLONES
+static void fast_zrip(struct LBADFastFFT* f, float* re, float* im) {
+    const unsigned M = f->M, R = f->R, logR = f->logR;
+    float* restrict ar = f->ar; float* restrict ai = f->ai; float* restrict br = f->br; float* restrict bi = f->bi;
+    /* z[R n1 + n2] is already laid out as [n1][n2] */
+    memcpy(ar, re, M * sizeof(float)); memcpy(ai, im, M * sizeof(float));
+    rows_dif(ar, ai, 32, R, f->t1c, f->t1s);
+    /* twiddle (row r holds k1 = bitrev5(r); the table is stored in row order) and transpose to [n2][k1] */
+    {
+        const float* restrict c = f->twc; const float* restrict s = f->tws;
+        for (unsigned i = 0; i < M; i++) { const float xr = ar[i], xi = ai[i]; ar[i] = xr * c[i] + xi * s[i]; ai[i] = xi * c[i] - xr * s[i]; }
+    }
+    for (unsigned r = 0; r < 32; r++) {
+        const unsigned k1 = bitrev_n(r, 5);
+        const float* restrict xr = ar + (size_t)r * R; const float* restrict xi = ai + (size_t)r * R;
+        for (unsigned n2 = 0; n2 < R; n2++) { br[(size_t)n2 * 32 + k1] = xr[n2]; bi[(size_t)n2 * 32 + k1] = xi[n2]; }
+    }
+    rows_dif(br, bi, R, 32, f->t2c, f->t2s);
+    /* row r of b holds k2 = bitrev(r): natural order Z[k1 + 32 k2] */
+    float* restrict zr = f->zr; float* restrict zi = f->zi;
+    for (unsigned r = 0; r < R; r++) {
+        const unsigned k2 = bitrev_n(r, logR);
+        memcpy(zr + (size_t)k2 * 32, br + (size_t)r * 32, 32 * sizeof(float)); memcpy(zi + (size_t)k2 * 32, bi + (size_t)r * 32, 32 * sizeof(float));
+    }
+    zr[M] = zr[0]; zi[M] = zi[0];
+    const float dc = 2.0f * (zr[0] + zi[0]), ny = 2.0f * (zr[0] - zi[0]);
+    const float* restrict sc = f->sc; const float* restrict ss = f->ss;
+    for (unsigned k = 1; k < M; k++) {
+        const float yr = zr[M - k], yi = -zi[M - k];
+        const float er = zr[k] + yr, ei = zi[k] + yi, orr = zr[k] - yr, oi = zi[k] - yi;
+        const float c = sc[k], sn = ss[k];
+        re[k] = er + (c * oi - sn * orr); im[k] = ei - (c * orr + sn * oi);
+    }
+    re[0] = dc; im[0] = ny;
+}
+
 void vDSP_fft_zrip(FFTSetup s, const DSPSplitComplex* C, vDSP_Stride IC, vDSP_Length log2n, FFTDirection dir) {
     if (!s || dir != FFT_FORWARD || IC != 1 || log2n != s->log2n) { fprintf(stderr, "lbad shim: unsupported vDSP_fft_zrip call\n"); abort(); }
     size_t N = s->n, M = N / 2;
     float* re = C->realp; float* im = C->imagp;
+    if (lbad_shim_get_fft_mode() == 2 && s->fast) { fast_zrip(s->fast, re, im); return; }
     if (lbad_shim_get_fft_mode() == 0) {
         for (size_t i = 0; i < M; i++) { s->wa[2*i] = re[i]; s->wa[2*i+1] = im[i]; }
         const double* Z = stockham_f64(s->wa, s->wb, M, s->twd);

@@ -30,6 +30,34 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+# ---- figures: what the parity tests measured (worst errors, mismatch rates), kept even when pytest runs without -s ----
+_FIGURES = []
+
+
+@pytest.fixture
+def figure(request):
+    """figure("text") records a measured number under the test's name; all of them are printed in the terminal summary (so the
+    driver's pytest.log keeps them) and written to gpurun_out/pytest_figures.json when that directory exists."""
+    def rec(text):
+        _FIGURES.append((request.node.nodeid, str(text)))
+        print(text)
+    return rec
+
+
+def pytest_terminal_summary(terminalreporter):
+    if not _FIGURES:
+        return
+    terminalreporter.section("measured figures (parity tests)")
+    for node, text in _FIGURES:
+        terminalreporter.write_line("%s: %s" % (node.split("::", 1)[-1], text))
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        try:
+            json.dump([{"test": n, "figure": t} for n, t in _FIGURES], open(os.path.join(out, "pytest_figures.json"), "w"), indent=1)
+        except OSError:
+            pass
+
+
 @pytest.fixture(scope="session")
 def port():
     from oracle.oracle import Port

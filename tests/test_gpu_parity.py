@@ -35,7 +35,7 @@ def mismatch_rate(a, b):
 # ------------------------------------------------------------------ extraction ----
 
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "generic"])
-def test_config1_stages_against_golden(lb, config1, fused):
+def test_config1_stages_against_golden(lb, config1, fused, figure):
     d = lb.Detective()
     worst_band = worst_haar = 0.0; mism = 0; total = 0
     for c in range(2):
@@ -48,14 +48,14 @@ def test_config1_stages_against_golden(lb, config1, fused):
         assert np.linalg.norm(img - gi) / np.linalg.norm(gi) < BAND_NORMWISE
         worst_haar = max(worst_haar, float((np.abs(haar - gh).reshape(6, -1).max(axis=1) / np.abs(gh).reshape(6, -1).max(axis=1)).max()))
         mism += int((bits != gb).sum()); total += bits.size
-    print("band rel err %.3g, haar err/max %.3g, bit mismatches %d/%d" % (worst_band, worst_haar, mism, total))
+    figure("band rel err %.3g, haar err/max %.3g, bit mismatches %d/%d" % (worst_band, worst_haar, mism, total))
     assert worst_band < BAND_RTOL_PURE_MAX
     assert worst_haar < HAAR_RTOL_OF_MAX
     assert mism / total <= BIT_MISMATCH_BUDGET
 
 
 @pytest.mark.parametrize("window", [1024, 512, 256])
-def test_register_fft_kernel_other_windows(lb, checker, window):
+def test_register_fft_kernel_other_windows(lb, checker, window, figure):
     """Windows of 1024 / 512 / 256 samples run the same register-FFT kernel with 2 / 4 / 8 windows per warp: stages against the oracle."""
     cfg = Cfg.default(window=window); d = lb.Detective(); d.set_window_size(window)
     pcm = checker.synth_clip(33, 40000)
@@ -68,7 +68,7 @@ def test_register_fft_kernel_other_windows(lb, checker, window):
         assert np.array_equal(img[empty], want_img[empty])
         excess = np.abs(img - want_img) - floor
         rel = float((np.maximum(excess, 0)[~empty] / np.abs(want_img[~empty])).max())
-        print("window %d %s: band rel err beyond the floor %.3g, %d of %d elements above 1e-4" % (window, "register" if fused else "generic", rel, int((excess[~empty] > 1e-4 * np.abs(want_img[~empty])).sum()), img.size))
+        figure("window %d %s: band rel err beyond the floor %.3g, %d of %d elements above 1e-4" % (window, "register" if fused else "generic", rel, int((excess[~empty] > 1e-4 * np.abs(want_img[~empty])).sum()), img.size))
         assert rel < BAND_RTOL_PURE_MAX * 2, (window, fused)      # short windows: 1-3 bins per band, no averaging of the ill-conditioned Q4 terms
         assert np.linalg.norm(img - want_img) / np.linalg.norm(want_img) < BAND_NORMWISE
         assert float((np.abs(haar - want_haar).reshape(haar.shape[0], -1).max(axis=1) / np.abs(want_haar).reshape(haar.shape[0], -1).max(axis=1)).max()) < HAAR_RTOL_OF_MAX
@@ -83,7 +83,7 @@ def test_fused_equals_generic_bits(lb, port):
     assert bf.shape == (19, 200) and mismatch_rate(bf, bg) <= BIT_MISMATCH_BUDGET
 
 
-def test_process_pcm_against_oracle(lb, checker):
+def test_process_pcm_against_oracle(lb, checker, figure):
     cfg = Cfg.default(); d = lb.Detective(); mism = 0; total = 0
     for clip, n in ((40, 55120), (41, 165360), (42, 16536), (43, 10240), (44, 10240 + 8191), (45, 10240 + 8192)):
         pcm = checker.synth_clip(clip, n)
@@ -91,11 +91,11 @@ def test_process_pcm_against_oracle(lb, checker):
         assert fp.count == want.shape[0] and fp.subfingerprint_length == 200
         got = fp.booleans(); mism += int((got != want).sum()); total += want.size
         assert np.array_equal(lb.unpack_words(fp.packed(), 200), got)
-    print("bit mismatches %d/%d vs %s oracle" % (mism, total, checker.kind))
+    figure("bit mismatches %d/%d vs %s oracle" % (mism, total, checker.kind))
     assert mism / total <= BIT_MISMATCH_BUDGET
 
 
-def test_bit_mismatch_rate_on_a_large_sample(lb, checker):
+def test_bit_mismatch_rate_on_a_large_sample(lb, checker, figure):
     """The 0.1 % budget measured where it means something: 120 x 30 s clips (2,280 subfingerprints, 456,000 Booleans) plus quiet,
     loud and tonal variants, against the oracle run on all host threads."""
     cfg = Cfg.default(); d = lb.Detective()
@@ -112,7 +112,7 @@ def test_bit_mismatch_rate_on_a_large_sample(lb, checker):
         assert got.shape == want.shape
         rate = mismatch_rate(got, want)
         per_sub = (got != want).reshape(-1, 200).any(axis=1).mean()
-        print("%-32s %8d Booleans, mismatch rate %.2e (%.2f %% of subfingerprints touched)" % (name, want.size, rate, 100 * per_sub))
+        figure("%-32s %8d Booleans, mismatch rate %.2e (%.2f %% of subfingerprints touched)" % (name, want.size, rate, 100 * per_sub))
         if "pure tones" not in name:
             worst = max(worst, rate)
     assert worst <= BIT_MISMATCH_BUDGET
@@ -156,7 +156,7 @@ def test_bits_from_coefficients_with_exact_ties(lb, checker, kernel, monkeypatch
         assert np.array_equal(bits[i], checker.extract_bits(want_h, 200)[:200])
 
 
-def test_config5_sweep_against_golden(lb, sweep):
+def test_config5_sweep_against_golden(lb, sweep, figure):
     """Window-size x subfingerprint-length sweep (BASELINE config 5) through the generic path; budget over the sweep."""
     mism = total = 0
     for window in (512, 1024, 2048):
@@ -169,12 +169,12 @@ def test_config5_sweep_against_golden(lb, sweep):
                 assert fp.count == want.shape[0] and fp.subfingerprint_length == sublen
                 m = int((fp.booleans() != want).sum()); mism += m; total += want.size
                 if m:
-                    print("window %d sublen %d %s: %d mismatching Booleans" % (window, sublen, name, m))
-    print("sweep: %d/%d mismatching Booleans" % (mism, total))
+                    figure("window %d sublen %d %s: %d mismatching Booleans" % (window, sublen, name, m))
+    figure("sweep: %d/%d mismatching Booleans" % (mism, total))
     assert mism / total <= BIT_MISMATCH_BUDGET
 
 
-def test_other_geometry_against_oracle(lb, checker):
+def test_other_geometry_against_oracle(lb, checker, figure):
     cases = [dict(window=256, stride=64), dict(stride=128, sample_rate=8000.0), dict(bands=16, sublen=64), dict(stride=50), dict(bands=64, sublen=512),
              dict(stride=2), dict(window=1024, stride=1000),
              # window 2048 at hop 64 with other band tables: the carried-transform kernel with run-time band rows (rows above 23, rows below 2,
@@ -192,7 +192,7 @@ def test_other_geometry_against_oracle(lb, checker):
         assert got.shape == want.shape and want.shape[0] >= 1, kw
         m = int((got != want).sum()); mism += m; total += want.size
         if m:
-            print(kw, "%d mismatching Booleans of %d" % (m, want.size))
+            figure("%s: %d mismatching Booleans of %d" % (kw, m, want.size))
     assert mism / total <= BIT_MISMATCH_BUDGET
 
 
@@ -316,10 +316,12 @@ def test_int16_batch_equals_float_batch(lb, port):
     assert np.array_equal(d.process_batch_int16(odd), d.process_batch(odd.astype(np.float32) / np.float32(32768.0)))
 
 
-def test_streaming_equals_one_shot(lb, port):
-    """Any chunking of the PCM gives the one-shot fingerprint at every prefix (frame emission follows m:250-255 exactly)."""
-    d = lb.Detective(); pcm = port.synth_clip(90, 100000); rng = np.random.default_rng(15)
-    s = lb.Stream(d); pos = 0
+def test_streaming_equals_one_shot(lb, checker, figure):
+    """Any chunking of the PCM gives, at every prefix, what the reference's whole-clip loop (m:250-262) gives for that prefix: the
+    stream's Booleans are held against the oracle run on pcm[:pos] (within the bit budget) and against the one-shot GPU call (equal)."""
+    cfg = Cfg.default()
+    d = lb.Detective(); pcm = checker.synth_clip(90, 100000); rng = np.random.default_rng(15)
+    s = lb.Stream(d); pos = 0; mism = total = 0
     while pos < len(pcm):
         n = int(rng.choice([1, 63, 64, 1000, 8192, 10175, 10176, 20000])); n = min(n, len(pcm) - pos)
         s.append(pcm[pos:pos + n]); pos += n
@@ -328,6 +330,16 @@ def test_streaming_equals_one_shot(lb, port):
         assert fp.count == want and s.pending == pos - want * 8192
         if n >= 8192 and want:
             assert fp.equal(d.process_pcm(pcm[:pos]))
+            ob = checker.process(cfg, pcm[:pos])                             # the oracle on the same prefix
+            gb = fp.booleans()
+            assert ob.shape == gb.shape
+            mism += int((ob != gb).sum()); total += ob.size
+    whole = checker.process(cfg, pcm)
+    final = s.fingerprint().booleans()
+    assert final.shape == whole.shape == (11, 200)
+    mism += int((final != whole).sum()); total += whole.size
+    figure("stream prefixes vs %s oracle: %d mismatching Booleans of %d" % (checker.kind, mism, total))
+    assert mism / total <= BIT_MISMATCH_BUDGET
     assert s.fingerprint().equal(d.process_pcm(pcm)) and s.fingerprint().count == 11
     s2 = lb.Stream(d); s2.append(pcm[:10239]); assert s2.fingerprint().count == 0
     s2.append(pcm[10239:10240]); assert s2.fingerprint().count == 1          # exactly the reference's threshold: 128*64 + 2048 samples
