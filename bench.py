@@ -5,9 +5,13 @@
     python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's own CPU code on the host cores
 
 A step = one pass of fingerprint extraction over one batch of synthetic PCM: BASELINE config 2, 10,000 x 30 s clips
-(83.3 audio-hours, 6.6 GB of float32) per GPU, resident in HBM when the timed region starts.  Prints ONE JSON line.
+(83.3 audio-hours, 6.6 GB of float32) per GPU, resident in HBM when the timed region starts.  Prints ONE JSON line; besides the
+headline it carries the other configs of BASELINE.json as legs of their own (config 3: 1,000 hours sharded over the GPUs; config 4:
+the sharded database search; config 5: one-subfingerprint queries; config 1: one compare-audio call) and result hashes that must not
+change with the number of GPUs (`extract.words_sha256`, `search.topk_sha256`).
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -25,6 +29,9 @@ SUBFPS = 19
 ALGO_BYTES_PER_CLIP = CLIP_LEN * 4 + SUBFPS * 25        # 4 B per sample in + 25 B per subfingerprint out
 FLOP_PER_WINDOW = 60300.0                               # 2.5 N log2 N + band stage
 WINDOWS_PER_CLIP = SUBFPS * 128
+HASH_BLOCKS = 8              # extraction hash: the first HASH_CLIPS clips of the 10,000-clip block of each of 8 ranks (global clip ids)
+HASH_CLIPS = 8
+DB_SEED = 1234               # the search database is a function of (DB_SEED, global subfingerprint index), whatever the sharding
 
 
 def measured_peaks():
@@ -79,7 +86,10 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_extract_baseline(n_clips, threads, fft_f32=True):
+CPU_FFT = "fast"             # oracle/shim/shim.c mode 2: the tuned single-precision FFT standing in for vDSP in every CPU timing
+
+
+def cpu_extract_baseline(n_clips, threads, fft=CPU_FFT):
     """The reference's own code (oracle/_ref) — or the C port when it was never built — on a bounded sample of the workload."""
     from oracle import oracle as o
     chk = o.best()
@@ -87,9 +97,18 @@ def cpu_extract_baseline(n_clips, threads, fft_f32=True):
     pcm = np.stack([chk.synth_clip(c, CLIP_LEN) for c in range(min(n_clips, 64))])
     if n_clips > pcm.shape[0]:
         pcm = np.concatenate([pcm] * ((n_clips + pcm.shape[0] - 1) // pcm.shape[0]))[:n_clips]      # timing only: content repeats
-    _, secs = chk.extract_batch(cfg, pcm, threads=threads, want_bits=False, fft_f32=fft_f32)
+    _, secs = chk.extract_batch(cfg, pcm, threads=threads, want_bits=False, fft_f32=fft if chk.kind == "reference" else True)
     hours = n_clips * CLIP_LEN / SR / 3600.0
     return chk, hours / secs, secs
+
+
+def cpu_fft_note(chk):
+    """What stands in for vDSP in the CPU timing, and what it costs per window (so that the reader can discount)."""
+    if chk.kind != "reference":
+        return {"fft": "float32 radix-2 Stockham of the C port"}
+    return {"fft": "oracle/shim/shim.c mode 'fast': single-precision four-step FFT (32 x 32 points, SIMD clones AVX-512 / AVX2) behind vDSP_fft_zrip",
+            "fft_us_per_2048_window (ctoz + fft_zrip + ztoc, one core)": round(min(chk.fft_us_per_window(2048, CPU_FFT, 20000) for _ in range(3)), 2),
+            "round1_fft_us_per_2048_window (radix-2 Stockham stand-in, for comparison)": round(min(chk.fft_us_per_window(2048, "f32", 5000) for _ in range(2)), 2)}
 
 
 def cpu_search_baseline(chk, threads, n_db=20000, n_q=4):
@@ -133,14 +152,23 @@ def run_reference(args):
             times.append(secs)
     total = float(np.sum(times)); hours = args.ref_clips * CLIP_LEN / SR / 3600.0
     value = hours * args.steps / total
-    sample = "%d x 30 s clips (%.2f audio-hours) of the 10,000-clip workload per step; float32 FFT stands in for vDSP" % (args.ref_clips, hours)
+    sample = "%d x 30 s clips (%.2f audio-hours) of the 10,000-clip workload per step; %d threads in one process" % (args.ref_clips, hours, threads)
+    cpu = {"value": value, "unit": "audio-hours/s", "cores": threads, "kind": chk.kind, "sample": sample}
+    cpu.update(cpu_fft_note(chk))
     line = {"impl": "reference", "metric": "audio-hours/s fingerprinted", "value": value, "unit": "audio-hours/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": "configs[1] sample: batch fingerprint extraction of synthetic 30 s clips at reference defaults", "clips_per_step": args.ref_clips,
                                             "clip_seconds": 30, "window": 2048, "stride": 64, "bands": 32, "subfingerprint_length": 200},
-            "cpu_baseline": {"value": value, "unit": "audio-hours/s", "cores": threads, "kind": chk.kind, "sample": sample},
+            "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
+
+
+def sha(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
 
 
 def main():
@@ -153,9 +181,13 @@ def main():
     ap.add_argument("--ref-clips", type=int, default=384, help="clips per step of the CPU reference arm / cpu_baseline sample")
     ap.add_argument("--db-clips", type=int, default=1000000, help="database clips (whole job) for the search leg (config 4: 1M)")
     ap.add_argument("--queries", type=int, default=1000)
+    ap.add_argument("--config3-clips", type=int, default=120000, help="30 s clips of the whole job in the config-3 leg (1,000 hours = 120,000), sharded over the GPUs")
     ap.add_argument("--no-search", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-config3", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--no-group", action="store_true", help="skip the one-process sharded search (LBAudioDetectiveDatabaseGroup) leg that rank 0 runs when N > 1")
     ap.add_argument("--microbench", action="store_true", help="(default; kept for old command lines) measure the FP32 / POPC / LOP3 pipe rates the rooflines are quoted against")
     ap.add_argument("--no-microbench", action="store_true", help="skip the pipe-rate measurement (a fraction of a second)")
     args = ap.parse_args()
@@ -166,21 +198,10 @@ def main():
     import torch
     import torch.distributed as dist
     import lbaudiodetective_b200 as lb
-    from lbaudiodetective_b200.dist import shard_range, gather_and_merge_topk_device
+    from lbaudiodetective_b200.dist import shard_range, ShardedTopK
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    try:        # keep the pinned staging buffers of this rank on the NUMA node of its GPU (matters once 8 ranks upload at once)
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local)
-        n_words = (os.cpu_count() + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
-        cpus = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1}
-        if cpus:
-            os.sched_setaffinity(0, cpus & set(os.sched_getaffinity(0)) or cpus)
-    except Exception:
-        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lb.load_library(build_if_missing=False)          # the bench must run the in-tree CUDA library, never a fallback
@@ -205,7 +226,7 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
     pcm = torch.empty((n_clips, CLIP_LEN), dtype=torch.float32, device="cuda")
-    lb.synthesize_device(pcm.data_ptr(), n_clips, CLIP_LEN, CLIP_LEN, first_clip_id=rank * n_clips, stream=stream)      # every rank: its own clips
+    lb.synthesize_device(pcm.data_ptr(), n_clips, CLIP_LEN, CLIP_LEN, first_clip_id=rank * n_clips, stream=stream)      # every rank: its own clips, numbered globally
     words = torch.zeros((n_clips, SUBFPS, 8), dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
 
@@ -239,23 +260,55 @@ def main():
     w = words[:: max(1, n_clips // 64)].cpu().numpy().view(np.uint32)
     assert ((w[..., :4] & w[..., 4:]) == 0).all() and (np.unpackbits((w[..., :4] | w[..., 4:]).view(np.uint8), axis=-1).sum(-1) == 100).all()
 
-    # ---- roofline of the dominant kernel (the fused extraction kernel) ----
+    # ---- result hash that must not depend on the number of GPUs: the packed words of global clips r*clips .. r*clips+7, r = 0..7.
+    # Block r comes out of rank r's TIMED output when that rank exists; the blocks of ranks that do not exist in this run are
+    # extracted by rank 0 from the same synthetic clips (outside the timed region), so the list is the same at N = 1, 2, 4, 8. ----
+    my_block = sha(words[:HASH_CLIPS].cpu().numpy()) if n_clips >= HASH_CLIPS else None
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, my_block)
+    else:
+        gathered = [my_block]
+    extract_hashes = None
+    if rank == 0 and n_clips >= HASH_CLIPS:
+        blocks = list(gathered[:HASH_BLOCKS])
+        small = torch.empty((HASH_CLIPS, CLIP_LEN), dtype=torch.float32, device="cuda"); small_w = torch.zeros((HASH_CLIPS, SUBFPS, 8), dtype=torch.int32, device="cuda")
+        for r in range(len(blocks), HASH_BLOCKS):
+            lb.synthesize_device(small.data_ptr(), HASH_CLIPS, CLIP_LEN, CLIP_LEN, first_clip_id=r * n_clips, stream=stream)
+            det.process_batch_device(small.data_ptr(), HASH_CLIPS, CLIP_LEN, CLIP_LEN, small_w.data_ptr(), stream); torch.cuda.synchronize()
+            blocks.append(sha(small_w.cpu().numpy()))
+        extract_hashes = {"words_sha256": hashlib.sha256("".join(blocks).encode()).hexdigest(), "blocks_from_timed_output": min(world, HASH_BLOCKS),
+                          "what": "sha256 over the packed words of global clips r*%d .. r*%d+%d, r = 0..%d" % (n_clips, n_clips, HASH_CLIPS - 1, HASH_BLOCKS - 1)}
+        del small, small_w
+
+    # ---- roofline of the dominant kernel (the fused extraction kernel): FP32-pipe bound; HBM figures beside it ----
     hbm_peak, peak_src = measured_peaks()
     algo_bytes = n_clips * ALGO_BYTES_PER_CLIP
-    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
+    hbm_achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     flops = n_clips * WINDOWS_PER_CLIP * FLOP_PER_WINDOW
-    traffic = None
-    try:        # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch's clip count
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        traffic = tj["traffic_bytes_per_launch"] * n_clips / tj["clips_per_launch"] / 1e9
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
-                "peak_source": peak_src, "kernel": "bands_fused_kernel (FFT + band energies)", "kernel_ms": kernel_ms, "second_kernel": "haar_select32_kernel", "second_kernel_ms": kernel2_ms, "launches_per_step": n_timed // max(args.steps, 1), "algorithmic_bytes_per_launch": algo_bytes,
-                "note": "FP32-issue bound, not HBM bound (235 flop per new PCM byte, SURVEY.md §8d); fp32 figures alongside",
-                "fp32_tflops_algorithmic": flops / (kernel_ms * 1e-3) / 1e12, "fp32_peak_tflops_nominal": 148 * 128 * 2 * 1.965e9 / 1e12}
-    if not args.no_microbench and rank == 0:
-        mb = lb.microbench(); roofline["fp32_peak_tflops_measured"] = mb["fp32_tflops"]; roofline["fp32_frac_of_measured"] = roofline["fp32_tflops_algorithmic"] / mb["fp32_tflops"]
+    fp32_achieved = flops / (kernel_ms * 1e-3) / 1e12
+    fp32_nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+    traffic = None; traffic_src = None
+    for name in ("r02_traffic.json", "r01_traffic.json"):      # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this launch's clip count
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+            traffic = tj["traffic_bytes_per_launch"] * n_clips / tj["clips_per_launch"] / 1e9; traffic_src = "profiles/" + name + " (ncu --set full capture, not measured in this run)"
+            break
+        except Exception:
+            pass
+    mb = None
+    if not args.no_microbench:
+        mb = lb.microbench()          # every rank runs it (keeps the ranks in step); rank 0's numbers are reported
+    fp32_peak = mb["fp32_tflops"] if mb else fp32_nominal
+    roofline = {"bound": "fp32", "achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_achieved / fp32_peak,
+                "peak_source": "measured in this run: dependent-FMA microbenchmark, LBAudioDetectiveSupportMicrobench" if mb else "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
+                "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)", "traffic_source": traffic_src,
+                "kernel": "bands_fused_kernel (framing + real FFT + band energies)", "kernel_ms": kernel_ms, "second_kernel": "haar_select32_kernel", "second_kernel_ms": kernel2_ms,
+                "launches_per_step": n_timed // max(args.steps, 1), "algorithmic_flop_per_launch": flops, "algorithmic_bytes_per_launch": algo_bytes,
+                "fp32_peak_tflops_nominal": fp32_nominal,
+                "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak, "peak_source": peak_src,
+                        "note": "not the binding roofline: 235 flop per new PCM byte against a ridge of about 11 flop/B (SURVEY.md §8d)"}}
+    if mb:
         roofline["popc_gops_measured"] = mb["popc_gops"]; roofline["lop3_gops_measured"] = mb["lop3_gops"]
 
     # ---- e2e: the same pass through the host-buffer C-ABI call (H2D of the PCM and D2H of the words inside the timed region) ----
@@ -263,6 +316,16 @@ def main():
     if not args.no_e2e:
         host_pcm = torch.empty((n_clips, CLIP_LEN), dtype=torch.float32, pin_memory=True); host_pcm.copy_(pcm); torch.cuda.synchronize()
         host_words = torch.zeros((n_clips, SUBFPS, 8), dtype=torch.int32, pin_memory=True)
+        # the ceiling first: the same pinned bytes through plain cudaMemcpyAsync on every rank at once, nothing else running
+        scratch = torch.empty_like(pcm)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        scratch.copy_(host_pcm, non_blocking=True); barrier()
+        c0.record()
+        for _ in range(3):
+            scratch.copy_(host_pcm, non_blocking=True)
+        c1.record(); barrier()
+        ceil_ms = max_over_ranks(c0.elapsed_time(c1)) / 3
+        del scratch
         def e2e_step():
             det.process_batch_ptr(host_pcm.data_ptr(), n_clips, CLIP_LEN, CLIP_LEN, host_words.data_ptr())      # LBAudioDetectiveProcessPCMBatch: returns when the words are on the host
         e2e_step()
@@ -273,8 +336,13 @@ def main():
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         assert np.array_equal(host_words.numpy()[:: max(1, n_clips // 64)].view(np.uint32), w)
-        e2e = {"value": hours_per_gpu_step * world * args.steps / dt, "unit": "audio-hours/s", "h2d_bytes_per_step": n_clips * CLIP_LEN * 4,
-               "d2h_bytes_per_step": n_clips * SUBFPS * 32, "ms_per_step": 1e3 * dt / args.steps, "api": "LBAudioDetectiveProcessPCMBatch (pinned host buffers)"}
+        bytes_in = n_clips * CLIP_LEN * 4
+        e2e = {"value": hours_per_gpu_step * world * args.steps / dt, "unit": "audio-hours/s", "h2d_bytes_per_step": bytes_in,
+               "d2h_bytes_per_step": n_clips * SUBFPS * 32, "ms_per_step": 1e3 * dt / args.steps, "api": "LBAudioDetectiveProcessPCMBatch (pinned host buffers)",
+               "pcie_gbs": bytes_in / dt * args.steps / 1e9,
+               "h2d_ceiling_gbs_per_gpu": bytes_in / (ceil_ms * 1e-3) / 1e9, "h2d_ceiling_gbs_aggregate": world * bytes_in / (ceil_ms * 1e-3) / 1e9,
+               "h2d_ceiling_note": "the same pinned bytes copied by plain cudaMemcpyAsync on all %d rank(s) at once (max over ranks), nothing else running" % world,
+               "frac_of_h2d_ceiling": (bytes_in / dt * args.steps) / (bytes_in / (ceil_ms * 1e-3))}
         # extra: the same clips as signed 16-bit PCM through LBAudioDetectiveProcessPCMBatchInt16 (half the PCIe bytes; not the headline)
         host_i16 = torch.empty((n_clips, CLIP_LEN), dtype=torch.int16, pin_memory=True)
         host_i16.copy_((pcm * 32767.0).round().clamp_(-32768, 32767).to(torch.int16)); torch.cuda.synchronize()
@@ -285,10 +353,38 @@ def main():
         torch.cuda.synchronize(); dt16 = max_over_ranks(time.perf_counter() - t0)
         e2e["int16_pcm"] = {"value": hours_per_gpu_step * world * args.steps / dt16, "unit": "audio-hours/s", "h2d_bytes_per_step": n_clips * CLIP_LEN * 2,
                             "ms_per_step": 1e3 * dt16 / args.steps, "api": "LBAudioDetectiveProcessPCMBatchInt16 (extension; pinned host buffers)"}
-        e2e["pcie_gbs"] = n_clips * CLIP_LEN * 4 / dt * args.steps / 1e9
         del host_pcm, host_words, host_i16
-    del pcm
+    del pcm, words
     torch.cuda.empty_cache()
+
+    # ---- config 3: 1,000 hours (120,000 x 30 s clips) sharded by clip over the GPUs, device-resident, no collective on the data path ----
+    config3 = None
+    if not args.no_config3:
+        try:
+            lo3, hi3 = shard_range(args.config3_clips, rank, world); n3 = hi3 - lo3
+            pcm3 = torch.empty((n3, CLIP_LEN), dtype=torch.float32, device="cuda"); words3 = torch.zeros((n3, SUBFPS, 8), dtype=torch.int32, device="cuda")
+            lb.synthesize_device(pcm3.data_ptr(), n3, CLIP_LEN, CLIP_LEN, first_clip_id=lo3, stream=stream)
+            det.process_batch_device(pcm3.data_ptr(), n3, CLIP_LEN, CLIP_LEN, words3.data_ptr(), stream)       # warm-up (and the scratch slab)
+            barrier()
+            l0 = det.kernel_launches
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps3 = 2
+            a0.record()
+            for _ in range(steps3):
+                det.process_batch_device(pcm3.data_ptr(), n3, CLIP_LEN, CLIP_LEN, words3.data_ptr(), stream)
+            a1.record(); barrier()
+            ms3 = max_over_ranks(a0.elapsed_time(a1)) / steps3
+            hours3 = args.config3_clips * CLIP_LEN / SR / 3600.0
+            # the first 8 global clips are the first 8 clips of the config-2 workload: their words must be the same here
+            first_block = sha(words3[:HASH_CLIPS].cpu().numpy()) if rank == 0 else None
+            config3 = {"workload": "configs[2]: %d x 30 s clips = %.0f audio-hours resident in HBM, sharded by clip over %d GPU(s) (%d clips = %.1f GB per GPU), no collective" %
+                                   (args.config3_clips, hours3, world, n3, n3 * CLIP_LEN * 4 / 1e9),
+                       "value": hours3 / (ms3 * 1e-3), "unit": "audio-hours/s", "ms_per_step": ms3, "steps": steps3, "scaling": "strong",
+                       "gpu_launches_per_step": int((det.kernel_launches - l0) // steps3), "first_block_matches_config2": (first_block == gathered[0]) if rank == 0 else None}
+            del pcm3, words3
+        except Exception as ex:                                              # an allocation that does not fit must not take the headline with it
+            config3 = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+        torch.cuda.empty_cache()
 
     # ---- search leg (config 4): args.queries 10 s queries vs a args.db_clips-clip database sharded over the ranks, top-10, one gather ----
     search = None
@@ -297,25 +393,28 @@ def main():
         n_local = hi - lo
         db = lb.Database(200); db.set_clip_index_base(lo)
         codes = torch.empty((n_local, SUBFPS, 8), dtype=torch.int32, device="cuda")
-        lb.random_codes_device(codes.data_ptr(), n_local * SUBFPS, 200, seed=1234 + rank, stream=stream); torch.cuda.synchronize()
-        db.add_packed_device(codes.data_ptr(), n_local, SUBFPS)
-        g = torch.Generator(device="cpu"); g.manual_seed(7)
-        # queries: 6-subfingerprint excerpts of database clips of rank 0's shard (so every rank can build the same batch), at a random offset
-        q_src = torch.randint(0, max(1, args.db_clips // world), (args.queries,), generator=g)
-        q_off = torch.randint(0, SUBFPS - 6 + 1, (args.queries,), generator=g)
-        if rank == 0:
-            qw = torch.stack([codes[int(c), int(o):int(o) + 6] for c, o in zip(q_src, q_off)]).contiguous()
-        else:
-            qw = torch.empty((args.queries, 6, 8), dtype=torch.int32, device="cuda")
-        if world > 1:
-            dist.broadcast(qw, src=0)
+        # the database is a function of the GLOBAL subfingerprint index: the same 1M clips however many ranks hold them
+        lb.random_codes_device(codes.data_ptr(), n_local * SUBFPS, 200, seed=DB_SEED, stream=stream, first_subfp=lo * SUBFPS)
+        db.add_packed_device(codes.data_ptr(), n_local, SUBFPS, producer_stream=stream)
         del codes
-        d_sc = torch.empty((args.queries, 10), dtype=torch.float32, device="cuda"); d_idx = torch.empty((args.queries, 10), dtype=torch.int32, device="cuda")
+        g = torch.Generator(device="cpu"); g.manual_seed(7)
+        # queries: 6-subfingerprint excerpts of database clips anywhere in the database, at a random offset — built on every rank from the generator
+        q_src = torch.randint(0, args.db_clips, (args.queries,), generator=g)
+        q_off = torch.randint(0, SUBFPS - 6 + 1, (args.queries,), generator=g)
+        qw = torch.empty((args.queries, 6, 8), dtype=torch.int32, device="cuda")
+        for i, (c, o_) in enumerate(zip(q_src.tolist(), q_off.tolist())):
+            lb.random_codes_device(qw[i].data_ptr(), 6, 200, seed=DB_SEED, stream=stream, first_subfp=c * SUBFPS + o_)
+        torch.cuda.synchronize()
+        ex = ShardedTopK(args.queries, 10)
+        host_res = torch.empty((2, args.queries, 10), dtype=torch.int32, pin_memory=True)
         def search_step():
-            # per-GPU top-k on the shard, ONE NCCL all-gather of the [query][k] lists, device merge, then the result to the host
-            db.search_device(qw.data_ptr(), args.queries, 6, 10, d_sc.data_ptr(), d_idx.data_ptr(), stream=stream)
-            m_sc, m_id = gather_and_merge_topk_device(d_sc, d_idx, stream)
-            return m_sc.cpu().numpy(), m_id.cpu().numpy().view(np.uint32)
+            # per-GPU top-k on the shard written straight into the exchange payload, ONE NCCL all-gather, the merge kernel on the gather
+            # buffer in place, then ONE copy of the merged result to the host
+            db.search_device(qw.data_ptr(), args.queries, 6, 10, ex.scores_ptr, ex.indices_ptr, stream=stream)
+            m_sc, m_id = ex.gather_and_merge(stream)
+            host_res[0].copy_(m_sc.view(torch.int32), non_blocking=True); host_res[1].copy_(m_id, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return host_res[0].numpy().view(np.float32), host_res[1].numpy().view(np.uint32)
         for _ in range(2):
             sc, idx = search_step()
         db.kernel_timing(enable=True, reset=True)
@@ -328,11 +427,49 @@ def main():
         compares = args.queries * args.db_clips * 84
         search = {"metric": "Hamming compares/s", "value": compares * args.steps / dt, "unit": "compares/s", "ms_per_step": 1e3 * dt / args.steps,
                   "kernel_ms": k_ms / max(n_k, 1), "kernel_compares_per_s_per_gpu": (args.queries * n_local * 84) / (k_ms / max(n_k, 1) * 1e-3),
+                  "exchange_ms (all-gather + merge + result to host)": 1e3 * dt / args.steps - k_ms / max(n_k, 1),
                   "queries": args.queries, "db_clips": args.db_clips, "k": 10, "scaling": "strong", "workload": "configs[3]: 1,000 x 6-subfp queries vs 1M x 19-subfp clips, 14 offsets",
-                  "gpu_launches": db.kernel_launches}
+                  "gpu_launches": db.kernel_launches,
+                  "topk_sha256": sha(sc.copy(), idx.copy()), "topk_sha256_what": "sha256 over the merged [query][k] scores and global clip indices; the database and the queries are functions of global indices, so it must not change with the number of GPUs"}
+        topk_ref = (sc.copy(), idx.copy())
+
+    # ---- the same sharded search through the C-ABI alone: ONE process (rank 0) drives all the GPUs of the job (LBAudioDetectiveDatabaseGroup) ----
+    if search is not None and world > 1 and not args.no_group:
+        barrier()
+        store = dist.distributed_c10d._get_default_store()      # the other ranks wait on the host (a NCCL barrier would spin on their GPUs, which rank 0 is about to use)
+        if rank != 0:
+            store.wait(["lbad_group_leg_done"])
+        if rank == 0:
+            try:
+                group = lb.DatabaseGroup(200, list(range(world)))
+                for s in range(world):
+                    slo, shi = shard_range(args.db_clips, s, world)
+                    with torch.cuda.device(s):
+                        buf = torch.empty((shi - slo, SUBFPS, 8), dtype=torch.int32, device="cuda")
+                        st = torch.cuda.current_stream().cuda_stream
+                        lb.random_codes_device(buf.data_ptr(), (shi - slo) * SUBFPS, 200, seed=DB_SEED, stream=st, first_subfp=slo * SUBFPS)
+                        group.add_packed_device_to_shard(s, buf.data_ptr(), shi - slo, SUBFPS, slo, producer_stream=st)
+                        del buf
+                q_host = qw.cpu().numpy().view(np.uint32)
+                for _ in range(2):
+                    g_sc, g_id = group.search_packed(q_host, 10)
+                t0 = time.perf_counter(); dev_ms = []
+                for _ in range(args.steps):
+                    g_sc, g_id = group.search_packed(q_host, 10); dev_ms.append(group.last_search_ms)
+                dtg = time.perf_counter() - t0
+                search["group_api"] = {"api": "LBAudioDetectiveDatabaseGroupSearchPacked: one process, %d shards on %d GPUs, peer copies + device merge, no NCCL, host buffers in and out" % (world, world),
+                                       "value": compares * args.steps / dtg, "unit": "compares/s", "ms_per_step": 1e3 * dtg / args.steps, "device_ms_per_step": float(np.mean(dev_ms)),
+                                       "equals_torchrun_result": bool(np.array_equal(g_sc, topk_ref[0]) and np.array_equal(g_id, topk_ref[1])), "topk_sha256": sha(g_sc, g_id),
+                                       "gpu_launches": group.kernel_launches}
+                del group
+            except Exception as ex_:
+                search["group_api"] = {"error": "%s: %s" % (type(ex_).__name__, str(ex_)[:200])}
+            store.set("lbad_group_leg_done", "1")
+        barrier()
 
     if search is not None and world == 1:
         # the server-style call: ONE query against the whole database (lane-per-clip kernel + two-level merge), device-timed
+        d_sc = torch.empty((args.queries, 10), dtype=torch.float32, device="cuda"); d_idx = torch.empty((args.queries, 10), dtype=torch.int32, device="cuda")
         for _ in range(2):
             db.search_device(qw.data_ptr(), 1, 6, 10, d_sc.data_ptr(), d_idx.data_ptr(), stream=stream)
         q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -342,15 +479,45 @@ def main():
         q1.record(); torch.cuda.synchronize()
         assert int(d_idx[0, 0].item()) == int(q_src[0]) and float(d_sc[0, 0].item()) == 1.0
         search["single_query_ms"] = q0.elapsed_time(q1) / 10
-    if search is not None and rank == 0 and "popc_gops_measured" in roofline:
+    if search is not None and rank == 0 and mb:
         # the search is POPC-bound — 4 POPC per compare (one per 32-pair word) against the measured lane-POPC rate;
         # HBM only sees the database once per 128 queries
         per_gpu = search["kernel_compares_per_s_per_gpu"]
-        bound = roofline["popc_gops_measured"] * 1e9 / 4.0
+        bound = mb["popc_gops"] * 1e9 / 4.0
         db_bytes = (args.db_clips / world) * SUBFPS * (32 + 8)
         search["roofline"] = {"bound": "int-pipe (POPC)", "achieved": per_gpu, "peak": bound, "unit": "compares/s per GPU", "frac": per_gpu / bound,
-                              "note": "peak = measured lane-POPC rate / 4 POPC per compare; the kernel needs 3 (carry-save adder), so frac can exceed 1",
+                              "note": "peak = measured lane-POPC rate / 4 POPC per compare (SURVEY.md §8d); the kernel's carry-save form needs fewer, so frac can exceed 1",
                               "hbm_gbs": db_bytes * ((args.queries + 127) // 128) / (search["kernel_ms"] * 1e-3) / 1e9, "hbm_frac": db_bytes * ((args.queries + 127) // 128) / (search["kernel_ms"] * 1e-3) / 1e9 / hbm_peak}
+    if search is not None:
+        del db
+
+    # ---- config 5 shape (rank 0, one GPU): 1,000 one-subfingerprint (3 s) queries against 100,000 clips of 5 subfingerprints (9 s), 5 offsets each ----
+    config5 = None
+    if rank == 0 and not args.no_config5:
+        n5, c5, q5 = 100000, 5, 1000
+        db5 = lb.Database(200)
+        codes5 = torch.empty((n5, c5, 8), dtype=torch.int32, device="cuda")
+        lb.random_codes_device(codes5.data_ptr(), n5 * c5, 200, seed=55, stream=stream)
+        db5.add_packed_device(codes5.data_ptr(), n5, c5, producer_stream=stream)
+        g5 = torch.Generator(device="cpu"); g5.manual_seed(5)
+        src5 = torch.randint(0, n5, (q5,), generator=g5); off5 = torch.randint(0, c5, (q5,), generator=g5)
+        qw5 = codes5[src5.cuda(), off5.cuda()].reshape(q5, 1, 8).contiguous()
+        s5 = torch.empty((q5, 10), dtype=torch.float32, device="cuda"); i5 = torch.empty((q5, 10), dtype=torch.int32, device="cuda")
+        for _ in range(3):
+            db5.search_device(qw5.data_ptr(), q5, 1, 10, s5.data_ptr(), i5.data_ptr(), stream=stream)
+        db5.kernel_timing(enable=True, reset=True)
+        for _ in range(10):
+            db5.search_device(qw5.data_ptr(), q5, 1, 10, s5.data_ptr(), i5.data_ptr(), stream=stream)
+        torch.cuda.synchronize()
+        nk5, ms5 = db5.kernel_timing(enable=False, reset=True)
+        assert (s5[:, 0] == 1.0).all()
+        cmp5 = q5 * n5 * c5
+        config5 = {"workload": "configs[4] shape: 1,000 one-subfingerprint queries (3 s) vs 100,000 clips of 5 subfingerprints (9 s), 5 offsets per pair, top-10, one GPU",
+                   "kernel_ms": ms5 / max(nk5, 1), "value": cmp5 / (ms5 / max(nk5, 1) * 1e-3), "unit": "compares/s"}
+        if mb:
+            config5["roofline"] = {"bound": "int-pipe (POPC)", "achieved": config5["value"], "peak": mb["popc_gops"] * 1e9 / 4.0, "unit": "compares/s per GPU", "frac": config5["value"] / (mb["popc_gops"] * 1e9 / 4.0)}
+        del db5, codes5
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -360,8 +527,9 @@ def main():
         threads = os.cpu_count() or 1
         chk, v, secs = cpu_extract_baseline(args.ref_clips, threads)
         cpu = {"value": v, "unit": "audio-hours/s", "cores": threads, "kind": chk.kind,
-               "sample": "%d x 30 s clips of the same synthetic workload (%.1f s of wall time); float32 FFT stands in for vDSP" % (args.ref_clips, secs),
+               "sample": "%d x 30 s clips of the same synthetic workload (%.1f s of wall time), %d threads in one process" % (args.ref_clips, secs, threads),
                "search_compares_per_s": cpu_search_baseline(chk, threads)}
+        cpu.update(cpu_fft_note(chk))
     # ---- configs[0] (the reference's own headline call): compare two 10 s clips through the compare-audio path, one call at a time ----
     # (part of the cpu_baseline leg, skipped with --no-cpu: the oracle generates the two clips and is the timed CPU baseline, nothing else)
     config1 = None
@@ -379,13 +547,15 @@ def main():
             want = chk.compare_pcm(cfg, a, b, 0)
         cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
         config1 = {"workload": "configs[0]: compare two synthetic 10 s clips through the compare-audio path (LBAudioDetectiveComparePCM), one call at a time, host buffers",
-                   "us_per_call": gpu_us, "match": got, "reference_ms_per_call": cpu_ms, "reference_match": want, "reference_kind": chk.kind, "reference_cores": 1}
+                   "us_per_call": gpu_us, "match": got, "reference_ms_per_call": cpu_ms, "reference_match": want, "reference_kind": chk.kind, "reference_cores": 1,
+                   "reference_fft": "f64 definition (parity mode)"}
     line = {"metric": "audio-hours/s fingerprinted", "value": value, "unit": "audio-hours/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: batch fingerprint extraction of %d synthetic 30 s clips per GPU (FFT+band-energy kernel, then Haar+top-t+pack kernel)" % n_clips,
                        "clips_per_gpu": n_clips, "clip_seconds": 30, "window": 2048, "stride": 64, "bands": 32, "subfingerprint_length": 200,
                        "l2_policy": "inputs (%.1f GB per GPU) larger than L2" % (n_clips * CLIP_LEN * 4 / 1e9)},
-            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "search": search, "config1": config1}
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline, "cpu_baseline": cpu, "extract": extract_hashes,
+            "config3": config3, "search": search, "config5": config5, "config1": config1}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -97,7 +97,9 @@ LBAD_API OSStatus LBAudioDetectiveProcessPCMBatch(LBAudioDetectiveRef inDetectiv
  * the device as x / 32768, exactly what a float32 client format would have delivered. */
 LBAD_API OSStatus LBAudioDetectiveProcessPCMBatchInt16(LBAudioDetectiveRef inDetective, const SInt16* inSamples, UInt32 inNumberOfClips, UInt64 inFramesPerClip, UInt64 inClipStride, UInt32* outWords);
 /* Same, but inSamples and outWords are DEVICE pointers on the detective's device and the work is enqueued on
- * inStream (a cudaStream_t, NULL = the detective's own stream) without synchronising. */
+ * inStream (a cudaStream_t, NULL = the detective's own stream) without synchronising.  Calls on one detective share device scratch
+ * (the spectral images between the two kernels): the library orders them on the device, so calls enqueued on different streams are
+ * safe but run one after the other; use one detective per stream for concurrency. */
 LBAD_API OSStatus LBAudioDetectiveProcessPCMBatchDevice(LBAudioDetectiveRef inDetective, const Float32* inDeviceSamples, UInt32 inNumberOfClips, UInt64 inFramesPerClip, UInt64 inClipStride, UInt32* outDeviceWords, void* inStream);
 /* Stage dump for parity tests, one clip from host memory: outImages / outHaar are [subfp][128][B] floats (spectral
  * images before / after the Haar transform), outBooleans is [subfp][L]; any may be NULL.  inUseFusedKernel selects
@@ -112,8 +114,9 @@ LBAD_API OSStatus LBAudioDetectiveProcessPCMBatchStages(LBAudioDetectiveRef inDe
 LBAD_API OSStatus LBAudioDetectiveTransformImages(LBAudioDetectiveRef inDetective, const Float32* inImages, UInt32 inCount, Float32* outHaar, Boolean* outBooleans);
 /* ---- streaming extraction (addition): the recording use case of the essay (p.23-24) without the whole-clip requirement ---- */
 typedef struct LBAudioDetectiveStream *LBAudioDetectiveStreamRef;
-/* Borrows inDetective (which must outlive the stream and keep its window / stride / subfingerprint length); NULL if its
- * configuration is unsupported. */
+/* Borrows inDetective, which must outlive the stream and keep its configuration (window, stride, pitch steps, subfingerprint length,
+ * processing sample rate): an append after any of them changed returns kLBAudioDetectiveArgumentInvalid.  NULL if the configuration
+ * is unsupported. */
 LBAD_API LBAudioDetectiveStreamRef LBAudioDetectiveStreamNew(LBAudioDetectiveRef inDetective);
 LBAD_API OSStatus LBAudioDetectiveStreamDispose(LBAudioDetectiveStreamRef inStream);
 /* Appends PCM; every frame that the one-shot LBAudioDetectiveProcessPCM would produce for the samples appended so far is

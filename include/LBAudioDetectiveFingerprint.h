@@ -4,7 +4,8 @@
  * Drop-in for the reference's LBAudioDetective/LBAudioDetectiveFingerprint.h: same names, argument order,
  * ownership and return conventions.  Each entry point cites the reference declaration (FP.h) and definition
  * (FP.m = LBAudioDetectiveFingerprint.m) it replaces.  The two compare functions run on the GPU (CUDA, sm_100a);
- * there is no CPU fallback — they abort with a message if no CUDA device can be used.
+ * there is no CPU fallback — if the CUDA path cannot run they print the reason to stderr and return NaN (never a score computed some
+ * other way); LBAudioDetectiveFingerprintCompareToFingerprintStatus returns the status instead.
  *
  * Internal representation: besides the reference's one-byte-per-Boolean arrays (kept so that
  * GetSubfingerprintAtIndex is byte-identical), every subfingerprint is also held packed as two bit planes,
@@ -47,6 +48,11 @@ LBAD_API Float32 LBAudioDetectiveFingerprintCompareToFingerprint(LBAudioDetectiv
 LBAD_API Float32 LBAudioDetectiveFingerprintCompareSubfingerprints(LBAudioDetectiveFingerprintRef inFingerprint, Boolean* inSubfingerprint1, Boolean* inSubfingerprint2, UInt32 inRange);
 
 /* ---- additions (not in the reference): packed access and the reference's only wire format ----------- */
+
+/* LBAudioDetectiveFingerprintCompareToFingerprint with its status spelled out: noErr and *outMatch written, or
+ * kLBAudioDetectiveArgumentInvalid (NULL arguments, unsupported or mismatched subfingerprint lengths), kLBAudioDetectiveDeviceUnavailable,
+ * kLBAudioDetectiveDeviceError (reason in LBAudioDetectiveSupportLastError()) with *outMatch untouched. */
+LBAD_API OSStatus LBAudioDetectiveFingerprintCompareToFingerprintStatus(LBAudioDetectiveFingerprintRef inFingerprint1, LBAudioDetectiveFingerprintRef inFingerprint2, UInt32 inRange, Float32* outMatch);
 
 /* Words per bit plane for subfingerprint length L: 2, 4 or 8 (L <= 128, 256, 512); 0 if L is unsupported. */
 LBAD_API UInt32 LBAudioDetectiveFingerprintPackedWordsPerPlane(UInt32 inSubfingerprintLength);

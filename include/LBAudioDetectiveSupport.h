@@ -15,5 +15,10 @@ LBAD_API OSStatus LBAudioDetectiveSupportRandomCodesDevice(UInt32* d_words, UInt
 LBAD_API OSStatus LBAudioDetectiveSupportMicrobench(Float64* outFp32Tflops, Float64* outPopcGops, Float64* outLop3Gops);
 LBAD_API const char* LBAudioDetectiveSupportLastError(void);
 LBAD_API Boolean LBAudioDetectiveSupportDeviceAvailable(void);
+/* number of CUDA devices visible to this process (0 if none) */
+LBAD_API int LBAudioDetectiveSupportDeviceCount(void);
+/* LBAudioDetectiveSupportRandomCodesDevice for a slice of a larger set: subfingerprint i of the call is subfingerprint firstSubfp + i of
+ * the whole (the code depends on seed and the GLOBAL index only, so a sharded database holds the same clips however it is cut) */
+LBAD_API OSStatus LBAudioDetectiveSupportRandomCodesDeviceAt(UInt32* d_words, UInt64 nSubfps, UInt32 subfingerprintLength, UInt64 seed, UInt64 firstSubfp, void* stream);
 LBAD_EXTERN_C_END
 #endif

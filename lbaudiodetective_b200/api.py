@@ -93,6 +93,7 @@ def load_library(build_if_missing: bool = True):
         "LBAudioDetectiveFingerprintEqualToFingerprint": (u8, [vp, vp]),
         "LBAudioDetectiveFingerprintCompareToFingerprint": (f32, [vp, vp, u32]),
         "LBAudioDetectiveFingerprintCompareSubfingerprints": (f32, [vp, vp, vp, u32]),
+        "LBAudioDetectiveFingerprintCompareToFingerprintStatus": (C.c_int32, [vp, vp, u32, P(f32)]),
         "LBAudioDetectiveFingerprintPackedWordsPerPlane": (u32, [u32]),
         "LBAudioDetectiveFingerprintGetPackedSubfingerprintAtIndex": (u32, [vp, u32, vp]),
         "LBAudioDetectiveFingerprintAddPackedSubfingerprints": (C.c_int32, [vp, vp, u32]),
@@ -105,12 +106,26 @@ def load_library(build_if_missing: bool = True):
         "LBAudioDetectiveDatabaseSetClipIndexBase": (C.c_int32, [vp, u32]),
         "LBAudioDetectiveDatabaseAddFingerprint": (C.c_int32, [vp, vp, P(u32)]),
         "LBAudioDetectiveDatabaseAddPacked": (C.c_int32, [vp, vp, u32, vp, u32]),
-        "LBAudioDetectiveDatabaseAddPackedDevice": (C.c_int32, [vp, vp, u32, u32]),
+        "LBAudioDetectiveDatabaseAddPackedDevice": (C.c_int32, [vp, vp, u32, u32, vp]),
         "LBAudioDetectiveDatabaseSearchPacked": (C.c_int32, [vp, vp, u32, u32, u32, u32, vp, vp, vp]),
         "LBAudioDetectiveDatabaseSearch": (C.c_int32, [vp, P(vp), u32, u32, u32, vp, vp]),
         "LBAudioDetectiveDatabaseSearchDevice": (C.c_int32, [vp, vp, u32, u32, u32, u32, vp, vp, vp]),
         "LBAudioDetectiveDatabaseMergeTopK": (C.c_int32, [vp, vp, u32, u32, u32, vp, vp]),
         "LBAudioDetectiveDatabaseMergeTopKDevice": (C.c_int32, [vp, vp, u32, u32, u32, vp, vp, vp]),
+        "LBAudioDetectiveDatabaseMergeTopKDeviceStrided": (C.c_int32, [vp, vp, u32, u64, u32, u32, vp, vp, vp]),
+        "LBAudioDetectiveDatabaseGroupNew": (vp, [u32, P(C.c_int), u32]),
+        "LBAudioDetectiveDatabaseGroupDispose": (C.c_int32, [vp]),
+        "LBAudioDetectiveDatabaseGroupGetNumberOfShards": (u32, [vp]),
+        "LBAudioDetectiveDatabaseGroupGetNumberOfClips": (u64, [vp]),
+        "LBAudioDetectiveDatabaseGroupGetShardDevice": (C.c_int, [vp, u32]),
+        "LBAudioDetectiveDatabaseGroupGetShardNumberOfClips": (u32, [vp, u32]),
+        "LBAudioDetectiveDatabaseGroupAddPacked": (C.c_int32, [vp, vp, u32, vp, u32, P(u64)]),
+        "LBAudioDetectiveDatabaseGroupAddFingerprint": (C.c_int32, [vp, vp, P(u64)]),
+        "LBAudioDetectiveDatabaseGroupAddPackedDeviceToShard": (C.c_int32, [vp, u32, vp, u32, u32, u64, vp]),
+        "LBAudioDetectiveDatabaseGroupSearchPacked": (C.c_int32, [vp, vp, u32, u32, u32, u32, vp, vp]),
+        "LBAudioDetectiveDatabaseGroupSearch": (C.c_int32, [vp, P(vp), u32, u32, u32, vp, vp]),
+        "LBAudioDetectiveDatabaseGroupGetKernelLaunchCount": (u64, [vp]),
+        "LBAudioDetectiveDatabaseGroupGetLastSearchMilliseconds": (f64, [vp]),
         "LBAudioDetectiveDatabaseSave": (C.c_int32, [vp, C.c_char_p]),
         "LBAudioDetectiveDatabaseLoad": (vp, [C.c_char_p]),
         "LBAudioDetectiveDatabaseComparesPerQuery": (u64, [vp, u32]),
@@ -118,6 +133,8 @@ def load_library(build_if_missing: bool = True):
         "LBAudioDetectiveDatabaseGetKernelTiming": (u32, [vp, u8, u8, P(f64)]),
         "LBAudioDetectiveSupportSynthesizeDevice": (C.c_int32, [vp, u32, u64, u64, u64, u64, f64, vp]),
         "LBAudioDetectiveSupportRandomCodesDevice": (C.c_int32, [vp, u64, u32, u64, vp]),
+        "LBAudioDetectiveSupportRandomCodesDeviceAt": (C.c_int32, [vp, u64, u32, u64, u64, vp]),
+        "LBAudioDetectiveSupportDeviceCount": (C.c_int, []),
         "LBAudioDetectiveSupportMicrobench": (C.c_int32, [P(f64), P(f64), P(f64)]),
         "LBAudioDetectiveSupportLastError": (C.c_char_p, []),
         "LBAudioDetectiveSupportDeviceAvailable": (u8, []),
@@ -255,6 +272,12 @@ class Fingerprint:
     def compare(self, other, rng):
         """LBAudioDetectiveFingerprintCompareToFingerprint(self, other, rng) — runs on the GPU."""
         return float(self._L.LBAudioDetectiveFingerprintCompareToFingerprint(self.ref, other.ref, rng))
+
+    def compare_status(self, other, rng):
+        """(OSStatus, match) of LBAudioDetectiveFingerprintCompareToFingerprintStatus."""
+        out = C.c_float(-1.0)
+        st = self._L.LBAudioDetectiveFingerprintCompareToFingerprintStatus(self.ref, other.ref, rng, C.byref(out))
+        return int(st), float(out.value)
 
     def compare_subfingerprints(self, s1, s2, rng):
         a = np.ascontiguousarray(np.concatenate([s1, [0, 0]]), dtype=np.uint8); b = np.ascontiguousarray(np.concatenate([s2, [0, 0]]), dtype=np.uint8)
@@ -494,8 +517,9 @@ class Database:
             c = np.ascontiguousarray(counts, dtype=np.uint32)
             _check(self._L.LBAudioDetectiveDatabaseAddPacked(self.ref, _ptr(w), c.size, _ptr(c), 0), "DatabaseAddPacked")
 
-    def add_packed_device(self, d_words_ptr, n_clips, uniform_count):
-        _check(self._L.LBAudioDetectiveDatabaseAddPackedDevice(self.ref, d_words_ptr, n_clips, uniform_count), "DatabaseAddPackedDevice")
+    def add_packed_device(self, d_words_ptr, n_clips, uniform_count, producer_stream=None):
+        """producer_stream: the CUDA stream the words are being produced on (the append is ordered after it); None if they are complete."""
+        _check(self._L.LBAudioDetectiveDatabaseAddPackedDevice(self.ref, d_words_ptr, n_clips, uniform_count, producer_stream), "DatabaseAddPackedDevice")
 
     def search_packed(self, qwords, k, rng=0, all_scores=False):
         """qwords [queries][count][2W] -> (scores [q][k], clip indices [q][k][, full score matrix])."""
@@ -527,6 +551,69 @@ class Database:
         return int(n), float(ms.value)
 
 
+class DatabaseGroup:
+    """LBAudioDetectiveDatabaseGroupRef: a database sharded over several GPUs of this process (include/LBAudioDetectiveDatabase.h)."""
+
+    def __init__(self, subfingerprint_length=200, devices=(0,)):
+        self._L = lib(); self.L = subfingerprint_length
+        arr = (C.c_int * len(devices))(*devices)
+        self.ref = self._L.LBAudioDetectiveDatabaseGroupNew(subfingerprint_length, arr, len(devices))
+        if not self.ref:
+            raise LBADError(DEVICE_UNAVAILABLE, "LBAudioDetectiveDatabaseGroupNew")
+
+    def dispose(self):
+        if self.ref:
+            self._L.LBAudioDetectiveDatabaseGroupDispose(self.ref); self.ref = None
+
+    def __del__(self):
+        try:
+            self.dispose()
+        except Exception:
+            pass
+
+    shards = property(lambda s: int(s._L.LBAudioDetectiveDatabaseGroupGetNumberOfShards(s.ref)))
+    clips = property(lambda s: int(s._L.LBAudioDetectiveDatabaseGroupGetNumberOfClips(s.ref)))
+
+    def shard_device(self, i): return int(self._L.LBAudioDetectiveDatabaseGroupGetShardDevice(self.ref, i))
+    def shard_clips(self, i): return int(self._L.LBAudioDetectiveDatabaseGroupGetShardNumberOfClips(self.ref, i))
+
+    def add_packed(self, words, counts=None):
+        """words: [clips][count][2W] (uniform) or flat [total][2W] with counts[clips]; returns the first global clip index."""
+        w = np.ascontiguousarray(words, dtype=np.uint32); first = C.c_uint64(0)
+        if counts is None:
+            _check(self._L.LBAudioDetectiveDatabaseGroupAddPacked(self.ref, _ptr(w), w.shape[0], None, w.shape[1], C.byref(first)), "DatabaseGroupAddPacked")
+        else:
+            c = np.ascontiguousarray(counts, dtype=np.uint32)
+            _check(self._L.LBAudioDetectiveDatabaseGroupAddPacked(self.ref, _ptr(w), c.size, _ptr(c), 0, C.byref(first)), "DatabaseGroupAddPacked")
+        return int(first.value)
+
+    def add_fingerprint(self, fp):
+        idx = C.c_uint64(0)
+        _check(self._L.LBAudioDetectiveDatabaseGroupAddFingerprint(self.ref, fp.ref, C.byref(idx)), "DatabaseGroupAddFingerprint")
+        return int(idx.value)
+
+    def add_packed_device_to_shard(self, shard, d_words_ptr, n_clips, uniform_count, first_clip_index, producer_stream=None):
+        _check(self._L.LBAudioDetectiveDatabaseGroupAddPackedDeviceToShard(self.ref, shard, d_words_ptr, n_clips, uniform_count, first_clip_index, producer_stream), "DatabaseGroupAddPackedDeviceToShard")
+
+    def search_packed(self, qwords, k, rng=0):
+        q = np.ascontiguousarray(qwords, dtype=np.uint32); n_q, cq = q.shape[0], q.shape[1]
+        sc = np.zeros((n_q, k), np.float32); idx = np.zeros((n_q, k), np.uint32)
+        _check(self._L.LBAudioDetectiveDatabaseGroupSearchPacked(self.ref, _ptr(q), n_q, cq, rng, k, _ptr(sc), _ptr(idx)), "DatabaseGroupSearchPacked")
+        return sc, idx
+
+    def search(self, fingerprints, k, rng=0):
+        n = len(fingerprints); arr = (C.c_void_p * n)(*[f.ref for f in fingerprints])
+        sc = np.zeros((n, k), np.float32); idx = np.zeros((n, k), np.uint32)
+        _check(self._L.LBAudioDetectiveDatabaseGroupSearch(self.ref, arr, n, rng, k, _ptr(sc), _ptr(idx)), "DatabaseGroupSearch")
+        return sc, idx
+
+    @property
+    def kernel_launches(self): return int(self._L.LBAudioDetectiveDatabaseGroupGetKernelLaunchCount(self.ref))
+
+    @property
+    def last_search_ms(self): return float(self._L.LBAudioDetectiveDatabaseGroupGetLastSearchMilliseconds(self.ref))
+
+
 def merge_topk(scores, indices):
     """[lists][queries][k] -> merged [queries][k], ordered (score desc, index asc); runs the device merge kernel."""
     s = np.ascontiguousarray(scores, dtype=np.float32); i = np.ascontiguousarray(indices, dtype=np.uint32)
@@ -540,12 +627,22 @@ def merge_topk_device(d_scores_ptr, d_idx_ptr, n_lists, n_q, k, d_out_scores_ptr
     _check(lib().LBAudioDetectiveDatabaseMergeTopKDevice(d_scores_ptr, d_idx_ptr, n_lists, n_q, k, d_out_scores_ptr, d_out_idx_ptr, stream), "DatabaseMergeTopKDevice")
 
 
+def merge_topk_device_strided(d_scores_ptr, d_idx_ptr, n_lists, list_stride, n_q, k, d_out_scores_ptr, d_out_idx_ptr, stream=None):
+    """Lists list_stride elements apart (e.g. an all-gather buffer of [scores | indices] payloads, merged in place)."""
+    _check(lib().LBAudioDetectiveDatabaseMergeTopKDeviceStrided(d_scores_ptr, d_idx_ptr, n_lists, list_stride, n_q, k, d_out_scores_ptr, d_out_idx_ptr, stream), "DatabaseMergeTopKDeviceStrided")
+
+
 def synthesize_device(d_out_ptr, n_clips, clip_len, clip_stride, first_clip_id=0, base_seed=0x1BAD5EED, sample_rate=5512.0, stream=None):
     _check(lib().LBAudioDetectiveSupportSynthesizeDevice(d_out_ptr, n_clips, clip_len, clip_stride, first_clip_id, base_seed, sample_rate, stream), "SupportSynthesizeDevice")
 
 
-def random_codes_device(d_words_ptr, n_subfps, subfingerprint_length=200, seed=1, stream=None):
-    _check(lib().LBAudioDetectiveSupportRandomCodesDevice(d_words_ptr, n_subfps, subfingerprint_length, seed, stream), "SupportRandomCodesDevice")
+def random_codes_device(d_words_ptr, n_subfps, subfingerprint_length=200, seed=1, stream=None, first_subfp=0):
+    """Random rank-sign codes; subfingerprint i of the call is subfingerprint first_subfp + i of the whole set (a function of seed and global index)."""
+    _check(lib().LBAudioDetectiveSupportRandomCodesDeviceAt(d_words_ptr, n_subfps, subfingerprint_length, seed, first_subfp, stream), "SupportRandomCodesDeviceAt")
+
+
+def device_count() -> int:
+    return int(lib().LBAudioDetectiveSupportDeviceCount())
 
 
 def microbench():

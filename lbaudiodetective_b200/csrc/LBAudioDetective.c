@@ -408,7 +408,8 @@ struct LBAudioDetectiveStream {
     UInt64 pendingCount, pendingCapacity;
     UInt64 totalFrames;                         /* samples appended so far */
     UInt64 emitted;                             /* subfingerprints emitted so far */
-    UInt32 window, stride, sublen;              /* geometry frozen at creation */
+    UInt32 window, stride, sublen, bands;       /* configuration frozen at creation: a change on the borrowed detective fails the next append */
+    Float64 sampleRate;
 };
 
 LBAudioDetectiveStreamRef LBAudioDetectiveStreamNew(LBAudioDetectiveRef d) {
@@ -416,6 +417,7 @@ LBAudioDetectiveStreamRef LBAudioDetectiveStreamNew(LBAudioDetectiveRef d) {
     LBAudioDetectiveStreamRef s = calloc(1, sizeof *s);
     if (!s) return NULL;
     s->detective = d; s->window = d->windowSize; s->stride = d->analysisStride; s->sublen = d->subfingerprintLength;
+    s->bands = d->pitchStepCount; s->sampleRate = d->processingFormat.mSampleRate;
     s->fingerprint = LBAudioDetectiveFingerprintNew(0);
     UInt32 L = s->sublen;
     LBAudioDetectiveFingerprintSetSubfingerprintLength(s->fingerprint, &L);
@@ -432,7 +434,9 @@ OSStatus LBAudioDetectiveStreamDispose(LBAudioDetectiveStreamRef s) {
 OSStatus LBAudioDetectiveStreamAppend(LBAudioDetectiveStreamRef s, const Float32* inSamples, UInt64 inNumberFrames) {
     if (!s || (!inSamples && inNumberFrames)) return kLBAudioDetectiveArgumentInvalid;
     LBAudioDetectiveRef d = s->detective;
-    if (d->windowSize != s->window || d->analysisStride != s->stride || d->subfingerprintLength != s->sublen) return kLBAudioDetectiveArgumentInvalid;
+    /* subfingerprints of one fingerprint must come from one band table and one geometry */
+    if (d->windowSize != s->window || d->analysisStride != s->stride || d->subfingerprintLength != s->sublen || d->pitchStepCount != s->bands ||
+        d->processingFormat.mSampleRate != s->sampleRate) return kLBAudioDetectiveArgumentInvalid;
     if (s->pendingCount + inNumberFrames > s->pendingCapacity) {
         UInt64 cap = s->pendingCapacity ? s->pendingCapacity * 2 : 65536;
         while (cap < s->pendingCount + inNumberFrames) cap *= 2;

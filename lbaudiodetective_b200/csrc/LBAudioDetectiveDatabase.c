@@ -41,19 +41,19 @@ OSStatus LBAudioDetectiveDatabaseSetClipIndexBase(LBAudioDetectiveDatabaseRef d,
 OSStatus LBAudioDetectiveDatabaseAddFingerprint(LBAudioDetectiveDatabaseRef d, LBAudioDetectiveFingerprintRef fp, UInt32* outClipIndex) {
     if (!d || !fp || fp->subfingerprintLength != d->subfingerprintLength) return kLBAudioDetectiveArgumentInvalid;
     UInt32 idx = lbadcu_db_clips(d->db), n = fp->subfingerprintCount, dummy[16] = {0};
-    OSStatus e = lbad_status(lbadcu_db_append(d->db, n ? fp->words : dummy, 0, 1, &n, 0));
+    OSStatus e = lbad_status(lbadcu_db_append(d->db, n ? fp->words : dummy, 0, 1, &n, 0, NULL, -1));
     if (e == noErr && outClipIndex) *outClipIndex = idx;
     return e;
 }
 
 OSStatus LBAudioDetectiveDatabaseAddPacked(LBAudioDetectiveDatabaseRef d, const UInt32* inWords, UInt32 nClips, const UInt32* inCounts, UInt32 uniform) {
     if (!d || !inWords) return kLBAudioDetectiveArgumentInvalid;
-    return lbad_status(lbadcu_db_append(d->db, inWords, 0, nClips, inCounts, uniform));
+    return lbad_status(lbadcu_db_append(d->db, inWords, 0, nClips, inCounts, uniform, NULL, -1));
 }
 
-OSStatus LBAudioDetectiveDatabaseAddPackedDevice(LBAudioDetectiveDatabaseRef d, const UInt32* inDeviceWords, UInt32 nClips, UInt32 uniform) {
+OSStatus LBAudioDetectiveDatabaseAddPackedDevice(LBAudioDetectiveDatabaseRef d, const UInt32* inDeviceWords, UInt32 nClips, UInt32 uniform, void* inProducerStream) {
     if (!d || !inDeviceWords) return kLBAudioDetectiveArgumentInvalid;
-    return lbad_status(lbadcu_db_append(d->db, inDeviceWords, 1, nClips, NULL, uniform));
+    return lbad_status(lbadcu_db_append(d->db, inDeviceWords, 1, nClips, NULL, uniform, inProducerStream, -1));
 }
 
 static UInt32 pairs_for(LBAudioDetectiveDatabaseRef d, UInt32 inRange) {
@@ -94,7 +94,11 @@ OSStatus LBAudioDetectiveDatabaseMergeTopK(const Float32* inScores, const UInt32
 }
 
 OSStatus LBAudioDetectiveDatabaseMergeTopKDevice(const Float32* dScores, const UInt32* dIdx, UInt32 nLists, UInt32 nQ, UInt32 inK, Float32* dOutScores, UInt32* dOutIdx, void* stream) {
-    return lbad_status(lbadcu_merge_topk_device(dScores, dIdx, nLists, nQ, inK, dOutScores, dOutIdx, stream));
+    return lbad_status(lbadcu_merge_topk_device(dScores, dIdx, nLists, 0, nQ, inK, dOutScores, dOutIdx, stream));
+}
+
+OSStatus LBAudioDetectiveDatabaseMergeTopKDeviceStrided(const Float32* dScores, const UInt32* dIdx, UInt32 nLists, UInt64 inListStride, UInt32 nQ, UInt32 inK, Float32* dOutScores, UInt32* dOutIdx, void* stream) {
+    return lbad_status(lbadcu_merge_topk_device(dScores, dIdx, nLists, inListStride, nQ, inK, dOutScores, dOutIdx, stream));
 }
 
 UInt64 LBAudioDetectiveDatabaseComparesPerQuery(LBAudioDetectiveDatabaseRef d, UInt32 qCount) { return d ? lbadcu_db_compares_per_query(d->db, qCount) : 0; }
@@ -103,6 +107,89 @@ UInt32 LBAudioDetectiveDatabaseGetKernelTiming(LBAudioDetectiveDatabaseRef d, Bo
     if (outTotalMilliseconds) *outTotalMilliseconds = 0.0;
     return d ? lbadcu_db_timing(d->db, inEnable, inReset, outTotalMilliseconds) : 0;
 }
+
+/* ---- group: one process, several GPUs (include/LBAudioDetectiveDatabase.h) ---- */
+
+struct LBAudioDetectiveDatabaseGroup {
+    UInt32 subfingerprintLength;
+    UInt32 W;
+    lbadcu_group* group;
+};
+
+LBAudioDetectiveDatabaseGroupRef LBAudioDetectiveDatabaseGroupNew(UInt32 inSubfingerprintLength, const int* inDevices, UInt32 inNumberOfShards) {
+    UInt32 W = lbad_words_per_plane(inSubfingerprintLength);
+    if (!W || !inDevices || inNumberOfShards == 0) return NULL;
+    LBAudioDetectiveDatabaseGroupRef g = calloc(1, sizeof *g);
+    if (!g) return NULL;
+    g->subfingerprintLength = inSubfingerprintLength; g->W = W;
+    if (lbadcu_group_create(W, (inSubfingerprintLength + 1) / 2, inDevices, inNumberOfShards, &g->group) != LBAD_OK) { free(g); return NULL; }
+    return g;
+}
+
+OSStatus LBAudioDetectiveDatabaseGroupDispose(LBAudioDetectiveDatabaseGroupRef g) {
+    if (!g) return kLBAudioDetectiveArgumentInvalid;
+    lbadcu_group_destroy(g->group); free(g);
+    return noErr;
+}
+
+UInt32 LBAudioDetectiveDatabaseGroupGetNumberOfShards(LBAudioDetectiveDatabaseGroupRef g) { return g ? lbadcu_group_shards(g->group) : 0; }
+UInt64 LBAudioDetectiveDatabaseGroupGetNumberOfClips(LBAudioDetectiveDatabaseGroupRef g) { return g ? lbadcu_group_clips(g->group) : 0; }
+int LBAudioDetectiveDatabaseGroupGetShardDevice(LBAudioDetectiveDatabaseGroupRef g, UInt32 inShard) { return g ? lbadcu_group_shard_device(g->group, inShard) : -1; }
+UInt32 LBAudioDetectiveDatabaseGroupGetShardNumberOfClips(LBAudioDetectiveDatabaseGroupRef g, UInt32 inShard) {
+    lbadcu_db* db = g ? lbadcu_group_shard(g->group, inShard) : NULL;
+    return db ? lbadcu_db_clips(db) : 0;
+}
+
+OSStatus LBAudioDetectiveDatabaseGroupAddPacked(LBAudioDetectiveDatabaseGroupRef g, const UInt32* inWords, UInt32 nClips, const UInt32* inCounts, UInt32 uniform, UInt64* outFirst) {
+    if (!g || !inWords) return kLBAudioDetectiveArgumentInvalid;
+    UInt64 first = lbadcu_group_next_id(g->group);
+    OSStatus e = lbad_status(lbadcu_group_append(g->group, inWords, nClips, inCounts, uniform));
+    if (e == noErr && outFirst) *outFirst = first;
+    return e;
+}
+
+OSStatus LBAudioDetectiveDatabaseGroupAddFingerprint(LBAudioDetectiveDatabaseGroupRef g, LBAudioDetectiveFingerprintRef fp, UInt64* outClipIndex) {
+    if (!g || !fp || fp->subfingerprintLength != g->subfingerprintLength) return kLBAudioDetectiveArgumentInvalid;
+    UInt64 id = 0;
+    OSStatus e = lbad_status(lbadcu_group_append_one(g->group, fp->words, fp->subfingerprintCount, &id));
+    if (e == noErr && outClipIndex) *outClipIndex = id;
+    return e;
+}
+
+OSStatus LBAudioDetectiveDatabaseGroupAddPackedDeviceToShard(LBAudioDetectiveDatabaseGroupRef g, UInt32 inShard, const UInt32* dWords, UInt32 nClips, UInt32 uniform, UInt64 inFirst, void* inProducerStream) {
+    if (!g || !dWords) return kLBAudioDetectiveArgumentInvalid;
+    return lbad_status(lbadcu_group_append_device(g->group, inShard, dWords, nClips, uniform, inFirst, inProducerStream));
+}
+
+static UInt32 group_pairs_for(LBAudioDetectiveDatabaseGroupRef g, UInt32 inRange) {
+    if (inRange == 0) inRange = g->subfingerprintLength;                         /* LBAudioDetective.m:443-445 */
+    return lbad_pairs_for_range(inRange, g->subfingerprintLength);
+}
+
+OSStatus LBAudioDetectiveDatabaseGroupSearchPacked(LBAudioDetectiveDatabaseGroupRef g, const UInt32* inQueryWords, UInt32 nQ, UInt32 qCount, UInt32 inRange, UInt32 inK,
+                                                   Float32* outScores, UInt32* outClipIndices) {
+    if (!g || (!inQueryWords && qCount) || !outScores || !outClipIndices) return kLBAudioDetectiveArgumentInvalid;
+    UInt32 dummy[16] = {0};
+    return lbad_status(lbadcu_group_search_host(g->group, qCount ? inQueryWords : dummy, nQ, qCount, group_pairs_for(g, inRange), inK, outScores, outClipIndices));
+}
+
+OSStatus LBAudioDetectiveDatabaseGroupSearch(LBAudioDetectiveDatabaseGroupRef g, const LBAudioDetectiveFingerprintRef* inQueries, UInt32 nQ, UInt32 inRange, UInt32 inK,
+                                             Float32* outScores, UInt32* outClipIndices) {
+    if (!g || !inQueries || nQ == 0) return kLBAudioDetectiveArgumentInvalid;
+    UInt32 qCount = inQueries[0]->subfingerprintCount;
+    for (UInt32 i = 0; i < nQ; i++)
+        if (inQueries[i]->subfingerprintCount != qCount || inQueries[i]->subfingerprintLength != g->subfingerprintLength) return kLBAudioDetectiveArgumentInvalid;
+    size_t per = (size_t)qCount * 2 * g->W;
+    UInt32* words = malloc(((per * nQ) > 0 ? per * nQ : 1) * sizeof(UInt32));
+    if (!words) return kLBAudioDetectiveArgumentInvalid;
+    for (UInt32 i = 0; i < nQ; i++) memcpy(words + per * i, inQueries[i]->words, per * sizeof(UInt32));
+    OSStatus e = LBAudioDetectiveDatabaseGroupSearchPacked(g, words, nQ, qCount, inRange, inK, outScores, outClipIndices);
+    free(words);
+    return e;
+}
+
+UInt64 LBAudioDetectiveDatabaseGroupGetKernelLaunchCount(LBAudioDetectiveDatabaseGroupRef g) { return g ? lbadcu_group_launches(g->group) : 0; }
+Float64 LBAudioDetectiveDatabaseGroupGetLastSearchMilliseconds(LBAudioDetectiveDatabaseGroupRef g) { return g ? lbadcu_group_last_search_ms(g->group) : 0.0; }
 
 /* ---- persistence: a packed binary file, so that a database can be reloaded without re-extracting ----
  * little-endian: char magic[8] = "LBADDB1\0"; u32 L; u32 W; u32 clips; u32 reserved; u64 subfingerprints;
@@ -143,7 +230,7 @@ LBAudioDetectiveDatabaseRef LBAudioDetectiveDatabaseLoad(const char* inPath) {
     for (UInt32 c = 0; c < hdr[2]; c++) total += counts[c];
     if (total != subfps) goto done;
     d = LBAudioDetectiveDatabaseNew(hdr[0]);
-    if (d && hdr[2] && lbadcu_db_append(d->db, words, 0, hdr[2], counts, 0) != LBAD_OK) { LBAudioDetectiveDatabaseDispose(d); d = NULL; }
+    if (d && hdr[2] && lbadcu_db_append(d->db, words, 0, hdr[2], counts, 0, NULL, -1) != LBAD_OK) { LBAudioDetectiveDatabaseDispose(d); d = NULL; }
 done:
     fclose(f); free(counts); free(words);
     return d;

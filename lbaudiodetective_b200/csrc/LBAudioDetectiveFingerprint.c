@@ -4,6 +4,7 @@
  * lbad_search.cu (a one-clip database against a one-query batch) — no arithmetic of the match happens on the CPU.
  */
 #include "lbad_host.h"
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
@@ -138,31 +139,43 @@ Boolean LBAudioDetectiveFingerprintEqualToFingerprint(LBAudioDetectiveFingerprin
     return memcmp(a->booleans, b->booleans, (size_t)a->subfingerprintCount * a->subfingerprintLength) == 0;
 }
 
-static void die_no_device(const char* what, int code) {
-    fprintf(stderr, "%s: CUDA path unavailable (%d: %s). This library has no CPU fallback.\n", what, code, lbadcu_last_error());
-    abort();
+/* The two value-returning compare functions have no status to return an error in (FP.h:134, FP.h:147).  When the CUDA path cannot
+ * run — no device, or a CUDA call failed — they say so on stderr, leave the reason in LBAudioDetectiveSupportLastError() and return
+ * NaN: loud, never a plausible score and never a silently computed one (there is no CPU fallback), and the host process lives on.
+ * LBAudioDetectiveFingerprintCompareToFingerprintStatus is the same call with the status spelled out. */
+static Float32 compare_failed(const char* what, int code) {
+    fprintf(stderr, "%s: CUDA path unavailable (%d: %s). This library has no CPU fallback; returning NaN.\n", what, code, lbadcu_last_error());
+    return (Float32)NAN;
 }
 
 /* score = CompareToFingerprint(fp1, fp2, range) on the GPU (compare_pair_kernel, cached per-thread context) */
-static Float32 gpu_compare(const UInt32* w1, UInt32 c1, const UInt32* w2, UInt32 c2, UInt32 W, UInt32 pairs, UInt32 pairs_full) {
-    (void)pairs_full;
+static int gpu_compare(const UInt32* w1, UInt32 c1, const UInt32* w2, UInt32 c2, UInt32 W, UInt32 pairs, Float32* out) {
+    return lbadcu_compare_pair(W, pairs, w1, c1, w2, c2, out);
+}
+
+OSStatus LBAudioDetectiveFingerprintCompareToFingerprintStatus(LBAudioDetectiveFingerprintRef fp1, LBAudioDetectiveFingerprintRef fp2, UInt32 inRange, Float32* outMatch) {
+    if (!fp1 || !fp2 || !outMatch) return kLBAudioDetectiveArgumentInvalid;
+    /* after the swap of FP.m:123-131 the length used by FP.m:155 is that of the fingerprint with more subfingerprints */
+    LBAudioDetectiveFingerprintRef longer = fp1->subfingerprintCount < fp2->subfingerprintCount ? fp2 : fp1;
+    UInt32 L = longer->subfingerprintLength, W = lbad_words_per_plane(L);
+    if (!W || lbad_words_per_plane(fp1->subfingerprintLength) != W || lbad_words_per_plane(fp2->subfingerprintLength) != W) return kLBAudioDetectiveArgumentInvalid;
     Float32 score = 0.0f;
-    int e = lbadcu_compare_pair(W, pairs, w1, c1, w2, c2, &score);
-    if (e != LBAD_OK) die_no_device("LBAudioDetectiveFingerprintCompareToFingerprint", e);
-    return score;
+    OSStatus e = lbad_status(gpu_compare(fp1->words, fp1->subfingerprintCount, fp2->words, fp2->subfingerprintCount, W, lbad_pairs_for_range(inRange, L), &score));
+    if (e == noErr) *outMatch = score;
+    return e;
 }
 
 /* FP.m:119-149 */
 Float32 LBAudioDetectiveFingerprintCompareToFingerprint(LBAudioDetectiveFingerprintRef fp1, LBAudioDetectiveFingerprintRef fp2, UInt32 inRange) {
-    /* after the swap of FP.m:123-131 the length used by FP.m:155 is that of the fingerprint with more subfingerprints */
-    LBAudioDetectiveFingerprintRef longer = fp1->subfingerprintCount < fp2->subfingerprintCount ? fp2 : fp1;
-    UInt32 L = longer->subfingerprintLength, W = lbad_words_per_plane(L);
-    if (!W || lbad_words_per_plane(fp1->subfingerprintLength) != W || lbad_words_per_plane(fp2->subfingerprintLength) != W) {
+    Float32 score = 0.0f;
+    OSStatus e = LBAudioDetectiveFingerprintCompareToFingerprintStatus(fp1, fp2, inRange, &score);
+    if (e == kLBAudioDetectiveArgumentInvalid) {
         fprintf(stderr, "LBAudioDetectiveFingerprintCompareToFingerprint: unsupported or mismatched subfingerprint lengths (%u, %u)\n",
-                (unsigned)fp1->subfingerprintLength, (unsigned)fp2->subfingerprintLength);
+                fp1 ? (unsigned)fp1->subfingerprintLength : 0u, fp2 ? (unsigned)fp2->subfingerprintLength : 0u);
         return 0.0f;
     }
-    return gpu_compare(fp1->words, fp1->subfingerprintCount, fp2->words, fp2->subfingerprintCount, W, lbad_pairs_for_range(inRange, L), (L + 1) / 2);
+    if (e != noErr) return compare_failed("LBAudioDetectiveFingerprintCompareToFingerprint", (int)e);
+    return score;
 }
 
 /* FP.m:151-176 */
@@ -174,7 +187,10 @@ Float32 LBAudioDetectiveFingerprintCompareSubfingerprints(LBAudioDetectiveFinger
     UInt32 w1[16], w2[16];
     lbad_pack_booleans(s1, n, W, w1);
     lbad_pack_booleans(s2, n, W, w2);
-    return gpu_compare(w1, 1, w2, 1, W, (lim + 1) / 2, (L + 1) / 2);
+    Float32 score = 0.0f;
+    int e = gpu_compare(w1, 1, w2, 1, W, (lim + 1) / 2, &score);
+    if (e != LBAD_OK) return compare_failed("LBAudioDetectiveFingerprintCompareSubfingerprints", e);
+    return score;
 }
 
 /* ---- additions ---- */

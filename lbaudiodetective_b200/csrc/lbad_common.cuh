@@ -20,6 +20,21 @@ void set_error(const char* fmt, ...);
         }                                                                                           \
     } while (0)
 
+/* Makes `device` current for the scope of an entry point and puts the caller's device back on the way out: a drop-in library
+ * must not leave the host application on another GPU than the one it had selected. */
+struct DeviceScope {
+    int prev = -1; cudaError_t status = cudaSuccess;
+    explicit DeviceScope(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != device) status = cudaSetDevice(device);
+        else prev = -1;                                     /* nothing to restore */
+    }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define LBAD_ON_DEVICE(dev) ::lbad::DeviceScope _device_scope(dev); LBAD_CUDA_TRY(_device_scope.status)
+
 /* cudaMalloc with scope lifetime, so that an early error return does not leak */
 template <class T>
 struct DevBuf {

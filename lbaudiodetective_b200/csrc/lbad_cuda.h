@@ -38,6 +38,7 @@ typedef struct lbadcu_plan lbadcu_plan;
 
 /* 0 if a CUDA device is usable */
 int  lbadcu_device_available(void);
+int  lbadcu_device_count(void);
 const char* lbadcu_last_error(void);
 
 int  lbadcu_plan_create(const lbadcu_geometry* g, lbadcu_plan** out);
@@ -101,8 +102,11 @@ void lbadcu_db_set_base(lbadcu_db* db, uint32_t base);
 void* lbadcu_db_stream(lbadcu_db* db);
 uint64_t lbadcu_db_launches(const lbadcu_db* db);
 uint32_t lbadcu_db_timing(lbadcu_db* db, int enable, int reset, double* total_ms);
-/* counts == NULL -> uniform_count for every clip; words on host or device */
-int  lbadcu_db_append(lbadcu_db* db, const uint32_t* words, int words_on_device, uint32_t n_clips, const uint32_t* counts, uint32_t uniform_count);
+/* counts == NULL -> uniform_count for every clip; words on host or device.  producer_stream (device words only, may be NULL): the stream
+ * the words are being produced on — the copy is ordered after the work enqueued there so far.  first_global_id >= 0: the clips carry
+ * the global ids first_global_id, first_global_id + 1, ... (a shard whose clips are not one contiguous range); -1: id = base + index. */
+int  lbadcu_db_append(lbadcu_db* db, const uint32_t* words, int words_on_device, uint32_t n_clips, const uint32_t* counts, uint32_t uniform_count,
+                      void* producer_stream, int64_t first_global_id);
 int  lbadcu_db_download(lbadcu_db* db, uint32_t* h_words, uint32_t* h_counts);
 /* pairs = number of (P,M) bit pairs compared = ceil(min(range, L)/2).  Outputs [q][k]; d_all optional [q][clips]. */
 int  lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_qwords, uint32_t n_q, uint32_t q_count, uint32_t pairs, uint32_t k,
@@ -113,7 +117,24 @@ uint64_t lbadcu_db_compares_per_query(const lbadcu_db* db, uint32_t q_count);
 /* merges [list][q][k] top-k lists (host memory) with the device merge kernel; order (score desc, index asc) */
 int  lbadcu_merge_topk_host(const float* h_sc, const uint32_t* h_id, uint32_t n_lists, uint32_t n_q, uint32_t k, float* o_sc, uint32_t* o_id);
 
-int  lbadcu_merge_topk_device(const float* d_sc, const uint32_t* d_id, uint32_t n_lists, uint32_t n_q, uint32_t k, float* d_o_sc, uint32_t* d_o_id, void* stream);
+/* ---- a database sharded over several devices of this process (lbad_search.cu, "group") ---- */
+typedef struct lbadcu_group lbadcu_group;
+int  lbadcu_group_create(uint32_t words_per_plane, uint32_t pairs_full, const int* devices, uint32_t n_shards, lbadcu_group** out);
+void lbadcu_group_destroy(lbadcu_group* g);
+uint32_t lbadcu_group_shards(const lbadcu_group* g);
+lbadcu_db* lbadcu_group_shard(lbadcu_group* g, uint32_t i);
+int  lbadcu_group_shard_device(const lbadcu_group* g, uint32_t i);
+uint64_t lbadcu_group_clips(const lbadcu_group* g);
+uint64_t lbadcu_group_next_id(const lbadcu_group* g);
+uint64_t lbadcu_group_launches(const lbadcu_group* g);
+double lbadcu_group_last_search_ms(const lbadcu_group* g);
+int  lbadcu_group_append(lbadcu_group* g, const uint32_t* h_words, uint32_t n_clips, const uint32_t* counts, uint32_t uniform_count);
+int  lbadcu_group_append_one(lbadcu_group* g, const uint32_t* h_words, uint32_t count, uint64_t* out_id);
+int  lbadcu_group_append_device(lbadcu_group* g, uint32_t shard, const uint32_t* d_words, uint32_t n_clips, uint32_t uniform_count, uint64_t first_global_id, void* producer_stream);
+int  lbadcu_group_search_host(lbadcu_group* g, const uint32_t* h_qwords, uint32_t n_q, uint32_t q_count, uint32_t pairs, uint32_t k, float* h_scores, uint32_t* h_idx);
+
+/* list l starts at d_sc + l * list_stride / d_id + l * list_stride (elements; 0 = n_q * k, lists back to back) */
+int  lbadcu_merge_topk_device(const float* d_sc, const uint32_t* d_id, uint32_t n_lists, uint64_t list_stride, uint32_t n_q, uint32_t k, float* d_o_sc, uint32_t* d_o_id, void* stream);
 /* one pair, LBAudioDetectiveFingerprintCompareToFingerprint(fp1, fp2) with pairs = ceil(min(range, L)/2); cached per-thread context */
 int  lbadcu_compare_pair(uint32_t words_per_plane, uint32_t pairs, const uint32_t* w1, uint32_t c1, const uint32_t* w2, uint32_t c2, float* out);
 /* the same on packed words that are already on the device; the score stays on the device (d_out) — no synchronisation */
@@ -127,7 +148,7 @@ int  lbadcu_compare_pcm_host(lbadcu_plan* p, const float* h1, uint64_t n1, const
 int  lbadcu_synth_device(float* d_out, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride, uint64_t first_clip_id,
                          uint64_t base_seed, double sample_rate, void* stream);
 /* random rank-sign codes straight into packed words, for search timing at sizes extraction would take long to fill */
-int  lbadcu_random_codes_device(uint32_t* d_words, uint64_t n_subfps, uint32_t words_per_plane, uint32_t pairs, uint64_t seed, void* stream);
+int  lbadcu_random_codes_device(uint32_t* d_words, uint64_t n_subfps, uint32_t words_per_plane, uint32_t pairs, uint64_t seed, uint64_t first_subfp, void* stream);
 
 /* ---- microbenchmarks (roofline denominators measured on the box: FP32 FMA rate, POPC rate) ---- */
 int  lbadcu_microbench(double* fp32_tflops, double* popc_gops, double* lop3_gops);

@@ -879,6 +879,9 @@ struct lbadcu_plan {
     float2 *d_tw_m = nullptr, *d_tw_n = nullptr; float4 *d_tw1 = nullptr, *d_tw2 = nullptr;
     bool static_range = false;
     float* d_scratch[4] = {nullptr, nullptr, nullptr, nullptr}; size_t scratch_frames[4] = {0, 0, 0, 0};   /* spectral images: slot 0 for device-API calls, 1..3 for the host pipeline's chunk buffers */
+    /* a slot's images live between the two kernels of one call: a call on another stream than the slot's previous user waits for that
+     * one's second kernel (calls on one detective are serialised on the device, whatever streams they are enqueued on) */
+    cudaEvent_t scratch_done[4] = {nullptr, nullptr, nullptr, nullptr}; cudaStream_t scratch_stream[4] = {nullptr, nullptr, nullptr, nullptr}; bool scratch_used[4] = {false, false, false, false};
     int16_t* d_chunk_i16[3] = {nullptr, nullptr, nullptr}; size_t chunk_i16 = 0;
     float* d_chunk_pcm[3] = {nullptr, nullptr, nullptr}; uint32_t* d_chunk_words[3] = {nullptr, nullptr, nullptr};
     size_t chunk_pcm_floats = 0, chunk_words = 0;
@@ -900,6 +903,12 @@ extern "C" int lbadcu_device_available(void) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n <= 0) { cudaGetLastError(); return LBAD_ERR_NODEVICE; }
     return LBAD_OK;
+}
+
+extern "C" int lbadcu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
 }
 
 static uint32_t ilog2(uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l; }
@@ -972,6 +981,7 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     for (uint32_t b = 0; b < LBAD_MAX_BANDS; b++) { p->bt.klow[b] = b < B ? geo->klow[b] : 0; p->bt.khigh[b] = b < B ? geo->khigh[b] : 0; p->bt.divisor[b] = b < B ? geo->divisor[b] : 1.0f; }
     LBAD_CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 3; i++) LBAD_CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) LBAD_CUDA_TRY(cudaEventCreateWithFlags(&p->scratch_done[i], cudaEventDisableTiming));
     /* twiddle tables, evaluated in double and rounded once */
     std::vector<float2> twm(M / 2), twn(M); std::vector<float4> tw1(512), tw2(512);
     for (uint32_t j = 0; j < M / 2; j++) { const double a = 2.0 * M_PI * j / M; twm[j] = make_float2((float)cos(a), (float)-sin(a)); }
@@ -1033,8 +1043,9 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
 
 extern "C" void lbadcu_plan_destroy(lbadcu_plan* p) {
     if (!p) return;
-    cudaSetDevice(p->device);
+    DeviceScope _device_scope(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
+    for (int i = 0; i < 4; i++) if (p->scratch_done[i]) { if (p->scratch_used[i]) cudaEventSynchronize(p->scratch_done[i]); cudaEventDestroy(p->scratch_done[i]); }
     p->timer.clear(); p->timer2.clear();
     cudaFree(p->d_tw_m); cudaFree(p->d_tw_n); cudaFree(p->d_tw1); cudaFree(p->d_tw2); for (int i = 0; i < 4; i++) cudaFree(p->d_scratch[i]); for (int i = 0; i < 3; i++) cudaFree(p->d_chunk_i16[i]);
     for (int i = 0; i < 3; i++) { cudaFree(p->d_chunk_pcm[i]); cudaFree(p->d_chunk_words[i]); if (p->copy_streams[i]) cudaStreamDestroy(p->copy_streams[i]); }
@@ -1088,7 +1099,7 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
                                uint32_t* d_words, float* d_images, float* d_haar, int mode, void* stream, int slot) {
     if (!p || !d_pcm || !d_words) return LBAD_ERR_ARG;
     if (clip_len < p->g.window) return LBAD_ERR_ARG;
-    LBAD_CUDA_TRY(cudaSetDevice(p->device));
+    LBAD_ON_DEVICE(p->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : p->stream;
     const uint64_t frames_per_clip = ((clip_len - p->g.window) / p->g.stride) / LBAD_ROWS_PER_FRAME;   /* m:250-255 */
     const uint64_t total_frames64 = frames_per_clip * n_clips;
@@ -1098,6 +1109,11 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
     Geo g = p->g; g.frames_per_clip = (uint32_t)frames_per_clip; g.clip_stride = clip_stride;
     const bool fused = mode == 1 ? true : mode == 2 ? false : p->fused_ok;
     if (fused && !p->fused_ok) return LBAD_ERR_ARG;
+    struct SlotOrder {           /* orders this call after the slot's previous user and marks the slot on every way out */
+        lbadcu_plan* p; int slot; cudaStream_t s; bool active;
+        ~SlotOrder() { if (active && cudaEventRecord(p->scratch_done[slot], s) == cudaSuccess) { p->scratch_stream[slot] = s; p->scratch_used[slot] = true; } }
+    } slot_order{p, slot, s, d_images == nullptr};
+    if (!d_images && p->scratch_used[slot] && p->scratch_stream[slot] != s) LBAD_CUDA_TRY(cudaStreamWaitEvent(s, p->scratch_done[slot], 0));
     if (fused) {
         /* fast path: FFT + bands kernel -> spectral images (global, L2-friendly 16 KB each) -> Haar/select/pack kernel */
         const bool carry = g.window == 2048 && g.stride == 64;           /* consecutive windows one pass-1 input apart: half transforms are shared */
@@ -1125,6 +1141,7 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
         const uint32_t slab_cap = p->slab_frames_cap;                     /* <= 4 GB of images per slab (LBAD_SLAB_FRAMES overrides, for tests) */
         const uint32_t slab_frames = d_images ? total_frames : (total_frames < slab_cap ? total_frames : slab_cap);
         if (!d_images && p->scratch_frames[slot] < slab_frames) {
+            if (p->scratch_used[slot]) LBAD_CUDA_TRY(cudaEventSynchronize(p->scratch_done[slot]));
             LBAD_CUDA_TRY(cudaStreamSynchronize(s));
             cudaFree(p->d_scratch[slot]); p->d_scratch[slot] = nullptr; p->scratch_frames[slot] = 0;
             LBAD_CUDA_TRY(cudaMalloc(&p->d_scratch[slot], (size_t)slab_frames * LBAD_ROWS_PER_FRAME * 32 * sizeof(float)));
@@ -1162,6 +1179,7 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
         clips_per_slab = (uint32_t)(want_clips < n_clips ? want_clips : n_clips);
         const size_t need = (size_t)clips_per_slab * frames_per_clip;
         if (p->scratch_frames[slot] < need * 2) {                         /* sized for 64 bands: twice the 32-band frame size */
+            if (p->scratch_used[slot]) LBAD_CUDA_TRY(cudaEventSynchronize(p->scratch_done[slot]));
             LBAD_CUDA_TRY(cudaStreamSynchronize(s));
             cudaFree(p->d_scratch[slot]); p->d_scratch[slot] = nullptr; p->scratch_frames[slot] = 0;
             LBAD_CUDA_TRY(cudaMalloc(&p->d_scratch[slot], need * 2 * LBAD_ROWS_PER_FRAME * 32 * sizeof(float)));
@@ -1189,7 +1207,7 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
 
 extern "C" int lbadcu_transform_images_host(lbadcu_plan* p, const float* h_images, uint32_t count, float* h_haar, uint32_t* h_words) {
     if (!p || !h_images || count == 0) return LBAD_ERR_ARG;
-    LBAD_CUDA_TRY(cudaSetDevice(p->device));
+    LBAD_ON_DEVICE(p->device);
     const size_t n = (size_t)count * LBAD_ROWS_PER_FRAME * p->g.bands, nw = (size_t)count * 2 * p->g.words_per_plane;
     DevBuf<float> d_img, d_haar; DevBuf<uint32_t> d_words;
     LBAD_CUDA_TRY(d_img.alloc(n)); LBAD_CUDA_TRY(d_haar.alloc(n)); LBAD_CUDA_TRY(d_words.alloc(nw));
@@ -1222,7 +1240,7 @@ static int extract_host_impl(lbadcu_plan* p, const void* h_pcm_v, int sample_byt
                              uint32_t* h_words, float* h_images, float* h_haar, int mode) {
     if (!p || !h_pcm_v || !h_words || n_clips == 0) return LBAD_ERR_ARG;
     if (clip_len < p->g.window) return LBAD_ERR_ARG;
-    LBAD_CUDA_TRY(cudaSetDevice(p->device));
+    LBAD_ON_DEVICE(p->device);
     const char* h_pcm = static_cast<const char*>(h_pcm_v);
     const uint64_t frames_per_clip = ((clip_len - p->g.window) / p->g.stride) / LBAD_ROWS_PER_FRAME;
     if (frames_per_clip == 0) return LBAD_OK;
@@ -1294,7 +1312,7 @@ extern "C" int lbadcu_extract_host_i16(lbadcu_plan* p, const int16_t* h_pcm, uin
 extern "C" int lbadcu_compare_pcm_host(lbadcu_plan* p, const float* h1, uint64_t n1, const float* h2, uint64_t n2, uint32_t pairs, float* out) {
     if (!p || !h1 || !h2 || !out) return LBAD_ERR_ARG;
     if (n1 < p->g.window || n2 < p->g.window) return LBAD_ERR_ARG;
-    LBAD_CUDA_TRY(cudaSetDevice(p->device));
+    LBAD_ON_DEVICE(p->device);
     const uint64_t f1 = ((n1 - p->g.window) / p->g.stride) / LBAD_ROWS_PER_FRAME, f2 = ((n2 - p->g.window) / p->g.stride) / LBAD_ROWS_PER_FRAME;   /* m:250-255 */
     if (f1 == 0 || f2 == 0 || f1 + f2 > 0x7fffffffull) return LBAD_ERR_ARG;
     const uint64_t pad1 = (n1 + 7) & ~7ull, pad2 = (n2 + 7) & ~7ull;

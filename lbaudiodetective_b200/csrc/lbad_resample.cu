@@ -255,7 +255,7 @@ extern "C" int lbadcu_resampler_create(const lbadcu_resample_design* d, lbadcu_r
 
 extern "C" void lbadcu_resampler_destroy(lbadcu_resampler* r) {
     if (!r) return;
-    cudaSetDevice(r->device);
+    DeviceScope _device_scope(r->device);
     if (r->stream) { cudaStreamSynchronize(r->stream); cudaStreamDestroy(r->stream); }
     cudaFree(r->d_g); cudaFree(r->d_hc);
     delete r;
@@ -267,7 +267,7 @@ extern "C" int lbadcu_resample_device(lbadcu_resampler* r, const float* d_in, ui
                                       float* d_out, uint64_t out_len, uint64_t out_stride, void* stream) {
     if (!r || !d_in || !d_out || n_clips == 0) return LBAD_ERR_ARG;
     if (out_len == 0) return LBAD_OK;
-    LBAD_CUDA_TRY(cudaSetDevice(r->device));
+    LBAD_ON_DEVICE(r->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : r->stream;
     ResampleParams P = r->P;
     P.in_len = in_len; P.in_stride = in_stride; P.out_len = out_len; P.out_stride = out_stride;
@@ -293,7 +293,7 @@ extern "C" int lbadcu_resample_device(lbadcu_resampler* r, const float* d_in, ui
 extern "C" int lbadcu_resample_host(lbadcu_resampler* r, const float* h_in, uint64_t n_in, float* h_out, uint64_t n_out) {
     if (!r || !h_in || !h_out) return LBAD_ERR_ARG;
     if (n_out == 0) return LBAD_OK;
-    LBAD_CUDA_TRY(cudaSetDevice(r->device));
+    LBAD_ON_DEVICE(r->device);
     DevBuf<float> d_in, d_out;
     LBAD_CUDA_TRY(d_in.alloc(n_in)); LBAD_CUDA_TRY(d_out.alloc(n_out));
     LBAD_CUDA_TRY(cudaMemcpyAsync(d_in, h_in, n_in * sizeof(float), cudaMemcpyHostToDevice, r->stream));
@@ -306,7 +306,7 @@ extern "C" int lbadcu_resample_host(lbadcu_resampler* r, const float* h_in, uint
 
 extern "C" int lbadcu_process_recorded_host(lbadcu_plan* p, lbadcu_resampler* r, const float* h_in, uint64_t n_in, uint64_t out_len, uint32_t* h_words, size_t n_words) {
     if (!p || !r || !h_in || !h_words) return LBAD_ERR_ARG;
-    LBAD_CUDA_TRY(cudaSetDevice(r->device));
+    LBAD_ON_DEVICE(r->device);
     cudaStream_t s = (cudaStream_t)lbadcu_plan_stream(p);
     DevBuf<float> d_in, d_mid; DevBuf<uint32_t> d_words;
     LBAD_CUDA_TRY(d_in.alloc(n_in)); LBAD_CUDA_TRY(d_mid.alloc(out_len + 4)); LBAD_CUDA_TRY(d_words.alloc(n_words));

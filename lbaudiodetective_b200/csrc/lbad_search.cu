@@ -134,7 +134,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int W, int CQ, bool MASKED>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32)
 search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ meta, const uint32_t* __restrict__ offsets, const uint32_t n_clips,
-                   const uint32_t clip_base, const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t pairs, const int k,
+                   const uint32_t clip_base, const uint32_t* __restrict__ clip_ids, const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t pairs, const int k,
                    const uint32_t n_qgroups, const uint32_t clips_per_chunk, float* __restrict__ part_sc, uint32_t* __restrict__ part_id,
                    float* __restrict__ all_scores, const uint32_t groups_per_chunk, const int db_regular, const uint32_t rep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -276,7 +276,7 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
             }
             if (qvalid) {
                 if (all_scores) all_scores[(size_t)q * n_clips + c] = best;
-                if (best > worst) { top.insert(best, clip_base + c); worst = top.worst(); }
+                if (best > worst) { top.insert(best, clip_ids ? clip_ids[c] : clip_base + c); worst = top.worst(); }
             }
         }
         c0 = n0; c1 = n1; buf ^= 1;
@@ -292,7 +292,7 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
 template <int W>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32)
 search_generic_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ offsets, const uint32_t n_clips, const uint32_t clip_base,
-                      const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t cq, const uint32_t pairs, const int k,
+                      const uint32_t* __restrict__ clip_ids, const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t cq, const uint32_t pairs, const int k,
                       const uint32_t n_qgroups, const uint32_t clips_per_chunk, float* __restrict__ part_sc, uint32_t* __restrict__ part_id,
                       float* __restrict__ all_scores, const uint32_t total_warps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -339,7 +339,7 @@ search_generic_kernel(const uint32_t* __restrict__ db, const uint32_t* __restric
         }
         if (qvalid) {
             if (all_scores) all_scores[(size_t)q * n_clips + c] = best;
-            if (best > top.worst()) top.insert(best, clip_base + c);
+            if (best > top.worst()) top.insert(best, clip_ids ? clip_ids[c] : clip_base + c);
         }
     }
     if (qvalid) for (int r = 0; r < k; r++) {
@@ -398,7 +398,7 @@ constexpr uint32_t FEW_MAX_Q = 8, FEW_MAX_CQ = 6;       /* beyond 8 queries the 
 template <int W>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32)
 search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ offsets, const uint32_t n_clips, const uint32_t clip_base,
-                  const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t cq, const uint32_t pairs, const int k,
+                  const uint32_t* __restrict__ clip_ids, const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t cq, const uint32_t pairs, const int k,
                   const uint32_t clips_per_warp, float* __restrict__ part_sc, uint32_t* __restrict__ part_id, float* __restrict__ all_scores,
                   const uint32_t total_warps) {
     const int lane = threadIdx.x & 31;
@@ -479,7 +479,7 @@ search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
                 if (all_scores) all_scores[(size_t)q * n_clips + c] = best;
             }
             /* into the warp's list: first those that beat its last entry, one at a time */
-            const uint32_t cid = clip_base + c;
+            const uint32_t cid = (clip_ids && valid) ? clip_ids[c] : clip_base + c;
             const float last_sc = __shfl_sync(0xffffffffu, tsc, k - 1); const uint32_t last_id = __shfl_sync(0xffffffffu, tid, k - 1);
             uint32_t pass = __ballot_sync(0xffffffffu, valid && (last_id == EMPTY_IDX || better(best, cid, last_sc, last_id)));
             while (pass) {
@@ -503,7 +503,7 @@ search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
 constexpr uint32_t MERGE_GROUP = 64;
 __global__ void __launch_bounds__(128)
 merge_topk_kernel(const float* __restrict__ part_sc, const uint32_t* __restrict__ part_id, const uint32_t n_lists, const uint32_t n_q, const int k,
-                  float* __restrict__ out_sc, uint32_t* __restrict__ out_id, const uint32_t group_size) {
+                  float* __restrict__ out_sc, uint32_t* __restrict__ out_id, const uint32_t group_size, const size_t list_stride) {
     const int lane = threadIdx.x & 31;
     const uint32_t wq = blockIdx.x * 4 + (threadIdx.x >> 5);
     const uint32_t n_groups = (n_lists + group_size - 1) / group_size;
@@ -518,7 +518,7 @@ merge_topk_kernel(const float* __restrict__ part_sc, const uint32_t* __restrict_
         float bs = -2.0f; uint32_t bi = EMPTY_IDX; bool have = false;
         for (uint32_t t = lane; t < n_cand; t += 32) {
             const uint32_t list = list0 + t / k, slot = t % k;
-            const float s = part_sc[((size_t)list * n_q + q) * k + slot]; const uint32_t i = part_id[((size_t)list * n_q + q) * k + slot];
+            const float s = part_sc[(size_t)list * list_stride + (size_t)q * k + slot]; const uint32_t i = part_id[(size_t)list * list_stride + (size_t)q * k + slot];
             if (i == EMPTY_IDX) continue;
             if (!first && !better(last_s, last_i, s, i)) continue;             /* already emitted */
             if (!have || better(s, i, bs, bi)) { bs = s; bi = i; have = true; }
@@ -549,6 +549,12 @@ struct lbadcu_db {
     uint32_t min_count = 0xffffffffu, max_count = 0, base = 0;
     bool regular = true; uint32_t* d_irregular = nullptr;    /* device counter of subfingerprints that are not "one sign bit per rank" */
     float* d_part_sc = nullptr; uint32_t* d_part_id = nullptr; size_t part_cap = 0;
+    /* the partial-list buffers are shared by every search of this database: a search on another stream than the previous one waits
+     * for that one's merge (searches on one database are serialised on the device, whatever streams they are enqueued on) */
+    cudaEvent_t part_done = nullptr; cudaStream_t part_stream = nullptr; bool part_used = false;
+    /* global clip ids (sharded databases whose clips are not one contiguous id range): ids[c] for every local clip c, ascending */
+    std::vector<uint32_t> h_ids; uint32_t* d_ids = nullptr; size_t d_ids_cap = 0; bool use_ids = false;
+    const uint32_t* ids_ptr() const { return use_ids ? d_ids : nullptr; }
     int sm_count = 0; size_t smem_optin = 0;
     uint64_t launches = 0;
     LaunchTimer timer;
@@ -571,6 +577,7 @@ extern "C" int lbadcu_db_create(uint32_t W, uint32_t pairs_full, lbadcu_db** out
     cudaDeviceProp prop; LBAD_CUDA_TRY(cudaGetDeviceProperties(&prop, db->device));
     db->sm_count = prop.multiProcessorCount; db->smem_optin = prop.sharedMemPerBlockOptin;
     LBAD_CUDA_TRY(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+    LBAD_CUDA_TRY(cudaEventCreateWithFlags(&db->part_done, cudaEventDisableTiming));
     int e = upload_rcp(); if (e != LBAD_OK) return e;       /* per device; cheap enough to repeat per database */
     *out = guard.release();
     return LBAD_OK;
@@ -578,10 +585,11 @@ extern "C" int lbadcu_db_create(uint32_t W, uint32_t pairs_full, lbadcu_db** out
 
 extern "C" void lbadcu_db_destroy(lbadcu_db* db) {
     if (!db) return;
-    cudaSetDevice(db->device);
+    DeviceScope _device_scope(db->device);
     if (db->stream) cudaStreamSynchronize(db->stream);
     db->timer.clear();
-    cudaFree(db->d_words); cudaFree(db->d_meta); cudaFree(db->d_irregular); cudaFree(db->d_offsets); cudaFree(db->d_part_sc); cudaFree(db->d_part_id);
+    if (db->part_done) { cudaEventSynchronize(db->part_done); cudaEventDestroy(db->part_done); }
+    cudaFree(db->d_words); cudaFree(db->d_meta); cudaFree(db->d_irregular); cudaFree(db->d_offsets); cudaFree(db->d_part_sc); cudaFree(db->d_part_id); cudaFree(db->d_ids);
     if (db->stream) cudaStreamDestroy(db->stream);
     delete db;
 }
@@ -599,9 +607,24 @@ extern "C" uint32_t lbadcu_db_timing(lbadcu_db* db, int enable, int reset, doubl
     return n;
 }
 
-extern "C" int lbadcu_db_append(lbadcu_db* db, const uint32_t* words, int on_device, uint32_t n_clips, const uint32_t* counts, uint32_t uniform) {
+extern "C" int lbadcu_db_append(lbadcu_db* db, const uint32_t* words, int on_device, uint32_t n_clips, const uint32_t* counts, uint32_t uniform,
+                                void* producer_stream, int64_t first_global_id) {
     if (!db || (!words && n_clips)) return LBAD_ERR_ARG;
-    LBAD_CUDA_TRY(cudaSetDevice(db->device));
+    LBAD_ON_DEVICE(db->device);
+    /* global ids: either every clip of the database has one (ascending, so that ties keep the lower id in front) or none has */
+    const uint32_t have = lbadcu_db_clips(db);
+    if (first_global_id >= 0) {
+        if ((have && !db->use_ids) || (uint64_t)first_global_id + n_clips > 0xfffffff0ull) return LBAD_ERR_ARG;
+        if (have && (uint64_t)first_global_id <= db->h_ids.back()) return LBAD_ERR_ARG;
+    } else if (db->use_ids && n_clips) return LBAD_ERR_ARG;
+    if (on_device && producer_stream) {
+        /* the words may still be in the making on the caller's stream (an asynchronous extraction): order the copy after it */
+        cudaEvent_t ready;
+        LBAD_CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        cudaError_t e1 = cudaEventRecord(ready, (cudaStream_t)producer_stream), e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(db->stream, ready, 0) : e1;
+        cudaEventDestroy(ready);
+        LBAD_CUDA_TRY(e2);
+    }
     uint64_t add = 0;
     for (uint32_t c = 0; c < n_clips; c++) add += counts ? counts[c] : uniform;
     if (db->n_subfps + add > 0xfffffff0ull) return LBAD_ERR_ARG;
@@ -638,6 +661,10 @@ extern "C" int lbadcu_db_append(lbadcu_db* db, const uint32_t* words, int on_dev
         db->h_offsets.push_back(db->h_offsets.back() + n);
         db->min_count = std::min(db->min_count, n); db->max_count = std::max(db->max_count, n);
     }
+    if (first_global_id >= 0 && n_clips) {
+        db->use_ids = true;
+        for (uint32_t c = 0; c < n_clips; c++) db->h_ids.push_back((uint32_t)first_global_id + c);
+    }
     db->n_subfps += add; db->offsets_dirty = true;
     return LBAD_OK;
 }
@@ -645,7 +672,7 @@ extern "C" int lbadcu_db_append(lbadcu_db* db, const uint32_t* words, int on_dev
 /* copies the packed words and the per-clip counts back to the host (for persisting a database) */
 extern "C" int lbadcu_db_download(lbadcu_db* db, uint32_t* h_words, uint32_t* h_counts) {
     if (!db) return LBAD_ERR_ARG;
-    LBAD_CUDA_TRY(cudaSetDevice(db->device));
+    LBAD_ON_DEVICE(db->device);
     if (h_words && db->n_subfps) {
         LBAD_CUDA_TRY(cudaMemcpyAsync(h_words, db->d_words, db->n_subfps * 2 * db->W * sizeof(uint32_t), cudaMemcpyDeviceToHost, db->stream));
         LBAD_CUDA_TRY(cudaStreamSynchronize(db->stream));
@@ -673,11 +700,11 @@ static void launch_fast(lbadcu_db* db, bool masked, uint32_t n_chunks, size_t sm
     const size_t smem = smem_topk + (size_t)2 * STAGE_SUBFPS * (2 * W * sizeof(uint32_t) + sizeof(float2)) + 260 * sizeof(float);
     if (masked) {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        search_fast_kernel<W, CQ, true><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
+        search_fast_kernel<W, CQ, true><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, pairs, k, n_qgroups, cpc,
                                                                                 db->d_part_sc, db->d_part_id, d_all, total_warps, db->regular ? 1 : 0, rep);
     } else {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        search_fast_kernel<W, CQ, false><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, d_q, n_q, pairs, k, n_qgroups, cpc,
+        search_fast_kernel<W, CQ, false><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, pairs, k, n_qgroups, cpc,
                                                                                  db->d_part_sc, db->d_part_id, d_all, total_warps, db->regular ? 1 : 0, rep);
     }
 }
@@ -686,14 +713,14 @@ template <int W>
 static void launch_generic(lbadcu_db* db, uint32_t blocks, size_t smem, cudaStream_t s, const uint32_t* d_q, uint32_t n_q, uint32_t cq, uint32_t pairs, int k,
                            uint32_t n_qgroups, uint32_t cpc, float* d_all, uint32_t total_warps) {
     cudaFuncSetAttribute(search_generic_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    search_generic_kernel<W><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_offsets, lbadcu_db_clips(db), db->base, d_q, n_q, cq, pairs, k, n_qgroups, cpc,
+    search_generic_kernel<W><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_offsets, lbadcu_db_clips(db), db->base, db->ids_ptr(), d_q, n_q, cq, pairs, k, n_qgroups, cpc,
                                                                      db->d_part_sc, db->d_part_id, d_all, total_warps);
 }
 
 extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint32_t n_q, uint32_t cq, uint32_t pairs, uint32_t k,
                                        float* d_scores, uint32_t* d_idx, float* d_all, void* stream) {
     if (!db || !d_q || !d_scores || !d_idx || n_q == 0 || k == 0 || k > 64) return LBAD_ERR_ARG;
-    LBAD_CUDA_TRY(cudaSetDevice(db->device));
+    LBAD_ON_DEVICE(db->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : db->stream;
     const uint32_t W = db->W, n_clips = lbadcu_db_clips(db);
     if (pairs > 32 * W) pairs = 32 * W;
@@ -704,6 +731,14 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
             db->d_offsets_cap = db->h_offsets.size();
         }
         LBAD_CUDA_TRY(cudaMemcpyAsync(db->d_offsets, db->h_offsets.data(), db->h_offsets.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        if (db->use_ids) {
+            if (db->d_ids_cap < db->h_ids.size()) {
+                cudaFree(db->d_ids); db->d_ids = nullptr;
+                LBAD_CUDA_TRY(cudaMalloc(&db->d_ids, db->h_ids.size() * sizeof(uint32_t)));
+                db->d_ids_cap = db->h_ids.size();
+            }
+            LBAD_CUDA_TRY(cudaMemcpyAsync(db->d_ids, db->h_ids.data(), db->h_ids.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        }
         LBAD_CUDA_TRY(cudaStreamSynchronize(s));
         db->offsets_dirty = false;
     }
@@ -720,7 +755,9 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
     const uint32_t rep = (fast && !few && n_qgroups <= 2) ? (uint32_t)SEARCH_WARPS / n_qgroups : 1u;      /* search_fast_kernel: lists per chunk */
     const uint32_t n_lists = n_chunks * rep;
     const size_t need = ((size_t)n_lists + (n_lists + MERGE_GROUP - 1) / MERGE_GROUP) * n_q * k;      /* chunk lists + (two-level merge) group lists */
+    if (db->part_used && db->part_stream != s) LBAD_CUDA_TRY(cudaStreamWaitEvent(s, db->part_done, 0));      /* the previous search, on another stream, still owns the lists */
     if (db->part_cap < need) {
+        if (db->part_used) LBAD_CUDA_TRY(cudaEventSynchronize(db->part_done));
         LBAD_CUDA_TRY(cudaStreamSynchronize(s));
         cudaFree(db->d_part_sc); cudaFree(db->d_part_id); db->d_part_sc = nullptr; db->d_part_id = nullptr;
         LBAD_CUDA_TRY(cudaMalloc(&db->d_part_sc, need * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&db->d_part_id, need * sizeof(uint32_t)));
@@ -737,9 +774,9 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
 #define LBAD_GEN(WW) launch_generic<WW>(db, blocks, smem_gen, s, d_q, n_q, cq, pairs, (int)k, n_qgroups, cpc, d_all, total_warps)
     if (few) {
         const uint32_t fblocks = (n_chunks + SEARCH_WARPS - 1) / SEARCH_WARPS;
-        if (W == 2) search_few_kernel<2><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, d_all, n_chunks);
-        else if (W == 4) search_few_kernel<4><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, d_all, n_chunks);
-        else search_few_kernel<8><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, d_all, n_chunks);
+        if (W == 2) search_few_kernel<2><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, d_all, n_chunks);
+        else if (W == 4) search_few_kernel<4><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, d_all, n_chunks);
+        else search_few_kernel<8><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, d_all, n_chunks);
     } else if (fast) {
 #define LBAD_FAST_W(WW) switch (cq) { case 1: LBAD_FAST(WW, 1); break; case 2: LBAD_FAST(WW, 2); break; case 3: LBAD_FAST(WW, 3); break; \
                                       case 4: LBAD_FAST(WW, 4); break; case 5: LBAD_FAST(WW, 5); break; default: LBAD_FAST(WW, 6); break; }
@@ -757,21 +794,23 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
         /* many lists (few queries): merged group by group, then the groups — behind the chunk lists in the same buffer */
         const uint32_t n_groups = (n_lists + MERGE_GROUP - 1) / MERGE_GROUP;
         float* g_sc = db->d_part_sc + (size_t)n_lists * n_q * k; uint32_t* g_id = db->d_part_id + (size_t)n_lists * n_q * k;
-        merge_topk_kernel<<<(n_q * n_groups + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_lists, n_q, (int)k, g_sc, g_id, MERGE_GROUP);
-        merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(g_sc, g_id, n_groups, n_q, (int)k, d_scores, d_idx, n_groups);
+        merge_topk_kernel<<<(n_q * n_groups + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_lists, n_q, (int)k, g_sc, g_id, MERGE_GROUP, (size_t)n_q * k);
+        merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(g_sc, g_id, n_groups, n_q, (int)k, d_scores, d_idx, n_groups, (size_t)n_q * k);
         db->launches += 2;
     } else {
-        merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_lists, n_q, (int)k, d_scores, d_idx, n_lists);
+        merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_lists, n_q, (int)k, d_scores, d_idx, n_lists, (size_t)n_q * k);
         db->launches++;
     }
     LBAD_CUDA_TRY(cudaGetLastError());
+    LBAD_CUDA_TRY(cudaEventRecord(db->part_done, s));
+    db->part_stream = s; db->part_used = true;
     return LBAD_OK;
 }
 
 extern "C" int lbadcu_db_search_host(lbadcu_db* db, const uint32_t* h_q, uint32_t n_q, uint32_t cq, uint32_t pairs, uint32_t k,
                                      float* h_scores, uint32_t* h_idx, float* h_all) {
     if (!db || !h_scores || !h_idx || n_q == 0 || k == 0) return LBAD_ERR_ARG;
-    LBAD_CUDA_TRY(cudaSetDevice(db->device));
+    LBAD_ON_DEVICE(db->device);
     const uint32_t W = db->W, n_clips = lbadcu_db_clips(db);
     const size_t qn = (size_t)n_q * cq * 2 * W;
     DevBuf<uint32_t> d_q, d_id; DevBuf<float> d_sc, d_all;
@@ -796,16 +835,17 @@ extern "C" int lbadcu_merge_topk_host(const float* h_sc, const uint32_t* h_id, u
     DevBuf<float> d_sc, d_o; DevBuf<uint32_t> d_id, d_oi;
     LBAD_CUDA_TRY(d_sc.alloc(n)); LBAD_CUDA_TRY(d_id.alloc(n)); LBAD_CUDA_TRY(d_o.alloc((size_t)n_q * k)); LBAD_CUDA_TRY(d_oi.alloc((size_t)n_q * k));
     LBAD_CUDA_TRY(cudaMemcpy(d_sc, h_sc, n * 4, cudaMemcpyHostToDevice)); LBAD_CUDA_TRY(cudaMemcpy(d_id, h_id, n * 4, cudaMemcpyHostToDevice));
-    merge_topk_kernel<<<(n_q + 3) / 4, 128>>>(d_sc, d_id, n_lists, n_q, (int)k, d_o, d_oi, n_lists);
+    merge_topk_kernel<<<(n_q + 3) / 4, 128>>>(d_sc, d_id, n_lists, n_q, (int)k, d_o, d_oi, n_lists, (size_t)n_q * k);
     LBAD_CUDA_TRY(cudaGetLastError());
     LBAD_CUDA_TRY(cudaMemcpy(o_sc, d_o, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost)); LBAD_CUDA_TRY(cudaMemcpy(o_id, d_oi, (size_t)n_q * k * 4, cudaMemcpyDeviceToHost));
     return LBAD_OK;
 }
 
 /* same merge on lists that already live on the device (e.g. the output of an NCCL all-gather), enqueued on the caller's stream */
-extern "C" int lbadcu_merge_topk_device(const float* d_sc, const uint32_t* d_id, uint32_t n_lists, uint32_t n_q, uint32_t k, float* d_o_sc, uint32_t* d_o_id, void* stream) {
+extern "C" int lbadcu_merge_topk_device(const float* d_sc, const uint32_t* d_id, uint32_t n_lists, uint64_t list_stride, uint32_t n_q, uint32_t k, float* d_o_sc, uint32_t* d_o_id, void* stream) {
     if (!d_sc || !d_id || !d_o_sc || !d_o_id || n_lists == 0 || n_q == 0 || k == 0) return LBAD_ERR_ARG;
-    merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_sc, d_id, n_lists, n_q, (int)k, d_o_sc, d_o_id, n_lists);
+    if (list_stride == 0) list_stride = (uint64_t)n_q * k;
+    merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, (cudaStream_t)stream>>>(d_sc, d_id, n_lists, n_q, (int)k, d_o_sc, d_o_id, n_lists, (size_t)list_stride);
     LBAD_CUDA_TRY(cudaGetLastError());
     return LBAD_OK;
 }
@@ -871,5 +911,175 @@ extern "C" int lbadcu_compare_pair(uint32_t W, uint32_t pairs, const uint32_t* w
     LBAD_CUDA_TRY(cudaMemcpyAsync(c.h_score, c.d_score, sizeof(float), cudaMemcpyDeviceToHost, c.stream));
     LBAD_CUDA_TRY(cudaStreamSynchronize(c.stream));
     *out = *c.h_score;
+    return LBAD_OK;
+}
+
+/* ================================================================================================ group ==== */
+/* A database sharded by clip over several GPUs, driven by ONE process (include/LBAudioDetectiveDatabase.h,
+ * LBAudioDetectiveDatabaseGroup*).  Every shard is an ordinary lbadcu_db on its own device whose clips carry global ids; a search
+ * uploads the query batch to every shard, runs the per-shard top-k kernels concurrently (each on its shard's stream), brings the
+ * [query][k] lists to the first shard's device with peer copies over NVLink and merges them there with merge_topk_kernel — the result
+ * is what ONE database holding all the clips returns, bit for bit (order: score descending, global clip id ascending).  No NCCL: the
+ * exchange is 8 x 80 KB, latency-bound, and a peer copy enqueued behind each shard's kernel is the shortest path. */
+struct lbadcu_group {
+    std::vector<lbadcu_db*> shards;
+    uint32_t W = 4, pairs_full = 0;
+    uint64_t next_id = 0;
+    /* per shard: query words, [query][k] result lists, an event marking "this shard's lists are on the root device" */
+    std::vector<uint32_t*> d_q; std::vector<float*> d_sc; std::vector<uint32_t*> d_id; std::vector<cudaEvent_t> landed;
+    size_t q_cap = 0, r_cap = 0;
+    float* d_gather_sc = nullptr; uint32_t* d_gather_id = nullptr; float* d_out_sc = nullptr; uint32_t* d_out_id = nullptr;     /* on the root device */
+    uint32_t* h_q = nullptr; float* h_sc = nullptr; uint32_t* h_id = nullptr; size_t hq_cap = 0, hr_cap = 0;                    /* pinned staging */
+    uint64_t launches = 0;
+    double last_ms = 0.0; cudaEvent_t t0 = nullptr, t1 = nullptr;
+};
+
+extern "C" void lbadcu_group_destroy(lbadcu_group* g) {
+    if (!g) return;
+    for (size_t i = 0; i < g->shards.size(); i++) {
+        if (!g->shards[i]) continue;
+        DeviceScope ds(g->shards[i]->device);
+        cudaStreamSynchronize(g->shards[i]->stream);
+        if (i < g->d_q.size()) { cudaFree(g->d_q[i]); cudaFree(g->d_sc[i]); cudaFree(g->d_id[i]); if (g->landed[i]) cudaEventDestroy(g->landed[i]); }
+        if (i == 0) { cudaFree(g->d_gather_sc); cudaFree(g->d_gather_id); cudaFree(g->d_out_sc); cudaFree(g->d_out_id); if (g->t0) cudaEventDestroy(g->t0); if (g->t1) cudaEventDestroy(g->t1); }
+    }
+    cudaFreeHost(g->h_q); cudaFreeHost(g->h_sc); cudaFreeHost(g->h_id);
+    for (auto* db : g->shards) lbadcu_db_destroy(db);
+    delete g;
+}
+
+extern "C" int lbadcu_group_create(uint32_t W, uint32_t pairs_full, const int* devices, uint32_t n_shards, lbadcu_group** out) {
+    *out = nullptr;
+    if (!devices || n_shards == 0 || n_shards > 64) return LBAD_ERR_ARG;
+    if (lbadcu_device_available() != LBAD_OK) { set_error("no CUDA device available (this library has no CPU fallback)"); return LBAD_ERR_NODEVICE; }
+    int n_dev = 0; LBAD_CUDA_TRY(cudaGetDeviceCount(&n_dev));
+    for (uint32_t i = 0; i < n_shards; i++) if (devices[i] < 0 || devices[i] >= n_dev) return LBAD_ERR_ARG;
+    lbadcu_group* g = new lbadcu_group(); g->W = W; g->pairs_full = pairs_full;
+    Guard<lbadcu_group> guard(g, lbadcu_group_destroy);
+    g->shards.assign(n_shards, nullptr); g->d_q.assign(n_shards, nullptr); g->d_sc.assign(n_shards, nullptr); g->d_id.assign(n_shards, nullptr); g->landed.assign(n_shards, nullptr);
+    for (uint32_t i = 0; i < n_shards; i++) {
+        LBAD_ON_DEVICE(devices[i]);
+        int e = lbadcu_db_create(W, pairs_full, &g->shards[i]); if (e != LBAD_OK) return e;
+        LBAD_CUDA_TRY(cudaEventCreateWithFlags(&g->landed[i], cudaEventDisableTiming));
+        if (i > 0 && devices[i] != devices[0]) {              /* direct peer copies between the shard and the root where the topology allows it */
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) == cudaSuccess && can) { cudaError_t pe = cudaDeviceEnablePeerAccess(devices[0], 0); if (pe != cudaSuccess) cudaGetLastError(); }
+        }
+    }
+    { LBAD_ON_DEVICE(devices[0]); LBAD_CUDA_TRY(cudaEventCreate(&g->t0)); LBAD_CUDA_TRY(cudaEventCreate(&g->t1)); }
+    *out = guard.release();
+    return LBAD_OK;
+}
+
+extern "C" uint32_t lbadcu_group_shards(const lbadcu_group* g) { return (uint32_t)g->shards.size(); }
+extern "C" lbadcu_db* lbadcu_group_shard(lbadcu_group* g, uint32_t i) { return i < g->shards.size() ? g->shards[i] : nullptr; }
+extern "C" int lbadcu_group_shard_device(const lbadcu_group* g, uint32_t i) { return i < g->shards.size() ? g->shards[i]->device : -1; }
+extern "C" uint64_t lbadcu_group_clips(const lbadcu_group* g) { uint64_t n = 0; for (auto* db : g->shards) n += lbadcu_db_clips(db); return n; }
+extern "C" uint64_t lbadcu_group_next_id(const lbadcu_group* g) { return g->next_id; }
+extern "C" uint64_t lbadcu_group_launches(const lbadcu_group* g) { uint64_t n = g->launches; for (auto* db : g->shards) n += db->launches; return n; }
+extern "C" double lbadcu_group_last_search_ms(const lbadcu_group* g) { return g->last_ms; }
+
+/* Appends n_clips clips with the next global ids, in contiguous blocks over the shards (block i on shard i), host memory. */
+extern "C" int lbadcu_group_append(lbadcu_group* g, const uint32_t* h_words, uint32_t n_clips, const uint32_t* counts, uint32_t uniform) {
+    if (!g || (!h_words && n_clips)) return LBAD_ERR_ARG;
+    const uint32_t S = (uint32_t)g->shards.size();
+    if (g->next_id + n_clips > 0xfffffff0ull) return LBAD_ERR_ARG;
+    const uint32_t* w = h_words;
+    for (uint32_t i = 0; i < S; i++) {
+        const uint32_t lo = (uint32_t)((uint64_t)n_clips * i / S), hi = (uint32_t)((uint64_t)n_clips * (i + 1) / S);
+        if (hi == lo) continue;
+        uint64_t sub = 0;
+        for (uint32_t c = lo; c < hi; c++) sub += counts ? counts[c] : uniform;
+        int e = lbadcu_db_append(g->shards[i], w, 0, hi - lo, counts ? counts + lo : nullptr, uniform, nullptr, (int64_t)(g->next_id + lo));
+        if (e != LBAD_OK) return e;
+        w += sub * 2 * g->W;
+    }
+    g->next_id += n_clips;
+    return LBAD_OK;
+}
+
+/* One clip (host memory) with the next global id, to the shard that holds the fewest clips: appended one at a time the shards stay balanced. */
+extern "C" int lbadcu_group_append_one(lbadcu_group* g, const uint32_t* h_words, uint32_t count, uint64_t* out_id) {
+    if (!g || (!h_words && count)) return LBAD_ERR_ARG;
+    if (g->next_id + 1 > 0xfffffff0ull) return LBAD_ERR_ARG;
+    size_t best = 0;
+    for (size_t i = 1; i < g->shards.size(); i++) if (lbadcu_db_clips(g->shards[i]) < lbadcu_db_clips(g->shards[best])) best = i;
+    static const uint32_t none[16] = {0};
+    int e = lbadcu_db_append(g->shards[best], count ? h_words : none, 0, 1, &count, 0, nullptr, (int64_t)g->next_id);
+    if (e != LBAD_OK) return e;
+    if (out_id) *out_id = g->next_id;
+    g->next_id++;
+    return LBAD_OK;
+}
+
+/* Appends clips whose packed words already sit on shard `shard`'s device, with explicit global ids [first_global_id, +n_clips). */
+extern "C" int lbadcu_group_append_device(lbadcu_group* g, uint32_t shard, const uint32_t* d_words, uint32_t n_clips, uint32_t uniform, uint64_t first_global_id, void* producer_stream) {
+    if (!g || shard >= g->shards.size() || !d_words) return LBAD_ERR_ARG;
+    int e = lbadcu_db_append(g->shards[shard], d_words, 1, n_clips, nullptr, uniform, producer_stream, (int64_t)first_global_id);
+    if (e == LBAD_OK && first_global_id + n_clips > g->next_id) g->next_id = first_global_id + n_clips;
+    return e;
+}
+
+extern "C" int lbadcu_group_search_host(lbadcu_group* g, const uint32_t* h_qwords, uint32_t n_q, uint32_t cq, uint32_t pairs, uint32_t k, float* h_scores, uint32_t* h_idx) {
+    if (!g || !h_scores || !h_idx || n_q == 0 || k == 0 || k > 64 || (!h_qwords && cq)) return LBAD_ERR_ARG;
+    const uint32_t S = (uint32_t)g->shards.size();
+    const size_t qn = (size_t)n_q * cq * 2 * g->W, rn = (size_t)n_q * k;
+    lbadcu_db* root = g->shards[0];
+    /* buffers: grown on demand, kept between calls */
+    if (g->hq_cap < qn || g->hr_cap < rn) {
+        cudaFreeHost(g->h_q); cudaFreeHost(g->h_sc); cudaFreeHost(g->h_id); g->h_q = nullptr; g->h_sc = nullptr; g->h_id = nullptr; g->hq_cap = g->hr_cap = 0;
+        LBAD_CUDA_TRY(cudaHostAlloc(&g->h_q, (qn ? qn : 1) * sizeof(uint32_t), cudaHostAllocPortable));
+        LBAD_CUDA_TRY(cudaHostAlloc(&g->h_sc, rn * sizeof(float), cudaHostAllocPortable)); LBAD_CUDA_TRY(cudaHostAlloc(&g->h_id, rn * sizeof(uint32_t), cudaHostAllocPortable));
+        g->hq_cap = qn; g->hr_cap = rn;
+    }
+    if (g->q_cap < qn || g->r_cap < rn) {
+        for (uint32_t i = 0; i < S; i++) {
+            LBAD_ON_DEVICE(g->shards[i]->device);
+            LBAD_CUDA_TRY(cudaStreamSynchronize(g->shards[i]->stream));
+            cudaFree(g->d_q[i]); cudaFree(g->d_sc[i]); cudaFree(g->d_id[i]); g->d_q[i] = nullptr; g->d_sc[i] = nullptr; g->d_id[i] = nullptr;
+            LBAD_CUDA_TRY(cudaMalloc(&g->d_q[i], (qn ? qn : 1) * sizeof(uint32_t))); LBAD_CUDA_TRY(cudaMalloc(&g->d_sc[i], rn * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&g->d_id[i], rn * sizeof(uint32_t)));
+            if (i == 0) {
+                cudaFree(g->d_gather_sc); cudaFree(g->d_gather_id); cudaFree(g->d_out_sc); cudaFree(g->d_out_id); g->d_gather_sc = nullptr; g->d_gather_id = nullptr; g->d_out_sc = nullptr; g->d_out_id = nullptr;
+                LBAD_CUDA_TRY(cudaMalloc(&g->d_gather_sc, S * rn * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&g->d_gather_id, S * rn * sizeof(uint32_t)));
+                LBAD_CUDA_TRY(cudaMalloc(&g->d_out_sc, rn * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&g->d_out_id, rn * sizeof(uint32_t)));
+            }
+        }
+        g->q_cap = qn; g->r_cap = rn;
+    }
+    if (qn) memcpy(g->h_q, h_qwords, qn * sizeof(uint32_t));
+    { LBAD_ON_DEVICE(root->device); LBAD_CUDA_TRY(cudaEventRecord(g->t0, root->stream)); }
+    /* 1: the query batch to every shard; 2: every shard's search (kernels of different shards run concurrently); 3: every shard's lists to
+     * the root by a peer copy enqueued behind its kernels.  Three passes, so that no shard's launch waits for another shard's copies. */
+    for (uint32_t i = 0; i < S; i++) {
+        LBAD_ON_DEVICE(g->shards[i]->device);
+        if (qn) LBAD_CUDA_TRY(cudaMemcpyAsync(g->d_q[i], g->h_q, qn * sizeof(uint32_t), cudaMemcpyHostToDevice, g->shards[i]->stream));
+    }
+    for (uint32_t i = 0; i < S; i++) {
+        int e = lbadcu_db_search_device(g->shards[i], g->d_q[i], n_q, cq, pairs, k, i == 0 ? g->d_gather_sc : g->d_sc[i], i == 0 ? g->d_gather_id : g->d_id[i], nullptr, g->shards[i]->stream);
+        if (e != LBAD_OK) return e;
+    }
+    for (uint32_t i = 1; i < S; i++) {
+        LBAD_ON_DEVICE(g->shards[i]->device);
+        LBAD_CUDA_TRY(cudaMemcpyPeerAsync(g->d_gather_sc + (size_t)i * rn, root->device, g->d_sc[i], g->shards[i]->device, rn * sizeof(float), g->shards[i]->stream));
+        LBAD_CUDA_TRY(cudaMemcpyPeerAsync(g->d_gather_id + (size_t)i * rn, root->device, g->d_id[i], g->shards[i]->device, rn * sizeof(uint32_t), g->shards[i]->stream));
+        LBAD_CUDA_TRY(cudaEventRecord(g->landed[i], g->shards[i]->stream));
+    }
+    {
+        LBAD_ON_DEVICE(root->device);
+        for (uint32_t i = 1; i < S; i++) LBAD_CUDA_TRY(cudaStreamWaitEvent(root->stream, g->landed[i], 0));
+        const float* src_sc = g->d_gather_sc; const uint32_t* src_id = g->d_gather_id;
+        if (S > 1) {
+            merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, root->stream>>>(g->d_gather_sc, g->d_gather_id, S, n_q, (int)k, g->d_out_sc, g->d_out_id, S, rn);
+            g->launches++;
+            LBAD_CUDA_TRY(cudaGetLastError());
+            src_sc = g->d_out_sc; src_id = g->d_out_id;
+        }
+        LBAD_CUDA_TRY(cudaMemcpyAsync(g->h_sc, src_sc, rn * sizeof(float), cudaMemcpyDeviceToHost, root->stream));
+        LBAD_CUDA_TRY(cudaMemcpyAsync(g->h_id, src_id, rn * sizeof(uint32_t), cudaMemcpyDeviceToHost, root->stream));
+        LBAD_CUDA_TRY(cudaEventRecord(g->t1, root->stream));
+        LBAD_CUDA_TRY(cudaStreamSynchronize(root->stream));
+        float ms = 0; if (cudaEventElapsedTime(&ms, g->t0, g->t1) == cudaSuccess) g->last_ms = ms;
+    }
+    memcpy(h_scores, g->h_sc, rn * sizeof(float)); memcpy(h_idx, g->h_id, rn * sizeof(uint32_t));
     return LBAD_OK;
 }

@@ -11,8 +11,14 @@ OSStatus LBAudioDetectiveSupportSynthesizeDevice(Float32* d_out, UInt32 nClips, 
 OSStatus LBAudioDetectiveSupportRandomCodesDevice(UInt32* d_words, UInt64 nSubfps, UInt32 subfingerprintLength, UInt64 seed, void* stream) {
     UInt32 W = lbad_words_per_plane(subfingerprintLength);
     if (!W) return kLBAudioDetectiveArgumentInvalid;
-    return lbad_status(lbadcu_random_codes_device(d_words, nSubfps, W, (subfingerprintLength + 1) / 2, seed, stream));
+    return lbad_status(lbadcu_random_codes_device(d_words, nSubfps, W, (subfingerprintLength + 1) / 2, seed, 0, stream));
 }
+OSStatus LBAudioDetectiveSupportRandomCodesDeviceAt(UInt32* d_words, UInt64 nSubfps, UInt32 subfingerprintLength, UInt64 seed, UInt64 firstSubfp, void* stream) {
+    UInt32 W = lbad_words_per_plane(subfingerprintLength);
+    if (!W) return kLBAudioDetectiveArgumentInvalid;
+    return lbad_status(lbadcu_random_codes_device(d_words, nSubfps, W, (subfingerprintLength + 1) / 2, seed, firstSubfp, stream));
+}
+int LBAudioDetectiveSupportDeviceCount(void) { return lbadcu_device_count(); }
 OSStatus LBAudioDetectiveSupportMicrobench(Float64* outFp32Tflops, Float64* outPopcGops, Float64* outLop3Gops) {
     return lbad_status(lbadcu_microbench(outFp32Tflops, outPopcGops, outLop3Gops));
 }

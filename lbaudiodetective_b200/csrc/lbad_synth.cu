@@ -39,10 +39,10 @@ __global__ void synth_kernel(float* __restrict__ out, const uint32_t n_clips, co
 }
 
 /* every one of the first `pairs` ranks carries exactly one sign bit, as extraction produces for non-zero coefficients */
-__global__ void random_codes_kernel(uint32_t* __restrict__ words, const uint64_t n_subfps, const uint32_t W, const uint32_t pairs, const uint64_t seed) {
+__global__ void random_codes_kernel(uint32_t* __restrict__ words, const uint64_t n_subfps, const uint32_t W, const uint32_t pairs, const uint64_t seed, const uint64_t first_subfp) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_subfps * W; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t sub = i / W; const uint32_t w = (uint32_t)(i % W);
-        const uint32_t r = (uint32_t)splitmix64(seed ^ splitmix64(i));
+        const uint32_t r = (uint32_t)splitmix64(seed ^ splitmix64(first_subfp * W + i));      /* a function of the GLOBAL word index */
         const uint32_t mask = pairs >= 32u * (w + 1) ? 0xffffffffu : (pairs > 32u * w ? ((1u << (pairs - 32u * w)) - 1u) : 0u);
         words[sub * 2 * W + w] = r & mask;
         words[sub * 2 * W + W + w] = ~r & mask;
@@ -98,9 +98,9 @@ extern "C" int lbadcu_synth_device(float* d_out, uint32_t n_clips, uint64_t clip
     return LBAD_OK;
 }
 
-extern "C" int lbadcu_random_codes_device(uint32_t* d_words, uint64_t n_subfps, uint32_t W, uint32_t pairs, uint64_t seed, void* stream) {
+extern "C" int lbadcu_random_codes_device(uint32_t* d_words, uint64_t n_subfps, uint32_t W, uint32_t pairs, uint64_t seed, uint64_t first_subfp, void* stream) {
     if (!d_words || n_subfps == 0) return LBAD_ERR_ARG;
-    random_codes_kernel<<<2048, 256, 0, (cudaStream_t)stream>>>(d_words, n_subfps, W, pairs, seed);
+    random_codes_kernel<<<2048, 256, 0, (cudaStream_t)stream>>>(d_words, n_subfps, W, pairs, seed, first_subfp);
     LBAD_CUDA_TRY(cudaGetLastError());
     return LBAD_OK;
 }

@@ -251,16 +251,20 @@ class Ref(Port):
         finally:
             self.set_fft_mode("f64")
 
-    def extract_batch_stages(self, cfg, pcm2d, threads=1, images=True, haar=True):
-        """(bits, images, haar, seconds) of a whole batch through the reference's own internals (f64 FFT definition), threaded."""
+    def extract_batch_stages(self, cfg, pcm2d, threads=1, images=True, haar=True, fft_mode="f64"):
+        """(bits, images, haar, seconds) of a whole batch through the reference's own internals, threaded.  fft_mode "f64" is the parity
+        definition; "fast" / "f32" run the same reference code on a single-precision FFT (what a float32 vDSP would deliver)."""
         pcm2d = _f32(pcm2d); n_clips, clip_len = pcm2d.shape; n = subfp_count(cfg, clip_len)
         bits = np.zeros((n_clips, max(n, 1), cfg.sublen), np.uint8)
         img = np.zeros((n_clips, max(n, 1), ROWS_PER_FRAME, cfg.bands), np.float32) if images else None
         hr = np.zeros((n_clips, max(n, 1), ROWS_PER_FRAME, cfg.bands), np.float32) if haar else None
         self.ref.lbad_ref_extract_batch_stages.restype = C.c_double
-        self.set_fft_mode("f64")
-        secs = self.ref.lbad_ref_extract_batch_stages(C.byref(cfg), _p(pcm2d, C.c_float), C.c_uint32(n_clips), C.c_int64(clip_len), C.c_uint32(threads), C.c_uint32(max(n, 1)),
-                                                      _p(img, C.c_float) if images else None, _p(hr, C.c_float) if haar else None, _p(bits, C.c_uint8))
+        self.set_fft_mode(fft_mode)
+        try:
+            secs = self.ref.lbad_ref_extract_batch_stages(C.byref(cfg), _p(pcm2d, C.c_float), C.c_uint32(n_clips), C.c_int64(clip_len), C.c_uint32(threads), C.c_uint32(max(n, 1)),
+                                                          _p(img, C.c_float) if images else None, _p(hr, C.c_float) if haar else None, _p(bits, C.c_uint8))
+        finally:
+            self.set_fft_mode("f64")
         return bits[:, :n], (img[:, :n] if images else None), (hr[:, :n] if haar else None), float(secs)
 
     def search(self, db_bits, q_bits, rng, threads=1):

@@ -101,8 +101,10 @@ def detective_for(lb, cfg):
     return d
 
 
-def compare_batch(lb, ref, cfg, pcm, threads, chunk, stats, fused=True, stages=True, log=None):
-    """pcm [clips][samples] host float32: GPU batch words + stage dumps against the reference's, chunk by chunk.  Returns (gpu bits, ref bits)."""
+def compare_batch(lb, ref, cfg, pcm, threads, chunk, stats, fused=True, stages=True, log=None, cpu_f32_stats=None, cpu_f32_chunks=1):
+    """pcm [clips][samples] host float32: GPU batch words + stage dumps against the reference's, chunk by chunk.  Returns (gpu bits, ref bits).
+    cpu_f32_stats: for the first cpu_f32_chunks chunks, the SAME reference code run on a single-precision CPU FFT is held against the f64
+    definition as well — the yardstick for what float32 arithmetic (a real vDSP included) does to these figures."""
     d = detective_for(lb, cfg)
     n = pcm.shape[0]
     words_all = d.process_batch(pcm)                                      # LBAudioDetectiveProcessPCMBatch: the e2e entry point, whole batch in one call
@@ -116,6 +118,11 @@ def compare_batch(lb, ref, cfg, pcm, threads, chunk, stats, fused=True, stages=T
             words, img, haar = d.process_batch_stages(part, fused=fused)
             assert np.array_equal(words, words_all[c0:c0 + chunk]), "stage-dump call and batch call disagree"
             stats.add_images(img, wimg); stats.add_haar(haar, whaar)
+        if cpu_f32_stats is not None and c0 < cpu_f32_chunks * chunk and hasattr(ref, "extract_batch_stages"):
+            fbits, fimg, fhaar, _ = ref.extract_batch_stages(cfg, part, threads=threads, images=stages, haar=stages, fft_mode="fast")
+            if stages:
+                cpu_f32_stats.add_images(fimg, wimg); cpu_f32_stats.add_haar(fhaar, whaar)
+            cpu_f32_stats.add_bits(fbits, wbits)
         gbits = lb.unpack_words(words_all[c0:c0 + chunk], cfg.sublen)
         stats.add_bits(gbits, wbits)
         got_bits_all.append(gbits); want_bits_all.append(wbits)
@@ -155,12 +162,13 @@ def run(clips=10000, chunk=250, sweep_clips=2000, sweep_queries=500, db_clips=20
     # ---- config 1: two 10 s clips, stages + the compare-audio score ----
     cfg = o.Cfg.default()
     a, b = ref.synth_clip(0, 55120), ref.synth_clip(1, 55120)
-    st = StageStats()
-    gb, wb, _ = compare_batch(lb, ref, cfg, np.stack([a, b]), threads, 2, st)
+    st = StageStats(); f32 = StageStats()
+    gb, wb, _ = compare_batch(lb, ref, cfg, np.stack([a, b]), threads, 2, st, cpu_f32_stats=f32)
     d = lb.Detective()
     got = np.float32(d.compare_pcm(a, b, 0)); want = np.float32(ref.compare_pcm(cfg, a, b, 0))
     on_ref_bits = np.float32(lb.Fingerprint.from_booleans(wb[0]).compare(lb.Fingerprint.from_booleans(wb[1]), 200))
     rep = st.report()
+    rep["yardstick: the reference on a float32 CPU FFT against the same f64 definition"] = f32.report()
     rep["score"] = {"LBAudioDetectiveComparePCM": float(got), "reference CompareAudioURLs": float(want), "abs_diff": float(abs(got - want)),
                     "gpu_compare_on_reference_bits": float(on_ref_bits), "abs_diff_on_identical_bits": float(abs(on_ref_bits - want))}
     record["config1 (two 10 s clips, compare-audio path)"] = rep
@@ -169,10 +177,11 @@ def run(clips=10000, chunk=250, sweep_clips=2000, sweep_queries=500, db_clips=20
     # ---- config 2: the bench workload, clips x 30 s, every Boolean and every stage element ----
     log("config 2: %d x 30 s clips (device-synthesised, the clips bench.py times), reference on %d threads" % (clips, threads))
     pcm = device_synth(lb, clips, 165360)
-    st = StageStats()
+    st = StageStats(); f32 = StageStats()
     t0 = time.time()
-    gb, wb, ref_secs = compare_batch(lb, ref, cfg, pcm, threads, chunk, st, log=log)
+    gb, wb, ref_secs = compare_batch(lb, ref, cfg, pcm, threads, chunk, st, log=log, cpu_f32_stats=f32, cpu_f32_chunks=8)
     rep = st.report()
+    rep["yardstick: the reference on a float32 CPU FFT against the same f64 definition (first %d clips)" % min(clips, 8 * chunk)] = f32.report()
     rep["clips"] = clips; rep["reference_seconds"] = ref_secs; rep["wall_seconds"] = time.time() - t0
     rep["reference_audio_hours_per_s (f64 FFT + stage dumps, not the timing baseline)"] = clips * 30.0 / 3600.0 / ref_secs
     record["config2 (batch extraction of %d x 30 s clips)" % clips] = rep
@@ -207,12 +216,13 @@ def run(clips=10000, chunk=250, sweep_clips=2000, sweep_queries=500, db_clips=20
     qsrc = np.arange(sweep_queries) % sweep_clips
     queries = np.stack([ref.add_noise(base[c, 8192:8192 + 16536], 7000 + i, 0.0158) for i, c in enumerate(qsrc)])      # 3 s excerpts + 1.58 % noise (essay p.34)
     for window in (512, 1024, 2048):
-        wst = StageStats()
+        wst = StageStats(); wf32 = StageStats()
         for sublen in (100, 200, 400):
             cfg5 = o.Cfg.default(window=window, sublen=sublen)
             st = StageStats()
             want_stage = sublen == 200
-            gdb, wdb, _ = compare_batch(lb, ref, cfg5, base, threads, chunk * 4, st if not want_stage else wst, stages=want_stage)
+            gdb, wdb, _ = compare_batch(lb, ref, cfg5, base, threads, chunk * 4, st if not want_stage else wst, stages=want_stage,
+                                        cpu_f32_stats=wf32 if want_stage else None, cpu_f32_chunks=1000)
             if want_stage:
                 st.add_bits(gdb, wdb)
             gq, wq, _ = compare_batch(lb, ref, cfg5, queries, threads, chunk * 4, st, stages=False)
@@ -231,6 +241,7 @@ def run(clips=10000, chunk=250, sweep_clips=2000, sweep_queries=500, db_clips=20
             sweep["window %d, subfingerprint length %d" % (window, sublen)] = r
             log("config 5 window %d L %d: %s" % (window, sublen, json.dumps(r)))
         sweep["window %d, stages (subfingerprint length 200)" % window] = {k: v for k, v in wst.report().items() if k != "booleans"}
+        sweep["window %d, stages, yardstick: the reference on a float32 CPU FFT against the same f64 definition" % window] = wf32.report()
         log("config 5 window %d stages: %s" % (window, json.dumps(sweep["window %d, stages (subfingerprint length 200)" % window])))
     record["config5 (%d x 9 s clips, %d noisy 3 s queries; window x subfingerprint-length sweep)" % (sweep_clips, sweep_queries)] = sweep
     record["total_seconds"] = time.time() - t_all

@@ -631,3 +631,104 @@ def test_full_size_search_sharded_equals_whole(lb):
     m_sc = torch.empty((n_q, k), dtype=torch.float32, device="cuda"); m_ix = torch.empty((n_q, k), dtype=torch.int32, device="cuda")
     lb.merge_topk_device(s_sc.data_ptr(), s_ix.data_ptr(), shards, n_q, k, m_sc.data_ptr(), m_ix.data_ptr()); torch.cuda.synchronize()
     assert np.array_equal(m_ix.cpu().numpy().view(np.uint32), ix_w) and np.array_equal(m_sc.cpu().numpy(), sc_w)
+
+
+# ------------------------------------------------------- multi-GPU group, stream ordering ----
+
+@pytest.mark.parametrize("n_shards", [1, 3, 8])
+def test_database_group_equals_single_database(lb, checker, n_shards):
+    """LBAudioDetectiveDatabaseGroup: a database sharded over the GPUs of one process returns what ONE database returns, bit for bit —
+    ragged clips, several appends (so shards hold several runs of global indices), clips added one by one, few and many queries,
+    a shortened range; scores are held against the oracle as well."""
+    rng = np.random.default_rng(40 + n_shards); L = 200
+    n_dev = lb.device_count()
+    group = lb.DatabaseGroup(L, [i % n_dev for i in range(n_shards)])
+    whole = lb.Database(L)
+    all_bits = []
+    for n_clips in (700, 1, 333):
+        counts = rng.integers(6, 25, size=n_clips)
+        bits = [rank_sign_codes(rng, 1, int(c), L)[0] for c in counts]
+        words = np.concatenate([lb.pack_booleans(b) for b in bits])
+        first = group.add_packed(words, counts=counts); whole.add_packed(words, counts=counts)
+        assert first == len(all_bits)
+        all_bits += bits
+    for _ in range(5):                                                       # one by one, through fingerprint objects
+        b = rank_sign_codes(rng, 1, 9, L)[0]
+        assert group.add_fingerprint(lb.Fingerprint.from_booleans(b)) == len(all_bits)
+        whole.add_fingerprint(lb.Fingerprint.from_booleans(b)); all_bits.append(b)
+    assert group.clips == whole.clips == len(all_bits) and group.shards == n_shards
+    assert sum(group.shard_clips(i) for i in range(n_shards)) == len(all_bits)
+    for n_q, rg in ((40, 0), (3, 0), (1, 77)):
+        src = rng.integers(0, len(all_bits), n_q)
+        qb = np.stack([all_bits[c][1:7] for c in src]).copy()
+        qb[::2, 0, 0:2] ^= 1                                                 # every other query: one rank flipped
+        q = lb.pack_booleans(qb)
+        g_sc, g_id = group.search_packed(q, 10, rng=rg)
+        w_sc, w_id = whole.search_packed(q, 10, rng=rg)
+        assert np.array_equal(g_sc, w_sc) and np.array_equal(g_id, w_id)
+        for qi in range(min(n_q, 3)):                                        # and against the oracle
+            want = np.array([np.float32(checker.compare_fp(b, qb[qi], rg if rg else L)) for b in all_bits])
+            order = np.lexsort((np.arange(len(want)), -want.astype(np.float64)))[:10]
+            assert np.array_equal(g_id[qi], order.astype(np.uint32)) and np.array_equal(g_sc[qi], want[order])
+    assert group.kernel_launches > 0 and group.last_search_ms > 0
+
+
+def test_database_group_device_appends_with_global_ids(lb):
+    """Shards filled on their devices with explicit global clip indices (what bench.py does at full size): same top-k as one database."""
+    import torch
+    n_dev = lb.device_count(); shards = 4; per = 5000; c = 19
+    group = lb.DatabaseGroup(200, [i % n_dev for i in range(shards)])
+    whole = lb.Database(200)
+    for s in range(shards):
+        with torch.cuda.device(group.shard_device(s)):
+            codes = torch.empty((per, c, 8), dtype=torch.int32, device="cuda")
+            st = torch.cuda.current_stream().cuda_stream
+            lb.random_codes_device(codes.data_ptr(), per * c, 200, seed=99, stream=st, first_subfp=s * per * c)
+            group.add_packed_device_to_shard(s, codes.data_ptr(), per, c, s * per, producer_stream=st)     # no synchronisation in between: ordered by the library
+            host = codes.cpu().numpy().view(np.uint32)
+        whole.add_packed(host)
+    allc = torch.empty((shards * per, c, 8), dtype=torch.int32, device="cuda")
+    lb.random_codes_device(allc.data_ptr(), shards * per * c, 200, seed=99); torch.cuda.synchronize()
+    q = allc[::997, 3:9].contiguous().cpu().numpy().view(np.uint32)
+    g = group.search_packed(q, 10); w = whole.search_packed(q, 10)
+    assert np.array_equal(g[0], w[0]) and np.array_equal(g[1], w[1])
+    assert np.array_equal(g[1][:, 0], np.arange(0, shards * per, 997).astype(np.uint32)) and (g[0][:, 0] == 1.0).all()
+
+
+def test_calls_on_different_streams_are_ordered(lb, port):
+    """One detective (one database) used from several CUDA streams without synchronising in between: the calls share device scratch
+    (spectral images, partial top-k lists), so the library orders them; every result must equal the single-stream one."""
+    import torch
+    d = lb.Detective(); n, clip_len = 96, 165360
+    xs = [torch.empty((n, clip_len), dtype=torch.float32, device="cuda") for _ in range(3)]
+    for i, x in enumerate(xs):
+        lb.synthesize_device(x.data_ptr(), n, clip_len, clip_len, first_clip_id=3000 + 1000 * i)
+    torch.cuda.synchronize()
+    want = []
+    for x in xs:
+        o = torch.zeros((n, 19, 8), dtype=torch.int32, device="cuda")
+        d.process_batch_device(x.data_ptr(), n, clip_len, clip_len, o.data_ptr(), torch.cuda.current_stream().cuda_stream); torch.cuda.synchronize()
+        want.append(o.cpu().numpy())
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    for rep in range(3):
+        outs = [torch.zeros((n, 19, 8), dtype=torch.int32, device="cuda") for _ in range(3)]
+        torch.cuda.synchronize()
+        for x, o, s in zip(xs, outs, streams):
+            d.process_batch_device(x.data_ptr(), n, clip_len, clip_len, o.data_ptr(), s.cuda_stream)
+        torch.cuda.synchronize()
+        for o, w in zip(outs, want):
+            assert np.array_equal(o.cpu().numpy(), w)
+    # extraction on one stream, database append ordered after it, searches from three streams
+    db = lb.Database(200)
+    o = torch.zeros((n, 19, 8), dtype=torch.int32, device="cuda"); torch.cuda.synchronize()
+    d.process_batch_device(xs[0].data_ptr(), n, clip_len, clip_len, o.data_ptr(), streams[0].cuda_stream)
+    db.add_packed_device(o.data_ptr(), n, 19, producer_stream=streams[0].cuda_stream)
+    q = torch.from_numpy(want[0][::5, 2:8].copy()).cuda()
+    res = [(torch.empty((q.shape[0], 5), dtype=torch.float32, device="cuda"), torch.empty((q.shape[0], 5), dtype=torch.int32, device="cuda")) for _ in range(3)]
+    torch.cuda.synchronize()
+    for (sc, ix), s in zip(res, streams):
+        db.search_device(q.data_ptr(), q.shape[0], 6, 5, sc.data_ptr(), ix.data_ptr(), stream=s.cuda_stream)
+    torch.cuda.synchronize()
+    for sc, ix in res:
+        assert np.array_equal(ix[:, 0].cpu().numpy(), np.arange(0, n, 5).astype(np.int32)) and (sc[:, 0] == 1.0).all()
+        assert torch.equal(sc, res[0][0]) and torch.equal(ix, res[0][1])

@@ -186,3 +186,11 @@ def test_no_gpu_means_loud_failure(lb):
     assert "-7001" in str(err.value)
     with pytest.raises(lb.LBADError):
         d.resample(np.zeros(44100, np.float32))
+    # the value-returning compare functions have no status: NaN (never a score computed some other way), the process lives on
+    a = lb.Fingerprint.from_booleans(np.ones((2, 200), np.uint8)); b = lb.Fingerprint.from_booleans(np.ones((2, 200), np.uint8))
+    assert np.isnan(a.compare(b, 200))
+    assert np.isnan(a.compare_subfingerprints(np.ones(200, np.uint8), np.ones(200, np.uint8), 200))
+    st, _ = a.compare_status(b, 200)
+    assert st == lb.DEVICE_UNAVAILABLE
+    with pytest.raises(lb.LBADError):
+        lb.DatabaseGroup(200, [0, 0])

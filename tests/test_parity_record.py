@@ -1,14 +1,18 @@
 """The full-size parity record (tests/parity_record.py) at reduced sizes, so that every `pytest -m gpu` run re-measures what
 profiles/r02_parity.json records at the sizes of BASELINE.json's configs, and prints the figures (terminal summary)."""
 import json
+import os
+import sys
 
 import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
 
 def test_parity_record_reduced(lb, figure):
-    from tests import parity_record as pr
+    import parity_record as pr
     rec = pr.run(clips=300, chunk=100, sweep_clips=150, sweep_queries=40, db_clips=300, db_queries=24, log=lambda *_: None)
     for name, part in rec.items():
         if not isinstance(part, dict) or name == "tolerances":
