@@ -660,7 +660,7 @@ def test_database_group_equals_single_database(lb, checker, n_shards):
     assert sum(group.shard_clips(i) for i in range(n_shards)) == len(all_bits)
     for n_q, rg in ((40, 0), (3, 0), (1, 77)):
         src = rng.integers(0, len(all_bits), n_q)
-        qb = np.stack([all_bits[c][1:7] for c in src]).copy()
+        qb = np.stack([all_bits[c][0:6] for c in src]).copy()
         qb[::2, 0, 0:2] ^= 1                                                 # every other query: one rank flipped
         q = lb.pack_booleans(qb)
         g_sc, g_id = group.search_packed(q, 10, rng=rg)
