@@ -624,19 +624,22 @@ constexpr int STATIC_HALF0 = 9, STATIC_HALF1 = 25;     /* longest half-band of b
 constexpr int FUSED_WARPS = 8;
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;
 constexpr int SCR_LDF = 36;                  /* transpose scratch row stride (floats): LDS.128-aligned and conflict-free */
+constexpr int SCR_LD2 = 34;                  /* pair transposition (AOS): row stride in (re, im) pairs — 272 bytes: STS.64 rows and LDS.128 columns both conflict-free */
 
 struct FusedSmemLayout {
     uint32_t samples_bytes, total_bytes;
     uint32_t off_scratch, off_tw1, off_tw2, off_bar;
 };
-static FusedSmemLayout fused_layout(uint32_t span_floats) {
+/* groups: warp groups of FUSED_WARPS warps per CTA, each with its own sample buffer, barrier and scratch; carried: the carried-transform
+ * kernel reads 17 rows of the pass-1 table and 16 of the real-split table (8.25 KB instead of 16 KB) */
+static FusedSmemLayout fused_layout(uint32_t span_floats, bool aos = false, uint32_t groups = 1, bool carried = false) {
     FusedSmemLayout L;
-    L.samples_bytes = (span_floats * 4 + 15) & ~15u;
-    uint32_t o = L.samples_bytes;
-    L.off_scratch = o; o += FUSED_WARPS * 32 * SCR_LDF * 4;      /* one float component at a time: 4.5 KB per warp */
-    L.off_tw1 = o;     o += 32 * 32 * 8;
-    L.off_tw2 = o;     o += 32 * 32 * 8;
-    L.off_bar = o;     o += 16;
+    L.samples_bytes = (span_floats * 4 + 127) & ~127u;
+    uint32_t o = L.samples_bytes * groups;
+    L.off_scratch = o; o += groups * FUSED_WARPS * 32 * (aos ? SCR_LD2 * 2 : SCR_LDF) * 4;      /* one float component at a time: 4.5 KB per warp; whole pairs (AOS): 8.5 KB */
+    L.off_tw1 = o;     o += carried ? 17 * 32 * 8 : 32 * 32 * 8;
+    L.off_tw2 = o;     o += carried ? 16 * 32 * 8 : 32 * 32 * 8;
+    L.off_bar = o;     o += 16 * groups;
     L.total_bytes = o;
     return L;
 }
@@ -648,8 +651,13 @@ static FusedSmemLayout fused_layout(uint32_t span_floats) {
  * 8 for latency, when a call brings fewer frames than half the CTAs the device holds (a single clip, LBAudioDetectiveProcessPCM):
  * a frame is then spread over eight CTAs of 16 windows, two per warp — same windows, same arithmetic (a carried half transform and a
  * recomputed one are the same instructions on the same samples), one eighth of the serial chain. */
-template <int R, bool STATIC_RANGE, bool CARRY, int SUBS = 1>
-__global__ void __launch_bounds__(FUSED_THREADS, 2)
+/* AOS: the transposition between the two passes moves whole (re, im) pairs — 32 STS.64 + 16 LDS.128, ONE round trip through an 8.5 KB
+ * per-warp scratch, and the loaded registers are (re, im) pairs already, so pass 2 runs packed from its first stage — instead of one
+ * component at a time (64 STS.32 + 16 LDS.128 in two round trips through 4.5 KB).  Same values, same arithmetic per element. */
+/* GROUPS = 2: ONE CTA per SM of two independent 8-warp groups, each working on its own frame (own sample buffer, mbarrier and named
+ * barrier) and sharing only the twiddle tables: what two CTAs per SM did, in the shared memory that two CTAs with pair scratch no longer fit. */
+template <int R, bool STATIC_RANGE, bool CARRY, int SUBS = 1, bool AOS = false, int GROUPS = 1>
+__global__ void __launch_bounds__(FUSED_THREADS * GROUPS, GROUPS == 1 ? 2 : 1)
 bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, const float4* __restrict__ g_tw1, const float4* __restrict__ g_tw2,
                    const Geo g, const BandTable bt, const FusedSmemLayout L, const uint32_t span_floats,
                    const uint32_t total_frames, const int use_tma, const uint32_t frame0) {
@@ -659,16 +667,26 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
     constexpr uint32_t UNIT_ROWS = LBAD_ROWS_PER_FRAME / SUBS;      /* windows per CTA iteration */
     constexpr int S = 32 / R;                                /* windows per warp */
     constexpr int M = 32 * R;                                /* complex points per window = bins of the half spectrum */
+    static_assert(GROUPS == 1 || (CARRY && SUBS == 1), "two groups per CTA only in the throughput form of the carried kernel");
     extern __shared__ __align__(128) unsigned char smem[];
-    float*  samples = reinterpret_cast<float*>(smem);
+    const int grp = GROUPS == 1 ? 0 : (int)(threadIdx.x / FUSED_THREADS);               /* warp group of this thread */
+    const int tid = GROUPS == 1 ? (int)threadIdx.x : (int)(threadIdx.x % FUSED_THREADS), lane = tid & 31, wid = tid >> 5;   /* thread / warp index inside the group */
+    float*  samples = reinterpret_cast<float*>(smem + (size_t)grp * L.samples_bytes);
     float4* tw1 = reinterpret_cast<float4*>(smem + L.off_tw1);     /* [p/2][lane]: twiddles of register positions p, p+1 */
     float4* tw2 = reinterpret_cast<float4*>(smem + L.off_tw2);     /* R < 32: [k2/2][lane]: (cos, sin) of bins lane+32k2, lane+32(k2+1); R == 32: float2 [k2][lane] */
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    float* scr = reinterpret_cast<float*>(smem + L.off_scratch) + wid * (32 * SCR_LDF);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar) + 2 * grp;
+    float* scr = reinterpret_cast<float*>(smem + L.off_scratch) + (grp * FUSED_WARPS + wid) * (32 * (AOS ? SCR_LD2 * 2 : SCR_LDF));
     float* vbuf = scr;                                       /* band scratch (S x M = 1024 floats) aliases the transpose scratch */
+    auto group_sync = [&]() {                                /* all threads of this warp group */
+        if constexpr (GROUPS == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(FUSED_THREADS) : "memory");
+    };
 
-    for (int i = tid; i < 512; i += FUSED_THREADS) { tw1[i] = g_tw1[i]; tw2[i] = g_tw2[i]; }
+    {
+        constexpr int TW1_ENTRIES = CARRY ? 17 * 16 : 512, TW2_ENTRIES = CARRY ? 16 * 16 : 512;      /* float4 entries actually read (see fused_layout) */
+        for (int i = threadIdx.x; i < TW1_ENTRIES; i += FUSED_THREADS * GROUPS) tw1[i] = g_tw1[i];
+        for (int i = threadIdx.x; i < TW2_ENTRIES; i += FUSED_THREADS * GROUPS) tw2[i] = g_tw2[i];
+    }
     if (tid == 0 && use_tma) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
 
@@ -695,15 +713,15 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
         return pcm + (uint64_t)clip * g.clip_stride + ((uint64_t)fr * LBAD_ROWS_PER_FRAME + part * UNIT_ROWS) * hop;   /* m:262-290 */
     };
 
-    uint32_t f = blockIdx.x, parity = 0;
+    uint32_t f = blockIdx.x * GROUPS + grp, parity = 0;
     if (f < total_frames && use_tma && tid == 0) { mbar_arrive_expect_tx(bar, bytes); bulk_copy_g2s(samples, frame_src(f), bytes, bar); }
 
-    for (; f < total_frames; f += gridDim.x) {
+    for (; f < total_frames; f += gridDim.x * GROUPS) {
         if (use_tma) { mbar_wait(bar, parity); parity ^= 1; }
         else {
             const float* src = frame_src(f);
             for (uint32_t i = tid; i < span_floats; i += FUSED_THREADS) samples[i] = src[i];
-            __syncthreads();
+            group_sync();
         }
 
         /* ---- the frame's 128 windows, S at a time per warp, round-robin over the warps: FFT -> bands -> image rows ---- */
@@ -758,6 +776,19 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                     z[p + 1] = make_float2(z[p + 1].x * w.z - z[p + 1].y * w.w, z[p + 1].x * w.w + z[p + 1].y * w.z);
                 }
             }
+            if constexpr (AOS) {
+                /* 32x32 transpose of (re, im) pairs: row k1 = bitrev5(p) receives this lane's pair at column lane; lane k1 then reads its row */
+                float2* scr2 = reinterpret_cast<float2*>(scr);
+#pragma unroll
+                for (int p = 0; p < 32; p++) scr2[bitrev5(p) * SCR_LD2 + lane] = z[p];
+                __syncwarp();
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const float4 t = *reinterpret_cast<const float4*>(&scr2[lane * SCR_LD2 + 2 * q]);
+                    z[2 * q] = make_float2(t.x, t.y); z[2 * q + 1] = make_float2(t.z, t.w);
+                }
+                fft32_tail<R>(z);                                                   /* over n2, per window; position s R + q holds Z_s[lane + 32 bitrevR(q)] */
+            } else {
             /* 32x32 transpose through shared memory, one component at a time: lane k1 ends up with A_s[n2][k1] at position s R + n2 */
             float zx[32], zy[32];
 #pragma unroll
@@ -778,6 +809,7 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                 zy[4 * q] = t.x; zy[4 * q + 1] = t.y; zy[4 * q + 2] = t.z; zy[4 * q + 3] = t.w;
             }
             fft32_tail_soa<R>(zx, zy, z);                                       /* over n2, per window; position s R + q holds Z_s[lane + 32 bitrevR(q)] */
+            }
             __syncwarp();                                                       /* scratch is about to be reused as vbuf */
             const int src_lane = (32 - lane) & 31;
             if constexpr (R == 32) {
@@ -858,8 +890,8 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
             }
             __syncwarp();
         }
-        __syncthreads();                                                        /* every warp is done with the samples */
-        const uint32_t fnext = f + gridDim.x;
+        group_sync();                                                           /* every warp of the group is done with the samples */
+        const uint32_t fnext = f + gridDim.x * GROUPS;
         if (use_tma && tid == 0 && fnext < total_frames) { mbar_arrive_expect_tx(bar, bytes); bulk_copy_g2s(samples, frame_src(fnext), bytes, bar); }
     }
 }
@@ -892,7 +924,9 @@ struct lbadcu_plan {
     bool transform_generic = false;      /* env LBAD_TRANSFORM=generic: lbadcu_transform_images_host uses the any-geometry Haar/select kernel */
     uint32_t slab_frames_cap = 1u << 18;
     struct { const void* fn; uint32_t smem; int per_sm; } occ_cache[8] = {};      /* per kernel variant: opt-in shared memory set, resident CTAs per SM */
-    int force_subs = 0;                  /* env LBAD_SUBFRAMES=1|8: pin the CTA iterations per frame (tests); 0 = by frame count */
+    int force_subs = 0;                  /* env LBAD_SUBFRAMES=1|2|8: pin the CTA iterations per frame (tests); 0 = by frame count */
+    int pair_transpose = -1;             /* env LBAD_TRANSPOSE=pairs|components: the AOS / component-wise transposition of the carried kernel; -1 = default (pairs) */
+    int force_groups = 0;                /* env LBAD_GROUPS=1|2: warp groups per CTA of the pair-transposition kernel; 0 = default (2) */
     float *d_score = nullptr, *h_score = nullptr;      /* lbadcu_compare_pcm_host: the match on the device and its pinned landing place */
 };
 
@@ -1031,10 +1065,13 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     /* fused path: window 2048, 32 bands, even hop, frame span fits in shared memory */
     const uint64_t span = 127ull * geo->stride + N;
     p->fused_ok = ((N == 2048 || N == 1024 || N == 512 || N == 256) && B == 32 && (geo->stride % 2 == 0) && span * 4 < (1u << 20) &&
-                   fused_layout((uint32_t)span).total_bytes <= p->smem_optin);
+                   fused_layout((uint32_t)span).total_bytes <= p->smem_optin &&
+                   (!(N == 2048 && geo->stride == 64) || fused_layout((uint32_t)span, true, 2, true).total_bytes <= p->smem_optin));
     const char* st = getenv("LBAD_STAGE");
     p->stage_mode = st ? (strcmp(st, "tma") == 0 ? 1 : strcmp(st, "ldg") == 0 ? 0 : -1) : -1;
-    if (const char* sb = getenv("LBAD_SUBFRAMES")) p->force_subs = atoi(sb) == 8 ? 8 : atoi(sb) == 1 ? 1 : 0;
+    if (const char* sb = getenv("LBAD_SUBFRAMES")) p->force_subs = atoi(sb) == 8 ? 8 : atoi(sb) == 2 ? 2 : atoi(sb) == 1 ? 1 : 0;
+    if (const char* gp = getenv("LBAD_GROUPS")) p->force_groups = atoi(gp) == 1 ? 1 : atoi(gp) == 2 ? 2 : 0;
+    if (const char* tp = getenv("LBAD_TRANSPOSE")) p->pair_transpose = strcmp(tp, "pairs") == 0 ? 1 : strcmp(tp, "components") == 0 ? 0 : -1;
     if (const char* tf = getenv("LBAD_TRANSFORM")) p->transform_generic = strcmp(tf, "generic") == 0;
     if (const char* sf = getenv("LBAD_SLAB_FRAMES")) { const unsigned long v = strtoul(sf, nullptr, 10); if (v >= 1 && v <= (1u << 18)) p->slab_frames_cap = (uint32_t)v; }
     *out = guard.release();
@@ -1118,13 +1155,23 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
         /* fast path: FFT + bands kernel -> spectral images (global, L2-friendly 16 KB each) -> Haar/select/pack kernel */
         const bool carry = g.window == 2048 && g.stride == 64;           /* consecutive windows one pass-1 input apart: half transforms are shared */
         /* few frames (a single clip): eight CTAs per frame, so the call's latency is two windows per warp instead of sixteen */
-        const uint32_t subs = !carry ? 1u : p->force_subs ? (uint32_t)p->force_subs : (total_frames <= (uint32_t)p->sm_count ? 8u : 1u);
+        /* pair transposition (default for the carried kernel): twice the scratch per warp, which two CTAs per SM no longer fit with a whole
+         * frame of samples each — so ONE CTA per SM runs two 8-warp groups that share the twiddle tables (LBAD_GROUPS=1: half a frame per
+         * CTA iteration and two CTAs per SM instead; LBAD_TRANSPOSE=components: round 1's component-wise transposition) */
+        const bool aos = carry && p->pair_transpose != 0;
+        const uint32_t subs = !carry ? 1u : p->force_subs ? (uint32_t)p->force_subs : (total_frames <= (uint32_t)p->sm_count ? 8u : (aos && p->force_groups == 1) ? 2u : 1u);
+        const uint32_t groups = (aos && subs == 1 && p->force_groups != 1) ? 2u : 1u;
         const uint32_t span = (LBAD_ROWS_PER_FRAME / subs - 1u) * g.stride + g.window;
-        const FusedSmemLayout L = fused_layout(span);
+        const FusedSmemLayout L = fused_layout(span, aos, groups, carry);
         /* TMA bulk copies need 16-byte aligned sources and sizes */
         bool tma_ok = ((uintptr_t)d_pcm % 16 == 0) && (clip_stride % 4 == 0) && (g.stride % 4 == 0);
         if (p->stage_mode == 0) tma_ok = false;
-        auto kern = carry ? (subs == 8 ? (p->static_range ? bands_fused_kernel<32, true, true, 8> : bands_fused_kernel<32, false, true, 8>)
+        auto kern = carry ? (aos ? (subs == 8 ? (p->static_range ? bands_fused_kernel<32, true, true, 8, true> : bands_fused_kernel<32, false, true, 8, true>)
+                                  : subs == 2 ? (p->static_range ? bands_fused_kernel<32, true, true, 2, true> : bands_fused_kernel<32, false, true, 2, true>)
+                                  : groups == 2 ? (p->static_range ? bands_fused_kernel<32, true, true, 1, true, 2> : bands_fused_kernel<32, false, true, 1, true, 2>)
+                                              : (p->static_range ? bands_fused_kernel<32, true, true, 1, true> : bands_fused_kernel<32, false, true, 1, true>))
+                           : subs == 8 ? (p->static_range ? bands_fused_kernel<32, true, true, 8> : bands_fused_kernel<32, false, true, 8>)
+                           : subs == 2 ? (p->static_range ? bands_fused_kernel<32, true, true, 2> : bands_fused_kernel<32, false, true, 2>)
                                        : (p->static_range ? bands_fused_kernel<32, true, true> : bands_fused_kernel<32, false, true>))
                   : g.window == 2048 ? bands_fused_kernel<32, false, false> : g.window == 1024 ? bands_fused_kernel<16, false, false>
                   : g.window == 512 ? bands_fused_kernel<8, false, false> : bands_fused_kernel<4, false, false>;
@@ -1133,7 +1180,7 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
         if (!per_sm) {                                                    /* first launch of this variant with this footprint */
             /* the attribute is a ceiling shared by every plan of the process: raise it to the device's limit once, never lower it */
             LBAD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_optin));
-            LBAD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, L.total_bytes));
+            LBAD_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)(FUSED_THREADS * groups), L.total_bytes));
             if (per_sm < 1) per_sm = 1;
             for (auto& c : p->occ_cache) if (!c.fn) { c.fn = (const void*)kern; c.smem = L.total_bytes; c.per_sm = per_sm; break; }
         }
@@ -1153,9 +1200,10 @@ static int extract_device_slot(lbadcu_plan* p, const float* d_pcm, uint32_t n_cl
             /* a slab starts at frame f0 of the flattened (clip, frame) order: hand the kernel a view that starts there */
             Geo gs = g;
             const uint32_t units = nf * subs;
-            const uint32_t grid = units < cap ? units : cap;
+            const uint32_t ctas = (units + groups - 1) / groups;
+            const uint32_t grid = ctas < cap ? ctas : cap;
             p->timer.begin(s);
-            kern<<<grid, FUSED_THREADS, L.total_bytes, s>>>(d_pcm, imgs, p->d_tw1, p->d_tw2, gs, p->bt, L, span, units, tma_ok ? 1 : 0, f0);
+            kern<<<grid, FUSED_THREADS * groups, L.total_bytes, s>>>(d_pcm, imgs, p->d_tw1, p->d_tw2, gs, p->bt, L, span, units, tma_ok ? 1 : 0, f0);
             p->timer.end(s);
             p->launches++;
             LBAD_CUDA_TRY(cudaGetLastError());
