@@ -609,17 +609,21 @@ __device__ __forceinline__ float seg_sum(const float* __restrict__ v, uint32_t a
     return (s0 + s1) + (s2 + s3);
 }
 
-/* same sum with a compile-time bound on the length: fully unrolled, predicated, no loop-carried control flow */
-template <int L>
+/* same sum with compile-time bounds on the length, LMIN <= len <= L: fully unrolled, the first LMIN terms unconditional, the rest predicated */
+template <int LMIN, int L>
 __device__ __forceinline__ float seg_sum_static(const float* __restrict__ v, const uint32_t a, const uint32_t len) {
     float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
     for (int i = 0; i < L; i++) {
-        if ((uint32_t)i < len) { if (i & 1) s1 += v[a + i]; else s0 += v[a + i]; }
+        if (i < LMIN || (uint32_t)i < len) { if (i & 1) s1 += v[a + i]; else s0 += v[a + i]; }
     }
     return s0 + s1;
 }
 constexpr int STATIC_HALF0 = 9, STATIC_HALF1 = 25;     /* longest half-band of bands 0..15 / 16..31 in the reference-default table */
+#ifndef LBAD_BANDSUM_MIN
+#define LBAD_BANDSUM_MIN 1
+#endif
+constexpr int STATIC_MIN0 = LBAD_BANDSUM_MIN ? 3 : 0, STATIC_MIN1 = LBAD_BANDSUM_MIN ? 9 : 0;        /* ... and the shortest the cuts are allowed to make them (band widths there: >= 6 / >= 18) */
 
 constexpr int FUSED_WARPS = 8;
 constexpr int FUSED_THREADS = FUSED_WARPS * 32;
@@ -746,9 +750,12 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
         };
         if constexpr (CARRY) half_transform(samples + (size_t)(wid * ITERS) * hop - hop, carry);     /* even n1 of the first window = odd n1 of the one before */
 #ifndef LBAD_WINDOW_UNROLL
-#define LBAD_WINDOW_UNROLL 1
+#define LBAD_WINDOW_UNROLL 2
 #endif
-        constexpr int WINDOW_UNROLL = LBAD_WINDOW_UNROLL;                       /* A/B knob (build.py --variant) */
+        /* the carried kernel handles two windows per trip: the half transform carried out of the first is the one carried into the second,
+         * so the 32 register moves that would hand it over disappear (35.4 against 36.3 ms); four windows per trip outgrow the instruction
+         * cache (40.1 ms).  A/B knob: build.py --variant NAME -DLBAD_WINDOW_UNROLL=n */
+        constexpr int WINDOW_UNROLL = CARRY ? LBAD_WINDOW_UNROLL : 1;
 #pragma unroll WINDOW_UNROLL
         for (int it = 0; it < ITERS; it++) {
             const int row0 = CARRY ? wid * ITERS + it : (wid + it * FUSED_WARPS) * S;
@@ -821,7 +828,10 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                 for (int k2 = 0; k2 < 16; k2++) {
                     const bool need_lo = row_needed(k2), need_hi = row_needed(31 - k2) || (k2 > 0 && row_needed(32 - k2));   /* warp-uniform */
                     if (need_lo || need_hi) {
-                        const float2 w = reinterpret_cast<const float2*>(tw2)[k2 * 32 + lane];   /* (cos, sin) of 2 pi k / N, k = lane + 32 k2: one conflict-free LDS.64 */
+                        /* (cos, sin) of 2 pi k / N, k = lane + 32 k2: one conflict-free LDS.64.  (Deriving it from the lane's factor and a
+                         * compile-time row factor instead — two FMAs more per row, 28 shared-memory wavefronts less per window — was measured
+                         * again on the pair-transposition kernel: 35.6 against 35.4 ms.) */
+                        const float2 w = reinterpret_cast<const float2*>(tw2)[k2 * 32 + lane];
                         const float c = w.x, sn = w.y;
                         const int p = bitrev5(k2), pp = bitrev5(31 - k2), p0 = bitrev5((32 - k2) % 32);
                         /* Z[1024 - k] lives in lane 32 - lane, row 31 - k2 ... except for lane 0: own register, row 32 - k2.  Lane 0 is
@@ -876,7 +886,7 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
             for (int s = 0; s < S; s++) {
                 const float* v = vbuf + s * M;
                 float sa, sb;
-                if (STATIC_RANGE) { sa = seg_sum_static<STATIC_HALF0>(v, ra0, rb0 - ra0); sb = seg_sum_static<STATIC_HALF1>(v, ra1, rb1 - ra1); }
+                if (STATIC_RANGE) { sa = seg_sum_static<STATIC_MIN0, STATIC_HALF0>(v, ra0, rb0 - ra0); sb = seg_sum_static<STATIC_MIN1, STATIC_HALF1>(v, ra1, rb1 - ra1); }
                 else              { sa = seg_sum(v, ra0, rb0); sb = seg_sum(v, ra1, rb1); }
                 sa += __shfl_xor_sync(0xffffffffu, sa, 1);
                 sb += __shfl_xor_sync(0xffffffffu, sb, 1);
@@ -964,9 +974,9 @@ static uint32_t band_sum_wavefronts(const uint32_t* lo, const uint32_t* hi, cons
     }
     return total;
 }
-static void optimise_band_splits(const uint32_t* lo, const uint32_t* hi, uint32_t* split, const uint32_t lmax0, const uint32_t lmax1) {
+static void optimise_band_splits(const uint32_t* lo, const uint32_t* hi, uint32_t* split, const uint32_t lmax0, const uint32_t lmax1, const uint32_t lmin0, const uint32_t lmin1) {
     for (int r = 0; r < 2; r++) {
-        const uint32_t lmax = r ? lmax1 : lmax0;
+        const uint32_t lmax = r ? lmax1 : lmax0, lmin = r ? lmin1 : lmin0;       /* both parts of every band between lmin and lmax long */
         uint32_t cur[32], best[32];
         for (int b = 0; b < 32; b++) cur[b] = best[b] = split[b];
         uint32_t cw = band_sum_wavefronts(lo, hi, cur, r, lmax), bw = cw;
@@ -975,7 +985,9 @@ static void optimise_band_splits(const uint32_t* lo, const uint32_t* hi, uint32_
         for (int it = 0; it < 40000; it++) {
             rng = rng * 6364136223846793005ull + 1442695040888963407ull;
             const int b = 16 * r + (int)((rng >> 33) % 16);
-            const uint32_t smin = hi[b] > lo[b] + lmax ? hi[b] - lmax : lo[b], smax = lo[b] + lmax < hi[b] ? lo[b] + lmax : hi[b];
+            uint32_t smin = hi[b] > lo[b] + lmax ? hi[b] - lmax : lo[b], smax = lo[b] + lmax < hi[b] ? lo[b] + lmax : hi[b];
+            if (smin < lo[b] + lmin) smin = lo[b] + lmin;
+            if (smax > hi[b] - lmin) smax = hi[b] - lmin;
             rng = rng * 6364136223846793005ull + 1442695040888963407ull;
             const uint32_t s = smin + (uint32_t)((rng >> 33) % (smax - smin + 1)), old = cur[b];
             cur[b] = s;
@@ -1046,8 +1058,8 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     p->static_range = N == 2048 && (kmin >> 5) == 2 && ((kmax - 1) >> 5) == 23;
     for (uint32_t b = 0; b < LBAD_MAX_BANDS; b++) p->bt.split[b] = p->bt.klow[b] + (p->bt.khigh[b] - p->bt.klow[b] + 1) / 2;
     for (uint32_t b = 0; b < B && b < 32; b++) {
-        const uint32_t half = (geo->khigh[b] - geo->klow[b] + 1) / 2;
-        if (half > (uint32_t)(b < 16 ? STATIC_HALF0 : STATIC_HALF1)) p->static_range = false;
+        const uint32_t width = geo->khigh[b] - geo->klow[b], half = (width + 1) / 2;
+        if (half > (uint32_t)(b < 16 ? STATIC_HALF0 : STATIC_HALF1) || width < 2u * (uint32_t)(b < 16 ? STATIC_MIN0 : STATIC_MIN1)) p->static_range = false;
     }
     if (p->static_range && B == 32) {                                             /* (the run-time-range variants sum with plain loops: any cut would do, the middle stays) */
         static std::mutex cache_mutex; static std::vector<std::pair<std::vector<uint32_t>, std::vector<uint32_t>>> cache;      /* band table -> cuts */
@@ -1057,7 +1069,7 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
         for (auto& e : cache) if (e.first == key) hit = &e.second;
         if (!hit) {
             std::vector<uint32_t> sp(p->bt.split, p->bt.split + 32);
-            optimise_band_splits(p->bt.klow, p->bt.khigh, sp.data(), STATIC_HALF0, STATIC_HALF1);
+            optimise_band_splits(p->bt.klow, p->bt.khigh, sp.data(), STATIC_HALF0, STATIC_HALF1, STATIC_MIN0, STATIC_MIN1);
             cache.emplace_back(key, sp); hit = &cache.back().second;
         }
         for (int b = 0; b < 32; b++) p->bt.split[b] = (*hit)[b];

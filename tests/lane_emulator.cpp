@@ -1,9 +1,9 @@
 /*
  * lane_emulator.cpp — TEST SUPPORT (host only, g++): runs the fused kernel's per-window warp procedure
- * (lbad_extract.cu: bands_fused_kernel<R>, the per-warp window loop) lane by lane on the CPU, using the very same
- * lbad_math.cuh functions and the same index expressions, with shared memory and shuffles replaced by arrays.
+ * (lbaudiodetective_b200/csrc/lbad_extract.cu: bands_fused_kernel<R>, the per-warp window loop) lane by lane on the CPU, using the
+ * very same lbad_math.cuh functions and the same index expressions, with shared memory and shuffles replaced by arrays.
  * It lets the register/shared-memory index algebra of the kernel be checked against the oracle without a GPU
- * (tests/test_lane_emulation.py).  It is not part of libLBAudioDetectiveCUDA.so and never ships.
+ * (tests/test_lane_emulation.py).  It lives with the tests: it is not part of libLBAudioDetectiveCUDA.so and never ships.
  */
 #include "lbad_math.cuh"
 #include <cmath>
@@ -65,12 +65,19 @@ static void emulate_windows(const float* pcm, int hop, const uint32_t* klow, con
             }
         }
     }
+    if constexpr (R == 32) {                        /* the carried kernel transposes whole (re, im) pairs: row k1 = bitrev5(p), column lane; lane k1 reads its row */
+        constexpr int SCR_LD2 = 34;
+        std::vector<float2> scr2(32 * SCR_LD2);
+        for (int lane = 0; lane < 32; lane++) for (int p = 0; p < 32; p++) scr2[bitrev5(p) * SCR_LD2 + lane] = z[lane][p];
+        for (int lane = 0; lane < 32; lane++) { for (int q = 0; q < 32; q++) z[lane][q] = scr2[lane * SCR_LD2 + q]; fft32_tail<R>(z[lane]); }
+    } else {
     static float zx[32][32], zy[32][32];            /* [lane][position]: the transposed components, as the kernel's 128-bit loads deliver them */
     for (int comp = 0; comp < 2; comp++) {          /* one component at a time, as in the kernel */
         for (int lane = 0; lane < 32; lane++) for (int p = 0; p < 32; p++) scr[bitrev5(p) * SCR_LDF + lane] = comp ? z[lane][p].y : z[lane][p].x;
         for (int lane = 0; lane < 32; lane++) for (int q = 0; q < 8; q++) for (int j = 0; j < 4; j++) (comp ? zy[lane][4 * q + j] : zx[lane][4 * q + j]) = scr[lane * SCR_LDF + 4 * q + j];
     }
     for (int lane = 0; lane < 32; lane++) fft32_tail_soa<R>(zx[lane], zy[lane], z[lane]);
+    }
     const int k2lo = (int)(kmin >> 5), k2hi = (int)((kmax - 1) >> 5);
     if constexpr (R == 32) {                        /* mirrored rows share one evaluation of the real split (see the kernel) */
         auto row_needed = [&](int r) -> bool { return r >= k2lo && r <= k2hi; };

@@ -1,5 +1,5 @@
 """The fused kernel's per-window warp procedure, emulated lane by lane on the CPU with the same lbad_math.cuh code
-and index expressions (csrc/lane_emulator.cpp), against the oracle: checks the FFT/transposition/split algebra."""
+and index expressions (tests/lane_emulator.cpp), against the oracle: checks the FFT/transposition/split algebra."""
 import ctypes as C
 import os
 import subprocess
@@ -16,7 +16,7 @@ CSRC = os.path.join(ROOT, "lbaudiodetective_b200", "csrc")
 def emu(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("emu") / "liblane.so")
     subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", "-include", "cstdint",
-                    os.path.join(CSRC, "lane_emulator.cpp"), "-I", CSRC, "-o", so], check=True)
+                    os.path.join(ROOT, "tests", "lane_emulator.cpp"), "-I", CSRC, "-o", so], check=True)
     return C.CDLL(so)
 
 
