@@ -621,7 +621,7 @@ __device__ __forceinline__ float seg_sum_static(const float* __restrict__ v, con
 }
 constexpr int STATIC_HALF0 = 9, STATIC_HALF1 = 25;     /* longest half-band of bands 0..15 / 16..31 in the reference-default table */
 #ifndef LBAD_BANDSUM_MIN
-#define LBAD_BANDSUM_MIN 1
+#define LBAD_BANDSUM_MIN 0          /* measured: the unconditional head saves 20 instructions per window but narrows the choice of cuts (57 instead of 50 wavefronts) */
 #endif
 constexpr int STATIC_MIN0 = LBAD_BANDSUM_MIN ? 3 : 0, STATIC_MIN1 = LBAD_BANDSUM_MIN ? 9 : 0;        /* ... and the shortest the cuts are allowed to make them (band widths there: >= 6 / >= 18) */
 
@@ -742,11 +742,11 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
 #pragma unroll
             for (int m = 0; m < 16; m++) h[m] = *reinterpret_cast<const float2*>(w + 2 * (32 * (2 * m + 1) + lane));
             dft16(h);
+            /* one table entry per output (17 LDS.64 per window with the entry of the odd outputs).  Deriving eleven of the sixteen powers
+             * of the lane's root from four loaded ones — 24 wavefronts less, 22 packed multiplies more — was measured: 34.0 against 33.5 ms;
+             * the FMA pipe is as busy as the shared-memory pipe by now, and the twiddles lose half a digit. */
 #pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const float2 t = tw1h[q * 32 + lane];
-                h[q] = make_float2(h[q].x * t.x - h[q].y * t.y, h[q].x * t.y + h[q].y * t.x);
-            }
+            for (int q = 1; q < 16; q++) h[q] = cmul(h[q], tw1h[q * 32 + lane]);       /* q = 0 is k1 = 0: twiddle 1 */
         };
         if constexpr (CARRY) half_transform(samples + (size_t)(wid * ITERS) * hop - hop, carry);     /* even n1 of the first window = odd n1 of the one before */
 #ifndef LBAD_WINDOW_UNROLL
@@ -768,7 +768,7 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                 const float2 om = tw1h[16 * 32 + lane];
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
-                    z[2 * q + 1] = make_float2(z[2 * q + 1].x * om.x - z[2 * q + 1].y * om.y, z[2 * q + 1].x * om.y + z[2 * q + 1].y * om.x);
+                    z[2 * q + 1] = cmul(z[2 * q + 1], om);
                     carry[q] = odd[q];
                 }
             } else {
@@ -779,8 +779,8 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
 #pragma unroll
                 for (int p = 0; p < 32; p += 2) {                               /* x exp(-2 pi i n2 k1 / M) */
                     const float4 w = tw1[(p >> 1) * 32 + lane];
-                    z[p] = make_float2(z[p].x * w.x - z[p].y * w.y, z[p].x * w.y + z[p].y * w.x);
-                    z[p + 1] = make_float2(z[p + 1].x * w.z - z[p + 1].y * w.w, z[p + 1].x * w.w + z[p + 1].y * w.z);
+                    z[p] = cmul(z[p], make_float2(w.x, w.y));
+                    z[p + 1] = cmul(z[p + 1], make_float2(w.z, w.w));
                 }
             }
             if constexpr (AOS) {
@@ -824,15 +824,19 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                  * real split yields both, and the lane that did it stores both energies.  Lane 0 is its own mirror one row up
                  * (k = 32 k2 <-> 32 (32 - k2)), so its row 16 (bin 512, self-mirrored) is done separately below. */
                 auto row_needed = [&](int r) -> bool { return STATIC_RANGE ? (r >= 2 && r <= 23) : (r >= k2lo && r <= k2hi); };
+#ifndef LBAD_SPLIT_TABLE
+#define LBAD_SPLIT_TABLE 0
+#endif
+                /* the twiddle exp(i 2 pi k / N) of bin k = lane + 32 k2 is the lane's factor (row 0 of the table: ONE load per window) times
+                 * the row's compile-time factor (lbad_math.cuh real_split_pair_row): the kernel is bound by the shared-memory pipe, a table
+                 * entry per row cost 28 wavefronts per window, and with packed arithmetic the rotation costs no instruction more than the load
+                 * it replaces (LBAD_SPLIT_TABLE=1 keeps the table form for A/B) */
+                float2 wl = make_float2(1.0f, 0.0f);
+                if constexpr (!LBAD_SPLIT_TABLE) wl = reinterpret_cast<const float2*>(tw2)[lane];
 #pragma unroll
                 for (int k2 = 0; k2 < 16; k2++) {
                     const bool need_lo = row_needed(k2), need_hi = row_needed(31 - k2) || (k2 > 0 && row_needed(32 - k2));   /* warp-uniform */
                     if (need_lo || need_hi) {
-                        /* (cos, sin) of 2 pi k / N, k = lane + 32 k2: one conflict-free LDS.64.  (Deriving it from the lane's factor and a
-                         * compile-time row factor instead — two FMAs more per row, 28 shared-memory wavefronts less per window — was measured
-                         * again on the pair-transposition kernel: 35.6 against 35.4 ms.) */
-                        const float2 w = reinterpret_cast<const float2*>(tw2)[k2 * 32 + lane];
-                        const float c = w.x, sn = w.y;
                         const int p = bitrev5(k2), pp = bitrev5(31 - k2), p0 = bitrev5((32 - k2) % 32);
                         /* Z[1024 - k] lives in lane 32 - lane, row 31 - k2 ... except for lane 0: own register, row 32 - k2.  Lane 0 is
                          * read by nobody but itself, so it offers that register and the exception costs nothing after the shuffle. */
@@ -841,18 +845,14 @@ bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, co
                         pz.x = __shfl_sync(0xffffffffu, offer.x, src_lane);
                         pz.y = __shfl_sync(0xffffffffu, offer.y, src_lane);
                         const int k = k2 * 32 + lane;
-                        if (need_hi) {
-                            float2 lo, hi;
-                            real_split_pair_2x(z[p], pz, c, sn, lo, hi);
-                            if (k2 == 0 && lane == 0) { lo.x = 2.0f * (z[p].x + z[p].y); lo.y = 2.0f * (z[p].x - z[p].y); }       /* DC / packed Nyquist */
-                            if (need_lo) vbuf[k] = bin_energy_raw(lo.x, lo.y, scale_m1);                                     /* finiteness is checked on the band sum */
-                            if (k2 > 0 || lane > 0) vbuf[1024 - k] = bin_energy_raw_conj(hi.x, hi.y, scale_m1);
-                        } else {
-                            float xr, xi;
-                            real_split_2x(z[p], pz, c, sn, xr, xi);
-                            if (k2 == 0 && lane == 0) { xr = 2.0f * (z[p].x + z[p].y); xi = 2.0f * (z[p].x - z[p].y); }
-                            vbuf[k] = bin_energy_raw(xr, xi, scale_m1);
-                        }
+                        float2 lo, hi;
+                        if constexpr (LBAD_SPLIT_TABLE) {
+                            const float2 w = reinterpret_cast<const float2*>(tw2)[k2 * 32 + lane];   /* (cos, sin) of 2 pi k / N: one conflict-free LDS.64 */
+                            real_split_pair_2x(z[p], pz, w.x, w.y, lo, hi);
+                        } else real_split_pair_rows(k2, z[p], pz, wl, lo, hi);
+                        if (k2 == 0 && lane == 0) { lo.x = 2.0f * (z[p].x + z[p].y); lo.y = 2.0f * (z[p].x - z[p].y); }       /* DC / packed Nyquist */
+                        if (need_lo) vbuf[k] = bin_energy_raw(lo.x, lo.y, scale_m1);                                         /* finiteness is checked on the band sum */
+                        if (need_hi && (k2 > 0 || lane > 0)) vbuf[1024 - k] = bin_energy_raw_conj(hi.x, hi.y, scale_m1);      /* (a row without a mirror: hi is dead code) */
                     }
                 }
                 if (row_needed(16) && lane == 0) vbuf[512] = bin_energy_raw(2.0f * z[bitrev5(16)].x, -2.0f * z[bitrev5(16)].y, scale_m1);   /* w = -i, partner = itself */

@@ -61,6 +61,21 @@ LBAD_HD float2 fma2(float2 a, float2 b, float2 c) {
     return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
 #endif
 }
+LBAD_HD float2 mul2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul2_rn(a, b);
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+/* The packed instructions take their operands with modifiers — halves swapped, either half negated, one scalar broadcast to both halves
+ * (SASS: R.F32x2.LO_HI.NP, R.F32) — so -i b, i b and a broadcast cost nothing, and complex arithmetic written with them is ONE issue slot
+ * per (re, im) pair where the scalar form needs two: */
+LBAD_HD float2 mul_neg_i(float2 b) { return make_float2(b.y, -b.x); }       /* -i b */
+LBAD_HD float2 mul_pos_i(float2 b) { return make_float2(-b.y, b.x); }       /*  i b */
+LBAD_HD float2 both(float v) { return make_float2(v, v); }
+/* z x t: (z.x t.x - z.y t.y, z.x t.y + z.y t.x) as FMUL2 + FFMA2 */
+LBAD_HD float2 cmul(float2 z, float2 t) { return fma2(t, both(z.x), mul2(mul_pos_i(t), both(z.y))); }
 
 /* cos(2 pi m / 32), m = 0..8, to double precision; the remaining angles follow by symmetry */
 LBAD_HD constexpr double cos32d(int m) {
@@ -82,17 +97,17 @@ LBAD_HD void dit_bfly(const float2 A, const float2 B, float2& X, float2& Y) {
         X = add2(A, B);
         Y = fma2(B, make_float2(-1.0f, -1.0f), A);
     } else if constexpr (M == 8) {                                  /* w = -i: w B = (B.y, -B.x) */
-        X = make_float2(A.x + B.y, A.y - B.x);
-        Y = make_float2(A.x - B.y, A.y + B.x);
+        X = add2(A, mul_neg_i(B));
+        Y = add2(A, mul_pos_i(B));
     } else {
         constexpr double c = cos32d(M), s = sin32d(M);
         constexpr bool tan_form = (c < 0 ? -c : c) >= (s < 0 ? -s : s);
         constexpr float scale = (float)(tan_form ? c : s);
-        float2 u;
-        if constexpr (M == 4) u = make_float2(B.x + B.y, B.y - B.x);                  /* t = 1 */
-        else if constexpr (M == 12) u = make_float2(B.x - B.y, B.y + B.x);            /* t = -1 */
-        else if constexpr (tan_form) { constexpr float t = (float)(s / c); u = make_float2(fmaf(t, B.y, B.x), fmaf(-t, B.x, B.y)); }
-        else                         { constexpr float t = (float)(c / s); u = make_float2(fmaf(t, B.x, B.y), fmaf(t, B.y, -B.x)); }
+        float2 u;                                                                     /* w B = scale x u, every form one packed instruction */
+        if constexpr (M == 4) u = add2(B, mul_neg_i(B));                              /* t = 1:  (B.x + B.y, B.y - B.x) */
+        else if constexpr (M == 12) u = add2(B, mul_pos_i(B));                        /* t = -1: (B.x - B.y, B.y + B.x) */
+        else if constexpr (tan_form) { constexpr float t = (float)(s / c); u = fma2(mul_neg_i(B), both(t), B); }       /* (B.x + t B.y, B.y - t B.x) */
+        else                         { constexpr float t = (float)(c / s); u = fma2(B, both(t), mul_neg_i(B)); }       /* (t B.x + B.y, t B.y - B.x) */
         X = fma2(u, make_float2(scale, scale), A);
         Y = fma2(u, make_float2(-scale, -scale), A);
     }
@@ -178,8 +193,9 @@ LBAD_HD void fft32(float2 (&z)[32]) { fft32_tail<32>(z); }
 LBAD_HD void real_split_2x(float2 z, float2 p, float c, float s, float& xr, float& xi) {
     const float2 e = fma2(p, make_float2(1.0f, -1.0f), z);     /* Z + conj Z' */
     const float2 d = fma2(p, make_float2(-1.0f, 1.0f), z);     /* Z - conj Z' */
-    xr = fmaf(c, d.y, fmaf(-s, d.x, e.x));                     /* -i w d = (-s dr + c di) + i (-c dr - s di) */
-    xi = fmaf(-s, d.y, fmaf(-c, d.x, e.y));
+    /* -i w d = (-s dr + c di) + i (-c dr - s di): (xr, xi) = e + (-s, -c) dr + (c, -s) di, two packed FMAs */
+    const float2 x = fma2(make_float2(c, -s), both(d.y), fma2(make_float2(-s, -c), both(d.x), e));
+    xr = x.x; xi = x.y;
 }
 
 /* Both members of a mirrored pair of bins from one evaluation: with Z[k] = z and Z[M-k] = p (w as above),
@@ -188,11 +204,53 @@ LBAD_HD void real_split_2x(float2 z, float2 p, float c, float s, float& xr, floa
 LBAD_HD void real_split_pair_2x(float2 z, float2 p, float c, float s, float2& lo, float2& hi) {
     const float2 e = fma2(p, make_float2(1.0f, -1.0f), z);
     const float2 d = fma2(p, make_float2(-1.0f, 1.0f), z);
-    float2 g;
-    g.x = fmaf(c, d.y, -(s * d.x));
-    g.y = fmaf(s, d.y, c * d.x);
+    const float2 g = fma2(make_float2(c, s), both(d.y), mul2(make_float2(-s, c), both(d.x)));     /* (c di - s dr, s di + c dr) */
     lo = fma2(g, make_float2(1.0f, -1.0f), e);
     hi = fma2(g, make_float2(-1.0f, 1.0f), e);
+}
+
+/* cos(pi m / 32), m = 0..16, to double precision (the angle of the real-split twiddle advances by pi/32 per row of 32 bins) */
+LBAD_HD constexpr double cos64d(int m) {
+    return m == 0 ? 1.0 : m == 1 ? 0.99518472667219688624 : m == 2 ? 0.98078528040323044913 : m == 3 ? 0.95694033573220886494
+         : m == 4 ? 0.92387953251128675613 : m == 5 ? 0.88192126434835502971 : m == 6 ? 0.83146961230254523708 : m == 7 ? 0.77301045336273696081
+         : m == 8 ? 0.70710678118654752440 : m == 9 ? 0.63439328416364549822 : m == 10 ? 0.55557023301960222474 : m == 11 ? 0.47139673682599764856
+         : m == 12 ? 0.38268343236508977173 : m == 13 ? 0.29028467725446236764 : m == 14 ? 0.19509032201612826785 : m == 15 ? 0.09801714032956060199 : 0.0;
+}
+LBAD_HD constexpr double sin64d(int m) { return cos64d(16 - m); }
+
+/* The real split of row K2 (bins k = lane + 32 K2) without a twiddle table: exp(i 2 pi k / N) = exp(i 2 pi lane / N) x exp(i pi K2 / 32), a
+ * per-lane factor wl = (cos, sin) times a compile-time one.  With D = d.y + i d.x (d = Z[k] - conj Z[M-k]) the rotated difference of
+ * real_split_pair_2x is G = exp(i theta) D.  The row's rotation goes first, in the Linzer-Feig form — ONE packed FMA, its scale rides on
+ * the packed FMAs that form e +- G — then the lane's (two packed instructions, as with a table): the same instruction count as the table
+ * form, one table load (two shared-memory wavefronts) less per row. */
+template <int K2>
+LBAD_HD void real_split_pair_row(float2 z, float2 p, float2 wl, float2& lo, float2& hi) {
+    static_assert(K2 >= 0 && K2 <= 16, "rows of the lower half spectrum");
+    const float2 e = fma2(p, make_float2(1.0f, -1.0f), z);
+    const float2 d = fma2(p, make_float2(-1.0f, 1.0f), z);
+    constexpr double c = cos64d(K2), s = sin64d(K2);
+    constexpr float scale = (float)(c >= s ? c : s);
+    const float2 D = make_float2(d.y, d.x), iD = make_float2(-d.x, d.y);             /* D and i D: operand modifiers, no instructions */
+    float2 U;                                                                        /* exp(i theta_row) D = scale x U */
+    if constexpr (K2 == 0) U = D;
+    else if constexpr (c >= s) { constexpr float t = (float)(s / c); U = fma2(iD, both(t), D); }      /* (1 + i t) D */
+    else { constexpr float t = (float)(c / s); U = fma2(D, both(t), iD); }                             /* (t + i) D */
+    const float2 g = cmul(U, wl);
+    lo = fma2(g, make_float2(scale, -scale), e);
+    hi = fma2(g, make_float2(-scale, scale), e);
+}
+/* the same with the row given as a value: inside a fully unrolled loop the switch folds to the one case */
+LBAD_HD void real_split_pair_rows(const int k2, float2 z, float2 p, float2 wl, float2& lo, float2& hi) {
+    switch (k2) {
+        case 0: real_split_pair_row<0>(z, p, wl, lo, hi); break;   case 1: real_split_pair_row<1>(z, p, wl, lo, hi); break;
+        case 2: real_split_pair_row<2>(z, p, wl, lo, hi); break;   case 3: real_split_pair_row<3>(z, p, wl, lo, hi); break;
+        case 4: real_split_pair_row<4>(z, p, wl, lo, hi); break;   case 5: real_split_pair_row<5>(z, p, wl, lo, hi); break;
+        case 6: real_split_pair_row<6>(z, p, wl, lo, hi); break;   case 7: real_split_pair_row<7>(z, p, wl, lo, hi); break;
+        case 8: real_split_pair_row<8>(z, p, wl, lo, hi); break;   case 9: real_split_pair_row<9>(z, p, wl, lo, hi); break;
+        case 10: real_split_pair_row<10>(z, p, wl, lo, hi); break; case 11: real_split_pair_row<11>(z, p, wl, lo, hi); break;
+        case 12: real_split_pair_row<12>(z, p, wl, lo, hi); break; case 13: real_split_pair_row<13>(z, p, wl, lo, hi); break;
+        case 14: real_split_pair_row<14>(z, p, wl, lo, hi); break; default: real_split_pair_row<15>(z, p, wl, lo, hi); break;
+    }
 }
 
 /* LBAudioDetective.m:387-401 for one bin: positive parts only are divided by pos_scale, then re^2 + im^2; a

@@ -47,9 +47,8 @@ static void emulate_windows(const float* pcm, int hop, const uint32_t* klow, con
             for (int m = 0; m < 16; m++) { ev[m] = make_float2(win[2 * (32 * (2 * m) + lane)], win[2 * (32 * (2 * m) + lane) + 1]); od[m] = make_float2(win[2 * (32 * (2 * m + 1) + lane)], win[2 * (32 * (2 * m + 1) + lane) + 1]); }
             dft16(ev); dft16(od);
             for (int q = 0; q < 16; q++) {
-                const double a = 2.0 * M_PI * (double)(lane * bitrevR<16>(q)) / (double)M; const float tx = (float)cos(a), ty = (float)-sin(a);
-                ev[q] = make_float2(ev[q].x * tx - ev[q].y * ty, ev[q].x * ty + ev[q].y * tx);
-                od[q] = make_float2(od[q].x * tx - od[q].y * ty, od[q].x * ty + od[q].y * tx);
+                const double a = 2.0 * M_PI * (double)(lane * bitrevR<16>(q)) / (double)M; const float2 t = make_float2((float)cos(a), (float)-sin(a));
+                ev[q] = cmul(ev[q], t); od[q] = cmul(od[q], t);
             }
             dit32_combine(ev, od, z[lane]);
             const double ao = 2.0 * M_PI * (double)(16 * lane) / (double)M; const float omx = (float)cos(ao), omy = (float)-sin(ao);
@@ -84,27 +83,19 @@ static void emulate_windows(const float* pcm, int hop, const uint32_t* klow, con
         auto spec_out = [&](int k, float xr, float xi) { if (out_spec) { out_spec[2 * k] = xr; out_spec[2 * k + 1] = xi; } };
         for (int lane = 0; lane < 32; lane++) {
             const int src_lane = (32 - lane) & 31;
+            const float2 wl = make_float2((&tw2[0][0])[2 * lane], (&tw2[0][0])[2 * lane + 1]);      /* the lane's factor: row 0 of the table */
             for (int k2 = 0; k2 < 16; k2++) {
                 const bool need_lo = row_needed(k2), need_hi = row_needed(31 - k2) || (k2 > 0 && row_needed(32 - k2));
                 if (need_lo || need_hi) {
-                    const float* w = &tw2[0][0] + 2 * (k2 * 32 + lane);       /* R == 32: float2 [k2][lane] */
-                    const float c = w[0], sn = w[1];
                     const int p = bitrev5(k2), pp = bitrev5(31 - k2), p0 = bitrev5((32 - k2) % 32);
                     float2 pz = z[src_lane][pp];                             /* __shfl_sync */
                     if (lane == 0) pz = z[lane][p0];
                     const int k = k2 * 32 + lane;
-                    if (need_hi) {
-                        float2 lo, hi;
-                        real_split_pair_2x(z[lane][p], pz, c, sn, lo, hi);
-                        if (k2 == 0 && lane == 0) { lo.x = 2.0f * (z[lane][p].x + z[lane][p].y); lo.y = 2.0f * (z[lane][p].x - z[lane][p].y); }
-                        if (need_lo) { vbuf[k] = bin_energy_raw(lo.x, lo.y, scale_m1); spec_out(k, lo.x, lo.y); }
-                        if (k2 > 0 || lane > 0) { vbuf[1024 - k] = bin_energy_raw_conj(hi.x, hi.y, scale_m1); spec_out(1024 - k, hi.x, -hi.y); }
-                    } else {
-                        float xr, xi;
-                        real_split_2x(z[lane][p], pz, c, sn, xr, xi);
-                        if (k2 == 0 && lane == 0) { xr = 2.0f * (z[lane][p].x + z[lane][p].y); xi = 2.0f * (z[lane][p].x - z[lane][p].y); }
-                        vbuf[k] = bin_energy_raw(xr, xi, scale_m1); spec_out(k, xr, xi);
-                    }
+                    float2 lo, hi;
+                    real_split_pair_rows(k2, z[lane][p], pz, wl, lo, hi);
+                    if (k2 == 0 && lane == 0) { lo.x = 2.0f * (z[lane][p].x + z[lane][p].y); lo.y = 2.0f * (z[lane][p].x - z[lane][p].y); }
+                    if (need_lo) { vbuf[k] = bin_energy_raw(lo.x, lo.y, scale_m1); spec_out(k, lo.x, lo.y); }
+                    if (need_hi && (k2 > 0 || lane > 0)) { vbuf[1024 - k] = bin_energy_raw_conj(hi.x, hi.y, scale_m1); spec_out(1024 - k, hi.x, -hi.y); }
                 }
             }
             if (row_needed(16) && lane == 0) {
