@@ -22,6 +22,7 @@
 #include <vector>
 #include <algorithm>
 #include <string.h>
+#include <stdlib.h>
 
 namespace lbad {
 
@@ -495,12 +496,14 @@ search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
     }
 }
 
-/* One warp per (group of lists, query): k-way merge of the partial top-k lists [list][q][k] of the group by repeated selection into
- * out[group][q][k].  group_size >= n_lists is the plain merge (one group); a search with few queries cuts the database into thousands
- * of chunks to fill the device, and merges their lists in two levels (groups of MERGE_GROUP, then the groups) instead of letting one
- * warp walk all of them.  The order (score desc, clip asc) is strict and every clip sits in exactly one list, so the top k of the
- * groups' top k are the top k of everything. */
-constexpr uint32_t MERGE_GROUP = 64;
+/* One warp per (group of lists, query): k-way merge of the partial top-k lists [list][q][k] of the group into out[group][q][k].  Every
+ * list is sorted best first (unused slots last), so the merge is a tournament of list heads: lane l owns lists l, l + 32, .. (at most
+ * MERGE_LPL of them) and keeps their heads in registers; a round finds the best head of the warp by shuffles and only the lane that
+ * owned it fetches a successor — k rounds of a few dozen instructions, whatever the number of lists (the earlier form rescanned every
+ * candidate in every round).  group_size >= n_lists is the plain merge (one group); more than 32 x MERGE_LPL lists (a search with few
+ * queries cuts the database into thousands of chunks to fill the device) are merged in two levels.  The order (score desc, clip asc) is
+ * strict and every clip sits in exactly one list, so the top k of the groups' top k are the top k of everything. */
+constexpr uint32_t MERGE_LPL = 8, MERGE_GROUP = 32 * MERGE_LPL;
 __global__ void __launch_bounds__(128)
 merge_topk_kernel(const float* __restrict__ part_sc, const uint32_t* __restrict__ part_id, const uint32_t n_lists, const uint32_t n_q, const int k,
                   float* __restrict__ out_sc, uint32_t* __restrict__ out_id, const uint32_t group_size, const size_t list_stride) {
@@ -509,28 +512,37 @@ merge_topk_kernel(const float* __restrict__ part_sc, const uint32_t* __restrict_
     const uint32_t n_groups = (n_lists + group_size - 1) / group_size;
     if (wq >= n_q * n_groups) return;
     const uint32_t grp = wq / n_q, q = wq % n_q;
-    const uint32_t list0 = grp * group_size, lists = (n_lists - list0 < group_size) ? n_lists - list0 : group_size;
-    const uint32_t n_cand = lists * (uint32_t)k;
+    const uint32_t list0 = grp * group_size, lists = (n_lists - list0 < group_size) ? n_lists - list0 : group_size;      /* <= MERGE_GROUP */
     float* o_sc = out_sc + ((size_t)grp * n_q + q) * k; uint32_t* o_id = out_id + ((size_t)grp * n_q + q) * k;
-    float last_s = INFINITY; uint32_t last_i = 0;                              /* everything is "after" (+inf, 0) */
-    bool first = true;
+    float hs[MERGE_LPL]; uint32_t hi[MERGE_LPL], pos[MERGE_LPL];                /* head of each of my lists: score, clip (EMPTY_IDX: exhausted), slot */
+    auto head = [&](uint32_t j, uint32_t slot, float& sc, uint32_t& id) {
+        const size_t at = (size_t)(list0 + lane + 32u * j) * list_stride + (size_t)q * k + slot;
+        sc = part_sc[at]; id = part_id[at];
+    };
+#pragma unroll
+    for (uint32_t j = 0; j < MERGE_LPL; j++) {
+        hs[j] = -2.0f; hi[j] = EMPTY_IDX; pos[j] = 0;
+        if (lane + 32u * j < lists) head(j, 0, hs[j], hi[j]);
+    }
     for (int r = 0; r < k; r++) {
-        float bs = -2.0f; uint32_t bi = EMPTY_IDX; bool have = false;
-        for (uint32_t t = lane; t < n_cand; t += 32) {
-            const uint32_t list = list0 + t / k, slot = t % k;
-            const float s = part_sc[(size_t)list * list_stride + (size_t)q * k + slot]; const uint32_t i = part_id[(size_t)list * list_stride + (size_t)q * k + slot];
-            if (i == EMPTY_IDX) continue;
-            if (!first && !better(last_s, last_i, s, i)) continue;             /* already emitted */
-            if (!have || better(s, i, bs, bi)) { bs = s; bi = i; have = true; }
-        }
+        float bs = -2.0f; uint32_t bi = EMPTY_IDX;                            /* my best head */
+#pragma unroll
+        for (uint32_t j = 0; j < MERGE_LPL; j++) if (hi[j] != EMPTY_IDX && (bi == EMPTY_IDX || better(hs[j], hi[j], bs, bi))) { bs = hs[j]; bi = hi[j]; }
+        float ws = bs; uint32_t wi = bi;                                     /* the warp's */
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) {
-            const float os = __shfl_xor_sync(0xffffffffu, bs, d); const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, d);
-            const bool oh = __shfl_xor_sync(0xffffffffu, have ? 1 : 0, d) != 0;
-            if (oh && (!have || better(os, oi, bs, bi))) { bs = os; bi = oi; have = true; }
+            const float os = __shfl_xor_sync(0xffffffffu, ws, d); const uint32_t oi = __shfl_xor_sync(0xffffffffu, wi, d);
+            if (oi != EMPTY_IDX && (wi == EMPTY_IDX || better(os, oi, ws, wi))) { ws = os; wi = oi; }
         }
-        if (lane == 0) { o_sc[r] = have ? bs : -1.0f; o_id[r] = have ? bi : EMPTY_IDX; }
-        if (have) { last_s = bs; last_i = bi; first = false; } else { last_s = -INFINITY; last_i = EMPTY_IDX; first = false; }
+        if (lane == 0) { o_sc[r] = wi != EMPTY_IDX ? ws : -1.0f; o_id[r] = wi; }
+        if (wi == EMPTY_IDX) { for (int rr = r + 1; rr < k; rr++) if (lane == 0) { o_sc[rr] = -1.0f; o_id[rr] = EMPTY_IDX; } break; }      /* every list exhausted (warp-uniform) */
+        if (bi == wi) {                                                      /* mine won (clip ids are unique): its list moves on */
+#pragma unroll
+            for (uint32_t j = 0; j < MERGE_LPL; j++) if (hi[j] == wi) {
+                pos[j]++;
+                if (pos[j] < (uint32_t)k) head(j, pos[j], hs[j], hi[j]); else hi[j] = EMPTY_IDX;
+            }
+        }
     }
 }
 
@@ -745,7 +757,10 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
     const uint32_t n_qgroups = (n_q + 31) / 32;
     const bool fast = n_clips > 0 && db->min_count >= cq && db->max_count <= (uint32_t)STAGE_SUBFPS && cq >= 1 && cq <= 6;
     const bool few = fast && n_q <= FEW_MAX_Q && k <= 32;                 /* lane = clip: every lane works even for ONE query */
-    uint32_t n_chunks = ((uint32_t)db->sm_count * 32 + n_qgroups - 1) / n_qgroups;       /* ~32 warps per SM */
+    static const uint32_t warps_per_sm = [] { const char* e = getenv("LBAD_SEARCH_WARPS_PER_SM"); const int v = e ? atoi(e) : 0; return (uint32_t)(v >= 4 && v <= 512 ? v : 128); }();
+    uint32_t n_chunks = ((uint32_t)db->sm_count * warps_per_sm + n_qgroups - 1) / n_qgroups;       /* chunks for ~128 warps per SM, several times what is resident (20 warps of the 95-register CQ = 6 kernel): the block scheduler hands
+                                                                                           * the next chunk to whichever SM frees a slot, which evens out the SMs (measured on a 125,000-clip shard:
+                                                                                           * 9.33 ms with 32, 8.93 with 128, 9.03 with 384 where the chunk lists start to cost; LBAD_SEARCH_WARPS_PER_SM) */
     if (few) n_chunks = std::min<uint32_t>((n_clips + 31) / 32, (uint32_t)db->sm_count * 32);      /* one list per warp, 32 clips per step */
     if (n_chunks > n_clips) n_chunks = n_clips;
     if (n_chunks < 1) n_chunks = 1;
@@ -790,7 +805,7 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
     db->timer.end(s);
     db->launches++;
     LBAD_CUDA_TRY(cudaGetLastError());
-    if (n_lists > 2 * MERGE_GROUP) {
+    if (n_lists > MERGE_GROUP) {
         /* many lists (few queries): merged group by group, then the groups — behind the chunk lists in the same buffer */
         const uint32_t n_groups = (n_lists + MERGE_GROUP - 1) / MERGE_GROUP;
         float* g_sc = db->d_part_sc + (size_t)n_lists * n_q * k; uint32_t* g_id = db->d_part_id + (size_t)n_lists * n_q * k;
