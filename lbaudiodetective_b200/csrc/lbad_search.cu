@@ -137,7 +137,10 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
 search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ meta, const uint32_t* __restrict__ offsets, const uint32_t n_clips,
                    const uint32_t clip_base, const uint32_t* __restrict__ clip_ids, const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t pairs, const int k,
                    const uint32_t n_qgroups, const uint32_t clips_per_chunk, float* __restrict__ part_sc, uint32_t* __restrict__ part_id,
-                   float* __restrict__ all_scores, const uint32_t groups_per_chunk, const int db_regular, const uint32_t rep) {
+                   float* __restrict__ all_scores, const uint32_t groups_per_chunk, const int db_regular, const uint32_t rep,
+                   const uint32_t all_stride, const float* __restrict__ floor_sc, const uint32_t uniform) {
+    /* uniform: every clip has that many subfingerprints (0: ragged) — clip c then starts at subfingerprint c * uniform and neither the
+     * tile bounds nor the clips need the offsets array */
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     /* rep > 1 (one or two query groups, i.e. at most 64 queries): the warps a CTA would leave idle take a share of the tile's clips —
@@ -162,7 +165,13 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
         }
     const uint32_t c_begin = chunk * clips_per_chunk;
     const uint32_t c_end = min(n_clips, c_begin + clips_per_chunk);
-    float worst = top.worst();
+    /* floor_sc (optional): per query the k-th best score of a SAMPLE of the database (the threshold pass of lbadcu_db_search_device):
+     * at least k clips score that much, so a clip scoring strictly less is in nobody's top k and never enters a list.  Folded into the
+     * running `worst` as the largest float below the floor, the test stays the one compare per clip it was — and the per-lane list
+     * insertion (which the whole warp walks through whenever ANY lane inserts) becomes rare instead of happening for nearly every clip. */
+    float floor_below = -1.0f;
+    if (floor_sc && qvalid) { const float f = floor_sc[(size_t)q * k + (k - 1)]; if (f > 0.0f) floor_below = __int_as_float(__float_as_int(f) - 1); }
+    float worst = fmaxf(top.worst(), floor_below);
     /* "Regular" codes: every one of the first `pairs` ranks carries exactly one sign bit, which is what extraction produces whenever
      * the selected coefficients are non-zero.  Then M = ~P on those ranks, possible = pairs, and a pair hits iff the P bits agree:
      * one LOP3 per word instead of two, no M plane, no per-subfingerprint (possible, 1/possible).  The database side is checked
@@ -184,14 +193,17 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
     /* (visible to every warp after the first __syncthreads of the tile loop) */
 
     /* tile = clips [c0, c1) whose subfingerprints [s_lo, s_hi) fit the staging buffer; every thread computes the same bounds */
+    const uint32_t uniform_per_tile = uniform ? (uint32_t)STAGE_SUBFPS / uniform : 0u;
+    auto first_subfp = [&](uint32_t c) -> uint32_t { return uniform ? c * uniform : offsets[c]; };
     auto tile_end = [&](uint32_t c0) -> uint32_t {
+        if (uniform) return min(c_end, c0 + uniform_per_tile);
         const uint32_t s_lo = offsets[c0];
         uint32_t c1 = c0;
         while (c1 < c_end && offsets[c1 + 1] - s_lo <= (uint32_t)STAGE_SUBFPS) c1++;
         return c1;
     };
     auto issue_tile = [&](uint32_t c0, uint32_t c1, int buf) {
-        const uint32_t s_lo = offsets[c0], n_sub = offsets[c1] - s_lo;
+        const uint32_t s_lo = first_subfp(c0), n_sub = first_subfp(c1) - s_lo;
         const uint4* src = reinterpret_cast<const uint4*>(db + (size_t)s_lo * 2 * W);
         uint4* dst = reinterpret_cast<uint4*>(st_words + (size_t)buf * STAGE_SUBFPS * 2 * W);
         for (uint32_t i = tid; i < n_sub * (2 * W / 4); i += SEARCH_WARPS * 32) cp_async16(dst + i, src + i);
@@ -207,17 +219,21 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
         __syncthreads();                                                       /* tile `buf` has landed; everyone is done with the other buffer */
         const uint32_t n0 = c1, n1 = n0 < c_end ? tile_end(n0) : n0;
         if (n0 < c_end) issue_tile(n0, n1, buf ^ 1);                           /* prefetch the next tile while this one is compared */
-        const uint32_t s_lo = offsets[c0];
+        const uint32_t s_lo = first_subfp(c0);
         const uint32_t* tw = st_words + (size_t)buf * STAGE_SUBFPS * 2 * W;
         const float2* tm = st_meta + (size_t)buf * STAGE_SUBFPS;
         if (qg < n_qgroups) for (uint32_t c = c0 + sub; c < c1; c += rep) {
-            const uint32_t s0 = offsets[c] - s_lo, cnt = offsets[c + 1] - offsets[c];      /* warp-uniform */
+            uint32_t s0, cnt;                                                 /* warp-uniform */
+            if (uniform) { s0 = (c - c0) * uniform; cnt = uniform; }
+            else { const uint32_t a = offsets[c]; s0 = a - s_lo; cnt = offsets[c + 1] - a; }
             float best = 0.0f;                                                /* FP.m:133 */
-            if (regular) for (uint32_t o = 0; o + CQ <= cnt; o++) {            /* FP.m:136, short form */
+            if (regular) {
+                const uint32_t* src0 = tw + (size_t)s0 * 2 * W;               /* the clip's subfingerprint o; one pointer step per offset */
+                for (uint32_t n_off = cnt - CQ + 1; n_off; n_off--, src0 += 2 * W) {      /* FP.m:136, short form (cnt >= CQ on this path) */
                 float sum = 0.0f;
 #pragma unroll
                 for (int i = 0; i < CQ; i++) {
-                    const uint32_t* src = tw + (size_t)(s0 + o + i) * 2 * W;
+                    const uint32_t* src = src0 + i * 2 * W;
                     uint32_t h[W];
                     if (W % 4 == 0) {
 #pragma unroll
@@ -233,10 +249,12 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
                             h[w] = lop3<0x82>(a.x, qp[i][w], mask.w[w]); h[w + 1] = lop3<0x82>(a.y, qp[i][w + 1], mask.w[w + 1]);
                         }
                     }
-                    sum = __fadd_rn(sum, ratio_tab[popc_words<W>(h)]);          /* hits / pairs, tabulated with the IEEE divide */
+                    const float r = ratio_tab[popc_words<W>(h)];               /* hits / pairs, tabulated with the IEEE divide */
+                    sum = i == 0 ? r : __fadd_rn(sum, r);                      /* 0 + r = r */
                 }
-                const float mean = mean_exact<CQ>(sum);
-                best = (best < mean) ? mean : best;
+                const float mean = CQ == 1 ? sum : mean_exact<CQ>(sum);
+                best = fmaxf(best, mean);                                      /* Apple MAX: no NaN on this path (cnt >= CQ >= 1) */
+                }
             }
             else for (uint32_t o = 0; o + CQ <= cnt; o++) {                   /* FP.m:136 */
                 float sum = 0.0f;
@@ -276,8 +294,8 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
                 best = (best < mean) ? mean : best;                            /* Apple MAX */
             }
             if (qvalid) {
-                if (all_scores) all_scores[(size_t)q * n_clips + c] = best;
-                if (best > worst) { top.insert(best, clip_ids ? clip_ids[c] : clip_base + c); worst = top.worst(); }
+                if (all_scores) all_scores[(size_t)q * all_stride + c] = best;
+                if (best > worst) { top.insert(best, clip_ids ? clip_ids[c] : clip_base + c); worst = fmaxf(top.worst(), floor_below); }
             }
         }
         c0 = n0; c1 = n1; buf ^= 1;
@@ -561,6 +579,7 @@ struct lbadcu_db {
     uint32_t min_count = 0xffffffffu, max_count = 0, base = 0;
     bool regular = true; uint32_t* d_irregular = nullptr;    /* device counter of subfingerprints that are not "one sign bit per rank" */
     float* d_part_sc = nullptr; uint32_t* d_part_id = nullptr; size_t part_cap = 0;
+    float* d_floor_sc = nullptr; uint32_t* d_floor_id = nullptr; size_t floor_cap = 0;      /* [q][k] top-k of the sample (threshold pass) */
     /* the partial-list buffers are shared by every search of this database: a search on another stream than the previous one waits
      * for that one's merge (searches on one database are serialised on the device, whatever streams they are enqueued on) */
     cudaEvent_t part_done = nullptr; cudaStream_t part_stream = nullptr; bool part_used = false;
@@ -601,7 +620,7 @@ extern "C" void lbadcu_db_destroy(lbadcu_db* db) {
     if (db->stream) cudaStreamSynchronize(db->stream);
     db->timer.clear();
     if (db->part_done) { cudaEventSynchronize(db->part_done); cudaEventDestroy(db->part_done); }
-    cudaFree(db->d_words); cudaFree(db->d_meta); cudaFree(db->d_irregular); cudaFree(db->d_offsets); cudaFree(db->d_part_sc); cudaFree(db->d_part_id); cudaFree(db->d_ids);
+    cudaFree(db->d_words); cudaFree(db->d_meta); cudaFree(db->d_irregular); cudaFree(db->d_offsets); cudaFree(db->d_part_sc); cudaFree(db->d_part_id); cudaFree(db->d_ids); cudaFree(db->d_floor_sc); cudaFree(db->d_floor_id);
     if (db->stream) cudaStreamDestroy(db->stream);
     delete db;
 }
@@ -703,21 +722,22 @@ extern "C" uint64_t lbadcu_db_compares_per_query(const lbadcu_db* db, uint32_t c
     return total;
 }
 
+/* n_search: the first n_search clips are searched (the whole database, or the sample of the threshold pass); floor_sc: see the kernel */
 template <int W, int CQ>
 static void launch_fast(lbadcu_db* db, bool masked, uint32_t n_chunks, size_t smem_topk, cudaStream_t s, const uint32_t* d_q, uint32_t n_q, uint32_t pairs, int k,
-                        uint32_t n_qgroups, uint32_t cpc, float* d_all, uint32_t rep) {
-    const uint32_t n_clips = lbadcu_db_clips(db);
+                        uint32_t n_qgroups, uint32_t cpc, float* d_all, uint32_t rep, uint32_t n_search, const float* floor_sc) {
+    const uint32_t n_clips = n_search, all_stride = lbadcu_db_clips(db);
     const uint32_t total_warps = (n_qgroups + SEARCH_WARPS - 1) / SEARCH_WARPS;      /* = CTAs per clip chunk (passed in the last kernel argument) */
     const uint32_t blocks = n_chunks * total_warps;
     const size_t smem = smem_topk + (size_t)2 * STAGE_SUBFPS * (2 * W * sizeof(uint32_t) + sizeof(float2)) + 260 * sizeof(float);
     if (masked) {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         search_fast_kernel<W, CQ, true><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, pairs, k, n_qgroups, cpc,
-                                                                                db->d_part_sc, db->d_part_id, d_all, total_warps, db->regular ? 1 : 0, rep);
+                                                                                db->d_part_sc, db->d_part_id, d_all, total_warps, db->regular ? 1 : 0, rep, all_stride, floor_sc, db->min_count == db->max_count ? db->min_count : 0u);
     } else {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         search_fast_kernel<W, CQ, false><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, pairs, k, n_qgroups, cpc,
-                                                                                 db->d_part_sc, db->d_part_id, d_all, total_warps, db->regular ? 1 : 0, rep);
+                                                                                 db->d_part_sc, db->d_part_id, d_all, total_warps, db->regular ? 1 : 0, rep, all_stride, floor_sc, db->min_count == db->max_count ? db->min_count : 0u);
     }
 }
 
@@ -758,65 +778,96 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
     const bool fast = n_clips > 0 && db->min_count >= cq && db->max_count <= (uint32_t)STAGE_SUBFPS && cq >= 1 && cq <= 6;
     const bool few = fast && n_q <= FEW_MAX_Q && k <= 32;                 /* lane = clip: every lane works even for ONE query */
     static const uint32_t warps_per_sm = [] { const char* e = getenv("LBAD_SEARCH_WARPS_PER_SM"); const int v = e ? atoi(e) : 0; return (uint32_t)(v >= 4 && v <= 512 ? v : 128); }();
-    uint32_t n_chunks = ((uint32_t)db->sm_count * warps_per_sm + n_qgroups - 1) / n_qgroups;       /* chunks for ~128 warps per SM, several times what is resident (20 warps of the 95-register CQ = 6 kernel): the block scheduler hands
-                                                                                           * the next chunk to whichever SM frees a slot, which evens out the SMs (measured on a 125,000-clip shard:
-                                                                                           * 9.33 ms with 32, 8.93 with 128, 9.03 with 384 where the chunk lists start to cost; LBAD_SEARCH_WARPS_PER_SM) */
-    if (few) n_chunks = std::min<uint32_t>((n_clips + 31) / 32, (uint32_t)db->sm_count * 32);      /* one list per warp, 32 clips per step */
-    if (n_chunks > n_clips) n_chunks = n_clips;
-    if (n_chunks < 1) n_chunks = 1;
-    uint32_t cpc = n_clips ? (n_clips + n_chunks - 1) / n_chunks : 1;
-    if (few) cpc = (cpc + 31) & ~31u;
-    n_chunks = n_clips ? (n_clips + cpc - 1) / cpc : 1;
     const uint32_t rep = (fast && !few && n_qgroups <= 2) ? (uint32_t)SEARCH_WARPS / n_qgroups : 1u;      /* search_fast_kernel: lists per chunk */
-    const uint32_t n_lists = n_chunks * rep;
-    const size_t need = ((size_t)n_lists + (n_lists + MERGE_GROUP - 1) / MERGE_GROUP) * n_q * k;      /* chunk lists + (two-level merge) group lists */
-    if (db->part_used && db->part_stream != s) LBAD_CUDA_TRY(cudaStreamWaitEvent(s, db->part_done, 0));      /* the previous search, on another stream, still owns the lists */
-    if (db->part_cap < need) {
-        if (db->part_used) LBAD_CUDA_TRY(cudaEventSynchronize(db->part_done));
-        LBAD_CUDA_TRY(cudaStreamSynchronize(s));
-        cudaFree(db->d_part_sc); cudaFree(db->d_part_id); db->d_part_sc = nullptr; db->d_part_id = nullptr;
-        LBAD_CUDA_TRY(cudaMalloc(&db->d_part_sc, need * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&db->d_part_id, need * sizeof(uint32_t)));
-        db->part_cap = need;
-    }
-    const uint32_t total_warps = n_chunks * n_qgroups;
-    const uint32_t blocks = (total_warps + SEARCH_WARPS - 1) / SEARCH_WARPS;
     const bool masked = pairs < db->pairs_full;       /* words beyond L are zero already; a mask is only needed for a shorter range */
     const size_t smem_fast = (size_t)SEARCH_WARPS * 2 * k * 32 * 4;
     const size_t smem_gen = (size_t)SEARCH_WARPS * ((size_t)2 * k * 32 + (size_t)cq * 2 * W * 32) * 4;
     if (!fast && smem_gen > db->smem_optin) return LBAD_ERR_ARG;
-    db->timer.begin(s);
-#define LBAD_FAST(WW, CC) launch_fast<WW, CC>(db, masked, n_chunks, smem_fast, s, d_q, n_q, pairs, (int)k, n_qgroups, cpc, d_all, rep)
-#define LBAD_GEN(WW) launch_generic<WW>(db, blocks, smem_gen, s, d_q, n_q, cq, pairs, (int)k, n_qgroups, cpc, d_all, total_warps)
-    if (few) {
-        const uint32_t fblocks = (n_chunks + SEARCH_WARPS - 1) / SEARCH_WARPS;
-        if (W == 2) search_few_kernel<2><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, d_all, n_chunks);
-        else if (W == 4) search_few_kernel<4><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, d_all, n_chunks);
-        else search_few_kernel<8><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, d_all, n_chunks);
-    } else if (fast) {
+    /* how the first n_search clips are cut into chunks: ~128 warps per SM, several times what is resident (20 warps of the 95-register
+     * CQ = 6 kernel) — the block scheduler hands the next chunk to whichever SM frees a slot, which evens out the SMs (measured on a
+     * 125,000-clip shard: 9.33 ms with 32, 8.93 with 128, 9.03 with 384 where the chunk lists start to cost; LBAD_SEARCH_WARPS_PER_SM) */
+    struct Cut { uint32_t n_chunks, cpc, n_lists; };
+    auto cut = [&](uint32_t n_search) {
+        uint32_t n_chunks = ((uint32_t)db->sm_count * warps_per_sm + n_qgroups - 1) / n_qgroups;
+        if (few) n_chunks = std::min<uint32_t>((n_search + 31) / 32, (uint32_t)db->sm_count * 32);      /* one list per warp, 32 clips per step */
+        if (n_chunks > n_search) n_chunks = n_search;
+        if (n_chunks < 1) n_chunks = 1;
+        uint32_t cpc = n_search ? (n_search + n_chunks - 1) / n_chunks : 1;
+        if (few) cpc = (cpc + 31) & ~31u;
+        n_chunks = n_search ? (n_search + cpc - 1) / cpc : 1;
+        return Cut{n_chunks, cpc, n_chunks * rep};
+    };
+    /* threshold pass (large databases, the query-per-lane kernel): the top k of a SAMPLE — the first n_sample clips — give, per query, a
+     * score that at least k clips reach; the main pass then lets only clips at or above it into its lists.  Exact: the main pass still
+     * visits every clip, the sample included.  Costs n_sample / n_clips more compares; saves the list insertions, which the whole warp
+     * walks through whenever any of its 32 queries inserts — with short chunks that was nearly every clip (a third of all stall samples
+     * at one subfingerprint per query). */
+    const bool no_floor = getenv("LBAD_SEARCH_NO_FLOOR") != nullptr;       /* (tests: the same search with and without the threshold pass) */
+    /* sample size: 1/24 of the clips for one or two subfingerprints per query (few compares per clip: the insertions dominate), 1/96 for
+     * longer queries; measured with 1,000 queries: one subfingerprint per query 1.11 -> 0.64 ms on 100,000 clips of 5 (with the leaner
+     * inner loop), six per query 8.01 -> 7.96 ms on 125,000 clips of 19 */
+    const uint32_t n_sample = std::min<uint32_t>(8192u, std::max<uint32_t>(1024u, n_clips / (cq <= 2 ? 24u : 96u)));
+    const bool use_floor = fast && !few && !no_floor && n_clips >= 65536u;
+    const Cut main_cut = cut(n_clips), pre_cut = use_floor ? cut(n_sample) : Cut{0, 0, 0};
+    const uint32_t max_lists = std::max(main_cut.n_lists, pre_cut.n_lists);
+    const size_t need = ((size_t)max_lists + (max_lists + MERGE_GROUP - 1) / MERGE_GROUP) * n_q * k;      /* chunk lists + (two-level merge) group lists */
+    if (db->part_used && db->part_stream != s) LBAD_CUDA_TRY(cudaStreamWaitEvent(s, db->part_done, 0));      /* the previous search, on another stream, still owns the lists */
+    if (db->part_cap < need || (use_floor && db->floor_cap < (size_t)n_q * k)) {
+        if (db->part_used) LBAD_CUDA_TRY(cudaEventSynchronize(db->part_done));
+        LBAD_CUDA_TRY(cudaStreamSynchronize(s));
+        if (db->part_cap < need) {
+            cudaFree(db->d_part_sc); cudaFree(db->d_part_id); db->d_part_sc = nullptr; db->d_part_id = nullptr; db->part_cap = 0;
+            LBAD_CUDA_TRY(cudaMalloc(&db->d_part_sc, need * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&db->d_part_id, need * sizeof(uint32_t)));
+            db->part_cap = need;
+        }
+        if (use_floor && db->floor_cap < (size_t)n_q * k) {
+            cudaFree(db->d_floor_sc); cudaFree(db->d_floor_id); db->d_floor_sc = nullptr; db->d_floor_id = nullptr; db->floor_cap = 0;
+            LBAD_CUDA_TRY(cudaMalloc(&db->d_floor_sc, (size_t)n_q * k * sizeof(float))); LBAD_CUDA_TRY(cudaMalloc(&db->d_floor_id, (size_t)n_q * k * sizeof(uint32_t)));
+            db->floor_cap = (size_t)n_q * k;
+        }
+    }
+    /* one pass: the search kernel over the first n_search clips, then the merge of its chunk lists into o_sc / o_id */
+    auto pass = [&](const Cut& c, uint32_t n_search, float* all, const float* floor_sc, float* o_sc, uint32_t* o_id) -> int {
+        const uint32_t n_chunks = c.n_chunks, cpc = c.cpc, n_lists = c.n_lists;
+        const uint32_t total_warps = n_chunks * n_qgroups;
+        const uint32_t blocks = (total_warps + SEARCH_WARPS - 1) / SEARCH_WARPS;
+#define LBAD_FAST(WW, CC) launch_fast<WW, CC>(db, masked, n_chunks, smem_fast, s, d_q, n_q, pairs, (int)k, n_qgroups, cpc, all, rep, n_search, floor_sc)
+#define LBAD_GEN(WW) launch_generic<WW>(db, blocks, smem_gen, s, d_q, n_q, cq, pairs, (int)k, n_qgroups, cpc, all, total_warps)
+        if (few) {
+            const uint32_t fblocks = (n_chunks + SEARCH_WARPS - 1) / SEARCH_WARPS;
+            if (W == 2) search_few_kernel<2><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, all, n_chunks);
+            else if (W == 4) search_few_kernel<4><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, all, n_chunks);
+            else search_few_kernel<8><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, all, n_chunks);
+        } else if (fast) {
 #define LBAD_FAST_W(WW) switch (cq) { case 1: LBAD_FAST(WW, 1); break; case 2: LBAD_FAST(WW, 2); break; case 3: LBAD_FAST(WW, 3); break; \
                                       case 4: LBAD_FAST(WW, 4); break; case 5: LBAD_FAST(WW, 5); break; default: LBAD_FAST(WW, 6); break; }
-        if (W == 2) { LBAD_FAST_W(2) } else if (W == 4) { LBAD_FAST_W(4) } else { LBAD_FAST_W(8) }
+            if (W == 2) { LBAD_FAST_W(2) } else if (W == 4) { LBAD_FAST_W(4) } else { LBAD_FAST_W(8) }
 #undef LBAD_FAST_W
-    } else {
-        if (W == 2) LBAD_GEN(2); else if (W == 4) LBAD_GEN(4); else LBAD_GEN(8);
-    }
+        } else {
+            if (W == 2) LBAD_GEN(2); else if (W == 4) LBAD_GEN(4); else LBAD_GEN(8);
+        }
 #undef LBAD_FAST
 #undef LBAD_GEN
-    db->timer.end(s);
-    db->launches++;
-    LBAD_CUDA_TRY(cudaGetLastError());
-    if (n_lists > MERGE_GROUP) {
-        /* many lists (few queries): merged group by group, then the groups — behind the chunk lists in the same buffer */
-        const uint32_t n_groups = (n_lists + MERGE_GROUP - 1) / MERGE_GROUP;
-        float* g_sc = db->d_part_sc + (size_t)n_lists * n_q * k; uint32_t* g_id = db->d_part_id + (size_t)n_lists * n_q * k;
-        merge_topk_kernel<<<(n_q * n_groups + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_lists, n_q, (int)k, g_sc, g_id, MERGE_GROUP, (size_t)n_q * k);
-        merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(g_sc, g_id, n_groups, n_q, (int)k, d_scores, d_idx, n_groups, (size_t)n_q * k);
-        db->launches += 2;
-    } else {
-        merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_lists, n_q, (int)k, d_scores, d_idx, n_lists, (size_t)n_q * k);
         db->launches++;
-    }
-    LBAD_CUDA_TRY(cudaGetLastError());
+        LBAD_CUDA_TRY(cudaGetLastError());
+        if (n_lists > MERGE_GROUP) {
+            /* many lists (few queries): merged group by group, then the groups — behind the chunk lists in the same buffer */
+            const uint32_t n_groups = (n_lists + MERGE_GROUP - 1) / MERGE_GROUP;
+            float* g_sc = db->d_part_sc + (size_t)n_lists * n_q * k; uint32_t* g_id = db->d_part_id + (size_t)n_lists * n_q * k;
+            merge_topk_kernel<<<(n_q * n_groups + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_lists, n_q, (int)k, g_sc, g_id, MERGE_GROUP, (size_t)n_q * k);
+            merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(g_sc, g_id, n_groups, n_q, (int)k, o_sc, o_id, n_groups, (size_t)n_q * k);
+            db->launches += 2;
+        } else {
+            merge_topk_kernel<<<(n_q + 3) / 4, 128, 0, s>>>(db->d_part_sc, db->d_part_id, n_lists, n_q, (int)k, o_sc, o_id, n_lists, (size_t)n_q * k);
+            db->launches++;
+        }
+        LBAD_CUDA_TRY(cudaGetLastError());
+        return LBAD_OK;
+    };
+    db->timer.begin(s);                                                   /* the timed span: both passes with their merges */
+    if (use_floor) { const int e = pass(pre_cut, n_sample, nullptr, nullptr, db->d_floor_sc, db->d_floor_id); if (e != LBAD_OK) return e; }
+    { const int e = pass(main_cut, n_clips, d_all, use_floor ? db->d_floor_sc : nullptr, d_scores, d_idx); if (e != LBAD_OK) return e; }
+    db->timer.end(s);
     LBAD_CUDA_TRY(cudaEventRecord(db->part_done, s));
     db->part_stream = s; db->part_used = true;
     return LBAD_OK;

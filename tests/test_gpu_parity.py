@@ -732,3 +732,33 @@ def test_calls_on_different_streams_are_ordered(lb, port):
     for sc, ix in res:
         assert np.array_equal(ix[:, 0].cpu().numpy(), np.arange(0, n, 5).astype(np.int32)) and (sc[:, 0] == 1.0).all()
         assert torch.equal(sc, res[0][0]) and torch.equal(ix, res[0][1])
+
+
+@pytest.mark.parametrize("L,q_count,db_count,n_q", [(200, 1, 5, 100), (100, 2, 6, 40), (200, 6, 19, 70)])
+def test_threshold_pass_changes_nothing(lb, checker, monkeypatch, L, q_count, db_count, n_q):
+    """Databases of 65,536 clips and more are searched in two passes — the top k of a sample first, whose k-th score then keeps clips
+    below it out of the per-chunk lists.  The result must be the one of the single pass, ties included (short codes and noisy excerpts
+    make plenty of equal scores), and equal the oracle's on the queries checked."""
+    rng = np.random.default_rng(900 + L + q_count)
+    n_db, k = 70000, 10
+    dbb = rank_sign_codes(rng, n_db, db_count, L)
+    dbb[1000:1200] = dbb[0:200]                                             # exact duplicates: equal scores, the lower clip index must win
+    src = rng.integers(0, n_db, n_q)
+    qb = np.stack([dbb[c, 1:1 + q_count] for c in src]).copy()
+    flip = rng.random(qb.shape[:2] + (L // 2,)) < 0.1
+    qb[..., 0::2] ^= flip.astype(np.uint8); qb[..., 1::2] ^= flip.astype(np.uint8)
+    qb[0] = dbb[50, 1:1 + q_count]                                          # clip 50 and its duplicate 1050 both score 1
+    words = lb.pack_booleans(dbb); q = lb.pack_booleans(qb)
+    db = lb.Database(L); db.add_packed(words)
+    two = db.search_packed(q, k)
+    monkeypatch.setenv("LBAD_SEARCH_NO_FLOOR", "1")
+    one = db.search_packed(q, k)
+    monkeypatch.delenv("LBAD_SEARCH_NO_FLOOR")
+    assert np.array_equal(two[0], one[0]) and np.array_equal(two[1], one[1])
+    assert two[1][0, 0] == 50 and two[1][0, 1] == 1050 and two[0][0, 0] == 1.0 and two[0][0, 1] == 1.0
+    for qi in (0, 1, n_q - 1):
+        want = np.array([np.float32(checker.compare_fp(dbb[c], qb[qi], L)) for c in range(0, n_db, 1)][:4000] , np.float32)      # the oracle on the first 4,000 clips
+        sub = lb.Database(L); sub.add_packed(words[:4000])
+        sc, ix = sub.search_packed(q[qi:qi + 1], k)
+        order = np.lexsort((np.arange(4000), -want.astype(np.float64)))[:k]
+        assert np.array_equal(ix[0], order.astype(np.uint32)) and np.array_equal(sc[0], want[order])
