@@ -411,8 +411,8 @@ def main():
             # per-GPU top-k on the shard written straight into the exchange payload, ONE NCCL all-gather, the merge kernel on the gather
             # buffer in place, then ONE copy of the merged result to the host
             db.search_device(qw.data_ptr(), args.queries, 6, 10, ex.scores_ptr, ex.indices_ptr, stream=stream)
-            m_sc, m_id = ex.gather_and_merge(stream)
-            host_res[0].copy_(m_sc.view(torch.int32), non_blocking=True); host_res[1].copy_(m_id, non_blocking=True)
+            ex.gather_and_merge(stream)
+            host_res.copy_(ex.merged, non_blocking=True)                       # scores and indices are one buffer: one copy
             torch.cuda.current_stream().synchronize()
             return host_res[0].numpy().view(np.float32), host_res[1].numpy().view(np.uint32)
         for _ in range(2):
@@ -486,7 +486,8 @@ def main():
         bound = mb["popc_gops"] * 1e9 / 4.0
         db_bytes = (args.db_clips / world) * SUBFPS * (32 + 8)
         search["roofline"] = {"bound": "int-pipe (POPC)", "achieved": per_gpu, "peak": bound, "unit": "compares/s per GPU", "frac": per_gpu / bound,
-                              "note": "peak = measured lane-POPC rate / 4 POPC per compare (SURVEY.md §8d); the kernel's carry-save form needs fewer, so frac can exceed 1",
+                              "note": "peak = measured lane-POPC rate / 4 POPC per compare (SURVEY.md §8d); the kernel's carry-save form issues 3, so frac can exceed 1",
+                              "frac_of_3_popc_bound": per_gpu / (mb["popc_gops"] * 1e9 / 3.0),
                               "hbm_gbs": db_bytes * ((args.queries + 127) // 128) / (search["kernel_ms"] * 1e-3) / 1e9, "hbm_frac": db_bytes * ((args.queries + 127) // 128) / (search["kernel_ms"] * 1e-3) / 1e9 / hbm_peak}
     if search is not None:
         del db

@@ -132,8 +132,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
  * nest.  The four warps of a CTA work on the SAME clips with different query groups: tiles of whole clips (words and
  * (possible, 1/possible)) are brought into shared memory by cp.async, double buffered, and read back as warp-uniform
  * broadcast loads; the CQ query subfingerprints live in registers. */
+#ifndef LBAD_SEARCH_MIN_CTAS
+#define LBAD_SEARCH_MIN_CTAS 6          /* at most 85 registers: six CTAs (24 warps) per SM for the longest queries; measured 7.61 ms on a 125,000-clip shard against 8.19 with 7 (spills) and 9.38 with 1 */
+#endif
 template <int W, int CQ, bool MASKED>
-__global__ void __launch_bounds__(SEARCH_WARPS * 32)
+__global__ void __launch_bounds__(SEARCH_WARPS * 32, CQ >= 4 ? LBAD_SEARCH_MIN_CTAS : 0)      /* (0: no constraint — the short-query variants are far below it and compile best left alone) */
 search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ meta, const uint32_t* __restrict__ offsets, const uint32_t n_clips,
                    const uint32_t clip_base, const uint32_t* __restrict__ clip_ids, const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t pairs, const int k,
                    const uint32_t n_qgroups, const uint32_t clips_per_chunk, float* __restrict__ part_sc, uint32_t* __restrict__ part_id,
@@ -188,8 +191,23 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
         }
         regular = __all_sync(0xffffffffu, mine || !qvalid);
     }
+    uint32_t qnib = 0;                                                          /* nibble i: the fourth-word bits of query subfingerprint i */
+    if constexpr (W == 4) {
+#pragma unroll
+        for (int i = 0; i < CQ; i++) qnib |= (qp[i][3] & 0xFu) << (4 * i);
+    }
     float* ratio_tab = reinterpret_cast<float*>(st_meta + 2 * STAGE_SUBFPS);        /* [pairs + 1]: (float)h / (float)pairs */
     for (uint32_t h = tid; h <= pairs; h += SEARCH_WARPS * 32) ratio_tab[h] = pairs ? __fdiv_rn((float)h, (float)pairs) : 0.0f;
+    /* 100 ranks (the reference's default subfingerprint) are three full words and FOUR bits of the fourth: the fourth word's bits of eight
+     * consecutive subfingerprints are gathered into one "window" word per subfingerprint when a tile lands, so that a query's leftover
+     * bits against ALL of its offset's subfingerprints are one XOR and one nibble-wise population count in plain integer arithmetic —
+     * and a compare needs TWO POPC (carry-save over the three full words) instead of three.  The kernel was bound by exactly that
+     * quarter-rate instruction.  miss_tab[m] = (100 - m) / 100 for m mismatching ranks. */
+    constexpr bool CAN100 = W == 4 && !MASKED && CQ >= 4;      /* (shorter queries: the per-offset window arithmetic is not amortised — measured 0.83 against 0.64 ms at CQ = 1) */
+    const bool tile100 = CAN100 && db_regular && pairs == 100;                   /* CTA-uniform: windows are built for every tile */
+    float* miss_tab = ratio_tab + 260;                                          /* [101] */
+    uint32_t* st_win = reinterpret_cast<uint32_t*>(miss_tab + 104);             /* [2][STAGE_SUBFPS] */
+    if (tile100) for (uint32_t m = tid; m <= 100; m += SEARCH_WARPS * 32) miss_tab[m] = __fdiv_rn((float)(100 - m), 100.0f);
     /* (visible to every warp after the first __syncthreads of the tile loop) */
 
     /* tile = clips [c0, c1) whose subfingerprints [s_lo, s_hi) fit the staging buffer; every thread computes the same bounds */
@@ -222,12 +240,43 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
         const uint32_t s_lo = first_subfp(c0);
         const uint32_t* tw = st_words + (size_t)buf * STAGE_SUBFPS * 2 * W;
         const float2* tm = st_meta + (size_t)buf * STAGE_SUBFPS;
+        if (tile100) {                                                         /* windows of this tile: win[j] nibble t = fourth-word bits of subfingerprint j + t */
+            const uint32_t n_sub = first_subfp(c1) - s_lo;
+            for (uint32_t j = tid; j < n_sub; j += SEARCH_WARPS * 32) {
+                uint32_t wv = 0;
+#pragma unroll
+                for (uint32_t t = 0; t < 8; t++) if (j + t < n_sub) wv |= (tw[(size_t)(j + t) * 2 * W + 3] & 0xFu) << (4 * t);
+                st_win[buf * STAGE_SUBFPS + j] = wv;
+            }
+            __syncthreads();
+        }
         if (qg < n_qgroups) for (uint32_t c = c0 + sub; c < c1; c += rep) {
             uint32_t s0, cnt;                                                 /* warp-uniform */
             if (uniform) { s0 = (c - c0) * uniform; cnt = uniform; }
             else { const uint32_t a = offsets[c]; s0 = a - s_lo; cnt = offsets[c + 1] - a; }
             float best = 0.0f;                                                /* FP.m:133 */
-            if (regular) {
+            if (CAN100 && regular && tile100) {
+                const uint32_t* src0 = tw + (size_t)s0 * 2 * W;
+                const uint32_t* wn = st_win + buf * STAGE_SUBFPS + s0;
+                constexpr uint32_t NIB_MASK = CQ >= 8 ? 0xffffffffu : ((1u << (4 * CQ)) - 1u);
+                for (uint32_t n_off = cnt - CQ + 1; n_off; n_off--, src0 += 2 * W, wn++) {      /* FP.m:136 */
+                    uint32_t x = (*wn ^ qnib) & NIB_MASK;                      /* mismatching leftover bits, nibble i belongs to compare i */
+                    x = x - ((x >> 1) & 0x55555555u);
+                    x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);          /* nibble i: how many of them (0..4) */
+                    float sum = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < CQ; i++) {                            /* FP.m:139-142 */
+                        const uint4 a = *reinterpret_cast<const uint4*>(src0 + i * 2 * W);
+                        const uint32_t x0 = a.x ^ qp[i][0], x1 = a.y ^ qp[i][1], x2 = a.z ^ qp[i][2];
+                        const uint32_t miss = __popc(lop3<0x96>(x0, x1, x2)) + 2 * __popc(lop3<0xE8>(x0, x1, x2)) + ((x >> (4 * i)) & 7u);
+                        const float r = miss_tab[miss];                        /* (100 - miss) / 100, tabulated with the IEEE divide */
+                        sum = i == 0 ? r : __fadd_rn(sum, r);
+                    }
+                    const float mean = CQ == 1 ? sum : mean_exact<CQ>(sum);
+                    best = fmaxf(best, mean);
+                }
+            }
+            else if (regular) {
                 const uint32_t* src0 = tw + (size_t)s0 * 2 * W;               /* the clip's subfingerprint o; one pointer step per offset */
                 for (uint32_t n_off = cnt - CQ + 1; n_off; n_off--, src0 += 2 * W) {      /* FP.m:136, short form (cnt >= CQ on this path) */
                 float sum = 0.0f;
@@ -729,7 +778,7 @@ static void launch_fast(lbadcu_db* db, bool masked, uint32_t n_chunks, size_t sm
     const uint32_t n_clips = n_search, all_stride = lbadcu_db_clips(db);
     const uint32_t total_warps = (n_qgroups + SEARCH_WARPS - 1) / SEARCH_WARPS;      /* = CTAs per clip chunk (passed in the last kernel argument) */
     const uint32_t blocks = n_chunks * total_warps;
-    const size_t smem = smem_topk + (size_t)2 * STAGE_SUBFPS * (2 * W * sizeof(uint32_t) + sizeof(float2)) + 260 * sizeof(float);
+    const size_t smem = smem_topk + (size_t)2 * STAGE_SUBFPS * (2 * W * sizeof(uint32_t) + sizeof(float2)) + (260 + 104) * sizeof(float) + 2 * STAGE_SUBFPS * sizeof(uint32_t);
     if (masked) {
         cudaFuncSetAttribute(search_fast_kernel<W, CQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         search_fast_kernel<W, CQ, true><<<blocks, SEARCH_WARPS * 32, smem, s>>>(db->d_words, db->d_meta, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, pairs, k, n_qgroups, cpc,
