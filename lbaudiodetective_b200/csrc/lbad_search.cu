@@ -204,7 +204,20 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
      * and a compare needs TWO POPC (carry-save over the three full words) instead of three.  The kernel was bound by exactly that
      * quarter-rate instruction.  miss_tab[m] = (100 - m) / 100 for m mismatching ranks. */
     constexpr bool CAN100 = W == 4 && !MASKED && CQ >= 4;      /* (shorter queries: the per-offset window arithmetic is not amortised — measured 0.83 against 0.64 ms at CQ = 1) */
-    const bool tile100 = CAN100 && db_regular && pairs == 100;                   /* CTA-uniform: windows are built for every tile */
+    /* CTA-uniform, and only when EVERY warp of the CTA takes the short form: the landed tile is then rewritten in place (below), which
+     * the general form of another warp could not read */
+    bool tile100 = false;
+    if constexpr (CAN100) tile100 = __syncthreads_and(regular && db_regular && pairs == 100) != 0;
+    if constexpr (CAN100) {
+        /* The carry-save adder over the three full words needs ones = x0 ^ x1 ^ x2 and twos = maj(x0, x1, x2) with x_w = a_w ^ q_w.  The
+         * ones word is (a0 ^ a1 ^ a2) ^ (q0 ^ q1 ^ q2): both XORs of three are formed once — the database's when its tile lands, in place
+         * of word 2, the query's here — and x2 = ones ^ x0 ^ x1 makes the majority a function of (x0, x1, ones): four integer-pipe
+         * instructions per compare instead of five (the kernel is bound by that pipe: 59 of 108 instructions per offset). */
+        if (tile100) {
+#pragma unroll
+            for (int i = 0; i < CQ; i++) qp[i][2] ^= qp[i][0] ^ qp[i][1];
+        }
+    }
     float* miss_tab = ratio_tab + 260;                                          /* [101] */
     uint32_t* st_win = reinterpret_cast<uint32_t*>(miss_tab + 104);             /* [2][STAGE_SUBFPS] */
     if (tile100) for (uint32_t m = tid; m <= 100; m += SEARCH_WARPS * 32) miss_tab[m] = __fdiv_rn((float)(100 - m), 100.0f);
@@ -247,6 +260,8 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
 #pragma unroll
                 for (uint32_t t = 0; t < 8; t++) if (j + t < n_sub) wv |= (tw[(size_t)(j + t) * 2 * W + 3] & 0xFu) << (4 * t);
                 st_win[buf * STAGE_SUBFPS + j] = wv;
+                uint32_t* own = const_cast<uint32_t*>(tw) + (size_t)j * 2 * W;      /* word 2 <- a0 ^ a1 ^ a2 (nobody else touches this subfingerprint's words 0..2) */
+                own[2] ^= own[0] ^ own[1];
             }
             __syncthreads();
         }
@@ -255,21 +270,31 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
             if (uniform) { s0 = (c - c0) * uniform; cnt = uniform; }
             else { const uint32_t a = offsets[c]; s0 = a - s_lo; cnt = offsets[c + 1] - a; }
             float best = 0.0f;                                                /* FP.m:133 */
-            if (CAN100 && regular && tile100) {
+            if (CAN100 && tile100) {
                 const uint32_t* src0 = tw + (size_t)s0 * 2 * W;
                 const uint32_t* wn = st_win + buf * STAGE_SUBFPS + s0;
-                constexpr uint32_t NIB_MASK = CQ >= 8 ? 0xffffffffu : ((1u << (4 * CQ)) - 1u);
+                const uint32_t miss_tab_addr = smem_u32(miss_tab);
                 for (uint32_t n_off = cnt - CQ + 1; n_off; n_off--, src0 += 2 * W, wn++) {      /* FP.m:136 */
-                    uint32_t x = (*wn ^ qnib) & NIB_MASK;                      /* mismatching leftover bits, nibble i belongs to compare i */
+                    uint32_t x = *wn ^ qnib;                                   /* mismatching leftover bits, nibble i belongs to compare i (nibbles >= CQ: never read) */
                     x = x - ((x >> 1) & 0x55555555u);
                     x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);          /* nibble i: how many of them (0..4) */
+                    /* ... spread to bytes, times four: byte t of xe / xo = 4 x the count of compare 2t / 2t + 1 — a compare then takes its
+                     * byte with ONE permute, already scaled as the table's byte offset (a shift and a mask per compare before) */
+                    const uint32_t xe = (x << 2) & 0x3C3C3C3Cu, xo = (x >> 2) & 0x3C3C3C3Cu;
                     float sum = 0.0f;
 #pragma unroll
                     for (int i = 0; i < CQ; i++) {                            /* FP.m:139-142 */
-                        const uint4 a = *reinterpret_cast<const uint4*>(src0 + i * 2 * W);
-                        const uint32_t x0 = a.x ^ qp[i][0], x1 = a.y ^ qp[i][1], x2 = a.z ^ qp[i][2];
-                        const uint32_t miss = __popc(lop3<0x96>(x0, x1, x2)) + 2 * __popc(lop3<0xE8>(x0, x1, x2)) + ((x >> (4 * i)) & 7u);
-                        const float r = miss_tab[miss];                        /* (100 - miss) / 100, tabulated with the IEEE divide */
+                        const uint4 a = *reinterpret_cast<const uint4*>(src0 + i * 2 * W);      /* a.z = a0 ^ a1 ^ a2 (rewritten when the tile landed) */
+                        const uint32_t x0 = a.x ^ qp[i][0], x1 = a.y ^ qp[i][1], ones = a.z ^ qp[i][2];
+                        const uint32_t twos = lop3<0xD4>(x0, x1, ones);        /* maj(x0, x1, x2) with x2 = ones ^ x0 ^ x1: (x0 & x1) | ((x0 ^ x1) & ~ones) */
+                        const uint32_t nib4 = __byte_perm((i & 1) ? xo : xe, 0u, 0x4440u + (uint32_t)(i >> 1));
+                        /* address of miss_tab[popc(ones) + 2 popc(twos) + nibble], every step a multiply-add (FMA pipe) instead of a shift or
+                         * a three-input add (integer pipe, the binding one) */
+                        uint32_t addr; float r;
+                        asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(addr) : "r"(nib4), "r"(miss_tab_addr));
+                        asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(__popc(ones)), "r"(addr));
+                        asm("mad.lo.u32 %0, %1, 8, %2;" : "=r"(addr) : "r"(__popc(twos)), "r"(addr));
+                        asm("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));      /* (100 - miss) / 100, tabulated with the IEEE divide (filled before the tile loop's first barrier) */
                         sum = i == 0 ? r : __fadd_rn(sum, r);
                     }
                     const float mean = CQ == 1 ? sum : mean_exact<CQ>(sum);
