@@ -177,10 +177,12 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
     float worst = fmaxf(top.worst(), floor_below);
     /* "Regular" codes: every one of the first `pairs` ranks carries exactly one sign bit, which is what extraction produces whenever
      * the selected coefficients are non-zero.  Then M = ~P on those ranks, possible = pairs, and a pair hits iff the P bits agree:
-     * one LOP3 per word instead of two, no M plane, no per-subfingerprint (possible, 1/possible).  The database side is checked
-     * when it is appended (db_regular), the query side here; a warp takes the short form only if all of its queries qualify. */
-    bool regular = false;
-    if (!MASKED && db_regular) {
+     * one LOP3 per word instead of two, no M plane, no per-subfingerprint (possible, 1/possible).  The query side is checked here (a
+     * warp takes the short form only if all of its queries qualify); the database side per TILE: a database found regular when it was
+     * appended (db_regular) needs no check, in any other the subfingerprints of a landed tile are inspected — so the few clips with
+     * empty ranks (digital silence) cost their own tiles the general form, not the whole database. */
+    bool q_regular = false;
+    if (!MASKED) {
         bool mine = true;
 #pragma unroll
         for (int i = 0; i < CQ; i++) {
@@ -189,7 +191,7 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
             for (int w = 0; w < W; w++) { both |= qp[i][w] & qm[i][w]; cover += __popc(qp[i][w] | qm[i][w]); }
             mine = mine && both == 0 && cover == pairs;
         }
-        regular = __all_sync(0xffffffffu, mine || !qvalid);
+        q_regular = __all_sync(0xffffffffu, mine || !qvalid);
     }
     uint32_t qnib = 0;                                                          /* nibble i: the fourth-word bits of query subfingerprint i */
     if constexpr (W == 4) {
@@ -206,21 +208,21 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
     constexpr bool CAN100 = W == 4 && !MASKED && CQ >= 4;      /* (shorter queries: the per-offset window arithmetic is not amortised — measured 0.83 against 0.64 ms at CQ = 1) */
     /* CTA-uniform, and only when EVERY warp of the CTA takes the short form: the landed tile is then rewritten in place (below), which
      * the general form of another warp could not read */
-    bool tile100 = false;
-    if constexpr (CAN100) tile100 = __syncthreads_and(regular && db_regular && pairs == 100) != 0;
+    bool cta100 = false;
+    if constexpr (CAN100) cta100 = __syncthreads_and(q_regular && pairs == 100) != 0;
     if constexpr (CAN100) {
         /* The carry-save adder over the three full words needs ones = x0 ^ x1 ^ x2 and twos = maj(x0, x1, x2) with x_w = a_w ^ q_w.  The
          * ones word is (a0 ^ a1 ^ a2) ^ (q0 ^ q1 ^ q2): both XORs of three are formed once — the database's when its tile lands, in place
          * of word 2, the query's here — and x2 = ones ^ x0 ^ x1 makes the majority a function of (x0, x1, ones): four integer-pipe
          * instructions per compare instead of five (the kernel is bound by that pipe: 59 of 108 instructions per offset). */
-        if (tile100) {
+        if (cta100) {
 #pragma unroll
             for (int i = 0; i < CQ; i++) qp[i][2] ^= qp[i][0] ^ qp[i][1];
         }
     }
     float* miss_tab = ratio_tab + 260;                                          /* [101] */
     uint32_t* st_win = reinterpret_cast<uint32_t*>(miss_tab + 104);             /* [2][STAGE_SUBFPS] */
-    if (tile100) for (uint32_t m = tid; m <= 100; m += SEARCH_WARPS * 32) miss_tab[m] = __fdiv_rn((float)(100 - m), 100.0f);
+    if (cta100) for (uint32_t m = tid; m <= 100; m += SEARCH_WARPS * 32) miss_tab[m] = __fdiv_rn((float)(100 - m), 100.0f);
     /* (visible to every warp after the first __syncthreads of the tile loop) */
 
     /* tile = clips [c0, c1) whose subfingerprints [s_lo, s_hi) fit the staging buffer; every thread computes the same bounds */
@@ -253,6 +255,18 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
         const uint32_t s_lo = first_subfp(c0);
         const uint32_t* tw = st_words + (size_t)buf * STAGE_SUBFPS * 2 * W;
         const float2* tm = st_meta + (size_t)buf * STAGE_SUBFPS;
+        bool tile_reg = db_regular != 0;
+        if (!MASKED && !db_regular) {                                          /* (CTA-uniform) is every subfingerprint of this tile regular?  P ^ M = the rank mask, word by word */
+            const uint32_t n_sub = first_subfp(c1) - s_lo;
+            bool ok = true;
+            for (uint32_t j = tid; j < n_sub; j += SEARCH_WARPS * 32) {
+#pragma unroll
+                for (int w = 0; w < W; w++) ok = ok && ((tw[(size_t)j * 2 * W + w] ^ tw[(size_t)j * 2 * W + W + w]) == mask.w[w]);
+            }
+            tile_reg = __syncthreads_and(ok) != 0;
+        }
+        const bool regular = q_regular && tile_reg;
+        const bool tile100 = cta100 && tile_reg;                               /* (cta100 implies q_regular in every warp) */
         if (tile100) {                                                         /* windows of this tile: win[j] nibble t = fourth-word bits of subfingerprint j + t */
             const uint32_t n_sub = first_subfp(c1) - s_lo;
             for (uint32_t j = tid; j < n_sub; j += SEARCH_WARPS * 32) {
@@ -361,7 +375,11 @@ search_fast_kernel(const uint32_t* __restrict__ db, const float2* __restrict__ m
                     }
                     uint32_t h[W];
 #pragma unroll
-                    for (int w = 0; w < W; w++) h[w] = hit_word2(p1[w], m1[w], qp[i][w], qm[i][w]);            /* FP.m:162-167 */
+                    for (int w = 0; w < W; w++) {
+                        uint32_t qw = qp[i][w];
+                        if (CAN100 && w == 2 && cta100) qw ^= qp[i][0] ^ qp[i][1];                          /* (the register holds q0 ^ q1 ^ q2 for the 100-rank form) */
+                        h[w] = hit_word2(p1[w], m1[w], qw, qm[i][w]);                                       /* FP.m:162-167 */
+                    }
                     sum = __fadd_rn(sum, ratio_exact(popc_words<W>(h), fposs, rcp));
                 }
                 const float mean = mean_exact<CQ>(sum);                        /* FP.m:144 */

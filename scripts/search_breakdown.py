@@ -6,9 +6,14 @@ import torch
 import lbaudiodetective_b200 as lb
 
 s = torch.cuda.Stream(); torch.cuda.set_stream(s); st = s.cuda_stream
-def run(n_db, c_db, n_q, c_q, reps=10):
+def run(n_db, c_db, n_q, c_q, reps=10, silent_every=0):
+    """silent_every = m: every m-th clip (beyond the query sources) loses the sign bits of one subfingerprint — an empty-rank code as
+    digital silence produces — so the database as a whole is no longer 'regular' and only the tiles without such a clip keep the short form"""
     db = lb.Database(200)
     codes = torch.empty((n_db, c_db, 8), dtype=torch.int32, device="cuda"); lb.random_codes_device(codes.data_ptr(), n_db * c_db, 200, seed=5, stream=st)
+    if silent_every:
+        with torch.cuda.stream(s):
+            codes[n_q + 1::silent_every, c_db // 2, :] = 0
     db.add_packed_device(codes.data_ptr(), n_db, c_db, producer_stream=st)
     q = codes[:n_q, :c_q].contiguous(); sc = torch.empty((n_q, 10), dtype=torch.float32, device="cuda"); ix = torch.empty((n_q, 10), dtype=torch.int32, device="cuda")
     for _ in range(3):
@@ -22,10 +27,12 @@ def run(n_db, c_db, n_q, c_q, reps=10):
     n, k_ms = db.kernel_timing(enable=False, reset=True)
     total = e0.elapsed_time(e1) / reps; kern = k_ms / n
     cmp_ = n_q * n_db * (c_db - c_q + 1) * c_q
-    print("db %8d x %2d, %4d queries x %d: search kernel %.3f ms (%.3e compares/s), whole call %.3f ms, merge + gaps %.3f ms" % (n_db, c_db, n_q, c_q, kern, cmp_ / kern * 1e3, total, total - kern), flush=True)
+    print(("silent 1/%d " % silent_every if silent_every else "") + "db %8d x %2d, %4d queries x %d: search kernel %.3f ms (%.3e compares/s), whole call %.3f ms, merge + gaps %.3f ms" % (n_db, c_db, n_q, c_q, kern, cmp_ / kern * 1e3, total, total - kern), flush=True)
     assert (ix[:, 0].cpu() == torch.arange(n_q, dtype=torch.int32)).all()
 
-if os.environ.get("BREAKDOWN_SHORT"):
+if os.environ.get("BREAKDOWN_MIXED"):
+    run(250000, 19, 1000, 6); run(250000, 19, 1000, 6, silent_every=1000); run(250000, 19, 1000, 6, silent_every=100); run(250000, 19, 1000, 6, silent_every=1)
+elif os.environ.get("BREAKDOWN_SHORT"):
     run(250000, 19, 1000, 6); run(125000, 19, 1000, 6)
 else:
     for n in (1000000, 500000, 250000, 125000):

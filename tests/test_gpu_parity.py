@@ -496,6 +496,36 @@ def test_search_regular_codes_short_form(lb, checker, L, q_count, db_count):
     assert np.array_equal(full2, want2)
 
 
+@pytest.mark.parametrize("q_count,db_count", [(6, 19), (4, 9), (5, 5)])
+def test_search_100_rank_form_and_mixed_databases(lb, checker, q_count, db_count):
+    """L = 200 with regular queries in every warp of the CTA: the two-POPC form (tile words rewritten in place, leftover bits through the
+    window words).  Then the same queries against a database in which a few clips carry empty or doubled ranks: regularity is decided
+    per landed tile, so those tiles take the general form and all others keep the short one — every score must still equal the oracle's."""
+    rng = np.random.default_rng(900 + q_count + db_count); L = 200
+    n_db, n_q, k = 1500, 96, 10
+    dbb = rank_sign_codes(rng, n_db, db_count, L)
+    qb = rank_sign_codes(rng, n_q, q_count, L)
+    for q in range(0, n_q, 2):
+        c = int(rng.integers(0, n_db)); o = int(rng.integers(0, db_count - q_count + 1))
+        qb[q] = dbb[c, o:o + q_count]; flip = rng.random((q_count, L // 2)) < 0.05
+        qb[q, :, 0::2] ^= flip.astype(np.uint8); qb[q, :, 1::2] ^= flip.astype(np.uint8)     # sign flips keep the codes regular
+    def check(bits):
+        db = lb.Database(L); db.add_packed(lb.pack_booleans(bits))
+        sc, idx, full = db.search_packed(lb.pack_booleans(qb), k, all_scores=True)
+        want, _ = checker.search(bits, qb, L)
+        assert np.array_equal(full, want)
+        order = np.lexsort((np.arange(n_db)[None, :].repeat(n_q, 0), -want.astype(np.float64)), axis=1)[:, :k]
+        assert np.array_equal(idx, order.astype(np.uint32)) and np.array_equal(sc, np.take_along_axis(want, order, axis=1))
+    check(dbb)
+    mixed = dbb.copy()
+    for c in rng.choice(n_db, 12, replace=False):
+        j = int(rng.integers(0, db_count)); r = int(rng.integers(0, L // 2))
+        mixed[c, j, 2 * r] = mixed[c, j, 2 * r + 1] = int(rng.integers(0, 2))          # a '00' or a '11' rank (the last four ranks included)
+    mixed[7, :, :] = 0                                                                  # digital silence: no rank carries a bit
+    mixed[8, 0, 198] = mixed[8, 0, 199] = 0
+    check(mixed)
+
+
 def test_search_ragged_database_and_fingerprint_api(lb, checker):
     rng = np.random.default_rng(12); L = 200
     counts = rng.integers(0, 25, size=120)
