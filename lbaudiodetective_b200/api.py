@@ -99,6 +99,21 @@ def load_library(build_if_missing: bool = True):
         "LBAudioDetectiveFingerprintAddPackedSubfingerprints": (C.c_int32, [vp, vp, u32]),
         "LBAudioDetectiveFingerprintToString": (C.c_size_t, [vp, C.c_char_p, C.c_size_t]),
         "LBAudioDetectiveFingerprintFromString": (vp, [C.c_char_p]),
+        "LBAudioDetectiveFrameNew": (vp, [u32]),
+        "LBAudioDetectiveFrameDispose": (None, [vp]),
+        "LBAudioDetectiveFrameCopy": (vp, [vp]),
+        "LBAudioDetectiveFrameGetNumberOfRows": (u32, [vp]),
+        "LBAudioDetectiveFrameGetRow": (P(f32), [vp, u32]),
+        "LBAudioDetectiveFrameGetValue": (f32, [vp, u32, u32]),
+        "LBAudioDetectiveFrameFull": (u8, [vp]),
+        "LBAudioDetectiveFrameSetRow": (u8, [vp, vp, u32, u32]),
+        "LBAudioDetectiveFrameDecompose": (None, [vp]),
+        "LBAudioDetectiveFrameFingerprintSize": (C.c_size_t, [vp]),
+        "LBAudioDetectiveFrameFingerprintLength": (u32, [vp]),
+        "LBAudioDetectiveFrameExtractFingerprint": (None, [vp, u32, vp]),
+        "LBAudioDetectiveFrameEqualToFrame": (u8, [vp, vp]),
+        "LBAudioDetectiveFrameDecomposeStatus": (C.c_int32, [vp]),
+        "LBAudioDetectiveFrameExtractFingerprintStatus": (C.c_int32, [vp, u32, vp]),
         "LBAudioDetectiveDatabaseNew": (vp, [u32]),
         "LBAudioDetectiveDatabaseDispose": (C.c_int32, [vp]),
         "LBAudioDetectiveDatabaseGetNumberOfClips": (u32, [vp]),
@@ -293,6 +308,67 @@ class Fingerprint:
     def from_string(s):
         ref = lib().LBAudioDetectiveFingerprintFromString(s.encode())
         return Fingerprint(_ref=ref) if ref else None
+
+
+class Frame:
+    """ctypes mirror of LBAudioDetectiveFrameRef (include/LBAudioDetectiveFrame.h; LBAudioDetectiveFrame.h:27-162 upstream)."""
+
+    def __init__(self, max_rows, _ref=None):
+        self._L = lib()
+        self.ref = _ref if _ref is not None else self._L.LBAudioDetectiveFrameNew(max_rows)
+
+    def dispose(self):
+        if getattr(self, "ref", None):
+            self._L.LBAudioDetectiveFrameDispose(self.ref); self.ref = None
+
+    def __del__(self):
+        try:
+            self.dispose()
+        except Exception:
+            pass
+
+    @staticmethod
+    def from_array(a):
+        a = np.asarray(a, np.float32); f = Frame(a.shape[0])
+        for r in range(a.shape[0]):
+            assert f.set_row(a[r], r)
+        return f
+
+    def copy(self): return Frame(0, _ref=self._L.LBAudioDetectiveFrameCopy(self.ref))
+    @property
+    def rows(self): return int(self._L.LBAudioDetectiveFrameGetNumberOfRows(self.ref))
+    @property
+    def fingerprint_length(self): return int(self._L.LBAudioDetectiveFrameFingerprintLength(self.ref))
+    @property
+    def fingerprint_size(self): return int(self._L.LBAudioDetectiveFrameFingerprintSize(self.ref))
+    @property
+    def row_length(self): return self.fingerprint_length // (2 * self.rows) if self.rows else 0
+    def full(self): return bool(self._L.LBAudioDetectiveFrameFull(self.ref))
+    def value(self, r, c): return float(self._L.LBAudioDetectiveFrameGetValue(self.ref, r, c))
+    def equal(self, other): return bool(self._L.LBAudioDetectiveFrameEqualToFrame(self.ref, other.ref))
+
+    def set_row(self, row, index, count=None):
+        row = _f32(row)
+        return bool(self._L.LBAudioDetectiveFrameSetRow(self.ref, _ptr(row), index, len(row) if count is None else count))
+
+    def row(self, r):
+        p = self._L.LBAudioDetectiveFrameGetRow(self.ref, r)
+        return np.ctypeslib.as_array(p, shape=(self.row_length,)).copy()
+
+    def array(self):
+        return np.stack([self.row(r) for r in range(self.rows)]) if self.rows else np.zeros((0, 0), np.float32)
+
+    def decompose(self, status=False):
+        if status:
+            return int(self._L.LBAudioDetectiveFrameDecomposeStatus(self.ref))
+        self._L.LBAudioDetectiveFrameDecompose(self.ref)
+
+    def extract_fingerprint(self, wavelets, status=False):
+        out = np.zeros(2 * wavelets, np.uint8)
+        if status:
+            return int(self._L.LBAudioDetectiveFrameExtractFingerprintStatus(self.ref, wavelets, _ptr(out))), out
+        self._L.LBAudioDetectiveFrameExtractFingerprint(self.ref, wavelets, _ptr(out))
+        return out
 
 
 class Detective:

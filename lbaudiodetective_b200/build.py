@@ -9,8 +9,8 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libLBAudioDetectiveCUDA.so")
 OBJ = os.path.join(PKG, "build")
 
-CU = ["lbad_extract.cu", "lbad_search.cu", "lbad_synth.cu", "lbad_resample.cu"]
-C = ["LBAudioDetective.c", "LBAudioDetectiveFingerprint.c", "LBAudioDetectiveDatabase.c", "lbad_support.c", "lbad_resample_design.c"]
+CU = ["lbad_extract.cu", "lbad_search.cu", "lbad_synth.cu", "lbad_resample.cu", "lbad_frame.cu"]
+C = ["LBAudioDetective.c", "LBAudioDetectiveFingerprint.c", "LBAudioDetectiveDatabase.c", "LBAudioDetectiveFrame.c", "lbad_support.c", "lbad_resample_design.c"]
 HDRS = ["lbad_cuda.h", "lbad_common.cuh", "lbad_math.cuh", "lbad_host.h"]
 
 NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",

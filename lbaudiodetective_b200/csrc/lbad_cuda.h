@@ -63,6 +63,12 @@ int  lbadcu_extract_host_i16(lbadcu_plan* p, const int16_t* h_pcm, uint32_t n_cl
 /* Haar + top-t + pack on device images [count][128][B] (generic kernel). */
 int  lbadcu_transform_images_host(lbadcu_plan* p, const float* h_images, uint32_t count, float* h_haar, uint32_t* h_words);
 
+/* ---- the Frame API's two computing functions on frames of any shape (lbad_frame.cu; current device) ---- */
+/* h_a: [rows][cols] in host memory, transformed in place (LBAudioDetectiveFrame.m:113-153) */
+int  lbadcu_frame_decompose_host(float* h_a, uint32_t rows, uint32_t cols);
+/* h_a: n coefficients in flat order; h_out: 2t bytes, 1 where LBAudioDetectiveFrame.m:182-190 sets TRUE, 0 elsewhere */
+int  lbadcu_frame_extract_host(const float* h_a, uint32_t n, uint32_t t, unsigned char* h_out);
+
 /* ---- recording-rate -> processing-rate conversion (include/LBAudioDetectiveResample.h) ---- */
 #define LBAD_RS_PHASES 64u
 typedef struct {

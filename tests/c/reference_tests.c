@@ -8,6 +8,8 @@
  *   testFingerprintingWithBlurredBirds    (suffix _blu1/_blu2 : crop + 1.58 % / 3.16 % noise)            -> asserted here
  *   testFingerprintVersatility            Tests.m:119-139                                                -> asserted
  *   testFingerprintComparison             Tests.m:141-155                                                -> asserted
+ *   testHaarWaveletDecomposition          Tests.m:157-176  (upstream prints the 3 x 4 result)            -> asserted against the values the
+ *                                                                                                           compiled reference prints
  *   (addition) the same identification from 44.1 kHz PCM, the rate of the bundled recordings, through the recording-rate entry
  *   points that stand in for ExtAudioFile's client-format conversion (LBAudioDetective.m:229)             -> asserted
  *
@@ -19,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "LBAudioDetective.h"
+#include "LBAudioDetectiveFrame.h"
 #include "LBAudioDetectiveResample.h"
 #include "LBAudioDetectiveSupport.h"
 
@@ -131,6 +134,32 @@ int main(void) {
         printf("  -> %d/%d identified\n", identified, BIRDS);
         CHECK(identified == BIRDS, "a crop of a 44.1 kHz recording must identify its bird");
         for (int b = 0; b < BIRDS; b++) { LBAudioDetectiveFingerprintDispose(fa[b]); LBAudioDetectiveFingerprintDispose(fc[b]); }
+    }
+    /* Tests.m:157-176 through the Frame API, as written upstream; the expected values are what the compiled reference prints */
+    {
+        LBAudioDetectiveFrameRef frame = LBAudioDetectiveFrameNew(3);
+        Float32 row1[] = {538, 940, 1940, 1794};
+        Float32 row2[] = {1840, 213, 1320, 913};
+        Float32 row3[] = {192, 591, 492, 1921};
+        LBAudioDetectiveFrameSetRow(frame, row1, 0, 4);
+        LBAudioDetectiveFrameSetRow(frame, row2, 1, 4);
+        LBAudioDetectiveFrameSetRow(frame, row3, 2, 4);
+        LBAudioDetectiveFrameDecompose(frame);
+        static const double expected[3][4] = {{969.385559, -248.623199, 176.813522, 79.818680}, {94.509499, -211.880875, -292.860931, -37.672104},
+                                              {461.302917, -235.270218, -81.445541, -291.693420}};
+        int close = 1;
+        for (int r = 0; r < 3; r++) {
+            for (int c = 0; c < 4; c++) {
+                printf("%f\t", LBAudioDetectiveFrameGetValue(frame, r, c));
+                close = close && fabs(LBAudioDetectiveFrameGetValue(frame, r, c) - expected[r][c]) < 5e-7 * fabs(expected[r][c]) + 1e-6;      /* six printed decimals */
+            }
+            printf("\n");
+        }
+        CHECK(close, "Haar decomposition of the 3 x 4 frame");
+        Boolean signs[8] = {0};
+        LBAudioDetectiveFrameExtractFingerprint(frame, 4, signs);                          /* ranks: 969.39 (+), 461.30 (+), -292.86, -291.69 */
+        CHECK(signs[0] && !signs[1] && signs[2] && !signs[3] && !signs[4] && signs[5] && !signs[6] && signs[7], "signs of the four largest coefficients");
+        LBAudioDetectiveFrameDispose(frame);
     }
     CHECK(LBAudioDetectiveDispose(detective) == noErr, "Dispose");                          /* Tests.m:46 */
     CHECK(LBAudioDetectiveDispose(NULL) == kLBAudioDetectiveArgumentInvalid, "Dispose(NULL)");

@@ -13,6 +13,8 @@ Tolerances (BASELINE.json north_star):
 """
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 from oracle.oracle import Cfg
@@ -407,6 +409,35 @@ def test_compare_pcm_equals_its_three_steps(lb, port):
     d2 = lb.Detective(); d2.set_window_size(1024); d2.set_subfingerprint_length(100)
     f = [d2.process_pcm(clips[n]) for n in (55120, 165360)]
     assert np.float32(d2.compare_pcm(clips[55120], clips[165360], 0)) == np.float32(f[0].compare(f[1], 100))
+
+
+def test_frame_api_on_the_gpu(lb, ref, kat):
+    """The reference's Frame API (include/LBAudioDetectiveFrame.h): Decompose and ExtractFingerprint run on the GPU for any shape and
+    must equal the compiled reference's own functions bit for bit — first the 3 x 4 frame of the reference's Haar test
+    (LBAudioDetectiveTests.m:158-172; expected values in tests/golden/kat.json came from the compiled reference), then shapes that are
+    not powers of two (integer halving leaves their tails alone, Frame.m:144-152), ties, zeros and every wavelet count up to the size."""
+    f = lb.Frame.from_array(np.array(kat["haar_3x4_in"], np.float32))
+    f.decompose()
+    assert np.array_equal(f.array(), np.array(kat["haar_3x4_out"], np.float32).reshape(3, 4))
+    rng = np.random.default_rng(77)
+    for rows, cols in ((3, 4), (1, 1), (1, 9), (5, 7), (128, 32), (17, 64), (100, 33), (2, 300)):
+        img = (rng.standard_normal((rows, cols)) * 10.0 ** rng.integers(-3, 4)).astype(np.float32)
+        if rows * cols > 8:
+            img.flat[3] = 0.0; img.flat[5] = -img.flat[4]                      # a zero and a pair of equal magnitudes survive as ties in the input
+        fr = lb.Frame.from_array(img)
+        assert fr.decompose(status=True) == 0
+        want = ref.haar(img)
+        assert np.array_equal(fr.array(), want), (rows, cols)
+        coef = want.copy()
+        coef.flat[::3] = np.round(coef.flat[::3], 1)                           # plenty of exactly equal magnitudes, zeros included
+        fc = lb.Frame.from_array(coef)
+        n = rows * cols
+        for t in sorted({1, min(n, 2), n // 2, n - 1, n} - {0}):
+            assert np.array_equal(fc.extract_fingerprint(t), ref.extract_bits(coef, t)), (rows, cols, t)
+    # like upstream, ExtractFingerprint only ever sets TRUE: what the caller's buffer held stays
+    out = np.ones(8, np.uint8); fr = lb.Frame.from_array(np.array([[1.0, -2.0], [0.0, 3.0]], np.float32))
+    lb.lib().LBAudioDetectiveFrameExtractFingerprint(fr.ref, 4, out.ctypes.data_as(C.c_void_p))
+    assert out.all()
 
 
 def rank_sign_codes(rng, n, count, L):

@@ -133,6 +133,43 @@ def test_fingerprint_container(lb):
     lb.lib().LBAudioDetectiveFingerprintDispose(None)                      # no-op (FP.m:29-31)
 
 
+def test_frame_container_matches_reference(lb, ref):
+    """The host side of the Frame API (include/LBAudioDetectiveFrame.h) against the compiled reference's own functions
+    (LBAudioDetectiveFrame.m:22-105, :155-161, :193-210), call by call."""
+    R = ref.ref
+    for name, res in (("LBAudioDetectiveFrameNew", C.c_void_p), ("LBAudioDetectiveFrameCopy", C.c_void_p), ("LBAudioDetectiveFrameGetNumberOfRows", C.c_uint32),
+                      ("LBAudioDetectiveFrameGetValue", C.c_float), ("LBAudioDetectiveFrameFull", C.c_ubyte), ("LBAudioDetectiveFrameSetRow", C.c_ubyte),
+                      ("LBAudioDetectiveFrameFingerprintSize", C.c_size_t), ("LBAudioDetectiveFrameFingerprintLength", C.c_uint32),
+                      ("LBAudioDetectiveFrameEqualToFrame", C.c_ubyte), ("LBAudioDetectiveFrameDispose", None)):
+        getattr(R, name).restype = res
+    vp = C.c_void_p
+    rng = np.random.default_rng(5)
+    rows = [rng.standard_normal(n).astype(np.float32) for n in (7, 5, 9, 5)]
+    mine = lb.Frame(3); theirs = vp(R.LBAudioDetectiveFrameNew(C.c_uint32(3)))
+    for i, row in enumerate(rows):                                            # the fourth SetRow meets a full frame on both sides
+        want = R.LBAudioDetectiveFrameSetRow(theirs, row.ctypes.data_as(vp), C.c_uint32(min(i, 2)), C.c_uint32(len(row))) if i < 3 else \
+            R.LBAudioDetectiveFrameSetRow(theirs, row.ctypes.data_as(vp), C.c_uint32(2), C.c_uint32(len(row)))
+        got = mine.set_row(row, min(i, 2))
+        assert bool(want) == got
+        assert mine.rows == R.LBAudioDetectiveFrameGetNumberOfRows(theirs)
+        assert mine.full() == bool(R.LBAudioDetectiveFrameFull(theirs))
+        assert mine.fingerprint_length == R.LBAudioDetectiveFrameFingerprintLength(theirs)
+        assert mine.fingerprint_size == R.LBAudioDetectiveFrameFingerprintSize(theirs)
+    assert mine.rows == 3 and mine.row_length == 5                             # the shortest row sets the row length (Frame.m:96-101)
+    for r in range(3):
+        for c in range(5):
+            assert mine.value(r, c) == R.LBAudioDetectiveFrameGetValue(theirs, C.c_uint32(r), C.c_uint32(c))
+    cp = mine.copy(); tcp = vp(R.LBAudioDetectiveFrameCopy(theirs))
+    assert cp.equal(mine) and mine.equal(cp) and bool(R.LBAudioDetectiveFrameEqualToFrame(theirs, tcp))
+    other = lb.Frame.from_array(np.stack([r[:5] for r in rows[:3]]) + np.float32(1))
+    assert not other.equal(mine) and not lb.Frame(3).equal(mine)
+    assert np.array_equal(cp.array(), np.stack([r[:5] for r in rows[:3]]))
+    R.LBAudioDetectiveFrameDispose(theirs); R.LBAudioDetectiveFrameDispose(tcp)
+    lb.lib().LBAudioDetectiveFrameDispose(None)                                # no-op, as upstream (Frame.m:34-36)
+    empty = lb.Frame(4)
+    assert empty.rows == 0 and not empty.full() and empty.fingerprint_length == 0 and lb.Frame(0).full()
+
+
 def test_packed_layout_round_trip(lb):
     rng = np.random.default_rng(1)
     for L, W in ((100, 2), (128, 2), (130, 4), (200, 4), (256, 4), (400, 8), (512, 8)):
@@ -194,3 +231,9 @@ def test_no_gpu_means_loud_failure(lb):
     assert st == lb.DEVICE_UNAVAILABLE
     with pytest.raises(lb.LBADError):
         lb.DatabaseGroup(200, [0, 0])
+    # the Frame API's two computing functions: status -7001, the frame and the output stay as they were
+    img = np.arange(12, dtype=np.float32).reshape(3, 4); f = lb.Frame.from_array(img)
+    assert f.decompose(status=True) == lb.DEVICE_UNAVAILABLE and np.array_equal(f.array(), img)
+    f.decompose(); assert np.array_equal(f.array(), img)
+    st, bits = f.extract_fingerprint(3, status=True)
+    assert st == lb.DEVICE_UNAVAILABLE and not bits.any() and not f.extract_fingerprint(3).any()
