@@ -491,6 +491,32 @@ def main():
                               "hbm_gbs": db_bytes * ((args.queries + 127) // 128) / (search["kernel_ms"] * 1e-3) / 1e9, "hbm_frac": db_bytes * ((args.queries + 127) // 128) / (search["kernel_ms"] * 1e-3) / 1e9 / hbm_peak}
     if search is not None:
         del db
+    if search is not None and world == 1 and rank == 0 and not args.no_config5:
+        # codes with empty ranks (what digital silence produces) cannot take the short compare forms.  Regularity is decided per landed tile:
+        # a database with one such clip in 1,000 stays near the full rate, one made of nothing else runs the general form throughout.
+        irregular = {"workload": "1,000 x 6-subfp queries vs 250,000 x 19-subfp clips; 'silent' clips lose the sign bits of one subfingerprint"}
+        n_i = 250000
+        for label, every in (("regular", 0), ("one_silent_clip_in_1000", 1000), ("every_clip_silent (general form)", 1)):
+            dbi = lb.Database(200)
+            ci = torch.empty((n_i, SUBFPS, 8), dtype=torch.int32, device="cuda")
+            lb.random_codes_device(ci.data_ptr(), n_i * SUBFPS, 200, seed=DB_SEED, stream=stream)
+            qi = ci[:args.queries, 3:9].contiguous()
+            if every:
+                ci[args.queries + 1::every, SUBFPS // 2, :] = 0
+            dbi.add_packed_device(ci.data_ptr(), n_i, SUBFPS, producer_stream=stream)
+            si = torch.empty((args.queries, 10), dtype=torch.float32, device="cuda"); ii = torch.empty((args.queries, 10), dtype=torch.int32, device="cuda")
+            for _ in range(2):
+                dbi.search_device(qi.data_ptr(), args.queries, 6, 10, si.data_ptr(), ii.data_ptr(), stream=stream)
+            dbi.kernel_timing(enable=True, reset=True)
+            for _ in range(5):
+                dbi.search_device(qi.data_ptr(), args.queries, 6, 10, si.data_ptr(), ii.data_ptr(), stream=stream)
+            torch.cuda.synchronize()
+            nki, msi = dbi.kernel_timing(enable=False, reset=True)
+            assert (ii[:, 0].cpu() == torch.arange(args.queries, dtype=torch.int32)).all()
+            rate = args.queries * n_i * 84 / (msi / max(nki, 1) * 1e-3)
+            irregular[label] = {"kernel_ms": msi / max(nki, 1), "compares_per_s": rate, "frac_of_4_popc_bound": rate / (mb["popc_gops"] * 1e9 / 4.0) if mb else None}
+            del dbi, ci, qi
+        search["irregular_codes"] = irregular
 
     # ---- config 5 shape (rank 0, one GPU): 1,000 one-subfingerprint (3 s) queries against 100,000 clips of 5 subfingerprints (9 s), 5 offsets each ----
     config5 = None

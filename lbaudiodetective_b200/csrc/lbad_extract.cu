@@ -661,7 +661,10 @@ static FusedSmemLayout fused_layout(uint32_t span_floats, bool aos = false, uint
 /* GROUPS = 2: ONE CTA per SM of two independent 8-warp groups, each working on its own frame (own sample buffer, mbarrier and named
  * barrier) and sharing only the twiddle tables: what two CTAs per SM did, in the shared memory that two CTAs with pair scratch no longer fit. */
 template <int R, bool STATIC_RANGE, bool CARRY, int SUBS = 1, bool AOS = false, int GROUPS = 1>
-__global__ void __launch_bounds__(FUSED_THREADS * GROUPS, GROUPS == 1 ? 2 : 1)
+#ifndef LBAD_G1_MINBLOCKS
+#define LBAD_G1_MINBLOCKS 2          /* A/B knob: 1 lets the one-group variants use up to 255 registers */
+#endif
+__global__ void __launch_bounds__(FUSED_THREADS * GROUPS, GROUPS == 1 ? LBAD_G1_MINBLOCKS : 1)
 bands_fused_kernel(const float* __restrict__ pcm, float* __restrict__ images, const float4* __restrict__ g_tw1, const float4* __restrict__ g_tw2,
                    const Geo g, const BandTable bt, const FusedSmemLayout L, const uint32_t span_floats,
                    const uint32_t total_frames, const int use_tma, const uint32_t frame0) {

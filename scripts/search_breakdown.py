@@ -30,7 +30,10 @@ def run(n_db, c_db, n_q, c_q, reps=10, silent_every=0):
     print(("silent 1/%d " % silent_every if silent_every else "") + "db %8d x %2d, %4d queries x %d: search kernel %.3f ms (%.3e compares/s), whole call %.3f ms, merge + gaps %.3f ms" % (n_db, c_db, n_q, c_q, kern, cmp_ / kern * 1e3, total, total - kern), flush=True)
     assert (ix[:, 0].cpu() == torch.arange(n_q, dtype=torch.int32)).all()
 
-if os.environ.get("BREAKDOWN_MIXED"):
+if os.environ.get("BREAKDOWN_SIZES"):                      # BREAKDOWN_SIZES=65536,131072,...: the fixed cost of a search (intercept over the database size)
+    for n in os.environ["BREAKDOWN_SIZES"].split(","):
+        run(int(n), 19, 1000, 6)
+elif os.environ.get("BREAKDOWN_MIXED"):
     run(250000, 19, 1000, 6); run(250000, 19, 1000, 6, silent_every=1000); run(250000, 19, 1000, 6, silent_every=100); run(250000, 19, 1000, 6, silent_every=1)
 elif os.environ.get("BREAKDOWN_SHORT"):
     run(250000, 19, 1000, 6); run(125000, 19, 1000, 6)

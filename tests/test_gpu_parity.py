@@ -527,13 +527,13 @@ def test_search_regular_codes_short_form(lb, checker, L, q_count, db_count):
     assert np.array_equal(full2, want2)
 
 
-@pytest.mark.parametrize("q_count,db_count", [(6, 19), (4, 9), (5, 5)])
-def test_search_100_rank_form_and_mixed_databases(lb, checker, q_count, db_count):
+@pytest.mark.parametrize("q_count,db_count,n_q", [(6, 19, 96), (4, 9, 40), (5, 5, 20), (6, 19, 33)])
+def test_search_100_rank_form_and_mixed_databases(lb, checker, q_count, db_count, n_q):
     """L = 200 with regular queries in every warp of the CTA: the two-POPC form (tile words rewritten in place, leftover bits through the
     window words).  Then the same queries against a database in which a few clips carry empty or doubled ranks: regularity is decided
     per landed tile, so those tiles take the general form and all others keep the short one — every score must still equal the oracle's."""
-    rng = np.random.default_rng(900 + q_count + db_count); L = 200
-    n_db, n_q, k = 1500, 96, 10
+    rng = np.random.default_rng(900 + q_count + db_count + n_q); L = 200      # (40 / 20 queries: the CTA's spare warps share each tile's clips)
+    n_db, k = 1500, 10
     dbb = rank_sign_codes(rng, n_db, db_count, L)
     qb = rank_sign_codes(rng, n_q, q_count, L)
     for q in range(0, n_q, 2):
