@@ -38,6 +38,6 @@ bits[5, 3, 10:12] = 0; bits[600, :, :] = 0
 mix = lb.Database(200); mix.add_packed(lb.pack_booleans(bits)); sc7, idx7 = mix.search_packed(lb.pack_booleans(bits[:40, 2:8]), k=3)
 assert (idx6[:, 0] == np.arange(40)).all() and (idx7[:5, 0] == np.arange(5)).all()
 # the Frame API's kernels on a frame that is not a power of two in either direction
-fr = lb.Frame.from_array(rs.standard_normal((37, 19)).astype(np.float32)); fr.decompose(); fb = fr.extract_fingerprint(50)
+frm = lb.Frame.from_array(rs.standard_normal((37, 19)).astype(np.float32)); frm.decompose(); fb = frm.extract_fingerprint(50)
 f0 = lb.Fingerprint(200); f0.add_packed(w[0]); f1 = lb.Fingerprint(200); f1.add_packed(w[1])
 print("ok", int(fb.sum()), tb.shape, r1.shape, r2.shape, fr.count, w.shape, (bits != bits2).sum(), b3.shape, sc[:, 0], f0.compare(f1, 200), lb.merge_topk(np.stack([sc, sc]), np.stack([idx, idx + 10]))[1][0])
