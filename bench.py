@@ -467,6 +467,44 @@ def main():
             store.set("lbad_group_leg_done", "1")
         barrier()
 
+    # ---- extraction over all the GPUs of the job through the C-ABI alone: ONE process (rank 0), one detective per device
+    #      (LBAudioDetectiveSetDevice), one call (LBAudioDetectiveProcessPCMBatchSharded), pinned host buffers in, words out ----
+    sharded_api = None
+    if world > 1 and not args.no_group and not args.no_e2e:
+        barrier()
+        store = dist.distributed_c10d._get_default_store()      # the other ranks wait on the host: rank 0 is about to use their GPUs
+        if rank != 0:
+            store.wait(["lbad_sharded_extract_done"])
+        if rank == 0:
+            try:
+                per = min(2000, args.clips); n_all = per * world
+                gen = torch.empty((n_all, CLIP_LEN), dtype=torch.float32, device="cuda")
+                lb.synthesize_device(gen.data_ptr(), n_all, CLIP_LEN, CLIP_LEN, first_clip_id=0, stream=stream)
+                h_pcm = torch.empty((n_all, CLIP_LEN), dtype=torch.float32, pin_memory=True); h_pcm.copy_(gen)
+                ref_words = torch.zeros((per, SUBFPS, 8), dtype=torch.int32, device="cuda")
+                det.process_batch_device(gen.data_ptr(), per, CLIP_LEN, CLIP_LEN, ref_words.data_ptr(), stream); torch.cuda.synchronize()
+                del gen; torch.cuda.empty_cache()
+                h_words = torch.zeros((n_all, SUBFPS, 8), dtype=torch.int32, pin_memory=True)
+                dets = []
+                for dev in range(world):
+                    dd = lb.Detective(); assert dd.set_device(dev) == 0; dets.append(dd)
+                call = lambda: lb.Detective.process_batch_sharded(dets, None, out_words=h_words.data_ptr(), host_ptr=h_pcm.data_ptr(), n_clips=n_all, clip_len=CLIP_LEN, clip_stride=CLIP_LEN)
+                call()
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    call()
+                dts = time.perf_counter() - t0
+                same = bool(np.array_equal(h_words.numpy()[:per], ref_words.cpu().numpy()))
+                sharded_api = {"api": "LBAudioDetectiveProcessPCMBatchSharded: one process, one detective per GPU (%d), one call; pinned host buffers in, words out" % world,
+                               "clips": n_all, "value": n_all * CLIP_LEN / SR / 3600.0 * args.steps / dts, "unit": "audio-hours/s", "ms_per_step": 1e3 * dts / args.steps,
+                               "pcie_gbs_aggregate": n_all * CLIP_LEN * 4 * args.steps / dts / 1e9, "first_shard_equals_one_detective": same,
+                               "words_sha256": hashlib.sha256(h_words.numpy().tobytes()).hexdigest()}
+                del dets, h_pcm, h_words, ref_words
+            except Exception as ex_:
+                sharded_api = {"error": "%s: %s" % (type(ex_).__name__, str(ex_)[:200])}
+            store.set("lbad_sharded_extract_done", "1")
+        barrier()
+
     if search is not None and world == 1:
         # the server-style call: ONE query against the whole database (lane-per-clip kernel + two-level merge), device-timed
         d_sc = torch.empty((args.queries, 10), dtype=torch.float32, device="cuda"); d_idx = torch.empty((args.queries, 10), dtype=torch.int32, device="cuda")
@@ -576,6 +614,8 @@ def main():
         config1 = {"workload": "configs[0]: compare two synthetic 10 s clips through the compare-audio path (LBAudioDetectiveComparePCM), one call at a time, host buffers",
                    "us_per_call": gpu_us, "match": got, "reference_ms_per_call": cpu_ms, "reference_match": want, "reference_kind": chk.kind, "reference_cores": 1,
                    "reference_fft": "f64 definition (parity mode)"}
+    if sharded_api is not None and e2e is not None:
+        e2e["sharded_api"] = sharded_api
     line = {"metric": "audio-hours/s fingerprinted", "value": value, "unit": "audio-hours/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: batch fingerprint extraction of %d synthetic 30 s clips per GPU (FFT+band-energy kernel, then Haar+top-t+pack kernel)" % n_clips,

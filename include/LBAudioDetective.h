@@ -96,6 +96,17 @@ LBAD_API OSStatus LBAudioDetectiveProcessPCMBatch(LBAudioDetectiveRef inDetectiv
 /* Same for signed 16-bit PCM (the reference's recording format, essay p.VI ff.): half the bytes cross PCIe; samples are converted on
  * the device as x / 32768, exactly what a float32 client format would have delivered. */
 LBAD_API OSStatus LBAudioDetectiveProcessPCMBatchInt16(LBAudioDetectiveRef inDetective, const SInt16* inSamples, UInt32 inNumberOfClips, UInt64 inFramesPerClip, UInt64 inClipStride, UInt32* outWords);
+/* Which CUDA device a detective computes on.  By default (-1) it is the device that is current when the first computing call builds the
+ * detective's device plan; a caller that does not use the CUDA runtime itself chooses one here (0 <= inDevice < number of devices;
+ * kLBAudioDetectiveArgumentInvalid otherwise).  Changing the device drops the plan, like any other setter. */
+LBAD_API OSStatus LBAudioDetectiveSetDevice(LBAudioDetectiveRef inDetective, int inDevice);
+LBAD_API int LBAudioDetectiveGetDevice(LBAudioDetectiveRef inDetective);
+/* LBAudioDetectiveProcessPCMBatch over SEVERAL detectives at once — normally one per GPU (LBAudioDetectiveSetDevice), all configured
+ * alike: the clips are cut into contiguous shares, every detective fingerprints its share on its own host thread, nothing is exchanged
+ * between the GPUs (extraction shards by clip).  outWords as above, in clip order; the result does not depend on the
+ * number of detectives.  Returns the first error of any share; kLBAudioDetectiveArgumentInvalid if the configurations differ. */
+LBAD_API OSStatus LBAudioDetectiveProcessPCMBatchSharded(const LBAudioDetectiveRef* inDetectives, UInt32 inNumberOfDetectives, const Float32* inSamples, UInt32 inNumberOfClips,
+                                                         UInt64 inFramesPerClip, UInt64 inClipStride, UInt32* outWords);
 /* Same, but inSamples and outWords are DEVICE pointers on the detective's device and the work is enqueued on
  * inStream (a cudaStream_t, NULL = the detective's own stream) without synchronising.  Calls on one detective share device scratch
  * (the spectral images between the two kernels): the library orders them on the device, so calls enqueued on different streams are

@@ -70,6 +70,9 @@ def load_library(build_if_missing: bool = True):
         "LBAudioDetectiveGetBandTable": (C.c_int32, [vp, vp, vp, vp]),
         "LBAudioDetectiveProcessPCMBatch": (C.c_int32, [vp, vp, u32, u64, u64, vp]),
         "LBAudioDetectiveProcessPCMBatchInt16": (C.c_int32, [vp, vp, u32, u64, u64, vp]),
+        "LBAudioDetectiveSetDevice": (C.c_int32, [vp, C.c_int]),
+        "LBAudioDetectiveGetDevice": (C.c_int, [vp]),
+        "LBAudioDetectiveProcessPCMBatchSharded": (C.c_int32, [P(vp), u32, vp, u32, u64, u64, vp]),
         "LBAudioDetectiveProcessPCMBatchDevice": (C.c_int32, [vp, vp, u32, u64, u64, vp, vp]),
         "LBAudioDetectiveProcessPCMStages": (C.c_int32, [vp, vp, u64, vp, vp, vp, u8]),
         "LBAudioDetectiveProcessPCMBatchStages": (C.c_int32, [vp, vp, u32, u64, u64, vp, vp, vp, u8]),
@@ -458,6 +461,24 @@ class Detective:
         if out_words is None:
             out_words = np.zeros((n_clips, n, 2 * W), np.uint32)
         _check(self._L.LBAudioDetectiveProcessPCMBatch(self.ref, _ptr(pcm2d), n_clips, clip_len, clip_len, _ptr(out_words)), "LBAudioDetectiveProcessPCMBatch")
+        return out_words
+
+    def set_device(self, device): return int(self._L.LBAudioDetectiveSetDevice(self.ref, device))
+    @property
+    def device(self): return int(self._L.LBAudioDetectiveGetDevice(self.ref))
+
+    @staticmethod
+    def process_batch_sharded(detectives, pcm2d, out_words=None, host_ptr=None, n_clips=None, clip_len=None, clip_stride=None):
+        """LBAudioDetectiveProcessPCMBatchSharded: one batch over several detectives (one per GPU), each on its own host thread."""
+        d0 = detectives[0]
+        refs = (C.c_void_p * len(detectives))(*[d.ref for d in detectives])
+        if host_ptr is None:
+            pcm2d = np.ascontiguousarray(pcm2d, np.float32); n_clips, clip_len = pcm2d.shape; clip_stride = clip_len; host_ptr = pcm2d.ctypes.data
+        count = d0.subfingerprints_for_length(clip_len); W = words_per_plane(d0.subfingerprint_length)
+        if out_words is None:
+            out_words = np.zeros((n_clips, count, 2 * W), np.uint32)
+        out_ptr = out_words if isinstance(out_words, int) else out_words.ctypes.data
+        _check(d0._L.LBAudioDetectiveProcessPCMBatchSharded(refs, len(detectives), host_ptr, n_clips, clip_len, clip_stride, out_ptr), "LBAudioDetectiveProcessPCMBatchSharded")
         return out_words
 
     def process_batch_int16(self, pcm2d):

@@ -4,6 +4,7 @@
  * touches a sample.  Reference: /root/reference/LBAudioDetective/LBAudioDetective.m (m:) and .h (h:).
  */
 #include "lbad_host.h"
+#include <pthread.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -32,6 +33,7 @@ struct LBAudioDetective {
     Float64 recordingSampleRate;        /* rate of the PCM given to the ...Recorded... entry points (LBAudioDetectiveResample.h) */
     lbadcu_resampler* resampler;        /* built lazily for (recordingSampleRate, processing rate) */
     Float32* dResampled; UInt64 dResampledCapacity;     /* device scratch of ProcessRecordedPCMBatchDevice */
+    int device;                 /* CUDA device of the plan, the resampler and the scratch; -1: whichever is current when they are built */
 };
 
 static void invalidate_resampler(LBAudioDetectiveRef d) {
@@ -51,6 +53,7 @@ LBAudioDetectiveRef LBAudioDetectiveNew(void) {
     d->analysisStride = kLBAudioDetectiveDefaultAnalysisStride;
     d->pitchStepCount = kLBAudioDetectiveDefaultNumberOfPitchSteps;
     d->recordingSampleRate = 44100.0;
+    d->device = -1;
     return d;
 }
 
@@ -176,7 +179,32 @@ static OSStatus ensure_plan(LBAudioDetectiveRef d) {
     lbadcu_geometry g;
     OSStatus e = fill_geometry(d, &g, NULL);
     if (e != noErr) return e;
-    return lbad_status(lbadcu_plan_create(&g, &d->plan));
+    int prev;
+    e = lbad_status(lbadcu_push_device(d->device, &prev));
+    if (e != noErr) return e;
+    e = lbad_status(lbadcu_plan_create(&g, &d->plan));
+    lbadcu_pop_device(prev);
+    return e;
+}
+
+/* Additions: which CUDA device a detective computes on.  The default (-1) is the device that is current when the first computing call
+ * builds the device plan; a caller that does not use the CUDA runtime itself picks one here.  Changing it drops the plan. */
+OSStatus LBAudioDetectiveSetDevice(LBAudioDetectiveRef d, int inDevice) {
+    if (!d || inDevice < -1) return kLBAudioDetectiveArgumentInvalid;
+    if (inDevice >= 0) {
+        if (lbadcu_device_available() != LBAD_OK) return kLBAudioDetectiveDeviceUnavailable;
+        if (inDevice >= lbadcu_device_count()) return kLBAudioDetectiveArgumentInvalid;
+    }
+    if (inDevice != d->device) {
+        invalidate_plan(d); invalidate_resampler(d);
+        if (d->dResampled) { lbadcu_device_free(d->dResampled); d->dResampled = NULL; d->dResampledCapacity = 0; }
+        d->device = inDevice;
+    }
+    return noErr;
+}
+int LBAudioDetectiveGetDevice(LBAudioDetectiveRef d) {
+    if (!d) return -1;
+    return d->plan ? lbadcu_plan_device(d->plan) : d->device;
 }
 
 OSStatus LBAudioDetectiveCheckConfiguration(LBAudioDetectiveRef d) {
@@ -257,6 +285,45 @@ OSStatus LBAudioDetectiveProcessPCMBatch(LBAudioDetectiveRef d, const Float32* i
     return lbad_status(lbadcu_extract_host(d->plan, inSamples, nClips, framesPerClip, clipStride, outWords, NULL, NULL, 0));
 }
 
+/* one share of LBAudioDetectiveProcessPCMBatchSharded, on its own host thread */
+struct shard_job { LBAudioDetectiveRef d; const Float32* samples; UInt32 nClips; UInt64 framesPerClip, clipStride; UInt32* words; OSStatus status; };
+static void* shard_main(void* arg) {
+    struct shard_job* j = arg;
+    j->status = LBAudioDetectiveProcessPCMBatch(j->d, j->samples, j->nClips, j->framesPerClip, j->clipStride, j->words);
+    return NULL;
+}
+
+OSStatus LBAudioDetectiveProcessPCMBatchSharded(const LBAudioDetectiveRef* dets, UInt32 nDets, const Float32* inSamples, UInt32 nClips, UInt64 framesPerClip, UInt64 clipStride, UInt32* outWords) {
+    if (!dets || nDets == 0 || nDets > 64 || !inSamples || !outWords || nClips == 0 || clipStride < framesPerClip) return kLBAudioDetectiveArgumentInvalid;
+    for (UInt32 i = 0; i < nDets; i++) {
+        if (!dets[i]) return kLBAudioDetectiveArgumentInvalid;
+        if (dets[i]->windowSize != dets[0]->windowSize || dets[i]->analysisStride != dets[0]->analysisStride || dets[i]->pitchStepCount != dets[0]->pitchStepCount ||
+            dets[i]->subfingerprintLength != dets[0]->subfingerprintLength || dets[i]->processingFormat.mSampleRate != dets[0]->processingFormat.mSampleRate)
+            return kLBAudioDetectiveArgumentInvalid;
+        for (UInt32 k = 0; k < i; k++) if (dets[k] == dets[i]) return kLBAudioDetectiveArgumentInvalid;      /* a detective is not re-entrant (one per thread) */
+    }
+    if (framesPerClip < dets[0]->windowSize) return kLBAudioDetectiveArgumentInvalid;
+    const UInt64 perClip = LBAudioDetectiveGetNumberOfSubfingerprintsForLength(dets[0], framesPerClip) * 2 * lbad_words_per_plane(dets[0]->subfingerprintLength);
+    struct shard_job jobs[64]; pthread_t threads[64]; int started[64];
+    UInt32 lo = 0;
+    for (UInt32 i = 0; i < nDets; i++) {                                          /* contiguous shares that differ by at most one clip */
+        const UInt32 n = nClips / nDets + (i < nClips % nDets ? 1u : 0u);
+        jobs[i] = (struct shard_job){dets[i], inSamples + (UInt64)lo * clipStride, n, framesPerClip, clipStride, outWords + (UInt64)lo * perClip, noErr};
+        started[i] = 0;
+        if (n) {
+            if (pthread_create(&threads[i], NULL, shard_main, &jobs[i]) == 0) started[i] = 1;
+            else shard_main(&jobs[i]);                                            /* no thread to be had: the share runs here */
+        }
+        lo += n;
+    }
+    OSStatus e = noErr;
+    for (UInt32 i = 0; i < nDets; i++) {
+        if (started[i]) pthread_join(threads[i], NULL);
+        if (e == noErr && jobs[i].nClips) e = jobs[i].status;
+    }
+    return e;
+}
+
 OSStatus LBAudioDetectiveProcessPCMBatchInt16(LBAudioDetectiveRef d, const SInt16* inSamples, UInt32 nClips, UInt64 framesPerClip, UInt64 clipStride, UInt32* outWords) {
     if (!d || !inSamples || !outWords || nClips == 0 || clipStride < framesPerClip) return kLBAudioDetectiveArgumentInvalid;
     OSStatus e = ensure_plan(d);
@@ -319,7 +386,9 @@ static OSStatus ensure_resampler(LBAudioDetectiveRef d) {
     if (d->resampler) return noErr;
     lbadcu_resample_design des;
     if (lbad_resample_design_create(d->recordingSampleRate, d->processingFormat.mSampleRate, &des) != LBAD_OK) return kLBAudioDetectiveArgumentInvalid;
-    OSStatus e = lbad_status(lbadcu_resampler_create(&des, &d->resampler));
+    int prev;                                                                      /* on the plan's device (or the one chosen with LBAudioDetectiveSetDevice) */
+    OSStatus e = lbad_status(lbadcu_push_device(d->plan ? lbadcu_plan_device(d->plan) : d->device, &prev));
+    if (e == noErr) { e = lbad_status(lbadcu_resampler_create(&des, &d->resampler)); lbadcu_pop_device(prev); }
     lbad_resample_design_free(&des);
     return e;
 }
@@ -347,7 +416,9 @@ OSStatus LBAudioDetectiveProcessRecordedPCMBatchDevice(LBAudioDetectiveRef d, co
     if (d->dResampledCapacity < outStride * nClips) {
         if (d->dResampled) lbadcu_device_free(d->dResampled);
         d->dResampled = NULL; d->dResampledCapacity = 0;
-        e = lbad_status(lbadcu_device_alloc_floats(outStride * nClips, &d->dResampled));
+        int prev;
+        e = lbad_status(lbadcu_push_device(lbadcu_plan_device(d->plan), &prev));
+        if (e == noErr) { e = lbad_status(lbadcu_device_alloc_floats(outStride * nClips, &d->dResampled)); lbadcu_pop_device(prev); }
         if (e != noErr) return e;
         d->dResampledCapacity = outStride * nClips;
     }

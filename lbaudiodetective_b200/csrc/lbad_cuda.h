@@ -41,7 +41,13 @@ int  lbadcu_device_available(void);
 int  lbadcu_device_count(void);
 const char* lbadcu_last_error(void);
 
+/* make `device` current for the calling thread (device < 0: leave it) / put the previous one back */
+int  lbadcu_push_device(int device, int* prev);
+void lbadcu_pop_device(int prev);
+
+/* the plan is bound to the device that is current when it is created */
 int  lbadcu_plan_create(const lbadcu_geometry* g, lbadcu_plan** out);
+int  lbadcu_plan_device(const lbadcu_plan* p);
 void lbadcu_plan_destroy(lbadcu_plan* p);
 int  lbadcu_plan_fused_supported(const lbadcu_plan* p);
 void* lbadcu_plan_stream(lbadcu_plan* p);

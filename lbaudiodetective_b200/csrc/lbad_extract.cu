@@ -958,6 +958,20 @@ extern "C" int lbadcu_device_count(void) {
     return n;
 }
 
+/* Makes `device` current for the calling thread and reports the one that was (for lbadcu_pop_device); device < 0: nothing changes. */
+extern "C" int lbadcu_push_device(int device, int* prev) {
+    *prev = -1;
+    if (device < 0) return LBAD_OK;
+    if (lbadcu_device_available() != LBAD_OK) { set_error("no CUDA device available (this library has no CPU fallback)"); return LBAD_ERR_NODEVICE; }
+    if (device >= lbadcu_device_count()) { set_error("CUDA device %d does not exist (%d device(s))", device, lbadcu_device_count()); return LBAD_ERR_ARG; }
+    int cur = -1;
+    LBAD_CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != device) { LBAD_CUDA_TRY(cudaSetDevice(device)); *prev = cur; }
+    return LBAD_OK;
+}
+extern "C" void lbadcu_pop_device(int prev) { if (prev >= 0) cudaSetDevice(prev); }
+extern "C" int lbadcu_plan_device(const lbadcu_plan* p);
+
 static uint32_t ilog2(uint32_t v) { uint32_t l = 0; while ((1u << l) < v) l++; return l; }
 
 /* Where the two lanes of a band split it.  In round r (bands 16 r .. 16 r + 15) step i of the band sums has lane (b, h) read the
@@ -1107,6 +1121,7 @@ extern "C" void lbadcu_plan_destroy(lbadcu_plan* p) {
 }
 
 extern "C" int lbadcu_plan_fused_supported(const lbadcu_plan* p) { return p->fused_ok ? 1 : 0; }
+extern "C" int lbadcu_plan_device(const lbadcu_plan* p) { return p->device; }
 extern "C" void* lbadcu_plan_stream(lbadcu_plan* p) { return p->stream; }
 extern "C" uint64_t lbadcu_plan_launches(const lbadcu_plan* p) { return p->launches; }
 extern "C" uint32_t lbadcu_plan_timing(lbadcu_plan* p, int which, int enable, int reset, double* total_ms) {

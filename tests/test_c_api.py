@@ -57,3 +57,25 @@ def test_sharded_search_in_c(sharded_binary, figure):
     figure(r.stdout.strip().splitlines()[0] if r.stdout.strip() else r.stderr.strip())
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all checks passed" in r.stdout
+
+
+@pytest.fixture(scope="module")
+def sharded_extract_binary(tmp_path_factory, lb):
+    return compile_c(tmp_path_factory, "sharded_extract")
+
+
+def test_sharded_extract_program_links_and_reports_missing_device(sharded_extract_binary, lb):
+    if lb.device_available():
+        pytest.skip("a CUDA device is present; see the gpu test")
+    r = subprocess.run([sharded_extract_binary], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 77 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_sharded_extract_in_c(sharded_extract_binary, figure):
+    """A plain-C caller fingerprints one batch on several GPUs through the library alone: one detective per device
+    (LBAudioDetectiveSetDevice), one call (LBAudioDetectiveProcessPCMBatchSharded); same words as one detective."""
+    r = subprocess.run([sharded_extract_binary], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    figure(r.stdout.strip().splitlines()[0] if r.stdout.strip() else r.stderr.strip())
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout

@@ -411,6 +411,29 @@ def test_compare_pcm_equals_its_three_steps(lb, port):
     assert np.float32(d2.compare_pcm(clips[55120], clips[165360], 0)) == np.float32(f[0].compare(f[1], 100))
 
 
+def test_sharded_batch_equals_one_detective(lb, port):
+    """LBAudioDetectiveProcessPCMBatchSharded: the clips of one batch spread over several detectives (one per GPU where there are
+    several; here they share the devices round-robin), each on its own host thread — same words as one detective, for clip counts
+    that do not divide evenly, for fewer clips than detectives, and with a non-default geometry."""
+    pcm = np.stack([port.synth_clip(40 + i, 55120) for i in range(7)])
+    n_dev = lb.device_count()
+    for window, sublen in ((2048, 200), (1024, 100)):
+        dets = []
+        for i in range(3):
+            d = lb.Detective(); d.set_window_size(window); d.set_subfingerprint_length(sublen)
+            assert d.set_device(i % n_dev) == 0 and d.device == i % n_dev
+            dets.append(d)
+        one = lb.Detective(); one.set_window_size(window); one.set_subfingerprint_length(sublen)
+        want = one.process_batch(pcm)
+        assert np.array_equal(lb.Detective.process_batch_sharded(dets, pcm), want)
+        assert np.array_equal(lb.Detective.process_batch_sharded(dets, pcm[:2]), want[:2])
+        assert np.array_equal(lb.Detective.process_batch_sharded(dets[:1], pcm), want)
+    assert dets[0].set_device(n_dev) == lb.ARGUMENT_INVALID
+    dets[1].set_subfingerprint_length(200)
+    with pytest.raises(lb.LBADError):
+        lb.Detective.process_batch_sharded(dets, pcm)
+
+
 def test_frame_api_on_the_gpu(lb, ref, kat):
     """The reference's Frame API (include/LBAudioDetectiveFrame.h): Decompose and ExtractFingerprint run on the GPU for any shape and
     must equal the compiled reference's own functions bit for bit — first the 3 x 4 frame of the reference's Haar test

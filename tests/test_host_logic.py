@@ -231,6 +231,11 @@ def test_no_gpu_means_loud_failure(lb):
     assert st == lb.DEVICE_UNAVAILABLE
     with pytest.raises(lb.LBADError):
         lb.DatabaseGroup(200, [0, 0])
+    # device selection and the sharded batch: no device to choose, nothing computed
+    assert d.device == -1 and d.set_device(-1) == 0 and d.set_device(0) == lb.DEVICE_UNAVAILABLE and d.set_device(-2) == lb.ARGUMENT_INVALID
+    with pytest.raises(lb.LBADError) as err2:
+        lb.Detective.process_batch_sharded([lb.Detective(), lb.Detective()], np.zeros((3, 55120), np.float32))
+    assert "-7001" in str(err2.value)
     # the Frame API's two computing functions: status -7001, the frame and the output stay as they were
     img = np.arange(12, dtype=np.float32).reshape(3, 4); f = lb.Frame.from_array(img)
     assert f.decompose(status=True) == lb.DEVICE_UNAVAILABLE and np.array_equal(f.array(), img)
