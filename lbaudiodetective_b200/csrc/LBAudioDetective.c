@@ -286,10 +286,12 @@ OSStatus LBAudioDetectiveProcessPCMBatch(LBAudioDetectiveRef d, const Float32* i
 }
 
 /* one share of LBAudioDetectiveProcessPCMBatchSharded, on its own host thread */
-struct shard_job { LBAudioDetectiveRef d; const Float32* samples; UInt32 nClips; UInt64 framesPerClip, clipStride; UInt32* words; OSStatus status; };
+struct shard_job { LBAudioDetectiveRef d; const Float32* samples; UInt32 nClips; UInt64 framesPerClip, clipStride; UInt32* words; OSStatus status; char message[256]; };
 static void* shard_main(void* arg) {
     struct shard_job* j = arg;
     j->status = LBAudioDetectiveProcessPCMBatch(j->d, j->samples, j->nClips, j->framesPerClip, j->clipStride, j->words);
+    j->message[0] = 0;
+    if (j->status != noErr) snprintf(j->message, sizeof j->message, "%s", lbadcu_last_error());      /* the error text lives in this thread */
     return NULL;
 }
 
@@ -308,7 +310,7 @@ OSStatus LBAudioDetectiveProcessPCMBatchSharded(const LBAudioDetectiveRef* dets,
     UInt32 lo = 0;
     for (UInt32 i = 0; i < nDets; i++) {                                          /* contiguous shares that differ by at most one clip */
         const UInt32 n = nClips / nDets + (i < nClips % nDets ? 1u : 0u);
-        jobs[i] = (struct shard_job){dets[i], inSamples + (UInt64)lo * clipStride, n, framesPerClip, clipStride, outWords + (UInt64)lo * perClip, noErr};
+        jobs[i] = (struct shard_job){dets[i], inSamples + (UInt64)lo * clipStride, n, framesPerClip, clipStride, outWords + (UInt64)lo * perClip, noErr, {0}};
         started[i] = 0;
         if (n) {
             if (pthread_create(&threads[i], NULL, shard_main, &jobs[i]) == 0) started[i] = 1;
@@ -319,7 +321,7 @@ OSStatus LBAudioDetectiveProcessPCMBatchSharded(const LBAudioDetectiveRef* dets,
     OSStatus e = noErr;
     for (UInt32 i = 0; i < nDets; i++) {
         if (started[i]) pthread_join(threads[i], NULL);
-        if (e == noErr && jobs[i].nClips) e = jobs[i].status;
+        if (e == noErr && jobs[i].nClips && jobs[i].status != noErr) { e = jobs[i].status; lbadcu_set_last_error(jobs[i].message); }
     }
     return e;
 }

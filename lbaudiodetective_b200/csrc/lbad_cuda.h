@@ -39,7 +39,8 @@ typedef struct lbadcu_plan lbadcu_plan;
 /* 0 if a CUDA device is usable */
 int  lbadcu_device_available(void);
 int  lbadcu_device_count(void);
-const char* lbadcu_last_error(void);
+const char* lbadcu_last_error(void);          /* per thread */
+void lbadcu_set_last_error(const char* msg);
 
 /* make `device` current for the calling thread (device < 0: leave it) / put the previous one back */
 int  lbadcu_push_device(int device, int* prev);

@@ -944,6 +944,8 @@ struct lbadcu_plan {
 };
 
 extern "C" const char* lbadcu_last_error(void) { return g_err; }
+/* the message of another thread's failure, handed to the thread that reports it (the buffer is per thread) */
+extern "C" void lbadcu_set_last_error(const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg ? msg : ""); }
 
 extern "C" int lbadcu_device_available(void) {
     int n = 0;
