@@ -477,7 +477,7 @@ def main():
             store.wait(["lbad_sharded_extract_done"])
         if rank == 0:
             try:
-                per = min(2000, args.clips); n_all = per * world
+                per = min(5000, args.clips); n_all = per * world          # enough chunks (about 300 clips each) for the shares to follow the links' speeds
                 gen = torch.empty((n_all, CLIP_LEN), dtype=torch.float32, device="cuda")
                 lb.synthesize_device(gen.data_ptr(), n_all, CLIP_LEN, CLIP_LEN, first_clip_id=0, stream=stream)
                 h_pcm = torch.empty((n_all, CLIP_LEN), dtype=torch.float32, pin_memory=True); h_pcm.copy_(gen)
@@ -495,7 +495,7 @@ def main():
                     call()
                 dts = time.perf_counter() - t0
                 same = bool(np.array_equal(h_words.numpy()[:per], ref_words.cpu().numpy()))
-                sharded_api = {"api": "LBAudioDetectiveProcessPCMBatchSharded: one process, one detective per GPU (%d), one call; pinned host buffers in, words out" % world,
+                sharded_api = {"api": "LBAudioDetectiveProcessPCMBatchSharded: one process, one detective per GPU (%d), one call; chunks taken from a shared cursor as each GPU's buffers drain; pinned host buffers in, words out" % world,
                                "clips": n_all, "value": n_all * CLIP_LEN / SR / 3600.0 * args.steps / dts, "unit": "audio-hours/s", "ms_per_step": 1e3 * dts / args.steps,
                                "pcie_gbs_aggregate": n_all * CLIP_LEN * 4 * args.steps / dts / 1e9, "first_shard_equals_one_detective": same,
                                "words_sha256": hashlib.sha256(h_words.numpy().tobytes()).hexdigest()}

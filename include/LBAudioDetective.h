@@ -102,9 +102,10 @@ LBAD_API OSStatus LBAudioDetectiveProcessPCMBatchInt16(LBAudioDetectiveRef inDet
 LBAD_API OSStatus LBAudioDetectiveSetDevice(LBAudioDetectiveRef inDetective, int inDevice);
 LBAD_API int LBAudioDetectiveGetDevice(LBAudioDetectiveRef inDetective);
 /* LBAudioDetectiveProcessPCMBatch over SEVERAL detectives at once — normally one per GPU (LBAudioDetectiveSetDevice), all configured
- * alike: the clips are cut into contiguous shares, every detective fingerprints its share on its own host thread, nothing is exchanged
- * between the GPUs (extraction shards by clip).  outWords as above, in clip order; the result does not depend on the
- * number of detectives.  Returns the first error of any share; kLBAudioDetectiveArgumentInvalid if the configurations differ. */
+ * alike: every detective's host thread runs the upload / kernel / download pipeline of LBAudioDetectiveProcessPCMBatch on the same
+ * batch and takes its chunks (about 190 MB of PCM) from one shared cursor as its buffers drain — a GPU behind a slower host link ends
+ * up with a smaller share —, nothing is exchanged between the GPUs (extraction shards by
+ * clip).  outWords as above, in clip order; the result does not depend on the number of detectives or on who took what.  Returns the first error of any share; kLBAudioDetectiveArgumentInvalid if the configurations differ. */
 LBAD_API OSStatus LBAudioDetectiveProcessPCMBatchSharded(const LBAudioDetectiveRef* inDetectives, UInt32 inNumberOfDetectives, const Float32* inSamples, UInt32 inNumberOfClips,
                                                          UInt64 inFramesPerClip, UInt64 inClipStride, UInt32* outWords);
 /* Same, but inSamples and outWords are DEVICE pointers on the detective's device and the work is enqueued on

@@ -285,11 +285,14 @@ OSStatus LBAudioDetectiveProcessPCMBatch(LBAudioDetectiveRef d, const Float32* i
     return lbad_status(lbadcu_extract_host(d->plan, inSamples, nClips, framesPerClip, clipStride, outWords, NULL, NULL, 0));
 }
 
-/* one share of LBAudioDetectiveProcessPCMBatchSharded, on its own host thread */
-struct shard_job { LBAudioDetectiveRef d; const Float32* samples; UInt32 nClips; UInt64 framesPerClip, clipStride; UInt32* words; OSStatus status; char message[256]; };
+/* LBAudioDetectiveProcessPCMBatchSharded: every detective's host thread runs the chunked upload / kernel / download pipeline of
+ * LBAudioDetectiveProcessPCMBatch on the SAME batch, taking its chunks (about 190 MB of PCM) from one shared cursor as its buffers
+ * drain.  The GPUs of one box do not reach the host at the same speed — on the 8-GPU B200 box of this pool four links deliver 23 GB/s
+ * and four 35 GB/s when all copy at once — so equal shares would wait for the slowest link; this way the shares follow the links. */
+struct shard_job { LBAudioDetectiveRef d; const Float32* samples; UInt32 nClips; UInt64 framesPerClip, clipStride; UInt32* words; uint64_t* cursor; OSStatus status; char message[256]; };
 static void* shard_main(void* arg) {
     struct shard_job* j = arg;
-    j->status = LBAudioDetectiveProcessPCMBatch(j->d, j->samples, j->nClips, j->framesPerClip, j->clipStride, j->words);
+    j->status = lbad_status(lbadcu_extract_host_shared(j->d->plan, j->samples, j->nClips, j->framesPerClip, j->clipStride, j->words, j->cursor));
     j->message[0] = 0;
     if (j->status != noErr) snprintf(j->message, sizeof j->message, "%s", lbadcu_last_error());      /* the error text lives in this thread */
     return NULL;
@@ -305,23 +308,18 @@ OSStatus LBAudioDetectiveProcessPCMBatchSharded(const LBAudioDetectiveRef* dets,
         for (UInt32 k = 0; k < i; k++) if (dets[k] == dets[i]) return kLBAudioDetectiveArgumentInvalid;      /* a detective is not re-entrant (one per thread) */
     }
     if (framesPerClip < dets[0]->windowSize) return kLBAudioDetectiveArgumentInvalid;
-    const UInt64 perClip = LBAudioDetectiveGetNumberOfSubfingerprintsForLength(dets[0], framesPerClip) * 2 * lbad_words_per_plane(dets[0]->subfingerprintLength);
+    for (UInt32 i = 0; i < nDets; i++) { OSStatus e = ensure_plan(dets[i]); if (e != noErr) return e; }
+    uint64_t cursor = 0;                                                          /* clips handed out so far */
     struct shard_job jobs[64]; pthread_t threads[64]; int started[64];
-    UInt32 lo = 0;
-    for (UInt32 i = 0; i < nDets; i++) {                                          /* contiguous shares that differ by at most one clip */
-        const UInt32 n = nClips / nDets + (i < nClips % nDets ? 1u : 0u);
-        jobs[i] = (struct shard_job){dets[i], inSamples + (UInt64)lo * clipStride, n, framesPerClip, clipStride, outWords + (UInt64)lo * perClip, noErr, {0}};
-        started[i] = 0;
-        if (n) {
-            if (pthread_create(&threads[i], NULL, shard_main, &jobs[i]) == 0) started[i] = 1;
-            else shard_main(&jobs[i]);                                            /* no thread to be had: the share runs here */
-        }
-        lo += n;
+    for (UInt32 i = 0; i < nDets; i++) {
+        jobs[i] = (struct shard_job){dets[i], inSamples, nClips, framesPerClip, clipStride, outWords, &cursor, noErr, {0}};
+        started[i] = pthread_create(&threads[i], NULL, shard_main, &jobs[i]) == 0;
+        if (!started[i]) shard_main(&jobs[i]);                                    /* no thread to be had: this detective works here (and may take everything) */
     }
     OSStatus e = noErr;
     for (UInt32 i = 0; i < nDets; i++) {
         if (started[i]) pthread_join(threads[i], NULL);
-        if (e == noErr && jobs[i].nClips && jobs[i].status != noErr) { e = jobs[i].status; lbadcu_set_last_error(jobs[i].message); }
+        if (e == noErr && jobs[i].status != noErr) { e = jobs[i].status; lbadcu_set_last_error(jobs[i].message); }
     }
     return e;
 }

@@ -936,6 +936,7 @@ struct lbadcu_plan {
     int stage_mode = -1;      /* -1 auto, 0 plain loads, 1 TMA (env LBAD_STAGE=ldg|tma) */
     bool transform_generic = false;      /* env LBAD_TRANSFORM=generic: lbadcu_transform_images_host uses the any-geometry Haar/select kernel */
     uint32_t slab_frames_cap = 1u << 18;
+    uint32_t chunk_clips_override = 0;   /* env LBAD_CHUNK_CLIPS: clips per upload chunk of the host pipeline (tests: many chunks from few clips); 0 = by size */
     struct { const void* fn; uint32_t smem; int per_sm; } occ_cache[8] = {};      /* per kernel variant: opt-in shared memory set, resident CTAs per SM */
     int force_subs = 0;                  /* env LBAD_SUBFRAMES=1|2|8: pin the CTA iterations per frame (tests); 0 = by frame count */
     int pair_transpose = -1;             /* env LBAD_TRANSPOSE=pairs|components: the AOS / component-wise transposition of the carried kernel; -1 = default (pairs) */
@@ -1104,6 +1105,7 @@ extern "C" int lbadcu_plan_create(const lbadcu_geometry* geo, lbadcu_plan** out)
     if (const char* gp = getenv("LBAD_GROUPS")) p->force_groups = atoi(gp) == 1 ? 1 : atoi(gp) == 2 ? 2 : 0;
     if (const char* tp = getenv("LBAD_TRANSPOSE")) p->pair_transpose = strcmp(tp, "pairs") == 0 ? 1 : strcmp(tp, "components") == 0 ? 0 : -1;
     if (const char* tf = getenv("LBAD_TRANSFORM")) p->transform_generic = strcmp(tf, "generic") == 0;
+    if (const char* cc = getenv("LBAD_CHUNK_CLIPS")) { const unsigned long v = strtoul(cc, nullptr, 10); if (v >= 1 && v <= (1u << 20)) p->chunk_clips_override = (uint32_t)v; }
     if (const char* sf = getenv("LBAD_SLAB_FRAMES")) { const unsigned long v = strtoul(sf, nullptr, 10); if (v >= 1 && v <= (1u << 18)) p->slab_frames_cap = (uint32_t)v; }
     *out = guard.release();
     return LBAD_OK;
@@ -1316,8 +1318,11 @@ __global__ void i16_to_f32_kernel(const int16_t* __restrict__ in, float* __restr
  * kernels of chunk i and the D2H of chunk i-1 overlap (they do when the caller's buffers are pinned).  Each chunk
  * buffer has its own spectral-image scratch (slots 1..3), because the streams run concurrently.
  * sample_bytes: 4 = float32 PCM, 2 = signed 16-bit PCM (converted on the device as x / 32768, which is exact). */
+/* cursor (optional): a clip counter SHARED by several plans working on the same batch from different host threads (one plan per GPU,
+ * lbadcu_extract_host_shared): a plan takes its next chunk from it only when the buffer that chunk goes to has been drained, so every
+ * GPU keeps three chunks in flight and the batch divides itself by how fast each GPU gets its data — the host links of one box differ. */
 static int extract_host_impl(lbadcu_plan* p, const void* h_pcm_v, int sample_bytes, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
-                             uint32_t* h_words, float* h_images, float* h_haar, int mode) {
+                             uint32_t* h_words, float* h_images, float* h_haar, int mode, uint64_t* cursor = nullptr) {
     if (!p || !h_pcm_v || !h_words || n_clips == 0) return LBAD_ERR_ARG;
     if (clip_len < p->g.window) return LBAD_ERR_ARG;
     LBAD_ON_DEVICE(p->device);
@@ -1328,6 +1333,7 @@ static int extract_host_impl(lbadcu_plan* p, const void* h_pcm_v, int sample_byt
     const size_t img_per_clip = (size_t)frames_per_clip * LBAD_ROWS_PER_FRAME * p->g.bands;
     const uint64_t clip_pad = (clip_len + 7) & ~7ull;                  /* device clip stride: keeps every clip 16-byte aligned in both sample formats */
     uint64_t clips_per_chunk = (48ull << 20) / clip_pad;                /* ~192 MB of float PCM per chunk */
+    if (p->chunk_clips_override) clips_per_chunk = p->chunk_clips_override;
     if (clips_per_chunk < 1) clips_per_chunk = 1;
     if (clips_per_chunk > n_clips) clips_per_chunk = n_clips;
     const size_t need_pcm = (size_t)clips_per_chunk * clip_pad, need_words = (size_t)clips_per_chunk * words_per_clip;
@@ -1350,10 +1356,13 @@ static int extract_host_impl(lbadcu_plan* p, const void* h_pcm_v, int sample_byt
     if (h_haar) LBAD_CUDA_TRY(d_haar.alloc((size_t)clips_per_chunk * img_per_clip));
     int rc = LBAD_OK;
     uint32_t chunk = 0;
-    for (uint64_t c0 = 0; c0 < n_clips && rc == LBAD_OK; c0 += clips_per_chunk, chunk++) {
-        const uint32_t nc = (uint32_t)((n_clips - c0) < clips_per_chunk ? (n_clips - c0) : clips_per_chunk);
+    for (uint64_t own = 0;; own += clips_per_chunk, chunk++) {
         const int b = (int)(chunk % (uint32_t)nbuf);
         cudaStream_t s = nbuf == 1 ? p->stream : p->copy_streams[b];
+        if (cursor && chunk >= (uint32_t)nbuf) LBAD_CUDA_TRY(cudaStreamSynchronize(s));      /* shared batch: another chunk only once this buffer's last one is through */
+        const uint64_t c0 = cursor ? __atomic_fetch_add(cursor, clips_per_chunk, __ATOMIC_RELAXED) : own;
+        if (c0 >= n_clips) break;
+        const uint32_t nc = (uint32_t)((n_clips - c0) < clips_per_chunk ? (n_clips - c0) : clips_per_chunk);
         void* d_in = sample_bytes == 2 ? static_cast<void*>(p->d_chunk_i16[b]) : static_cast<void*>(p->d_chunk_pcm[b]);
         const char* src = h_pcm + c0 * clip_stride * sample_bytes;
         /* one contiguous copy when the host layout already has the device stride — up to the last clip's last SAMPLE, not its padded end:
@@ -1380,6 +1389,12 @@ static int extract_host_impl(lbadcu_plan* p, const void* h_pcm_v, int sample_byt
 extern "C" int lbadcu_extract_host(lbadcu_plan* p, const float* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
                                    uint32_t* h_words, float* h_images, float* h_haar, int mode) {
     return extract_host_impl(p, h_pcm, 4, n_clips, clip_len, clip_stride, h_words, h_images, h_haar, mode);
+}
+
+/* the same batch shared between several plans (see extract_host_impl): every caller passes the whole batch and the same zero-initialised cursor */
+extern "C" int lbadcu_extract_host_shared(lbadcu_plan* p, const float* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride, uint32_t* h_words, uint64_t* cursor) {
+    if (!cursor) return LBAD_ERR_ARG;
+    return extract_host_impl(p, h_pcm, 4, n_clips, clip_len, clip_stride, h_words, nullptr, nullptr, 0, cursor);
 }
 
 extern "C" int lbadcu_extract_host_i16(lbadcu_plan* p, const int16_t* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride, uint32_t* h_words) {

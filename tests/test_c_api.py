@@ -75,7 +75,8 @@ def test_sharded_extract_program_links_and_reports_missing_device(sharded_extrac
 def test_sharded_extract_in_c(sharded_extract_binary, figure):
     """A plain-C caller fingerprints one batch on several GPUs through the library alone: one detective per device
     (LBAudioDetectiveSetDevice), one call (LBAudioDetectiveProcessPCMBatchSharded); same words as one detective."""
-    r = subprocess.run([sharded_extract_binary], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    # two clips per upload chunk (a test knob read when a plan is built), so that the seven clips really are divided between the detectives
+    r = subprocess.run([sharded_extract_binary], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, env={**os.environ, "LBAD_CHUNK_CLIPS": "2"})
     figure(r.stdout.strip().splitlines()[0] if r.stdout.strip() else r.stderr.strip())
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all checks passed" in r.stdout

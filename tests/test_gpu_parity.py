@@ -411,13 +411,16 @@ def test_compare_pcm_equals_its_three_steps(lb, port):
     assert np.float32(d2.compare_pcm(clips[55120], clips[165360], 0)) == np.float32(f[0].compare(f[1], 100))
 
 
-def test_sharded_batch_equals_one_detective(lb, port):
+def test_sharded_batch_equals_one_detective(lb, port, monkeypatch):
     """LBAudioDetectiveProcessPCMBatchSharded: the clips of one batch spread over several detectives (one per GPU where there are
-    several; here they share the devices round-robin), each on its own host thread — same words as one detective, for clip counts
-    that do not divide evenly, for fewer clips than detectives, and with a non-default geometry."""
+    several; here they share the devices round-robin), each on its own host thread taking chunks from a shared cursor — same words as
+    one detective, with one clip, two clips or the whole batch per chunk (LBAD_CHUNK_CLIPS pins the chunk size, read when a plan is
+    built), for fewer clips than detectives, and with a non-default geometry."""
     pcm = np.stack([port.synth_clip(40 + i, 55120) for i in range(7)])
     n_dev = lb.device_count()
-    for window, sublen in ((2048, 200), (1024, 100)):
+    for window, sublen, chunk in ((2048, 200, "1"), (2048, 200, "2"), (2048, 200, None), (1024, 100, "1")):
+        if chunk: monkeypatch.setenv("LBAD_CHUNK_CLIPS", chunk)
+        else: monkeypatch.delenv("LBAD_CHUNK_CLIPS", raising=False)
         dets = []
         for i in range(3):
             d = lb.Detective(); d.set_window_size(window); d.set_subfingerprint_length(sublen)
@@ -428,6 +431,7 @@ def test_sharded_batch_equals_one_detective(lb, port):
         assert np.array_equal(lb.Detective.process_batch_sharded(dets, pcm), want)
         assert np.array_equal(lb.Detective.process_batch_sharded(dets, pcm[:2]), want[:2])
         assert np.array_equal(lb.Detective.process_batch_sharded(dets[:1], pcm), want)
+    monkeypatch.delenv("LBAD_CHUNK_CLIPS", raising=False)
     assert dets[0].set_device(n_dev) == lb.ARGUMENT_INVALID
     dets[1].set_subfingerprint_length(200)
     with pytest.raises(lb.LBADError):
