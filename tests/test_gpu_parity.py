@@ -822,15 +822,18 @@ def test_calls_on_different_streams_are_ordered(lb, port):
         assert torch.equal(sc, res[0][0]) and torch.equal(ix, res[0][1])
 
 
-@pytest.mark.parametrize("L,q_count,db_count,n_q", [(200, 1, 5, 100), (100, 2, 6, 40), (200, 6, 19, 70)])
-def test_threshold_pass_changes_nothing(lb, checker, monkeypatch, L, q_count, db_count, n_q):
-    """Databases of 65,536 clips and more are searched in two passes — the top k of a sample first, whose k-th score then keeps clips
+@pytest.mark.parametrize("L,q_count,db_count,n_q,silent", [(200, 1, 5, 100, 0), (100, 2, 6, 40, 0), (200, 6, 19, 70, 0), (200, 6, 19, 70, 37), (200, 4, 5, 33, 501)])
+def test_threshold_pass_changes_nothing(lb, checker, monkeypatch, L, q_count, db_count, n_q, silent):
+    """(silent > 0: the same with empty-rank subfingerprints sprinkled over the database.)
+    Databases of 65,536 clips and more are searched in two passes — the top k of a sample first, whose k-th score then keeps clips
     below it out of the per-chunk lists.  The result must be the one of the single pass, ties included (short codes and noisy excerpts
     make plenty of equal scores), and equal the oracle's on the queries checked."""
     rng = np.random.default_rng(900 + L + q_count)
     n_db, k = 70000, 10
     dbb = rank_sign_codes(rng, n_db, db_count, L)
     dbb[1000:1200] = dbb[0:200]                                             # exact duplicates: equal scores, the lower clip index must win
+    if silent:                                                              # every silent-th clip loses the bits of one subfingerprint: a mixed database,
+        dbb[2000::silent, db_count // 2, :] = 0                             # regular tiles keep the short compare forms, the others take the general one
     src = rng.integers(0, n_db, n_q)
     qb = np.stack([dbb[c, 1:1 + q_count] for c in src]).copy()
     flip = rng.random(qb.shape[:2] + (L // 2,)) < 0.1
