@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32)
 search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ offsets, const uint32_t n_clips, const uint32_t clip_base,
                   const uint32_t* __restrict__ clip_ids, const uint32_t* __restrict__ qwords, const uint32_t n_q, const uint32_t cq, const uint32_t pairs, const int k,
                   const uint32_t clips_per_warp, float* __restrict__ part_sc, uint32_t* __restrict__ part_id, float* __restrict__ all_scores,
-                  const uint32_t total_warps) {
+                  const uint32_t total_warps, const int db_regular) {
     const int lane = threadIdx.x & 31;
     const uint32_t gw = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5);
     if (gw >= total_warps) return;
@@ -529,6 +529,16 @@ search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
             qw[i][w] = i < cq ? (__ldg(qwords + ((size_t)q * cq + i) * 2 * W + w) & mask.w[w % W]) : 0u;
         }
         __syncwarp();
+        /* Regular codes on both sides (one sign bit on every one of the first `pairs` ranks: what extraction produces; the database was
+         * checked when it was appended, the query is checked here): M = ~P on those ranks, possible = pairs, and a rank hits iff the P bits
+         * agree — the M plane is neither loaded nor compared, `possible` and its reciprocal are constants.  Same scores, bit for bit. */
+        bool short_form = db_regular != 0;
+        if (short_form) {
+            for (uint32_t i = 0; i < cq; i++)
+#pragma unroll
+                for (int w = 0; w < W; w++) short_form = short_form && ((qw[i][w] ^ qw[i][W + w]) == mask.w[w]);      /* (warp-uniform: every lane reads the same words) */
+        }
+        const float fpairs = small_uint_to_float(pairs), rcp_pairs = pairs ? __frcp_rn(fpairs) : 0.0f;
         float tsc = -1.0f; uint32_t tid = EMPTY_IDX;                           /* lane r < k: entry r of the warp's list, best first */
         for (uint32_t c0 = c_begin; c0 < c_end; c0 += 32) {
             const uint32_t c = c0 + lane;
@@ -545,26 +555,42 @@ search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
                     if constexpr (W >= 4) {                                     /* subfingerprints are 8 W bytes apart: 16-byte aligned planes for W = 4, 8 */
 #pragma unroll
                         for (int w = 0; w < W; w += 4) {
-                            const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + w)), b = __ldg(reinterpret_cast<const uint4*>(src + W + w));
-                            p[w] = a.x; p[w + 1] = a.y; p[w + 2] = a.z; p[w + 3] = a.w; m[w] = b.x; m[w + 1] = b.y; m[w + 2] = b.z; m[w + 3] = b.w;
+                            const uint4 a = __ldg(reinterpret_cast<const uint4*>(src + w));
+                            p[w] = a.x; p[w + 1] = a.y; p[w + 2] = a.z; p[w + 3] = a.w;
+                            if (!short_form) { const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + W + w)); m[w] = b.x; m[w + 1] = b.y; m[w + 2] = b.z; m[w + 3] = b.w; }
                         }
                     } else {
-                        const uint2 a = __ldg(reinterpret_cast<const uint2*>(src)), b = __ldg(reinterpret_cast<const uint2*>(src + W));
-                        p[0] = a.x; p[1] = a.y; m[0] = b.x; m[1] = b.y;
+                        const uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
+                        p[0] = a.x; p[1] = a.y;
+                        if (!short_form) { const uint2 b = __ldg(reinterpret_cast<const uint2*>(src + W)); m[0] = b.x; m[1] = b.y; }
                     }
                 };
                 uint32_t np[W], nm[W];
+#pragma unroll
+                for (int w = 0; w < W; w++) nm[w] = 0u;
                 if (cd) load_words(0, np, nm);
                 for (uint32_t j = 0; j < cd; j++) {
                     uint32_t dp[W], dm[W], cover[W];
 #pragma unroll
                     for (int w = 0; w < W; w++) { dp[w] = np[w]; dm[w] = nm[w]; }
                     if (j + 1 < cd) load_words(j + 1, np, nm);
+                    float r[FEW_MAX_CQ];
+                    if (short_form) {                                           /* warp-uniform */
+#pragma unroll
+                        for (uint32_t i = 0; i < FEW_MAX_CQ; i++) {
+                            r[i] = 0.0f;
+                            if (i < cq) {
+                                uint32_t x[W];
+#pragma unroll
+                                for (int w = 0; w < W; w++) x[w] = (dp[w] ^ qw[i][w]) & mask.w[w];               /* ranks whose P bits differ */
+                                r[i] = ratio_exact(pairs - popc_words<W>(x), fpairs, rcp_pairs);                  /* hits / possible with possible = pairs */
+                            }
+                        }
+                    } else {
 #pragma unroll
                     for (int w = 0; w < W; w++) { dp[w] &= mask.w[w]; dm[w] &= mask.w[w]; cover[w] = dp[w] | dm[w]; }
                     const uint32_t possible = popc_words<W>(cover);            /* FP.m:159-160 */
                     const float fposs = small_uint_to_float(possible), rcp = possible ? __frcp_rn(fposs) : 0.0f;
-                    float r[FEW_MAX_CQ];
 #pragma unroll
                     for (uint32_t i = 0; i < FEW_MAX_CQ; i++) {
                         r[i] = 0.0f;
@@ -574,6 +600,7 @@ search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
                             for (int w = 0; w < W; w++) h[w] = hit_word2(dp[w], dm[w], qw[i][w], qw[i][W + w]);  /* FP.m:162-167 */
                             r[i] = ratio_exact(popc_words<W>(h), fposs, rcp);   /* FP.m:171-175 */
                         }
+                    }
                     }
                     /* offset j - i gets its term number i: in decreasing i, so that ring[i - 1] is still the sum of terms 0 .. i - 1 */
 #pragma unroll
@@ -927,9 +954,9 @@ extern "C" int lbadcu_db_search_device(lbadcu_db* db, const uint32_t* d_q, uint3
 #define LBAD_GEN(WW) launch_generic<WW>(db, blocks, smem_gen, s, d_q, n_q, cq, pairs, (int)k, n_qgroups, cpc, all, total_warps)
         if (few) {
             const uint32_t fblocks = (n_chunks + SEARCH_WARPS - 1) / SEARCH_WARPS;
-            if (W == 2) search_few_kernel<2><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, all, n_chunks);
-            else if (W == 4) search_few_kernel<4><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, all, n_chunks);
-            else search_few_kernel<8><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, all, n_chunks);
+            if (W == 2) search_few_kernel<2><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, all, n_chunks, db->regular ? 1 : 0);
+            else if (W == 4) search_few_kernel<4><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, all, n_chunks, db->regular ? 1 : 0);
+            else search_few_kernel<8><<<fblocks, SEARCH_WARPS * 32, 0, s>>>(db->d_words, db->d_offsets, n_clips, db->base, db->ids_ptr(), d_q, n_q, cq, pairs, (int)k, cpc, db->d_part_sc, db->d_part_id, all, n_chunks, db->regular ? 1 : 0);
         } else if (fast) {
 #define LBAD_FAST_W(WW) switch (cq) { case 1: LBAD_FAST(WW, 1); break; case 2: LBAD_FAST(WW, 2); break; case 3: LBAD_FAST(WW, 3); break; \
                                       case 4: LBAD_FAST(WW, 4); break; case 5: LBAD_FAST(WW, 5); break; default: LBAD_FAST(WW, 6); break; }

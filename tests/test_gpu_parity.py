@@ -526,6 +526,29 @@ def test_few_query_kernel_bit_exact(lb, checker, L, q_count, db_count, rng_len, 
         assert np.array_equal(idx2[0], o2.astype(np.uint32)) and np.array_equal(sc2[0], want2[o2]) and idx2[0, 0] == 17
 
 
+@pytest.mark.parametrize("L,q_count,db_count,rng_len,n_q", [(200, 6, 19, 0, 1), (200, 6, 19, 77, 4), (200, 1, 5, 0, 8), (100, 3, 7, 0, 3), (400, 2, 9, 300, 5)])
+def test_few_query_kernel_regular_short_form(lb, checker, L, q_count, db_count, rng_len, n_q):
+    """The lane-per-clip kernel on a database of regular codes: queries that are regular too take the short form (P planes only, possible =
+    the range), decided per query — the last query here carries a '00' rank and runs the general form in the same launch.  Whole score
+    matrix and top-k against the oracle, also with a shortened comparison range."""
+    rng = np.random.default_rng(1300 + L + q_count + db_count + rng_len + n_q)
+    n_db, k = 900, 10
+    dbb = rank_sign_codes(rng, n_db, db_count, L)
+    qb = rank_sign_codes(rng, n_q, q_count, L)
+    for q in range(n_q):
+        c = int(rng.integers(0, n_db)); o = int(rng.integers(0, db_count - q_count + 1))
+        qb[q] = dbb[c, o:o + q_count]; flip = rng.random((q_count, L // 2)) < 0.04
+        qb[q, :, 0::2] ^= flip.astype(np.uint8); qb[q, :, 1::2] ^= flip.astype(np.uint8)     # sign flips keep the codes regular
+    if n_q > 1:
+        qb[-1, 0, 6] = qb[-1, 0, 7] = 0
+    db = lb.Database(L); db.add_packed(lb.pack_booleans(dbb))
+    sc, idx, full = db.search_packed(lb.pack_booleans(qb), k, rng=rng_len, all_scores=True)
+    want, _ = checker.search(dbb, qb, rng_len if rng_len else L)
+    assert np.array_equal(full, want)
+    order = np.lexsort((np.arange(n_db)[None, :].repeat(n_q, 0), -want.astype(np.float64)), axis=1)[:, :k]
+    assert np.array_equal(idx, order.astype(np.uint32)) and np.array_equal(sc, np.take_along_axis(want, order, axis=1))
+
+
 @pytest.mark.parametrize("L,q_count,db_count", [(200, 6, 19), (200, 1, 5), (100, 3, 7), (400, 2, 9)])
 def test_search_regular_codes_short_form(lb, checker, L, q_count, db_count):
     """Databases in which every rank carries exactly one sign bit take the kernel's short form (one LOP3 per word, no M plane);
