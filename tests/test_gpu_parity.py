@@ -607,6 +607,31 @@ def test_search_100_rank_form_and_mixed_databases(lb, checker, q_count, db_count
     check(mixed)
 
 
+def test_search_100_rank_form_on_a_ragged_database(lb, checker):
+    """The two-POPC form with clips of different lengths (tile bounds and clip positions come from the offsets array instead of a uniform
+    count), regular queries in every warp, clips of 6 to 30 subfingerprints — and the same database with a silent clip in it."""
+    rng = np.random.default_rng(77); L = 200
+    counts = rng.integers(6, 31, size=400)
+    fps_bits = [rank_sign_codes(rng, 1, int(c), L)[0] for c in counts]
+    qs = []
+    for q in range(40):
+        c = int(rng.integers(0, len(counts))); o = int(rng.integers(0, counts[c] - 6 + 1))
+        b = fps_bits[c][o:o + 6].copy(); flip = rng.random((6, L // 2)) < 0.05
+        b[:, 0::2] ^= flip.astype(np.uint8); b[:, 1::2] ^= flip.astype(np.uint8)
+        qs.append(b)
+    for silent in (False, True):
+        if silent:
+            fps_bits[123] = fps_bits[123].copy(); fps_bits[123][2, :] = 0
+        db = lb.Database(L)
+        for b in fps_bits:
+            db.add_fingerprint(lb.Fingerprint.from_booleans(b))
+        sc, idx = db.search([lb.Fingerprint.from_booleans(q) for q in qs], k=6)
+        for qi, q in enumerate(qs):
+            want = np.array([np.float32(checker.compare_fp(b, q, L)) for b in fps_bits])
+            order = np.lexsort((np.arange(len(want)), -want.astype(np.float64)))[:6]
+            assert np.array_equal(idx[qi], order.astype(np.uint32)) and np.array_equal(sc[qi], want[order]), (silent, qi)
+
+
 def test_search_ragged_database_and_fingerprint_api(lb, checker):
     rng = np.random.default_rng(12); L = 200
     counts = rng.integers(0, 25, size=120)
