@@ -575,11 +575,14 @@ search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
                     for (int w = 0; w < W; w++) { dp[w] = np[w]; dm[w] = nm[w]; }
                     if (j + 1 < cd) load_words(j + 1, np, nm);
                     float r[FEW_MAX_CQ];
+                    /* subfingerprint j meets query subfingerprint i only where offset j - i exists (0 <= j - i <= cd - cq): at the two ends of a
+                     * clip the other pairs belong to no offset — their sums are never read — and are skipped (30 of 114 pairs for 19 against 6) */
+                    const uint32_t last_off = cd - cq;
                     if (short_form) {                                           /* warp-uniform */
 #pragma unroll
                         for (uint32_t i = 0; i < FEW_MAX_CQ; i++) {
                             r[i] = 0.0f;
-                            if (i < cq) {
+                            if (i < cq && j >= i && j - i <= last_off) {
                                 uint32_t x[W];
 #pragma unroll
                                 for (int w = 0; w < W; w++) x[w] = (dp[w] ^ qw[i][w]) & mask.w[w];               /* ranks whose P bits differ */
@@ -594,7 +597,7 @@ search_few_kernel(const uint32_t* __restrict__ db, const uint32_t* __restrict__ 
 #pragma unroll
                     for (uint32_t i = 0; i < FEW_MAX_CQ; i++) {
                         r[i] = 0.0f;
-                        if (i < cq) {                                           /* warp-uniform */
+                        if (i < cq && j >= i && j - i <= last_off) {           /* (uniform over the warp when the clips are equally long) */
                             uint32_t h[W];
 #pragma unroll
                             for (int w = 0; w < W; w++) h[w] = hit_word2(dp[w], dm[w], qw[i][w], qw[i][W + w]);  /* FP.m:162-167 */
