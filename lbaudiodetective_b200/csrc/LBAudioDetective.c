@@ -309,10 +309,10 @@ OSStatus LBAudioDetectiveProcessPCMBatchSharded(const LBAudioDetectiveRef* dets,
     }
     if (framesPerClip < dets[0]->windowSize) return kLBAudioDetectiveArgumentInvalid;
     for (UInt32 i = 0; i < nDets; i++) { OSStatus e = ensure_plan(dets[i]); if (e != noErr) return e; }
-    uint64_t cursor = 0;                                                          /* clips handed out so far */
+    uint64_t cursor[2] = {0, 0};                                                  /* clips handed out so far; clips per chunk (fixed by the first pipeline to start) */
     struct shard_job jobs[64]; pthread_t threads[64]; int started[64];
     for (UInt32 i = 0; i < nDets; i++) {
-        jobs[i] = (struct shard_job){dets[i], inSamples, nClips, framesPerClip, clipStride, outWords, &cursor, noErr, {0}};
+        jobs[i] = (struct shard_job){dets[i], inSamples, nClips, framesPerClip, clipStride, outWords, cursor, noErr, {0}};
         started[i] = pthread_create(&threads[i], NULL, shard_main, &jobs[i]) == 0;
         if (!started[i]) shard_main(&jobs[i]);                                    /* no thread to be had: this detective works here (and may take everything) */
     }

@@ -66,7 +66,7 @@ int  lbadcu_extract_device(lbadcu_plan* p, const float* d_pcm, uint32_t n_clips,
 int  lbadcu_extract_host(lbadcu_plan* p, const float* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride,
                          uint32_t* h_words, float* h_images, float* h_haar, int mode);
 /* One batch shared by several plans (one per GPU), each called from its own host thread with the WHOLE batch and the same cursor
- * (a clip counter the caller sets to 0): a plan takes its next chunk from the cursor when one of its three buffers has drained, so the
+ * (TWO 64-bit words the caller sets to 0: the clips handed out so far, and the chunk size the first plan to arrive fixes for all): a plan takes its next chunk from the cursor when one of its three buffers has drained, so the
  * batch divides itself by how fast each GPU is fed.  Every clip is processed by exactly one plan; h_words is filled in clip order. */
 int  lbadcu_extract_host_shared(lbadcu_plan* p, const float* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride, uint32_t* h_words, uint64_t* cursor);
 /* same for signed 16-bit PCM (uploaded as 2 bytes per sample, converted on the device as x / 32768) */

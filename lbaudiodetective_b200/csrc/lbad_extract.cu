@@ -1336,6 +1336,11 @@ static int extract_host_impl(lbadcu_plan* p, const void* h_pcm_v, int sample_byt
     if (p->chunk_clips_override) clips_per_chunk = p->chunk_clips_override;
     if (clips_per_chunk < 1) clips_per_chunk = 1;
     if (clips_per_chunk > n_clips) clips_per_chunk = n_clips;
+    if (cursor) {                                                       /* plans that share a batch must cut it alike: the first one to arrive fixes the chunk size (cursor[1]) */
+        uint64_t unset = 0;
+        __atomic_compare_exchange_n(&cursor[1], &unset, clips_per_chunk, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+        clips_per_chunk = __atomic_load_n(&cursor[1], __ATOMIC_ACQUIRE);
+    }
     const size_t need_pcm = (size_t)clips_per_chunk * clip_pad, need_words = (size_t)clips_per_chunk * words_per_clip;
     const int nbuf = n_clips > clips_per_chunk ? 3 : 1;
     if (p->chunk_pcm_floats < need_pcm || p->chunk_words < need_words || (sample_bytes == 2 && p->chunk_i16 < need_pcm)) {
@@ -1360,7 +1365,7 @@ static int extract_host_impl(lbadcu_plan* p, const void* h_pcm_v, int sample_byt
         const int b = (int)(chunk % (uint32_t)nbuf);
         cudaStream_t s = nbuf == 1 ? p->stream : p->copy_streams[b];
         if (cursor && chunk >= (uint32_t)nbuf) LBAD_CUDA_TRY(cudaStreamSynchronize(s));      /* shared batch: another chunk only once this buffer's last one is through */
-        const uint64_t c0 = cursor ? __atomic_fetch_add(cursor, clips_per_chunk, __ATOMIC_RELAXED) : own;
+        const uint64_t c0 = cursor ? __atomic_fetch_add(&cursor[0], clips_per_chunk, __ATOMIC_RELAXED) : own;
         if (c0 >= n_clips) break;
         const uint32_t nc = (uint32_t)((n_clips - c0) < clips_per_chunk ? (n_clips - c0) : clips_per_chunk);
         void* d_in = sample_bytes == 2 ? static_cast<void*>(p->d_chunk_i16[b]) : static_cast<void*>(p->d_chunk_pcm[b]);
@@ -1391,7 +1396,8 @@ extern "C" int lbadcu_extract_host(lbadcu_plan* p, const float* h_pcm, uint32_t 
     return extract_host_impl(p, h_pcm, 4, n_clips, clip_len, clip_stride, h_words, h_images, h_haar, mode);
 }
 
-/* the same batch shared between several plans (see extract_host_impl): every caller passes the whole batch and the same zero-initialised cursor */
+/* the same batch shared between several plans (see extract_host_impl): every caller passes the whole batch and the same cursor,
+ * two zero-initialised 64-bit words (clips handed out so far; clips per chunk, fixed by the first plan to arrive) */
 extern "C" int lbadcu_extract_host_shared(lbadcu_plan* p, const float* h_pcm, uint32_t n_clips, uint64_t clip_len, uint64_t clip_stride, uint32_t* h_words, uint64_t* cursor) {
     if (!cursor) return LBAD_ERR_ARG;
     return extract_host_impl(p, h_pcm, 4, n_clips, clip_len, clip_stride, h_words, nullptr, nullptr, 0, cursor);
